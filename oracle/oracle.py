@@ -1,0 +1,360 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE ONLY -- see oracle/trgt_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (trgt_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libtrgt_oracle.so")
+
+INDEL, EDIT, LINEAR, AFFINE, AFFINE2P = 0, 1, 2, 3, 4
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/*.c into libtrgt_oracle.so (gcc via oracle/Makefile)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    )
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "libtrgt_oracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class _Params(C.Structure):
+    _fields_ = [
+        ("metric", C.c_int), ("x", C.c_int), ("o1", C.c_int), ("e1", C.c_int),
+        ("o2", C.c_int), ("e2", C.c_int), ("ends_free", C.c_int),
+        ("pattern_begin_free", C.c_int), ("pattern_end_free", C.c_int),
+        ("text_begin_free", C.c_int), ("text_end_free", C.c_int),
+        ("score_only", C.c_int), ("max_steps", C.c_int),
+    ]
+
+
+class _Result(C.Structure):
+    _fields_ = [
+        ("status", C.c_int), ("score", C.c_int), ("ops", C.POINTER(C.c_uint8)),
+        ("n_ops", C.c_int64), ("end_k", C.c_int), ("end_offset", C.c_int),
+    ]
+
+
+class _Span(C.Structure):
+    _fields_ = [("motif_index", C.c_uint32), ("start", C.c_uint32), ("end", C.c_uint32)]
+
+
+class _OptSpan(C.Structure):
+    _fields_ = [("found", C.c_int32), ("start", C.c_uint32), ("end", C.c_uint32)]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("n_loci", C.c_uint32),
+        ("left_pieces", C.c_void_p), ("left_off", C.c_void_p),
+        ("right_pieces", C.c_void_p), ("right_off", C.c_void_p),
+        ("motifs", C.c_void_p), ("motif_off", C.c_void_p),
+        ("locus_motif_off", C.c_void_p),
+        ("reads", C.c_void_p), ("read_off", C.c_void_p),
+        ("locus_read_off", C.c_void_p),
+        ("read_hap", C.c_void_p),
+        ("x", C.c_int), ("o", C.c_int), ("e", C.c_int),
+        ("min_flank_id_frac", C.c_double),
+    ]
+
+
+class BatchOut(C.Structure):
+    _fields_ = [("spans", C.c_void_p), ("checksum", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.tro_hmm_build.restype = C.c_void_p
+        L.tro_hmm_build.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.c_uint32]
+        L.tro_hmm_free.argtypes = [C.c_void_p]
+        L.tro_hmm_num_states.argtypes = [C.c_void_p]
+        L.tro_hmm_em.restype = C.c_double
+        L.tro_hmm_em.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.tro_hmm_num_in.argtypes = [C.c_void_p, C.c_int]
+        L.tro_hmm_in_state.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.tro_hmm_in_lp.restype = C.c_double
+        L.tro_hmm_in_lp.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.tro_hmm_label.restype = C.c_int64
+        L.tro_hmm_label.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32,
+                                    C.POINTER(C.c_uint32), C.c_uint64]
+        L.tro_remove_imperfect_motifs.restype = C.c_int64
+        L.tro_remove_imperfect_motifs.argtypes = [
+            C.c_void_p, C.POINTER(C.c_uint32), C.c_uint64, C.c_char_p, C.c_uint32, C.c_uint32,
+            C.POINTER(C.c_uint32), C.c_uint64]
+        L.tro_label_motifs.restype = C.c_int64
+        L.tro_label_motifs.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint64,
+                                       C.POINTER(_Span), C.c_uint64]
+        L.tro_calc_purity.restype = C.c_double
+        L.tro_calc_purity.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint64,
+                                      C.c_char_p, C.c_uint32]
+        L.tro_get_base_match.restype = C.c_uint8
+        L.tro_get_base_match.argtypes = [C.c_void_p, C.c_int]
+        L.tro_annotate_allele.restype = C.c_int64
+        L.tro_annotate_allele.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32,
+                                          C.POINTER(C.c_uint32), C.POINTER(_Span), C.c_uint64,
+                                          C.POINTER(C.c_double)]
+        L.tro_wfa_align.argtypes = [C.POINTER(_Params), C.c_char_p, C.c_int, C.c_char_p, C.c_int,
+                                    C.POINTER(_Result)]
+        L.tro_wfa_result_free.argtypes = [C.POINTER(_Result)]
+        L.tro_sam_cigar.restype = C.c_int64
+        L.tro_sam_cigar.argtypes = [C.POINTER(C.c_uint8), C.c_int64, C.c_int,
+                                    C.POINTER(C.c_uint32), C.c_uint64]
+        L.tro_count_matches.argtypes = [C.POINTER(C.c_uint8), C.c_int64]
+        L.tro_alignment_span.argtypes = [C.POINTER(C.c_uint8), C.c_int64, C.c_int, C.c_int,
+                                         C.c_int] + [C.POINTER(C.c_int)] * 4
+        L.tro_cigar_score.argtypes = [C.POINTER(_Params), C.POINTER(C.c_uint8), C.c_int64]
+        L.tro_cigar_score_clipped.argtypes = [C.POINTER(_Params), C.POINTER(C.c_uint8), C.c_int64,
+                                              C.c_int]
+        L.tro_find_span.restype = _OptSpan
+        L.tro_find_span.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.tro_align_consensus.restype = C.c_int64
+        L.tro_align_consensus.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int,
+                                          C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(C.c_int)]
+        L.tro_get_dist.restype = C.c_double
+        L.tro_get_dist.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        L.tro_process_loci.argtypes = [C.POINTER(Batch), C.c_uint32, C.c_uint32,
+                                       C.POINTER(BatchOut)]
+        _lib = L
+    return _lib
+
+
+# ------------------------------------------------------------------ HMM --
+
+def replace_invalid_bases(seq: bytes, allowed: bytes) -> bytes:
+    """src/hmm/utils.rs:29-42"""
+    return bytes(b if b in allowed else allowed[i % len(allowed)] for i, b in enumerate(seq))
+
+
+class Hmm:
+    """build_hmm (src/hmm/builder.rs:4) + Hmm methods (src/hmm/hmm_model.rs)."""
+
+    def __init__(self, motifs: Sequence[bytes]):
+        self.motifs = [bytes(m) for m in motifs]
+        data = b"".join(self.motifs)
+        offs = [0]
+        for m in self.motifs:
+            offs.append(offs[-1] + len(m))
+        arr = (C.c_uint32 * len(offs))(*offs)
+        self._h = lib().tro_hmm_build(data, arr, len(self.motifs))
+        if not self._h:
+            raise ValueError("invalid motif base")
+        self.num_states = lib().tro_hmm_num_states(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().tro_hmm_free(self._h)
+            self._h = None
+
+    def label(self, query: bytes) -> List[int]:
+        cap = (len(query) + 2) * self.num_states + 8
+        out = (C.c_uint32 * cap)()
+        n = lib().tro_hmm_label(self._h, query, len(query), out, cap)
+        if n < 0:
+            raise ValueError(f"label failed rc={n}")
+        return list(out[:n])
+
+    def remove_imperfect_motifs(self, states: Sequence[int], query: bytes,
+                                max_motif_len: int = 6) -> List[int]:
+        cap = len(states) + 3 * len(query) + 16
+        inp = (C.c_uint32 * max(1, len(states)))(*states)
+        out = (C.c_uint32 * cap)()
+        n = lib().tro_remove_imperfect_motifs(self._h, inp, len(states), query, len(query),
+                                              max_motif_len, out, cap)
+        if n < 0:
+            raise ValueError(f"remove_imperfect_motifs failed rc={n}")
+        return list(out[:n])
+
+    def label_motifs(self, states: Sequence[int]) -> List[Tuple[int, int, int]]:
+        """-> [(motif_index, start, end)]"""
+        cap = len(states) + 1
+        inp = (C.c_uint32 * max(1, len(states)))(*states)
+        out = (_Span * cap)()
+        n = lib().tro_label_motifs(self._h, inp, len(states), out, cap)
+        if n < 0:
+            raise ValueError(f"label_motifs failed rc={n}")
+        return [(out[i].motif_index, out[i].start, out[i].end) for i in range(n)]
+
+    def calc_purity(self, query: bytes, states: Sequence[int]) -> float:
+        inp = (C.c_uint32 * max(1, len(states)))(*states)
+        return lib().tro_calc_purity(self._h, inp, len(states), query, len(query))
+
+    def get_base_match(self, state: int) -> bytes:
+        return bytes([lib().tro_get_base_match(self._h, state)])
+
+    def annotate(self, allele: bytes):
+        """label_with_hmm for one allele (src/trgt/workflows/tr.rs:464-489)
+        -> (motif_counts, collapsed spans [(motif,start,end)], purity)"""
+        nm = len(self.motifs)
+        mc = (C.c_uint32 * max(1, nm))()
+        cap = len(allele) + 1
+        spans = (_Span * cap)()
+        purity = C.c_double()
+        n = lib().tro_annotate_allele(self._h, allele, len(allele), mc, spans, cap,
+                                      C.byref(purity))
+        if n < 0:
+            raise ValueError(f"annotate failed rc={n}")
+        return (list(mc[:nm]), [(spans[i].motif_index, spans[i].start, spans[i].end)
+                                for i in range(n)], purity.value)
+
+    def tables(self):
+        """(ems[S][5], in_states[S][..], in_lps[S][..]) for model-table parity tests."""
+        L = lib()
+        ems, ins, lps = [], [], []
+        for s in range(self.num_states):
+            ems.append([L.tro_hmm_em(self._h, s, i) for i in range(5)])
+            n = L.tro_hmm_num_in(self._h, s)
+            ins.append([L.tro_hmm_in_state(self._h, s, i) for i in range(n)])
+            lps.append([L.tro_hmm_in_lp(self._h, s, i) for i in range(n)])
+        return ems, ins, lps
+
+
+# ------------------------------------------------------------------ WFA --
+
+@dataclass
+class Alignment:
+    status: int
+    score: int
+    ops: bytes            # b"MXID..." forward order
+    end_k: int
+    end_offset: int
+    params: "_Params"
+    plen: int
+    tlen: int
+
+    def cigar_string(self, flank_len: int = 0) -> str:
+        """wfaligner.rs cigar_string(Some(flank_len))"""
+        ops = self.ops[flank_len:len(self.ops) - flank_len] if flank_len else self.ops
+        out, i = [], 0
+        while i < len(ops):
+            j = i
+            while j < len(ops) and ops[j] == ops[i]:
+                j += 1
+            out.append(f"{j - i}{chr(ops[i])}")
+            i = j
+        return "".join(out)
+
+    def _ops_ptr(self):
+        buf = (C.c_uint8 * max(1, len(self.ops))).from_buffer_copy(self.ops or b"\0")
+        return buf
+
+    def count_matches(self) -> int:
+        return lib().tro_count_matches(self._ops_ptr(), len(self.ops))
+
+    def alignment_span(self):
+        """get_alignment_span -> ((xstart,xend),(ystart,yend))"""
+        xs, xe, ys, ye = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        lib().tro_alignment_span(self._ops_ptr(), len(self.ops), self.params.ends_free,
+                                 self.plen, self.tlen, C.byref(xs), C.byref(xe), C.byref(ys),
+                                 C.byref(ye))
+        return (xs.value, xe.value), (ys.value, ye.value)
+
+    def sam_cigar(self, show_mismatches: bool = True) -> List[int]:
+        cap = len(self.ops) + 1
+        out = (C.c_uint32 * cap)()
+        n = lib().tro_sam_cigar(self._ops_ptr(), len(self.ops), int(show_mismatches), out, cap)
+        return list(out[:n])
+
+    def cigar_score(self) -> int:
+        return lib().tro_cigar_score(C.byref(self.params), self._ops_ptr(), len(self.ops))
+
+    def cigar_score_clipped(self, flank_len: int) -> int:
+        return lib().tro_cigar_score_clipped(C.byref(self.params), self._ops_ptr(),
+                                             len(self.ops), flank_len)
+
+
+def decode_sam_cigar(words: Sequence[int]) -> List[Tuple[int, str]]:
+    """WFAligner::decode_sam_cigar (wfaligner.rs:961-984)"""
+    tab = "MIDNSHP=X"
+    return [(w >> 4, tab[w & 0xF] if (w & 0xF) < len(tab) else "?") for w in words]
+
+
+def wfa_align(pattern: bytes, text: bytes, metric: int = AFFINE, x: int = 0, o: int = 0,
+              e: int = 0, o2: int = 0, e2: int = 0, ends_free: Optional[Tuple[int, int, int, int]] = None,
+              score_only: bool = False, max_steps: int = 0) -> Alignment:
+    """ends_free = (pattern_begin_free, pattern_end_free, text_begin_free, text_end_free)"""
+    p = _Params(metric, x, o, e, o2, e2, 0, 0, 0, 0, 0, int(score_only), max_steps)
+    if ends_free is not None:
+        p.ends_free = 1
+        (p.pattern_begin_free, p.pattern_end_free, p.text_begin_free, p.text_end_free) = ends_free
+    r = _Result()
+    lib().tro_wfa_align(C.byref(p), pattern, len(pattern), text, len(text), C.byref(r))
+    ops = bytes(r.ops[:r.n_ops]) if r.ops else b""
+    out = Alignment(r.status, r.score, ops, r.end_k, r.end_offset, p, len(pattern), len(text))
+    lib().tro_wfa_result_free(C.byref(r))
+    return out
+
+
+def find_span(piece: bytes, seq: bytes, scoring=(2, 5, 1), threshold: Optional[float] = None):
+    """find_spans for one read (span_locater.rs:7-30) -> (span or None, via, matches)"""
+    if threshold is None:
+        threshold = len(piece) * 0.7
+    via, nm = C.c_int(), C.c_int()
+    r = lib().tro_find_span(piece, len(piece), seq, len(seq), scoring[0], scoring[1], scoring[2],
+                            threshold, C.byref(via), C.byref(nm))
+    return ((r.start, r.end) if r.found else None), via.value, nm.value
+
+
+def find_tr_spans(lf: bytes, rf: bytes, reads: Sequence[bytes], search_flank_len: int = 250,
+                  min_flank_id_frac: float = 0.7, scoring=(2, 5, 1)):
+    """find_tr_spans (span_locater.rs:32-68)"""
+    lf_piece = lf[len(lf) - search_flank_len:]
+    rf_piece = rf[:search_flank_len]
+    thr = search_flank_len * min_flank_id_frac
+    out = []
+    for r in reads:
+        a, _, _ = find_span(lf_piece, r, scoring, thr)
+        b, _, _ = find_span(rf_piece, r, scoring, thr)
+        if a is not None and b is not None and a[1] <= b[0]:
+            out.append((a[1], b[0]))
+        else:
+            out.append(None)
+    return out
+
+
+def align(backbone: bytes, seqs: Sequence[bytes]) -> List[List[Tuple[int, str]]]:
+    """utils::align (src/utils/align.rs:14-28)"""
+    out = []
+    for s in seqs:
+        cap = len(backbone) + len(s) + 2
+        buf = (C.c_uint32 * cap)()
+        sc = C.c_int()
+        n = lib().tro_align_consensus(backbone, len(backbone), s, len(s), buf, cap, C.byref(sc))
+        out.append(decode_sam_cigar(buf[:n]))
+    return out
+
+
+def align_words(backbone: bytes, seq: bytes) -> Tuple[List[int], int]:
+    cap = len(backbone) + len(seq) + 2
+    buf = (C.c_uint32 * cap)()
+    sc = C.c_int()
+    n = lib().tro_align_consensus(backbone, len(backbone), seq, len(seq), buf, cap, C.byref(sc))
+    return list(buf[:n]), sc.value
+
+
+def get_dist(a: bytes, b: bytes) -> float:
+    """genotype_cluster.rs:236-248"""
+    return lib().tro_get_dist(a, len(a), b, len(b))
+
+
+def get_dist_matrix(trs: Sequence[bytes]) -> List[float]:
+    """genotype_cluster.rs:250-286 (condensed upper triangle)"""
+    n = len(trs)
+    return [get_dist(trs[i], trs[j]) for i in range(n) for j in range(i + 1, n)]

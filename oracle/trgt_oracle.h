@@ -1,0 +1,181 @@
+/*
+ * trgt_oracle.h -- CPU restatement of the TRGT hot path (TEST INFRASTRUCTURE ONLY).
+ *
+ * This is the parity oracle for the B200 engine.  It restates, in plain C, the
+ * algorithms of the reference (PacificBiosciences/trgt v3.0.0) for the path
+ * named in BASELINE.json: wavefront alignment (src/wfaligner.rs over WFA2-lib)
+ * and the motif HMM (src/hmm/).  Every function cites the reference file:line
+ * it follows.  It is NOT part of the product: only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may link or call it.
+ *
+ * Pinning: checked against every golden vector the reference's own unit tests
+ * hold for this path (tests/test_oracle_golden.py).
+ * Parity UNPINNED (no reference test fixes the result, upstream WFA2-lib source
+ * absent from /root/reference): BiWFA (MemoryUltraLow) CIGAR tie-breaking and
+ * the default wfadaptive heuristic; this oracle implements exact
+ * (Heuristic::None) unidirectional WFA for every aligner configuration.
+ */
+#ifndef TRGT_ORACLE_H
+#define TRGT_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ HMM -- */
+
+typedef struct tro_hmm tro_hmm;
+
+/* build_hmm: src/hmm/builder.rs:4-78.  motifs = concatenated bytes, CSR offsets[n+1].
+ * Motif bytes must be in ACGTN (the caller applies replace_invalid_bases).
+ * Returns NULL on an invalid base (the reference panics, builder.rs:182). */
+tro_hmm *tro_hmm_build(const uint8_t *motifs, const uint32_t *offsets, uint32_t n_motifs);
+void tro_hmm_free(tro_hmm *h);
+int tro_hmm_num_states(const tro_hmm *h);
+/* raw table access (for tests): ln emission of `state` for symbol 0..4 (#ATCG) */
+double tro_hmm_em(const tro_hmm *h, int state, int sym);
+int tro_hmm_num_in(const tro_hmm *h, int state);
+int tro_hmm_in_state(const tro_hmm *h, int state, int i);
+double tro_hmm_in_lp(const tro_hmm *h, int state, int i);
+
+/* Hmm::label: src/hmm/hmm_model.rs:144-156 (Viterbi :54-114, traceback :125-142).
+ * query = ACGT bytes (no sentinels).  Writes the state path into out (capacity cap)
+ * and returns its length, 0 for an empty query, -1 on invalid base, -2 if cap is
+ * too small. */
+int64_t tro_hmm_label(const tro_hmm *h, const uint8_t *query, uint32_t len,
+                      uint32_t *out, uint64_t cap);
+
+/* remove_imperfect_motifs: src/hmm/operations.rs:6-80.  Returns new length. */
+int64_t tro_remove_imperfect_motifs(const tro_hmm *h, const uint32_t *states, uint64_t n_states,
+                                    const uint8_t *query, uint32_t qlen, uint32_t max_motif_len,
+                                    uint32_t *out, uint64_t cap);
+
+typedef struct {
+  uint32_t motif_index, start, end;
+} tro_span;
+
+/* Hmm::label_motifs: src/hmm/hmm_model.rs:158-200.  Returns number of spans. */
+int64_t tro_label_motifs(const tro_hmm *h, const uint32_t *states, uint64_t n_states,
+                         tro_span *out, uint64_t cap);
+
+/* calc_purity: src/hmm/purity.rs:6-41 via get_events src/hmm/events.rs:17-86. */
+double tro_calc_purity(const tro_hmm *h, const uint32_t *states, uint64_t n_states,
+                       const uint8_t *query, uint32_t qlen);
+
+/* get_base_match: src/hmm/events.rs:88-117 */
+uint8_t tro_get_base_match(const tro_hmm *h, int state);
+
+/* replace_invalid_bases: src/hmm/utils.rs:29-42; allowed = "ATCG" or "ATCGN". In place. */
+void tro_replace_invalid_bases(uint8_t *seq, uint32_t len, const char *allowed);
+
+/* label_with_hmm for ONE allele: src/trgt/workflows/tr.rs:464-489.
+ * `allele` is the raw allele (replace_invalid_bases is applied inside).
+ * motif_counts[n_motifs] out; spans_out = collapsed labels (skip spans dropped);
+ * returns number of collapsed spans (0 <=> labels None), or <0 on error. */
+int64_t tro_annotate_allele(const tro_hmm *h, const uint8_t *allele, uint32_t len,
+                            uint32_t *motif_counts, tro_span *spans_out, uint64_t span_cap,
+                            double *purity_out);
+
+/* ------------------------------------------------------------------ WFA -- */
+
+enum { TRO_INDEL = 0, TRO_EDIT = 1, TRO_LINEAR = 2, TRO_AFFINE = 3, TRO_AFFINE2P = 4 };
+
+/* wfa2 status codes as surfaced by src/wfaligner.rs:132-159 */
+enum {
+  TRO_STATUS_OK = 0,
+  TRO_STATUS_MAX_STEPS = -100,
+  TRO_STATUS_OOM = -200,
+  TRO_STATUS_UNATTAINABLE = -300
+};
+
+typedef struct {
+  int metric;            /* TRO_* */
+  int x;                 /* mismatch */
+  int o1, e1;            /* gap open/extend (linear: e1 = indel penalty) */
+  int o2, e2;            /* second affine piece */
+  int ends_free;         /* 0 = end-to-end */
+  int pattern_begin_free, pattern_end_free, text_begin_free, text_end_free;
+  int score_only;        /* AlignmentScope::Score */
+  int max_steps;         /* <=0: unlimited */
+} tro_wfa_params;
+
+typedef struct {
+  int status;
+  int score;             /* sign convention of wfaligner.rs:530 (edit/indel +cost, others -cost) */
+  uint8_t *ops;          /* 'M','X','I','D' in forward order; malloc'ed; NULL if score_only */
+  int64_t n_ops;
+  int end_k, end_offset; /* diagonal / text offset at which the wavefront terminated */
+} tro_wfa_result;
+
+/* wavefront_align as driven by WFAligner::align_end_to_end / align_ends_free
+ * (src/wfaligner.rs:489-528).  The DP itself lives in WFA2-lib (wfa2-sys 0.1.0,
+ * git rev 4342b3b0..., not vendored); rules restated in SURVEY.md section 8c. */
+int tro_wfa_align(const tro_wfa_params *p, const uint8_t *pattern, int plen,
+                  const uint8_t *text, int tlen, tro_wfa_result *res);
+void tro_wfa_result_free(tro_wfa_result *res);
+
+/* accessors: wfaligner.rs:988 count_matches, :864 get_alignment_span, :932 get_sam_cigar,
+ * :1002 cigar_score, :595 cigar_score_clipped */
+int tro_count_matches(const uint8_t *ops, int64_t n);
+void tro_alignment_span(const uint8_t *ops, int64_t n, int ends_free, int plen, int tlen,
+                        int *xs, int *xe, int *ys, int *ye);
+int64_t tro_sam_cigar(const uint8_t *ops, int64_t n, int show_mismatches, uint32_t *out,
+                      uint64_t cap);
+int tro_cigar_score(const tro_wfa_params *p, const uint8_t *ops, int64_t n);
+int tro_cigar_score_clipped(const tro_wfa_params *p, const uint8_t *ops, int64_t n, int flank_len);
+
+/* ----------------------------------------------------- callers (a1-a6) -- */
+
+typedef struct {
+  int32_t found;         /* Option::is_some */
+  uint32_t start, end;
+} tro_opt_span;
+
+/* find_spans for ONE read: src/trgt/genotype/span_locater.rs:7-30.
+ * via (optional): 0 none, 1 exact window hit, 2 WFA fallback accepted, 3 WFA fallback rejected.
+ * matches (optional): count_matches of the fallback alignment (or piece_len for exact). */
+tro_opt_span tro_find_span(const uint8_t *piece, int piece_len, const uint8_t *seq, int seq_len,
+                           int x, int o, int e, double threshold, int *via, int *matches);
+
+/* find_tr_spans combine rule: span_locater.rs:53-67 */
+tro_opt_span tro_combine_spans(tro_opt_span lf, tro_opt_span rf);
+
+/* utils::align for ONE (backbone, seq): src/utils/align.rs:14-28 -> run-length SAM cigar words
+ * (len<<4|op with '='=7 'X'=8 'I'=1 'D'=2).  Gap-affine (2,5,1), exact WFA. */
+int64_t tro_align_consensus(const uint8_t *backbone, int blen, const uint8_t *seq, int slen,
+                            uint32_t *out, uint64_t cap, int *score);
+
+/* get_dist: src/trgt/genotype/genotype_cluster.rs:236-248 */
+double tro_get_dist(const uint8_t *a, int alen, const uint8_t *b, int blen);
+
+/* ------------------------------------------- batched CPU baseline path -- */
+
+/* One pass of the hot path (phases A+B+C as bench.py defines them) over loci
+ * [lo,hi) of a packed batch; used ONLY as the timed CPU baseline / checker. */
+typedef struct {
+  uint32_t n_loci;
+  const uint8_t *left_pieces;  const uint64_t *left_off;    /* [n_loci+1] */
+  const uint8_t *right_pieces; const uint64_t *right_off;
+  const uint8_t *motifs;       const uint32_t *motif_off;   /* per motif, [n_motifs_total+1] */
+  const uint32_t *locus_motif_off;                           /* [n_loci+1] into motif list */
+  const uint8_t *reads;        const uint64_t *read_off;    /* [n_reads+1] */
+  const uint32_t *locus_read_off;                            /* [n_loci+1] */
+  const uint8_t *read_hap;                                   /* generator's haplotype label per read */
+  int x, o, e;
+  double min_flank_id_frac;
+} tro_batch;
+
+typedef struct {
+  tro_opt_span *spans;          /* [n_reads] */
+  uint64_t *checksum;           /* [n_loci] order-independent digest of all per-locus results */
+} tro_batch_out;
+
+int tro_process_loci(const tro_batch *b, uint32_t lo, uint32_t hi, tro_batch_out *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

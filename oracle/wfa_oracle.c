@@ -1,0 +1,536 @@
+/*
+ * wfa_oracle.c -- CPU restatement of the wavefront alignment the reference drives through
+ * src/wfaligner.rs (TEST INFRASTRUCTURE ONLY; see trgt_oracle.h).
+ *
+ * The DP lives in WFA2-lib (wfa2-sys 0.1.0 @ git rev 4342b3b06278656fa51c0a33b4eb0b67d53bfa8c,
+ * Cargo.toml:36; sources NOT under /root/reference).  This file restates the published WFA
+ * recurrences (Marco-Sola et al. 2021) with the tie-breaking and ends-free conventions pinned
+ * by the reference's own golden tests (src/wfaligner.rs:1137-1828); rules in SURVEY.md 8c:
+ *   - offsets are text positions h on diagonal k = h - v;
+ *   - I[s][k] = max(M[s-o-e][k-1], I[s-e][k-1]) + 1;  D[s][k] = max(M[s-o-e][k+1], D[s-e][k+1]);
+ *     M[s][k] = max(M[s-x][k]+1, I[s][k], D[s][k]), NULL when h>T or v>P or negative; then extend;
+ *   - termination scans diagonals low k -> high k;
+ *   - backtrace picks max over (offset<<4 | tag), tags M=9 > D2e=8 > D2o=7 > D1e=6 > D1o=5 >
+ *     I2e=4 > I2o=3 > I1e=2 > I1o=1.
+ * Full wavefront history is kept (MemoryHigh equivalent); exact, no heuristic.
+ */
+#include "trgt_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define OFF_NULL (INT_MIN / 2)
+
+enum { C_M = 0, C_I1 = 1, C_D1 = 2, C_I2 = 3, C_D2 = 4, N_COMP = 5 };
+enum { T_I1O = 1, T_I1E = 2, T_I2O = 3, T_I2E = 4, T_D1O = 5, T_D1E = 6, T_D2O = 7, T_D2E = 8, T_M = 9 };
+
+typedef struct {
+  int lo, hi;        /* inclusive; lo > hi <=> null */
+  int *off[N_COMP];  /* off[c][k - lo] */
+} wf_t;
+
+typedef struct {
+  wf_t *wf;
+  int n, cap;
+} wf_hist;
+
+static inline int wf_get(const wf_hist *H, int s, int c, int k) {
+  if (s < 0 || s >= H->n) return OFF_NULL;
+  const wf_t *w = &H->wf[s];
+  if (k < w->lo || k > w->hi || !w->off[c]) return OFF_NULL;
+  return w->off[c][k - w->lo];
+}
+static inline int wf_present(const wf_hist *H, int s, int c) {
+  return s >= 0 && s < H->n && H->wf[s].lo <= H->wf[s].hi && H->wf[s].off[c] != NULL;
+}
+static inline int imax(int a, int b) { return a > b ? a : b; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+
+static wf_t *hist_push(wf_hist *H) {
+  if (H->n == H->cap) {
+    H->cap = H->cap ? H->cap * 2 : 64;
+    H->wf = (wf_t *)realloc(H->wf, sizeof(wf_t) * (size_t)H->cap);
+  }
+  wf_t *w = &H->wf[H->n++];
+  memset(w, 0, sizeof(*w));
+  w->lo = 1;
+  w->hi = -1;
+  return w;
+}
+static void hist_free(wf_hist *H) {
+  for (int s = 0; s < H->n; s++)
+    for (int c = 0; c < N_COMP; c++) free(H->wf[s].off[c]);
+  free(H->wf);
+}
+
+static void extend(wf_t *w, const uint8_t *p, int P, const uint8_t *t, int T) {
+  for (int k = w->lo; k <= w->hi; k++) {
+    int h = w->off[C_M][k - w->lo];
+    if (h < 0) continue;
+    int v = h - k;
+    while (v < P && h < T && p[v] == t[h]) {
+      v++;
+      h++;
+    }
+    w->off[C_M][k - w->lo] = h;
+  }
+}
+
+/* returns 1 and sets (k, offset) for the first (lowest k) diagonal that satisfies the end condition */
+static int terminated(const wf_t *w, const tro_wfa_params *prm, int P, int T, int *ek, int *eo) {
+  if (w->lo > w->hi) return 0;
+  if (!prm->ends_free) {
+    const int k = T - P;
+    if (k < w->lo || k > w->hi) return 0;
+    const int h = w->off[C_M][k - w->lo];
+    if (h >= T) {
+      *ek = k;
+      *eo = h;
+      return 1;
+    }
+    return 0;
+  }
+  for (int k = w->lo; k <= w->hi; k++) {
+    const int h = w->off[C_M][k - w->lo];
+    if (h < 0) continue;
+    const int v = h - k;
+    if (v < 0 || v > P || h > T) continue;
+    if ((h >= T && P - v <= prm->pattern_end_free) || (v >= P && T - h <= prm->text_end_free)) {
+      *ek = k;
+      *eo = h;
+      return 1;
+    }
+  }
+  return 0;
+}
+
+static inline int64_t pg(int off, int tag) {
+  return off < 0 ? (int64_t)OFF_NULL : (((int64_t)off << 4) | tag);
+}
+static inline int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
+
+typedef struct {
+  uint8_t *buf;
+  int64_t n, cap;
+} opvec;
+static void op_push(opvec *v, uint8_t op, int64_t count) {
+  if (count <= 0) return;
+  if (v->n + count > v->cap) {
+    while (v->n + count > v->cap) v->cap = v->cap ? v->cap * 2 : 256;
+    v->buf = (uint8_t *)realloc(v->buf, (size_t)v->cap);
+  }
+  memset(v->buf + v->n, op, (size_t)count);
+  v->n += count;
+}
+
+int tro_wfa_align(const tro_wfa_params *prm, const uint8_t *p, int P, const uint8_t *t, int T,
+                  tro_wfa_result *res) {
+  memset(res, 0, sizeof(*res));
+  const int metric = prm->metric;
+  const int x = (metric == TRO_EDIT) ? 1 : prm->x;
+  /* per-metric source distances */
+  int o1e1, e1, o2e2 = 0, e2 = 0;
+  if (metric == TRO_INDEL || metric == TRO_EDIT) {
+    o1e1 = 1;
+    e1 = 0;
+  } else if (metric == TRO_LINEAR) {
+    o1e1 = prm->e1;
+    e1 = 0;
+  } else {
+    o1e1 = prm->o1 + prm->e1;
+    e1 = prm->e1;
+    o2e2 = prm->o2 + prm->e2;
+    e2 = prm->e2;
+  }
+  const int affine = (metric == TRO_AFFINE || metric == TRO_AFFINE2P);
+  const int two = (metric == TRO_AFFINE2P);
+  const int use_x = (metric != TRO_INDEL);
+
+  wf_hist H = {0};
+  /* initial wavefront: src/wfaligner.rs:464-487 semantics */
+  {
+    wf_t *w = hist_push(&H);
+    if (prm->ends_free) {
+      w->lo = -prm->pattern_begin_free;
+      w->hi = prm->text_begin_free;
+    } else {
+      w->lo = 0;
+      w->hi = 0;
+    }
+    w->off[C_M] = (int *)malloc(sizeof(int) * (size_t)(w->hi - w->lo + 1));
+    for (int k = w->lo; k <= w->hi; k++) w->off[C_M][k - w->lo] = k >= 0 ? k : 0;
+    extend(w, p, P, t, T);
+  }
+  int s = 0, ek = 0, eo = 0;
+  int status = TRO_STATUS_OK;
+  for (;;) {
+    if (terminated(&H.wf[s], prm, P, T, &ek, &eo)) break;
+    s++;
+    if (prm->max_steps > 0 && s > prm->max_steps) {
+      status = TRO_STATUS_MAX_STEPS;
+      break;
+    }
+    wf_t *w = hist_push(&H);
+    /* gather sources */
+    int lo = INT_MAX, hi = INT_MIN;
+#define SRC(ss, c)                                 \
+  if (wf_present(&H, (ss), (c))) {                 \
+    lo = imin(lo, H.wf[(ss)].lo);                  \
+    hi = imax(hi, H.wf[(ss)].hi);                  \
+  }
+    if (use_x) SRC(s - x, C_M);
+    SRC(s - o1e1, C_M);
+    if (affine) {
+      SRC(s - e1, C_I1);
+      SRC(s - e1, C_D1);
+    }
+    if (two) {
+      SRC(s - o2e2, C_M);
+      SRC(s - e2, C_I2);
+      SRC(s - e2, C_D2);
+    }
+#undef SRC
+    if (lo > hi) continue; /* null wavefront */
+    lo -= 1;
+    hi += 1;
+    /* diagonals outside [-P, T] can never hold a valid M offset and cannot feed one */
+    lo = imax(lo, -P);
+    hi = imin(hi, T);
+    if (lo > hi) continue;
+    w->lo = lo;
+    w->hi = hi;
+    const size_t width = (size_t)(hi - lo + 1);
+    w->off[C_M] = (int *)malloc(sizeof(int) * width);
+    if (affine) {
+      w->off[C_I1] = (int *)malloc(sizeof(int) * width);
+      w->off[C_D1] = (int *)malloc(sizeof(int) * width);
+    }
+    if (two) {
+      w->off[C_I2] = (int *)malloc(sizeof(int) * width);
+      w->off[C_D2] = (int *)malloc(sizeof(int) * width);
+    }
+    for (int k = lo; k <= hi; k++) {
+      int ins, del;
+      if (affine) {
+        const int i1 = imax(wf_get(&H, s - o1e1, C_M, k - 1), wf_get(&H, s - e1, C_I1, k - 1)) + 1;
+        const int d1 = imax(wf_get(&H, s - o1e1, C_M, k + 1), wf_get(&H, s - e1, C_D1, k + 1));
+        w->off[C_I1][k - lo] = i1;
+        w->off[C_D1][k - lo] = d1;
+        ins = i1;
+        del = d1;
+        if (two) {
+          const int i2 = imax(wf_get(&H, s - o2e2, C_M, k - 1), wf_get(&H, s - e2, C_I2, k - 1)) + 1;
+          const int d2 = imax(wf_get(&H, s - o2e2, C_M, k + 1), wf_get(&H, s - e2, C_D2, k + 1));
+          w->off[C_I2][k - lo] = i2;
+          w->off[C_D2][k - lo] = d2;
+          ins = imax(ins, i2);
+          del = imax(del, d2);
+        }
+      } else {
+        ins = wf_get(&H, s - o1e1, C_M, k - 1) + 1;
+        del = wf_get(&H, s - o1e1, C_M, k + 1);
+      }
+      const int mm = use_x ? wf_get(&H, s - x, C_M, k) + 1 : OFF_NULL;
+      int mx = imax(mm, imax(ins, del));
+      const int h = mx, v = mx - k;
+      if (mx < 0 || h > T || v > P || v < 0) mx = OFF_NULL;
+      w->off[C_M][k - lo] = mx;
+    }
+    extend(w, p, P, t, T);
+  }
+
+  res->status = status;
+  if (status != TRO_STATUS_OK) {
+    res->score = INT_MIN; /* wfaligner.rs:1448: failed alignments report i32::MIN */
+    hist_free(&H);
+    return status;
+  }
+  res->score = (metric == TRO_INDEL || metric == TRO_EDIT) ? s : -s;
+  res->end_k = ek;
+  res->end_offset = eo;
+  if (prm->score_only) {
+    hist_free(&H);
+    return status;
+  }
+
+  /* ---- backtrace (reverse order, then flipped) ---- */
+  opvec rev = {0};
+  int k = ek, off = eo;
+  int v = off - k, h = off;
+  const int tail_d = P - v, tail_i = T - h; /* ends-free: unaligned pattern tail as D, text tail as I */
+  int mt = C_M, sc = s;
+  while (v > 0 && h > 0 && sc > 0) {
+    const int ms = sc - x, go1 = sc - o1e1, ge1 = sc - e1, go2 = sc - o2e2, ge2 = sc - e2;
+    int64_t mx;
+    if (affine) {
+      const int64_t c_m = pg(wf_get(&H, ms, C_M, k) + 1, T_M);
+      const int64_t c_i1o = pg(wf_get(&H, go1, C_M, k - 1) + 1, T_I1O);
+      const int64_t c_i1e = pg(wf_get(&H, ge1, C_I1, k - 1) + 1, T_I1E);
+      const int64_t c_d1o = pg(wf_get(&H, go1, C_M, k + 1), T_D1O);
+      const int64_t c_d1e = pg(wf_get(&H, ge1, C_D1, k + 1), T_D1E);
+      int64_t c_i2o = OFF_NULL, c_i2e = OFF_NULL, c_d2o = OFF_NULL, c_d2e = OFF_NULL;
+      if (two) {
+        c_i2o = pg(wf_get(&H, go2, C_M, k - 1) + 1, T_I2O);
+        c_i2e = pg(wf_get(&H, ge2, C_I2, k - 1) + 1, T_I2E);
+        c_d2o = pg(wf_get(&H, go2, C_M, k + 1), T_D2O);
+        c_d2e = pg(wf_get(&H, ge2, C_D2, k + 1), T_D2E);
+      }
+      switch (mt) {
+        case C_M:
+          mx = max64(c_m, max64(max64(max64(c_i1o, c_i1e), max64(c_i2o, c_i2e)),
+                                max64(max64(c_d1o, c_d1e), max64(c_d2o, c_d2e))));
+          break;
+        case C_I1: mx = max64(c_i1o, c_i1e); break;
+        case C_I2: mx = max64(c_i2o, c_i2e); break;
+        case C_D1: mx = max64(c_d1o, c_d1e); break;
+        default: mx = max64(c_d2o, c_d2e); break;
+      }
+    } else {
+      const int64_t c_m = use_x ? pg(wf_get(&H, ms, C_M, k) + 1, T_M) : (int64_t)OFF_NULL;
+      const int64_t c_io = pg(wf_get(&H, go1, C_M, k - 1) + 1, T_I1O);
+      const int64_t c_do = pg(wf_get(&H, go1, C_M, k + 1), T_D1O);
+      mx = max64(c_m, max64(c_io, c_do));
+    }
+    if (mx < 0) break; /* no predecessor: cannot happen for a completed alignment */
+    if (mt == C_M) {
+      const int mo = (int)(mx >> 4);
+      op_push(&rev, 'M', off - mo);
+      off = mo;
+      v = off - k;
+      h = off;
+      if (v <= 0 || h <= 0) break;
+    }
+    switch ((int)(mx & 15)) {
+      case T_M: sc = ms; mt = C_M; op_push(&rev, 'X', 1); off -= 1; break;
+      case T_I1O: sc = go1; mt = C_M; op_push(&rev, 'I', 1); k -= 1; off -= 1; break;
+      case T_I1E: sc = ge1; mt = C_I1; op_push(&rev, 'I', 1); k -= 1; off -= 1; break;
+      case T_I2O: sc = go2; mt = C_M; op_push(&rev, 'I', 1); k -= 1; off -= 1; break;
+      case T_I2E: sc = ge2; mt = C_I2; op_push(&rev, 'I', 1); k -= 1; off -= 1; break;
+      case T_D1O: sc = go1; mt = C_M; op_push(&rev, 'D', 1); k += 1; break;
+      case T_D1E: sc = ge1; mt = C_D1; op_push(&rev, 'D', 1); k += 1; break;
+      case T_D2O: sc = go2; mt = C_M; op_push(&rev, 'D', 1); k += 1; break;
+      case T_D2E: sc = ge2; mt = C_D2; op_push(&rev, 'D', 1); k += 1; break;
+      default: break;
+    }
+    v = off - k;
+    h = off;
+  }
+  if (mt == C_M && v > 0 && h > 0) {
+    const int n = imin(v, h);
+    op_push(&rev, 'M', n);
+    v -= n;
+    h -= n;
+  }
+  op_push(&rev, 'D', v);
+  op_push(&rev, 'I', h);
+
+  const int64_t n_ops = rev.n + (tail_d > 0 ? tail_d : 0) + (tail_i > 0 ? tail_i : 0);
+  uint8_t *ops = (uint8_t *)malloc((size_t)(n_ops ? n_ops : 1));
+  for (int64_t i = 0; i < rev.n; i++) ops[i] = rev.buf[rev.n - 1 - i];
+  int64_t w = rev.n;
+  for (int i = 0; i < tail_d; i++) ops[w++] = 'D';
+  for (int i = 0; i < tail_i; i++) ops[w++] = 'I';
+  free(rev.buf);
+  res->ops = ops;
+  res->n_ops = n_ops;
+  hist_free(&H);
+  return status;
+}
+
+void tro_wfa_result_free(tro_wfa_result *res) {
+  free(res->ops);
+  res->ops = NULL;
+  res->n_ops = 0;
+}
+
+/* cigar_count_matches (wfaligner.rs:988-1000) */
+int tro_count_matches(const uint8_t *ops, int64_t n) {
+  int c = 0;
+  for (int64_t i = 0; i < n; i++) c += (ops[i] == 'M');
+  return c;
+}
+
+/* get_alignment_span: wfaligner.rs:864-908 */
+void tro_alignment_span(const uint8_t *ops, int64_t n, int ends_free, int plen, int tlen, int *xs,
+                        int *xe, int *ys, int *ye) {
+  if (!ends_free) {
+    *xs = 0; *xe = plen; *ys = 0; *ye = tlen;
+    return;
+  }
+  int pi = 0, ti = 0, started = 0;
+  *xs = *xe = *ys = *ye = 0;
+  for (int64_t i = 0; i < n; i++) {
+    switch (ops[i]) {
+      case 'I': ti++; break;
+      case 'D': pi++; break;
+      default:
+        if (!started) {
+          *xs = pi;
+          *ys = ti;
+          started = 1;
+        }
+        pi++;
+        ti++;
+        *xe = pi;
+        *ye = ti;
+    }
+  }
+}
+
+/* get_sam_cigar (wfaligner.rs:932-959 -> WFA2 cigar_get_CIGAR): run-length, (len<<4)|op */
+int64_t tro_sam_cigar(const uint8_t *ops, int64_t n, int show_mismatches, uint32_t *out,
+                      uint64_t cap) {
+  uint64_t n_out = 0;
+  int64_t i = 0;
+  while (i < n) {
+    uint8_t op = ops[i];
+    if (!show_mismatches && op == 'X') op = 'M';
+    int64_t j = i + 1;
+    while (j < n) {
+      uint8_t o2 = ops[j];
+      if (!show_mismatches && o2 == 'X') o2 = 'M';
+      if (o2 != op) break;
+      j++;
+    }
+    uint32_t code;
+    switch (op) {
+      case 'M': code = show_mismatches ? 7u : 0u; break;
+      case 'X': code = 8u; break;
+      case 'I': code = 1u; break;
+      default: code = 2u; break;
+    }
+    if (n_out >= cap) return -2;
+    out[n_out++] = ((uint32_t)(j - i) << 4) | code;
+    i = j;
+  }
+  return (int64_t)n_out;
+}
+
+static int run_score(const tro_wfa_params *p, uint8_t op, int len) {
+  /* wfaligner.rs:534-593; match penalty is 0 for every configuration the path builds */
+  switch (p->metric) {
+    case TRO_INDEL:
+    case TRO_EDIT: return op == 'M' ? 0 : len;
+    case TRO_LINEAR: return op == 'M' ? 0 : (op == 'X' ? len * p->x : len * p->e1);
+    case TRO_AFFINE: return op == 'M' ? 0 : (op == 'X' ? len * p->x : p->o1 + p->e1 * len);
+    default: {
+      if (op == 'M') return 0;
+      if (op == 'X') return len * p->x;
+      const int s1 = p->o1 + p->e1 * len, s2 = p->o2 + p->e2 * len;
+      return s1 < s2 ? s1 : s2;
+    }
+  }
+}
+
+static int score_range(const tro_wfa_params *p, const uint8_t *ops, int64_t b, int64_t e) {
+  int score = 0;
+  int64_t i = b;
+  while (i < e) {
+    int64_t j = i + 1;
+    while (j < e && ops[j] == ops[i]) j++;
+    score += run_score(p, ops[i], (int)(j - i));
+    i = j;
+  }
+  return (p->metric == TRO_INDEL || p->metric == TRO_EDIT) ? score : -score;
+}
+
+int tro_cigar_score(const tro_wfa_params *p, const uint8_t *ops, int64_t n) {
+  return score_range(p, ops, 0, n);
+}
+
+/* cigar_score_clipped: wfaligner.rs:595-705 */
+int tro_cigar_score_clipped(const tro_wfa_params *p, const uint8_t *ops, int64_t n, int flank_len) {
+  const int64_t b = flank_len;
+  int64_t e = n - flank_len;
+  if (e < b) e = b;
+  if (b >= e) return 0;
+  return score_range(p, ops, b, e);
+}
+
+/* ----------------------------------------------------------- callers -- */
+
+tro_opt_span tro_find_span(const uint8_t *piece, int piece_len, const uint8_t *seq, int seq_len,
+                           int x, int o, int e, double threshold, int *via, int *matches) {
+  tro_opt_span r = {0, 0, 0};
+  /* span_locater.rs:10-12: first exact window */
+  if (piece_len > 0) {
+    for (int s = 0; s + piece_len <= seq_len; s++) {
+      if (memcmp(seq + s, piece, (size_t)piece_len) == 0) {
+        r.found = 1;
+        r.start = (uint32_t)s;
+        r.end = (uint32_t)(s + piece_len);
+        if (via) *via = 1;
+        if (matches) *matches = piece_len;
+        return r;
+      }
+    }
+  }
+  /* span_locater.rs:14-25: WFA ends-free fallback, flank aligner of commands/genotype.rs:66-80 */
+  tro_wfa_params prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.metric = TRO_AFFINE;
+  prm.x = x;
+  prm.o1 = o;
+  prm.e1 = e;
+  prm.ends_free = 1;
+  prm.text_begin_free = seq_len;
+  prm.text_end_free = seq_len;
+  tro_wfa_result res;
+  tro_wfa_align(&prm, piece, piece_len, seq, seq_len, &res);
+  const int nm = tro_count_matches(res.ops, res.n_ops);
+  if (matches) *matches = nm;
+  if ((double)nm >= threshold) {
+    int xs, xe, ys, ye;
+    tro_alignment_span(res.ops, res.n_ops, 1, piece_len, seq_len, &xs, &xe, &ys, &ye);
+    r.found = 1;
+    r.start = (uint32_t)ys;
+    r.end = (uint32_t)ye;
+    if (via) *via = 2;
+  } else {
+    if (via) *via = 3;
+  }
+  tro_wfa_result_free(&res);
+  return r;
+}
+
+tro_opt_span tro_combine_spans(tro_opt_span lf, tro_opt_span rf) {
+  tro_opt_span r = {0, 0, 0};
+  if (lf.found && rf.found && lf.end <= rf.start) {
+    r.found = 1;
+    r.start = lf.end;
+    r.end = rf.start;
+  }
+  return r;
+}
+
+int64_t tro_align_consensus(const uint8_t *backbone, int blen, const uint8_t *seq, int slen,
+                            uint32_t *out, uint64_t cap, int *score) {
+  tro_wfa_params prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.metric = TRO_AFFINE;
+  prm.x = 2;
+  prm.o1 = 5;
+  prm.e1 = 1;
+  tro_wfa_result res;
+  tro_wfa_align(&prm, backbone, blen, seq, slen, &res);
+  if (score) *score = res.score;
+  const int64_t n = tro_sam_cigar(res.ops, res.n_ops, 1, out, cap);
+  tro_wfa_result_free(&res);
+  return n;
+}
+
+double tro_get_dist(const uint8_t *a, int alen, const uint8_t *b, int blen) {
+  const size_t MAX_OPS = 10000; /* genotype_cluster.rs:237 */
+  if ((size_t)alen * (size_t)blen > MAX_OPS) {
+    return sqrt((double)(alen > blen ? alen - blen : blen - alen));
+  }
+  tro_wfa_params prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.metric = TRO_EDIT;
+  prm.score_only = 1;
+  tro_wfa_result res;
+  tro_wfa_align(&prm, a, alen, b, blen, &res);
+  return sqrt((double)res.score);
+}

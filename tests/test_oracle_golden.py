@@ -1,0 +1,317 @@
+"""Pins the CPU oracle against every golden vector the reference's own unit tests hold for the
+hot path.  Each case cites the reference test it restates."""
+import json
+import math
+import os
+
+import pytest
+
+PATTERN = b"AGCTAGTGTCAATGGCTACTTTTCAGGTCCT"          # src/wfaligner.rs:1133
+TEXT = b"AACTAAGTGTCGGTGGCTACTATATATCAGGTCCT"         # src/wfaligner.rs:1134
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ------------------------------------------------------------------ WFA --
+
+def test_aligner_indel(oracle):  # wfaligner.rs:1137-1150
+    a = oracle.wfa_align(PATTERN, TEXT, oracle.INDEL)
+    assert a.status == 0 and a.score == 10
+    assert a.cigar_string() == "1M1I1D3M1I5M2I2D8M1I1M1I1M1I9M"
+
+
+def test_aligner_edit(oracle):  # wfaligner.rs:1153-1166
+    a = oracle.wfa_align(PATTERN, TEXT, oracle.EDIT)
+    assert a.status == 0 and a.score == 7
+    assert a.cigar_string() == "1M1X3M1I5M2X8M1I1M1I1M1I9M"
+
+
+def test_aligner_gap_linear(oracle):  # wfaligner.rs:1169-1182
+    a = oracle.wfa_align(PATTERN, TEXT, oracle.LINEAR, x=6, e=2)
+    assert a.score == -20
+    assert a.cigar_string() == "1M1I1D3M1I5M2I2D8M1I1M1I1M1I9M"
+
+
+def test_aligner_gap_affine(oracle):  # wfaligner.rs:1185-1198
+    a = oracle.wfa_align(PATTERN, TEXT, oracle.AFFINE, 6, 4, 2)
+    assert a.score == -40
+    assert a.cigar_string() == "1M1X3M1I5M2X8M3I1M1X9M"
+
+
+def test_aligner_score_only(oracle):  # wfaligner.rs:1201-1211
+    a = oracle.wfa_align(PATTERN, TEXT, oracle.AFFINE, 6, 4, 2, score_only=True)
+    assert a.score == -40 and a.cigar_string() == ""
+
+
+def test_aligner_gap_affine_2pieces(oracle):  # wfaligner.rs:1214-1227
+    a = oracle.wfa_align(PATTERN, TEXT, oracle.AFFINE2P, 6, 2, 2, 4, 1)
+    assert a.score == -34
+    assert a.cigar_string() == "1M1X3M1I5M2X8M1I1M1I1M1I9M"
+
+
+def test_aligner_span_1(oracle):  # wfaligner.rs:1230-1243
+    p = b"AATTTAAGTCTAGGCTACTTTC"
+    t = b"CCGACTACTACGAAATTTAAGTATAGGCTACTTTCCGTACGTACGTACGT"
+    a = oracle.wfa_align(p, t, oracle.AFFINE2P, 8, 4, 2, 24, 1, ends_free=(0, 0, 0, len(t)))
+    assert a.status == 0
+    assert a.alignment_span() == ((0, 22), (13, 35))
+
+
+def test_aligner_span_2(oracle):  # wfaligner.rs:1246-1261
+    v = json.load(open(os.path.join(GOLD, "wfa_long_vectors.json")))["span_2"]
+    p, t = v["pattern"].encode(), v["text"].encode()
+    a = oracle.wfa_align(p, t, oracle.AFFINE2P, 8, 4, 2, 24, 1, ends_free=(0, 0, 0, len(t)))
+    assert a.status == 0
+    assert a.alignment_span() == ((78, 250), (0, 172))
+
+
+def test_aligner_ends_free_global(oracle):  # wfaligner.rs:1264-1279
+    p = b"AATTTAAGTCTAGGCTACTTTC"
+    t = b"CCGACTACTACGAAATTTAAGTATAGGCTACTTTCCGTACGTACGTACGT"
+    a = oracle.wfa_align(p, t, oracle.AFFINE, 6, 4, 2, ends_free=(0, 0, 0, len(t)))
+    assert a.score == -36
+    assert a.cigar_string() == "13I9M1X12M15I"
+
+
+def test_aligner_ends_free_right_extent(oracle):  # wfaligner.rs:1282-1298
+    p = b"AATTTAAGTCTGCTACTTTCACGCAGCT"
+    t = b"AATTTCAGTCTGGCTACTTTCACGTACGATGACAGACTCT"
+    a = oracle.wfa_align(p, t, oracle.AFFINE, 6, 4, 2, ends_free=(0, len(p), 0, len(t)))
+    assert a.score == -24
+    assert a.cigar_string() == "5M1X6M1I11M4D1M15I"
+
+
+def test_aligner_ends_free_left_extent(oracle):  # wfaligner.rs:1301-1316
+    p = b"CTTTCACGTACGTGACAGTCTCT"
+    t = b"AATTTCAGTCTGGCTACTTTCACGTACGATGACAGACTCT"
+    a = oracle.wfa_align(p, t, oracle.AFFINE, 6, 4, 2, ends_free=(0, 0, 0, 0))
+    assert a.score == -48
+    assert a.cigar_string() == "16I12M1I6M1X4M"
+
+
+def test_aligner_ends_free_right_overlap(oracle):  # wfaligner.rs:1319-1334
+    p = b"CGCGTCTGACTGACTGACTAAACTTTCATGTACCTGACA"
+    t = b"AAACTTTCACGTACGTGACATATAGCGATCGATGACT"
+    a = oracle.wfa_align(p, t, oracle.AFFINE, 6, 4, 2, ends_free=(0, 0, 0, 0))
+    assert a.score == -92
+    assert a.cigar_string() == "19D9M1X4M1X5M17I"
+
+
+def test_clipping_score(oracle):  # wfaligner.rs:1337-1381
+    text_lf = b"AAGGAGCTGAGAATTGTTCTTCCAGATACCTTTCCGACCTCTTCTTGGTT"
+    text_rf = b"GGAGTGCAGTGGTGCAATCTTGGCTCACTACAACCTCCGCATCCTGGGTT"
+    pattern_lf = b"AAGGAGCTGAGAATTGTTCGTCCAGATACCTTTCCGACCTCTTCTTGGTT"
+    pattern_rf = b"GGAGTGCAGTGGTGCAATCTTGGCTCACTACAACCTCTGCATCCTGGGTT"
+    text = text_lf + b"ATTT" * 10 + text_rf
+    pattern = pattern_lf + b"ATTT" * 8 + pattern_rf
+    a = oracle.wfa_align(pattern, text, oracle.AFFINE2P, 8, 4, 2, 24, 1)
+    assert a.score == -36
+    assert a.cigar_string() == "19M1X62M8I37M1X12M"
+    assert a.cigar_score() == -36
+    assert a.cigar_score_clipped(50) == -20
+    assert a.cigar_string(50) == "32M8I"
+    b = oracle.wfa_align(pattern, text, oracle.INDEL)
+    assert b.score == 12 and b.cigar_score() == 12
+    assert b.cigar_score_clipped(19) == 10
+    assert b.cigar_score_clipped(0) == 12
+
+
+def test_memory_modes(oracle):  # wfaligner.rs:1384-1421 (High/Med/Low give one result)
+    a = oracle.wfa_align(PATTERN, TEXT, oracle.AFFINE2P, 8, 4, 2, 24, 1)
+    assert a.score == -48 and a.cigar_score() == -48 and a.cigar_score_clipped(0) == -48
+    assert a.cigar_string() == "1M1X3M1I5M2X8M3I1M1X9M"
+
+
+def test_invalid_sequence_heuristic_none(oracle):  # wfaligner.rs:1438-1454 (second half)
+    v = json.load(open(os.path.join(GOLD, "wfa_long_vectors.json")))["invalid_sequence"]
+    a = oracle.wfa_align(v["pattern"].encode(), v["text"].encode(), oracle.AFFINE2P, 8, 4, 2, 24, 1)
+    assert a.status == 0 and a.score == -881
+    assert a.cigar_score() == -881
+
+
+def test_get_and_decode_sam_cigar(oracle):  # wfaligner.rs:1590-1676
+    a = oracle.wfa_align(b"TCTTTACTCTT", b"TCTTTACTCTT", oracle.AFFINE, 4, 6, 2)
+    assert a.sam_cigar(True) == [183]
+    assert oracle.decode_sam_cigar([183]) == [(11, "=")]
+    assert a.sam_cigar(False) == [176]
+    assert oracle.decode_sam_cigar([176]) == [(11, "M")]
+    b = oracle.wfa_align(b"TCTTTACTCTT", b"TCTTTACTATT", oracle.AFFINE, 4, 6, 2)
+    assert b.sam_cigar(True) == [135, 24, 39]
+    assert oracle.decode_sam_cigar([135, 24, 39]) == [(8, "="), (1, "X"), (2, "=")]
+    assert b.sam_cigar(False) == [176]
+
+
+def test_get_alignment_global(oracle):  # wfaligner.rs:1719-1752
+    a = oracle.wfa_align(PATTERN, TEXT, oracle.AFFINE, 1, 5, 1)
+    assert a.score == -18
+    assert a.ops == b"MXMMMIMMMMMXXMMMMMMMMIIIMXMMMMMMMMM"
+    assert a.alignment_span() == ((0, 31), (0, 35))
+
+
+def test_get_alignment_ends_free(oracle):  # wfaligner.rs:1795-1828 (the production flank call shape)
+    p = b"AGTGTCAATGGCTAC"
+    t = b"GGGGGGGGGGAGTGTCAATGGCTACGGGGGGGGGG"
+    a = oracle.wfa_align(p, t, oracle.AFFINE, 1, 5, 1, ends_free=(0, 0, len(t), len(t)))
+    assert a.score == 0
+    assert a.ops == b"I" * 10 + b"M" * 15 + b"I" * 10
+    assert a.alignment_span() == ((0, len(p)), (10, 25))
+
+
+def test_wfa_score_matches_gotoh(oracle):
+    """Not a reference vector: WFA scores must equal a textbook O(nm) affine-gap DP."""
+    import random
+    rng = random.Random(7)
+
+    def gotoh(p, t, x, o, e):
+        INF = 10 ** 9
+        n, m = len(p), len(t)
+        M = [[INF] * (m + 1) for _ in range(n + 1)]
+        I = [[INF] * (m + 1) for _ in range(n + 1)]
+        D = [[INF] * (m + 1) for _ in range(n + 1)]
+        M[0][0] = 0
+        for i in range(n + 1):
+            for j in range(m + 1):
+                if i > 0:
+                    D[i][j] = min(M[i - 1][j] + o + e, D[i - 1][j] + e)
+                if j > 0:
+                    I[i][j] = min(M[i][j - 1] + o + e, I[i][j - 1] + e)
+                if i > 0 and j > 0:
+                    M[i][j] = min(M[i][j], M[i - 1][j - 1] + (0 if p[i - 1] == t[j - 1] else x))
+                M[i][j] = min(M[i][j], I[i][j], D[i][j])
+        return M[n][m]
+
+    for _ in range(60):
+        n = rng.randint(0, 40)
+        p = bytes(rng.choice(b"ACGT") for _ in range(n))
+        t = bytearray(p)
+        for _ in range(rng.randint(0, 6)):
+            r = rng.random()
+            pos = rng.randint(0, len(t))
+            if r < 0.4 and len(t):
+                t[min(pos, len(t) - 1)] = rng.choice(b"ACGT")
+            elif r < 0.7:
+                t[pos:pos] = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 4)))
+            else:
+                del t[pos:pos + rng.randint(1, 4)]
+        t = bytes(t)
+        for (x, o, e) in [(2, 5, 1), (1, 0, 1), (6, 4, 2)]:
+            a = oracle.wfa_align(p, t, oracle.AFFINE, x, o, e)
+            assert -a.score == gotoh(p, t, x, o, e), (p, t, x, o, e)
+            assert a.cigar_score() == a.score
+            # the ops must spell a valid alignment
+            pi = ti = 0
+            for op in a.ops:
+                if op == ord("M"):
+                    assert p[pi] == t[ti]
+                if op == ord("X"):
+                    assert p[pi] != t[ti]
+                if op in b"MX":
+                    pi += 1; ti += 1
+                elif op == ord("I"):
+                    ti += 1
+                else:
+                    pi += 1
+            assert (pi, ti) == (len(p), len(t))
+
+
+# ------------------------------------------------------------------ HMM --
+
+def summarize(spans):
+    """builder.rs:191-205"""
+    out = []
+    for m, s, e in spans:
+        if out and out[-1][2] == m:
+            out[-1] = (out[-1][0], e, m)
+        else:
+            out.append((s, e, m))
+    return out
+
+
+def test_annotate_two_perfect_motif_runs(oracle):  # builder.rs:208-216
+    hmm = oracle.Hmm([b"CAG", b"A"])
+    labels = hmm.label_motifs(hmm.label(b"CAGCAGCAGCAGAAAAA"))
+    assert summarize(labels) == [(0, 12, 0), (12, 17, 1)]
+
+
+def test_annotate_motif_runs_separated_by_insertion(oracle):  # builder.rs:219-240
+    motifs = [b"CAG", b"A"]
+    hmm = oracle.Hmm(motifs)
+    q = b"CAGCAGATCGATCGATCGATCGAAAAA"
+    states = hmm.remove_imperfect_motifs(hmm.label(q), q, 6)
+    assert summarize(hmm.label_motifs(states)) == [
+        (0, 6, 0), (6, 7, 1), (7, 10, 2), (10, 11, 1), (11, 14, 2), (14, 15, 1),
+        (15, 18, 2), (18, 19, 1), (19, 22, 2), (22, 27, 1)]
+
+
+def test_annotate_imperfect_repeat_run(oracle):  # builder.rs:243-250
+    hmm = oracle.Hmm([b"CAG", b"A"])
+    labels = hmm.label_motifs(hmm.label(b"CAGCAGCTGCAGCAGAAACAG"))
+    assert summarize(labels) == [(0, 15, 0), (15, 18, 1), (18, 21, 0)]
+
+
+def test_parse_aga_repeat(oracle):  # builder.rs:253-273
+    hmm = oracle.Hmm([b"AAG", b"CAAC"])
+    q = (b"TCTATGCAACCAACTTTCTGTTAGTCATAGTACCCCAAGAAGAAGAAGAAGAAGAAGAAGAAGAAGAAGAAGAAGAAGAAGAAGAAG"
+         b"AAGAAGAATAGAAATGTGTTTAAGAATTCCTCAATAAG")
+    states = hmm.remove_imperfect_motifs(hmm.label(q), q, 6)
+    assert summarize(hmm.label_motifs(states)) == [
+        (0, 6, 2), (6, 14, 1), (14, 36, 2), (36, 93, 0), (93, 108, 2), (108, 111, 0),
+        (111, 122, 2), (122, 125, 0)]
+
+
+@pytest.mark.parametrize("motifs,query,expect", [
+    ([b"CAG", b"CCG"], b"CAGCAGCAGCCGCCGCCGCCG", 1.0),                # purity.rs:48-55
+    ([b"CAG", b"CCG"], b"CAGCGCAGCCGCCGCCGGG", 17.0 / 20.0),          # purity.rs:58-66
+    ([b"CAG", b"CCG"], b"CAGCAGCAGTTTTTTTTCCGCCGCCG", 18.0 / 26.0),   # purity.rs:69-76
+    ([b"GCN"], b"GCAGCCGCTGAG", 11.0 / 12.0),                         # purity.rs:79-87
+])
+def test_calc_purity(oracle, motifs, query, expect):
+    hmm = oracle.Hmm(motifs)
+    assert hmm.calc_purity(query, hmm.label(query)) == expect
+
+
+def test_calc_purity_empty(oracle):  # purity.rs:90-96
+    hmm = oracle.Hmm([b"CAG", b"CCG"])
+    assert hmm.label(b"") == []
+    assert math.isnan(hmm.calc_purity(b"", []))
+
+
+def test_get_base_match(oracle):  # events.rs:124-145
+    assert oracle.Hmm([b"A"]).get_base_match(3) == b"A"
+    assert oracle.Hmm([b"N"]).get_base_match(3) == b"N"
+    assert oracle.Hmm([b"A"]).get_base_match(1) == b" "      # silent state
+
+
+def test_tutorial_vcf_record(oracle):
+    """docs/tutorial.md:42-45: allele CAG x11 (after the padding base) -> MC=11, MS=0(0-33), AP=1."""
+    hmm = oracle.Hmm([b"CAG"])
+    mc, spans, purity = hmm.annotate(b"CAG" * 11)
+    assert mc == [11] and spans == [(0, 0, 33)] and purity == 1.0
+    mc, spans, purity = hmm.annotate(b"CAG" * 20)          # the REF allele of the record
+    assert mc == [20] and spans == [(0, 0, 60)] and purity == 1.0
+
+
+def test_replace_invalid_bases(oracle):  # src/hmm/utils.rs:29-42
+    assert oracle.replace_invalid_bases(b"ACGTNRYacgt", b"ATCG") == b"ACGTACGTATCG"[:4] + \
+        bytes(b"ATCG"[i % 4] for i in range(4, 11))
+    assert oracle.replace_invalid_bases(b"GCN", b"ATCGN") == b"GCN"
+
+
+def test_find_span_exact_and_fallback(oracle):
+    """span_locater.rs:7-30 semantics on a hand-made case."""
+    import random
+    rng = random.Random(3)
+    flank = bytes(rng.choice(b"ACGT") for _ in range(250))
+    left = bytes(rng.choice(b"ACGT") for _ in range(300))
+    right = bytes(rng.choice(b"ACGT") for _ in range(300))
+    read = left + flank + right
+    span, via, nm = oracle.find_span(flank, read)
+    assert span == (300, 550) and via == 1 and nm == 250
+    bad = bytearray(flank)
+    bad[100] = ord("A") if bad[100] != ord("A") else ord("C")
+    read2 = left + bytes(bad) + right
+    span, via, nm = oracle.find_span(flank, read2)
+    assert span == (300, 550) and via == 2 and nm == 249
+    # unrelated read: alignment completes but is rejected by the match threshold
+    junk = bytes(rng.choice(b"ACGT") for _ in range(700))
+    span, via, nm = oracle.find_span(flank, junk)
+    assert span is None and via == 3 and nm < 175
