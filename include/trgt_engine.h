@@ -1,0 +1,213 @@
+/*
+ * trgt_engine.h -- C ABI of the B200 tandem-repeat DP engine (libtrgt_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of `trgt genotype` (PacificBiosciences/trgt
+ * v3.0.0): the host (Rust in the reference) keeps its Locus/Genotyper surface and per-locus
+ * worker logic and replaces four leaf calls by batched, stateless calls into this library.
+ * All pointers are plain host pointers unless a function says "device"; no torch / C++ types
+ * cross the boundary; nothing throws or aborts across it.  The reference reaches its aligner
+ * through the one-alignment-at-a-time WFA2-lib FFI re-exported by src/wfa2.rs:2 (call sites
+ * src/wfaligner.rs:371,458,467,479-485,492-498,519-525,944-949,999) and calls its HMM as plain
+ * Rust (src/hmm/); each entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *  - sequences are ASCII bytes in one contiguous buffer with CSR offsets (uint64_t[n+1]);
+ *  - a call blocks until its batch is complete and results are in host memory;
+ *  - return value: 0 = OK, <0 = engine failure (trgt_engine_last_error() has the text);
+ *    per-item failures are reported in per-item status arrays with the WFA2 status codes
+ *    the reference surfaces (src/wfaligner.rs:132-159);
+ *  - entry points may be called from any host thread; calls on one engine serialise.
+ *  - there is NO CPU fallback: without a CUDA device trgt_engine_create fails.
+ */
+#ifndef TRGT_ENGINE_H
+#define TRGT_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRGT_OK 0
+#define TRGT_ERR_CUDA (-1)
+#define TRGT_ERR_ARG (-2)
+#define TRGT_ERR_NO_DEVICE (-4)
+#define TRGT_ERR_INTERNAL (-5)
+
+/* per-item status, numerically the WF_STATUS_* codes of WFA2-lib */
+#define TRGT_ITEM_OK 0
+#define TRGT_ITEM_MAX_STEPS (-100)
+#define TRGT_ITEM_OOM (-200)
+#define TRGT_ITEM_UNATTAINABLE (-300)
+#define TRGT_ITEM_INVALID_BASE (-400) /* reference panics: hmm_model.rs:250, builder.rs:182 */
+
+typedef struct trgt_engine trgt_engine_t;
+
+/* CSR set of byte sequences */
+typedef struct {
+  const uint8_t *data;
+  const uint64_t *offsets; /* [n+1] */
+  uint64_t n;
+} trgt_seqs_t;
+
+/* --aln-scoring (src/cli.rs:271-280): gap-affine penalties of the flank aligner */
+typedef struct {
+  int32_t mismatch, gap_open, gap_extend;
+} trgt_scoring_t;
+
+/* Option<(usize,usize)> */
+typedef struct {
+  int32_t found;
+  uint32_t start, end;
+} trgt_span_t;
+
+/* how one (read, flank) pair was resolved; optional diagnostic output of trgt_flank_spans */
+#define TRGT_VIA_NONE 0
+#define TRGT_VIA_EXACT 1        /* span_locater.rs:10-12 */
+#define TRGT_VIA_WFA 2          /* span_locater.rs:14-25, accepted */
+#define TRGT_VIA_WFA_REJECTED 3 /* count_matches below threshold */
+typedef struct {
+  int32_t via;
+  int32_t matches; /* count_matches (piece length for an exact hit) */
+  int32_t score;   /* WFA score (<= 0), 0 for an exact hit */
+  uint32_t start, end;
+} trgt_flank_hit_t;
+
+/* ---- lifetime ---------------------------------------------------------- */
+
+/* One engine per GPU.  Replaces the thread-local aligner trio of
+ * src/commands/genotype.rs:94-103 (THREAD_WFA_FLANK / _CONSENSUS / _ED). */
+int32_t trgt_engine_create(int32_t device, trgt_engine_t **out);
+void trgt_engine_destroy(trgt_engine_t *eng);
+const char *trgt_engine_last_error(const trgt_engine_t *eng);
+/* text of the last failure of trgt_engine_create (no engine to ask) */
+const char *trgt_last_create_error(void);
+/* cudaStream_t the engine launches on (for external CUDA-event timing) */
+void *trgt_engine_stream(trgt_engine_t *eng);
+int32_t trgt_engine_sm_count(const trgt_engine_t *eng);
+
+/* pinned host memory for the caller's packing buffers (DMA-direct H2D/D2H) */
+void *trgt_host_alloc(size_t bytes);
+void trgt_host_free(void *p);
+
+/* ---- phase A: flank location (a1-a4) ------------------------------------ */
+
+/* find_tr_spans for a chunk of loci: src/trgt/genotype/span_locater.rs:32-68 (find_spans :7-30,
+ * WFA fallback = WFAligner::align_ends_free src/wfaligner.rs:503-528 with the aligner of
+ * src/commands/genotype.rs:66-80: gap-affine, Heuristic::None, MemoryHigh; then count_matches
+ * :988 and get_alignment_span :864).
+ *   left_pieces/right_pieces: n_loci flank pieces (lf[len-P..], rf[..P]; span_locater.rs:38-39)
+ *   reads: all clipped reads of the chunk; locus_read_offsets[n_loci+1] delimits each locus
+ *   spans_out[n_reads]; hits_out[2*n_reads] optional (may be NULL): [2*r] left, [2*r+1] right */
+int32_t trgt_flank_spans(trgt_engine_t *eng, const trgt_seqs_t *left_pieces,
+                         const trgt_seqs_t *right_pieces, const trgt_seqs_t *reads,
+                         const uint32_t *locus_read_offsets, uint32_t n_loci,
+                         trgt_scoring_t scoring, double min_flank_id_frac,
+                         trgt_span_t *spans_out, trgt_flank_hit_t *hits_out);
+
+/* ---- phase B: consensus alignments (a5) and edit distances (a6) ---------- */
+
+typedef struct {
+  uint64_t n;              /* number of alignments */
+  const uint64_t *offsets; /* [n+1] into words */
+  const uint32_t *words;   /* run-length SAM CIGAR: (len<<4)|op, '='=7 'X'=8 'I'=1 'D'=2,
+                              exactly what WFAligner::decode_sam_cigar expects (wfaligner.rs:961) */
+  const int32_t *scores;   /* WFA score, -cost */
+  const int32_t *status;   /* per-item TRGT_ITEM_* */
+} trgt_cigars_t;
+
+/* utils::align for many (backbone, seqs) groups: src/utils/align.rs:14-28
+ * (WFAligner::align_end_to_end src/wfaligner.rs:489, gap-affine (2,5,1) fixed, then
+ * get_sam_cigar(true) :932).  group_seq_offsets[n_groups+1] delimits each backbone's seqs.
+ * Exact WFA; the reference's BiWFA + default heuristic are not pinned by any reference test
+ * (see DESIGN.md "parity unpinned").  `out` points into engine-owned memory that stays valid
+ * until the next call on this engine (as WFA2 owns its CIGAR until the next wavefront_align). */
+int32_t trgt_align_e2e(trgt_engine_t *eng, const trgt_seqs_t *backbones, const trgt_seqs_t *seqs,
+                       const uint32_t *group_seq_offsets, uint32_t n_groups, trgt_cigars_t *out);
+
+/* get_dist_matrix for many loci: src/trgt/genotype/genotype_cluster.rs:236-286.
+ * locus_seq_offsets[n_loci+1] delimits each locus' TR sequences; dists_out receives, locus after
+ * locus, the condensed upper triangles (index i*n - i(i+1)/2 + (j-i-1)), sqrt applied. */
+int32_t trgt_edit_dist(trgt_engine_t *eng, const trgt_seqs_t *seqs,
+                       const uint32_t *locus_seq_offsets, uint32_t n_loci, double *dists_out);
+
+/* ---- phase C: motif HMM (a7-a13) ---------------------------------------- */
+
+typedef struct {
+  uint32_t motif_index, start, end;
+} trgt_motif_span_t;
+
+typedef struct {
+  uint64_t n;                        /* number of alleles */
+  const uint64_t *motif_count_offsets; /* [n+1] */
+  const uint32_t *motif_counts;        /* MC: copies per motif of the allele's locus */
+  const uint64_t *span_offsets;        /* [n+1] */
+  const trgt_motif_span_t *spans;      /* MS: collapsed labels, skip spans dropped; empty <=> None */
+  const double *purity;                /* AP (NaN for an empty allele) */
+  const int32_t *status;               /* TRGT_ITEM_* */
+  /* optional raw Viterbi state paths (Hmm::label), filled only when want_paths != 0 */
+  const uint64_t *path_offsets;        /* [n+1] or NULL */
+  const uint32_t *paths;
+} trgt_annotations_t;
+
+/* label_with_hmm for many loci: src/trgt/workflows/tr.rs:454-492 = build_hmm
+ * (src/hmm/builder.rs:4) once per locus, then per allele Hmm::label (hmm_model.rs:144),
+ * calc_purity (purity.rs:6), remove_imperfect_motifs(.., 6) (operations.rs:6), label_motifs
+ * (hmm_model.rs:158), skip-span filter, count_motifs / collapse_labels (utils.rs:3,11).
+ * replace_invalid_bases (utils.rs:29) is applied inside to motifs (ATCGN) and alleles (ATCG).
+ *   motifs: all motifs of all loci; locus_motif_offsets[n_loci+1] delimits each locus
+ *   alleles: sequences to annotate; allele_locus[n_alleles] = locus of each
+ * Also serves filter_impure_trs (tr.rs:400-452): pass reads' TR sequences as alleles. */
+int32_t trgt_hmm_label(trgt_engine_t *eng, const trgt_seqs_t *motifs,
+                       const uint32_t *locus_motif_offsets, uint32_t n_loci,
+                       const trgt_seqs_t *alleles, const uint32_t *allele_locus,
+                       int32_t want_paths, trgt_annotations_t *out);
+
+/* ---- resident-batch interface (same phases, inputs kept in HBM) ---------- */
+
+/* upload once, run many times: lets a caller (and bench.py) separate PCIe from kernel time */
+typedef struct trgt_flank_batch trgt_flank_batch_t;
+int32_t trgt_flank_upload(trgt_engine_t *eng, const trgt_seqs_t *left_pieces,
+                          const trgt_seqs_t *right_pieces, const trgt_seqs_t *reads,
+                          const uint32_t *locus_read_offsets, uint32_t n_loci,
+                          trgt_scoring_t scoring, double min_flank_id_frac,
+                          trgt_flank_batch_t **out);
+int32_t trgt_flank_run(trgt_engine_t *eng, trgt_flank_batch_t *batch);            /* async on the engine stream */
+int32_t trgt_flank_download(trgt_engine_t *eng, trgt_flank_batch_t *batch,
+                            trgt_span_t *spans_out, trgt_flank_hit_t *hits_out);   /* syncs */
+void trgt_flank_free(trgt_engine_t *eng, trgt_flank_batch_t *batch);
+
+typedef struct trgt_align_batch trgt_align_batch_t;
+int32_t trgt_align_upload(trgt_engine_t *eng, const trgt_seqs_t *backbones,
+                          const trgt_seqs_t *seqs, const uint32_t *group_seq_offsets,
+                          uint32_t n_groups, trgt_align_batch_t **out);
+int32_t trgt_align_run(trgt_engine_t *eng, trgt_align_batch_t *batch);
+int32_t trgt_align_download(trgt_engine_t *eng, trgt_align_batch_t *batch, trgt_cigars_t *out);
+void trgt_align_free(trgt_engine_t *eng, trgt_align_batch_t *batch);
+
+typedef struct trgt_hmm_batch trgt_hmm_batch_t;
+int32_t trgt_hmm_upload(trgt_engine_t *eng, const trgt_seqs_t *motifs,
+                        const uint32_t *locus_motif_offsets, uint32_t n_loci,
+                        const trgt_seqs_t *alleles, const uint32_t *allele_locus,
+                        int32_t want_paths, trgt_hmm_batch_t **out);
+int32_t trgt_hmm_run(trgt_engine_t *eng, trgt_hmm_batch_t *batch);
+int32_t trgt_hmm_download(trgt_engine_t *eng, trgt_hmm_batch_t *batch, trgt_annotations_t *out);
+void trgt_hmm_free(trgt_engine_t *eng, trgt_hmm_batch_t *batch);
+
+/* ---- instrumentation ------------------------------------------------------ */
+
+/* When enabled, every kernel launch is bracketed by CUDA events on the engine stream. */
+void trgt_engine_set_profiling(trgt_engine_t *eng, int32_t on);
+void trgt_engine_reset_stats(trgt_engine_t *eng);
+/* number of distinct kernels seen; i-th: name, launches, total device ms (syncs the stream) */
+int32_t trgt_engine_kernel_count(trgt_engine_t *eng);
+int32_t trgt_engine_kernel_stat(trgt_engine_t *eng, int32_t i, const char **name,
+                                uint64_t *launches, double *total_ms);
+/* launches since the last reset (counted whether or not profiling is on) */
+uint64_t trgt_engine_launches(const trgt_engine_t *eng);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,72 @@
+// emul_hmm.cpp -- TEST INFRASTRUCTURE ONLY.  Instantiates the HMM core (trgt_b200/csrc/hmm_core.h)
+// with the one-lane SerialGroup so that its index arithmetic and tie-breaking can be compared with
+// the oracle on a machine without a GPU.  Never linked into libtrgt_b200.so.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../trgt_b200/csrc/hmm_core.h"
+#include "../../trgt_b200/csrc/hmm_host.h"
+
+using namespace trgt;
+
+extern "C" {
+
+// returns n_spans (collapsed) or <0; path_out gets Hmm::label (forward order), *path_len its length
+long emu_hmm_annotate(const uint8_t *motifs, const uint64_t *moff, int nm, const uint8_t *allele, int L,
+                      uint32_t *mc, HmmSpan *spans, uint32_t span_cap, double *purity,
+                      uint32_t *path_out, uint64_t path_cap, uint64_t *path_len, int *S_out) {
+  static HmmJumpTable jt;
+  int max_len = 0;
+  int mbytes = 0;
+  for (int b = 0; b < nm; b++) {
+    int n = (int)(moff[b + 1] - moff[b]);
+    if (n > max_len) max_len = n;
+    mbytes += n;
+  }
+  jt.ensure(max_len);
+  const HmmConsts c = hmm_make_consts();
+  const int nb = nm + 1;
+  std::vector<uint8_t> o_bytes(mbytes + 1);
+  std::vector<uint32_t> o_moff(nb), o_mmoff(nb);
+  std::vector<uint16_t> o_n(nb), o_ms(nb);
+  int S_guess = 7;
+  for (int b = 0; b < nm; b++) S_guess += 3 * (int)(moff[b + 1] - moff[b]) + 1;
+  std::vector<uint16_t> o_stblk(S_guess + 8);
+  HmmModel model;
+  SerialGroup g;
+  const int S = hmm_model_build(g, motifs, moff, nm, jt.off.data(), o_bytes.data(), o_moff.data(),
+                                o_mmoff.data(), o_n.data(), o_ms.data(), o_stblk.data(), &model);
+  if (S < 0) return -400;
+  if (S != S_guess) return -401;
+  if (S_out) *S_out = S;
+  for (int b = 0; b < nm; b++) mc[b] = 0;
+  if (L == 0) {
+    *purity = NAN;
+    if (path_len) *path_len = 0;
+    return 0;
+  }
+  std::vector<double> sc0(S), sc1(S);
+  std::vector<uint8_t> bp((size_t)(L + 2) * S, 0xEE);
+  hmm_viterbi(g, model, c, jt.lp.data(), allele, L, sc0.data(), sc1.data(), bp.data());
+  // counting walk, then writing walk (as the device does)
+  std::vector<uint32_t> mc_tmp(nm + 1, 0);
+  std::vector<uint32_t> rev(path_cap ? path_cap : 1);
+  uint64_t plen = 0;
+  HmmAnnot a = hmm_annotate(model, allele, L, bp.data(), 6, mc_tmp.data(), nullptr, 0, rev.data(),
+                            path_cap, &plen);
+  if (a.status < 0) return -402;
+  if (a.n_spans > span_cap) return -2;
+  HmmAnnot b2 = hmm_annotate(model, allele, L, bp.data(), 6, mc, spans, a.n_spans, nullptr, 0, nullptr);
+  if (b2.n_spans != a.n_spans) return -403;
+  *purity = a.purity;
+  if (path_len) *path_len = plen;
+  if (path_out) {
+    const uint64_t n = plen < path_cap ? plen : path_cap;
+    for (uint64_t i = 0; i < n; i++) path_out[i] = rev[n - 1 - i];
+  }
+  return (long)a.n_spans;
+}
+
+}  // extern "C"

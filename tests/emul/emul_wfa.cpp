@@ -1,0 +1,57 @@
+// emul_wfa.cpp -- TEST INFRASTRUCTURE ONLY.  Serial instantiation of trgt_b200/csrc/wfa_core.h
+// (see emul_hmm.cpp).  Never linked into libtrgt_b200.so.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../trgt_b200/csrc/wfa_core.h"
+
+using namespace trgt;
+
+extern "C" {
+
+// Two-pass alignment exactly as the device runs it: ring score pass, cone trace pass.
+// out[0]=status out[1]=score(-cost) out[2]=k out[3]=off out[4]=matches out[5]=ystart out[6]=yend
+// out[7]=n_words out[8]=trace ints used (bound)
+int emu_wfa_align(const uint8_t *p, int P, const uint8_t *t, int T, int x, int o, int e, int pbf, int pef,
+                  int tbf, int tef, int *out, uint32_t *words, uint32_t words_cap) {
+  WfaProb pr;
+  pr.p = p; pr.P = P; pr.t = t; pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
+  pr.pbf = pbf; pr.pef = pef; pr.tbf = tbf; pr.tef = tef;
+  SerialGroup g;
+  std::vector<int> ring(wfa_ring_ints(pr) + 1, 0x7ead);
+  const WfaEnd end = wfa_score_ring(g, pr, ring.data(), wfa_score_cap(pr));
+  out[0] = end.status; out[1] = -end.s; out[2] = end.k; out[3] = end.off;
+  if (end.status != TRGT_WFA_OK) return end.status;
+  const size_t need = wfa_trace_ints(pr, end.s);
+  std::vector<int> ws(need + 1, 0x7ead);
+  const int rc = wfa_trace_forward(g, pr, end.s, end.k, ws.data(), need);
+  if (rc != 0) { out[0] = rc; return rc; }
+  // the cone must reproduce the terminating cell
+  {
+    WfaView v = wfa_hist_view(ws.data(), end.s);
+    if (wfa_at(v.m, v, end.k) != end.off) { out[0] = -999; return -999; }
+  }
+  WfaFlankSink fs(T);
+  wfa_backtrace(pr, end.s, end.k, end.off, ws.data(), fs);
+  out[4] = fs.matches; out[5] = fs.ystart(); out[6] = fs.yend();
+  WfaCigarSink cs(words, words_cap);
+  wfa_backtrace(pr, end.s, end.k, end.off, ws.data(), cs);
+  out[7] = (int)cs.finish();
+  if (cs.overflow) { out[0] = -998; return -998; }
+  out[8] = (int)need;
+  return 0;
+}
+
+int emu_flank_scan(const uint8_t *piece, int P, const uint8_t *t, int T) {
+  SerialGroup g;
+  return flank_scan(g, piece, P, t, T);
+}
+
+int emu_edit_distance(const uint8_t *a, int la, const uint8_t *b, int lb) {
+  return edit_distance_128(a, la, b, lb);
+}
+
+}  // extern "C"

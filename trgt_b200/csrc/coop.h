@@ -1,0 +1,85 @@
+// coop.h -- cooperative-group shim shared by every kernel core in this directory.
+//
+// The DP cores (hmm_core.h, wfa_core.h) are written once, as templates over a "group" of
+// lanes that cooperate on ONE work item: a warp (WarpGroup), a whole CTA (BlockGroup) or,
+// in the CPU unit tests only, a single host lane (SerialGroup, tests/emul/).  All
+// cross-lane communication goes through memory followed by g.sync(), or through the
+// reductions below, so a loop of the form
+//     for (int i = g.lane(); i < n; i += g.size()) { ... independent iterations ... }
+//     g.sync();
+// has identical semantics on the device and in the serial test build.  The serial build
+// exists so the index arithmetic and tie-breaking of the cores can be checked against the
+// oracle on a machine without a GPU; it is never part of libtrgt_b200.so.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TRGT_HD __host__ __device__ __forceinline__
+#define TRGT_D __device__ __forceinline__
+#else
+#define TRGT_HD inline
+#endif
+
+namespace trgt {
+
+// One lane doing everything (CPU tests; also usable for a thread-per-item kernel).
+struct SerialGroup {
+  TRGT_HD int lane() const { return 0; }
+  TRGT_HD int size() const { return 1; }
+  TRGT_HD void sync() const {}
+  TRGT_HD int min_i(int v) const { return v; }
+  TRGT_HD int max_i(int v) const { return v; }
+  TRGT_HD int any(int p) const { return p; }
+  TRGT_HD int bcast0(int v) const { return v; }
+};
+
+#if defined(__CUDACC__)
+// 32 lanes of one warp; several warps of a CTA each own a different item.
+struct WarpGroup {
+  TRGT_D int lane() const { return (int)(threadIdx.x & 31u); }
+  TRGT_D int size() const { return 32; }
+  TRGT_D void sync() const { __syncwarp(); }
+  TRGT_D int min_i(int v) const { return __reduce_min_sync(0xffffffffu, v); }
+  TRGT_D int max_i(int v) const { return __reduce_max_sync(0xffffffffu, v); }
+  TRGT_D int any(int p) const { return __any_sync(0xffffffffu, p); }
+  TRGT_D int bcast0(int v) const { return __shfl_sync(0xffffffffu, v, 0); }
+};
+
+// The whole CTA (blockDim.x threads, a multiple of 32, <= 1024) on one item.
+// `scratch` points at 33 ints of shared memory owned by the group.
+struct BlockGroup {
+  int *scratch;
+  TRGT_D explicit BlockGroup(int *s) : scratch(s) {}
+  TRGT_D int lane() const { return (int)threadIdx.x; }
+  TRGT_D int size() const { return (int)blockDim.x; }
+  TRGT_D void sync() const { __syncthreads(); }
+  TRGT_D int min_i(int v) const {
+    v = __reduce_min_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31u) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = scratch[0];
+    for (unsigned w = 1; w < (blockDim.x >> 5); w++) r = min(r, scratch[w]);
+    __syncthreads();
+    return r;
+  }
+  TRGT_D int max_i(int v) const {
+    v = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31u) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = scratch[0];
+    for (unsigned w = 1; w < (blockDim.x >> 5); w++) r = max(r, scratch[w]);
+    __syncthreads();
+    return r;
+  }
+  TRGT_D int any(int p) const { return __syncthreads_or(p); }
+  TRGT_D int bcast0(int v) const {
+    if (threadIdx.x == 0) scratch[32] = v;
+    __syncthreads();
+    int r = scratch[32];
+    __syncthreads();
+    return r;
+  }
+};
+#endif
+
+}  // namespace trgt

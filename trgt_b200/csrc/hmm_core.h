@@ -1,0 +1,455 @@
+// hmm_core.h -- motif HMM of `trgt genotype` restructured for one cooperating group per allele.
+//
+// Replaces (reference, PacificBiosciences/trgt v3.0.0):
+//   build_hmm / define_motif_block      src/hmm/builder.rs:4-184
+//   Hmm::label (Viterbi + traceback)    src/hmm/hmm_model.rs:54-156, order_states :206-240
+//   calc_purity / get_events            src/hmm/purity.rs:6-41, src/hmm/events.rs:17-117
+//   remove_imperfect_motifs             src/hmm/operations.rs:6-80
+//   Hmm::label_motifs                   src/hmm/hmm_model.rs:158-200
+//   skip filter, count_motifs, collapse src/trgt/workflows/tr.rs:471-476, src/hmm/utils.rs:3-27
+//   replace_invalid_bases               src/hmm/utils.rs:29-42
+//
+// Design (not the reference's): the model is never materialised as edge lists.  A state's role
+// (ms / match_i / ins_i / del_i / me / skip ...) is decoded from its index and the motif block
+// table, and its in-edges are enumerated by arithmetic in the reference's list order, which is
+// the tie-break order of the strict '>' argmax.  Only ln() constants computed by the host libm
+// are shipped (HmmConsts + the jump-in table), so every score is the same left-to-right f64 sum
+// `prev + ln(trans) + ln(emit)` the reference forms.  A column is evaluated in three barriers:
+// (1) all emitting states from the previous column, (2) per motif block the silent chain
+// del_0..del_{n-2}, me, (3) re, rs, ms.  That is a topological order of the silent sub-graph,
+// so it yields the same values as the reference's Kahn layering.  Only two score columns live
+// on chip; the per-column back-pointer (in-edge index, one byte per state) goes to HBM, S
+// contiguous bytes per column.  Post-processing (purity, imperfect-copy removal, span
+// labelling, skip filtering, counting, collapsing) is a single reverse walk over the
+// back-pointers that never materialises the state path.
+#pragma once
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "coop.h"
+
+namespace trgt {
+
+struct HmmConsts {
+  double lp_match;       // ln(0.90)            match->match, ms->match_0, match->me
+  double lp_ins_exit;    // ln(1.0 - 0.25)      ins->match, ins->me
+  double lp_half;        // ln(0.50)            del->match, del->del, me->ms, me->re, skip->skip, skip->me
+  double lp_ins_loop;    // ln(0.25)            ins->ins
+  double lp_indel_open;  // ln((1.0 - 0.90)/2)  match->ins, match->del
+  double lp_end;         // ln(0.10)            re->end
+  double lp_one;         // ln(1.00)            start->rs, re->rs, rs->ms, ms->skip, del->me
+  double em_hi;          // ln(0.90)
+  double em_lo;          // ln(0.03)
+  double em_quarter;     // ln(0.25)
+  double em_one;         // ln(1.00)
+};
+
+struct HmmSpan {
+  uint32_t motif_index, start, end;
+};
+
+// Block table of one locus' model.  Block b < nb-1 is motif b, block nb-1 is the skip block.
+struct HmmModel {
+  int S;                      // 7 + sum(3 n + 1)                      builder.rs:5-6
+  int nb;                     // motifs + 1
+  const uint8_t *motif_bytes; // sanitised motif bytes, concatenated
+  const uint32_t *blk_moff;   // [nb] offset of the motif's bytes
+  const uint32_t *blk_mmoff;  // [nb] offset of the motif's jump-in ln table (indexed by match index)
+  const uint16_t *blk_n;      // [nb] motif length (skip block: 0)
+  const uint16_t *blk_ms;     // [nb] state index of the block's ms
+  const uint16_t *st_blk;     // [S] block of each state (0xFFFF: start, rs, re, end)
+};
+
+enum HmmRoleKind {
+  HR_START = 0, HR_RS, HR_RE, HR_END, HR_MS, HR_MATCH, HR_INS, HR_DEL, HR_ME, HR_SKIP_MS, HR_SKIP, HR_SKIP_ME
+};
+
+struct HmmRole {
+  int kind, b, i, n, ms;
+};
+
+TRGT_HD HmmRole hmm_role(const HmmModel &m, int st) {
+  HmmRole r;
+  r.b = -1; r.i = 0; r.n = 0; r.ms = 0;
+  if (st == 0) { r.kind = HR_START; return r; }
+  if (st == 1) { r.kind = HR_RS; return r; }
+  if (st == m.S - 2) { r.kind = HR_RE; return r; }
+  if (st == m.S - 1) { r.kind = HR_END; return r; }
+  const int b = m.st_blk[st];
+  r.b = b;
+  r.ms = m.blk_ms[b];
+  const int off = st - r.ms;
+  if (b == m.nb - 1) {
+    r.kind = off == 0 ? HR_SKIP_MS : (off == 1 ? HR_SKIP : HR_SKIP_ME);
+    return r;
+  }
+  const int n = m.blk_n[b];
+  r.n = n;
+  if (off == 0) { r.kind = HR_MS; }
+  else if (off <= n) { r.kind = HR_MATCH; r.i = off - 1; }
+  else if (off <= 2 * n) { r.kind = HR_INS; r.i = off - n - 1; }
+  else if (off < 3 * n) { r.kind = HR_DEL; r.i = off - 2 * n - 1; }
+  else { r.kind = HR_ME; }
+  return r;
+}
+
+// replace_invalid_bases(seq, ATCG) for one base, utils.rs:29-42
+TRGT_HD uint8_t hmm_clean_base(uint8_t b, uint32_t index) {
+  if (b == 'A' || b == 'T' || b == 'C' || b == 'G') return b;
+  const uint32_t r = index & 3u;
+  return r == 0 ? 'A' : (r == 1 ? 'T' : (r == 2 ? 'C' : 'G'));
+}
+// replace_invalid_bases(motif, ATCGN)
+TRGT_HD uint8_t hmm_clean_motif_base(uint8_t b, uint32_t index) {
+  if (b == 'A' || b == 'T' || b == 'C' || b == 'G' || b == 'N') return b;
+  const uint32_t r = index % 5u;
+  return r == 0 ? 'A' : (r == 1 ? 'T' : (r == 2 ? 'C' : (r == 3 ? 'G' : 'N')));
+}
+// encode_base, hmm_model.rs:243-252 ('#' = 0 is produced by the column loop itself)
+TRGT_HD int hmm_symbol(uint8_t b) { return b == 'A' ? 1 : (b == 'T' ? 2 : (b == 'C' ? 3 : 4)); }
+
+// Fill the block table for one locus.  `motifs`/`moff` are the raw motif bytes and offsets of
+// this locus' nm motifs (moff[0..nm], absolute offsets into `motifs`).  mm_off[n] locates the
+// jump-in table of motif length n.  Out arrays are caller-provided (shared memory on the device).
+// Returns S, or -1 if a motif is empty.
+template <class G>
+TRGT_HD int hmm_model_build(const G &g, const uint8_t *motifs, const uint64_t *moff, int nm,
+                            const uint32_t *mm_off, uint8_t *o_bytes, uint32_t *o_moff,
+                            uint32_t *o_mmoff, uint16_t *o_n, uint16_t *o_ms, uint16_t *o_stblk,
+                            HmmModel *model) {
+  const int nb = nm + 1;
+  // block offsets: a short serial prefix sum (nm is 1 for most loci, <= 10 in shipped catalogs)
+  int S = 0;
+  int bad = 0;
+  if (g.lane() == 0) {
+    int ms = 2;
+    uint32_t bytes = 0;
+    for (int b = 0; b < nm; b++) {
+      const int n = (int)(moff[b + 1] - moff[b]);
+      if (n <= 0) bad = 1;
+      o_ms[b] = (uint16_t)ms;
+      o_n[b] = (uint16_t)n;
+      o_moff[b] = bytes;
+      o_mmoff[b] = n > 0 ? mm_off[n] : 0;
+      bytes += (uint32_t)(n > 0 ? n : 0);
+      ms += 3 * n + 1;
+    }
+    o_ms[nm] = (uint16_t)ms;
+    o_n[nm] = 0;
+    o_moff[nm] = bytes;
+    o_mmoff[nm] = 0;
+    S = ms + 3 + 2;  // skip block (3) + re + end
+  }
+  S = g.bcast0(S);
+  bad = g.bcast0(bad);
+  g.sync();
+  if (bad) return -1;
+  for (int b = g.lane(); b < nb; b += g.size()) {
+    const int n = o_n[b];
+    const int ms = o_ms[b];
+    const int cnt = (b == nm) ? 3 : 3 * n + 1;
+    for (int j = 0; j < cnt; j++) o_stblk[ms + j] = (uint16_t)b;
+    if (b < nm) {
+      const uint8_t *src = motifs + moff[b];
+      for (int j = 0; j < n; j++) o_bytes[o_moff[b] + j] = hmm_clean_motif_base(src[j], (uint32_t)j);
+    }
+  }
+  if (g.lane() == 0) {
+    o_stblk[0] = 0xFFFF; o_stblk[1] = 0xFFFF; o_stblk[S - 2] = 0xFFFF; o_stblk[S - 1] = 0xFFFF;
+  }
+  g.sync();
+  model->S = S;
+  model->nb = nb;
+  model->motif_bytes = o_bytes;
+  model->blk_moff = o_moff;
+  model->blk_mmoff = o_mmoff;
+  model->blk_n = o_n;
+  model->blk_ms = o_ms;
+  model->st_blk = o_stblk;
+  return S;
+}
+
+#define TRGT_HMM_NONE 255
+
+// One candidate of the argmax, reference order, strict '>' (hmm_model.rs:79-88).
+#define TRGT_CAND(from_score, lp)                   \
+  do {                                              \
+    const double sc_ = ((from_score) + (lp)) + em;  \
+    if (sc_ > best) { best = sc_; arg = idx; }      \
+    idx++;                                          \
+  } while (0)
+
+// Viterbi over '#' + allele + '#'.  sc0/sc1: two columns of S doubles (on-chip).  bp: (L+2)*S bytes.
+template <class G>
+TRGT_HD void hmm_viterbi(const G &g, const HmmModel &m, const HmmConsts &c, const double *mm_lp,
+                         const uint8_t *allele, int L, double *sc0, double *sc1, uint8_t *bp) {
+  const int S = m.S, nb = m.nb;
+  double *prev = sc0, *cur = sc1;
+  const double NEG = -INFINITY;
+  for (int col = 0; col <= L + 1; col++) {
+    const int sym = (col == 0 || col == L + 1)
+                        ? 0 : hmm_symbol(hmm_clean_base(allele[col - 1], (uint32_t)(col - 1)));
+    uint8_t *bpc = bp + (size_t)col * (size_t)S;
+    // (1) emitting states, look back one column (hmm_model.rs:62-69)
+    for (int st = g.lane(); st < S; st += g.size()) {
+      const HmmRole r = hmm_role(m, st);
+      double best = NEG;
+      int arg = TRGT_HMM_NONE, idx = 0;
+      double em;
+      switch (r.kind) {
+        case HR_START:
+          if (col == 0) { best = c.em_one; arg = 0; }  // hmm_model.rs:91-94
+          break;
+        case HR_END:
+          if (col > 0 && sym == 0) { em = c.em_one; TRGT_CAND(prev[S - 2], c.lp_end); }
+          break;
+        case HR_MATCH:
+          if (col > 0 && sym != 0) {
+            const uint8_t mb = m.motif_bytes[m.blk_moff[r.b] + r.i];
+            em = (mb == 'N') ? c.em_quarter : (hmm_symbol(mb) == sym ? c.em_hi : c.em_lo);
+            if (r.i == 0) {
+              TRGT_CAND(prev[r.ms], c.lp_match);
+            } else {
+              TRGT_CAND(prev[st - 1], c.lp_match);
+              TRGT_CAND(prev[r.ms], mm_lp[m.blk_mmoff[r.b] + r.i]);
+              TRGT_CAND(prev[r.ms + r.n + r.i], c.lp_ins_exit);                     // ins_{i-1}
+              if (r.i >= 2) TRGT_CAND(prev[r.ms + 2 * r.n + r.i - 1], c.lp_half);   // del_{i-2}
+            }
+          }
+          break;
+        case HR_INS:
+          if (col > 0 && sym != 0) {
+            em = c.em_quarter;
+            TRGT_CAND(prev[st], c.lp_ins_loop);
+            TRGT_CAND(prev[r.ms + 1 + r.i], c.lp_indel_open);
+          }
+          break;
+        case HR_SKIP:
+          if (col > 0 && sym != 0) {
+            em = c.em_quarter;
+            TRGT_CAND(prev[r.ms], c.lp_one);
+            TRGT_CAND(prev[st], c.lp_half);
+          }
+          break;
+        default:
+          continue;  // silent: steps (2) and (3)
+      }
+      cur[st] = best;
+      bpc[st] = (uint8_t)arg;
+    }
+    g.sync();
+    // (2) per block: del chain then me, same column (silent states, hmm_model.rs:62-69)
+    for (int b = g.lane(); b < nb; b += g.size()) {
+      const int ms = m.blk_ms[b];
+      const double em = 0.0;
+      if (b == nb - 1) {
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        TRGT_CAND(cur[ms + 1], c.lp_half);
+        cur[ms + 2] = best;
+        bpc[ms + 2] = (uint8_t)arg;
+        continue;
+      }
+      const int n = m.blk_n[b];
+      const int m0 = ms + 1, i0 = ms + 1 + n, d0 = ms + 1 + 2 * n, me = ms + 3 * n;
+      for (int i = 0; i + 1 < n; i++) {
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        TRGT_CAND(cur[m0 + i], c.lp_indel_open);
+        if (i > 0) TRGT_CAND(cur[d0 + i - 1], c.lp_half);
+        cur[d0 + i] = best;
+        bpc[d0 + i] = (uint8_t)arg;
+      }
+      {
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        TRGT_CAND(cur[m0 + n - 1], c.lp_match);
+        TRGT_CAND(cur[i0 + n - 1], c.lp_ins_exit);
+        if (n > 1) TRGT_CAND(cur[d0 + n - 2], c.lp_one);
+        cur[me] = best;
+        bpc[me] = (uint8_t)arg;
+      }
+    }
+    g.sync();
+    // (3) re, rs, then every ms
+    for (int b = g.lane(); b < nb; b += g.size()) {
+      const double em = 0.0;
+      double re_sc, rs_sc;
+      int re_arg, rs_arg;
+      {
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        for (int bb = 0; bb < nb; bb++) {
+          const int me = m.blk_ms[bb] + (bb == nb - 1 ? 2 : 3 * (int)m.blk_n[bb]);
+          TRGT_CAND(cur[me], c.lp_half);
+        }
+        re_sc = best; re_arg = arg;
+      }
+      {
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        TRGT_CAND(cur[0], c.lp_one);
+        TRGT_CAND(re_sc, c.lp_one);
+        rs_sc = best; rs_arg = arg;
+      }
+      {
+        const int ms = m.blk_ms[b];
+        const int me = ms + (b == nb - 1 ? 2 : 3 * (int)m.blk_n[b]);
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        TRGT_CAND(rs_sc, c.lp_one);
+        TRGT_CAND(cur[me], c.lp_half);
+        cur[ms] = best;
+        bpc[ms] = (uint8_t)arg;
+      }
+      if (b == 0) {
+        cur[S - 2] = re_sc; bpc[S - 2] = (uint8_t)re_arg;
+        cur[1] = rs_sc;     bpc[1] = (uint8_t)rs_arg;
+      }
+    }
+    g.sync();
+    double *t = prev; prev = cur; cur = t;
+  }
+}
+
+// predecessor of `st` through in-edge `e` (inverse of the enumeration order above)
+TRGT_HD int hmm_pred(const HmmModel &m, const HmmRole &r, int st, int e) {
+  switch (r.kind) {
+    case HR_END: return m.S - 2;
+    case HR_RE: return m.blk_ms[e] + (e == m.nb - 1 ? 2 : 3 * (int)m.blk_n[e]);
+    case HR_RS: return e == 0 ? 0 : m.S - 2;
+    case HR_MS: return e == 0 ? 1 : r.ms + 3 * r.n;
+    case HR_SKIP_MS: return e == 0 ? 1 : r.ms + 2;
+    case HR_MATCH:
+      if (r.i == 0) return r.ms;
+      return e == 0 ? st - 1 : (e == 1 ? r.ms : (e == 2 ? r.ms + r.n + r.i : r.ms + 2 * r.n + r.i - 1));
+    case HR_INS: return e == 0 ? st : r.ms + 1 + r.i;
+    case HR_DEL: return e == 0 ? r.ms + 1 + r.i : st - 1;
+    case HR_ME: return e == 0 ? r.ms + r.n : (e == 1 ? r.ms + 2 * r.n : r.ms + 3 * r.n - 1);
+    case HR_SKIP: return e == 0 ? r.ms : st;
+    case HR_SKIP_ME: return r.ms + 1;
+    default: return 0;
+  }
+}
+
+struct HmmAnnot {
+  double purity;
+  uint32_t n_spans;
+  int32_t status;  // 0 ok, <0 broken back-pointer chain
+};
+
+// One reverse walk from (end, L+1) to start.  mc[nb-1] must be zeroed by the caller when non-null.
+// When spans_out is non-null the collapsed spans are written in forward order given their total
+// count n_total from a previous counting walk.  max_motif_len: tr.rs:468 passes 6.
+// path_out (optional): receives the state path in REVERSE order (Hmm::label reversed), up to
+// path_cap entries; *path_len gets the full length.
+TRGT_HD HmmAnnot hmm_annotate(const HmmModel &m, const uint8_t *allele, int L, const uint8_t *bp,
+                              int max_motif_len, uint32_t *mc, HmmSpan *spans_out, uint32_t n_total,
+                              uint32_t *path_out, uint64_t path_cap, uint64_t *path_len) {
+  HmmAnnot out;
+  out.purity = 0.0; out.n_spans = 0; out.status = 0;
+  const int S = m.S;
+  uint64_t n_match = 0, n_mis = 0, n_ins = 0, n_del = 0, n_skip = 0;
+  int st = S - 1, col = L + 1, last = -1;
+  int copy_end = 0;
+  bool have_p = false;
+  uint32_t p_motif = 0, p_start = 0, p_end = 0, emitted = 0;
+  uint64_t plen = 0;
+  // every column visits each state at most once going backwards; anything longer is a cycle
+  const uint64_t max_steps = ((uint64_t)L + 2) * (uint64_t)S + 2;
+  uint64_t steps = 0;
+  while (st != 0) {
+    if (++steps > max_steps) { out.status = -1; break; }
+    if (path_out && plen < path_cap) path_out[plen] = (uint32_t)st;
+    plen++;
+    const HmmRole r = hmm_role(m, st);
+    bool emits = false;
+    switch (r.kind) {
+      case HR_END: emits = true; break;
+      case HR_ME: case HR_SKIP_ME: copy_end = col; break;
+      case HR_MS: case HR_SKIP_MS: {
+        const int copy_start = col;
+        n_del += (uint64_t)(last - st - 1);  // jump-in to match_i counts i deletions, events.rs:44-46
+        if (r.kind == HR_MS) {
+          bool keep = true;  // operations.rs:46-62
+          if (r.n <= max_motif_len) {
+            if (copy_end - copy_start < r.n) {
+              keep = false;
+            } else {
+              for (int i = 0; i < r.n; i++) {
+                const uint8_t expected = m.motif_bytes[m.blk_moff[r.b] + i];
+                const uint8_t observed = hmm_clean_base(allele[copy_start + i], (uint32_t)(copy_start + i));
+                if (expected != 'N' && observed != expected) keep = false;
+              }
+            }
+          }
+          if (keep) {  // a real motif copy: count it and fold it into the run being collapsed
+            if (mc) mc[r.b]++;
+            if (have_p && p_motif == (uint32_t)r.b && p_start == (uint32_t)copy_end) {
+              p_start = (uint32_t)copy_start;
+            } else {
+              if (have_p) {
+                if (spans_out) {
+                  HmmSpan s; s.motif_index = p_motif; s.start = p_start; s.end = p_end;
+                  spans_out[n_total - 1 - emitted] = s;
+                }
+                emitted++;
+              }
+              have_p = true;
+              p_motif = (uint32_t)r.b; p_start = (uint32_t)copy_start; p_end = (uint32_t)copy_end;
+            }
+          }
+        }
+        break;
+      }
+      case HR_MATCH: {
+        emits = true;
+        const uint8_t expected = m.motif_bytes[m.blk_moff[r.b] + r.i];
+        const uint8_t base = hmm_clean_base(allele[col - 1], (uint32_t)(col - 1));
+        if (base == expected || expected == 'N') n_match++; else n_mis++;
+        break;
+      }
+      case HR_INS: emits = true; n_ins++; break;
+      case HR_DEL: n_del++; break;
+      case HR_SKIP: emits = true; n_skip++; break;
+      default: break;  // rs, re
+    }
+    const int e = bp[(size_t)col * (size_t)S + (size_t)st];
+    if (e == TRGT_HMM_NONE) { out.status = -1; break; }
+    const int p = hmm_pred(m, r, st, e);
+    if (emits) col -= 1;
+    last = st;
+    st = p;
+  }
+  if (path_out && plen < path_cap) path_out[plen] = 0;
+  plen++;
+  if (path_len) *path_len = plen;
+  if (have_p) {
+    if (spans_out) {
+      HmmSpan s; s.motif_index = p_motif; s.start = p_start; s.end = p_end;
+      spans_out[n_total - 1 - emitted] = s;
+    }
+    emitted++;
+  }
+  out.n_spans = emitted;
+  // purity.rs:11-40
+  const double edit = (double)(n_del + n_ins + n_mis + n_skip);
+  const uint64_t ref_len = n_match + n_mis + n_del + n_skip;
+  const double max_dist = (double)(ref_len > (uint64_t)L ? ref_len : (uint64_t)L);
+  out.purity = (max_dist - edit) / max_dist;
+  return out;
+}
+
+// bytes of on-chip storage one group needs for a model with S states, nb blocks, `mbytes` motif bytes
+TRGT_HD size_t hmm_onchip_bytes(int S, int nb, int mbytes) {
+  size_t b = 0;
+  b += 2 * (size_t)S * sizeof(double);
+  b += 2 * (size_t)nb * sizeof(uint32_t);
+  b += 2 * (size_t)nb * sizeof(uint16_t);
+  b += (size_t)S * sizeof(uint16_t);
+  b += (size_t)mbytes;
+  return (b + 15) & ~(size_t)15;
+}
+
+}  // namespace trgt

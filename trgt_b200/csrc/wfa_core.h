@@ -1,0 +1,477 @@
+// wfa_core.h -- gap-affine wavefront alignment restructured for one cooperating group per pair.
+//
+// Replaces the alignment the reference performs through WFA2-lib (wfa2-sys 0.1.0, un-vendored):
+//   WFAligner::align_ends_free / align_end_to_end    src/wfaligner.rs:489-528
+//   count_matches :988, get_alignment_span :864, get_sam_cigar :932 (run-length SAM words)
+// as called by find_spans (src/trgt/genotype/span_locater.rs:7-30), utils::align
+// (src/utils/align.rs:14-28) and get_dist (src/trgt/genotype/genotype_cluster.rs:236-248).
+//
+// Semantics (recurrences, NULL handling, lowest-diagonal termination, back-trace priority
+// M > D-ext > D-open > I-ext > I-open) are those pinned by the reference's golden tests, see
+// SURVEY.md section 8(c).  The organisation is this repo's own:
+//
+//   pass 1  wfa_score_ring   forward wavefronts with only the last max(x,o+e)+1 M and e+1 I/D
+//                            wavefronts alive (a ring, on chip when it fits): finds the optimal
+//                            score s*, the terminating diagonal k* and offset.  No history.
+//   pass 2  wfa_trace        recomputes ONLY the dependency cone of (s*, k*):
+//                            |k - k*| <= (s* - s) / e at score s.  Every predecessor of a cone cell is
+//                            a cone cell, so the recomputed offsets equal the full computation's,
+//                            and the back-trace never leaves the cone.  For the wide-and-shallow
+//                            flank problem (T+1 start diagonals, s* ~ 6) this replaces the
+//                            reference's 12 B x (T+1) x (s*+1) history by a few hundred bytes.
+//
+// Lanes of the group stride over diagonals; all communication is through the wavefront arrays
+// followed by g.sync(), so the same code runs serially in the CPU unit tests.
+#pragma once
+#include <limits.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "coop.h"
+
+namespace trgt {
+
+#define TRGT_WFA_NULL (INT_MIN / 2)
+
+// per-item status (numerically WFA2's WF_STATUS_*, src/wfaligner.rs:132-159)
+#define TRGT_WFA_OK 0
+#define TRGT_WFA_MAX_STEPS (-100)
+#define TRGT_WFA_OOM (-200)
+
+struct WfaProb {
+  const uint8_t *p; int P;  // pattern (consumed by 'D')
+  const uint8_t *t; int T;  // text (consumed by 'I')
+  int x, oe, e;             // mismatch, gap_open + gap_extend, gap_extend
+  int pbf, pef, tbf, tef;   // ends-free allowances (all 0 = end-to-end)
+};
+
+struct WfaEnd {
+  int status;
+  int s;    // optimal cost (score = -s)
+  int k;    // terminating diagonal
+  int off;  // terminating offset (text position)
+};
+
+// One stored wavefront.  Arrays are indexed by k - base; [lo,hi] is what is stored, [tlo,thi]
+// the range the full computation would hold (they differ only in cone mode).
+struct WfaView {
+  int *m, *i, *d;
+  int base, lo, hi, tlo, thi;
+};
+
+TRGT_HD int wfa_imax(int a, int b) { return a > b ? a : b; }
+TRGT_HD int wfa_imin(int a, int b) { return a < b ? a : b; }
+
+TRGT_HD int wfa_at(const int *a, const WfaView &v, int k) {
+  return (a != nullptr && k >= v.lo && k <= v.hi) ? a[k - v.base] : TRGT_WFA_NULL;
+}
+
+TRGT_HD WfaView wfa_null_view() {
+  WfaView v;
+  v.m = v.i = v.d = nullptr;
+  v.base = 0; v.lo = 1; v.hi = 0; v.tlo = 1; v.thi = 0;
+  return v;
+}
+
+// match extension along diagonal k from text offset h
+TRGT_HD int wfa_extend(const WfaProb &pr, int k, int h) {
+  int v = h - k;
+  while (v < pr.P && h < pr.T && pr.p[v] == pr.t[h]) { v++; h++; }
+  return h;
+}
+
+// true diagonal range of wavefront s from its sources' true ranges; returns false if null
+TRGT_HD bool wfa_next_range(const WfaProb &pr, const WfaView &vx, const WfaView &vo, const WfaView &ve,
+                            int *lo_out, int *hi_out) {
+  int lo = INT_MAX, hi = INT_MIN;
+  if (vx.tlo <= vx.thi) { lo = wfa_imin(lo, vx.tlo); hi = wfa_imax(hi, vx.thi); }
+  if (vo.tlo <= vo.thi) { lo = wfa_imin(lo, vo.tlo); hi = wfa_imax(hi, vo.thi); }
+  if (ve.tlo <= ve.thi && ve.i != nullptr) { lo = wfa_imin(lo, ve.tlo); hi = wfa_imax(hi, ve.thi); }
+  if (lo > hi) return false;
+  lo -= 1; hi += 1;
+  lo = wfa_imax(lo, -pr.P);
+  hi = wfa_imin(hi, pr.T);
+  if (lo > hi) return false;
+  *lo_out = lo; *hi_out = hi;
+  return true;
+}
+
+// cells dst.lo..dst.hi of one wavefront from its three source wavefronts, then match extension
+template <class G>
+TRGT_HD void wfa_compute(const G &g, const WfaProb &pr, const WfaView &vx, const WfaView &vo,
+                         const WfaView &ve, const WfaView &dst) {
+  for (int k = dst.lo + g.lane(); k <= dst.hi; k += g.size()) {
+    const int i1 = wfa_imax(wfa_at(vo.m, vo, k - 1), wfa_at(ve.i, ve, k - 1)) + 1;
+    const int d1 = wfa_imax(wfa_at(vo.m, vo, k + 1), wfa_at(ve.d, ve, k + 1));
+    const int mm = wfa_at(vx.m, vx, k) + 1;
+    int mx = wfa_imax(mm, wfa_imax(i1, d1));
+    const int h = mx, v = mx - k;
+    if (mx < 0 || h > pr.T || v > pr.P || v < 0) mx = TRGT_WFA_NULL;
+    else mx = wfa_extend(pr, k, mx);
+    dst.i[k - dst.base] = i1;
+    dst.d[k - dst.base] = d1;
+    dst.m[k - dst.base] = mx;
+  }
+}
+
+// score-0 wavefront: M[k] = max(k, 0) on [-pbf, tbf], extended
+template <class G>
+TRGT_HD void wfa_init(const G &g, const WfaProb &pr, const WfaView &dst) {
+  for (int k = dst.lo + g.lane(); k <= dst.hi; k += g.size()) {
+    const int h = k >= 0 ? k : 0;
+    dst.m[k - dst.base] = wfa_extend(pr, k, h);
+  }
+}
+
+// lowest diagonal of `w` that satisfies the end condition, INT_MAX if none
+template <class G>
+TRGT_HD int wfa_terminated(const G &g, const WfaProb &pr, const WfaView &w) {
+  int best = INT_MAX;
+  for (int k = w.lo + g.lane(); k <= w.hi; k += g.size()) {
+    const int h = w.m[k - w.base];
+    if (h < 0) continue;
+    const int v = h - k;
+    if (v < 0 || v > pr.P || h > pr.T) continue;
+    if ((h >= pr.T && pr.P - v <= pr.pef) || (v >= pr.P && pr.T - h <= pr.tef)) {
+      best = k;
+      break;
+    }
+  }
+  return g.min_i(best);
+}
+
+// ---------------------------------------------------------------- pass 1: ring ----------
+
+TRGT_HD int wfa_ring_depth_m(const WfaProb &pr) { return wfa_imax(pr.x, pr.oe) + 1; }
+TRGT_HD int wfa_ring_depth_g(const WfaProb &pr) { return pr.e + 1; }
+// stride of one ring slot: every diagonal a valid cell can live on
+TRGT_HD int wfa_ring_stride(const WfaProb &pr) { return pr.P + pr.T + 1; }
+TRGT_HD size_t wfa_ring_ints(const WfaProb &pr) {
+  const size_t dm = (size_t)wfa_ring_depth_m(pr), dg = (size_t)wfa_ring_depth_g(pr);
+  return 2 * dm + (dm + 2 * dg) * (size_t)wfa_ring_stride(pr);
+}
+// generous bound on the optimal cost: align min(P,T) columns as mismatches plus one gap
+TRGT_HD int wfa_score_cap(const WfaProb &pr) {
+  const long long c = (long long)pr.x * wfa_imin(pr.P, pr.T) + 2LL * pr.oe + (long long)pr.e * (pr.P + pr.T) + 8;
+  return c > (long long)(INT_MAX / 4) ? INT_MAX / 4 : (int)c;
+}
+
+TRGT_HD WfaView wfa_ring_view(const WfaProb &pr, int *ring, int s) {
+  if (s < 0) return wfa_null_view();
+  const int dm = wfa_ring_depth_m(pr), dg = wfa_ring_depth_g(pr), W = wfa_ring_stride(pr);
+  int *meta = ring;
+  int *mbase = ring + 2 * dm;
+  int *ibase = mbase + (size_t)dm * W;
+  int *dbase = ibase + (size_t)dg * W;
+  WfaView v;
+  v.base = -pr.P;
+  v.tlo = v.lo = meta[2 * (s % dm)];
+  v.thi = v.hi = meta[2 * (s % dm) + 1];
+  v.m = mbase + (size_t)(s % dm) * W;
+  if (s >= 1) {
+    v.i = ibase + (size_t)(s % dg) * W;
+    v.d = dbase + (size_t)(s % dg) * W;
+  } else {
+    v.i = v.d = nullptr;
+  }
+  return v;
+}
+
+// Forward pass without history.  `ring` holds wfa_ring_ints(pr) ints (shared or global memory).
+template <class G>
+TRGT_HD WfaEnd wfa_score_ring(const G &g, const WfaProb &pr, int *ring, int s_cap) {
+  WfaEnd out;
+  out.status = TRGT_WFA_OK; out.s = 0; out.k = 0; out.off = 0;
+  const int dm = wfa_ring_depth_m(pr);
+  int *meta = ring;
+  if (g.lane() == 0) {
+    meta[0] = -pr.pbf;
+    meta[1] = pr.tbf;
+  }
+  g.sync();
+  {
+    WfaView w0 = wfa_ring_view(pr, ring, 0);
+    wfa_init(g, pr, w0);
+  }
+  g.sync();
+  int s = 0;
+  for (;;) {
+    WfaView cur = wfa_ring_view(pr, ring, s);
+    if (cur.lo <= cur.hi) {
+      const int kmin = wfa_terminated(g, pr, cur);
+      if (kmin != INT_MAX) {
+        out.s = s; out.k = kmin; out.off = cur.m[kmin - cur.base];
+        return out;
+      }
+    }
+    s++;
+    if (s > s_cap) { out.status = TRGT_WFA_MAX_STEPS; out.s = s; return out; }
+    const WfaView vx = wfa_ring_view(pr, ring, s - pr.x);
+    const WfaView vo = wfa_ring_view(pr, ring, s - pr.oe);
+    const WfaView ve = wfa_ring_view(pr, ring, s - pr.e);
+    int lo, hi;
+    const bool live = wfa_next_range(pr, vx, vo, ve, &lo, &hi);
+    g.sync();  // everyone has read the slot that is about to be recycled
+    if (g.lane() == 0) {
+      meta[2 * (s % dm)] = live ? lo : 1;
+      meta[2 * (s % dm) + 1] = live ? hi : 0;
+    }
+    if (live) {
+      WfaView dst = wfa_ring_view(pr, ring, s);
+      dst.lo = dst.tlo = lo; dst.hi = dst.thi = hi;
+      wfa_compute(g, pr, vx, vo, ve, dst);
+    }
+    g.sync();
+  }
+}
+
+// ---------------------------------------------------------------- pass 2: cone + back-trace ----
+
+#define TRGT_WFA_META 6  // ints per score in the history header: tlo, thi, lo, hi, data offset, unused
+
+TRGT_HD int wfa_cone_radius(const WfaProb &pr, int s_end, int s) { return (s_end - s) / pr.e; }
+
+// ints of workspace wfa_trace needs (upper bound: assumes every cone row is as wide as allowed)
+TRGT_HD size_t wfa_trace_ints(const WfaProb &pr, int s_end) {
+  size_t n = (size_t)TRGT_WFA_META * ((size_t)s_end + 1);
+  const long long wmax = (long long)pr.P + pr.T + 1;
+  for (int s = 0; s <= s_end; s++) {
+    long long w = 2LL * wfa_cone_radius(pr, s_end, s) + 1;
+    if (w > wmax) w = wmax;
+    n += (size_t)w * (s == 0 ? 1 : 3);
+  }
+  return n;
+}
+
+TRGT_HD WfaView wfa_hist_view(int *ws, int s) {
+  if (s < 0) return wfa_null_view();
+  const int *meta = ws + (size_t)TRGT_WFA_META * s;
+  WfaView v;
+  v.tlo = meta[0]; v.thi = meta[1]; v.lo = meta[2]; v.hi = meta[3];
+  v.base = v.lo;
+  const int w = v.hi >= v.lo ? v.hi - v.lo + 1 : 0;
+  int *data = ws + (size_t)(unsigned)meta[4] + (((size_t)(unsigned)meta[5]) << 32);
+  v.m = data;
+  if (s >= 1 && w > 0) { v.i = data + w; v.d = data + 2 * (size_t)w; }
+  else if (s >= 1) { v.i = data; v.d = data; }  // present but empty: keeps "has I/D" for range tracking
+  else { v.i = v.d = nullptr; }
+  return v;
+}
+
+// Recompute the dependency cone of (s_end, k_end) with full history in ws.
+// Returns 0, or TRGT_WFA_OOM if cap_ints is too small.
+template <class G>
+TRGT_HD int wfa_trace_forward(const G &g, const WfaProb &pr, int s_end, int k_end, int *ws, size_t cap_ints) {
+  size_t top = (size_t)TRGT_WFA_META * ((size_t)s_end + 1);
+  if (top > cap_ints) return TRGT_WFA_OOM;
+  for (int s = 0; s <= s_end; s++) {
+    int tlo, thi;
+    bool live;
+    WfaView vx = wfa_null_view(), vo = wfa_null_view(), ve = wfa_null_view();
+    if (s == 0) {
+      tlo = -pr.pbf; thi = pr.tbf; live = true;
+    } else {
+      vx = wfa_hist_view(ws, s - pr.x);
+      vo = wfa_hist_view(ws, s - pr.oe);
+      ve = wfa_hist_view(ws, s - pr.e);
+      live = wfa_next_range(pr, vx, vo, ve, &tlo, &thi);
+      if (!live) { tlo = 1; thi = 0; }
+    }
+    const int R = wfa_cone_radius(pr, s_end, s);
+    int lo = live ? wfa_imax(tlo, k_end - R) : 1;
+    int hi = live ? wfa_imin(thi, k_end + R) : 0;
+    if (lo > hi) { lo = 1; hi = 0; }
+    const size_t w = hi >= lo ? (size_t)(hi - lo + 1) : 0;
+    const size_t need = w * (s == 0 ? 1 : 3);
+    if (top + need > cap_ints) return TRGT_WFA_OOM;
+    g.sync();
+    if (g.lane() == 0) {
+      int *meta = ws + (size_t)TRGT_WFA_META * s;
+      meta[0] = tlo; meta[1] = thi; meta[2] = lo; meta[3] = hi;
+      meta[4] = (int)(unsigned)(top & 0xffffffffu);
+      meta[5] = (int)(unsigned)(top >> 32);
+    }
+    g.sync();
+    if (w > 0) {
+      WfaView dst = wfa_hist_view(ws, s);
+      if (s == 0) wfa_init(g, pr, dst);
+      else wfa_compute(g, pr, vx, vo, ve, dst);
+    }
+    top += need;
+  }
+  g.sync();
+  return 0;
+}
+
+// Back-trace from (s_end, k_end) through the history in ws; ops are handed to the sink from the
+// LAST operation to the first.  One lane.
+template <class Sink>
+TRGT_HD void wfa_backtrace(const WfaProb &pr, int s_end, int k_end, int off_end, int *ws, Sink &sink) {
+  enum { T_I1O = 1, T_I1E = 2, T_D1O = 5, T_D1E = 6, T_M = 9 };
+  enum { C_M = 0, C_I = 1, C_D = 2 };
+  int k = k_end, off = off_end;
+  int v = off - k, h = off;
+  sink.op('I', pr.T - h);  // free text tail
+  sink.op('D', pr.P - v);  // unaligned pattern tail
+  int mt = C_M, sc = s_end;
+#define TRGT_PG(o, tag) ((o) < 0 ? (long long)TRGT_WFA_NULL : ((((long long)(o)) << 4) | (tag)))
+  while (v > 0 && h > 0 && sc > 0) {
+    const int sx = sc - pr.x, so = sc - pr.oe, se = sc - pr.e;
+    const WfaView vx = wfa_hist_view(ws, sx), vo = wfa_hist_view(ws, so), ve = wfa_hist_view(ws, se);
+    const long long c_m = TRGT_PG(wfa_at(vx.m, vx, k) + 1, T_M);
+    const long long c_io = TRGT_PG(wfa_at(vo.m, vo, k - 1) + 1, T_I1O);
+    const long long c_ie = TRGT_PG(wfa_at(ve.i, ve, k - 1) + 1, T_I1E);
+    const long long c_do = TRGT_PG(wfa_at(vo.m, vo, k + 1), T_D1O);
+    const long long c_de = TRGT_PG(wfa_at(ve.d, ve, k + 1), T_D1E);
+    long long mx;
+    if (mt == C_M) {
+      mx = c_m;
+      if (c_io > mx) mx = c_io;
+      if (c_ie > mx) mx = c_ie;
+      if (c_do > mx) mx = c_do;
+      if (c_de > mx) mx = c_de;
+    } else if (mt == C_I) {
+      mx = c_io > c_ie ? c_io : c_ie;
+    } else {
+      mx = c_do > c_de ? c_do : c_de;
+    }
+    if (mx < 0) break;
+    if (mt == C_M) {
+      const int mo = (int)(mx >> 4);
+      sink.op('M', off - mo);
+      off = mo;
+      v = off - k; h = off;
+      if (v <= 0 || h <= 0) break;
+    }
+    switch ((int)(mx & 15)) {
+      case T_M:   sc = sx; mt = C_M; sink.op('X', 1); off -= 1; break;
+      case T_I1O: sc = so; mt = C_M; sink.op('I', 1); k -= 1; off -= 1; break;
+      case T_I1E: sc = se; mt = C_I; sink.op('I', 1); k -= 1; off -= 1; break;
+      case T_D1O: sc = so; mt = C_M; sink.op('D', 1); k += 1; break;
+      case T_D1E: sc = se; mt = C_D; sink.op('D', 1); k += 1; break;
+      default: break;
+    }
+    v = off - k; h = off;
+  }
+#undef TRGT_PG
+  if (mt == C_M && v > 0 && h > 0) {
+    const int n = wfa_imin(v, h);
+    sink.op('M', n);
+    v -= n; h -= n;
+  }
+  sink.op('D', v);
+  sink.op('I', h);
+}
+
+// count_matches (wfaligner.rs:988) and the text span of get_alignment_span (:864-908)
+struct WfaFlankSink {
+  int T;
+  int matches, trailing_i, i_run, seen, ye;
+  TRGT_HD explicit WfaFlankSink(int T_) : T(T_), matches(0), trailing_i(0), i_run(0), seen(0), ye(0) {}
+  TRGT_HD void op(char c, int n) {
+    if (n <= 0) return;
+    if (c == 'M' || c == 'X') {
+      if (c == 'M') matches += n;
+      if (!seen) { seen = 1; ye = T - trailing_i; }
+      i_run = 0;
+    } else if (c == 'I') {
+      if (!seen) trailing_i += n; else i_run += n;
+    }
+  }
+  TRGT_HD int ystart() const { return seen ? i_run : 0; }
+  TRGT_HD int yend() const { return seen ? ye : 0; }
+};
+
+// run-length SAM words (len << 4 | op) with '=' 7, 'X' 8, 'I' 1, 'D' 2 (get_sam_cigar(true),
+// wfaligner.rs:932-959); collected last-to-first, then flipped by finish()
+struct WfaCigarSink {
+  uint32_t *out;
+  uint32_t cap, n;
+  uint32_t cur_code, cur_len;
+  int overflow;
+  TRGT_HD WfaCigarSink(uint32_t *o, uint32_t c) : out(o), cap(c), n(0), cur_code(0xF), cur_len(0), overflow(0) {}
+  TRGT_HD void flush() {
+    if (cur_len == 0) return;
+    if (n < cap) out[n] = (cur_len << 4) | cur_code; else overflow = 1;
+    n++;
+    cur_len = 0;
+  }
+  TRGT_HD void op(char c, int cnt) {
+    if (cnt <= 0) return;
+    const uint32_t code = c == 'M' ? 7u : (c == 'X' ? 8u : (c == 'I' ? 1u : 2u));
+    if (code != cur_code) { flush(); cur_code = code; }
+    cur_len += (uint32_t)cnt;
+  }
+  TRGT_HD uint32_t finish() {
+    flush();
+    if (!overflow)
+      for (uint32_t a = 0, b = n; a + 1 < b; a++) { b--; const uint32_t t = out[a]; out[a] = out[b]; out[b] = t; }
+    return n;
+  }
+};
+
+// ---------------------------------------------------------------- exact flank scan ----------
+
+// first start s with t[s..s+P) == piece, or -1     span_locater.rs:10-12
+template <class G>
+TRGT_HD int flank_scan(const G &g, const uint8_t *piece, int P, const uint8_t *t, int T) {
+  const int n_starts = T - P + 1;
+  for (int base = 0; base < n_starts; base += g.size()) {
+    const int s = base + g.lane();
+    int hit = INT_MAX;
+    if (s < n_starts) {
+      int j = 0;
+      while (j < P && t[s + j] == piece[j]) j++;
+      if (j == P) hit = s;
+    }
+    hit = g.min_i(hit);
+    if (hit != INT_MAX) return hit;
+  }
+  return -1;
+}
+
+// ---------------------------------------------------------------- unit-cost edit distance ------
+
+// Levenshtein distance, one lane per pair: bit-vector DP (Myers 1999, global variant of Hyyro 2003)
+// over the shorter sequence, which get_dist's MAX_OPS guard (genotype_cluster.rs:237-243) bounds
+// by 100 symbols, so one 128-bit word holds the column.  Score-only, so any exact algorithm
+// returns what the reference's WFA edit aligner returns.
+TRGT_HD int edit_distance_128(const uint8_t *a, int la, const uint8_t *b, int lb) {
+  typedef unsigned __int128 u128;
+  const uint8_t *pat = a; int m = la;
+  const uint8_t *txt = b; int n = lb;
+  if (m > n) { pat = b; m = lb; txt = a; n = la; }
+  if (m == 0) return n;
+  u128 peqA = 0, peqC = 0, peqG = 0, peqT = 0;
+  for (int i = 0; i < m; i++) {
+    const u128 bit = (u128)1 << i;
+    const uint8_t c = pat[i];
+    if (c == 'A') peqA |= bit; else if (c == 'C') peqC |= bit; else if (c == 'G') peqG |= bit; else if (c == 'T') peqT |= bit;
+  }
+  const u128 ones = (m == 128) ? ~(u128)0 : (((u128)1 << m) - 1);
+  const u128 top = (u128)1 << (m - 1);
+  u128 Pv = ones, Mv = 0;
+  int score = m;
+  for (int j = 0; j < n; j++) {
+    const uint8_t c = txt[j];
+    u128 Eq;
+    if (c == 'A') Eq = peqA; else if (c == 'C') Eq = peqC; else if (c == 'G') Eq = peqG; else if (c == 'T') Eq = peqT;
+    else {
+      Eq = 0;
+      for (int i = 0; i < m; i++) if (pat[i] == c) Eq |= (u128)1 << i;
+    }
+    const u128 Xv = Eq | Mv;
+    const u128 Xh = ((((Eq & Pv) + Pv) ^ Pv) | Eq) & ones;
+    u128 Ph = (Mv | ~(Xh | Pv)) & ones;
+    u128 Mh = Pv & Xh;
+    if (Ph & top) score++;
+    else if (Mh & top) score--;
+    Ph = ((Ph << 1) | 1) & ones;
+    Mh = (Mh << 1) & ones;
+    Pv = (Mh | ~(Xv | Ph)) & ones;
+    Mv = Ph & Xv;
+  }
+  return score;
+}
+
+}  // namespace trgt
