@@ -86,6 +86,11 @@ const char *trgt_last_create_error(void);
 /* cudaStream_t the engine launches on (for external CUDA-event timing) */
 void *trgt_engine_stream(trgt_engine_t *eng);
 int32_t trgt_engine_sm_count(const trgt_engine_t *eng);
+/* block until everything queued on the engine stream has finished */
+int32_t trgt_engine_sync(trgt_engine_t *eng);
+/* cap (bytes) on the device workspace one wave of work may use (HMM back-pointers, WFA trace
+ * history); larger batches are processed in several waves.  Default 24 GiB. */
+void trgt_engine_set_workspace_budget(trgt_engine_t *eng, size_t bytes);
 
 /* pinned host memory for the caller's packing buffers (DMA-direct H2D/D2H) */
 void *trgt_host_alloc(size_t bytes);
@@ -173,10 +178,18 @@ int32_t trgt_flank_upload(trgt_engine_t *eng, const trgt_seqs_t *left_pieces,
                           const uint32_t *locus_read_offsets, uint32_t n_loci,
                           trgt_scoring_t scoring, double min_flank_id_frac,
                           trgt_flank_batch_t **out);
-int32_t trgt_flank_run(trgt_engine_t *eng, trgt_flank_batch_t *batch);            /* async on the engine stream */
+/* the *_run calls enqueue on the engine stream; they synchronise internally where a later launch
+ * is sized by an earlier one (work-list length, workspace), but results are only guaranteed in
+ * place after the matching *_download (or trgt_engine_sync) */
+int32_t trgt_flank_run(trgt_engine_t *eng, trgt_flank_batch_t *batch);
 int32_t trgt_flank_download(trgt_engine_t *eng, trgt_flank_batch_t *batch,
                             trgt_span_t *spans_out, trgt_flank_hit_t *hits_out);   /* syncs */
 void trgt_flank_free(trgt_engine_t *eng, trgt_flank_batch_t *batch);
+/* device pointers of a resident flank batch (reads, CSR offsets, spans, hits) for device-side
+ * consumers; n_wfa = (read, flank) pairs the last run sent to the WFA fallback */
+int32_t trgt_flank_device_views(trgt_flank_batch_t *batch, const void **d_reads, const void **d_read_off,
+                                const void **d_spans, const void **d_hits, uint32_t *n_reads,
+                                uint32_t *n_wfa);
 
 typedef struct trgt_align_batch trgt_align_batch_t;
 int32_t trgt_align_upload(trgt_engine_t *eng, const trgt_seqs_t *backbones,

@@ -2,7 +2,9 @@
 
 Run in the build container (where /root/reference exists):
     python tests/golden/extract_reference_vectors.py
-Writes tests/golden/wfa_long_vectors.json.  The expected values come from the asserts of
+Writes tests/golden/wfa_long_vectors.json and tests/golden/pathogenic_motifs.json (the ID and
+motif list of every locus of repeats/pathogenic_repeats.hg38.bed; workload shape for BASELINE
+config 2).  The expected values come from the asserts of
 /root/reference/src/wfaligner.rs (test_aligner_span_2 :1246-1261, test_invalid_sequence :1438-1454).
 The GPU box has no /root/reference; tests only read the committed JSON.
 """
@@ -50,6 +52,17 @@ def main():
     with open(OUT, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", OUT, {k: (len(v["pattern"]), len(v["text"])) for k, v in out.items()})
+    loci = []
+    for line in open("/root/reference/repeats/pathogenic_repeats.hg38.bed"):
+        f = line.rstrip("\n").split("\t")
+        if len(f) < 4:
+            continue
+        info = dict(kv.split("=", 1) for kv in f[3].split(";"))
+        loci.append({"id": info["ID"], "ref_len": int(f[2]) - int(f[1]), "motifs": info["MOTIFS"].split(",")})
+    out2 = os.path.join(os.path.dirname(OUT), "pathogenic_motifs.json")
+    with open(out2, "w") as fh:
+        json.dump({"source": "repeats/pathogenic_repeats.hg38.bed", "loci": loci}, fh, indent=0)
+    print("wrote", out2, len(loci), "loci")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,201 @@
+"""CPU checks of the kernel cores (trgt_b200/csrc/{hmm,wfa}_core.h) in their one-lane serial
+instantiation against the oracle.  The same templates are what the CUDA kernels instantiate with
+warp / CTA groups; the GPU parity tests proper are in test_engine_gpu.py."""
+import ctypes as C
+import json
+import math
+import os
+import random
+
+import pytest
+
+from tests.emul import build as emul_build
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+class _Span(C.Structure):
+    _fields_ = [("m", C.c_uint32), ("s", C.c_uint32), ("e", C.c_uint32)]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    L = C.CDLL(emul_build.build())
+    L.emu_hmm_annotate.restype = C.c_long
+    return L
+
+
+def emu_hmm(L, motifs, allele):
+    data = b"".join(motifs)
+    offs = [0]
+    for m in motifs:
+        offs.append(offs[-1] + len(m))
+    moff = (C.c_uint64 * len(offs))(*offs)
+    mc = (C.c_uint32 * (len(motifs) + 1))()
+    cap = len(allele) + 2
+    spans = (_Span * cap)()
+    pur = C.c_double()
+    pcap = (len(allele) + 2) * 64
+    path = (C.c_uint32 * pcap)()
+    plen, S = C.c_uint64(), C.c_int()
+    n = L.emu_hmm_annotate(data, moff, len(motifs), allele, len(allele), mc, spans, cap, C.byref(pur), path,
+                           C.c_uint64(pcap), C.byref(plen), C.byref(S))
+    assert n >= 0, n
+    return (list(mc[:len(motifs)]), [(spans[i].m, spans[i].s, spans[i].e) for i in range(n)], pur.value,
+            list(path[:plen.value]), S.value)
+
+
+def emu_wfa(L, p, t, x, o, e, ef=None):
+    out = (C.c_int * 9)()
+    cap = 2 * (len(p) + len(t)) + 16
+    words = (C.c_uint32 * cap)()
+    pbf, pef, tbf, tef = ef if ef else (0, 0, 0, 0)
+    rc = L.emu_wfa_align(p, len(p), t, len(t), x, o, e, pbf, pef, tbf, tef, out, words, cap)
+    return rc, list(out), list(words[:out[7]])
+
+
+def rnd(rng, n, alpha="ACGT"):
+    return "".join(rng.choice(alpha) for _ in range(n)).encode()
+
+
+def mutate(rng, s, rate):
+    o = []
+    for c in s:
+        r = rng.random()
+        if r < rate / 3:
+            o.append(rng.choice(b"ACGT"))
+        elif r < 2 * rate / 3:
+            pass
+        elif r < rate:
+            o.append(c)
+            o.append(rng.choice(b"ACGT"))
+        else:
+            o.append(c)
+    return bytes(o)
+
+
+def noisy_repeat(rng, motifs, max_units=12):
+    parts = []
+    for _ in range(rng.randint(0, max_units)):
+        m = rng.choice(motifs).replace(b"N", rng.choice([b"A", b"C", b"G", b"T"]))
+        r = rng.random()
+        if r < 0.7:
+            parts.append(m)
+        elif r < 0.8:
+            parts.append(rnd(rng, rng.randint(1, 5)))
+        elif r < 0.9:
+            parts.append(m[:-1])
+        else:
+            parts.append(m + rnd(rng, 1))
+    return b"".join(parts)
+
+
+def test_hmm_core_random(emul, oracle):
+    rng = random.Random(1)
+    for _ in range(1200):
+        k = rng.choice([1, 1, 1, 2, 3, 5])
+        motifs = [rnd(rng, rng.choice([1, 2, 2, 3, 4, 5, 6, 7, 12]), "ACGTN" if rng.random() < 0.2 else "ACGT")
+                  for _ in range(k)]
+        allele = noisy_repeat(rng, motifs)
+        if rng.random() < 0.1:
+            allele = allele[:3] + b"N" + allele[3:] + b"X"
+        h = oracle.Hmm([oracle.replace_invalid_bases(m, b"ATCGN") for m in motifs])
+        exp_mc, exp_sp, exp_pur = h.annotate(allele)
+        exp_path = h.label(oracle.replace_invalid_bases(allele, b"ATCG")) if allele else []
+        mc, sp, pur, path, S = emu_hmm(emul, motifs, allele)
+        assert S == h.num_states
+        assert path == exp_path
+        assert mc == exp_mc and sp == exp_sp
+        assert (math.isnan(pur) and math.isnan(exp_pur)) or pur == exp_pur
+
+
+def test_hmm_core_reference_goldens(emul):
+    # src/hmm/builder.rs:208-217 and :243-250 (spans after remove_imperfect_motifs are what annotate collapses)
+    mc, sp, pur, _, _ = emu_hmm(emul, [b"CAG", b"A"], b"CAGCAGCAGCAGAAAAA")
+    assert sp == [(0, 0, 12), (1, 12, 17)] and mc == [4, 5] and pur == 1.0
+    # docs/tutorial.md:44: MC=11, MS=0(0-33), AP=1.000000
+    mc, sp, pur, _, _ = emu_hmm(emul, [b"CAG"], b"CAG" * 11)
+    assert mc == [11] and sp == [(0, 0, 33)] and pur == 1.0
+
+
+def test_wfa_core_random(emul, oracle):
+    rng = random.Random(7)
+    for _ in range(1500):
+        x, o, e = rng.choice([(2, 5, 1), (1, 0, 1), (4, 6, 2), (6, 4, 2), (1, 5, 1), (3, 1, 3)])
+        mode = rng.random()
+        if mode < 0.5:  # the production flank shape: pattern global, text free at both ends
+            p = rnd(rng, rng.randint(1, 40))
+            t = rnd(rng, rng.randint(0, 60)) + mutate(rng, p, rng.choice([0, 0.05, 0.2, 0.6])) + rnd(rng, rng.randint(0, 60))
+            if rng.random() < 0.1:
+                t = t[:rng.randint(0, len(t))]
+            t = t or b"A"
+            ef = (0, 0, len(t), len(t))
+        elif mode < 0.8:  # end-to-end
+            p = rnd(rng, rng.randint(1, 50))
+            t = mutate(rng, p, rng.choice([0, 0.05, 0.2, 0.5])) if rng.random() < 0.8 else rnd(rng, rng.randint(1, 50))
+            t = t or b"C"
+            ef = None
+        else:  # arbitrary ends-free allowances
+            p, t = rnd(rng, rng.randint(1, 30)), rnd(rng, rng.randint(1, 30))
+            ef = (rng.randint(0, len(p)), rng.randint(0, len(p)), rng.randint(0, len(t)), rng.randint(0, len(t)))
+        a = oracle.wfa_align(p, t, oracle.AFFINE, x, o, e, ends_free=ef)
+        rc, out, words = emu_wfa(emul, p, t, x, o, e, ef)
+        assert rc == 0
+        assert (out[1], out[2], out[3]) == (a.score, a.end_k, a.end_offset)
+        assert out[4] == a.count_matches()
+        if ef is not None:
+            assert (out[5], out[6]) == a.alignment_span()[1]
+        assert words == a.sam_cigar(True)
+
+
+def test_wfa_core_reference_goldens(emul):
+    P = b"AGCTAGTGTCAATGGCTACTTTTCAGGTCCT"       # src/wfaligner.rs:1133
+    T = b"AACTAAGTGTCGGTGGCTACTATATATCAGGTCCT"   # src/wfaligner.rs:1134
+
+    def cig(words):
+        return "".join(f"{w >> 4}{'MIDNSHP=X'[w & 15]}" for w in words).replace("=", "M")
+
+    rc, out, words = emu_wfa(emul, P, T, 6, 4, 2)            # wfaligner.rs:1185-1198
+    assert rc == 0 and out[1] == -40 and cig(words) == "1M1X3M1I5M2X8M3I1M1X9M"
+    # wfaligner.rs:1795-1828: text free at both ends, the production flank call shape
+    p = b"ACGTACGTACGTACG"
+    t = b"T" * 10 + p + b"T" * 10
+    rc, out, words = emu_wfa(emul, p, t, 2, 5, 1, (0, 0, len(t), len(t)))
+    assert rc == 0 and out[1] == 0 and cig(words) == "10I15M10I" and (out[4], out[5], out[6]) == (15, 10, 25)
+
+
+def test_flank_scan_core(emul):
+    rng = random.Random(3)
+    for _ in range(1500):
+        P = rng.randint(1, 8)
+        piece = rnd(rng, P) if rng.random() < 0.5 else b"A" * P
+        t = rnd(rng, rng.randint(0, 70), "AC") if rng.random() < 0.5 else rnd(rng, rng.randint(0, 70))
+        if rng.random() < 0.5 and len(t) >= P:
+            i = rng.randint(0, len(t) - P)
+            t = t[:i] + piece + t[i + P:]
+        assert emul.emu_flank_scan(piece, P, t, len(t)) == t.find(piece)
+
+
+def test_edit_distance_core(emul, oracle):
+    rng = random.Random(5)
+
+    def lev(a, b):
+        prev = list(range(len(b) + 1))
+        for i, ca in enumerate(a, 1):
+            cur = [i]
+            for j, cb in enumerate(b, 1):
+                cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+            prev = cur
+        return prev[-1]
+
+    for _ in range(800):
+        a = rnd(rng, rng.randint(0, 128), "ACGTN")
+        b = mutate(rng, a, rng.choice([0, 0.1, 0.5])) if rng.random() < 0.7 else rnd(rng, rng.randint(0, 200))
+        if rng.random() < 0.1:
+            b += b"XQ"
+        if min(len(a), len(b)) > 128:
+            continue
+        got = emul.emu_edit_distance(a, len(a), b, len(b))
+        assert got == lev(a, b)
+        if a and b and len(a) * len(b) <= 10000:
+            assert math.sqrt(got) == oracle.get_dist(a, b)

@@ -1,0 +1,242 @@
+"""GPU parity tests: the CUDA path (libtrgt_b200.so through its C ABI) against the oracle on the same
+seeded inputs.  Integer / index results must be bit-exact; AP (purity) is an integer ratio evaluated in
+f64 on both sides and must be identical."""
+import json
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tests.test_cores_serial import mutate, noisy_repeat, rnd
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ------------------------------------------------------------------ phase C: HMM ---------
+
+def _check_annotations(oracle, loci, got, paths=None):
+    k = 0
+    for li, (motifs, alleles) in enumerate(loci):
+        h = oracle.Hmm([oracle.replace_invalid_bases(m, b"ATCGN") for m in motifs])
+        for ai, allele in enumerate(alleles):
+            exp_mc, exp_sp, exp_pur = h.annotate(allele)
+            ann = got[li][ai]
+            assert ann.motif_counts == exp_mc, (motifs, allele)
+            assert (ann.labels or []) == exp_sp, (motifs, allele)
+            assert (math.isnan(ann.purity) and math.isnan(exp_pur)) or ann.purity == exp_pur, (motifs, allele)
+            if paths is not None:
+                exp_path = h.label(oracle.replace_invalid_bases(allele, b"ATCG")) if allele else []
+                assert paths[k] == exp_path, (motifs, allele)
+            k += 1
+
+
+def test_hmm_reference_goldens(engine, oracle):
+    # src/hmm/builder.rs:208-217, docs/tutorial.md:44, src/hmm/purity.rs:48-96
+    loci = [
+        ([b"CAG", b"A"], [b"CAGCAGCAGCAGAAAAA"]),
+        ([b"CAG"], [b"CAG" * 11, b""]),
+        ([b"CAG", b"CCG"], [b"CAGCAGCAGCCGCCGCCG", b"CAGCAGCATCAGCCGCCG"]),
+        ([b"GCN"], [b"GCAGCGGCTGCC"]),
+    ]
+    got = engine.label_with_hmm(loci)
+    assert got[0][0].labels == [(0, 0, 12), (1, 12, 17)] and got[0][0].motif_counts == [4, 5]
+    assert got[1][0].motif_counts == [11] and got[1][0].labels == [(0, 0, 33)] and got[1][0].purity == 1.0
+    assert got[1][1].labels is None and math.isnan(got[1][1].purity) and got[1][1].motif_counts == [0]
+    _check_annotations(oracle, loci, got)
+
+
+def test_hmm_random_parity_with_paths(engine, oracle):
+    from trgt_b200 import PackedSeqs
+    rng = random.Random(11)
+    loci = []
+    for _ in range(400):
+        k = rng.choice([1, 1, 1, 2, 3, 5])
+        motifs = [rnd(rng, rng.choice([1, 2, 2, 3, 4, 5, 6, 7, 12]), "ACGTN" if rng.random() < 0.2 else "ACGT")
+                  for _ in range(k)]
+        alleles = []
+        for _ in range(rng.randint(1, 3)):
+            a = noisy_repeat(rng, motifs, rng.choice([4, 12, 40]))
+            if rng.random() < 0.1:
+                a = a[:3] + b"N" + a[3:] + b"X"
+            alleles.append(a)
+        loci.append((motifs, alleles))
+    got = engine.label_with_hmm(loci)
+    motifs = PackedSeqs.from_list([m for ms, _ in loci for m in ms])
+    lmo = np.cumsum([0] + [len(ms) for ms, _ in loci]).astype(np.uint32)
+    alleles = PackedSeqs.from_list([a for _, als in loci for a in als])
+    al = np.array([i for i, (_, als) in enumerate(loci) for _ in als], dtype=np.uint32)
+    res = engine.hmm_label_packed(motifs, lmo, alleles, al, want_paths=True)
+    paths = [res.path(i) for i in range(len(alleles))]
+    _check_annotations(oracle, loci, got, paths)
+
+
+def test_hmm_pathogenic_catalog_shapes(engine, oracle):
+    """BASELINE config 2 shapes: the 56 motif sets of repeats/pathogenic_repeats.hg38.bed (up to 10
+    motifs, 170 states, N allowed)."""
+    from trgt_b200 import workload
+    sets = workload.pathogenic_motif_sets()
+    w = workload.generate(len(sets), 4, motif_sets=sets, tr_len_median=60.0)
+    rng = random.Random(5)
+    loci = []
+    for l in range(w.n_loci):
+        als = [w.alleles.get(2 * l), mutate(rng, w.alleles.get(2 * l + 1), 0.05)]
+        loci.append((w.locus_motifs(l), als))
+    _check_annotations(oracle, loci, engine.label_with_hmm(loci))
+
+
+def test_hmm_long_allele_and_waves(engine, oracle):
+    rng = random.Random(13)
+    motifs = [b"CAG", b"CCG"]
+    long_allele = mutate(rng, b"CAG" * 5000 + b"CCG" * 2000, 0.02)
+    loci = [(motifs, [long_allele, b"CAGCAG"]), ([b"AT"], [b"AT" * 9000, mutate(rng, b"AT" * 5000, 0.05)])]
+    engine.set_workspace_budget(1 << 20)  # forces several back-pointer waves
+    try:
+        got = engine.label_with_hmm(loci)
+    finally:
+        engine.set_workspace_budget(24 << 30)
+    _check_annotations(oracle, loci, got)
+
+
+# ------------------------------------------------------------------ phase A: flanks --------
+
+def _check_flanks(oracle, w, spans, hits, scoring, frac):
+    n_wfa = 0
+    for l in range(w.n_loci):
+        lp, rp = w.left.get(l), w.right.get(l)
+        for r in range(int(w.locus_read_off[l]), int(w.locus_read_off[l + 1])):
+            read = w.reads.get(r)
+            sides = []
+            for side, piece in enumerate((lp, rp)):
+                exp, via, nm = oracle.find_span(piece, read, scoring, len(piece) * frac)
+                h = hits[2 * r + side]
+                assert int(h["via"]) == via, (l, r, side)
+                assert int(h["matches"]) == nm, (l, r, side)
+                if exp is not None:
+                    assert (int(h["start"]), int(h["end"])) == exp, (l, r, side)
+                n_wfa += via >= 2
+                sides.append(exp)
+            exp_span = None
+            if sides[0] is not None and sides[1] is not None and sides[0][1] <= sides[1][0]:
+                exp_span = (sides[0][1], sides[1][0])
+            s = spans[r]
+            got = (int(s["start"]), int(s["end"])) if s["found"] else None
+            assert got == exp_span, (l, r)
+    return n_wfa
+
+
+def test_flank_spans_synthetic_hifi(engine, oracle):
+    from trgt_b200 import workload
+    w = workload.generate(40, 12, seed=99)
+    spans, hits = engine.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+    n_wfa = _check_flanks(oracle, w, spans, hits, w.scoring, w.min_flank_id_frac)
+    assert n_wfa > 20  # the WFA fallback was exercised
+
+
+def test_flank_spans_noisy_targeted_scoring(engine, oracle):
+    """--preset targeted scoring (1,0,1), 0.8 identity, 200-bp pieces (cli.rs:271-302); noisy reads so
+    that accepted, rejected and discordant cases all occur."""
+    from trgt_b200 import workload
+    w = workload.generate(24, 10, seed=5, context=260, piece=200, sub_rate=0.03, ins_rate=0.03, del_rate=0.03)
+    spans, hits = engine.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, (1, 0, 1), 0.8)
+    _check_flanks(oracle, w, spans, hits, (1, 0, 1), 0.8)
+    vias = set(int(v) for v in hits["via"])
+    assert 2 in vias and 3 in vias
+
+
+def test_flank_spans_edge_cases(engine, oracle):
+    rng = random.Random(21)
+    lf = rnd(rng, 300)
+    rf = rnd(rng, 300)
+    tr = b"CAG" * 10
+    good = lf[-250:] + tr + rf[:250]
+    reads = [
+        good,
+        good[100:],                      # left flank truncated
+        rnd(rng, 600),                   # unrelated read
+        rf[:250] + tr + lf[-250:],       # flanks in the wrong order (discordant)
+        lf[-250:] + rf[:250],            # empty repeat
+        lf[-250:][:120],                 # read shorter than the piece
+        b"A",
+    ]
+    out, hits = engine.find_tr_spans([(lf, rf, reads)], return_hits=True)
+    exp = oracle.find_tr_spans(lf, rf, reads)
+    assert out[0] == exp
+    assert out[0][0] == (250, 280) and out[0][4] == (250, 250) and out[0][2] is None and out[0][3] is None
+    # ragged batch: a locus without reads between two with reads
+    out2 = engine.find_tr_spans([(lf, rf, [good]), (lf, rf, []), (lf, rf, [good, good[100:]])])
+    assert out2 == [[(250, 280)], [], [(250, 280), exp[1]]]
+    assert engine.find_tr_spans([]) == []
+
+
+# ------------------------------------------------------------------ phase B ------------------
+
+def test_align_parity_short(engine, oracle):
+    rng = random.Random(31)
+    groups = []
+    for _ in range(150):
+        bb = rnd(rng, rng.randint(1, 80))
+        seqs = []
+        for _ in range(rng.randint(0, 6)):
+            r = rng.random()
+            seqs.append(bb if r < 0.3 else (mutate(rng, bb, rng.choice([0.02, 0.1, 0.4])) or b"A") if r < 0.9
+                        else rnd(rng, rng.randint(1, 80)))
+        groups.append((bb, seqs))
+    got = engine.align(groups)
+    for (bb, seqs), res in zip(groups, got):
+        assert res == oracle.align(bb, seqs)
+
+
+def test_align_parity_long_and_scores(engine, oracle):
+    from trgt_b200 import PackedSeqs
+    rng = random.Random(37)
+    bbs, seqs, offs = [], [], [0]
+    for L in (300, 1500, 6000):
+        bb = rnd(rng, L)
+        bbs.append(bb)
+        seqs += [mutate(rng, bb, 0.01), mutate(rng, bb, 0.03), bb]
+        offs.append(len(seqs))
+    res = engine.align_packed(PackedSeqs.from_list(bbs), PackedSeqs.from_list(seqs), np.array(offs, dtype=np.uint32))
+    assert not res.status.any()
+    for i, s in enumerate(seqs):
+        words, score = oracle.align_words(bbs[i // 3], s)
+        assert res.cigar(i) == words and int(res.scores[i]) == score
+
+
+def test_edit_dist_parity(engine, oracle):
+    rng = random.Random(41)
+    loci = []
+    for _ in range(40):
+        base = rnd(rng, rng.randint(1, 90))
+        n = rng.choice([0, 1, 2, 5, 12])
+        trs = [mutate(rng, base, rng.choice([0, 0.05, 0.3])) or b"G" for _ in range(n)]
+        if n > 2 and rng.random() < 0.3:
+            trs[1] = rnd(rng, 400)  # len1*len2 > MAX_OPS -> length difference
+        loci.append(trs)
+    got = engine.get_dist_matrix(loci)
+    for trs, g in zip(loci, got):
+        assert g == oracle.get_dist_matrix(trs)
+
+
+# ------------------------------------------------------------------ boundary behaviour -------
+
+def test_error_reporting(engine):
+    from trgt_b200 import PackedSeqs, TrgtError
+    one = PackedSeqs.from_list([b"ACGT"])
+    with pytest.raises(TrgtError):  # one piece per locus is required
+        engine.flank_spans_packed(one, PackedSeqs.from_list([]), one, np.array([0, 1], dtype=np.uint32))
+    with pytest.raises(TrgtError):  # gap_extend must be >= 1
+        engine.flank_spans_packed(one, one, one, np.array([0, 1], dtype=np.uint32), scoring=(2, 5, 0))
+    with pytest.raises(TrgtError):  # allele pointing at a locus that does not exist
+        engine.hmm_label_packed(one, np.array([0, 1], dtype=np.uint32), one, np.array([3], dtype=np.uint32))
+    # the engine is still usable afterwards
+    assert engine.label_with_hmm([([b"CAG"], [b"CAGCAG"])])[0][0].motif_counts == [2]
+
+
+def test_kernels_actually_launched(engine):
+    engine.reset_stats()
+    engine.label_with_hmm([([b"CAG"], [b"CAGCAGCAG"])])
+    stats = engine.kernel_stats()
+    assert stats["k_hmm_viterbi"][0] >= 1 and engine.launches() >= 2

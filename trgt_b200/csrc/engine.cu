@@ -1,0 +1,1211 @@
+// engine.cu -- C ABI of libtrgt_b200.so (include/trgt_engine.h): device memory, streams, launches.
+//
+// There is no CPU path in this library: every entry point that computes launches the sm_100a
+// kernels of kernels.cuh, and trgt_engine_create fails without a CUDA device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/trgt_engine.h"
+#include "hmm_host.h"
+#include "kernels.cuh"
+
+using namespace trgt;
+
+// ------------------------------------------------------------------ plumbing --------------
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct KernelStat {
+  const char *name;
+  uint64_t launches;
+  double total_ms;
+};
+
+struct PendingEvent {
+  int stat;
+  cudaEvent_t a, b;
+};
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct CastU64 {
+  __host__ __device__ unsigned long long operator()(const uint32_t &v) const { return (unsigned long long)v; }
+};
+
+}  // namespace
+
+struct trgt_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  int smem_optin = 0;
+  std::string error;
+  std::mutex mu;
+  bool profiling = false;
+  uint64_t launches = 0;
+  std::vector<KernelStat> stats;
+  std::vector<PendingEvent> pending;
+  std::vector<cudaEvent_t> event_pool;
+  // HMM constants
+  HmmConsts hmm_consts;
+  HmmJumpTable jump;
+  DevBuf d_mm_off, d_mm_lp;
+  size_t jump_uploaded_len = 0;
+  // scan scratch
+  DevBuf d_scan_tmp;
+  // pinned staging for small read-backs
+  Counters *h_ctr = nullptr;
+  unsigned long long *h_u64 = nullptr;
+  // one-shot batches (results stay valid until the next call)
+  trgt_flank_batch_t *one_flank = nullptr;
+  trgt_align_batch_t *one_align = nullptr;
+  trgt_hmm_batch_t *one_hmm = nullptr;
+  DevBuf d_ed[6];
+  size_t workspace_budget = (size_t)24 << 30;  // cap on back-pointer / trace workspace per wave
+};
+
+namespace {
+
+int fail(trgt_engine *e, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->error = buf;
+  return code;
+}
+
+#define CU(e, call)                                                                          \
+  do {                                                                                       \
+    cudaError_t err_ = (call);                                                               \
+    if (err_ != cudaSuccess)                                                                 \
+      return fail((e), TRGT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err_), \
+                  __FILE__, __LINE__);                                                       \
+  } while (0)
+
+#define TRY(expr)          \
+  do {                     \
+    int rc_ = (expr);      \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+int dev_reserve(trgt_engine *e, DevBuf &b, size_t bytes, bool keep = false) {
+  if (bytes <= b.cap && b.p) return 0;
+  size_t ncap = bytes + bytes / 8 + 256;
+  void *np = nullptr;
+  CU(e, cudaMalloc(&np, ncap));
+  if (keep && b.p && b.cap) CU(e, cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, e->stream));
+  if (b.p) {
+    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaFree(b.p));
+  }
+  b.p = np;
+  b.cap = ncap;
+  return 0;
+}
+
+void dev_free(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+int h2d(trgt_engine *e, DevBuf &b, const void *src, size_t bytes, size_t pad = 16) {
+  TRY(dev_reserve(e, b, bytes + pad));
+  if (bytes) CU(e, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream));
+  return 0;
+}
+
+int stat_index(trgt_engine *e, const char *name) {
+  for (size_t i = 0; i < e->stats.size(); i++)
+    if (e->stats[i].name == name || strcmp(e->stats[i].name, name) == 0) return (int)i;
+  e->stats.push_back(KernelStat{name, 0, 0.0});
+  return (int)e->stats.size() - 1;
+}
+
+cudaEvent_t get_event(trgt_engine *e) {
+  if (!e->event_pool.empty()) {
+    cudaEvent_t ev = e->event_pool.back();
+    e->event_pool.pop_back();
+    return ev;
+  }
+  cudaEvent_t ev;
+  cudaEventCreate(&ev);
+  return ev;
+}
+
+struct LaunchScope {
+  trgt_engine *e;
+  int si;
+  cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(trgt_engine *e_, const char *name) : e(e_) {
+    si = stat_index(e, name);
+    e->stats[si].launches++;
+    e->launches++;
+    if (e->profiling) {
+      a = get_event(e);
+      b = get_event(e);
+      cudaEventRecord(a, e->stream);
+    }
+  }
+  ~LaunchScope() {
+    if (e->profiling) {
+      cudaEventRecord(b, e->stream);
+      e->pending.push_back(PendingEvent{si, a, b});
+    }
+  }
+};
+
+void resolve_pending(trgt_engine *e) {
+  if (e->pending.empty()) return;
+  cudaStreamSynchronize(e->stream);
+  for (auto &p : e->pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) e->stats[p.stat].total_ms += ms;
+    e->event_pool.push_back(p.a);
+    e->event_pool.push_back(p.b);
+  }
+  e->pending.clear();
+}
+
+int check_launch(trgt_engine *e, const char *name) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(e, TRGT_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(err));
+  return 0;
+}
+
+template <class K>
+int persistent_grid(trgt_engine *e, K kernel, int block, size_t smem, int *grid_out) {
+  if (smem > 48 * 1024)
+    CU(e, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CU(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+  if (per_sm < 1) return fail(e, TRGT_ERR_INTERNAL, "kernel does not fit on an SM (smem %zu)", smem);
+  *grid_out = per_sm * e->sm_count;
+  return 0;
+}
+
+int check_seqs(trgt_engine *e, const trgt_seqs_t *s, const char *what) {
+  if (!s || (s->n && (!s->offsets))) return fail(e, TRGT_ERR_ARG, "%s: null sequence set", what);
+  for (uint64_t i = 0; i < s->n; i++)
+    if (s->offsets[i + 1] < s->offsets[i]) return fail(e, TRGT_ERR_ARG, "%s: offsets not monotone at %llu", what, (unsigned long long)i);
+  if (s->n && s->offsets[s->n] > s->offsets[0] && !s->data) return fail(e, TRGT_ERR_ARG, "%s: null data", what);
+  return 0;
+}
+
+uint64_t max_len(const trgt_seqs_t *s) {
+  uint64_t m = 0;
+  for (uint64_t i = 0; i < s->n; i++) {
+    const uint64_t l = s->offsets[i + 1] - s->offsets[i];
+    if (l > m) m = l;
+  }
+  return m;
+}
+
+int upload_seqs(trgt_engine *e, const trgt_seqs_t *s, DevBuf &data, DevBuf &off) {
+  static const uint64_t zero_off[1] = {0};
+  const uint64_t total = s->n ? s->offsets[s->n] : 0;
+  TRY(h2d(e, data, s->data, (size_t)total));
+  TRY(h2d(e, off, s->n ? s->offsets : zero_off, (size_t)(s->n + 1) * sizeof(uint64_t)));
+  return 0;
+}
+
+int exclusive_scan_u32(trgt_engine *e, const uint32_t *d_in, unsigned long long *d_out, size_t n) {
+  cub::TransformInputIterator<unsigned long long, CastU64, const uint32_t *> it(d_in, CastU64());
+  size_t tmp = 0;
+  CU(e, cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, d_out, (int)n, e->stream));
+  TRY(dev_reserve(e, e->d_scan_tmp, tmp));
+  LaunchScope ls(e, "cub_exclusive_scan");
+  CU(e, cub::DeviceScan::ExclusiveSum(e->d_scan_tmp.p, tmp, it, d_out, (int)n, e->stream));
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ lifetime --------------
+
+extern "C" {
+
+const char *trgt_last_create_error(void) { return g_create_error.c_str(); }
+
+int32_t trgt_engine_create(int32_t device, trgt_engine_t **out) {
+  if (!out) return TRGT_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device: ") + (err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+    return TRGT_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "device index out of range";
+    return TRGT_ERR_ARG;
+  }
+  cudaDeviceProp prop;
+  if ((err = cudaSetDevice(device)) != cudaSuccess || (err = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice failed: ") + cudaGetErrorString(err);
+    return TRGT_ERR_CUDA;
+  }
+  if (prop.major < 10) {
+    g_create_error = "libtrgt_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return TRGT_ERR_NO_DEVICE;
+  }
+  trgt_engine *e = new trgt_engine();
+  e->device = device;
+  e->sm_count = prop.multiProcessorCount;
+  e->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if ((err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (err = cudaMallocHost((void **)&e->h_ctr, sizeof(Counters))) != cudaSuccess ||
+      (err = cudaMallocHost((void **)&e->h_u64, 8 * sizeof(unsigned long long))) != cudaSuccess) {
+    g_create_error = std::string("engine setup failed: ") + cudaGetErrorString(err);
+    delete e;
+    return TRGT_ERR_CUDA;
+  }
+  e->hmm_consts = hmm_make_consts();
+  *out = e;
+  return TRGT_OK;
+}
+
+void trgt_engine_destroy(trgt_engine_t *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  if (e->one_flank) trgt_flank_free(e, e->one_flank);
+  if (e->one_align) trgt_align_free(e, e->one_align);
+  if (e->one_hmm) trgt_hmm_free(e, e->one_hmm);
+  resolve_pending(e);
+  for (auto ev : e->event_pool) cudaEventDestroy(ev);
+  dev_free(e->d_mm_off);
+  dev_free(e->d_mm_lp);
+  dev_free(e->d_scan_tmp);
+  for (auto &b : e->d_ed) dev_free(b);
+  if (e->h_ctr) cudaFreeHost(e->h_ctr);
+  if (e->h_u64) cudaFreeHost(e->h_u64);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char *trgt_engine_last_error(const trgt_engine_t *e) { return e ? e->error.c_str() : ""; }
+void *trgt_engine_stream(trgt_engine_t *e) { return e ? (void *)e->stream : nullptr; }
+int32_t trgt_engine_sm_count(const trgt_engine_t *e) { return e ? e->sm_count : 0; }
+
+int32_t trgt_engine_sync(trgt_engine_t *e) {
+  if (!e) return TRGT_ERR_ARG;
+  CU(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+void *trgt_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void trgt_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+void trgt_engine_set_profiling(trgt_engine_t *e, int32_t on) {
+  if (!e) return;
+  resolve_pending(e);
+  e->profiling = on != 0;
+}
+void trgt_engine_reset_stats(trgt_engine_t *e) {
+  if (!e) return;
+  resolve_pending(e);
+  e->stats.clear();
+  e->launches = 0;
+}
+int32_t trgt_engine_kernel_count(trgt_engine_t *e) {
+  if (!e) return 0;
+  resolve_pending(e);
+  return (int32_t)e->stats.size();
+}
+int32_t trgt_engine_kernel_stat(trgt_engine_t *e, int32_t i, const char **name, uint64_t *launches, double *total_ms) {
+  if (!e || i < 0 || (size_t)i >= e->stats.size()) return TRGT_ERR_ARG;
+  resolve_pending(e);
+  if (name) *name = e->stats[i].name;
+  if (launches) *launches = e->stats[i].launches;
+  if (total_ms) *total_ms = e->stats[i].total_ms;
+  return 0;
+}
+uint64_t trgt_engine_launches(const trgt_engine_t *e) { return e ? e->launches : 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ phase A ----------------
+
+struct trgt_flank_batch {
+  uint32_t n_loci = 0, n_reads = 0;
+  int Pmax = 0, Tmax = 0;
+  trgt_scoring_t scoring{2, 5, 1};
+  double frac = 0.7;
+  DevBuf reads, read_off, lp, lp_off, rp, rp_off, locus_read_off, read_locus;
+  DevBuf hits, spans, work, ends, ctr, gring, gws;
+  uint32_t last_n_work = 0;
+};
+
+namespace {
+
+WfaSrc flank_src(const trgt_flank_batch *b) {
+  WfaSrc s;
+  memset(&s, 0, sizeof s);
+  s.mode = WFA_MODE_FLANK;
+  s.x = b->scoring.mismatch;
+  s.oe = b->scoring.gap_open + b->scoring.gap_extend;
+  s.e = b->scoring.gap_extend;
+  s.reads = (const uint8_t *)b->reads.p;
+  s.read_off = (const uint64_t *)b->read_off.p;
+  s.read_locus = (const uint32_t *)b->read_locus.p;
+  s.lp = (const uint8_t *)b->lp.p;
+  s.lp_off = (const uint64_t *)b->lp_off.p;
+  s.rp = (const uint8_t *)b->rp.p;
+  s.rp_off = (const uint64_t *)b->rp_off.p;
+  return s;
+}
+
+size_t ring_ints_bound(int x, int oe, int e, int Pmax, int Tmax) {
+  WfaProb pr;
+  memset(&pr, 0, sizeof pr);
+  pr.x = x; pr.oe = oe; pr.e = e; pr.P = Pmax; pr.T = Tmax;
+  return wfa_ring_ints(pr);
+}
+
+int check_scoring(trgt_engine *e, int x, int o, int ext) {
+  if (x < 1 || o < 0 || ext < 1 || x > 4096 || o > 4096 || ext > 4096)
+    return fail(e, TRGT_ERR_ARG, "scoring (%d,%d,%d) unsupported: need mismatch>=1, gap_open>=0, gap_extend>=1", x, o, ext);
+  return 0;
+}
+
+// WFA pass 2 launch shared by phases A and B
+int launch_trace(trgt_engine *e, const WfaSrc &src, const uint32_t *work, const unsigned int *n_work_ptr,
+                 uint32_t n_work_host, const WfaEnd *ends, unsigned long long max_trace_ints, DevBuf &gws,
+                 double frac, trgt_flank_hit_t *hits, uint32_t *pool, unsigned long long pool_cap,
+                 unsigned long long *cig_off, uint32_t *cig_n, int32_t *status, Counters *ctr) {
+  if (n_work_host == 0) return 0;
+  const int block = 128, wpb = block / 32;
+  const size_t smem_cap_ints = 3072;  // 12 KB per warp: cones up to cost ~25 stay on chip
+  const int smem_ws_ints = (int)(max_trace_ints < smem_cap_ints ? (max_trace_ints ? max_trace_ints : 1) : smem_cap_ints);
+  const size_t smem = (size_t)wpb * smem_ws_ints * sizeof(int);
+  int grid = 0;
+  TRY(persistent_grid(e, k_wfa_trace, block, smem, &grid));
+  const uint32_t need_blocks = (n_work_host + wpb - 1) / wpb;
+  if ((uint32_t)grid > need_blocks) grid = (int)need_blocks;
+  size_t stride = 0;
+  int *gws_p = nullptr;
+  if (max_trace_ints > (unsigned long long)smem_ws_ints) {
+    stride = (size_t)max_trace_ints;
+    // fewer resident warps when one slot is huge
+    size_t slots = (size_t)grid * wpb;
+    const size_t budget_ints = e->workspace_budget / sizeof(int);
+    if (stride > budget_ints) return fail(e, TRGT_ERR_INTERNAL, "trace workspace of %zu ints exceeds the budget", stride);
+    if (slots * stride > budget_ints) {
+      slots = budget_ints / stride;
+      grid = (int)((slots + wpb - 1) / wpb);
+      if (grid < 1) grid = 1;
+      if ((size_t)grid * wpb > slots && grid > 1) grid--;
+    }
+    TRY(dev_reserve(e, gws, (size_t)grid * wpb * stride * sizeof(int)));
+    gws_p = (int *)gws.p;
+  }
+  LaunchScope ls(e, "k_wfa_trace");
+  k_wfa_trace<<<grid, block, smem, e->stream>>>(src, work, n_work_ptr, ends, gws_p, stride, smem_ws_ints, frac, hits,
+                                                pool, pool_cap, cig_off, cig_n, status, ctr);
+  return check_launch(e, "k_wfa_trace");
+}
+
+}  // namespace
+
+extern "C" {
+
+void trgt_flank_free(trgt_engine_t *e, trgt_flank_batch_t *b) {
+  if (!b) return;
+  if (e) {
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    if (e->one_flank == b) e->one_flank = nullptr;
+  }
+  DevBuf *all[] = {&b->reads, &b->read_off, &b->lp, &b->lp_off, &b->rp, &b->rp_off, &b->locus_read_off,
+                   &b->read_locus, &b->hits, &b->spans, &b->work, &b->ends, &b->ctr, &b->gring, &b->gws};
+  for (auto *d : all) dev_free(*d);
+  delete b;
+}
+
+static int flank_upload_into(trgt_engine_t *e, trgt_flank_batch *b, const trgt_seqs_t *left_pieces,
+                             const trgt_seqs_t *right_pieces, const trgt_seqs_t *reads,
+                             const uint32_t *locus_read_offsets, uint32_t n_loci, trgt_scoring_t scoring,
+                             double min_flank_id_frac) {
+  TRY(check_seqs(e, left_pieces, "left_pieces"));
+  TRY(check_seqs(e, right_pieces, "right_pieces"));
+  TRY(check_seqs(e, reads, "reads"));
+  TRY(check_scoring(e, scoring.mismatch, scoring.gap_open, scoring.gap_extend));
+  if (left_pieces->n != n_loci || right_pieces->n != n_loci) return fail(e, TRGT_ERR_ARG, "need one left and one right piece per locus");
+  if (n_loci && !locus_read_offsets) return fail(e, TRGT_ERR_ARG, "locus_read_offsets is null");
+  if (reads->n > 0x7fffffffull) return fail(e, TRGT_ERR_ARG, "too many reads in one batch");
+  for (uint32_t l = 0; l < n_loci; l++)
+    if (locus_read_offsets[l + 1] < locus_read_offsets[l]) return fail(e, TRGT_ERR_ARG, "locus_read_offsets not monotone");
+  if (n_loci && (locus_read_offsets[0] != 0 || locus_read_offsets[n_loci] != reads->n))
+    return fail(e, TRGT_ERR_ARG, "locus_read_offsets must cover all reads");
+  const uint64_t pm = max_len(left_pieces) > max_len(right_pieces) ? max_len(left_pieces) : max_len(right_pieces);
+  const uint64_t tm = max_len(reads);
+  if (pm + tm > 0x3fffffffull) return fail(e, TRGT_ERR_ARG, "sequence too long");
+  b->n_loci = n_loci;
+  b->n_reads = (uint32_t)reads->n;
+  b->Pmax = (int)pm;
+  b->Tmax = (int)tm;
+  b->scoring = scoring;
+  b->frac = min_flank_id_frac;
+  CU(e, cudaSetDevice(e->device));
+  TRY(upload_seqs(e, reads, b->reads, b->read_off));
+  TRY(upload_seqs(e, left_pieces, b->lp, b->lp_off));
+  TRY(upload_seqs(e, right_pieces, b->rp, b->rp_off));
+  static const uint32_t zero32[1] = {0};
+  TRY(h2d(e, b->locus_read_off, n_loci ? locus_read_offsets : zero32, ((size_t)n_loci + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->read_locus, ((size_t)b->n_reads + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->hits, ((size_t)b->n_reads * 2 + 1) * sizeof(trgt_flank_hit_t)));
+  TRY(dev_reserve(e, b->spans, ((size_t)b->n_reads + 1) * sizeof(trgt_span_t)));
+  TRY(dev_reserve(e, b->work, ((size_t)b->n_reads * 2 + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->ends, ((size_t)b->n_reads * 2 + 1) * sizeof(WfaEnd)));
+  TRY(dev_reserve(e, b->ctr, sizeof(Counters)));
+  if (n_loci) {
+    LaunchScope ls(e, "k_expand_offsets");
+    k_expand_offsets<<<(n_loci + 255) / 256, 256, 0, e->stream>>>((const uint32_t *)b->locus_read_off.p, n_loci,
+                                                                   (uint32_t *)b->read_locus.p);
+    TRY(check_launch(e, "k_expand_offsets"));
+  }
+  return 0;
+}
+
+int32_t trgt_flank_upload(trgt_engine_t *e, const trgt_seqs_t *left_pieces, const trgt_seqs_t *right_pieces,
+                          const trgt_seqs_t *reads, const uint32_t *locus_read_offsets, uint32_t n_loci,
+                          trgt_scoring_t scoring, double min_flank_id_frac, trgt_flank_batch_t **out) {
+  if (!e || !out) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  *out = nullptr;
+  trgt_flank_batch *b = new trgt_flank_batch();
+  const int rc = flank_upload_into(e, b, left_pieces, right_pieces, reads, locus_read_offsets, n_loci, scoring,
+                                   min_flank_id_frac);
+  if (rc != 0) {
+    trgt_flank_free(nullptr, b);
+    return rc;
+  }
+  *out = b;
+  return 0;
+}
+
+static int flank_run_locked(trgt_engine_t *e, trgt_flank_batch *b) {
+  CU(e, cudaSetDevice(e->device));
+  if (b->n_reads == 0) return 0;
+  const WfaSrc src = flank_src(b);
+  Counters *ctr = (Counters *)b->ctr.p;
+  CU(e, cudaMemsetAsync(ctr, 0, sizeof(Counters), e->stream));
+  {
+    const int block = 256;
+    int grid = 0;
+    TRY(persistent_grid(e, k_flank_scan, block, 0, &grid));
+    const uint32_t need = (b->n_reads + 7) / 8;
+    if ((uint32_t)grid > need) grid = (int)need;
+    LaunchScope ls(e, "k_flank_scan");
+    k_flank_scan<<<grid, block, 0, e->stream>>>(src, b->n_reads, (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p, ctr);
+    TRY(check_launch(e, "k_flank_scan"));
+  }
+  {
+    // pass 1: one CTA per (read, flank) that missed; ring in shared memory when it fits
+    const int block = 128;
+    const size_t bound = ring_ints_bound(src.x, src.oe, src.e, b->Pmax, b->Tmax);
+    const size_t cap_ints = 24 * 1024;  // 96 KB: two CTAs per SM
+    const int smem_ring_ints = (int)(bound < cap_ints ? bound : cap_ints);
+    const size_t smem = (size_t)(40 + smem_ring_ints) * sizeof(int);
+    int grid = 0;
+    TRY(persistent_grid(e, k_wfa_score<true>, block, smem, &grid));
+    const uint32_t max_items = b->n_reads * 2;
+    if ((uint32_t)grid > max_items) grid = (int)max_items;
+    int *gring = nullptr;
+    size_t stride = 0;
+    if (bound > (size_t)smem_ring_ints) {
+      stride = bound;
+      TRY(dev_reserve(e, b->gring, (size_t)grid * stride * sizeof(int)));
+      gring = (int *)b->gring.p;
+    }
+    LaunchScope ls(e, "k_wfa_score_block");
+    k_wfa_score<true><<<grid, block, smem, e->stream>>>(src, (const uint32_t *)b->work.p, &ctr->n_work, 0,
+                                                         (WfaEnd *)b->ends.p, gring, stride, smem_ring_ints, nullptr,
+                                                         nullptr, ctr);
+    TRY(check_launch(e, "k_wfa_score_block"));
+  }
+  CU(e, cudaMemcpyAsync(e->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  b->last_n_work = e->h_ctr->n_work;
+  TRY(launch_trace(e, src, (const uint32_t *)b->work.p, &ctr->n_work, e->h_ctr->n_work, (const WfaEnd *)b->ends.p,
+                   e->h_ctr->max_trace_ints, b->gws, b->frac, (trgt_flank_hit_t *)b->hits.p, nullptr, 0, nullptr,
+                   nullptr, nullptr, ctr));
+  {
+    LaunchScope ls(e, "k_flank_combine");
+    const uint32_t grid = (b->n_reads + 255) / 256;
+    k_flank_combine<<<grid, 256, 0, e->stream>>>((const trgt_flank_hit_t *)b->hits.p, b->n_reads, (trgt_span_t *)b->spans.p);
+    TRY(check_launch(e, "k_flank_combine"));
+  }
+  return 0;
+}
+
+int32_t trgt_flank_run(trgt_engine_t *e, trgt_flank_batch_t *b) {
+  if (!e || !b) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return flank_run_locked(e, b);
+}
+
+static int flank_download_locked(trgt_engine_t *e, trgt_flank_batch *b, trgt_span_t *spans_out,
+                                 trgt_flank_hit_t *hits_out) {
+  CU(e, cudaSetDevice(e->device));
+  if (b->n_reads) {
+    if (spans_out)
+      CU(e, cudaMemcpyAsync(spans_out, b->spans.p, (size_t)b->n_reads * sizeof(trgt_span_t), cudaMemcpyDeviceToHost, e->stream));
+    if (hits_out)
+      CU(e, cudaMemcpyAsync(hits_out, b->hits.p, (size_t)b->n_reads * 2 * sizeof(trgt_flank_hit_t), cudaMemcpyDeviceToHost, e->stream));
+  }
+  CU(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int32_t trgt_flank_download(trgt_engine_t *e, trgt_flank_batch_t *b, trgt_span_t *spans_out, trgt_flank_hit_t *hits_out) {
+  if (!e || !b) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return flank_download_locked(e, b, spans_out, hits_out);
+}
+
+int32_t trgt_flank_spans(trgt_engine_t *e, const trgt_seqs_t *left_pieces, const trgt_seqs_t *right_pieces,
+                         const trgt_seqs_t *reads, const uint32_t *locus_read_offsets, uint32_t n_loci,
+                         trgt_scoring_t scoring, double min_flank_id_frac, trgt_span_t *spans_out,
+                         trgt_flank_hit_t *hits_out) {
+  if (!e) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->one_flank) e->one_flank = new trgt_flank_batch();
+  TRY(flank_upload_into(e, e->one_flank, left_pieces, right_pieces, reads, locus_read_offsets, n_loci, scoring,
+                        min_flank_id_frac));
+  TRY(flank_run_locked(e, e->one_flank));
+  return flank_download_locked(e, e->one_flank, spans_out, hits_out);
+}
+
+/* device pointers of a resident flank batch (for device-side consumers such as the pipeline) */
+int32_t trgt_flank_device_views(trgt_flank_batch_t *b, const void **d_reads, const void **d_read_off,
+                                const void **d_spans, const void **d_hits, uint32_t *n_reads, uint32_t *n_wfa) {
+  if (!b) return TRGT_ERR_ARG;
+  if (d_reads) *d_reads = b->reads.p;
+  if (d_read_off) *d_read_off = b->read_off.p;
+  if (d_spans) *d_spans = b->spans.p;
+  if (d_hits) *d_hits = b->hits.p;
+  if (n_reads) *n_reads = b->n_reads;
+  if (n_wfa) *n_wfa = b->last_n_work;
+  return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ phase B: align ---------
+
+struct trgt_align_batch {
+  uint32_t n_groups = 0, n_seqs = 0;
+  int Pmax = 0, Tmax = 0;
+  DevBuf bb, bb_off, seqs, seq_off, group_off, seq_group;
+  DevBuf ends, trace_work, cig_n, cig_off, pool, ctr, gring, gws;
+  DevBuf out_off, out_words, scores, status;
+  // host copies handed out by download
+  std::vector<uint64_t> h_off;
+  std::vector<uint32_t> h_words;
+  std::vector<int32_t> h_scores, h_status;
+  unsigned long long total_words = 0;
+  bool ran = false;
+};
+
+namespace {
+
+WfaSrc align_src(const trgt_align_batch *b) {
+  WfaSrc s;
+  memset(&s, 0, sizeof s);
+  s.mode = WFA_MODE_E2E;
+  s.x = 2; s.oe = 5 + 1; s.e = 1;  // create_thread_local_ga_aligner: affine(2,5,1), commands/genotype.rs:82-86
+  s.bb = (const uint8_t *)b->bb.p;
+  s.bb_off = (const uint64_t *)b->bb_off.p;
+  s.seqs = (const uint8_t *)b->seqs.p;
+  s.seq_off = (const uint64_t *)b->seq_off.p;
+  s.seq_group = (const uint32_t *)b->seq_group.p;
+  return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+void trgt_align_free(trgt_engine_t *e, trgt_align_batch_t *b) {
+  if (!b) return;
+  if (e) {
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    if (e->one_align == b) e->one_align = nullptr;
+  }
+  DevBuf *all[] = {&b->bb, &b->bb_off, &b->seqs, &b->seq_off, &b->group_off, &b->seq_group, &b->ends, &b->trace_work,
+                   &b->cig_n, &b->cig_off, &b->pool, &b->ctr, &b->gring, &b->gws, &b->out_off, &b->out_words,
+                   &b->scores, &b->status};
+  for (auto *d : all) dev_free(*d);
+  delete b;
+}
+
+static int align_upload_into(trgt_engine_t *e, trgt_align_batch *b, const trgt_seqs_t *backbones,
+                             const trgt_seqs_t *seqs, const uint32_t *group_seq_offsets, uint32_t n_groups) {
+  TRY(check_seqs(e, backbones, "backbones"));
+  TRY(check_seqs(e, seqs, "seqs"));
+  if (backbones->n != n_groups) return fail(e, TRGT_ERR_ARG, "need one backbone per group");
+  if (n_groups && !group_seq_offsets) return fail(e, TRGT_ERR_ARG, "group_seq_offsets is null");
+  if (seqs->n > 0x7fffffffull) return fail(e, TRGT_ERR_ARG, "too many sequences in one batch");
+  for (uint32_t g = 0; g < n_groups; g++)
+    if (group_seq_offsets[g + 1] < group_seq_offsets[g]) return fail(e, TRGT_ERR_ARG, "group_seq_offsets not monotone");
+  if (n_groups && (group_seq_offsets[0] != 0 || group_seq_offsets[n_groups] != seqs->n))
+    return fail(e, TRGT_ERR_ARG, "group_seq_offsets must cover all sequences");
+  if (!n_groups && seqs->n) return fail(e, TRGT_ERR_ARG, "sequences without groups");
+  const uint64_t pm = max_len(backbones), tm = max_len(seqs);
+  if (pm + tm > 0x0fffffffull) return fail(e, TRGT_ERR_ARG, "sequence too long");
+  b->n_groups = n_groups;
+  b->n_seqs = (uint32_t)seqs->n;
+  b->Pmax = (int)pm;
+  b->Tmax = (int)tm;
+  b->ran = false;
+  CU(e, cudaSetDevice(e->device));
+  TRY(upload_seqs(e, backbones, b->bb, b->bb_off));
+  TRY(upload_seqs(e, seqs, b->seqs, b->seq_off));
+  static const uint32_t zero32[1] = {0};
+  TRY(h2d(e, b->group_off, n_groups ? group_seq_offsets : zero32, ((size_t)n_groups + 1) * sizeof(uint32_t)));
+  const size_t n = b->n_seqs;
+  TRY(dev_reserve(e, b->seq_group, (n + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->ends, (n + 1) * sizeof(WfaEnd)));
+  TRY(dev_reserve(e, b->trace_work, (n + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->cig_n, (n + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->cig_off, (n + 1) * sizeof(unsigned long long)));
+  TRY(dev_reserve(e, b->out_off, (n + 1) * sizeof(unsigned long long)));
+  TRY(dev_reserve(e, b->scores, (n + 1) * sizeof(int32_t)));
+  TRY(dev_reserve(e, b->status, (n + 1) * sizeof(int32_t)));
+  TRY(dev_reserve(e, b->ctr, sizeof(Counters)));
+  if (n_groups) {
+    LaunchScope ls(e, "k_expand_offsets");
+    k_expand_offsets<<<(n_groups + 255) / 256, 256, 0, e->stream>>>((const uint32_t *)b->group_off.p, n_groups,
+                                                                     (uint32_t *)b->seq_group.p);
+    TRY(check_launch(e, "k_expand_offsets"));
+  }
+  return 0;
+}
+
+int32_t trgt_align_upload(trgt_engine_t *e, const trgt_seqs_t *backbones, const trgt_seqs_t *seqs,
+                          const uint32_t *group_seq_offsets, uint32_t n_groups, trgt_align_batch_t **out) {
+  if (!e || !out) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  *out = nullptr;
+  trgt_align_batch *b = new trgt_align_batch();
+  const int rc = align_upload_into(e, b, backbones, seqs, group_seq_offsets, n_groups);
+  if (rc != 0) {
+    trgt_align_free(nullptr, b);
+    return rc;
+  }
+  *out = b;
+  return 0;
+}
+
+static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
+  CU(e, cudaSetDevice(e->device));
+  b->ran = true;
+  b->total_words = 0;
+  if (b->n_seqs == 0) return 0;
+  const WfaSrc src = align_src(b);
+  const uint32_t n = b->n_seqs;
+  Counters *ctr = (Counters *)b->ctr.p;
+  CU(e, cudaMemsetAsync(ctr, 0, sizeof(Counters), e->stream));
+  CU(e, cudaMemsetAsync(b->cig_n.p, 0, ((size_t)n + 1) * sizeof(uint32_t), e->stream));
+  CU(e, cudaMemsetAsync(b->status.p, 0, ((size_t)n + 1) * sizeof(int32_t), e->stream));
+  const size_t bound = ring_ints_bound(src.x, src.oe, src.e, b->Pmax, b->Tmax);
+  if ((size_t)b->Pmax + (size_t)b->Tmax > 4096) {
+    // long alleles: a CTA per pair
+    const int block = 128;
+    const size_t cap_ints = 24 * 1024;
+    const int smem_ring_ints = (int)(bound < cap_ints ? bound : cap_ints);
+    const size_t smem = (size_t)(40 + smem_ring_ints) * sizeof(int);
+    int grid = 0;
+    TRY(persistent_grid(e, k_wfa_score<true>, block, smem, &grid));
+    if ((uint32_t)grid > n) grid = (int)n;
+    int *gring = nullptr;
+    size_t stride = 0;
+    if (bound > (size_t)smem_ring_ints) {
+      stride = bound;
+      TRY(dev_reserve(e, b->gring, (size_t)grid * stride * sizeof(int)));
+      gring = (int *)b->gring.p;
+    }
+    LaunchScope ls(e, "k_wfa_score_block");
+    k_wfa_score<true><<<grid, block, smem, e->stream>>>(src, nullptr, nullptr, n, (WfaEnd *)b->ends.p, gring, stride,
+                                                         smem_ring_ints, (uint32_t *)b->trace_work.p,
+                                                         (uint32_t *)b->cig_n.p, ctr);
+    TRY(check_launch(e, "k_wfa_score_block"));
+  } else {
+    const int block = 128, wpb = 4;
+    const size_t cap_ints = 6 * 1024;  // 24 KB per warp
+    const int smem_ring_ints = (int)(bound < cap_ints ? bound : cap_ints);
+    const size_t smem = (size_t)wpb * smem_ring_ints * sizeof(int);
+    int grid = 0;
+    TRY(persistent_grid(e, k_wfa_score<false>, block, smem, &grid));
+    const uint32_t need = (n + wpb - 1) / wpb;
+    if ((uint32_t)grid > need) grid = (int)need;
+    int *gring = nullptr;
+    size_t stride = 0;
+    if (bound > (size_t)smem_ring_ints) {
+      stride = bound;
+      TRY(dev_reserve(e, b->gring, (size_t)grid * wpb * stride * sizeof(int)));
+      gring = (int *)b->gring.p;
+    }
+    LaunchScope ls(e, "k_wfa_score_warp");
+    k_wfa_score<false><<<grid, block, smem, e->stream>>>(src, nullptr, nullptr, n, (WfaEnd *)b->ends.p, gring, stride,
+                                                          smem_ring_ints, (uint32_t *)b->trace_work.p,
+                                                          (uint32_t *)b->cig_n.p, ctr);
+    TRY(check_launch(e, "k_wfa_score_warp"));
+  }
+  CU(e, cudaMemcpyAsync(e->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  const unsigned long long words_bound = e->h_ctr->words_bound;
+  TRY(dev_reserve(e, b->pool, (size_t)(words_bound + 1) * sizeof(uint32_t)));
+  TRY(launch_trace(e, src, (const uint32_t *)b->trace_work.p, &ctr->n_trace, e->h_ctr->n_trace, (const WfaEnd *)b->ends.p,
+                   e->h_ctr->max_trace_ints, b->gws, 0.0, nullptr, (uint32_t *)b->pool.p, words_bound,
+                   (unsigned long long *)b->cig_off.p, (uint32_t *)b->cig_n.p, (int32_t *)b->status.p, ctr));
+  TRY(exclusive_scan_u32(e, (const uint32_t *)b->cig_n.p, (unsigned long long *)b->out_off.p, (size_t)n + 1));
+  TRY(dev_reserve(e, b->out_words, (size_t)(words_bound + n + 1) * sizeof(uint32_t)));
+  {
+    LaunchScope ls(e, "k_cigar_gather");
+    k_cigar_gather<<<(n + 255) / 256, 256, 0, e->stream>>>(src, n, (const WfaEnd *)b->ends.p, (const uint32_t *)b->pool.p,
+                                                           (const unsigned long long *)b->cig_off.p,
+                                                           (const uint32_t *)b->cig_n.p,
+                                                           (const unsigned long long *)b->out_off.p,
+                                                           (uint32_t *)b->out_words.p, (int32_t *)b->scores.p,
+                                                           (int32_t *)b->status.p);
+    TRY(check_launch(e, "k_cigar_gather"));
+  }
+  return 0;
+}
+
+int32_t trgt_align_run(trgt_engine_t *e, trgt_align_batch_t *b) {
+  if (!e || !b) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return align_run_locked(e, b);
+}
+
+static int align_download_locked(trgt_engine_t *e, trgt_align_batch *b, trgt_cigars_t *out) {
+  if (!out) return fail(e, TRGT_ERR_ARG, "out is null");
+  if (!b->ran) return fail(e, TRGT_ERR_ARG, "trgt_align_download before trgt_align_run");
+  CU(e, cudaSetDevice(e->device));
+  const size_t n = b->n_seqs;
+  b->h_off.assign(n + 1, 0);
+  b->h_scores.assign(n, 0);
+  b->h_status.assign(n, 0);
+  if (n) {
+    CU(e, cudaMemcpyAsync(b->h_off.data(), b->out_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(b->h_scores.data(), b->scores.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(b->h_status.data(), b->status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    b->total_words = b->h_off[n];
+    b->h_words.resize((size_t)b->total_words);
+    if (b->total_words)
+      CU(e, cudaMemcpyAsync(b->h_words.data(), b->out_words.p, (size_t)b->total_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+  } else {
+    b->h_words.clear();
+  }
+  out->n = n;
+  out->offsets = b->h_off.data();
+  out->words = b->h_words.data();
+  out->scores = b->h_scores.data();
+  out->status = b->h_status.data();
+  return 0;
+}
+
+int32_t trgt_align_download(trgt_engine_t *e, trgt_align_batch_t *b, trgt_cigars_t *out) {
+  if (!e || !b) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return align_download_locked(e, b, out);
+}
+
+int32_t trgt_align_e2e(trgt_engine_t *e, const trgt_seqs_t *backbones, const trgt_seqs_t *seqs,
+                       const uint32_t *group_seq_offsets, uint32_t n_groups, trgt_cigars_t *out) {
+  if (!e) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->one_align) e->one_align = new trgt_align_batch();
+  TRY(align_upload_into(e, e->one_align, backbones, seqs, group_seq_offsets, n_groups));
+  TRY(align_run_locked(e, e->one_align));
+  return align_download_locked(e, e->one_align, out);
+}
+
+// ------------------------------------------------------------------ phase B: edit distance ---
+
+int32_t trgt_edit_dist(trgt_engine_t *e, const trgt_seqs_t *seqs, const uint32_t *locus_seq_offsets, uint32_t n_loci,
+                       double *dists_out) {
+  if (!e) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  TRY(check_seqs(e, seqs, "seqs"));
+  if (n_loci && !locus_seq_offsets) return fail(e, TRGT_ERR_ARG, "locus_seq_offsets is null");
+  if (n_loci == 0) return 0;
+  if (locus_seq_offsets[0] != 0 || locus_seq_offsets[n_loci] != seqs->n) return fail(e, TRGT_ERR_ARG, "locus_seq_offsets must cover all sequences");
+  std::vector<unsigned long long> pair_off((size_t)n_loci + 1, 0);
+  for (uint32_t l = 0; l < n_loci; l++) {
+    if (locus_seq_offsets[l + 1] < locus_seq_offsets[l]) return fail(e, TRGT_ERR_ARG, "locus_seq_offsets not monotone");
+    const unsigned long long n = locus_seq_offsets[l + 1] - locus_seq_offsets[l];
+    pair_off[l + 1] = pair_off[l] + (n < 2 ? 0 : n * (n - 1) / 2);
+  }
+  const unsigned long long total = pair_off[n_loci];
+  if (total == 0) return 0;
+  if (!dists_out) return fail(e, TRGT_ERR_ARG, "dists_out is null");
+  CU(e, cudaSetDevice(e->device));
+  TRY(upload_seqs(e, seqs, e->d_ed[0], e->d_ed[1]));
+  TRY(h2d(e, e->d_ed[2], locus_seq_offsets, ((size_t)n_loci + 1) * sizeof(uint32_t)));
+  TRY(h2d(e, e->d_ed[3], pair_off.data(), pair_off.size() * sizeof(unsigned long long)));
+  TRY(dev_reserve(e, e->d_ed[4], (size_t)total * sizeof(double)));
+  {
+    int grid = 0;
+    TRY(persistent_grid(e, k_edit_dist, 128, 0, &grid));
+    if ((uint32_t)grid > n_loci) grid = (int)n_loci;
+    LaunchScope ls(e, "k_edit_dist");
+    k_edit_dist<<<grid, 128, 0, e->stream>>>((const uint8_t *)e->d_ed[0].p, (const uint64_t *)e->d_ed[1].p,
+                                             (const uint32_t *)e->d_ed[2].p, (const unsigned long long *)e->d_ed[3].p,
+                                             n_loci, (double *)e->d_ed[4].p);
+    TRY(check_launch(e, "k_edit_dist"));
+  }
+  CU(e, cudaMemcpyAsync(dists_out, e->d_ed[4].p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ phase C: HMM -----------
+
+struct trgt_hmm_batch {
+  uint32_t n_loci = 0, n_alleles = 0;
+  int want_paths = 0;
+  int S_max = 0, nb_max = 0, mbytes_max = 0;
+  size_t warp_bytes = 0;
+  DevBuf motifs, motif_off, locus_motif_off, alleles, allele_off, allele_locus, bp_off, mc_off;
+  DevBuf bp, mc, purity, n_spans, span_off, spans, path_len, path_off, paths, status;
+  std::vector<unsigned long long> h_bp_off, h_mc_off;
+  std::vector<std::pair<uint32_t, uint32_t>> waves;
+  // host results
+  std::vector<uint64_t> r_mc_off, r_span_off, r_path_off;
+  std::vector<uint32_t> r_mc, r_paths;
+  std::vector<trgt_motif_span_t> r_spans;
+  std::vector<double> r_purity;
+  std::vector<int32_t> r_status;
+  unsigned long long total_spans = 0, total_path = 0;
+  bool ran = false;
+};
+
+extern "C" {
+
+void trgt_hmm_free(trgt_engine_t *e, trgt_hmm_batch_t *b) {
+  if (!b) return;
+  if (e) {
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    if (e->one_hmm == b) e->one_hmm = nullptr;
+  }
+  DevBuf *all[] = {&b->motifs, &b->motif_off, &b->locus_motif_off, &b->alleles, &b->allele_off, &b->allele_locus,
+                   &b->bp_off, &b->mc_off, &b->bp, &b->mc, &b->purity, &b->n_spans, &b->span_off, &b->spans,
+                   &b->path_len, &b->path_off, &b->paths, &b->status};
+  for (auto *d : all) dev_free(*d);
+  delete b;
+}
+
+static int hmm_upload_into(trgt_engine_t *e, trgt_hmm_batch *b, const trgt_seqs_t *motifs,
+                           const uint32_t *locus_motif_offsets, uint32_t n_loci, const trgt_seqs_t *alleles,
+                           const uint32_t *allele_locus, int32_t want_paths) {
+  TRY(check_seqs(e, motifs, "motifs"));
+  TRY(check_seqs(e, alleles, "alleles"));
+  if (n_loci && !locus_motif_offsets) return fail(e, TRGT_ERR_ARG, "locus_motif_offsets is null");
+  if (alleles->n && !allele_locus) return fail(e, TRGT_ERR_ARG, "allele_locus is null");
+  if (alleles->n > 0x7fffffffull) return fail(e, TRGT_ERR_ARG, "too many alleles in one batch");
+  if (n_loci && (locus_motif_offsets[0] != 0 || locus_motif_offsets[n_loci] != motifs->n))
+    return fail(e, TRGT_ERR_ARG, "locus_motif_offsets must cover all motifs");
+  // per-locus model size
+  std::vector<uint32_t> locus_S(n_loci, 0), locus_mb(n_loci, 0);
+  int S_max = 7, nb_max = 1, mb_max = 0;
+  uint64_t len_max = 0;
+  for (uint32_t l = 0; l < n_loci; l++) {
+    if (locus_motif_offsets[l + 1] < locus_motif_offsets[l]) return fail(e, TRGT_ERR_ARG, "locus_motif_offsets not monotone");
+    uint64_t S = 7, mb = 0;
+    const uint32_t nm = locus_motif_offsets[l + 1] - locus_motif_offsets[l];
+    for (uint32_t m = locus_motif_offsets[l]; m < locus_motif_offsets[l + 1]; m++) {
+      const uint64_t n = motifs->offsets[m + 1] - motifs->offsets[m];
+      S += 3 * n + 1;
+      mb += n;
+      if (n > len_max) len_max = n;
+    }
+    if (S > 65535 || nm + 1 > 255) return fail(e, TRGT_ERR_ARG, "locus %u: model too large (%llu states, %u motifs)", l, (unsigned long long)S, nm);
+    locus_S[l] = (uint32_t)S;
+    locus_mb[l] = (uint32_t)mb;
+    if ((int)S > S_max) S_max = (int)S;
+    if ((int)nm + 1 > nb_max) nb_max = (int)nm + 1;
+    if ((int)mb > mb_max) mb_max = (int)mb;
+  }
+  const size_t n = alleles->n;
+  b->h_bp_off.assign(n + 1, 0);
+  b->h_mc_off.assign(n + 1, 0);
+  for (size_t a = 0; a < n; a++) {
+    const uint32_t l = allele_locus[a];
+    if (l >= n_loci) return fail(e, TRGT_ERR_ARG, "allele %zu: locus %u out of range", a, l);
+    const uint64_t L = alleles->offsets[a + 1] - alleles->offsets[a];
+    if (L > 0x3ffffff0ull) return fail(e, TRGT_ERR_ARG, "allele too long");
+    b->h_bp_off[a + 1] = b->h_bp_off[a] + (L ? (L + 2) * (unsigned long long)locus_S[l] : 0);
+    b->h_mc_off[a + 1] = b->h_mc_off[a] + (locus_motif_offsets[l + 1] - locus_motif_offsets[l]);
+  }
+  b->n_loci = n_loci;
+  b->n_alleles = (uint32_t)n;
+  b->want_paths = want_paths;
+  b->S_max = S_max;
+  b->nb_max = nb_max;
+  b->mbytes_max = mb_max;
+  b->warp_bytes = hmm_onchip_bytes(S_max, nb_max, mb_max);
+  b->ran = false;
+  if (b->warp_bytes * 4 > (size_t)e->smem_optin) return fail(e, TRGT_ERR_ARG, "HMM with %d states does not fit in shared memory", S_max);
+  // waves: consecutive alleles whose back-pointers fit the workspace budget
+  b->waves.clear();
+  {
+    size_t a0 = 0;
+    while (a0 < n) {
+      size_t a1 = a0 + 1;
+      while (a1 < n && b->h_bp_off[a1 + 1] - b->h_bp_off[a0] <= e->workspace_budget) a1++;
+      b->waves.push_back({(uint32_t)a0, (uint32_t)a1});
+      a0 = a1;
+    }
+  }
+  CU(e, cudaSetDevice(e->device));
+  // jump-in ln table
+  e->jump.ensure((int)len_max);
+  if (e->jump_uploaded_len != e->jump.lp.size() || !e->d_mm_lp.p) {
+    TRY(h2d(e, e->d_mm_off, e->jump.off.data(), e->jump.off.size() * sizeof(uint32_t)));
+    TRY(h2d(e, e->d_mm_lp, e->jump.lp.data(), e->jump.lp.size() * sizeof(double)));
+    CU(e, cudaStreamSynchronize(e->stream));
+    e->jump_uploaded_len = e->jump.lp.size();
+  }
+  TRY(upload_seqs(e, motifs, b->motifs, b->motif_off));
+  TRY(upload_seqs(e, alleles, b->alleles, b->allele_off));
+  static const uint32_t zero32[1] = {0};
+  TRY(h2d(e, b->locus_motif_off, n_loci ? locus_motif_offsets : zero32, ((size_t)n_loci + 1) * sizeof(uint32_t)));
+  TRY(h2d(e, b->allele_locus, allele_locus, n * sizeof(uint32_t)));
+  TRY(h2d(e, b->bp_off, b->h_bp_off.data(), (n + 1) * sizeof(unsigned long long)));
+  TRY(h2d(e, b->mc_off, b->h_mc_off.data(), (n + 1) * sizeof(unsigned long long)));
+  CU(e, cudaStreamSynchronize(e->stream));  // h_* vectors may be reallocated by the next upload
+  TRY(dev_reserve(e, b->mc, (size_t)(b->h_mc_off[n] + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->purity, (n + 1) * sizeof(double)));
+  TRY(dev_reserve(e, b->n_spans, (n + 2) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->span_off, (n + 2) * sizeof(unsigned long long)));
+  TRY(dev_reserve(e, b->status, (n + 1) * sizeof(int32_t)));
+  if (want_paths) {
+    TRY(dev_reserve(e, b->path_len, (n + 2) * sizeof(unsigned long long)));
+    TRY(dev_reserve(e, b->path_off, (n + 2) * sizeof(unsigned long long)));
+  }
+  size_t bp_need = 0;
+  for (auto &w : b->waves) {
+    const size_t bytes = (size_t)(b->h_bp_off[w.second] - b->h_bp_off[w.first]);
+    if (bytes > bp_need) bp_need = bytes;
+  }
+  TRY(dev_reserve(e, b->bp, bp_need + 16));
+  return 0;
+}
+
+int32_t trgt_hmm_upload(trgt_engine_t *e, const trgt_seqs_t *motifs, const uint32_t *locus_motif_offsets,
+                        uint32_t n_loci, const trgt_seqs_t *alleles, const uint32_t *allele_locus,
+                        int32_t want_paths, trgt_hmm_batch_t **out) {
+  if (!e || !out) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  *out = nullptr;
+  trgt_hmm_batch *b = new trgt_hmm_batch();
+  const int rc = hmm_upload_into(e, b, motifs, locus_motif_offsets, n_loci, alleles, allele_locus, want_paths);
+  if (rc != 0) {
+    trgt_hmm_free(nullptr, b);
+    return rc;
+  }
+  *out = b;
+  return 0;
+}
+
+// inclusive-to-exclusive helper for u64 path lengths: offsets[i] = sum of len[0..i)
+__global__ void k_scan_u64_serial(const unsigned long long *len, unsigned long long *off, uint32_t a0, uint32_t a1,
+                                  unsigned long long base) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long acc = base;
+    for (uint32_t a = a0; a < a1; a++) {
+      off[a] = acc;
+      acc += len[a];
+    }
+    off[a1] = acc;
+  }
+}
+
+__global__ void k_add_base_u64(unsigned long long *v, uint32_t a0, uint32_t a1, unsigned long long base) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t a = a0 + blockIdx.x * blockDim.x + threadIdx.x; a <= a1; a += gsz) v[a] += base;
+}
+
+static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
+  CU(e, cudaSetDevice(e->device));
+  b->ran = true;
+  b->total_spans = 0;
+  b->total_path = 0;
+  if (b->n_alleles == 0) return 0;
+  HmmBatch hb;
+  hb.motifs = (const uint8_t *)b->motifs.p;
+  hb.motif_off = (const uint64_t *)b->motif_off.p;
+  hb.locus_motif_off = (const uint32_t *)b->locus_motif_off.p;
+  hb.alleles = (const uint8_t *)b->alleles.p;
+  hb.allele_off = (const uint64_t *)b->allele_off.p;
+  hb.allele_locus = (const uint32_t *)b->allele_locus.p;
+  hb.bp_off = (const unsigned long long *)b->bp_off.p;
+  hb.mc_off = (const unsigned long long *)b->mc_off.p;
+  hb.mm_off = (const uint32_t *)e->d_mm_off.p;
+  hb.mm_lp = (const double *)e->d_mm_lp.p;
+  hb.c = e->hmm_consts;
+  hb.S_max = b->S_max;
+  hb.nb_max = b->nb_max;
+  hb.mbytes_max = b->mbytes_max;
+  hb.warp_bytes = b->warp_bytes;
+  const int block = 128, wpb = 4;
+  const size_t smem = b->warp_bytes * wpb;
+  int grid_v = 0, grid_e = 0;
+  TRY(persistent_grid(e, k_hmm_viterbi, block, smem, &grid_v));
+  TRY(persistent_grid(e, k_hmm_emit, block, smem, &grid_e));
+  unsigned long long span_base = 0, path_base = 0;
+  for (auto &w : b->waves) {
+    const uint32_t a0 = w.first, a1 = w.second, cnt = a1 - a0;
+    const uint32_t need = (cnt + wpb - 1) / wpb;
+    const unsigned long long bp_base = b->h_bp_off[a0];
+    {
+      LaunchScope ls(e, "k_hmm_viterbi");
+      const int grid = (uint32_t)grid_v > need ? (int)need : grid_v;
+      k_hmm_viterbi<<<grid, block, smem, e->stream>>>(hb, a0, a1, bp_base, (uint8_t *)b->bp.p, (uint32_t *)b->mc.p,
+                                                      (double *)b->purity.p, (uint32_t *)b->n_spans.p,
+                                                      b->want_paths ? (unsigned long long *)b->path_len.p : nullptr,
+                                                      (int32_t *)b->status.p);
+      TRY(check_launch(e, "k_hmm_viterbi"));
+    }
+    // span offsets of this wave: base + exclusive scan (n_spans[a1] is scratch and zeroed first)
+    CU(e, cudaMemsetAsync((uint32_t *)b->n_spans.p + a1, 0, sizeof(uint32_t), e->stream));
+    TRY(exclusive_scan_u32(e, (const uint32_t *)b->n_spans.p + a0, (unsigned long long *)b->span_off.p + a0, (size_t)cnt + 1));
+    if (span_base) {
+      LaunchScope ls(e, "k_add_base_u64");
+      k_add_base_u64<<<(cnt + 256) / 256, 256, 0, e->stream>>>((unsigned long long *)b->span_off.p, a0, a1, span_base);
+      TRY(check_launch(e, "k_add_base_u64"));
+    }
+    CU(e, cudaMemcpyAsync(&e->h_u64[0], (unsigned long long *)b->span_off.p + a1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    if (b->want_paths) {
+      LaunchScope ls(e, "k_scan_u64_serial");
+      k_scan_u64_serial<<<1, 32, 0, e->stream>>>((const unsigned long long *)b->path_len.p, (unsigned long long *)b->path_off.p, a0, a1, path_base);
+      TRY(check_launch(e, "k_scan_u64_serial"));
+      CU(e, cudaMemcpyAsync(&e->h_u64[1], (unsigned long long *)b->path_off.p + a1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CU(e, cudaStreamSynchronize(e->stream));
+    const unsigned long long span_end = e->h_u64[0];
+    const unsigned long long path_end = b->want_paths ? e->h_u64[1] : 0;
+    TRY(dev_reserve(e, b->spans, (size_t)(span_end + 1) * sizeof(trgt_motif_span_t), true));
+    if (b->want_paths) TRY(dev_reserve(e, b->paths, (size_t)(path_end + 1) * sizeof(uint32_t), true));
+    if (span_end > span_base || path_end > path_base) {
+      LaunchScope ls(e, "k_hmm_emit");
+      const int grid = (uint32_t)grid_e > need ? (int)need : grid_e;
+      k_hmm_emit<<<grid, block, smem, e->stream>>>(hb, a0, a1, bp_base, (const uint8_t *)b->bp.p,
+                                                   (const uint32_t *)b->n_spans.p,
+                                                   (const unsigned long long *)b->span_off.p,
+                                                   (trgt_motif_span_t *)b->spans.p,
+                                                   b->want_paths ? (const unsigned long long *)b->path_off.p : nullptr,
+                                                   b->want_paths ? (uint32_t *)b->paths.p : nullptr,
+                                                   (const int32_t *)b->status.p);
+      TRY(check_launch(e, "k_hmm_emit"));
+    }
+    span_base = span_end;
+    path_base = path_end;
+  }
+  b->total_spans = span_base;
+  b->total_path = path_base;
+  return 0;
+}
+
+int32_t trgt_hmm_run(trgt_engine_t *e, trgt_hmm_batch_t *b) {
+  if (!e || !b) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return hmm_run_locked(e, b);
+}
+
+static int hmm_download_locked(trgt_engine_t *e, trgt_hmm_batch *b, trgt_annotations_t *out) {
+  if (!out) return fail(e, TRGT_ERR_ARG, "out is null");
+  if (!b->ran) return fail(e, TRGT_ERR_ARG, "trgt_hmm_download before trgt_hmm_run");
+  CU(e, cudaSetDevice(e->device));
+  const size_t n = b->n_alleles;
+  b->r_mc_off.assign(b->h_mc_off.begin(), b->h_mc_off.end());
+  if (b->r_mc_off.empty()) b->r_mc_off.assign(1, 0);
+  b->r_mc.assign((size_t)b->r_mc_off[n], 0);
+  b->r_span_off.assign(n + 1, 0);
+  b->r_spans.resize((size_t)b->total_spans);
+  b->r_purity.assign(n, 0.0);
+  b->r_status.assign(n, 0);
+  b->r_path_off.assign(n + 1, 0);
+  b->r_paths.resize((size_t)b->total_path);
+  if (n) {
+    if (!b->r_mc.empty())
+      CU(e, cudaMemcpyAsync(b->r_mc.data(), b->mc.p, b->r_mc.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(b->r_span_off.data(), b->span_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    if (b->total_spans)
+      CU(e, cudaMemcpyAsync(b->r_spans.data(), b->spans.p, (size_t)b->total_spans * sizeof(trgt_motif_span_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(b->r_purity.data(), b->purity.p, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(b->r_status.data(), b->status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (b->want_paths) {
+      CU(e, cudaMemcpyAsync(b->r_path_off.data(), b->path_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+      if (b->total_path)
+        CU(e, cudaMemcpyAsync(b->r_paths.data(), b->paths.p, (size_t)b->total_path * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CU(e, cudaStreamSynchronize(e->stream));
+  }
+  out->n = n;
+  out->motif_count_offsets = b->r_mc_off.data();
+  out->motif_counts = b->r_mc.data();
+  out->span_offsets = b->r_span_off.data();
+  out->spans = b->r_spans.data();
+  out->purity = b->r_purity.data();
+  out->status = b->r_status.data();
+  out->path_offsets = b->want_paths ? b->r_path_off.data() : nullptr;
+  out->paths = b->want_paths ? b->r_paths.data() : nullptr;
+  return 0;
+}
+
+int32_t trgt_hmm_download(trgt_engine_t *e, trgt_hmm_batch_t *b, trgt_annotations_t *out) {
+  if (!e || !b) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return hmm_download_locked(e, b, out);
+}
+
+int32_t trgt_hmm_label(trgt_engine_t *e, const trgt_seqs_t *motifs, const uint32_t *locus_motif_offsets,
+                       uint32_t n_loci, const trgt_seqs_t *alleles, const uint32_t *allele_locus, int32_t want_paths,
+                       trgt_annotations_t *out) {
+  if (!e) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->one_hmm) e->one_hmm = new trgt_hmm_batch();
+  TRY(hmm_upload_into(e, e->one_hmm, motifs, locus_motif_offsets, n_loci, alleles, allele_locus, want_paths));
+  TRY(hmm_run_locked(e, e->one_hmm));
+  return hmm_download_locked(e, e->one_hmm, out);
+}
+
+void trgt_engine_set_workspace_budget(trgt_engine_t *e, size_t bytes) {
+  if (e && bytes >= ((size_t)1 << 20)) e->workspace_budget = bytes;
+}
+
+}  // extern "C"

@@ -342,11 +342,13 @@ struct HmmAnnot {
 // One reverse walk from (end, L+1) to start.  mc[nb-1] must be zeroed by the caller when non-null.
 // When spans_out is non-null the collapsed spans are written in forward order given their total
 // count n_total from a previous counting walk.  max_motif_len: tr.rs:468 passes 6.
-// path_out (optional): receives the state path in REVERSE order (Hmm::label reversed), up to
-// path_cap entries; *path_len gets the full length.
+// path_out (optional): receives the state path (Hmm::label).  With path_total == 0 it is written
+// in REVERSE order, up to path_cap entries; with path_total = the length found by a previous walk
+// it is written in forward order.  *path_len gets the full length.
 TRGT_HD HmmAnnot hmm_annotate(const HmmModel &m, const uint8_t *allele, int L, const uint8_t *bp,
                               int max_motif_len, uint32_t *mc, HmmSpan *spans_out, uint32_t n_total,
-                              uint32_t *path_out, uint64_t path_cap, uint64_t *path_len) {
+                              uint32_t *path_out, uint64_t path_cap, uint64_t path_total,
+                              uint64_t *path_len) {
   HmmAnnot out;
   out.purity = 0.0; out.n_spans = 0; out.status = 0;
   const int S = m.S;
@@ -361,7 +363,7 @@ TRGT_HD HmmAnnot hmm_annotate(const HmmModel &m, const uint8_t *allele, int L, c
   uint64_t steps = 0;
   while (st != 0) {
     if (++steps > max_steps) { out.status = -1; break; }
-    if (path_out && plen < path_cap) path_out[plen] = (uint32_t)st;
+    if (path_out && plen < path_cap) path_out[path_total ? path_total - 1 - plen : plen] = (uint32_t)st;
     plen++;
     const HmmRole r = hmm_role(m, st);
     bool emits = false;
@@ -422,7 +424,7 @@ TRGT_HD HmmAnnot hmm_annotate(const HmmModel &m, const uint8_t *allele, int L, c
     last = st;
     st = p;
   }
-  if (path_out && plen < path_cap) path_out[plen] = 0;
+  if (path_out && plen < path_cap) path_out[path_total ? path_total - 1 - plen : plen] = 0;
   plen++;
   if (path_len) *path_len = plen;
   if (have_p) {

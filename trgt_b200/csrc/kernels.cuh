@@ -1,0 +1,451 @@
+// kernels.cuh -- sm_100a kernels of the tandem-repeat DP engine (included by engine.cu only).
+//
+//   phase A  k_flank_scan      exact flank search           span_locater.rs:10-12
+//            k_wfa_score       WFA pass 1 (ring, no history) wfaligner.rs:503-528 (flank), :489 (e2e)
+//            k_wfa_trace       WFA pass 2 (cone + back-trace) -> count_matches / span / SAM CIGAR
+//            k_flank_combine   find_tr_spans combine rule   span_locater.rs:53-67
+//   phase B  k_wfa_score / k_wfa_trace in end-to-end mode, k_cigar_gather   utils/align.rs:14-28
+//            k_edit_dist       get_dist_matrix              genotype_cluster.rs:236-286
+//   phase C  k_hmm_viterbi, k_hmm_emit                      src/hmm/*, tr.rs:454-492
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/trgt_engine.h"
+#include "coop.h"
+#include "hmm_core.h"
+#include "wfa_core.h"
+
+namespace trgt {
+
+// ------------------------------------------------------------------ shared structs ------
+
+struct Counters {
+  unsigned int n_work;                  // flank: (read, side) pairs that missed the exact scan
+  unsigned int n_trace;                 // e2e: pairs with non-zero cost
+  unsigned long long max_trace_ints;    // largest pass-2 workspace any item needs
+  unsigned long long words_bound;       // upper bound on CIGAR words pass 2 will emit
+  unsigned long long pool_used;         // CIGAR words actually emitted by pass 2
+  unsigned int n_failed;                // items that ended with a non-OK status
+  unsigned int pad;
+};
+
+enum { WFA_MODE_FLANK = 0, WFA_MODE_E2E = 1 };
+
+// where the (pattern, text) of work item `id` lives
+struct WfaSrc {
+  int mode;
+  int x, oe, e;
+  // flank mode: id = 2 * read + side
+  const uint8_t *reads; const uint64_t *read_off; const uint32_t *read_locus;
+  const uint8_t *lp; const uint64_t *lp_off;
+  const uint8_t *rp; const uint64_t *rp_off;
+  // e2e mode: id = sequence index
+  const uint8_t *bb; const uint64_t *bb_off;
+  const uint8_t *seqs; const uint64_t *seq_off; const uint32_t *seq_group;
+};
+
+__device__ __forceinline__ WfaProb wfa_prob_of(const WfaSrc &s, uint32_t id) {
+  WfaProb pr;
+  pr.x = s.x; pr.oe = s.oe; pr.e = s.e;
+  if (s.mode == WFA_MODE_FLANK) {
+    const uint32_t r = id >> 1, side = id & 1u;
+    const uint32_t l = s.read_locus[r];
+    const uint8_t *pb = side ? s.rp : s.lp;
+    const uint64_t *po = side ? s.rp_off : s.lp_off;
+    pr.p = pb + po[l];
+    pr.P = (int)(po[l + 1] - po[l]);
+    pr.t = s.reads + s.read_off[r];
+    pr.T = (int)(s.read_off[r + 1] - s.read_off[r]);
+    pr.pbf = 0; pr.pef = 0; pr.tbf = pr.T; pr.tef = pr.T;  // span_locater.rs:17
+  } else {
+    const uint32_t gidx = s.seq_group[id];
+    pr.p = s.bb + s.bb_off[gidx];
+    pr.P = (int)(s.bb_off[gidx + 1] - s.bb_off[gidx]);
+    pr.t = s.seqs + s.seq_off[id];
+    pr.T = (int)(s.seq_off[id + 1] - s.seq_off[id]);
+    pr.pbf = pr.pef = pr.tbf = pr.tef = 0;
+  }
+  return pr;
+}
+
+// ------------------------------------------------------------------ helpers --------------
+
+// out[i] = group g for every i in [off[g], off[g+1])
+__global__ void k_expand_offsets(const uint32_t *__restrict__ off, uint32_t n_groups, uint32_t *__restrict__ out) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gsz)
+    for (uint32_t i = off[g]; i < off[g + 1]; i++) out[i] = g;
+}
+
+// ------------------------------------------------------------------ phase A: exact scan ---
+
+// One warp per read, both flanks.  Misses are appended to `work` as 2*read+side.
+__global__ void __launch_bounds__(256)
+k_flank_scan(WfaSrc src, uint32_t n_reads, trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work,
+             Counters *ctr) {
+  const WarpGroup g;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += warps) {
+    for (uint32_t side = 0; side < 2; side++) {
+      const WfaProb pr = wfa_prob_of(src, 2 * r + side);
+      int pos = -1;
+      if (pr.P > 0) pos = flank_scan(g, pr.p, pr.P, pr.t, pr.T);
+      if (g.lane() == 0) {
+        trgt_flank_hit_t h;
+        h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
+        if (pos >= 0) {
+          h.via = TRGT_VIA_EXACT; h.matches = pr.P; h.start = (uint32_t)pos; h.end = (uint32_t)(pos + pr.P);
+        } else if (pr.P > 0) {
+          const unsigned int slot = atomicAdd(&ctr->n_work, 1u);
+          work[slot] = 2 * r + side;
+        }
+        hits[2 * r + side] = h;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ WFA pass 1 -------------
+
+// Persistent groups (a CTA when BLOCK, else a warp) pull items; ring on chip when it fits.
+//   work == nullptr: items are 0..n_direct-1, else work[0..*n_work)
+//   ends[i]: result of the i-th item (position in the work list)
+template <bool BLOCK>
+__global__ void k_wfa_score(WfaSrc src, const uint32_t *__restrict__ work, const unsigned int *n_work_ptr,
+                            uint32_t n_direct, WfaEnd *__restrict__ ends, int *gring, size_t gring_stride,
+                            int smem_ring_ints, uint32_t *__restrict__ trace_work, uint32_t *__restrict__ cig_n,
+                            Counters *ctr) {
+  extern __shared__ int smem_i[];
+  const uint32_t n = work ? *n_work_ptr : n_direct;
+  uint32_t slot, n_slots;
+  int *my_smem;
+  int lane0;
+  if (BLOCK) {
+    slot = blockIdx.x; n_slots = gridDim.x;
+    my_smem = smem_i + 40;  // first 40 ints: BlockGroup scratch
+    lane0 = threadIdx.x == 0;
+  } else {
+    const uint32_t wib = threadIdx.x >> 5;
+    slot = blockIdx.x * (blockDim.x >> 5) + wib; n_slots = gridDim.x * (blockDim.x >> 5);
+    my_smem = smem_i + (size_t)wib * smem_ring_ints;
+    lane0 = (threadIdx.x & 31u) == 0;
+  }
+  for (uint32_t i = slot; i < n; i += n_slots) {
+    const uint32_t id = work ? work[i] : i;
+    const WfaProb pr = wfa_prob_of(src, id);
+    const size_t need = wfa_ring_ints(pr);
+    int *ring = (need <= (size_t)smem_ring_ints) ? my_smem : (gring ? gring + (size_t)slot * gring_stride : nullptr);
+    WfaEnd end;
+    if (ring == nullptr || (ring != my_smem && need > gring_stride)) {
+      end.status = TRGT_WFA_OOM; end.s = 0; end.k = 0; end.off = 0;
+    } else if (BLOCK) {
+      const BlockGroup g(smem_i);
+      end = wfa_score_ring(g, pr, ring, wfa_score_cap(pr));
+      __syncthreads();
+    } else {
+      const WarpGroup g;
+      end = wfa_score_ring(g, pr, ring, wfa_score_cap(pr));
+      __syncwarp();
+    }
+    if (lane0) {
+      ends[i] = end;
+      if (end.status != TRGT_WFA_OK) {
+        atomicAdd(&ctr->n_failed, 1u);
+        if (cig_n) cig_n[id] = 0;
+      } else if (src.mode == WFA_MODE_FLANK) {
+        atomicMax(&ctr->max_trace_ints, (unsigned long long)wfa_trace_ints(pr, end.s));
+      } else {
+        if (end.s == 0) {
+          cig_n[id] = pr.P > 0 ? 1u : 0u;  // a single '=' run
+        } else {
+          const unsigned int t = atomicAdd(&ctr->n_trace, 1u);
+          trace_work[t] = id;
+          const unsigned long long wb = 2ull * (unsigned long long)end.s + 8ull;
+          atomicAdd(&ctr->words_bound, wb);
+          atomicMax(&ctr->max_trace_ints, (unsigned long long)wfa_trace_ints(pr, end.s) + wb);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ WFA pass 2 -------------
+
+// One warp per item.  Workspace: shared memory when the cone fits, else the warp's global slot.
+//   flank mode: work[i] = 2*read+side, ends[i]           -> hits[work[i]]
+//   e2e mode:   work[i] = sequence id, ends[work[i]]     -> CIGAR words in `pool`, cig_off/cig_n[id]
+__global__ void __launch_bounds__(128)
+k_wfa_trace(WfaSrc src, const uint32_t *__restrict__ work, const unsigned int *n_work_ptr,
+            const WfaEnd *__restrict__ ends, int *gws, size_t gws_stride, int smem_ws_ints,
+            double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ pool,
+            unsigned long long pool_cap, unsigned long long *__restrict__ cig_off, uint32_t *__restrict__ cig_n,
+            int32_t *__restrict__ status, Counters *ctr) {
+  extern __shared__ int smem_i[];
+  const WarpGroup g;
+  const uint32_t n = *n_work_ptr;
+  const uint32_t wib = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + wib, n_slots = gridDim.x * (blockDim.x >> 5);
+  int *my_smem = smem_i + (size_t)wib * smem_ws_ints;
+  for (uint32_t i = slot; i < n; i += n_slots) {
+    const uint32_t id = work[i];
+    const WfaProb pr = wfa_prob_of(src, id);
+    const WfaEnd end = (src.mode == WFA_MODE_FLANK) ? ends[i] : ends[id];
+    if (end.status != TRGT_WFA_OK) {
+      if (g.lane() == 0) {
+        if (src.mode == WFA_MODE_FLANK) {
+          trgt_flank_hit_t h;
+          h.via = TRGT_VIA_NONE; h.matches = 0; h.score = INT_MIN; h.start = 0; h.end = 0;
+          hits[id] = h;
+        } else {
+          status[id] = end.status;
+        }
+      }
+      continue;
+    }
+    const size_t hist = wfa_trace_ints(pr, end.s);
+    const size_t words_cap = (src.mode == WFA_MODE_E2E) ? 2 * (size_t)end.s + 8 : 0;
+    const size_t need = hist + words_cap;
+    int *ws = (need <= (size_t)smem_ws_ints) ? my_smem : ((gws && need <= gws_stride) ? gws + (size_t)slot * gws_stride : nullptr);
+    int rc = ws ? wfa_trace_forward(g, pr, end.s, end.k, ws, hist) : TRGT_WFA_OOM;
+    __syncwarp();
+    if (g.lane() == 0) {
+      if (src.mode == WFA_MODE_FLANK) {
+        trgt_flank_hit_t h;
+        h.via = TRGT_VIA_NONE; h.matches = 0; h.score = INT_MIN; h.start = 0; h.end = 0;
+        if (rc == 0) {
+          WfaFlankSink sink(pr.T);
+          wfa_backtrace(pr, end.s, end.k, end.off, ws, sink);
+          h.matches = sink.matches;
+          h.score = -end.s;
+          // span_locater.rs:19-25, threshold :46
+          if ((double)sink.matches >= (double)pr.P * min_flank_id_frac) {
+            h.via = TRGT_VIA_WFA; h.start = (uint32_t)sink.ystart(); h.end = (uint32_t)sink.yend();
+          } else {
+            h.via = TRGT_VIA_WFA_REJECTED;
+          }
+        } else {
+          atomicAdd(&ctr->n_failed, 1u);
+        }
+        hits[id] = h;
+      } else {
+        uint32_t nw = 0;
+        if (rc == 0) {
+          WfaCigarSink sink((uint32_t *)(ws + hist), (uint32_t)words_cap);
+          wfa_backtrace(pr, end.s, end.k, end.off, ws, sink);
+          nw = sink.finish();
+          if (sink.overflow) { rc = TRGT_WFA_OOM; nw = 0; }
+        }
+        unsigned long long off = 0;
+        if (nw) {
+          off = atomicAdd(&ctr->pool_used, (unsigned long long)nw);
+          if (off + nw > pool_cap) { rc = TRGT_WFA_OOM; nw = 0; }
+        }
+        const uint32_t *wsrc = (const uint32_t *)(ws + hist);
+        for (uint32_t w = 0; w < nw; w++) pool[off + w] = wsrc[w];
+        cig_off[id] = off;
+        cig_n[id] = nw;
+        status[id] = rc;
+        if (rc != 0) atomicAdd(&ctr->n_failed, 1u);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// find_tr_spans combine rule, span_locater.rs:53-67
+__global__ void k_flank_combine(const trgt_flank_hit_t *__restrict__ hits, uint32_t n_reads,
+                                trgt_span_t *__restrict__ spans) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gsz) {
+    const trgt_flank_hit_t a = hits[2 * r], b = hits[2 * r + 1];
+    const bool fa = a.via == TRGT_VIA_EXACT || a.via == TRGT_VIA_WFA;
+    const bool fb = b.via == TRGT_VIA_EXACT || b.via == TRGT_VIA_WFA;
+    trgt_span_t s;
+    s.found = 0; s.start = 0; s.end = 0;
+    if (fa && fb && a.end <= b.start) { s.found = 1; s.start = a.end; s.end = b.start; }
+    spans[r] = s;
+  }
+}
+
+// CSR order gather of the CIGAR words: offsets = exclusive scan of cig_n
+__global__ void k_cigar_gather(WfaSrc src, uint32_t n_seqs, const WfaEnd *__restrict__ ends,
+                               const uint32_t *__restrict__ pool, const unsigned long long *__restrict__ cig_off,
+                               const uint32_t *__restrict__ cig_n, const unsigned long long *__restrict__ out_off,
+                               uint32_t *__restrict__ out_words, int32_t *__restrict__ scores,
+                               int32_t *__restrict__ status) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n_seqs; id += gsz) {
+    const WfaEnd end = ends[id];
+    const uint32_t n = cig_n[id];
+    const unsigned long long o = out_off[id];
+    if (end.status != TRGT_WFA_OK) {
+      scores[id] = INT_MIN;  // wfaligner.rs:1448: failed alignments report i32::MIN
+      status[id] = end.status;
+      continue;
+    }
+    scores[id] = -end.s;
+    if (end.s == 0) {
+      status[id] = 0;
+      if (n) {
+        const uint32_t P = (uint32_t)(src.bb_off[src.seq_group[id] + 1] - src.bb_off[src.seq_group[id]]);
+        out_words[o] = (P << 4) | 7u;
+      }
+    } else {
+      const unsigned long long po = cig_off[id];
+      for (uint32_t w = 0; w < n; w++) out_words[o + w] = pool[po + w];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ edit distance ---------
+
+// get_dist_matrix: one CTA per locus, threads stride the condensed pair index.
+__global__ void __launch_bounds__(128)
+k_edit_dist(const uint8_t *__restrict__ seqs, const uint64_t *__restrict__ seq_off,
+            const uint32_t *__restrict__ locus_seq_off, const unsigned long long *__restrict__ pair_off,
+            uint32_t n_loci, double *__restrict__ dists) {
+  for (uint32_t l = blockIdx.x; l < n_loci; l += gridDim.x) {
+    const uint32_t s0 = locus_seq_off[l];
+    const uint32_t n = locus_seq_off[l + 1] - s0;
+    if (n < 2) continue;
+    const unsigned long long base = pair_off[l];
+    const unsigned long long np = (unsigned long long)n * (n - 1) / 2;
+    for (unsigned long long q = threadIdx.x; q < np; q += blockDim.x) {
+      // invert q = i*n - i(i+1)/2 + (j-i-1)
+      const double nn = 2.0 * (double)n - 1.0;
+      long long i = (long long)floor((nn - sqrt(nn * nn - 8.0 * (double)q)) / 2.0);
+      if (i < 0) i = 0;
+      if (i > (long long)n - 2) i = (long long)n - 2;
+      while (i > 0 && (unsigned long long)i * n - (unsigned long long)i * (i + 1) / 2 > q) i--;
+      while ((unsigned long long)(i + 1) * n - (unsigned long long)(i + 1) * (i + 2) / 2 <= q) i++;
+      const unsigned long long row0 = (unsigned long long)i * n - (unsigned long long)i * (i + 1) / 2;
+      const uint32_t j = (uint32_t)(i + 1 + (long long)(q - row0));
+      const uint8_t *a = seqs + seq_off[s0 + i];
+      const uint8_t *b = seqs + seq_off[s0 + j];
+      const int la = (int)(seq_off[s0 + i + 1] - seq_off[s0 + i]);
+      const int lb = (int)(seq_off[s0 + j + 1] - seq_off[s0 + j]);
+      int d;
+      if ((unsigned long long)la * (unsigned long long)lb > 10000ull) {  // MAX_OPS, genotype_cluster.rs:237-243
+        d = la > lb ? la - lb : lb - la;
+      } else {
+        d = edit_distance_128(a, la, b, lb);
+      }
+      dists[base + q] = sqrt((double)d);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ phase C: HMM ------------
+
+struct HmmBatch {
+  const uint8_t *motifs; const uint64_t *motif_off;   // all motifs
+  const uint32_t *locus_motif_off;                     // [n_loci+1]
+  const uint8_t *alleles; const uint64_t *allele_off; // [n_alleles+1]
+  const uint32_t *allele_locus;
+  const unsigned long long *bp_off;                    // [n_alleles+1] into bp (relative to wave base)
+  const unsigned long long *mc_off;                    // [n_alleles+1] into mc
+  const uint32_t *mm_off; const double *mm_lp;         // jump-in ln table
+  HmmConsts c;
+  int S_max, nb_max, mbytes_max;
+  size_t warp_bytes;                                   // hmm_onchip_bytes(S_max, nb_max, mbytes_max)
+};
+
+struct HmmWarpMem {
+  double *sc0, *sc1;
+  uint32_t *moff, *mmoff;
+  uint16_t *n, *ms, *stblk;
+  uint8_t *bytes;
+};
+
+__device__ __forceinline__ HmmWarpMem hmm_carve(unsigned char *base, int S_max, int nb_max) {
+  HmmWarpMem w;
+  w.sc0 = (double *)base;
+  w.sc1 = w.sc0 + S_max;
+  w.moff = (uint32_t *)(w.sc1 + S_max);
+  w.mmoff = w.moff + nb_max;
+  w.n = (uint16_t *)(w.mmoff + nb_max);
+  w.ms = w.n + nb_max;
+  w.stblk = w.ms + nb_max;
+  w.bytes = (uint8_t *)(w.stblk + S_max);
+  return w;
+}
+
+// One warp per allele: model build, Viterbi (back-pointers to HBM), counting walk.
+__global__ void __launch_bounds__(128)
+k_hmm_viterbi(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, uint8_t *__restrict__ bp,
+              uint32_t *__restrict__ mc, double *__restrict__ purity, uint32_t *__restrict__ n_spans,
+              unsigned long long *__restrict__ path_len, int32_t *__restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_b[];
+  const WarpGroup g;
+  const uint32_t wib = threadIdx.x >> 5;
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  const HmmWarpMem wm = hmm_carve(smem_b + (size_t)wib * hb.warp_bytes, hb.S_max, hb.nb_max);
+  for (uint32_t a = a0 + blockIdx.x * (blockDim.x >> 5) + wib; a < a1; a += warps) {
+    const uint32_t l = hb.allele_locus[a];
+    const uint32_t m0 = hb.locus_motif_off[l];
+    const int nm = (int)(hb.locus_motif_off[l + 1] - m0);
+    const uint8_t *allele = hb.alleles + hb.allele_off[a];
+    const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
+    uint32_t *my_mc = mc + hb.mc_off[a];
+    for (int b = g.lane(); b < nm; b += 32) my_mc[b] = 0;
+    HmmModel model;
+    const int S = hmm_model_build(g, hb.motifs, hb.motif_off + m0, nm, hb.mm_off, wm.bytes, wm.moff, wm.mmoff,
+                                  wm.n, wm.ms, wm.stblk, &model);
+    if (S < 0 || L == 0) {
+      if (g.lane() == 0) {
+        purity[a] = nan("");  // purity.rs:7-9
+        n_spans[a] = 0;
+        if (path_len) path_len[a] = 0;
+        status[a] = S < 0 ? TRGT_ITEM_INVALID_BASE : 0;
+      }
+      __syncwarp();
+      continue;
+    }
+    uint8_t *my_bp = bp + (hb.bp_off[a] - bp_base);
+    hmm_viterbi(g, model, hb.c, hb.mm_lp, allele, L, wm.sc0, wm.sc1, my_bp);
+    __syncwarp();
+    if (g.lane() == 0) {
+      uint64_t plen = 0;
+      const HmmAnnot an = hmm_annotate(model, allele, L, my_bp, 6, my_mc, nullptr, 0, nullptr, 0, 0, &plen);
+      purity[a] = an.purity;
+      n_spans[a] = an.n_spans;
+      if (path_len) path_len[a] = plen;
+      status[a] = an.status < 0 ? TRGT_ERR_INTERNAL : 0;
+    }
+    __syncwarp();
+  }
+}
+
+// Second walk: writes the collapsed spans (and optionally the state path) at their CSR offsets.
+__global__ void __launch_bounds__(128)
+k_hmm_emit(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, const uint8_t *__restrict__ bp,
+           const uint32_t *__restrict__ n_spans, const unsigned long long *__restrict__ span_off,
+           trgt_motif_span_t *__restrict__ spans, const unsigned long long *__restrict__ path_off,
+           uint32_t *__restrict__ paths, const int32_t *__restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_b[];
+  const WarpGroup g;
+  const uint32_t wib = threadIdx.x >> 5;
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  const HmmWarpMem wm = hmm_carve(smem_b + (size_t)wib * hb.warp_bytes, hb.S_max, hb.nb_max);
+  for (uint32_t a = a0 + blockIdx.x * (blockDim.x >> 5) + wib; a < a1; a += warps) {
+    const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
+    const uint32_t ns = n_spans[a];
+    const unsigned long long plen = path_off ? path_off[a + 1] - path_off[a] : 0;
+    if (L == 0 || status[a] != 0 || (ns == 0 && plen == 0)) continue;  // warp-uniform
+    const uint32_t l = hb.allele_locus[a];
+    const uint32_t m0 = hb.locus_motif_off[l];
+    const int nm = (int)(hb.locus_motif_off[l + 1] - m0);
+    HmmModel model;
+    hmm_model_build(g, hb.motifs, hb.motif_off + m0, nm, hb.mm_off, wm.bytes, wm.moff, wm.mmoff, wm.n, wm.ms,
+                    wm.stblk, &model);
+    if (g.lane() == 0) {
+      const uint8_t *allele = hb.alleles + hb.allele_off[a];
+      hmm_annotate(model, allele, L, bp + (hb.bp_off[a] - bp_base), 6, nullptr,
+                   (HmmSpan *)(spans + span_off[a]), ns, plen ? paths + path_off[a] : nullptr, plen, plen, nullptr);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace trgt

@@ -1,0 +1,416 @@
+"""ctypes binding of libtrgt_b200.so (include/trgt_engine.h) plus a host-side mirror of the
+reference's operator surface for the hot path, so tests read like the reference's own:
+
+    find_tr_spans      src/trgt/genotype/span_locater.rs:32
+    align              src/utils/align.rs:14
+    get_dist_matrix    src/trgt/genotype/genotype_cluster.rs:250
+    label_with_hmm     src/trgt/workflows/tr.rs:454
+
+All compute happens in the CUDA library; there is no CPU fallback.  Importing this module does
+not need a GPU, creating an Engine does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _build
+
+VIA_NONE, VIA_EXACT, VIA_WFA, VIA_WFA_REJECTED = 0, 1, 2, 3
+
+
+class TrgtError(RuntimeError):
+    pass
+
+
+class _Seqs(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("offsets", C.c_void_p), ("n", C.c_uint64)]
+
+
+class _Scoring(C.Structure):
+    _fields_ = [("mismatch", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32)]
+
+
+class _Cigars(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("offsets", C.POINTER(C.c_uint64)), ("words", C.POINTER(C.c_uint32)),
+                ("scores", C.POINTER(C.c_int32)), ("status", C.POINTER(C.c_int32))]
+
+
+class _Annotations(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("motif_count_offsets", C.POINTER(C.c_uint64)),
+                ("motif_counts", C.POINTER(C.c_uint32)), ("span_offsets", C.POINTER(C.c_uint64)),
+                ("spans", C.POINTER(C.c_uint32)), ("purity", C.POINTER(C.c_double)),
+                ("status", C.POINTER(C.c_int32)), ("path_offsets", C.POINTER(C.c_uint64)),
+                ("paths", C.POINTER(C.c_uint32))]
+
+
+SPAN_DTYPE = np.dtype([("found", np.int32), ("start", np.uint32), ("end", np.uint32)])
+HIT_DTYPE = np.dtype([("via", np.int32), ("matches", np.int32), ("score", np.int32),
+                      ("start", np.uint32), ("end", np.uint32)])
+
+# every symbol include/trgt_engine.h declares
+EXPORTS = [
+    "trgt_engine_create", "trgt_engine_destroy", "trgt_engine_last_error", "trgt_last_create_error",
+    "trgt_engine_stream", "trgt_engine_sm_count", "trgt_engine_sync", "trgt_engine_set_workspace_budget",
+    "trgt_host_alloc", "trgt_host_free",
+    "trgt_flank_spans", "trgt_align_e2e", "trgt_edit_dist", "trgt_hmm_label",
+    "trgt_flank_upload", "trgt_flank_run", "trgt_flank_download", "trgt_flank_free", "trgt_flank_device_views",
+    "trgt_align_upload", "trgt_align_run", "trgt_align_download", "trgt_align_free",
+    "trgt_hmm_upload", "trgt_hmm_run", "trgt_hmm_download", "trgt_hmm_free",
+    "trgt_engine_set_profiling", "trgt_engine_reset_stats", "trgt_engine_kernel_count",
+    "trgt_engine_kernel_stat", "trgt_engine_launches",
+]
+
+_lib = None
+
+
+def load_library(build: bool = True):
+    """dlopen trgt_b200/libtrgt_b200.so (building it with nvcc first if it is missing or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build:
+        try:
+            _build.build()
+        except RuntimeError:
+            if not os.path.exists(_build.LIB_PATH):
+                raise
+    if not os.path.exists(_build.LIB_PATH):
+        raise TrgtError("libtrgt_b200.so is missing: run __graft_entry__.build(); there is no CPU fallback")
+    L = C.CDLL(_build.LIB_PATH)
+    vp, u32, i32, u64 = C.c_void_p, C.c_uint32, C.c_int32, C.c_uint64
+    L.trgt_engine_create.argtypes = [i32, C.POINTER(vp)]
+    L.trgt_engine_destroy.argtypes = [vp]
+    L.trgt_engine_destroy.restype = None
+    L.trgt_engine_last_error.argtypes = [vp]
+    L.trgt_engine_last_error.restype = C.c_char_p
+    L.trgt_last_create_error.restype = C.c_char_p
+    L.trgt_engine_stream.argtypes = [vp]
+    L.trgt_engine_stream.restype = vp
+    L.trgt_engine_sm_count.argtypes = [vp]
+    L.trgt_engine_sync.argtypes = [vp]
+    L.trgt_engine_set_workspace_budget.argtypes = [vp, C.c_size_t]
+    L.trgt_engine_set_workspace_budget.restype = None
+    L.trgt_host_alloc.argtypes = [C.c_size_t]
+    L.trgt_host_alloc.restype = vp
+    L.trgt_host_free.argtypes = [vp]
+    L.trgt_host_free.restype = None
+    sp = C.POINTER(_Seqs)
+    L.trgt_flank_spans.argtypes = [vp, sp, sp, sp, vp, u32, _Scoring, C.c_double, vp, vp]
+    L.trgt_flank_upload.argtypes = [vp, sp, sp, sp, vp, u32, _Scoring, C.c_double, C.POINTER(vp)]
+    L.trgt_flank_run.argtypes = [vp, vp]
+    L.trgt_flank_download.argtypes = [vp, vp, vp, vp]
+    L.trgt_flank_free.argtypes = [vp, vp]
+    L.trgt_flank_free.restype = None
+    L.trgt_flank_device_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                          C.POINTER(u32), C.POINTER(u32)]
+    L.trgt_align_e2e.argtypes = [vp, sp, sp, vp, u32, C.POINTER(_Cigars)]
+    L.trgt_align_upload.argtypes = [vp, sp, sp, vp, u32, C.POINTER(vp)]
+    L.trgt_align_run.argtypes = [vp, vp]
+    L.trgt_align_download.argtypes = [vp, vp, C.POINTER(_Cigars)]
+    L.trgt_align_free.argtypes = [vp, vp]
+    L.trgt_align_free.restype = None
+    L.trgt_edit_dist.argtypes = [vp, sp, vp, u32, vp]
+    L.trgt_hmm_label.argtypes = [vp, sp, vp, u32, sp, vp, i32, C.POINTER(_Annotations)]
+    L.trgt_hmm_upload.argtypes = [vp, sp, vp, u32, sp, vp, i32, C.POINTER(vp)]
+    L.trgt_hmm_run.argtypes = [vp, vp]
+    L.trgt_hmm_download.argtypes = [vp, vp, C.POINTER(_Annotations)]
+    L.trgt_hmm_free.argtypes = [vp, vp]
+    L.trgt_hmm_free.restype = None
+    L.trgt_engine_set_profiling.argtypes = [vp, i32]
+    L.trgt_engine_set_profiling.restype = None
+    L.trgt_engine_reset_stats.argtypes = [vp]
+    L.trgt_engine_reset_stats.restype = None
+    L.trgt_engine_kernel_count.argtypes = [vp]
+    L.trgt_engine_kernel_stat.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(u64), C.POINTER(C.c_double)]
+    L.trgt_engine_launches.argtypes = [vp]
+    L.trgt_engine_launches.restype = u64
+    _lib = L
+    return L
+
+
+# ------------------------------------------------------------------ packing helpers ------
+
+class PackedSeqs:
+    """CSR set of byte sequences: one contiguous uint8 buffer + uint64 offsets[n+1]."""
+
+    def __init__(self, data: np.ndarray, offsets: np.ndarray):
+        self.data = np.ascontiguousarray(data, dtype=np.uint8)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        assert self.offsets.ndim == 1 and self.offsets.size >= 1
+        self._c = _Seqs(self.data.ctypes.data if self.data.size else None, self.offsets.ctypes.data,
+                        self.offsets.size - 1)
+
+    @classmethod
+    def from_list(cls, seqs: Sequence[bytes]) -> "PackedSeqs":
+        offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        if seqs:
+            offs[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+        data = np.frombuffer(b"".join(bytes(s) for s in seqs), dtype=np.uint8)
+        return cls(data, offs)
+
+    def __len__(self):
+        return self.offsets.size - 1
+
+    def get(self, i: int) -> bytes:
+        return self.data[int(self.offsets[i]):int(self.offsets[i + 1])].tobytes()
+
+    def ref(self):
+        return C.byref(self._c)
+
+
+def _group_offsets(groups: Sequence[Sequence[bytes]]) -> np.ndarray:
+    offs = np.zeros(len(groups) + 1, dtype=np.uint32)
+    if groups:
+        offs[1:] = np.cumsum([len(g) for g in groups], dtype=np.uint64).astype(np.uint32)
+    return offs
+
+
+def decode_sam_cigar(words: Sequence[int]) -> List[Tuple[int, str]]:
+    """WFAligner::decode_sam_cigar (src/wfaligner.rs:961-984)"""
+    tab = "MIDNSHP=X"
+    return [(int(w) >> 4, tab[int(w) & 0xF]) for w in words]
+
+
+@dataclass
+class Annotation:
+    """src/hmm/spans.rs:21-25"""
+    labels: Optional[List[Tuple[int, int, int]]]   # (motif_index, start, end) or None
+    motif_counts: List[int]
+    purity: float
+
+
+@dataclass
+class CigarBatch:
+    offsets: np.ndarray   # uint64 [n+1]
+    words: np.ndarray     # uint32
+    scores: np.ndarray    # int32, -cost
+    status: np.ndarray    # int32
+
+    def cigar(self, i: int) -> List[int]:
+        return self.words[int(self.offsets[i]):int(self.offsets[i + 1])].tolist()
+
+
+@dataclass
+class AnnotationBatch:
+    motif_count_offsets: np.ndarray
+    motif_counts: np.ndarray
+    span_offsets: np.ndarray
+    spans: np.ndarray        # uint32 [n_spans, 3]
+    purity: np.ndarray
+    status: np.ndarray
+    path_offsets: Optional[np.ndarray] = None
+    paths: Optional[np.ndarray] = None
+
+    def annotation(self, i: int) -> Annotation:
+        mc = self.motif_counts[int(self.motif_count_offsets[i]):int(self.motif_count_offsets[i + 1])].tolist()
+        sp = self.spans[int(self.span_offsets[i]):int(self.span_offsets[i + 1])]
+        labels = [tuple(int(v) for v in row) for row in sp] or None
+        return Annotation(labels, mc, float(self.purity[i]))
+
+    def path(self, i: int) -> List[int]:
+        return self.paths[int(self.path_offsets[i]):int(self.path_offsets[i + 1])].tolist()
+
+
+def _np_from(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).copy()
+
+
+class Engine:
+    """One engine per GPU (trgt_engine_t)."""
+
+    def __init__(self, device: int = 0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.trgt_engine_create(device, C.byref(h))
+        if rc != 0:
+            raise TrgtError(f"trgt_engine_create({device}) failed rc={rc}: "
+                            f"{self._L.trgt_last_create_error().decode()}")
+        self._h = h
+        self.device = device
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.trgt_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise TrgtError(f"{what} failed rc={rc}: {self._L.trgt_engine_last_error(self._h).decode()}")
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def lib(self):
+        return self._L
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self._L.trgt_engine_stream(self._h) or 0)
+
+    @property
+    def sm_count(self) -> int:
+        return self._L.trgt_engine_sm_count(self._h)
+
+    def sync(self):
+        self._check(self._L.trgt_engine_sync(self._h), "trgt_engine_sync")
+
+    def set_workspace_budget(self, nbytes: int):
+        self._L.trgt_engine_set_workspace_budget(self._h, nbytes)
+
+    # -- instrumentation ------------------------------------------------------------------
+    def set_profiling(self, on: bool):
+        self._L.trgt_engine_set_profiling(self._h, int(on))
+
+    def reset_stats(self):
+        self._L.trgt_engine_reset_stats(self._h)
+
+    def launches(self) -> int:
+        return int(self._L.trgt_engine_launches(self._h))
+
+    def kernel_stats(self):
+        out = {}
+        for i in range(self._L.trgt_engine_kernel_count(self._h)):
+            name, n, ms = C.c_char_p(), C.c_uint64(), C.c_double()
+            self._L.trgt_engine_kernel_stat(self._h, i, C.byref(name), C.byref(n), C.byref(ms))
+            out[name.value.decode()] = (int(n.value), float(ms.value))
+        return out
+
+    # -- phase A ---------------------------------------------------------------------------
+    def flank_spans_packed(self, left: PackedSeqs, right: PackedSeqs, reads: PackedSeqs,
+                           locus_read_offsets: np.ndarray, scoring=(2, 5, 1), min_flank_id_frac: float = 0.7,
+                           want_hits: bool = True, spans_out: Optional[np.ndarray] = None,
+                           hits_out: Optional[np.ndarray] = None):
+        """trgt_flank_spans on packed inputs -> (spans[n_reads], hits[2*n_reads] or None)"""
+        lro = np.ascontiguousarray(locus_read_offsets, dtype=np.uint32)
+        n_reads = len(reads)
+        spans = spans_out if spans_out is not None else np.zeros(n_reads, dtype=SPAN_DTYPE)
+        hits = hits_out if hits_out is not None else (np.zeros(2 * n_reads, dtype=HIT_DTYPE) if want_hits else None)
+        rc = self._L.trgt_flank_spans(self._h, left.ref(), right.ref(), reads.ref(), lro.ctypes.data, len(left),
+                                      _Scoring(*scoring), float(min_flank_id_frac), spans.ctypes.data,
+                                      hits.ctypes.data if hits is not None else None)
+        self._check(rc, "trgt_flank_spans")
+        return spans, hits
+
+    def find_tr_spans(self, loci: Sequence[Tuple[bytes, bytes, Sequence[bytes]]], search_flank_len: int = 250,
+                      min_flank_id_frac: float = 0.7, scoring=(2, 5, 1), return_hits: bool = False):
+        """find_tr_spans (span_locater.rs:32-68) for many loci: loci = [(lf, rf, reads)].
+        -> per locus a list of Optional[(start, end)]"""
+        left = PackedSeqs.from_list([lf[len(lf) - search_flank_len:] for lf, _, _ in loci])
+        right = PackedSeqs.from_list([rf[:search_flank_len] for _, rf, _ in loci])
+        reads = PackedSeqs.from_list([r for _, _, rs in loci for r in rs])
+        lro = _group_offsets([rs for _, _, rs in loci])
+        spans, hits = self.flank_spans_packed(left, right, reads, lro, scoring, min_flank_id_frac)
+        out, k = [], 0
+        for _, _, rs in loci:
+            cur = []
+            for _ in rs:
+                s = spans[k]
+                cur.append((int(s["start"]), int(s["end"])) if s["found"] else None)
+                k += 1
+            out.append(cur)
+        return (out, hits) if return_hits else out
+
+    # -- phase B ---------------------------------------------------------------------------
+    def align_packed(self, backbones: PackedSeqs, seqs: PackedSeqs, group_seq_offsets: np.ndarray) -> CigarBatch:
+        gso = np.ascontiguousarray(group_seq_offsets, dtype=np.uint32)
+        out = _Cigars()
+        rc = self._L.trgt_align_e2e(self._h, backbones.ref(), seqs.ref(), gso.ctypes.data, len(backbones), C.byref(out))
+        self._check(rc, "trgt_align_e2e")
+        n = int(out.n)
+        offs = _np_from(out.offsets, n + 1, np.uint64)
+        total = int(offs[n]) if n else 0
+        return CigarBatch(offs, _np_from(out.words, total, np.uint32), _np_from(out.scores, n, np.int32),
+                          _np_from(out.status, n, np.int32))
+
+    def align(self, groups: Sequence[Tuple[bytes, Sequence[bytes]]]) -> List[List[List[Tuple[int, str]]]]:
+        """utils::align (src/utils/align.rs:14-28) for many (backbone, seqs) groups."""
+        bb = PackedSeqs.from_list([b for b, _ in groups])
+        sq = PackedSeqs.from_list([s for _, ss in groups for s in ss])
+        res = self.align_packed(bb, sq, _group_offsets([ss for _, ss in groups]))
+        out, k = [], 0
+        for _, ss in groups:
+            cur = []
+            for _ in ss:
+                cur.append(decode_sam_cigar(res.cigar(k)))
+                k += 1
+            out.append(cur)
+        return out
+
+    def edit_dist_packed(self, seqs: PackedSeqs, locus_seq_offsets: np.ndarray) -> np.ndarray:
+        lso = np.ascontiguousarray(locus_seq_offsets, dtype=np.uint32)
+        n = np.diff(lso.astype(np.int64))
+        total = int((n * (n - 1) // 2).clip(min=0).sum())
+        out = np.zeros(total, dtype=np.float64)
+        rc = self._L.trgt_edit_dist(self._h, seqs.ref(), lso.ctypes.data, lso.size - 1, out.ctypes.data)
+        self._check(rc, "trgt_edit_dist")
+        return out
+
+    def get_dist_matrix(self, loci_trs: Sequence[Sequence[bytes]]) -> List[List[float]]:
+        """get_dist_matrix (genotype_cluster.rs:250-286) for many loci -> condensed upper triangles."""
+        sq = PackedSeqs.from_list([s for trs in loci_trs for s in trs])
+        flat = self.edit_dist_packed(sq, _group_offsets(loci_trs))
+        out, k = [], 0
+        for trs in loci_trs:
+            n = len(trs)
+            m = n * (n - 1) // 2 if n >= 2 else 0
+            out.append(flat[k:k + m].tolist())
+            k += m
+        return out
+
+    # -- phase C ---------------------------------------------------------------------------
+    def hmm_label_packed(self, motifs: PackedSeqs, locus_motif_offsets: np.ndarray, alleles: PackedSeqs,
+                         allele_locus: np.ndarray, want_paths: bool = False) -> AnnotationBatch:
+        lmo = np.ascontiguousarray(locus_motif_offsets, dtype=np.uint32)
+        al = np.ascontiguousarray(allele_locus, dtype=np.uint32)
+        out = _Annotations()
+        rc = self._L.trgt_hmm_label(self._h, motifs.ref(), lmo.ctypes.data, lmo.size - 1, alleles.ref(),
+                                    al.ctypes.data if al.size else None, int(want_paths), C.byref(out))
+        self._check(rc, "trgt_hmm_label")
+        n = int(out.n)
+        mco = _np_from(out.motif_count_offsets, n + 1, np.uint64)
+        so = _np_from(out.span_offsets, n + 1, np.uint64)
+        n_mc = int(mco[n]) if n else 0
+        n_sp = int(so[n]) if n else 0
+        spans = _np_from(out.spans, 3 * n_sp, np.uint32).reshape(-1, 3)
+        res = AnnotationBatch(mco, _np_from(out.motif_counts, n_mc, np.uint32), so, spans,
+                              _np_from(out.purity, n, np.float64), _np_from(out.status, n, np.int32))
+        if want_paths:
+            po = _np_from(out.path_offsets, n + 1, np.uint64)
+            res.path_offsets = po
+            res.paths = _np_from(out.paths, int(po[n]) if n else 0, np.uint32)
+        return res
+
+    def label_with_hmm(self, loci: Sequence[Tuple[Sequence[bytes], Sequence[bytes]]]) -> List[List[Annotation]]:
+        """label_with_hmm (tr.rs:454-492) for many loci: loci = [(motifs, allele_seqs)]."""
+        motifs = PackedSeqs.from_list([m for ms, _ in loci for m in ms])
+        lmo = _group_offsets([ms for ms, _ in loci])
+        alleles = PackedSeqs.from_list([a for _, als in loci for a in als])
+        al = np.array([i for i, (_, als) in enumerate(loci) for _ in als], dtype=np.uint32)
+        res = self.hmm_label_packed(motifs, lmo, alleles, al)
+        bad = np.nonzero(res.status)[0]
+        if bad.size:
+            raise TrgtError(f"trgt_hmm_label: allele {int(bad[0])} failed with status {int(res.status[bad[0]])}")
+        out, k = [], 0
+        for _, als in loci:
+            cur = []
+            for _ in als:
+                cur.append(res.annotation(k))
+                k += 1
+            out.append(cur)
+        return out
