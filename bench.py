@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- loci/sec of the hot path of `trgt genotype` (flank location + consensus alignment +
+motif HMM) on synthetic 30x HiFi reads, BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W            this repo's CUDA engine (C ABI)
+    python bench.py --impl reference --steps K --warmup W    the reference-equivalent CPU path
+                                                             (oracle port: no rustc/cargo in the image)
+
+One "step" = one pass of phases A+B+C over this rank's shard of the catalog.  Workload at N GPUs: the
+Adotto-scale genome-wide synthetic catalog of BASELINE config 4, 125 000 loci per GPU (1 M loci at 8
+GPUs), 30 reads per locus; loci are independent, so ranks shard by locus with no data-path collective
+(weak scaling) and one gather of per-locus records at the end of each end-to-end step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "loci/sec (genome-wide synthetic catalog, 30x HiFi; phases A+B+C of trgt genotype)"
+UNIT = "loci/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--loci", type=int, default=125000, help="loci per GPU (125000 x 8 = the 1M-locus catalog)")
+    ap.add_argument("--depth", type=int, default=30)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload_config(args, n_gpus: int) -> dict:
+    return {
+        "workload": f"Adotto-scale genome-wide synthetic catalog shard (BASELINE config 4): {args.loci} loci/GPU x "
+                    f"{n_gpus} GPU, {args.depth}x HiFi, clipped reads = 500 bp + allele + 500 bp, 250-bp flank pieces, "
+                    "2-6 bp motifs (57/8/25/7/2 %), TR length median 24 bp; sub/ins/del 2e-4/4e-4/4e-4 per base",
+        "loci_per_gpu": args.loci, "depth": args.depth, "scoring": [2, 5, 1], "min_flank_id_frac": 0.7,
+        "parallelism": f"locus shards x{n_gpus}, no data-path collective; one gather of per-locus records per e2e step",
+        "l2": "inputs (~3.9 GB of reads per GPU) are larger than the 126 MB L2; no explicit flush",
+    }
+
+
+# ------------------------------------------------------------------ clocks -----------------
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference arm ------------
+
+def cpu_pass_rate(w, n_threads: int, seconds: float, max_loci: int):
+    """Time the oracle pass on a bounded head of the workload sized for ~`seconds`.  -> (loci/s, n, dt)"""
+    from oracle import oracle as orc
+    from trgt_b200.pipeline import oracle_pass
+    probe = min(max_loci, max(64, 16 * n_threads))
+    t0 = time.perf_counter()
+    oracle_pass(orc, w.head(probe), n_threads)
+    dt = time.perf_counter() - t0
+    rate = probe / dt
+    n = int(min(max_loci, max(probe, rate * seconds)))
+    t0 = time.perf_counter()
+    ref = oracle_pass(orc, w.head(n), n_threads)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt, ref
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    from trgt_b200 import workload
+    from trgt_b200.pipeline import oracle_pass
+    cores = host_cores()
+    total = max(1, args.steps + args.warmup)
+    per_step = max(1.0, min(8.0, 150.0 / total))
+    # size the per-step sample with a probe
+    w0 = workload.generate(min(args.loci, max(64, 16 * cores)), args.depth)
+    t0 = time.perf_counter()
+    oracle_pass(orc, w0, cores)
+    rate = w0.n_loci / (time.perf_counter() - t0)
+    n = int(min(args.loci, max(w0.n_loci, rate * per_step)))
+    w = workload.generate(n, args.depth)
+    for _ in range(args.warmup):
+        oracle_pass(orc, w, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_pass(orc, w, cores)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = n / dt
+    cfg = workload_config(args, args.gpus)
+    sample = f"first {n} loci of the shard per step ({n * args.depth} reads), all host cores"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32 wavefront offsets + f64 Viterbi", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference-equivalent C restatement (oracle/): the Rust reference cannot be built here (no cargo/rustc, "
+                "WFA2-lib and htslib un-vendored); one task per locus over a pthread pool as the reference's rayon pool",
+    }))
+
+
+# ------------------------------------------------------------------ roofline -----------------
+
+def kernel_bytes(name: str, w, hp, res) -> float | None:
+    """Algorithmic bytes one launch of `name` must move for this workload ('Roofline')."""
+    P = 250
+    n_reads = w.n_reads
+    read_bytes = float(w.reads.data.nbytes)
+    if name == "k_flank_scan":
+        return read_bytes + 2.0 * P * w.n_loci + 2 * 20.0 * n_reads + 8.0 * n_reads
+    n_wfa = hp.n_wfa()
+    mean_t = read_bytes / max(1, n_reads)
+    if name == "k_wfa_score_block":
+        return n_wfa * (P + mean_t + 16.0 + 4.0)
+    if name == "k_wfa_trace":
+        return n_wfa * (2.0 * P + 20.0 + 16.0 + 4.0) + (len(res.glue.seqs) * 0.0)
+    if name == "k_hmm_viterbi":
+        a = res.annotations
+        L = np.diff(res.glue.backbones.offsets.astype(np.int64)).astype(np.float64)
+        nm = np.diff(w.locus_motif_off.astype(np.int64))[res.glue.group_locus]
+        mlen = np.diff(w.motifs.offsets.astype(np.int64))
+        # one motif per locus in this catalog: S = 7 + 3n + 1
+        first = w.locus_motif_off[:-1][res.glue.group_locus]
+        S = 7.0 + 3.0 * mlen[first] + 1.0
+        return float(((L + 2) * (1.0 + S) + 3.0 * (L + 2) + 4.0 * nm + 8.0 + 12.0).sum())
+    if name in ("k_wfa_score_warp",):
+        g = res.glue
+        return float(g.seqs.data.nbytes + np.diff(g.backbones.offsets.astype(np.int64))[
+            np.repeat(np.arange(len(g.backbones)), np.diff(g.group_seq_off.astype(np.int64)))].sum() + 16.0 * len(g.seqs))
+    return None
+
+
+# ------------------------------------------------------------------ main arm -----------------
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    import trgt_b200
+    from trgt_b200 import workload
+    from trgt_b200.pipeline import HotPath, compare_with_oracle
+
+    eng = trgt_b200.Engine(device=local_rank)  # fails loudly without the CUDA library / a GPU
+    stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.sync()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    t_gen = time.perf_counter()
+    w = workload.generate(args.loci, args.depth, locus_begin=rank * args.loci, alloc_reads=eng.pinned_array,
+                          name="genome-wide-synthetic")
+    t_gen = time.perf_counter() - t_gen
+    hp = HotPath(eng, w, want_hits=False, pinned_outputs=True)
+
+    # ---- warm-up: end-to-end passes (also builds the resident batches) ----
+    res = None
+    for _ in range(max(1, args.warmup)):
+        res = hp.run_e2e()
+    hp.prepare_resident()
+    for _ in range(max(1, args.warmup)):
+        hp.run_resident()
+
+    # ---- `value`: resident inputs, device-timed, per-kernel events on ----
+    eng.reset_stats()
+    eng.set_profiling(True)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    launches0 = eng.launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        hp.run_resident(sync=False)
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1) / max(1, args.steps)
+    launches = (eng.launches() - launches0) // max(1, args.steps)
+    stats = eng.kernel_stats()
+    eng.set_profiling(False)
+    res_resident = hp.download_resident()
+    dev_ms = max_over_ranks(dev_ms)
+    value = args.loci * world / (dev_ms * 1e-3)
+
+    # ---- `e2e`: host buffers through the C ABI, host<->device copies and host glue inside ----
+    def gather_records(r):
+        if world == 1:
+            return 0
+        a = r.annotations
+        payload = np.concatenate([a.motif_counts.view(np.uint8), a.spans.reshape(-1).view(np.uint8),
+                                  a.purity.view(np.uint8), r.glue.backbones.data,
+                                  r.glue.backbones.offsets.view(np.uint8)])
+        t = torch.from_numpy(payload).to(dev, non_blocking=False)
+        size = torch.tensor([t.numel()], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(size) for _ in range(world)]
+        dist.all_gather(sizes, size)
+        mx = int(max(int(s.item()) for s in sizes))
+        pad = torch.zeros(mx, dtype=torch.uint8, device=dev)
+        pad[:t.numel()] = t
+        out = [torch.empty(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, out, dst=0)
+        if rank == 0:
+            host = [o[:int(s.item())].cpu() for o, s in zip(out, sizes)]
+            return sum(h.numel() for h in host)
+        return 0
+
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = hp.run_e2e()
+        gather_records(res)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / max(1, args.steps)
+    clk = clocks.stop()
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = args.loci * world / e2e_s
+    h2d = hp.h2d_bytes(res.glue)
+    d2h = hp.d2h_bytes(res)
+
+    # the two paths must agree with each other on the full shard
+    assert np.array_equal(res.spans, res_resident.spans), "e2e and resident spans differ"
+    assert np.array_equal(res.cigars.words, res_resident.cigars.words), "e2e and resident CIGARs differ"
+    assert np.array_equal(res.annotations.spans, res_resident.annotations.spans)
+    assert np.array_equal(res.annotations.motif_counts, res_resident.annotations.motif_counts)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    kernels = {}
+    for name, (n, ms) in stats.items():
+        per = ms / max(1, n)
+        b = kernel_bytes(name, w, hp, res_resident)
+        kernels[name] = {"launches_per_step": n / max(1, args.steps), "ms_per_launch": per,
+                         "share": None, "algorithmic_bytes": b,
+                         "achieved_gbs": (b / (per * 1e-3) / 1e9) if (b and per > 0) else None}
+    tot_ms = sum(v["ms_per_launch"] * v["launches_per_step"] for v in kernels.values())
+    for v in kernels.values():
+        v["share"] = v["ms_per_launch"] * v["launches_per_step"] / tot_ms if tot_ms else None
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"])
+    d = kernels[dom]
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except OSError:
+        pass
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": (d["achieved_gbs"] / peak) if d["achieved_gbs"] else None, "traffic": traffic,
+                "peak_source": peak_kind, "ms_per_launch": d["ms_per_launch"], "share_of_step": d["share"],
+                "algorithmic_bytes_per_launch": d["algorithmic_bytes"]}
+
+    # ---- CPU baseline + parity on a bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        rate, n, dt, ref = cpu_pass_rate(w, cores, args.cpu_seconds, args.loci)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {n} loci of the shard ({n * args.depth} reads), one pass in {dt:.1f} s, all host cores"}
+        small = HotPath(eng, w.head(n), want_hits=False, pinned_outputs=False)
+        compare_with_oracle(small.run_e2e(), ref)
+        parity = {"checked_loci": n, "result": "bit-exact vs oracle (spans, CIGARs, scores, MC, MS, AP)"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32 wavefront offsets + f64 Viterbi", "data": "synthetic",
+        "config": workload_config(args, world), "clocks": clk, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "kernels": kernels,
+        "wfa_fallback_pairs": hp.n_wfa(), "workload_gen_s": t_gen,
+    }
+    print(json.dumps(out))
+    hp.free_resident()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -54,25 +54,6 @@ class _OptSpan(C.Structure):
     _fields_ = [("found", C.c_int32), ("start", C.c_uint32), ("end", C.c_uint32)]
 
 
-class Batch(C.Structure):
-    _fields_ = [
-        ("n_loci", C.c_uint32),
-        ("left_pieces", C.c_void_p), ("left_off", C.c_void_p),
-        ("right_pieces", C.c_void_p), ("right_off", C.c_void_p),
-        ("motifs", C.c_void_p), ("motif_off", C.c_void_p),
-        ("locus_motif_off", C.c_void_p),
-        ("reads", C.c_void_p), ("read_off", C.c_void_p),
-        ("locus_read_off", C.c_void_p),
-        ("read_hap", C.c_void_p),
-        ("x", C.c_int), ("o", C.c_int), ("e", C.c_int),
-        ("min_flank_id_frac", C.c_double),
-    ]
-
-
-class BatchOut(C.Structure):
-    _fields_ = [("spans", C.c_void_p), ("checksum", C.c_void_p)]
-
-
 _lib = None
 
 
@@ -130,8 +111,13 @@ def lib():
                                           C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(C.c_int)]
         L.tro_get_dist.restype = C.c_double
         L.tro_get_dist.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
-        L.tro_process_loci.argtypes = [C.POINTER(Batch), C.c_uint32, C.c_uint32,
-                                       C.POINTER(BatchOut)]
+        vp = C.c_void_p
+        L.tro_flank_batch.argtypes = [vp] * 7 + [C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, C.c_int]
+        L.tro_align_batch.argtypes = [vp] * 5 + [C.c_uint32, vp, C.POINTER(vp), vp, C.c_int]
+        L.tro_hmm_batch.argtypes = [vp] * 3 + [C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, vp, C.POINTER(vp),
+                                    vp, vp, C.c_int]
+        L.tro_free.argtypes = [vp]
+        L.tro_free.restype = None
         _lib = L
     return _lib
 
@@ -358,3 +344,70 @@ def get_dist_matrix(trs: Sequence[bytes]) -> List[float]:
     """genotype_cluster.rs:250-286 (condensed upper triangle)"""
     n = len(trs)
     return [get_dist(trs[i], trs[j]) for i in range(n) for j in range(i + 1, n)]
+
+
+# ------------------------------------------------- batched drivers (numpy) --
+
+def _np():
+    import numpy as np
+    return np
+
+
+def flank_batch(left, right, reads, locus_read_off, scoring=(2, 5, 1), min_flank_id_frac=0.7,
+                n_threads: int = 1, want_hits: bool = True):
+    """tro_flank_batch on CSR sets (objects with .data uint8 / .offsets uint64 numpy arrays).
+    -> (spans structured array (found,start,end), hits structured array or None)"""
+    np = _np()
+    lro = np.ascontiguousarray(locus_read_off, dtype=np.uint32)
+    n_reads = reads.offsets.size - 1
+    spans = np.zeros(n_reads, dtype=np.dtype([("found", np.int32), ("start", np.uint32), ("end", np.uint32)]))
+    hits = np.zeros(2 * n_reads, dtype=np.dtype([("via", np.int32), ("matches", np.int32), ("score", np.int32),
+                                                 ("start", np.uint32), ("end", np.uint32)])) if want_hits else None
+    lib().tro_flank_batch(left.data.ctypes.data, left.offsets.ctypes.data, right.data.ctypes.data,
+                          right.offsets.ctypes.data, reads.data.ctypes.data, reads.offsets.ctypes.data,
+                          lro.ctypes.data, lro.size - 1, scoring[0], scoring[1], scoring[2],
+                          float(min_flank_id_frac), spans.ctypes.data,
+                          hits.ctypes.data if hits is not None else None, n_threads)
+    return spans, hits
+
+
+def align_batch(backbones, seqs, group_seq_off, n_threads: int = 1):
+    """tro_align_batch -> (offsets uint64[n+1], words uint32, scores int32)"""
+    np = _np()
+    gso = np.ascontiguousarray(group_seq_off, dtype=np.uint32)
+    n = seqs.offsets.size - 1
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    scores = np.zeros(max(n, 1), dtype=np.int32)
+    wp = C.c_void_p()
+    lib().tro_align_batch(backbones.data.ctypes.data, backbones.offsets.ctypes.data, seqs.data.ctypes.data,
+                          seqs.offsets.ctypes.data, gso.ctypes.data, gso.size - 1, offs.ctypes.data, C.byref(wp),
+                          scores.ctypes.data, n_threads)
+    tot = int(offs[n])
+    words = np.ctypeslib.as_array(C.cast(wp, C.POINTER(C.c_uint32)), shape=(max(tot, 1),))[:tot].copy()
+    lib().tro_free(wp)
+    return offs, words, scores[:n]
+
+
+def hmm_batch(motifs, locus_motif_off, alleles, allele_locus, n_threads: int = 1):
+    """tro_hmm_batch -> (mc_off, mc, span_off, spans[n,3], purity, status)"""
+    np = _np()
+    lmo = np.ascontiguousarray(locus_motif_off, dtype=np.uint32)
+    al = np.ascontiguousarray(allele_locus, dtype=np.uint32)
+    n = al.size
+    nm = np.diff(lmo.astype(np.int64))
+    mc_off = np.zeros(n + 1, dtype=np.uint64)
+    if n:
+        mc_off[1:] = np.cumsum(nm[al])
+    mc = np.zeros(max(int(mc_off[n]), 1), dtype=np.uint32)
+    span_off = np.zeros(n + 1, dtype=np.uint64)
+    purity = np.zeros(max(n, 1), dtype=np.float64)
+    status = np.zeros(max(n, 1), dtype=np.int32)
+    sp = C.c_void_p()
+    lib().tro_hmm_batch(motifs.data.ctypes.data, motifs.offsets.ctypes.data, lmo.ctypes.data, lmo.size - 1,
+                        alleles.data.ctypes.data, alleles.offsets.ctypes.data, al.ctypes.data, n,
+                        mc_off.ctypes.data, mc.ctypes.data, span_off.ctypes.data, C.byref(sp),
+                        purity.ctypes.data, status.ctypes.data, n_threads)
+    tot = int(span_off[n])
+    spans = np.ctypeslib.as_array(C.cast(sp, C.POINTER(C.c_uint32)), shape=(max(3 * tot, 1),))[:3 * tot].copy()
+    lib().tro_free(sp)
+    return mc_off, mc[:int(mc_off[n])], span_off, spans.reshape(-1, 3), purity[:n], status[:n]

@@ -153,27 +153,36 @@ double tro_get_dist(const uint8_t *a, int alen, const uint8_t *b, int blen);
 
 /* ------------------------------------------- batched CPU baseline path -- */
 
-/* One pass of the hot path (phases A+B+C as bench.py defines them) over loci
- * [lo,hi) of a packed batch; used ONLY as the timed CPU baseline / checker. */
+/* Batched, multi-threaded drivers (batch_oracle.c) over the per-item functions above.  They take the
+ * packed CSR inputs of include/trgt_engine.h and fill the same packed outputs; used ONLY by the
+ * parity tests and by bench.py's cpu_baseline / --impl reference legs.  One task per locus (or
+ * group / allele chunk) over n_threads workers, as the reference's rayon pool runs them
+ * (src/commands/genotype.rs:178-187). */
 typedef struct {
-  uint32_t n_loci;
-  const uint8_t *left_pieces;  const uint64_t *left_off;    /* [n_loci+1] */
-  const uint8_t *right_pieces; const uint64_t *right_off;
-  const uint8_t *motifs;       const uint32_t *motif_off;   /* per motif, [n_motifs_total+1] */
-  const uint32_t *locus_motif_off;                           /* [n_loci+1] into motif list */
-  const uint8_t *reads;        const uint64_t *read_off;    /* [n_reads+1] */
-  const uint32_t *locus_read_off;                            /* [n_loci+1] */
-  const uint8_t *read_hap;                                   /* generator's haplotype label per read */
-  int x, o, e;
-  double min_flank_id_frac;
-} tro_batch;
+  int32_t via, matches, score;
+  uint32_t start, end;
+} tro_flank_hit;
 
-typedef struct {
-  tro_opt_span *spans;          /* [n_reads] */
-  uint64_t *checksum;           /* [n_loci] order-independent digest of all per-locus results */
-} tro_batch_out;
+/* find_tr_spans for a chunk of loci: span_locater.rs:32-68.  hits_out may be NULL. */
+int tro_flank_batch(const uint8_t *left, const uint64_t *left_off, const uint8_t *right, const uint64_t *right_off,
+                    const uint8_t *reads, const uint64_t *read_off, const uint32_t *locus_read_off, uint32_t n_loci,
+                    int x, int o, int e, double min_flank_id_frac, tro_opt_span *spans_out, tro_flank_hit *hits_out,
+                    int n_threads);
 
-int tro_process_loci(const tro_batch *b, uint32_t lo, uint32_t hi, tro_batch_out *out);
+/* utils::align for many (backbone, seqs) groups: src/utils/align.rs:14-28.
+ * offsets_out[n_seqs+1]; *words_out is malloc'ed (tro_free). */
+int tro_align_batch(const uint8_t *bb, const uint64_t *bb_off, const uint8_t *seqs, const uint64_t *seq_off,
+                    const uint32_t *group_off, uint32_t n_groups, uint64_t *offsets_out, uint32_t **words_out,
+                    int32_t *scores_out, int n_threads);
+
+/* label_with_hmm for many loci: tr.rs:454-492.  mc_off[n_alleles+1] = prefix sum of the motif count of
+ * each allele's locus; span_off_out[n_alleles+1]; *spans_out is malloc'ed (tro_free). */
+int tro_hmm_batch(const uint8_t *motifs, const uint64_t *motif_off, const uint32_t *locus_motif_off, uint32_t n_loci,
+                  const uint8_t *alleles, const uint64_t *allele_off, const uint32_t *allele_locus, uint32_t n_alleles,
+                  const uint64_t *mc_off, uint32_t *mc_out, uint64_t *span_off_out, tro_span **spans_out,
+                  double *purity_out, int32_t *status_out, int n_threads);
+
+void tro_free(void *p);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,136 @@
+// hostglue.cpp -- host-side stand-in for the reference's genotyper between the GPU phases (part of
+// libtrgt_host.so, used identically by the GPU arm and the CPU reference arm of bench.py).
+//
+// In the reference the scalar genotype logic (src/trgt/genotype/*) sits between span location and
+// consensus alignment / HMM annotation and is out of scope here.  For synthetic reads whose
+// haplotype of origin is known, this glue does what that logic would hand on: per locus and
+// haplotype the repeat sequences read[span.start..span.end] of the spanning reads
+// (tr.rs:139-165), the first of them as the backbone every member is aligned to
+// (genotype_cluster.rs:41-56 -> utils::align), and the backbones as the allele sequences the
+// HMM annotates (tr.rs:77).  Pure byte shuffling, multi-threaded over loci.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+extern "C" {
+
+typedef struct {
+  int32_t found;
+  uint32_t start, end;
+} glue_span;
+
+typedef struct {
+  uint32_t n_groups, n_seqs;
+  uint8_t *bb; uint64_t *bb_off;      // [n_groups+1]
+  uint8_t *seqs; uint64_t *seq_off;   // [n_seqs+1]
+  uint32_t *group_seq_off;            // [n_groups+1]
+  uint32_t *group_locus;              // [n_groups]
+  uint32_t *seq_read;                 // [n_seqs]
+} glue_out;
+
+}  // extern "C"
+
+namespace {
+
+template <class F>
+void par_loci(uint32_t n, uint32_t threads, F f) {
+  uint32_t nt = threads ? threads : std::max(1u, std::thread::hardware_concurrency());
+  if (nt > 64) nt = 64;
+  if (nt > n) nt = n ? n : 1;
+  std::vector<std::thread> th;
+  for (uint32_t t = 0; t < nt; t++)
+    th.emplace_back([&, t]() { f((uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt)); });
+  for (auto &x : th) x.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int glue_build(const uint8_t *reads, const uint64_t *read_off, const uint32_t *locus_read_off, uint32_t n_loci,
+               const glue_span *spans, const uint8_t *read_hap, uint32_t threads, glue_out *out) {
+  // pass 1: per-locus counts
+  std::vector<uint32_t> g_cnt((size_t)n_loci + 1, 0), s_cnt((size_t)n_loci + 1, 0);
+  std::vector<uint64_t> sb_cnt((size_t)n_loci + 1, 0), bb_cnt((size_t)n_loci + 1, 0);
+  par_loci(n_loci, threads, [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t l = lo; l < hi; l++) {
+      bool have[2] = {false, false};
+      uint32_t ns = 0, ng = 0;
+      uint64_t sb = 0, bb = 0;
+      for (uint32_t r = locus_read_off[l]; r < locus_read_off[l + 1]; r++) {
+        if (!spans[r].found) continue;
+        const int h = read_hap[r] ? 1 : 0;
+        const uint64_t len = spans[r].end - spans[r].start;
+        if (!have[h]) { have[h] = true; ng++; bb += len; }
+        ns++;
+        sb += len;
+      }
+      g_cnt[l] = ng; s_cnt[l] = ns; sb_cnt[l] = sb; bb_cnt[l] = bb;
+    }
+  });
+  std::vector<uint32_t> g0((size_t)n_loci + 1, 0), s0((size_t)n_loci + 1, 0);
+  std::vector<uint64_t> sb0((size_t)n_loci + 1, 0), bb0((size_t)n_loci + 1, 0);
+  for (uint32_t l = 0; l < n_loci; l++) {
+    g0[l + 1] = g0[l] + g_cnt[l];
+    s0[l + 1] = s0[l] + s_cnt[l];
+    sb0[l + 1] = sb0[l] + sb_cnt[l];
+    bb0[l + 1] = bb0[l] + bb_cnt[l];
+  }
+  const uint32_t ng = g0[n_loci], ns = s0[n_loci];
+  out->n_groups = ng;
+  out->n_seqs = ns;
+  out->bb = (uint8_t *)malloc((size_t)bb0[n_loci] + 16);
+  out->bb_off = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)ng + 1));
+  out->seqs = (uint8_t *)malloc((size_t)sb0[n_loci] + 16);
+  out->seq_off = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)ns + 1));
+  out->group_seq_off = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)ng + 1));
+  out->group_locus = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)ng + 1));
+  out->seq_read = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)ns + 1));
+  if (!out->bb || !out->bb_off || !out->seqs || !out->seq_off || !out->group_seq_off || !out->group_locus || !out->seq_read)
+    return -1;
+  out->bb_off[ng] = bb0[n_loci];
+  out->seq_off[ns] = sb0[n_loci];
+  out->group_seq_off[ng] = ns;
+  // pass 2: fill, haplotype 0's group first
+  par_loci(n_loci, threads, [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t l = lo; l < hi; l++) {
+      uint32_t g = g0[l], s = s0[l];
+      uint64_t sb = sb0[l], bb = bb0[l];
+      for (int h = 0; h < 2; h++) {
+        bool first = true;
+        for (uint32_t r = locus_read_off[l]; r < locus_read_off[l + 1]; r++) {
+          if (!spans[r].found || (read_hap[r] ? 1 : 0) != h) continue;
+          const uint64_t len = spans[r].end - spans[r].start;
+          const uint8_t *src = reads + read_off[r] + spans[r].start;
+          if (first) {
+            first = false;
+            out->bb_off[g] = bb;
+            out->group_seq_off[g] = s;
+            out->group_locus[g] = l;
+            memcpy(out->bb + bb, src, len);
+            bb += len;
+            g++;
+          }
+          out->seq_off[s] = sb;
+          out->seq_read[s] = r;
+          memcpy(out->seqs + sb, src, len);
+          sb += len;
+          s++;
+        }
+      }
+    }
+  });
+  return 0;
+}
+
+void glue_free(glue_out *o) {
+  free(o->bb); free(o->bb_off); free(o->seqs); free(o->seq_off);
+  free(o->group_seq_off); free(o->group_locus); free(o->seq_read);
+  memset(o, 0, sizeof(*o));
+}
+
+}  // extern "C"

@@ -66,6 +66,7 @@ EXPORTS = [
 ]
 
 _lib = None
+_PINNED_OWNERS = {}  # pinned allocations stay alive for the life of the process unless released
 
 
 def load_library(build: bool = True):
@@ -326,17 +327,122 @@ class Engine:
             out.append(cur)
         return (out, hits) if return_hits else out
 
+    # -- resident batches (upload once, run many times) -------------------------------------
+    def flank_upload(self, left: PackedSeqs, right: PackedSeqs, reads: PackedSeqs, locus_read_offsets: np.ndarray,
+                     scoring=(2, 5, 1), min_flank_id_frac: float = 0.7):
+        lro = np.ascontiguousarray(locus_read_offsets, dtype=np.uint32)
+        b = C.c_void_p()
+        self._check(self._L.trgt_flank_upload(self._h, left.ref(), right.ref(), reads.ref(), lro.ctypes.data,
+                                              len(left), _Scoring(*scoring), float(min_flank_id_frac), C.byref(b)),
+                    "trgt_flank_upload")
+        self.sync()  # the host arrays may go away after this call
+        return b
+
+    def flank_run(self, b):
+        self._check(self._L.trgt_flank_run(self._h, b), "trgt_flank_run")
+
+    def flank_download(self, b, n_reads: int, want_hits: bool = True):
+        spans = np.zeros(n_reads, dtype=SPAN_DTYPE)
+        hits = np.zeros(2 * n_reads, dtype=HIT_DTYPE) if want_hits else None
+        self._check(self._L.trgt_flank_download(self._h, b, spans.ctypes.data,
+                                                hits.ctypes.data if hits is not None else None), "trgt_flank_download")
+        return spans, hits
+
+    def flank_free(self, b):
+        self._L.trgt_flank_free(self._h, b)
+
+    def flank_n_wfa(self, b) -> int:
+        n = C.c_uint32()
+        self._L.trgt_flank_device_views(b, None, None, None, None, None, C.byref(n))
+        return int(n.value)
+
+    def align_upload(self, backbones: PackedSeqs, seqs: PackedSeqs, group_seq_offsets: np.ndarray):
+        gso = np.ascontiguousarray(group_seq_offsets, dtype=np.uint32)
+        b = C.c_void_p()
+        self._check(self._L.trgt_align_upload(self._h, backbones.ref(), seqs.ref(), gso.ctypes.data, len(backbones),
+                                              C.byref(b)), "trgt_align_upload")
+        self.sync()
+        return b
+
+    def align_run(self, b):
+        self._check(self._L.trgt_align_run(self._h, b), "trgt_align_run")
+
+    def align_download(self, b) -> "CigarBatch":
+        out = _Cigars()
+        self._check(self._L.trgt_align_download(self._h, b, C.byref(out)), "trgt_align_download")
+        return self._cigars(out)
+
+    def align_free(self, b):
+        self._L.trgt_align_free(self._h, b)
+
+    def hmm_upload(self, motifs: PackedSeqs, locus_motif_offsets: np.ndarray, alleles: PackedSeqs,
+                   allele_locus: np.ndarray, want_paths: bool = False):
+        lmo = np.ascontiguousarray(locus_motif_offsets, dtype=np.uint32)
+        al = np.ascontiguousarray(allele_locus, dtype=np.uint32)
+        b = C.c_void_p()
+        self._check(self._L.trgt_hmm_upload(self._h, motifs.ref(), lmo.ctypes.data, lmo.size - 1, alleles.ref(),
+                                            al.ctypes.data if al.size else None, int(want_paths), C.byref(b)),
+                    "trgt_hmm_upload")
+        self.sync()
+        return b
+
+    def hmm_run(self, b):
+        self._check(self._L.trgt_hmm_run(self._h, b), "trgt_hmm_run")
+
+    def hmm_download(self, b, want_paths: bool = False) -> "AnnotationBatch":
+        out = _Annotations()
+        self._check(self._L.trgt_hmm_download(self._h, b, C.byref(out)), "trgt_hmm_download")
+        return self._annotations(out, want_paths)
+
+    def hmm_free(self, b):
+        self._L.trgt_hmm_free(self._h, b)
+
+    @staticmethod
+    def _cigars(out) -> "CigarBatch":
+        n = int(out.n)
+        offs = _np_from(out.offsets, n + 1, np.uint64)
+        total = int(offs[n]) if n else 0
+        return CigarBatch(offs, _np_from(out.words, total, np.uint32), _np_from(out.scores, n, np.int32),
+                          _np_from(out.status, n, np.int32))
+
+    @staticmethod
+    def _annotations(out, want_paths: bool) -> "AnnotationBatch":
+        n = int(out.n)
+        mco = _np_from(out.motif_count_offsets, n + 1, np.uint64)
+        so = _np_from(out.span_offsets, n + 1, np.uint64)
+        n_mc = int(mco[n]) if n else 0
+        n_sp = int(so[n]) if n else 0
+        spans = _np_from(out.spans, 3 * n_sp, np.uint32).reshape(-1, 3)
+        res = AnnotationBatch(mco, _np_from(out.motif_counts, n_mc, np.uint32), so, spans,
+                              _np_from(out.purity, n, np.float64), _np_from(out.status, n, np.int32))
+        if want_paths:
+            po = _np_from(out.path_offsets, n + 1, np.uint64)
+            res.path_offsets = po
+            res.paths = _np_from(out.paths, int(po[n]) if n else 0, np.uint32)
+        return res
+
+    def pinned_array(self, nbytes: int) -> np.ndarray:
+        """uint8 array in pinned host memory (trgt_host_alloc); freed when the array is collected."""
+        ptr = self._L.trgt_host_alloc(max(1, nbytes))
+        if not ptr:
+            raise MemoryError(f"trgt_host_alloc({nbytes}) failed")
+        buf = (C.c_uint8 * max(1, nbytes)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        lib = self._L
+
+        class _Owner:
+            def __del__(self_inner):
+                lib.trgt_host_free(ptr)
+        _PINNED_OWNERS[ptr] = (_Owner(), buf)
+        return arr
+
     # -- phase B ---------------------------------------------------------------------------
     def align_packed(self, backbones: PackedSeqs, seqs: PackedSeqs, group_seq_offsets: np.ndarray) -> CigarBatch:
         gso = np.ascontiguousarray(group_seq_offsets, dtype=np.uint32)
         out = _Cigars()
         rc = self._L.trgt_align_e2e(self._h, backbones.ref(), seqs.ref(), gso.ctypes.data, len(backbones), C.byref(out))
         self._check(rc, "trgt_align_e2e")
-        n = int(out.n)
-        offs = _np_from(out.offsets, n + 1, np.uint64)
-        total = int(offs[n]) if n else 0
-        return CigarBatch(offs, _np_from(out.words, total, np.uint32), _np_from(out.scores, n, np.int32),
-                          _np_from(out.status, n, np.int32))
+        return self._cigars(out)
 
     def align(self, groups: Sequence[Tuple[bytes, Sequence[bytes]]]) -> List[List[List[Tuple[int, str]]]]:
         """utils::align (src/utils/align.rs:14-28) for many (backbone, seqs) groups."""
@@ -382,19 +488,7 @@ class Engine:
         rc = self._L.trgt_hmm_label(self._h, motifs.ref(), lmo.ctypes.data, lmo.size - 1, alleles.ref(),
                                     al.ctypes.data if al.size else None, int(want_paths), C.byref(out))
         self._check(rc, "trgt_hmm_label")
-        n = int(out.n)
-        mco = _np_from(out.motif_count_offsets, n + 1, np.uint64)
-        so = _np_from(out.span_offsets, n + 1, np.uint64)
-        n_mc = int(mco[n]) if n else 0
-        n_sp = int(so[n]) if n else 0
-        spans = _np_from(out.spans, 3 * n_sp, np.uint32).reshape(-1, 3)
-        res = AnnotationBatch(mco, _np_from(out.motif_counts, n_mc, np.uint32), so, spans,
-                              _np_from(out.purity, n, np.float64), _np_from(out.status, n, np.int32))
-        if want_paths:
-            po = _np_from(out.path_offsets, n + 1, np.uint64)
-            res.path_offsets = po
-            res.paths = _np_from(out.paths, int(po[n]) if n else 0, np.uint32)
-        return res
+        return self._annotations(out, want_paths)
 
     def label_with_hmm(self, loci: Sequence[Tuple[Sequence[bytes], Sequence[bytes]]]) -> List[List[Annotation]]:
         """label_with_hmm (tr.rs:454-492) for many loci: loci = [(motifs, allele_seqs)]."""

@@ -1,0 +1,136 @@
+"""One pass of the hot path over a chunk of loci, phase-structured as the reference's host would
+drive it: A = flank spans for every read, host genotype glue, B = consensus
+alignments, C = motif HMM annotation.  Used by bench.py, __graft_entry__.smoke() and the tests.
+
+    HotPath.run_e2e()        host buffers in, host buffers out, through the one-shot C-ABI calls
+    HotPath.run_resident()   the same three phases on batches already resident in HBM
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from .engine import AnnotationBatch, CigarBatch, Engine, HIT_DTYPE, SPAN_DTYPE
+from .workload import GenotypeGlue, Workload, genotype_glue
+
+
+@dataclass
+class HotPathResult:
+    spans: np.ndarray                 # SPAN_DTYPE [n_reads]
+    hits: Optional[np.ndarray]        # HIT_DTYPE [2*n_reads]
+    glue: GenotypeGlue
+    cigars: CigarBatch
+    annotations: AnnotationBatch
+
+
+class HotPath:
+    def __init__(self, engine: Engine, w: Workload, want_hits: bool = False, pinned_outputs: bool = True):
+        self.eng = engine
+        self.w = w
+        self.want_hits = want_hits
+        n = w.n_reads
+        if pinned_outputs:
+            self._spans = engine.pinned_array(max(1, n) * SPAN_DTYPE.itemsize)[:n * SPAN_DTYPE.itemsize].view(SPAN_DTYPE)
+            self._hits = (engine.pinned_array(max(1, 2 * n) * HIT_DTYPE.itemsize)[:2 * n * HIT_DTYPE.itemsize]
+                          .view(HIT_DTYPE)) if want_hits else None
+        else:
+            self._spans = np.zeros(n, dtype=SPAN_DTYPE)
+            self._hits = np.zeros(2 * n, dtype=HIT_DTYPE) if want_hits else None
+        self._fb = self._ab = self._hb = None
+        self.glue: Optional[GenotypeGlue] = None
+
+    # -- bytes that cross PCIe in one e2e step ------------------------------------------------
+    def h2d_bytes(self, glue: GenotypeGlue) -> int:
+        w = self.w
+        n = 0
+        for s in (w.reads, w.left, w.right, glue.backbones, glue.seqs, w.motifs):
+            n += s.data.nbytes + s.offsets.nbytes
+        n += glue.backbones.data.nbytes + glue.backbones.offsets.nbytes  # alleles = backbones, sent again for phase C
+        n += w.locus_read_off.nbytes + glue.group_seq_off.nbytes + w.locus_motif_off.nbytes + glue.group_locus.nbytes
+        n += 2 * 8 * (len(glue.backbones) + 1)  # bp / mc offsets of the HMM batch
+        return int(n)
+
+    def d2h_bytes(self, res: HotPathResult) -> int:
+        n = res.spans.nbytes + (res.hits.nbytes if res.hits is not None else 0)
+        c, a = res.cigars, res.annotations
+        n += c.offsets.nbytes + c.words.nbytes + c.scores.nbytes + c.status.nbytes
+        n += a.motif_counts.nbytes + a.span_offsets.nbytes + a.spans.nbytes + a.purity.nbytes + a.status.nbytes
+        return int(n)
+
+    # -- end to end through the one-shot C-ABI calls ------------------------------------------
+    def run_e2e(self) -> HotPathResult:
+        w, eng = self.w, self.eng
+        spans, hits = eng.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring,
+                                             w.min_flank_id_frac, want_hits=self.want_hits,
+                                             spans_out=self._spans, hits_out=self._hits)
+        glue = genotype_glue(w, spans)
+        cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off)
+        ann = eng.hmm_label_packed(w.motifs, w.locus_motif_off, glue.backbones, glue.group_locus)
+        return HotPathResult(spans, hits, glue, cigars, ann)
+
+    # -- resident batches ---------------------------------------------------------------------
+    def prepare_resident(self) -> GenotypeGlue:
+        """Upload phase A's inputs, run it once, derive phases B/C inputs on the host and upload them."""
+        w, eng = self.w, self.eng
+        self.free_resident()
+        self._fb = eng.flank_upload(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+        eng.flank_run(self._fb)
+        spans, _ = eng.flank_download(self._fb, w.n_reads, want_hits=False)
+        self.glue = genotype_glue(w, spans)
+        self._ab = eng.align_upload(self.glue.backbones, self.glue.seqs, self.glue.group_seq_off)
+        self._hb = eng.hmm_upload(w.motifs, w.locus_motif_off, self.glue.backbones, self.glue.group_locus)
+        return self.glue
+
+    def run_resident(self, sync: bool = True):
+        eng = self.eng
+        eng.flank_run(self._fb)
+        eng.align_run(self._ab)
+        eng.hmm_run(self._hb)
+        if sync:
+            eng.sync()
+
+    def download_resident(self) -> HotPathResult:
+        eng = self.eng
+        spans, hits = eng.flank_download(self._fb, self.w.n_reads, want_hits=self.want_hits)
+        return HotPathResult(spans, hits, self.glue, eng.align_download(self._ab), eng.hmm_download(self._hb))
+
+    def n_wfa(self) -> int:
+        return self.eng.flank_n_wfa(self._fb) if self._fb else 0
+
+    def free_resident(self):
+        if self._fb:
+            self.eng.flank_free(self._fb)
+        if self._ab:
+            self.eng.align_free(self._ab)
+        if self._hb:
+            self.eng.hmm_free(self._hb)
+        self._fb = self._ab = self._hb = None
+
+
+def oracle_pass(orc, w: Workload, n_threads: int):
+    """The same pass on the CPU oracle (TEST / BASELINE USE ONLY: callers are tests/, smoke() and
+    bench.py's cpu_baseline and --impl reference legs).  `orc` is the oracle.oracle module."""
+    spans, _ = orc.flank_batch(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac,
+                               n_threads=n_threads, want_hits=False)
+    glue = genotype_glue(w, spans)
+    offs, words, scores = orc.align_batch(glue.backbones, glue.seqs, glue.group_seq_off, n_threads=n_threads)
+    hmm = orc.hmm_batch(w.motifs, w.locus_motif_off, glue.backbones, glue.group_locus, n_threads=n_threads)
+    return spans, glue, (offs, words, scores), hmm
+
+
+def compare_with_oracle(res: HotPathResult, ref) -> None:
+    """Bit-exact comparison of a HotPathResult with oracle_pass output (raises AssertionError)."""
+    spans, glue, (offs, words, scores), (mc_off, mc, span_off, hspans, purity, status) = ref
+    assert np.array_equal(res.spans["found"], spans["found"]), "span found flags differ"
+    f = spans["found"] != 0
+    assert np.array_equal(res.spans["start"][f], spans["start"][f]) and np.array_equal(res.spans["end"][f], spans["end"][f]), "spans differ"
+    assert np.array_equal(res.glue.seq_read, glue.seq_read) and np.array_equal(res.glue.group_locus, glue.group_locus)
+    assert np.array_equal(res.cigars.offsets, offs) and np.array_equal(res.cigars.words, words), "CIGARs differ"
+    assert np.array_equal(res.cigars.scores, scores), "alignment scores differ"
+    assert not res.cigars.status.any() and not res.annotations.status.any() and not status.any()
+    a = res.annotations
+    assert np.array_equal(a.motif_counts, mc), "MC differs"
+    assert np.array_equal(a.span_offsets, span_off) and np.array_equal(a.spans, hspans), "MS differs"
+    assert np.array_equal(a.purity, purity, equal_nan=True), "AP differs"
