@@ -139,7 +139,7 @@ def test_flank_spans_noisy_targeted_scoring(engine, oracle):
     """--preset targeted scoring (1,0,1), 0.8 identity, 200-bp pieces (cli.rs:271-302); noisy reads so
     that accepted, rejected and discordant cases all occur."""
     from trgt_b200 import workload
-    w = workload.generate(24, 10, seed=5, context=260, piece=200, sub_rate=0.06, ins_rate=0.06, del_rate=0.06)
+    w = workload.generate(24, 10, seed=5, context=260, piece=200, sub_rate=0.1, ins_rate=0.1, del_rate=0.1)
     spans, hits = engine.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, (1, 0, 1), 0.8)
     _check_flanks(oracle, w, spans, hits, (1, 0, 1), 0.8)
     vias = set(int(v) for v in hits["via"])
