@@ -15,11 +15,17 @@ extern "C" {
 // Two-pass alignment exactly as the device runs it: ring score pass, cone trace pass.
 // out[0]=status out[1]=score(-cost) out[2]=k out[3]=off out[4]=matches out[5]=ystart out[6]=yend
 // out[7]=n_words out[8]=trace ints used (bound)
-int emu_wfa_align(const uint8_t *p, int P, const uint8_t *t, int T, int x, int o, int e, int pbf, int pef,
+int emu_wfa_align(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x, int o, int e, int pbf, int pef,
                   int tbf, int tef, int *out, uint32_t *words, uint32_t words_cap) {
+  // the cores read 8 bytes at a time: give them the 16-byte padding every engine buffer has
+  std::vector<uint8_t> pbuf(P + 16, 0), tbuf(T + 16, 0);
+  memcpy(pbuf.data(), p_in, P);
+  memcpy(tbuf.data(), t_in, T);
+  const uint8_t *p = pbuf.data(), *t = tbuf.data();
   WfaProb pr;
   pr.p = p; pr.P = P; pr.t = t; pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
   pr.pbf = pbf; pr.pef = pef; pr.tbf = tbf; pr.tef = tef;
+  wfa_unband(pr);
   SerialGroup g;
   std::vector<int> ring(wfa_ring_ints(pr) + 1, 0x7ead);
   const WfaEnd end = wfa_score_ring(g, pr, ring.data(), wfa_score_cap(pr));
@@ -46,8 +52,31 @@ int emu_wfa_align(const uint8_t *p, int P, const uint8_t *t, int T, int x, int o
 }
 
 int emu_flank_scan(const uint8_t *piece, int P, const uint8_t *t, int T) {
+  std::vector<uint8_t> pbuf(P + 16, 0), tbuf(T + 32, 0);
+  memcpy(pbuf.data(), piece, P);
+  memcpy(tbuf.data(), t, T);
   SerialGroup g;
-  return flank_scan(g, piece, P, t, T);
+  return flank_scan(g, pbuf.data(), P, tbuf.data(), T);
+}
+
+// flank fallback through the seed filter + banded pass + cone trace.
+// out: [0]=rc (0 resolved, 1 deferred) [1]=via [2]=matches [3]=score [4]=start [5]=end
+int emu_flank_banded(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x, int o, int e, int S, double frac,
+                     int ws_ints, int *out) {
+  std::vector<uint8_t> pbuf(P + 16, 0), tbuf(T + 16, 0);
+  memcpy(pbuf.data(), p_in, P);
+  memcpy(tbuf.data(), t_in, T);
+  WfaProb pr;
+  pr.p = pbuf.data(); pr.P = P; pr.t = tbuf.data(); pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
+  pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;
+  wfa_unband(pr);
+  SerialGroup g;
+  std::vector<int> ws(ws_ints + 1, 0x7ead);
+  uint64_t keys[32];
+  FlankHit hit = {0, 0, 0, 0, 0};
+  out[0] = flank_locate_banded(g, pr, S, frac, keys, ws.data(), (size_t)ws_ints, &hit);
+  out[1] = hit.via; out[2] = hit.matches; out[3] = hit.score; out[4] = hit.start; out[5] = hit.end;
+  return out[0];
 }
 
 int emu_edit_distance(const uint8_t *a, int la, const uint8_t *b, int lb) {

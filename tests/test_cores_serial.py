@@ -199,3 +199,42 @@ def test_edit_distance_core(emul, oracle):
         assert got == lev(a, b)
         if a and b and len(a) * len(b) <= 10000:
             assert math.sqrt(got) == oracle.get_dist(a, b)
+
+
+def test_flank_banded_core(emul, oracle):
+    """Seed filter + banded score pass + cone trace must give what the full-width alignment gives
+    whenever it claims to have settled the pair (rc 0), on clean, noisy and repetitive flanks."""
+    emul.emu_flank_banded.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_double, C.c_int, C.POINTER(C.c_int)]
+    rng = random.Random(77)
+    resolved = 0
+    for _ in range(2500):
+        x, o, e = rng.choice([(2, 5, 1), (2, 5, 1), (1, 0, 1), (4, 6, 2), (3, 1, 3)])
+        P = rng.choice([60, 120, 250])
+        kind = rng.random()
+        if kind < 0.3:  # low-complexity flank: many seed occurrences on many diagonals
+            unit = rnd(rng, rng.randint(1, 7))
+            p = mutate(rng, (unit * (P // len(unit) + 1))[:P], 0.02)[:P]
+        else:
+            p = rnd(rng, P)
+        pre, suf = rnd(rng, rng.randint(0, 300)), rnd(rng, rng.randint(0, 300))
+        if kind < 0.3 and rng.random() < 0.5:
+            pre += p[:len(p) // 2]
+        body = mutate(rng, p, rng.choice([0.004, 0.01, 0.03, 0.08]))
+        if rng.random() < 0.15:
+            body = body[:len(body) // 2] + rnd(rng, rng.randint(1, 12)) + body[len(body) // 2:]
+        t = pre + body + suf
+        if rng.random() < 0.1:
+            t = t[:rng.randint(len(pre) + 10, len(t))]
+        S = rng.choice([8, 16, 20, 24])
+        exp, via, nm = oracle.find_span(p, t, (x, o, e), len(p) * 0.7)
+        if via == 1:
+            continue
+        out = (C.c_int * 6)()
+        rc = emul.emu_flank_banded(p, len(p), t, len(t), x, o, e, S, 0.7, 8192, out)
+        if rc == 0:
+            resolved += 1
+            assert (out[1], out[2]) == (via, nm)
+            if exp is not None:
+                assert (out[4], out[5]) == exp
+    assert resolved > 300

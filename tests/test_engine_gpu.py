@@ -127,12 +127,45 @@ def _check_flanks(oracle, w, spans, hits, scoring, frac):
     return n_wfa
 
 
-def test_flank_spans_synthetic_hifi(engine, oracle):
+@pytest.mark.parametrize("band_budget", [20, 6, 0])
+def test_flank_spans_synthetic_hifi(engine, oracle, band_budget):
+    """band_budget 20: misses settled by the on-chip banded path; 0: all by the full-width kernels;
+    6: a mix.  All three must give the reference's answer."""
     from trgt_b200 import workload
     w = workload.generate(40, 12, seed=99)
-    spans, hits = engine.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+    engine.set_flank_band_budget(band_budget)
+    try:
+        engine.reset_stats()
+        spans, hits = engine.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring,
+                                                w.min_flank_id_frac)
+        stats = engine.kernel_stats()
+    finally:
+        engine.set_flank_band_budget(20)
     n_wfa = _check_flanks(oracle, w, spans, hits, w.scoring, w.min_flank_id_frac)
     assert n_wfa > 20  # the WFA fallback was exercised
+    assert ("k_wfa_score_block" in stats) == (band_budget < 20)
+
+
+def test_flank_spans_long_reads_and_repetitive_flanks(engine, oracle):
+    """Reads too long for the staged on-chip copy, and low-complexity flanks with many seed hits."""
+    rng = random.Random(17)
+    loci = []
+    for kind in range(6):
+        if kind % 2 == 0:
+            lf, rf = rnd(rng, 250), rnd(rng, 250)
+        else:
+            u1, u2 = rnd(rng, rng.randint(2, 9)), rnd(rng, rng.randint(2, 9))
+            lf = mutate(rng, (u1 * 200)[:260], 0.03)[:250].ljust(250, b"A")
+            rf = mutate(rng, (u2 * 200)[:260], 0.03)[:250].ljust(250, b"C")
+        reads = []
+        for _ in range(6):
+            ctx = rng.choice([300, 1200, 3000])
+            read = rnd(rng, ctx) + mutate(rng, lf, 0.01) + b"CAG" * rng.randint(3, 400) + mutate(rng, rf, 0.01) + rnd(rng, ctx)
+            reads.append(read)
+        loci.append((lf, rf, reads))
+    got = engine.find_tr_spans(loci)
+    for (lf, rf, reads), g in zip(loci, got):
+        assert g == oracle.find_tr_spans(lf, rf, reads)
 
 
 def test_flank_spans_noisy_targeted_scoring(engine, oracle):

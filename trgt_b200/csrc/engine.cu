@@ -9,7 +9,7 @@
 #include <string.h>
 
 #include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -76,6 +76,7 @@ struct trgt_engine {
   trgt_hmm_batch_t *one_hmm = nullptr;
   DevBuf d_ed[6];
   size_t workspace_budget = (size_t)24 << 30;  // cap on back-pointer / trace workspace per wave
+  int band_budget = 20;  // cost cap of the banded flank fallback (0: always use the full-width path)
 };
 
 namespace {
@@ -226,7 +227,7 @@ int upload_seqs(trgt_engine *e, const trgt_seqs_t *s, DevBuf &data, DevBuf &off)
 }
 
 int exclusive_scan_u32(trgt_engine *e, const uint32_t *d_in, unsigned long long *d_out, size_t n) {
-  cub::TransformInputIterator<unsigned long long, CastU64, const uint32_t *> it(d_in, CastU64());
+  auto it = thrust::make_transform_iterator(d_in, CastU64());
   size_t tmp = 0;
   CU(e, cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, d_out, (int)n, e->stream));
   TRY(dev_reserve(e, e->d_scan_tmp, tmp));
@@ -515,13 +516,15 @@ static int flank_run_locked(trgt_engine_t *e, trgt_flank_batch *b) {
   CU(e, cudaMemsetAsync(ctr, 0, sizeof(Counters), e->stream));
   {
     const int block = 256;
+    const size_t smem = (size_t)(block / 32) * sizeof(FlankWarpSmem);
     int grid = 0;
-    TRY(persistent_grid(e, k_flank_scan, block, 0, &grid));
+    TRY(persistent_grid(e, k_flank_locate, block, smem, &grid));
     const uint32_t need = (b->n_reads + 7) / 8;
     if ((uint32_t)grid > need) grid = (int)need;
-    LaunchScope ls(e, "k_flank_scan");
-    k_flank_scan<<<grid, block, 0, e->stream>>>(src, b->n_reads, (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p, ctr);
-    TRY(check_launch(e, "k_flank_scan"));
+    LaunchScope ls(e, "k_flank_locate");
+    k_flank_locate<<<grid, block, smem, e->stream>>>(src, b->n_reads, e->band_budget, b->frac,
+                                                     (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p, ctr);
+    TRY(check_launch(e, "k_flank_locate"));
   }
   {
     // pass 1: one CTA per (read, flank) that missed; ring in shared memory when it fits
@@ -1206,6 +1209,10 @@ int32_t trgt_hmm_label(trgt_engine_t *e, const trgt_seqs_t *motifs, const uint32
 
 void trgt_engine_set_workspace_budget(trgt_engine_t *e, size_t bytes) {
   if (e && bytes >= ((size_t)1 << 20)) e->workspace_budget = bytes;
+}
+
+void trgt_engine_set_flank_band_budget(trgt_engine_t *e, int32_t max_cost) {
+  if (e) e->band_budget = max_cost < 0 ? 0 : (max_cost > 64 ? 64 : max_cost);
 }
 
 }  // extern "C"

@@ -1,6 +1,6 @@
 // kernels.cuh -- sm_100a kernels of the tandem-repeat DP engine (included by engine.cu only).
 //
-//   phase A  k_flank_scan      exact flank search           span_locater.rs:10-12
+//   phase A  k_flank_locate    exact flank search + banded WFA fallback   span_locater.rs:7-30
 //            k_wfa_score       WFA pass 1 (ring, no history) wfaligner.rs:503-528 (flank), :489 (e2e)
 //            k_wfa_trace       WFA pass 2 (cone + back-trace) -> count_matches / span / SAM CIGAR
 //            k_flank_combine   find_tr_spans combine rule   span_locater.rs:53-67
@@ -27,7 +27,7 @@ struct Counters {
   unsigned long long words_bound;       // upper bound on CIGAR words pass 2 will emit
   unsigned long long pool_used;         // CIGAR words actually emitted by pass 2
   unsigned int n_failed;                // items that ended with a non-OK status
-  unsigned int pad;
+  unsigned int n_banded;                // flank: pairs settled by the banded on-chip path
 };
 
 enum { WFA_MODE_FLANK = 0, WFA_MODE_E2E = 1 };
@@ -66,6 +66,7 @@ __device__ __forceinline__ WfaProb wfa_prob_of(const WfaSrc &s, uint32_t id) {
     pr.T = (int)(s.seq_off[id + 1] - s.seq_off[id]);
     pr.pbf = pr.pef = pr.tbf = pr.tef = 0;
   }
+  wfa_unband(pr);
   return pr;
 }
 
@@ -78,30 +79,90 @@ __global__ void k_expand_offsets(const uint32_t *__restrict__ off, uint32_t n_gr
     for (uint32_t i = off[g]; i < off[g + 1]; i++) out[i] = g;
 }
 
-// ------------------------------------------------------------------ phase A: exact scan ---
+// ------------------------------------------------------------------ phase A: flank location ---
 
-// One warp per read, both flanks.  Misses are appended to `work` as 2*read+side.
+#define FL_TXT 2080        // bytes of staged read per warp (reads up to ~2 KB take the on-chip path)
+#define FL_PIECE 288       // bytes of staged flank piece
+#define FL_WS_INTS 1536    // WFA scratch per warp: banded ring, then the trace cone (cost <= ~20)
+
+struct __align__(16) FlankWarpSmem {
+  uint8_t txt[FL_TXT];
+  uint8_t lp[FL_PIECE];
+  uint8_t rp[FL_PIECE];
+  uint64_t keys[32];
+  int ws[FL_WS_INTS];
+};
+
+// copy `bytes` (+16 of slack) starting at global `src` into the 16-byte aligned staging buffer with
+// 16-byte cp.async; returns the staged address of src[0].  cap: staging capacity in bytes.
+__device__ __forceinline__ const uint8_t *stage_bytes(const uint8_t *src, int bytes, uint8_t *dst, int cap,
+                                                      int lane) {
+  const uintptr_t a = (uintptr_t)src;
+  const int shift = (int)(a & 15u);
+  const int chunks = (shift + bytes + 15 + 16) >> 4;
+  if (chunks * 16 > cap) return nullptr;
+  const uint4 *g = (const uint4 *)(a - (uintptr_t)shift);
+  for (int c = lane; c < chunks; c += 32) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 16 * c);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g + c) : "memory");
+  }
+  return dst + shift;
+}
+
+// One warp per read, both flanks: exact search (span_locater.rs:10-12); on a miss the WFA fallback
+// (:14-25) through the seed filter + banded pass + cone trace of wfa_core.h, all from the staged copy
+// of the read.  Pairs the banded path cannot settle are appended to `work` as 2*read+side for the
+// full-width kernels below.
 __global__ void __launch_bounds__(256)
-k_flank_scan(WfaSrc src, uint32_t n_reads, trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work,
-             Counters *ctr) {
+k_flank_locate(WfaSrc src, uint32_t n_reads, int band_budget, double min_flank_id_frac,
+               trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work, Counters *ctr) {
+  extern __shared__ __align__(16) unsigned char smem_b[];
   const WarpGroup g;
+  const int lane = g.lane();
+  FlankWarpSmem &sm = reinterpret_cast<FlankWarpSmem *>(smem_b)[threadIdx.x >> 5];
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += warps) {
+    const WfaProb pl = wfa_prob_of(src, 2 * r), prr = wfa_prob_of(src, 2 * r + 1);
+    // stage read and pieces (cp.async, all requests in flight before the first wait)
+    const uint8_t *t_s = stage_bytes(pl.t, pl.T, sm.txt, FL_TXT, lane);
+    const uint8_t *lp_s = stage_bytes(pl.p, pl.P, sm.lp, FL_PIECE, lane);
+    const uint8_t *rp_s = stage_bytes(prr.p, prr.P, sm.rp, FL_PIECE, lane);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
     for (uint32_t side = 0; side < 2; side++) {
-      const WfaProb pr = wfa_prob_of(src, 2 * r + side);
-      int pos = -1;
-      if (pr.P > 0) pos = flank_scan(g, pr.p, pr.P, pr.t, pr.T);
-      if (g.lane() == 0) {
-        trgt_flank_hit_t h;
-        h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
+      WfaProb pr = side ? prr : pl;
+      const uint8_t *ps = side ? rp_s : lp_s;
+      if (t_s) pr.t = t_s;   // otherwise (very long read) straight from global memory
+      if (ps) pr.p = ps;
+      wfa_unband(pr);
+      trgt_flank_hit_t h;
+      h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
+      int deferred = 0;
+      if (pr.P > 0) {
+        const int pos = flank_scan(g, pr.p, pr.P, pr.t, pr.T);
         if (pos >= 0) {
           h.via = TRGT_VIA_EXACT; h.matches = pr.P; h.start = (uint32_t)pos; h.end = (uint32_t)(pos + pr.P);
-        } else if (pr.P > 0) {
+        } else {
+          FlankHit fh;
+          fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
+          deferred = band_budget > 0
+                         ? flank_locate_banded(g, pr, band_budget, min_flank_id_frac, sm.keys, sm.ws, FL_WS_INTS, &fh)
+                         : 1;
+          if (!deferred) {
+            h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
+            h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
+          }
+        }
+      }
+      if (lane == 0) {
+        if (deferred) {
           const unsigned int slot = atomicAdd(&ctr->n_work, 1u);
           work[slot] = 2 * r + side;
         }
         hits[2 * r + side] = h;
       }
+      __syncwarp();
     }
   }
 }

@@ -26,6 +26,7 @@
 #include <limits.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "coop.h"
 
@@ -43,7 +44,49 @@ struct WfaProb {
   const uint8_t *t; int T;  // text (consumed by 'I')
   int x, oe, e;             // mismatch, gap_open + gap_extend, gap_extend
   int pbf, pef, tbf, tef;   // ends-free allowances (all 0 = end-to-end)
+  int blo, bhi;             // diagonal band the forward pass may use ([-P, T] = exact, unrestricted)
 };
+
+TRGT_HD void wfa_unband(WfaProb &pr) { pr.blo = -pr.P; pr.bhi = pr.T; }
+
+// 8 bytes starting at any byte address, assembled from the two aligned words that cover them.
+// May touch up to 15 bytes past `a`: every sequence buffer of the engine is padded by 16 bytes.
+TRGT_HD uint64_t wfa_ld64u(const uint8_t *a) {
+#if defined(__CUDA_ARCH__)
+  const uintptr_t addr = (uintptr_t)a;
+  const uint64_t *w = (const uint64_t *)(addr & ~(uintptr_t)7);
+  const unsigned sh = (unsigned)(addr & 7u) * 8u;
+  const uint64_t lo = w[0];
+  if (sh == 0) return lo;
+  return (lo >> sh) | (w[1] << (64u - sh));
+#else
+  uint64_t v;
+  memcpy(&v, a, 8);
+  return v;
+#endif
+}
+
+TRGT_HD int wfa_ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)x) - 1;
+#else
+  return __builtin_ctzll(x);
+#endif
+}
+
+// number of leading bytes (< n) on which a and b agree, 8 bytes per step
+TRGT_HD int wfa_match_len(const uint8_t *a, const uint8_t *b, int n) {
+  int i = 0;
+  while (i < n) {
+    const uint64_t x = wfa_ld64u(a + i) ^ wfa_ld64u(b + i);
+    if (x) {
+      i += wfa_ctz64(x) >> 3;
+      return i < n ? i : n;
+    }
+    i += 8;
+  }
+  return n;
+}
 
 struct WfaEnd {
   int status;
@@ -75,9 +118,10 @@ TRGT_HD WfaView wfa_null_view() {
 
 // match extension along diagonal k from text offset h
 TRGT_HD int wfa_extend(const WfaProb &pr, int k, int h) {
-  int v = h - k;
-  while (v < pr.P && h < pr.T && pr.p[v] == pr.t[h]) { v++; h++; }
-  return h;
+  const int v = h - k;
+  const int n = wfa_imin(pr.P - v, pr.T - h);
+  if (n <= 0 || pr.p[v] != pr.t[h]) return h;  // most diagonals of an ends-free wavefront stop here
+  return h + wfa_match_len(pr.p + v, pr.t + h, n);
 }
 
 // true diagonal range of wavefront s from its sources' true ranges; returns false if null
@@ -89,8 +133,8 @@ TRGT_HD bool wfa_next_range(const WfaProb &pr, const WfaView &vx, const WfaView 
   if (ve.tlo <= ve.thi && ve.i != nullptr) { lo = wfa_imin(lo, ve.tlo); hi = wfa_imax(hi, ve.thi); }
   if (lo > hi) return false;
   lo -= 1; hi += 1;
-  lo = wfa_imax(lo, -pr.P);
-  hi = wfa_imin(hi, pr.T);
+  lo = wfa_imax(lo, pr.blo);  // blo >= -P, bhi <= T: cells outside [-P, T] can never be valid
+  hi = wfa_imin(hi, pr.bhi);
   if (lo > hi) return false;
   *lo_out = lo; *hi_out = hi;
   return true;
@@ -145,7 +189,7 @@ TRGT_HD int wfa_terminated(const G &g, const WfaProb &pr, const WfaView &w) {
 TRGT_HD int wfa_ring_depth_m(const WfaProb &pr) { return wfa_imax(pr.x, pr.oe) + 1; }
 TRGT_HD int wfa_ring_depth_g(const WfaProb &pr) { return pr.e + 1; }
 // stride of one ring slot: every diagonal a valid cell can live on
-TRGT_HD int wfa_ring_stride(const WfaProb &pr) { return pr.P + pr.T + 1; }
+TRGT_HD int wfa_ring_stride(const WfaProb &pr) { return pr.bhi - pr.blo + 1; }
 TRGT_HD size_t wfa_ring_ints(const WfaProb &pr) {
   const size_t dm = (size_t)wfa_ring_depth_m(pr), dg = (size_t)wfa_ring_depth_g(pr);
   return 2 * dm + (dm + 2 * dg) * (size_t)wfa_ring_stride(pr);
@@ -164,7 +208,7 @@ TRGT_HD WfaView wfa_ring_view(const WfaProb &pr, int *ring, int s) {
   int *ibase = mbase + (size_t)dm * W;
   int *dbase = ibase + (size_t)dg * W;
   WfaView v;
-  v.base = -pr.P;
+  v.base = pr.blo;
   v.tlo = v.lo = meta[2 * (s % dm)];
   v.thi = v.hi = meta[2 * (s % dm) + 1];
   v.m = mbase + (size_t)(s % dm) * W;
@@ -185,8 +229,8 @@ TRGT_HD WfaEnd wfa_score_ring(const G &g, const WfaProb &pr, int *ring, int s_ca
   const int dm = wfa_ring_depth_m(pr);
   int *meta = ring;
   if (g.lane() == 0) {
-    meta[0] = -pr.pbf;
-    meta[1] = pr.tbf;
+    meta[0] = wfa_imax(-pr.pbf, pr.blo);
+    meta[1] = wfa_imin(pr.tbf, pr.bhi);
   }
   g.sync();
   {
@@ -269,7 +313,7 @@ TRGT_HD int wfa_trace_forward(const G &g, const WfaProb &pr, int s_end, int k_en
     bool live;
     WfaView vx = wfa_null_view(), vo = wfa_null_view(), ve = wfa_null_view();
     if (s == 0) {
-      tlo = -pr.pbf; thi = pr.tbf; live = true;
+      tlo = wfa_imax(-pr.pbf, pr.blo); thi = wfa_imin(pr.tbf, pr.bhi); live = tlo <= thi;
     } else {
       vx = wfa_hist_view(ws, s - pr.x);
       vo = wfa_hist_view(ws, s - pr.oe);
@@ -413,21 +457,124 @@ struct WfaCigarSink {
 // ---------------------------------------------------------------- exact flank scan ----------
 
 // first start s with t[s..s+P) == piece, or -1     span_locater.rs:10-12
+// Each lane tests 4 consecutive starts per step against the piece's first 8 bytes (two 8-byte
+// loads, three shifted windows); a key hit is verified 8 bytes at a time.
 template <class G>
 TRGT_HD int flank_scan(const G &g, const uint8_t *piece, int P, const uint8_t *t, int T) {
   const int n_starts = T - P + 1;
-  for (int base = 0; base < n_starts; base += g.size()) {
-    const int s = base + g.lane();
+  if (P < 8) {
+    for (int base = 0; base < n_starts; base += g.size()) {
+      const int s = base + g.lane();
+      int hit = INT_MAX;
+      if (s < n_starts) {
+        int j = 0;
+        while (j < P && t[s + j] == piece[j]) j++;
+        if (j == P) hit = s;
+      }
+      hit = g.min_i(hit);
+      if (hit != INT_MAX) return hit;
+    }
+    return -1;
+  }
+  const uint64_t key = wfa_ld64u(piece);
+  for (int base = 0; base < n_starts; base += 4 * g.size()) {
+    const int s0 = base + 4 * g.lane();
     int hit = INT_MAX;
-    if (s < n_starts) {
-      int j = 0;
-      while (j < P && t[s + j] == piece[j]) j++;
-      if (j == P) hit = s;
+    if (s0 < n_starts) {
+      const uint64_t w0 = wfa_ld64u(t + s0), w1 = wfa_ld64u(t + s0 + 8);
+      for (int a = 3; a >= 0; a--) {
+        const uint64_t win = a ? ((w0 >> (8 * a)) | (w1 << (64 - 8 * a))) : w0;
+        if (win == key && s0 + a < n_starts && wfa_match_len(piece + 8, t + s0 + a + 8, P - 8) == P - 8) hit = s0 + a;
+      }
     }
     hit = g.min_i(hit);
     if (hit != INT_MAX) return hit;
   }
   return -1;
+}
+
+// ---------------------------------------------------------------- seed filter ----------------
+
+// Diagonal band that provably contains every alignment of the whole pattern with cost <= S.
+// Such an alignment has at most S / min(x, o+e) mismatches and gaps, so of nb = that + 1
+// disjoint pattern blocks one is copied without any edit and shows up as an exact occurrence in the
+// text; the total gap length is at most (S - o) / e, which bounds how far the path strays from that
+// occurrence's diagonal.  Band = [min - R, max + R] over all exact block occurrences.
+// keys: scratch for 32 uint64 owned by the group.  Returns false if no band can be given (no
+// occurrence, blocks too short to be selective).
+template <class G>
+TRGT_HD bool flank_seed_band(const G &g, const WfaProb &pr, int S, uint64_t *keys, int *klo, int *khi) {
+  const int emin = wfa_imin(pr.x, pr.oe);
+  const int nb = S / emin + 1;
+  if (nb > 32) return false;
+  const int blen = pr.P / nb;
+  if (blen < 12 || pr.T < blen) return false;
+  const int o = pr.oe - pr.e;
+  const int R = S > o ? (S - o) / pr.e : 0;
+  for (int b = g.lane(); b < nb; b += g.size()) keys[b] = wfa_ld64u(pr.p + b * blen);
+  g.sync();
+  int kmin = INT_MAX, kmax = INT_MIN;
+  const int n_pos = pr.T - blen + 1;
+  for (int j = g.lane(); j < n_pos; j += g.size()) {
+    const uint64_t tw = wfa_ld64u(pr.t + j);
+    for (int b = 0; b < nb; b++) {
+      if (tw == keys[b] && wfa_match_len(pr.p + b * blen + 8, pr.t + j + 8, blen - 8) == blen - 8) {
+        const int k = j - b * blen;
+        kmin = wfa_imin(kmin, k);
+        kmax = wfa_imax(kmax, k);
+      }
+    }
+  }
+  kmin = g.min_i(kmin);
+  kmax = g.max_i(kmax);
+  g.sync();
+  if (kmin == INT_MAX) return false;
+  *klo = wfa_imax(-pr.P, kmin - R);
+  *khi = wfa_imin(pr.T, kmax + R);
+  // Offsets on band diagonals must stay clear of the text end: there the full computation drops
+  // cells whose insertion candidate runs past T, which a banded run could not reproduce.
+  if (*khi + pr.P >= pr.T) return false;
+  return true;
+}
+
+struct FlankHit {
+  int via;      // TRGT_VIA_* of include/trgt_engine.h: 2 accepted, 3 rejected
+  int matches;  // count_matches
+  int score;    // -cost
+  int start, end;
+};
+
+// WFA fallback of find_spans (span_locater.rs:14-25) for one (piece, read) pair without ever
+// building the T+1 wide wavefront: seed filter -> banded score pass (cost cap S) -> cone trace.
+// `pr` is the unbanded flank problem (pbf = pef = 0, tbf = tef = T).  ws: ws_ints ints of group
+// scratch (on chip), keys: 32 uint64.  Returns 0 and fills *hit (lane 0's copy is authoritative),
+// or 1 if this pair needs the full-width path (no seed, cost > S, scratch too small).
+template <class G>
+TRGT_HD int flank_locate_banded(const G &g, const WfaProb &pr, int S, double min_flank_id_frac, uint64_t *keys,
+                                int *ws, size_t ws_ints, FlankHit *hit) {
+  int klo, khi;
+  if (!flank_seed_band(g, pr, S, keys, &klo, &khi)) return 1;
+  WfaProb bp = pr;
+  bp.blo = klo; bp.bhi = khi;
+  if (wfa_ring_ints(bp) > ws_ints) return 1;
+  const WfaEnd end = wfa_score_ring(g, bp, ws, S);
+  g.sync();
+  if (end.status != TRGT_WFA_OK) return 1;
+  if (wfa_trace_ints(pr, end.s) > ws_ints) return 1;
+  if (wfa_trace_forward(g, pr, end.s, end.k, ws, ws_ints) != 0) return 1;
+  if (g.lane() == 0) {
+    WfaFlankSink sink(pr.T);
+    wfa_backtrace(pr, end.s, end.k, end.off, ws, sink);
+    hit->matches = sink.matches;
+    hit->score = -end.s;
+    if ((double)sink.matches >= (double)pr.P * min_flank_id_frac) {  // span_locater.rs:19-25, :46
+      hit->via = 2; hit->start = sink.ystart(); hit->end = sink.yend();
+    } else {
+      hit->via = 3; hit->start = 0; hit->end = 0;
+    }
+  }
+  g.sync();
+  return 0;
 }
 
 // ---------------------------------------------------------------- unit-cost edit distance ------

@@ -56,6 +56,7 @@ HIT_DTYPE = np.dtype([("via", np.int32), ("matches", np.int32), ("score", np.int
 EXPORTS = [
     "trgt_engine_create", "trgt_engine_destroy", "trgt_engine_last_error", "trgt_last_create_error",
     "trgt_engine_stream", "trgt_engine_sm_count", "trgt_engine_sync", "trgt_engine_set_workspace_budget",
+    "trgt_engine_set_flank_band_budget",
     "trgt_host_alloc", "trgt_host_free",
     "trgt_flank_spans", "trgt_align_e2e", "trgt_edit_dist", "trgt_hmm_label",
     "trgt_flank_upload", "trgt_flank_run", "trgt_flank_download", "trgt_flank_free", "trgt_flank_device_views",
@@ -96,6 +97,8 @@ def load_library(build: bool = True):
     L.trgt_engine_sync.argtypes = [vp]
     L.trgt_engine_set_workspace_budget.argtypes = [vp, C.c_size_t]
     L.trgt_engine_set_workspace_budget.restype = None
+    L.trgt_engine_set_flank_band_budget.argtypes = [vp, i32]
+    L.trgt_engine_set_flank_band_budget.restype = None
     L.trgt_host_alloc.argtypes = [C.c_size_t]
     L.trgt_host_alloc.restype = vp
     L.trgt_host_free.argtypes = [vp]
@@ -273,6 +276,9 @@ class Engine:
 
     def set_workspace_budget(self, nbytes: int):
         self._L.trgt_engine_set_workspace_budget(self._h, nbytes)
+
+    def set_flank_band_budget(self, max_cost: int):
+        self._L.trgt_engine_set_flank_band_budget(self._h, max_cost)
 
     # -- instrumentation ------------------------------------------------------------------
     def set_profiling(self, on: bool):
