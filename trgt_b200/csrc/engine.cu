@@ -383,6 +383,7 @@ size_t ring_ints_bound(int x, int oe, int e, int Pmax, int Tmax) {
   WfaProb pr;
   memset(&pr, 0, sizeof pr);
   pr.x = x; pr.oe = oe; pr.e = e; pr.P = Pmax; pr.T = Tmax;
+  wfa_unband(pr);
   return wfa_ring_ints(pr);
 }
 
