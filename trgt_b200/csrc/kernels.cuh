@@ -113,7 +113,7 @@ __device__ __forceinline__ const uint8_t *stage_bytes(const uint8_t *src, int by
 // (:14-25) through the seed filter + banded pass + cone trace of wfa_core.h, all from the staged copy
 // of the read.  Pairs the banded path cannot settle are appended to `work` as 2*read+side for the
 // full-width kernels below.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_flank_locate(WfaSrc src, uint32_t n_reads, int band_budget, double min_flank_id_frac,
                trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work, Counters *ctr) {
   extern __shared__ __align__(16) unsigned char smem_b[];
@@ -191,6 +191,61 @@ __global__ void k_wfa_score(WfaSrc src, const uint32_t *__restrict__ work, const
     slot = blockIdx.x * (blockDim.x >> 5) + wib; n_slots = gridDim.x * (blockDim.x >> 5);
     my_smem = smem_i + (size_t)wib * smem_ring_ints;
     lane0 = (threadIdx.x & 31u) == 0;
+  }
+  // warp variant, end-to-end mode: lanes first test 32 pairs for identity (most repeat sequences of a
+  // haplotype equal their backbone), then the warp aligns the remaining ones one at a time
+  if (!BLOCK && src.mode == WFA_MODE_E2E) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = slot * 32u; base < n; base += n_slots * 32u) {
+      const uint32_t i = base + lane;
+      bool pending = false;
+      if (i < n) {
+        const uint32_t id = work ? work[i] : i;
+        const WfaProb pr = wfa_prob_of(src, id);
+        if (pr.P == pr.T && (pr.P == 0 || wfa_match_len(pr.p, pr.t, pr.P) == pr.P)) {
+          WfaEnd end;
+          end.status = TRGT_WFA_OK; end.s = 0; end.k = 0; end.off = pr.T;
+          ends[i] = end;
+          cig_n[id] = pr.P > 0 ? 1u : 0u;  // a single '=' run
+        } else {
+          pending = true;
+        }
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, pending);
+      while (todo) {
+        const uint32_t src_lane = (uint32_t)__ffs((int)todo) - 1u;
+        todo &= todo - 1u;
+        const uint32_t ii = base + src_lane;
+        const uint32_t id = work ? work[ii] : ii;
+        const WfaProb pr = wfa_prob_of(src, id);
+        const size_t need = wfa_ring_ints(pr);
+        int *ring = (need <= (size_t)smem_ring_ints) ? my_smem : (gring ? gring + (size_t)slot * gring_stride : nullptr);
+        WfaEnd end;
+        if (ring == nullptr || (ring != my_smem && need > gring_stride)) {
+          end.status = TRGT_WFA_OOM; end.s = 0; end.k = 0; end.off = 0;
+        } else {
+          const WarpGroup g;
+          end = wfa_score_ring(g, pr, ring, wfa_score_cap(pr));
+          __syncwarp();
+        }
+        if (lane0) {
+          ends[ii] = end;
+          if (end.status != TRGT_WFA_OK) {
+            atomicAdd(&ctr->n_failed, 1u);
+            cig_n[id] = 0;
+          } else if (end.s == 0) {
+            cig_n[id] = pr.P > 0 ? 1u : 0u;
+          } else {
+            const unsigned int t = atomicAdd(&ctr->n_trace, 1u);
+            trace_work[t] = id;
+            const unsigned long long wb = 2ull * (unsigned long long)end.s + 8ull;
+            atomicAdd(&ctr->words_bound, wb);
+            atomicMax(&ctr->max_trace_ints, (unsigned long long)wfa_trace_ints(pr, end.s) + wb);
+          }
+        }
+      }
+    }
+    return;
   }
   for (uint32_t i = slot; i < n; i += n_slots) {
     const uint32_t id = work ? work[i] : i;

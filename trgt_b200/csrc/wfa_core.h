@@ -347,6 +347,58 @@ TRGT_HD int wfa_trace_forward(const G &g, const WfaProb &pr, int s_end, int k_en
   return 0;
 }
 
+// Forward pass inside the band [pr.blo, pr.bhi] that keeps every wavefront (same layout as
+// wfa_trace_forward, so wfa_backtrace can run on it) and stops at the first score whose wavefront
+// satisfies the end condition.  Cells a band drops only ever lower the offsets of cells that are not
+// on a cost-optimal alignment inside the band, so when every optimal alignment is known to lie
+// inside the band (flank_seed_band) both the end cell and the back-trace equal the unbanded run's.
+template <class G>
+TRGT_HD WfaEnd wfa_forward_band_hist(const G &g, const WfaProb &pr, int s_cap, int *ws, size_t cap_ints) {
+  WfaEnd out;
+  out.status = TRGT_WFA_OK; out.s = 0; out.k = 0; out.off = 0;
+  size_t top = (size_t)TRGT_WFA_META * ((size_t)s_cap + 1);
+  if (top > cap_ints) { out.status = TRGT_WFA_OOM; return out; }
+  for (int s = 0; s <= s_cap; s++) {
+    int lo, hi;
+    bool live;
+    WfaView vx = wfa_null_view(), vo = wfa_null_view(), ve = wfa_null_view();
+    if (s == 0) {
+      lo = wfa_imax(-pr.pbf, pr.blo); hi = wfa_imin(pr.tbf, pr.bhi); live = lo <= hi;
+    } else {
+      vx = wfa_hist_view(ws, s - pr.x);
+      vo = wfa_hist_view(ws, s - pr.oe);
+      ve = wfa_hist_view(ws, s - pr.e);
+      live = wfa_next_range(pr, vx, vo, ve, &lo, &hi);
+    }
+    if (!live) { lo = 1; hi = 0; }
+    const size_t w = live ? (size_t)(hi - lo + 1) : 0;
+    const size_t need = w * (s == 0 ? 1 : 3);
+    if (top + need > cap_ints) { out.status = TRGT_WFA_OOM; return out; }
+    g.sync();
+    if (g.lane() == 0) {
+      int *meta = ws + (size_t)TRGT_WFA_META * s;
+      meta[0] = lo; meta[1] = hi; meta[2] = lo; meta[3] = hi;
+      meta[4] = (int)(unsigned)(top & 0xffffffffu);
+      meta[5] = (int)(unsigned)(top >> 32);
+    }
+    g.sync();
+    if (live) {
+      const WfaView dst = wfa_hist_view(ws, s);
+      if (s == 0) wfa_init(g, pr, dst);
+      else wfa_compute(g, pr, vx, vo, ve, dst);
+      g.sync();
+      const int kmin = wfa_terminated(g, pr, dst);
+      if (kmin != INT_MAX) {
+        out.s = s; out.k = kmin; out.off = dst.m[kmin - dst.base];
+        return out;
+      }
+    }
+    top += need;
+  }
+  out.status = TRGT_WFA_MAX_STEPS;
+  return out;
+}
+
 // Back-trace from (s_end, k_end) through the history in ws; ops are handed to the sink from the
 // LAST operation to the first.  One lane.
 template <class Sink>
@@ -545,36 +597,41 @@ struct FlankHit {
 };
 
 // WFA fallback of find_spans (span_locater.rs:14-25) for one (piece, read) pair without ever
-// building the T+1 wide wavefront: seed filter -> banded score pass (cost cap S) -> cone trace.
-// `pr` is the unbanded flank problem (pbf = pef = 0, tbf = tef = T).  ws: ws_ints ints of group
-// scratch (on chip), keys: 32 uint64.  Returns 0 and fills *hit (lane 0's copy is authoritative),
-// or 1 if this pair needs the full-width path (no seed, cost > S, scratch too small).
+// building the T+1 wide wavefront: seed filter -> banded forward pass with history -> back-trace.
+// Two cost tiers: first the cost of a single mismatch or one-base gap (most HiFi misses), then the
+// caller's budget S.  `pr` is the unbanded flank problem (pbf = pef = 0, tbf = tef = T).
+// ws: ws_ints ints of group scratch (on chip), keys: 32 uint64.  Returns 0 and fills *hit (lane 0's
+// copy is authoritative), or 1 if this pair needs the full-width path (no seed, cost > S, scratch
+// too small).
 template <class G>
 TRGT_HD int flank_locate_banded(const G &g, const WfaProb &pr, int S, double min_flank_id_frac, uint64_t *keys,
                                 int *ws, size_t ws_ints, FlankHit *hit) {
-  int klo, khi;
-  if (!flank_seed_band(g, pr, S, keys, &klo, &khi)) return 1;
-  WfaProb bp = pr;
-  bp.blo = klo; bp.bhi = khi;
-  if (wfa_ring_ints(bp) > ws_ints) return 1;
-  const WfaEnd end = wfa_score_ring(g, bp, ws, S);
-  g.sync();
-  if (end.status != TRGT_WFA_OK) return 1;
-  if (wfa_trace_ints(pr, end.s) > ws_ints) return 1;
-  if (wfa_trace_forward(g, pr, end.s, end.k, ws, ws_ints) != 0) return 1;
-  if (g.lane() == 0) {
-    WfaFlankSink sink(pr.T);
-    wfa_backtrace(pr, end.s, end.k, end.off, ws, sink);
-    hit->matches = sink.matches;
-    hit->score = -end.s;
-    if ((double)sink.matches >= (double)pr.P * min_flank_id_frac) {  // span_locater.rs:19-25, :46
-      hit->via = 2; hit->start = sink.ystart(); hit->end = sink.yend();
-    } else {
-      hit->via = 3; hit->start = 0; hit->end = 0;
+  const int tier1 = wfa_imin(S, wfa_imax(pr.x, pr.oe));
+  for (int tier = 0; tier < 2; tier++) {
+    const int cap = tier == 0 ? tier1 : S;
+    if (tier == 1 && S <= tier1) break;
+    int klo, khi;
+    if (!flank_seed_band(g, pr, cap, keys, &klo, &khi)) continue;
+    WfaProb bp = pr;
+    bp.blo = klo; bp.bhi = khi;
+    const WfaEnd end = wfa_forward_band_hist(g, bp, cap, ws, ws_ints);
+    g.sync();
+    if (end.status != TRGT_WFA_OK) continue;
+    if (g.lane() == 0) {
+      WfaFlankSink sink(pr.T);
+      wfa_backtrace(pr, end.s, end.k, end.off, ws, sink);
+      hit->matches = sink.matches;
+      hit->score = -end.s;
+      if ((double)sink.matches >= (double)pr.P * min_flank_id_frac) {  // span_locater.rs:19-25, :46
+        hit->via = 2; hit->start = sink.ystart(); hit->end = sink.yend();
+      } else {
+        hit->via = 3; hit->start = 0; hit->end = 0;
+      }
     }
+    g.sync();
+    return 0;
   }
-  g.sync();
-  return 0;
+  return 1;
 }
 
 // ---------------------------------------------------------------- unit-cost edit distance ------
