@@ -8,15 +8,28 @@
 
 #include "../../trgt_b200/csrc/hmm_core.h"
 #include "../../trgt_b200/csrc/hmm_host.h"
+#include "lanes.h"
 
 using namespace trgt;
 
 extern "C" {
 
 // returns n_spans (collapsed) or <0; path_out gets Hmm::label (forward order), *path_len its length
+long emu_hmm_annotate_lanes(const uint8_t *motifs, const uint64_t *moff, int nm, const uint8_t *allele, int L,
+                            uint32_t *mc, HmmSpan *spans, uint32_t span_cap, double *purity,
+                            uint32_t *path_out, uint64_t path_cap, uint64_t *path_len, int *S_out, int lanes);
+
 long emu_hmm_annotate(const uint8_t *motifs, const uint64_t *moff, int nm, const uint8_t *allele, int L,
                       uint32_t *mc, HmmSpan *spans, uint32_t span_cap, double *purity,
                       uint32_t *path_out, uint64_t path_cap, uint64_t *path_len, int *S_out) {
+  return emu_hmm_annotate_lanes(motifs, moff, nm, allele, L, mc, spans, span_cap, purity, path_out, path_cap,
+                                path_len, S_out, 0);
+}
+
+// lanes == 0: one serial lane (SerialGroup); otherwise that many lock-step host threads
+long emu_hmm_annotate_lanes(const uint8_t *motifs, const uint64_t *moff, int nm, const uint8_t *allele, int L,
+                            uint32_t *mc, HmmSpan *spans, uint32_t span_cap, double *purity,
+                            uint32_t *path_out, uint64_t path_cap, uint64_t *path_len, int *S_out, int lanes) {
   static HmmJumpTable jt;
   int max_len = 0;
   int mbytes = 0;
@@ -36,8 +49,18 @@ long emu_hmm_annotate(const uint8_t *motifs, const uint64_t *moff, int nm, const
   std::vector<uint16_t> o_stblk(S_guess + 8);
   HmmModel model;
   SerialGroup g;
-  const int S = hmm_model_build(g, motifs, moff, nm, jt.off.data(), o_bytes.data(), o_moff.data(),
-                                o_mmoff.data(), o_n.data(), o_ms.data(), o_stblk.data(), &model);
+  int S = 0;
+  if (lanes == 0) {
+    S = hmm_model_build(g, motifs, moff, nm, jt.off.data(), o_bytes.data(), o_moff.data(), o_mmoff.data(),
+                        o_n.data(), o_ms.data(), o_stblk.data(), &model);
+  } else {
+    trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &lg) {
+      HmmModel m2;
+      const int s2 = hmm_model_build(lg, motifs, moff, nm, jt.off.data(), o_bytes.data(), o_moff.data(),
+                                     o_mmoff.data(), o_n.data(), o_ms.data(), o_stblk.data(), &m2);
+      if (lg.lane() == 0) { S = s2; model = m2; }
+    });
+  }
   if (S < 0) return -400;
   if (S != S_guess) return -401;
   if (S_out) *S_out = S;
@@ -49,7 +72,13 @@ long emu_hmm_annotate(const uint8_t *motifs, const uint64_t *moff, int nm, const
   }
   std::vector<double> sc0(S), sc1(S);
   std::vector<uint8_t> bp((size_t)(L + 2) * S, 0xEE);
-  hmm_viterbi(g, model, c, jt.lp.data(), allele, L, sc0.data(), sc1.data(), bp.data());
+  if (lanes == 0) {
+    hmm_viterbi(g, model, c, jt.lp.data(), allele, L, sc0.data(), sc1.data(), bp.data());
+  } else {
+    trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &lg) {
+      hmm_viterbi(lg, model, c, jt.lp.data(), allele, L, sc0.data(), sc1.data(), bp.data());
+    });
+  }
   // counting walk, then writing walk (as the device does)
   std::vector<uint32_t> mc_tmp(nm + 1, 0);
   std::vector<uint32_t> rev(path_cap ? path_cap : 1);

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../trgt_b200/csrc/wfa_core.h"
+#include "lanes.h"
 
 using namespace trgt;
 
@@ -81,6 +82,81 @@ int emu_flank_banded(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int
 
 int emu_edit_distance(const uint8_t *a, int la, const uint8_t *b, int lb) {
   return edit_distance_128(a, la, b, lb);
+}
+
+}  // extern "C"
+
+// ---- the same entry points with N lock-step host lanes instead of one --------------------------
+
+extern "C" {
+
+int emu_wfa_align_lanes(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x, int o, int e, int pbf, int pef,
+                        int tbf, int tef, int *out, uint32_t *words, uint32_t words_cap, int lanes) {
+  std::vector<uint8_t> pbuf(P + 16, 0), tbuf(T + 16, 0);
+  memcpy(pbuf.data(), p_in, P);
+  memcpy(tbuf.data(), t_in, T);
+  WfaProb pr;
+  pr.p = pbuf.data(); pr.P = P; pr.t = tbuf.data(); pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
+  pr.pbf = pbf; pr.pef = pef; pr.tbf = tbf; pr.tef = tef;
+  wfa_unband(pr);
+  std::vector<int> ring(wfa_ring_ints(pr) + 1, 0x7ead);
+  WfaEnd end{};
+  trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &g) {
+    const WfaEnd e2 = wfa_score_ring(g, pr, ring.data(), wfa_score_cap(pr));
+    if (g.lane() == 0) end = e2;
+  });
+  out[0] = end.status; out[1] = -end.s; out[2] = end.k; out[3] = end.off;
+  if (end.status != TRGT_WFA_OK) return end.status;
+  const size_t need = wfa_trace_ints(pr, end.s);
+  std::vector<int> ws(need + 1, 0x7ead);
+  int rc = 0;
+  trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &g) {
+    const int r = wfa_trace_forward(g, pr, end.s, end.k, ws.data(), need);
+    if (g.lane() == 0) rc = r;
+  });
+  if (rc != 0) { out[0] = rc; return rc; }
+  WfaFlankSink fs(T);
+  wfa_backtrace(pr, end.s, end.k, end.off, ws.data(), fs);
+  out[4] = fs.matches; out[5] = fs.ystart(); out[6] = fs.yend();
+  WfaCigarSink cs(words, words_cap);
+  wfa_backtrace(pr, end.s, end.k, end.off, ws.data(), cs);
+  out[7] = (int)cs.finish();
+  return 0;
+}
+
+int emu_flank_scan_lanes(const uint8_t *piece, int P, const uint8_t *t, int T, int lanes) {
+  std::vector<uint8_t> pbuf(P + 16, 0), tbuf(T + 32, 0);
+  memcpy(pbuf.data(), piece, P);
+  if (T > 0) memcpy(tbuf.data(), t, T);
+  int res = -2;
+  trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &g) {
+    const int r = flank_scan(g, pbuf.data(), P, tbuf.data(), T);
+    if (g.lane() == 0) res = r;
+  });
+  return res;
+}
+
+int emu_flank_banded_lanes(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x, int o, int e, int S,
+                           double frac, int ws_ints, int *out, int lanes) {
+  std::vector<uint8_t> pbuf(P + 16, 0), tbuf(T + 16, 0);
+  memcpy(pbuf.data(), p_in, P);
+  memcpy(tbuf.data(), t_in, T);
+  WfaProb pr;
+  pr.p = pbuf.data(); pr.P = P; pr.t = tbuf.data(); pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
+  pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;
+  wfa_unband(pr);
+  std::vector<int> ws(ws_ints + 1, 0x7ead);
+  uint64_t keys[32];
+  FlankHit hit = {0, 0, 0, 0, 0};
+  int rc = -1;
+  trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &g) {
+    FlankHit h = {0, 0, 0, 0, 0};
+    const int r = flank_locate_banded(g, pr, S, frac, keys, ws.data(), (size_t)ws_ints, &h);
+    if (g.lane() == 0) { rc = r; hit = h; }
+  });
+  out[0] = rc;
+  out[1] = hit.via; out[2] = hit.matches; out[3] = hit.score; out[4] = hit.start; out[5] = hit.end;
+  return rc;
 }
 
 }  // extern "C"

@@ -238,3 +238,85 @@ def test_flank_banded_core(emul, oracle):
             if exp is not None:
                 assert (out[4], out[5]) == exp
     assert resolved > 300
+
+
+# ---- the same cores with several lock-step host lanes (tests/emul/lanes.h): leader election,
+# ---- broadcasts and barrier placement are exercised, not just the index arithmetic --------------
+
+@pytest.mark.parametrize("lanes", [4, 32])
+def test_wfa_core_multilane(emul, oracle, lanes):
+    rng = random.Random(100 + lanes)
+    for it in range(120):
+        x, o, e = rng.choice([(2, 5, 1), (1, 0, 1), (4, 6, 2)])
+        if it % 2 == 0:
+            p = rnd(rng, rng.randint(20, 120))
+            t = rnd(rng, rng.randint(0, 200)) + mutate(rng, p, rng.choice([0, 0.02, 0.1])) + rnd(rng, rng.randint(0, 200))
+            ef = (0, 0, len(t), len(t))
+        else:
+            p = rnd(rng, rng.randint(1, 150))
+            t = mutate(rng, p, rng.choice([0, 0.03, 0.2])) or b"C"
+            ef = None
+        a = oracle.wfa_align(p, t, oracle.AFFINE, x, o, e, ends_free=ef)
+        out = (C.c_int * 9)()
+        cap = 2 * (len(p) + len(t)) + 16
+        words = (C.c_uint32 * cap)()
+        pbf, pef, tbf, tef = ef if ef else (0, 0, 0, 0)
+        rc = emul.emu_wfa_align_lanes(p, len(p), t, len(t), x, o, e, pbf, pef, tbf, tef, out, words, cap, lanes)
+        assert rc == 0
+        assert (out[1], out[2], out[3], out[4]) == (a.score, a.end_k, a.end_offset, a.count_matches())
+        assert list(words[:out[7]]) == a.sam_cigar(True)
+
+
+@pytest.mark.parametrize("lanes", [4, 32])
+def test_flank_locate_multilane(emul, oracle, lanes):
+    emul.emu_flank_banded_lanes.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), C.c_int]
+    rng = random.Random(200 + lanes)
+    resolved = 0
+    for it in range(150):
+        P = rng.choice([120, 250])
+        if it % 3 == 0:
+            unit = rnd(rng, rng.randint(2, 7))
+            p = mutate(rng, (unit * (P // len(unit) + 1))[:P], 0.03)[:P]
+        else:
+            p = rnd(rng, P)
+        t = rnd(rng, rng.randint(0, 400)) + mutate(rng, p, rng.choice([0.0, 0.004, 0.01, 0.03])) + rnd(rng, rng.randint(260, 500))
+        assert emul.emu_flank_scan_lanes(p, len(p), t, len(t), lanes) == t.find(p)
+        exp, via, nm = oracle.find_span(p, t, (2, 5, 1), len(p) * 0.7)
+        if via == 1:
+            continue
+        out = (C.c_int * 6)()
+        rc = emul.emu_flank_banded_lanes(p, len(p), t, len(t), 2, 5, 1, 20, 0.7, 1536, out, lanes)
+        if rc == 0:
+            resolved += 1
+            assert (out[1], out[2]) == (via, nm)
+            if exp is not None:
+                assert (out[4], out[5]) == exp
+    assert resolved > 15
+
+
+@pytest.mark.parametrize("lanes", [3, 32])
+def test_hmm_core_multilane(emul, oracle, lanes):
+    emul.emu_hmm_annotate_lanes.restype = C.c_long
+    rng = random.Random(300 + lanes)
+    for _ in range(60):
+        k = rng.choice([1, 1, 2, 5])
+        motifs = [rnd(rng, rng.choice([1, 2, 3, 4, 6, 12]), "ACGTN" if rng.random() < 0.2 else "ACGT") for _ in range(k)]
+        allele = noisy_repeat(rng, motifs) or b"A"
+        h = oracle.Hmm([oracle.replace_invalid_bases(m, b"ATCGN") for m in motifs])
+        exp_mc, exp_sp, exp_pur = h.annotate(allele)
+        data = b"".join(motifs)
+        offs = [0]
+        for m in motifs:
+            offs.append(offs[-1] + len(m))
+        moff = (C.c_uint64 * len(offs))(*offs)
+        mc = (C.c_uint32 * (len(motifs) + 1))()
+        cap = len(allele) + 2
+        spans = (_Span * cap)()
+        pur, plen, S = C.c_double(), C.c_uint64(), C.c_int()
+        n = emul.emu_hmm_annotate_lanes(data, moff, len(motifs), allele, len(allele), mc, spans, cap, C.byref(pur),
+                                        None, C.c_uint64(0), C.byref(plen), C.byref(S), lanes)
+        assert n >= 0
+        assert list(mc[:len(motifs)]) == exp_mc
+        assert [(spans[i].m, spans[i].s, spans[i].e) for i in range(n)] == exp_sp
+        assert pur.value == exp_pur

@@ -31,6 +31,7 @@ struct SerialGroup {
   TRGT_HD int max_i(int v) const { return v; }
   TRGT_HD int any(int p) const { return p; }
   TRGT_HD int bcast0(int v) const { return v; }
+  TRGT_HD int bcast(int v, int /*src_lane*/) const { return v; }
 };
 
 #if defined(__CUDACC__)
@@ -43,6 +44,7 @@ struct WarpGroup {
   TRGT_D int max_i(int v) const { return __reduce_max_sync(0xffffffffu, v); }
   TRGT_D int any(int p) const { return __any_sync(0xffffffffu, p); }
   TRGT_D int bcast0(int v) const { return __shfl_sync(0xffffffffu, v, 0); }
+  TRGT_D int bcast(int v, int src_lane) const { return __shfl_sync(0xffffffffu, v, src_lane); }
 };
 
 // The whole CTA (blockDim.x threads, a multiple of 32, <= 1024) on one item.
@@ -72,8 +74,9 @@ struct BlockGroup {
     return r;
   }
   TRGT_D int any(int p) const { return __syncthreads_or(p); }
-  TRGT_D int bcast0(int v) const {
-    if (threadIdx.x == 0) scratch[32] = v;
+  TRGT_D int bcast0(int v) const { return bcast(v, 0); }
+  TRGT_D int bcast(int v, int src_lane) const {
+    if ((int)threadIdx.x == src_lane) scratch[32] = v;
     __syncthreads();
     int r = scratch[32];
     __syncthreads();

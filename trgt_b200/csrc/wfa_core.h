@@ -88,6 +88,23 @@ TRGT_HD int wfa_match_len(const uint8_t *a, const uint8_t *b, int n) {
   return n;
 }
 
+// the same, with the lanes of a group each comparing one 8-byte chunk per step (all lanes must
+// call with the same arguments)
+template <class G>
+TRGT_HD int wfa_coop_match_len(const G &g, const uint8_t *a, const uint8_t *b, int n) {
+  for (int base = 0; base < n; base += 8 * g.size()) {
+    const int i = base + 8 * g.lane();
+    int m = INT_MAX;
+    if (i < n) {
+      const uint64_t x = wfa_ld64u(a + i) ^ wfa_ld64u(b + i);
+      if (x) m = i + (wfa_ctz64(x) >> 3);
+    }
+    m = g.min_i(m);
+    if (m != INT_MAX) return m < n ? m : n;
+  }
+  return n;
+}
+
 struct WfaEnd {
   int status;
   int s;    // optimal cost (score = -s)
@@ -116,12 +133,35 @@ TRGT_HD WfaView wfa_null_view() {
   return v;
 }
 
-// match extension along diagonal k from text offset h
-TRGT_HD int wfa_extend(const WfaProb &pr, int k, int h) {
+// Match extension along diagonal k from text offset h, first 8 bytes only (done by the lane that
+// owns the diagonal).  *more is set when all 8 matched and bases remain: the group finishes such
+// diagonals together in wfa_extend_finish.
+TRGT_HD int wfa_extend8(const WfaProb &pr, int k, int h, int *more) {
   const int v = h - k;
   const int n = wfa_imin(pr.P - v, pr.T - h);
+  *more = 0;
   if (n <= 0 || pr.p[v] != pr.t[h]) return h;  // most diagonals of an ends-free wavefront stop here
-  return h + wfa_match_len(pr.p + v, pr.t + h, n);
+  const uint64_t x = wfa_ld64u(pr.p + v) ^ wfa_ld64u(pr.t + h);
+  const int m = x ? (wfa_ctz64(x) >> 3) : 8;
+  if (m >= n) return h + n;
+  if (m < 8) return h + m;
+  *more = 1;
+  return h + 8;
+}
+
+// Long extensions: one diagonal at a time, 8 bytes per lane per step.  `more`, k, h are this lane's
+// pending diagonal (more = 0: none); returns this lane's final offset.
+template <class G>
+TRGT_HD int wfa_extend_finish(const G &g, const WfaProb &pr, int more, int k, int h) {
+  for (;;) {
+    const int leader = g.min_i(more ? g.lane() : INT_MAX);
+    if (leader == INT_MAX) return h;
+    const int lk = g.bcast(k, leader), lh = g.bcast(h, leader);
+    const int lv = lh - lk;
+    const int n = wfa_imin(pr.P - lv, pr.T - lh);
+    const int m = wfa_coop_match_len(g, pr.p + lv, pr.t + lh, n);
+    if (g.lane() == leader) { h = lh + m; more = 0; }
+  }
 }
 
 // true diagonal range of wavefront s from its sources' true ranges; returns false if null
@@ -144,26 +184,34 @@ TRGT_HD bool wfa_next_range(const WfaProb &pr, const WfaView &vx, const WfaView 
 template <class G>
 TRGT_HD void wfa_compute(const G &g, const WfaProb &pr, const WfaView &vx, const WfaView &vo,
                          const WfaView &ve, const WfaView &dst) {
-  for (int k = dst.lo + g.lane(); k <= dst.hi; k += g.size()) {
-    const int i1 = wfa_imax(wfa_at(vo.m, vo, k - 1), wfa_at(ve.i, ve, k - 1)) + 1;
-    const int d1 = wfa_imax(wfa_at(vo.m, vo, k + 1), wfa_at(ve.d, ve, k + 1));
-    const int mm = wfa_at(vx.m, vx, k) + 1;
-    int mx = wfa_imax(mm, wfa_imax(i1, d1));
-    const int h = mx, v = mx - k;
-    if (mx < 0 || h > pr.T || v > pr.P || v < 0) mx = TRGT_WFA_NULL;
-    else mx = wfa_extend(pr, k, mx);
-    dst.i[k - dst.base] = i1;
-    dst.d[k - dst.base] = d1;
-    dst.m[k - dst.base] = mx;
+  for (int kb = dst.lo; kb <= dst.hi; kb += g.size()) {  // uniform trip count: the finish step is collective
+    const int k = kb + g.lane();
+    int mx = TRGT_WFA_NULL, more = 0;
+    if (k <= dst.hi) {
+      const int i1 = wfa_imax(wfa_at(vo.m, vo, k - 1), wfa_at(ve.i, ve, k - 1)) + 1;
+      const int d1 = wfa_imax(wfa_at(vo.m, vo, k + 1), wfa_at(ve.d, ve, k + 1));
+      const int mm = wfa_at(vx.m, vx, k) + 1;
+      mx = wfa_imax(mm, wfa_imax(i1, d1));
+      const int h = mx, v = mx - k;
+      if (mx < 0 || h > pr.T || v > pr.P || v < 0) mx = TRGT_WFA_NULL;
+      else mx = wfa_extend8(pr, k, mx, &more);
+      dst.i[k - dst.base] = i1;
+      dst.d[k - dst.base] = d1;
+    }
+    mx = wfa_extend_finish(g, pr, more, k, mx);
+    if (k <= dst.hi) dst.m[k - dst.base] = mx;
   }
 }
 
 // score-0 wavefront: M[k] = max(k, 0) on [-pbf, tbf], extended
 template <class G>
 TRGT_HD void wfa_init(const G &g, const WfaProb &pr, const WfaView &dst) {
-  for (int k = dst.lo + g.lane(); k <= dst.hi; k += g.size()) {
-    const int h = k >= 0 ? k : 0;
-    dst.m[k - dst.base] = wfa_extend(pr, k, h);
+  for (int kb = dst.lo; kb <= dst.hi; kb += g.size()) {
+    const int k = kb + g.lane();
+    int h = TRGT_WFA_NULL, more = 0;
+    if (k <= dst.hi) h = wfa_extend8(pr, k, k >= 0 ? k : 0, &more);
+    h = wfa_extend_finish(g, pr, more, k, h);
+    if (k <= dst.hi) dst.m[k - dst.base] = h;
   }
 }
 
@@ -531,16 +579,23 @@ TRGT_HD int flank_scan(const G &g, const uint8_t *piece, int P, const uint8_t *t
   const uint64_t key = wfa_ld64u(piece);
   for (int base = 0; base < n_starts; base += 4 * g.size()) {
     const int s0 = base + 4 * g.lane();
-    int hit = INT_MAX;
+    unsigned cand = 0;  // bit a: start s0 + a passes the 8-byte key test
     if (s0 < n_starts) {
       const uint64_t w0 = wfa_ld64u(t + s0), w1 = wfa_ld64u(t + s0 + 8);
-      for (int a = 3; a >= 0; a--) {
+      for (int a = 0; a < 4; a++) {
         const uint64_t win = a ? ((w0 >> (8 * a)) | (w1 << (64 - 8 * a))) : w0;
-        if (win == key && s0 + a < n_starts && wfa_match_len(piece + 8, t + s0 + a + 8, P - 8) == P - 8) hit = s0 + a;
+        if (win == key && s0 + a < n_starts) cand |= 1u << a;
       }
     }
-    hit = g.min_i(hit);
-    if (hit != INT_MAX) return hit;
+    // candidates in increasing order, each verified by the whole group (8 bytes per lane per step)
+    for (;;) {
+      int first = INT_MAX;
+      for (int a = 3; a >= 0; a--) if (cand & (1u << a)) first = s0 + a;
+      const int c = g.min_i(first);
+      if (c == INT_MAX) break;
+      if (wfa_coop_match_len(g, piece + 8, t + c + 8, P - 8) == P - 8) return c;
+      if (first == c) cand &= ~(1u << (c - s0));
+    }
   }
   return -1;
 }
@@ -567,18 +622,29 @@ TRGT_HD bool flank_seed_band(const G &g, const WfaProb &pr, int S, uint64_t *key
   g.sync();
   int kmin = INT_MAX, kmax = INT_MIN;
   const int n_pos = pr.T - blen + 1;
-  for (int j = g.lane(); j < n_pos; j += g.size()) {
-    const uint64_t tw = wfa_ld64u(pr.t + j);
-    for (int b = 0; b < nb; b++) {
-      if (tw == keys[b] && wfa_match_len(pr.p + b * blen + 8, pr.t + j + 8, blen - 8) == blen - 8) {
-        const int k = j - b * blen;
+  for (int jb = 0; jb < n_pos; jb += g.size()) {
+    const int j = jb + g.lane();
+    unsigned cand = 0;  // bit b: block b passes the 8-byte key test at text position j
+    if (j < n_pos) {
+      const uint64_t tw = wfa_ld64u(pr.t + j);
+      for (int b = 0; b < nb; b++) if (tw == keys[b]) cand |= 1u << b;
+    }
+    // key hits are rare: verify them one at a time with the whole group
+    for (;;) {
+      const int leader = g.min_i(cand ? g.lane() : INT_MAX);
+      if (leader == INT_MAX) break;
+      const unsigned lc = (unsigned)g.bcast((int)cand, leader);
+      int b = 0;
+      while (!(lc & (1u << b))) b++;
+      const int lj = jb + leader;
+      if (wfa_coop_match_len(g, pr.p + b * blen + 8, pr.t + lj + 8, blen - 8) == blen - 8) {
+        const int k = lj - b * blen;
         kmin = wfa_imin(kmin, k);
         kmax = wfa_imax(kmax, k);
       }
+      if (g.lane() == leader) cand &= ~(1u << b);
     }
   }
-  kmin = g.min_i(kmin);
-  kmax = g.max_i(kmax);
   g.sync();
   if (kmin == INT_MAX) return false;
   *klo = wfa_imax(-pr.P, kmin - R);
