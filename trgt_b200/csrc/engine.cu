@@ -42,6 +42,13 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+// grow-only pinned host buffer: D2H copies land here at full PCIe rate and callers read it in place
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  template <class T> T *as() { return (T *)p; }
+};
+
 struct CastU64 {
   __host__ __device__ unsigned long long operator()(const uint32_t &v) const { return (unsigned long long)v; }
 };
@@ -51,6 +58,7 @@ struct CastU64 {
 struct trgt_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D of read chunks, overlapped with phase A kernels
   int sm_count = 0;
   int smem_optin = 0;
   std::string error;
@@ -118,6 +126,23 @@ int dev_reserve(trgt_engine *e, DevBuf &b, size_t bytes, bool keep = false) {
   b.p = np;
   b.cap = ncap;
   return 0;
+}
+
+int pin_reserve(trgt_engine *e, PinBuf &b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return 0;
+  if (b.p) cudaFreeHost(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t ncap = bytes + bytes / 8 + 256;
+  CU(e, cudaMallocHost(&b.p, ncap));
+  b.cap = ncap;
+  return 0;
+}
+
+void pin_free(PinBuf &b) {
+  if (b.p) cudaFreeHost(b.p);
+  b.p = nullptr;
+  b.cap = 0;
 }
 
 void dev_free(DevBuf &b) {
@@ -271,6 +296,7 @@ int32_t trgt_engine_create(int32_t device, trgt_engine_t **out) {
   e->sm_count = prop.multiProcessorCount;
   e->smem_optin = (int)prop.sharedMemPerBlockOptin;
   if ((err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (err = cudaMallocHost((void **)&e->h_ctr, sizeof(Counters))) != cudaSuccess ||
       (err = cudaMallocHost((void **)&e->h_u64, 8 * sizeof(unsigned long long))) != cudaSuccess) {
     g_create_error = std::string("engine setup failed: ") + cudaGetErrorString(err);
@@ -298,6 +324,7 @@ void trgt_engine_destroy(trgt_engine_t *e) {
   if (e->h_ctr) cudaFreeHost(e->h_ctr);
   if (e->h_u64) cudaFreeHost(e->h_u64);
   cudaStreamDestroy(e->stream);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   delete e;
 }
 
@@ -450,7 +477,7 @@ void trgt_flank_free(trgt_engine_t *e, trgt_flank_batch_t *b) {
 static int flank_upload_into(trgt_engine_t *e, trgt_flank_batch *b, const trgt_seqs_t *left_pieces,
                              const trgt_seqs_t *right_pieces, const trgt_seqs_t *reads,
                              const uint32_t *locus_read_offsets, uint32_t n_loci, trgt_scoring_t scoring,
-                             double min_flank_id_frac) {
+                             double min_flank_id_frac, bool defer_read_bytes = false) {
   TRY(check_seqs(e, left_pieces, "left_pieces"));
   TRY(check_seqs(e, right_pieces, "right_pieces"));
   TRY(check_seqs(e, reads, "reads"));
@@ -472,7 +499,13 @@ static int flank_upload_into(trgt_engine_t *e, trgt_flank_batch *b, const trgt_s
   b->scoring = scoring;
   b->frac = min_flank_id_frac;
   CU(e, cudaSetDevice(e->device));
-  TRY(upload_seqs(e, reads, b->reads, b->read_off));
+  if (defer_read_bytes) {  // the caller streams the read bytes in chunks (flank_oneshot_locked)
+    static const uint64_t zero_off[1] = {0};
+    TRY(dev_reserve(e, b->reads, (size_t)(reads->n ? reads->offsets[reads->n] : 0) + 16));
+    TRY(h2d(e, b->read_off, reads->n ? reads->offsets : zero_off, (size_t)(reads->n + 1) * sizeof(uint64_t)));
+  } else {
+    TRY(upload_seqs(e, reads, b->reads, b->read_off));
+  }
   TRY(upload_seqs(e, left_pieces, b->lp, b->lp_off));
   TRY(upload_seqs(e, right_pieces, b->rp, b->rp_off));
   static const uint32_t zero32[1] = {0};
@@ -509,26 +542,24 @@ int32_t trgt_flank_upload(trgt_engine_t *e, const trgt_seqs_t *left_pieces, cons
   return 0;
 }
 
-static int flank_run_locked(trgt_engine_t *e, trgt_flank_batch *b) {
-  CU(e, cudaSetDevice(e->device));
-  if (b->n_reads == 0) return 0;
-  const WfaSrc src = flank_src(b);
+static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src, uint32_t r0, uint32_t r1) {
+  if (r1 <= r0) return 0;
+  const int block = 256;
+  const size_t smem = (size_t)(block / 32) * sizeof(FlankWarpSmem);
+  int grid = 0;
+  TRY(persistent_grid(e, k_flank_locate, block, smem, &grid));
+  const uint32_t need = (r1 - r0 + 7) / 8;
+  if ((uint32_t)grid > need) grid = (int)need;
+  LaunchScope ls(e, "k_flank_locate");
+  k_flank_locate<<<grid, block, smem, e->stream>>>(src, r0, r1, e->band_budget, b->frac, (trgt_flank_hit_t *)b->hits.p,
+                                                   (uint32_t *)b->work.p, (Counters *)b->ctr.p);
+  return check_launch(e, "k_flank_locate");
+}
+
+// pairs the on-chip path deferred: full-width score pass + cone trace; then the combine rule
+static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src) {
   Counters *ctr = (Counters *)b->ctr.p;
-  CU(e, cudaMemsetAsync(ctr, 0, sizeof(Counters), e->stream));
   {
-    const int block = 256;
-    const size_t smem = (size_t)(block / 32) * sizeof(FlankWarpSmem);
-    int grid = 0;
-    TRY(persistent_grid(e, k_flank_locate, block, smem, &grid));
-    const uint32_t need = (b->n_reads + 7) / 8;
-    if ((uint32_t)grid > need) grid = (int)need;
-    LaunchScope ls(e, "k_flank_locate");
-    k_flank_locate<<<grid, block, smem, e->stream>>>(src, b->n_reads, e->band_budget, b->frac,
-                                                     (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p, ctr);
-    TRY(check_launch(e, "k_flank_locate"));
-  }
-  {
-    // pass 1: one CTA per (read, flank) that missed; ring in shared memory when it fits
     const int block = 128;
     const size_t bound = ring_ints_bound(src.x, src.oe, src.e, b->Pmax, b->Tmax);
     const size_t cap_ints = 24 * 1024;  // 96 KB: two CTAs per SM
@@ -566,6 +597,52 @@ static int flank_run_locked(trgt_engine_t *e, trgt_flank_batch *b) {
   return 0;
 }
 
+static int flank_run_locked(trgt_engine_t *e, trgt_flank_batch *b) {
+  CU(e, cudaSetDevice(e->device));
+  if (b->n_reads == 0) return 0;
+  const WfaSrc src = flank_src(b);
+  CU(e, cudaMemsetAsync(b->ctr.p, 0, sizeof(Counters), e->stream));
+  TRY(flank_launch_locate(e, b, src, 0, b->n_reads));
+  return flank_finish(e, b, src);
+}
+
+// One-shot phase A from host buffers: the read bytes go up in chunks on the copy stream while the
+// locate kernel works on the chunks that have landed.
+static int flank_oneshot_locked(trgt_engine_t *e, trgt_flank_batch *b, const trgt_seqs_t *reads,
+                                const uint32_t *locus_read_offsets, uint32_t n_loci) {
+  CU(e, cudaSetDevice(e->device));
+  if (b->n_reads == 0) return 0;
+  const WfaSrc src = flank_src(b);
+  CU(e, cudaMemsetAsync(b->ctr.p, 0, sizeof(Counters), e->stream));
+  // the copy stream may start once everything queued so far (allocations, small uploads) is done
+  cudaEvent_t ready = get_event(e);
+  CU(e, cudaEventRecord(ready, e->stream));
+  CU(e, cudaStreamWaitEvent(e->copy_stream, ready, 0));
+  const uint64_t total = reads->offsets[reads->n];
+  const uint64_t chunk_bytes = 192ull << 20;
+  std::vector<cudaEvent_t> evs;
+  uint32_t l0 = 0;
+  while (l0 < n_loci) {
+    uint32_t l1 = l0 + 1;
+    const uint64_t b0 = reads->offsets[locus_read_offsets[l0]];
+    while (l1 < n_loci && reads->offsets[locus_read_offsets[l1 + 1]] - b0 <= chunk_bytes) l1++;
+    const uint64_t b1 = reads->offsets[locus_read_offsets[l1]];
+    if (b1 > b0)
+      CU(e, cudaMemcpyAsync((uint8_t *)b->reads.p + b0, reads->data + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, e->copy_stream));
+    cudaEvent_t ev = get_event(e);
+    evs.push_back(ev);
+    CU(e, cudaEventRecord(ev, e->copy_stream));
+    CU(e, cudaStreamWaitEvent(e->stream, ev, 0));
+    TRY(flank_launch_locate(e, b, src, locus_read_offsets[l0], locus_read_offsets[l1]));
+    l0 = l1;
+  }
+  (void)total;
+  const int rc = flank_finish(e, b, src);  // synchronises e->stream, hence every chunk event
+  e->event_pool.push_back(ready);
+  for (auto ev : evs) e->event_pool.push_back(ev);
+  return rc;
+}
+
 int32_t trgt_flank_run(trgt_engine_t *e, trgt_flank_batch_t *b) {
   if (!e || !b) return TRGT_ERR_ARG;
   std::lock_guard<std::mutex> lk(e->mu);
@@ -599,8 +676,8 @@ int32_t trgt_flank_spans(trgt_engine_t *e, const trgt_seqs_t *left_pieces, const
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->one_flank) e->one_flank = new trgt_flank_batch();
   TRY(flank_upload_into(e, e->one_flank, left_pieces, right_pieces, reads, locus_read_offsets, n_loci, scoring,
-                        min_flank_id_frac));
-  TRY(flank_run_locked(e, e->one_flank));
+                        min_flank_id_frac, /*defer_read_bytes=*/true));
+  TRY(flank_oneshot_locked(e, e->one_flank, reads, locus_read_offsets, n_loci));
   return flank_download_locked(e, e->one_flank, spans_out, hits_out);
 }
 
@@ -628,9 +705,7 @@ struct trgt_align_batch {
   DevBuf ends, trace_work, cig_n, cig_off, pool, ctr, gring, gws;
   DevBuf out_off, out_words, scores, status;
   // host copies handed out by download
-  std::vector<uint64_t> h_off;
-  std::vector<uint32_t> h_words;
-  std::vector<int32_t> h_scores, h_status;
+  PinBuf h_off, h_words, h_scores, h_status;
   unsigned long long total_words = 0;
   bool ran = false;
 };
@@ -665,6 +740,7 @@ void trgt_align_free(trgt_engine_t *e, trgt_align_batch_t *b) {
                    &b->cig_n, &b->cig_off, &b->pool, &b->ctr, &b->gring, &b->gws, &b->out_off, &b->out_words,
                    &b->scores, &b->status};
   for (auto *d : all) dev_free(*d);
+  pin_free(b->h_off); pin_free(b->h_words); pin_free(b->h_scores); pin_free(b->h_status);
   delete b;
 }
 
@@ -814,27 +890,28 @@ static int align_download_locked(trgt_engine_t *e, trgt_align_batch *b, trgt_cig
   if (!b->ran) return fail(e, TRGT_ERR_ARG, "trgt_align_download before trgt_align_run");
   CU(e, cudaSetDevice(e->device));
   const size_t n = b->n_seqs;
-  b->h_off.assign(n + 1, 0);
-  b->h_scores.assign(n, 0);
-  b->h_status.assign(n, 0);
+  TRY(pin_reserve(e, b->h_off, (n + 1) * sizeof(uint64_t)));
+  TRY(pin_reserve(e, b->h_scores, (n + 1) * sizeof(int32_t)));
+  TRY(pin_reserve(e, b->h_status, (n + 1) * sizeof(int32_t)));
+  b->h_off.as<uint64_t>()[0] = 0;
+  b->total_words = 0;
   if (n) {
-    CU(e, cudaMemcpyAsync(b->h_off.data(), b->out_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaMemcpyAsync(b->h_scores.data(), b->scores.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaMemcpyAsync(b->h_status.data(), b->status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(b->h_off.p, b->out_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(b->h_scores.p, b->scores.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(b->h_status.p, b->status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
-    b->total_words = b->h_off[n];
-    b->h_words.resize((size_t)b->total_words);
-    if (b->total_words)
-      CU(e, cudaMemcpyAsync(b->h_words.data(), b->out_words.p, (size_t)b->total_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    b->total_words = b->h_off.as<uint64_t>()[n];
+  }
+  TRY(pin_reserve(e, b->h_words, (size_t)(b->total_words + 1) * sizeof(uint32_t)));
+  if (b->total_words) {
+    CU(e, cudaMemcpyAsync(b->h_words.p, b->out_words.p, (size_t)b->total_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
-  } else {
-    b->h_words.clear();
   }
   out->n = n;
-  out->offsets = b->h_off.data();
-  out->words = b->h_words.data();
-  out->scores = b->h_scores.data();
-  out->status = b->h_status.data();
+  out->offsets = b->h_off.as<uint64_t>();
+  out->words = b->h_words.as<uint32_t>();
+  out->scores = b->h_scores.as<int32_t>();
+  out->status = b->h_status.as<int32_t>();
   return 0;
 }
 
@@ -907,11 +984,7 @@ struct trgt_hmm_batch {
   std::vector<unsigned long long> h_bp_off, h_mc_off;
   std::vector<std::pair<uint32_t, uint32_t>> waves;
   // host results
-  std::vector<uint64_t> r_mc_off, r_span_off, r_path_off;
-  std::vector<uint32_t> r_mc, r_paths;
-  std::vector<trgt_motif_span_t> r_spans;
-  std::vector<double> r_purity;
-  std::vector<int32_t> r_status;
+  PinBuf r_mc, r_span_off, r_spans, r_purity, r_status, r_path_off, r_paths;
   unsigned long long total_spans = 0, total_path = 0;
   bool ran = false;
 };
@@ -929,6 +1002,8 @@ void trgt_hmm_free(trgt_engine_t *e, trgt_hmm_batch_t *b) {
                    &b->bp_off, &b->mc_off, &b->bp, &b->mc, &b->purity, &b->n_spans, &b->span_off, &b->spans,
                    &b->path_len, &b->path_off, &b->paths, &b->status};
   for (auto *d : all) dev_free(*d);
+  PinBuf *pins[] = {&b->r_mc, &b->r_span_off, &b->r_spans, &b->r_purity, &b->r_status, &b->r_path_off, &b->r_paths};
+  for (auto *q : pins) pin_free(*q);
   delete b;
 }
 
@@ -1155,39 +1230,40 @@ static int hmm_download_locked(trgt_engine_t *e, trgt_hmm_batch *b, trgt_annotat
   if (!b->ran) return fail(e, TRGT_ERR_ARG, "trgt_hmm_download before trgt_hmm_run");
   CU(e, cudaSetDevice(e->device));
   const size_t n = b->n_alleles;
-  b->r_mc_off.assign(b->h_mc_off.begin(), b->h_mc_off.end());
-  if (b->r_mc_off.empty()) b->r_mc_off.assign(1, 0);
-  b->r_mc.assign((size_t)b->r_mc_off[n], 0);
-  b->r_span_off.assign(n + 1, 0);
-  b->r_spans.resize((size_t)b->total_spans);
-  b->r_purity.assign(n, 0.0);
-  b->r_status.assign(n, 0);
-  b->r_path_off.assign(n + 1, 0);
-  b->r_paths.resize((size_t)b->total_path);
+  static const uint64_t zero_off[1] = {0};
+  const size_t n_mc = b->h_mc_off.empty() ? 0 : (size_t)b->h_mc_off[n];
+  TRY(pin_reserve(e, b->r_mc, (n_mc + 1) * sizeof(uint32_t)));
+  TRY(pin_reserve(e, b->r_span_off, (n + 1) * sizeof(uint64_t)));
+  TRY(pin_reserve(e, b->r_spans, (size_t)(b->total_spans + 1) * sizeof(trgt_motif_span_t)));
+  TRY(pin_reserve(e, b->r_purity, (n + 1) * sizeof(double)));
+  TRY(pin_reserve(e, b->r_status, (n + 1) * sizeof(int32_t)));
+  TRY(pin_reserve(e, b->r_path_off, (n + 1) * sizeof(uint64_t)));
+  TRY(pin_reserve(e, b->r_paths, (size_t)(b->total_path + 1) * sizeof(uint32_t)));
+  b->r_span_off.as<uint64_t>()[0] = 0;
+  b->r_path_off.as<uint64_t>()[0] = 0;
   if (n) {
-    if (!b->r_mc.empty())
-      CU(e, cudaMemcpyAsync(b->r_mc.data(), b->mc.p, b->r_mc.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaMemcpyAsync(b->r_span_off.data(), b->span_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    if (n_mc) CU(e, cudaMemcpyAsync(b->r_mc.p, b->mc.p, n_mc * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(b->r_span_off.p, b->span_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
     if (b->total_spans)
-      CU(e, cudaMemcpyAsync(b->r_spans.data(), b->spans.p, (size_t)b->total_spans * sizeof(trgt_motif_span_t), cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaMemcpyAsync(b->r_purity.data(), b->purity.p, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaMemcpyAsync(b->r_status.data(), b->status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      CU(e, cudaMemcpyAsync(b->r_spans.p, b->spans.p, (size_t)b->total_spans * sizeof(trgt_motif_span_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(b->r_purity.p, b->purity.p, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(b->r_status.p, b->status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     if (b->want_paths) {
-      CU(e, cudaMemcpyAsync(b->r_path_off.data(), b->path_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+      CU(e, cudaMemcpyAsync(b->r_path_off.p, b->path_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
       if (b->total_path)
-        CU(e, cudaMemcpyAsync(b->r_paths.data(), b->paths.p, (size_t)b->total_path * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        CU(e, cudaMemcpyAsync(b->r_paths.p, b->paths.p, (size_t)b->total_path * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     }
     CU(e, cudaStreamSynchronize(e->stream));
   }
   out->n = n;
-  out->motif_count_offsets = b->r_mc_off.data();
-  out->motif_counts = b->r_mc.data();
-  out->span_offsets = b->r_span_off.data();
-  out->spans = b->r_spans.data();
-  out->purity = b->r_purity.data();
-  out->status = b->r_status.data();
-  out->path_offsets = b->want_paths ? b->r_path_off.data() : nullptr;
-  out->paths = b->want_paths ? b->r_paths.data() : nullptr;
+  out->motif_count_offsets = b->h_mc_off.empty() ? zero_off : (const uint64_t *)b->h_mc_off.data();
+  out->motif_counts = b->r_mc.as<uint32_t>();
+  out->span_offsets = b->r_span_off.as<uint64_t>();
+  out->spans = b->r_spans.as<trgt_motif_span_t>();
+  out->purity = b->r_purity.as<double>();
+  out->status = b->r_status.as<int32_t>();
+  out->path_offsets = b->want_paths ? b->r_path_off.as<uint64_t>() : nullptr;
+  out->paths = b->want_paths ? b->r_paths.as<uint32_t>() : nullptr;
   return 0;
 }
 

@@ -114,14 +114,14 @@ __device__ __forceinline__ const uint8_t *stage_bytes(const uint8_t *src, int by
 // of the read.  Pairs the banded path cannot settle are appended to `work` as 2*read+side for the
 // full-width kernels below.
 __global__ void __launch_bounds__(256, 3)
-k_flank_locate(WfaSrc src, uint32_t n_reads, int band_budget, double min_flank_id_frac,
+k_flank_locate(WfaSrc src, uint32_t r_begin, uint32_t r_end, int band_budget, double min_flank_id_frac,
                trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work, Counters *ctr) {
   extern __shared__ __align__(16) unsigned char smem_b[];
   const WarpGroup g;
   const int lane = g.lane();
   FlankWarpSmem &sm = reinterpret_cast<FlankWarpSmem *>(smem_b)[threadIdx.x >> 5];
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += warps) {
+  for (uint32_t r = r_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < r_end; r += warps) {
     const WfaProb pl = wfa_prob_of(src, 2 * r), prr = wfa_prob_of(src, 2 * r + 1);
     // stage read and pieces (cp.async, all requests in flight before the first wait)
     const uint8_t *t_s = stage_bytes(pl.t, pl.T, sm.txt, FL_TXT, lane);

@@ -220,10 +220,13 @@ class AnnotationBatch:
         return self.paths[int(self.path_offsets[i]):int(self.path_offsets[i + 1])].tolist()
 
 
-def _np_from(ptr, n, dtype):
+def _np_from(ptr, n, dtype, copy=True):
+    """numpy view of n elements at a ctypes pointer; copy=False aliases the engine's pinned result
+    buffer, which stays valid until the next call of the same kind on that engine."""
     if n == 0:
         return np.zeros(0, dtype=dtype)
-    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).copy()
+    a = np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype)
+    return a.copy() if copy else a
 
 
 class Engine:
@@ -404,27 +407,27 @@ class Engine:
         self._L.trgt_hmm_free(self._h, b)
 
     @staticmethod
-    def _cigars(out) -> "CigarBatch":
+    def _cigars(out, copy: bool = True) -> "CigarBatch":
         n = int(out.n)
-        offs = _np_from(out.offsets, n + 1, np.uint64)
+        offs = _np_from(out.offsets, n + 1, np.uint64, copy)
         total = int(offs[n]) if n else 0
-        return CigarBatch(offs, _np_from(out.words, total, np.uint32), _np_from(out.scores, n, np.int32),
-                          _np_from(out.status, n, np.int32))
+        return CigarBatch(offs, _np_from(out.words, total, np.uint32, copy), _np_from(out.scores, n, np.int32, copy),
+                          _np_from(out.status, n, np.int32, copy))
 
     @staticmethod
-    def _annotations(out, want_paths: bool) -> "AnnotationBatch":
+    def _annotations(out, want_paths: bool, copy: bool = True) -> "AnnotationBatch":
         n = int(out.n)
         mco = _np_from(out.motif_count_offsets, n + 1, np.uint64)
-        so = _np_from(out.span_offsets, n + 1, np.uint64)
+        so = _np_from(out.span_offsets, n + 1, np.uint64, copy)
         n_mc = int(mco[n]) if n else 0
         n_sp = int(so[n]) if n else 0
-        spans = _np_from(out.spans, 3 * n_sp, np.uint32).reshape(-1, 3)
-        res = AnnotationBatch(mco, _np_from(out.motif_counts, n_mc, np.uint32), so, spans,
-                              _np_from(out.purity, n, np.float64), _np_from(out.status, n, np.int32))
+        spans = _np_from(out.spans, 3 * n_sp, np.uint32, copy).reshape(-1, 3)
+        res = AnnotationBatch(mco, _np_from(out.motif_counts, n_mc, np.uint32, copy), so, spans,
+                              _np_from(out.purity, n, np.float64, copy), _np_from(out.status, n, np.int32, copy))
         if want_paths:
-            po = _np_from(out.path_offsets, n + 1, np.uint64)
+            po = _np_from(out.path_offsets, n + 1, np.uint64, copy)
             res.path_offsets = po
-            res.paths = _np_from(out.paths, int(po[n]) if n else 0, np.uint32)
+            res.paths = _np_from(out.paths, int(po[n]) if n else 0, np.uint32, copy)
         return res
 
     def pinned_array(self, nbytes: int) -> np.ndarray:
@@ -443,12 +446,14 @@ class Engine:
         return arr
 
     # -- phase B ---------------------------------------------------------------------------
-    def align_packed(self, backbones: PackedSeqs, seqs: PackedSeqs, group_seq_offsets: np.ndarray) -> CigarBatch:
+    def align_packed(self, backbones: PackedSeqs, seqs: PackedSeqs, group_seq_offsets: np.ndarray,
+                     copy: bool = True) -> CigarBatch:
+        """copy=False: the result arrays alias the engine's pinned buffers (valid until the next align call)"""
         gso = np.ascontiguousarray(group_seq_offsets, dtype=np.uint32)
         out = _Cigars()
         rc = self._L.trgt_align_e2e(self._h, backbones.ref(), seqs.ref(), gso.ctypes.data, len(backbones), C.byref(out))
         self._check(rc, "trgt_align_e2e")
-        return self._cigars(out)
+        return self._cigars(out, copy)
 
     def align(self, groups: Sequence[Tuple[bytes, Sequence[bytes]]]) -> List[List[List[Tuple[int, str]]]]:
         """utils::align (src/utils/align.rs:14-28) for many (backbone, seqs) groups."""
@@ -487,14 +492,14 @@ class Engine:
 
     # -- phase C ---------------------------------------------------------------------------
     def hmm_label_packed(self, motifs: PackedSeqs, locus_motif_offsets: np.ndarray, alleles: PackedSeqs,
-                         allele_locus: np.ndarray, want_paths: bool = False) -> AnnotationBatch:
+                         allele_locus: np.ndarray, want_paths: bool = False, copy: bool = True) -> AnnotationBatch:
         lmo = np.ascontiguousarray(locus_motif_offsets, dtype=np.uint32)
         al = np.ascontiguousarray(allele_locus, dtype=np.uint32)
         out = _Annotations()
         rc = self._L.trgt_hmm_label(self._h, motifs.ref(), lmo.ctypes.data, lmo.size - 1, alleles.ref(),
                                     al.ctypes.data if al.size else None, int(want_paths), C.byref(out))
         self._check(rc, "trgt_hmm_label")
-        return self._annotations(out, want_paths)
+        return self._annotations(out, want_paths, copy)
 
     def label_with_hmm(self, loci: Sequence[Tuple[Sequence[bytes], Sequence[bytes]]]) -> List[List[Annotation]]:
         """label_with_hmm (tr.rs:454-492) for many loci: loci = [(motifs, allele_seqs)]."""

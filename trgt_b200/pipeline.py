@@ -66,8 +66,9 @@ class HotPath:
                                              w.min_flank_id_frac, want_hits=self.want_hits,
                                              spans_out=self._spans, hits_out=self._hits)
         glue = genotype_glue(w, spans)
-        cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off)
-        ann = eng.hmm_label_packed(w.motifs, w.locus_motif_off, glue.backbones, glue.group_locus)
+        # copy=False: results alias the engine's pinned buffers until the next pass on this engine
+        cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off, copy=False)
+        ann = eng.hmm_label_packed(w.motifs, w.locus_motif_off, glue.backbones, glue.group_locus, copy=False)
         return HotPathResult(spans, hits, glue, cigars, ann)
 
     # -- resident batches ---------------------------------------------------------------------
