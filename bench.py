@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--depth", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk-loci", type=int, default=15625, help="loci per chunk of the end-to-end driver")
+    ap.add_argument("--host-threads", type=int, default=2, help="host threads (one engine each) of the e2e driver")
     return ap.parse_args()
 
 
@@ -215,7 +217,7 @@ def run_b200(args):
 
     import trgt_b200
     from trgt_b200 import workload
-    from trgt_b200.pipeline import HotPath, compare_with_oracle
+    from trgt_b200.pipeline import ChunkedHotPath, HotPath, compare_with_oracle, concat_results
 
     eng = trgt_b200.Engine(device=local_rank)  # fails loudly without the CUDA library / a GPU
     stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
@@ -239,10 +241,14 @@ def run_b200(args):
     t_gen = time.perf_counter() - t_gen
     hp = HotPath(eng, w, want_hits=False, pinned_outputs=True)
 
+    # end-to-end driver: chunks of loci through `host_threads` engines on this GPU
+    engines = [eng] + [trgt_b200.Engine(device=local_rank) for _ in range(max(1, args.host_threads) - 1)]
+    chp = ChunkedHotPath(engines, w, chunk_loci=args.chunk_loci)
+
     # ---- warm-up: end-to-end passes (also builds the resident batches) ----
     res = None
     for _ in range(max(1, args.warmup)):
-        res = hp.run_e2e()
+        res = chp.run_e2e()
     hp.prepare_resident()
     for _ in range(max(1, args.warmup)):
         hp.run_resident()
@@ -269,13 +275,12 @@ def run_b200(args):
     value = args.loci * world / (dev_ms * 1e-3)
 
     # ---- `e2e`: host buffers through the C ABI, host<->device copies and host glue inside ----
-    def gather_records(r):
+    def gather_records(rs):
         if world == 1:
             return 0
-        a = r.annotations
-        payload = np.concatenate([a.motif_counts.view(np.uint8), a.spans.reshape(-1).view(np.uint8),
-                                  a.purity.view(np.uint8), r.glue.backbones.data,
-                                  r.glue.backbones.offsets.view(np.uint8)])
+        payload = np.concatenate([x for r in rs for x in (
+            r.annotations.motif_counts.view(np.uint8), r.annotations.spans.reshape(-1).view(np.uint8),
+            r.annotations.purity.view(np.uint8), r.glue.backbones.data, r.glue.backbones.offsets.view(np.uint8))])
         t = torch.from_numpy(payload).to(dev, non_blocking=False)
         size = torch.tensor([t.numel()], dtype=torch.int64, device=dev)
         sizes = [torch.zeros_like(size) for _ in range(world)]
@@ -293,21 +298,24 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = hp.run_e2e()
+        res = chp.run_e2e()
         gather_records(res)
     barrier()
     e2e_s = (time.perf_counter() - t0) / max(1, args.steps)
     clk = clocks.stop()
     e2e_s = max_over_ranks(e2e_s)
     e2e_value = args.loci * world / e2e_s
-    h2d = hp.h2d_bytes(res.glue)
-    d2h = hp.d2h_bytes(res)
+    h2d = chp.h2d_bytes(res)
+    d2h = chp.d2h_bytes(res)
 
-    # the two paths must agree with each other on the full shard
-    assert np.array_equal(res.spans, res_resident.spans), "e2e and resident spans differ"
-    assert np.array_equal(res.cigars.words, res_resident.cigars.words), "e2e and resident CIGARs differ"
-    assert np.array_equal(res.annotations.spans, res_resident.annotations.spans)
-    assert np.array_equal(res.annotations.motif_counts, res_resident.annotations.motif_counts)
+    # the chunked end-to-end pass and the resident pass must agree on the full shard
+    c_spans, c_words, c_scores, c_mc, c_hspans, c_pur = concat_results(res)
+    assert np.array_equal(c_spans, res_resident.spans), "e2e and resident spans differ"
+    assert np.array_equal(c_words, res_resident.cigars.words), "e2e and resident CIGARs differ"
+    assert np.array_equal(c_scores, res_resident.cigars.scores)
+    assert np.array_equal(c_hspans, res_resident.annotations.spans)
+    assert np.array_equal(c_mc, res_resident.annotations.motif_counts)
+    assert np.array_equal(c_pur, res_resident.annotations.purity, equal_nan=True)
 
     if rank != 0:
         if world > 1:
@@ -364,13 +372,14 @@ def run_b200(args):
         "dtype": "int32 wavefront offsets + f64 Viterbi", "data": "synthetic",
         "config": workload_config(args, world), "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h},
+                "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines)},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "kernels": kernels,
         "wfa_fallback_pairs": hp.n_wfa(), "workload_gen_s": t_gen,
     }
     print(json.dumps(out))
     hp.free_resident()
-    eng.close()
+    for e2 in engines:
+        e2.close()
     if world > 1:
         dist.destroy_process_group()
 

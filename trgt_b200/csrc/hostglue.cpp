@@ -32,6 +32,17 @@ typedef struct {
   uint32_t *seq_read;                 // [n_seqs]
 } glue_out;
 
+// Grow-only buffers reused from pass to pass; with the engine's trgt_host_alloc / trgt_host_free as
+// allocator they are pinned, so phases B and C upload from them at full PCIe rate.
+typedef void *(*glue_alloc_fn)(size_t);
+typedef void (*glue_free_fn)(void *);
+typedef struct {
+  glue_alloc_fn alloc;
+  glue_free_fn release;
+  void *buf[7];
+  size_t cap[7];
+} glue_ctx;
+
 }  // extern "C"
 
 namespace {
@@ -49,10 +60,39 @@ void par_loci(uint32_t n, uint32_t threads, F f) {
 
 }  // namespace
 
+namespace {
+
+void *ctx_reserve(glue_ctx *c, int slot, size_t bytes) {
+  if (!c) return malloc(bytes);
+  if (c->buf[slot] && c->cap[slot] >= bytes) return c->buf[slot];
+  if (c->buf[slot]) c->release(c->buf[slot]);
+  const size_t ncap = bytes + bytes / 4 + 4096;
+  c->buf[slot] = c->alloc(ncap);
+  c->cap[slot] = c->buf[slot] ? ncap : 0;
+  return c->buf[slot];
+}
+
+}  // namespace
+
 extern "C" {
 
+glue_ctx *glue_ctx_create(glue_alloc_fn a, glue_free_fn f) {
+  glue_ctx *c = (glue_ctx *)calloc(1, sizeof(glue_ctx));
+  c->alloc = a ? a : (glue_alloc_fn)malloc;
+  c->release = f ? f : (glue_free_fn)free;
+  return c;
+}
+
+void glue_ctx_destroy(glue_ctx *c) {
+  if (!c) return;
+  for (int i = 0; i < 7; i++) if (c->buf[i]) c->release(c->buf[i]);
+  free(c);
+}
+
+// ctx == NULL: plain malloc, release with glue_free; otherwise the outputs live in ctx's buffers and
+// stay valid until the next glue_build on that ctx.
 int glue_build(const uint8_t *reads, const uint64_t *read_off, const uint32_t *locus_read_off, uint32_t n_loci,
-               const glue_span *spans, const uint8_t *read_hap, uint32_t threads, glue_out *out) {
+               const glue_span *spans, const uint8_t *read_hap, uint32_t threads, glue_ctx *ctx, glue_out *out) {
   // pass 1: per-locus counts
   std::vector<uint32_t> g_cnt((size_t)n_loci + 1, 0), s_cnt((size_t)n_loci + 1, 0);
   std::vector<uint64_t> sb_cnt((size_t)n_loci + 1, 0), bb_cnt((size_t)n_loci + 1, 0);
@@ -83,13 +123,13 @@ int glue_build(const uint8_t *reads, const uint64_t *read_off, const uint32_t *l
   const uint32_t ng = g0[n_loci], ns = s0[n_loci];
   out->n_groups = ng;
   out->n_seqs = ns;
-  out->bb = (uint8_t *)malloc((size_t)bb0[n_loci] + 16);
-  out->bb_off = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)ng + 1));
-  out->seqs = (uint8_t *)malloc((size_t)sb0[n_loci] + 16);
-  out->seq_off = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)ns + 1));
-  out->group_seq_off = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)ng + 1));
-  out->group_locus = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)ng + 1));
-  out->seq_read = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)ns + 1));
+  out->bb = (uint8_t *)ctx_reserve(ctx, 0, (size_t)bb0[n_loci] + 16);
+  out->bb_off = (uint64_t *)ctx_reserve(ctx, 1, sizeof(uint64_t) * ((size_t)ng + 1));
+  out->seqs = (uint8_t *)ctx_reserve(ctx, 2, (size_t)sb0[n_loci] + 16);
+  out->seq_off = (uint64_t *)ctx_reserve(ctx, 3, sizeof(uint64_t) * ((size_t)ns + 1));
+  out->group_seq_off = (uint32_t *)ctx_reserve(ctx, 4, sizeof(uint32_t) * ((size_t)ng + 1));
+  out->group_locus = (uint32_t *)ctx_reserve(ctx, 5, sizeof(uint32_t) * ((size_t)ng + 1));
+  out->seq_read = (uint32_t *)ctx_reserve(ctx, 6, sizeof(uint32_t) * ((size_t)ns + 1));
   if (!out->bb || !out->bb_off || !out->seqs || !out->seq_off || !out->group_seq_off || !out->group_locus || !out->seq_read)
     return -1;
   out->bb_off[ng] = bb0[n_loci];

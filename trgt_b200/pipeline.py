@@ -13,7 +13,9 @@ from typing import Optional
 import numpy as np
 
 from .engine import AnnotationBatch, CigarBatch, Engine, HIT_DTYPE, SPAN_DTYPE
-from .workload import GenotypeGlue, Workload, genotype_glue
+import threading
+
+from .workload import GenotypeGlue, GlueContext, Workload, genotype_glue
 
 
 @dataclass
@@ -40,6 +42,7 @@ class HotPath:
             self._hits = np.zeros(2 * n, dtype=HIT_DTYPE) if want_hits else None
         self._fb = self._ab = self._hb = None
         self.glue: Optional[GenotypeGlue] = None
+        self._glue_ctx = GlueContext(engine.lib) if pinned_outputs else None  # pinned, reused every pass
 
     # -- bytes that cross PCIe in one e2e step ------------------------------------------------
     def h2d_bytes(self, glue: GenotypeGlue) -> int:
@@ -60,15 +63,15 @@ class HotPath:
         return int(n)
 
     # -- end to end through the one-shot C-ABI calls ------------------------------------------
-    def run_e2e(self) -> HotPathResult:
+    def run_e2e(self, copy: bool = False) -> HotPathResult:
+        """copy=False: results alias pinned buffers (the engine's, this object's) until the next pass."""
         w, eng = self.w, self.eng
         spans, hits = eng.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring,
                                              w.min_flank_id_frac, want_hits=self.want_hits,
                                              spans_out=self._spans, hits_out=self._hits)
-        glue = genotype_glue(w, spans)
-        # copy=False: results alias the engine's pinned buffers until the next pass on this engine
-        cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off, copy=False)
-        ann = eng.hmm_label_packed(w.motifs, w.locus_motif_off, glue.backbones, glue.group_locus, copy=False)
+        glue = genotype_glue(w, spans, ctx=self._glue_ctx)
+        cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off, copy=copy)
+        ann = eng.hmm_label_packed(w.motifs, w.locus_motif_off, glue.backbones, glue.group_locus, copy=copy)
         return HotPathResult(spans, hits, glue, cigars, ann)
 
     # -- resident batches ---------------------------------------------------------------------
@@ -108,6 +111,56 @@ class HotPath:
         if self._hb:
             self.eng.hmm_free(self._hb)
         self._fb = self._ab = self._hb = None
+
+
+class ChunkedHotPath:
+    """The end-to-end pass over a shard in chunks of loci, the way the reference's host drives its
+    worker pool: each host thread owns one engine (its own CUDA streams and pinned buffers) and
+    runs phases A, glue, B, C per chunk through the blocking C ABI, so one chunk's PCIe transfers
+    overlap another chunk's kernels and host glue."""
+
+    def __init__(self, engines, w: Workload, chunk_loci: int = 16384):
+        self.engines = list(engines)
+        self.w = w
+        self.bounds = [(l0, min(l0 + chunk_loci, w.n_loci)) for l0 in range(0, w.n_loci, chunk_loci)]
+        self.paths = [HotPath(self.engines[i % len(self.engines)], w.slice(l0, l1))
+                      for i, (l0, l1) in enumerate(self.bounds)]
+
+    def run_e2e(self):
+        n_eng = len(self.engines)
+        results = [None] * len(self.paths)
+        errors = []
+
+        def work(k):
+            try:
+                for i in range(k, len(self.paths), n_eng):
+                    results[i] = self.paths[i].run_e2e(copy=True)
+            except Exception as exc:  # surfaced to the caller below
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(n_eng)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results
+
+    def h2d_bytes(self, results) -> int:
+        return sum(p.h2d_bytes(r.glue) for p, r in zip(self.paths, results))
+
+    def d2h_bytes(self, results) -> int:
+        return sum(p.d2h_bytes(r) for p, r in zip(self.paths, results))
+
+
+def concat_results(results):
+    """(spans, cigar words, cigar scores, motif counts, HMM spans, purity) of chunk results, in locus order."""
+    return (np.concatenate([r.spans for r in results]), np.concatenate([r.cigars.words for r in results]),
+            np.concatenate([r.cigars.scores for r in results]),
+            np.concatenate([r.annotations.motif_counts for r in results]),
+            np.concatenate([r.annotations.spans for r in results]),
+            np.concatenate([r.annotations.purity for r in results]))
 
 
 def oracle_pass(orc, w: Workload, n_threads: int):
