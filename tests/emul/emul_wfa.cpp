@@ -160,3 +160,43 @@ int emu_flank_banded_lanes(const uint8_t *p_in, int P, const uint8_t *t_in, int 
 }
 
 }  // extern "C"
+
+// ---- index-based exact search and seed filter ---------------------------------------------------
+
+extern "C" {
+
+// lanes == 0: serial.  out[0] = flank_scan_indexed result; if it is -1 (no exact hit) also runs the
+// banded fallback through the index: out[1]=rc out[2]=via out[3]=matches out[4]=score out[5]=start out[6]=end
+int emu_flank_indexed(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x, int o, int e, int S, double frac,
+                      int ws_ints, int *out, int lanes) {
+  std::vector<uint8_t> pbuf(P + 16, 0), tbuf(T + 32, 0);
+  memcpy(pbuf.data(), p_in, P);
+  memcpy(tbuf.data(), t_in, T);
+  WfaProb pr;
+  pr.p = pbuf.data(); pr.P = P; pr.t = tbuf.data(); pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
+  pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;
+  wfa_unband(pr);
+  std::vector<uint64_t> ikey(TRGT_KIDX_SLOTS);
+  std::vector<uint32_t> ioff(TRGT_KIDX_SLOTS);
+  KmerIndex idx{ikey.data(), ioff.data()};
+  std::vector<int> ws(ws_ints + 1, 0x7ead), cand(TRGT_CAND_CAP + 1);
+  uint64_t keys[32];
+  FlankHit hit = {0, 0, 0, 0, 0};
+  int pos = -3, rc = -3;
+  auto body = [&](const auto &g) {
+    kidx_build(g, idx, pr.p, P);
+    int ps = flank_scan_indexed(g, idx, pr.p, P, pr.t, T, cand.data());
+    if (ps == -2) ps = flank_scan(g, pr.p, P, pr.t, T);
+    int r = -3;
+    FlankHit h = {0, 0, 0, 0, 0};
+    if (ps == -1) r = flank_locate_banded(g, pr, S, frac, keys, ws.data(), (size_t)ws_ints, &h, &idx, cand.data());
+    if (g.lane() == 0) { pos = ps; rc = r; hit = h; }
+  };
+  if (lanes == 0) { SerialGroup g; body(g); }
+  else trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &g) { body(g); });
+  out[0] = pos; out[1] = rc;
+  out[2] = hit.via; out[3] = hit.matches; out[4] = hit.score; out[5] = hit.start; out[6] = hit.end;
+  return 0;
+}
+
+}  // extern "C"

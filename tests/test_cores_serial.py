@@ -320,3 +320,50 @@ def test_hmm_core_multilane(emul, oracle, lanes):
         assert list(mc[:len(motifs)]) == exp_mc
         assert [(spans[i].m, spans[i].s, spans[i].e) for i in range(n)] == exp_sp
         assert pur.value == exp_pur
+
+
+@pytest.mark.parametrize("lanes", [0, 5, 32])
+def test_flank_indexed_core(emul, oracle, lanes):
+    """Exact search and seed filter through the per-piece 8-mer index (probe positions only), incl.
+    repetitive pieces (long hash clusters), two copies of the piece, truncated reads, and scratch too
+    small for the in-band history (ring pass + cone trace instead)."""
+    emul.emu_flank_indexed.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_double, C.c_int, C.POINTER(C.c_int), C.c_int]
+    rng = random.Random(500 + lanes)
+    seen = {"exact": 0, "resolved": 0, "deferred": 0}
+    for _ in range(1500 if lanes == 0 else 120):
+        x, o, e = rng.choice([(2, 5, 1), (2, 5, 1), (1, 0, 1), (4, 6, 2)])
+        P = rng.choice([60, 120, 200, 250, 250, 380])
+        kind = rng.random()
+        if kind < 0.3:
+            unit = rnd(rng, rng.randint(1, 9))
+            p = mutate(rng, (unit * (P // len(unit) + 1))[:P], rng.choice([0, 0.02, 0.05]))[:P]
+            if len(p) < 16:
+                continue
+        else:
+            p = rnd(rng, P)
+        pre, suf = rnd(rng, rng.randint(0, 600)), rnd(rng, rng.randint(0, 600))
+        if kind < 0.3 and rng.random() < 0.5:
+            pre += p[:len(p) // 2]
+        body = p if rng.random() < 0.3 else mutate(rng, p, rng.choice([0.004, 0.01, 0.03, 0.08]))
+        if rng.random() < 0.1:
+            body += rnd(rng, 20) + p
+        t = pre + body + suf
+        if rng.random() < 0.05:
+            t = t[:rng.randint(1, len(t))]
+        S = rng.choice([8, 20, 20, 24])
+        exp, via, nm = oracle.find_span(p, t, (x, o, e), len(p) * 0.7)
+        out = (C.c_int * 7)()
+        emul.emu_flank_indexed(p, len(p), t, len(t), x, o, e, S, 0.7, rng.choice([700, 1280, 8192]), out, lanes)
+        assert out[0] == t.find(p)
+        if out[0] >= 0:
+            seen["exact"] += 1
+            assert via == 1
+        elif out[1] == 0:
+            seen["resolved"] += 1
+            assert (out[2], out[3]) == (via, nm)
+            if exp is not None:
+                assert (out[5], out[6]) == exp
+        else:
+            seen["deferred"] += 1
+    assert seen["exact"] > 10 and seen["resolved"] > 10

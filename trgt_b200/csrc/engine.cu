@@ -542,17 +542,17 @@ int32_t trgt_flank_upload(trgt_engine_t *e, const trgt_seqs_t *left_pieces, cons
   return 0;
 }
 
-static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src, uint32_t r0, uint32_t r1) {
-  if (r1 <= r0) return 0;
-  const int block = 256;
-  const size_t smem = (size_t)(block / 32) * sizeof(FlankWarpSmem);
+static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src, uint32_t l0, uint32_t l1) {
+  if (l1 <= l0) return 0;
+  const int block = FL_WARPS * 32;
+  const size_t smem = sizeof(FlankCtaSmem);
   int grid = 0;
   TRY(persistent_grid(e, k_flank_locate, block, smem, &grid));
-  const uint32_t need = (r1 - r0 + 7) / 8;
-  if ((uint32_t)grid > need) grid = (int)need;
+  if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
   LaunchScope ls(e, "k_flank_locate");
-  k_flank_locate<<<grid, block, smem, e->stream>>>(src, r0, r1, e->band_budget, b->frac, (trgt_flank_hit_t *)b->hits.p,
-                                                   (uint32_t *)b->work.p, (Counters *)b->ctr.p);
+  k_flank_locate<<<grid, block, smem, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
+                                                   b->frac, (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p,
+                                                   (Counters *)b->ctr.p);
   return check_launch(e, "k_flank_locate");
 }
 
@@ -602,7 +602,7 @@ static int flank_run_locked(trgt_engine_t *e, trgt_flank_batch *b) {
   if (b->n_reads == 0) return 0;
   const WfaSrc src = flank_src(b);
   CU(e, cudaMemsetAsync(b->ctr.p, 0, sizeof(Counters), e->stream));
-  TRY(flank_launch_locate(e, b, src, 0, b->n_reads));
+  TRY(flank_launch_locate(e, b, src, 0, b->n_loci));
   return flank_finish(e, b, src);
 }
 
@@ -633,7 +633,7 @@ static int flank_oneshot_locked(trgt_engine_t *e, trgt_flank_batch *b, const trg
     evs.push_back(ev);
     CU(e, cudaEventRecord(ev, e->copy_stream));
     CU(e, cudaStreamWaitEvent(e->stream, ev, 0));
-    TRY(flank_launch_locate(e, b, src, locus_read_offsets[l0], locus_read_offsets[l1]));
+    TRY(flank_launch_locate(e, b, src, l0, l1));
     l0 = l1;
   }
   (void)total;

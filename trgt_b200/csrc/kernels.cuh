@@ -81,88 +81,127 @@ __global__ void k_expand_offsets(const uint32_t *__restrict__ off, uint32_t n_gr
 
 // ------------------------------------------------------------------ phase A: flank location ---
 
-#define FL_TXT 2080        // bytes of staged read per warp (reads up to ~2 KB take the on-chip path)
-#define FL_PIECE 288       // bytes of staged flank piece
-#define FL_WS_INTS 1536    // WFA scratch per warp: banded ring, then the trace cone (cost <= ~20)
+#define FL_WARPS 8         // warps per CTA; a CTA works on one locus at a time
+#define FL_TXT 1920        // bytes of staged read per warp (reads up to ~1.8 KB take the on-chip path)
+#define FL_PIECE 432       // bytes of staged flank piece (pieces up to TRGT_KIDX_MAX_P)
+#define FL_WS_INTS 1280    // WFA scratch per warp: banded history / ring, then the trace cone
 
 struct __align__(16) FlankWarpSmem {
   uint8_t txt[FL_TXT];
-  uint8_t lp[FL_PIECE];
-  uint8_t rp[FL_PIECE];
   uint64_t keys[32];
+  int cand[TRGT_CAND_CAP + 4];
   int ws[FL_WS_INTS];
 };
 
+struct __align__(16) FlankCtaSmem {
+  uint64_t key[2][TRGT_KIDX_SLOTS];   // 8-mer index of the left / right piece
+  uint32_t off[2][TRGT_KIDX_SLOTS];
+  uint8_t piece[2][FL_PIECE];
+  int scratch[40];                    // BlockGroup reductions
+  FlankWarpSmem w[FL_WARPS];
+};
+
 // copy `bytes` (+16 of slack) starting at global `src` into the 16-byte aligned staging buffer with
-// 16-byte cp.async; returns the staged address of src[0].  cap: staging capacity in bytes.
+// 16-byte cp.async issued by `nthreads` threads (this thread is `tid`); returns the staged address of
+// src[0], or nullptr if it does not fit.  The caller commits / waits.
 __device__ __forceinline__ const uint8_t *stage_bytes(const uint8_t *src, int bytes, uint8_t *dst, int cap,
-                                                      int lane) {
+                                                      int tid, int nthreads) {
   const uintptr_t a = (uintptr_t)src;
   const int shift = (int)(a & 15u);
   const int chunks = (shift + bytes + 15 + 16) >> 4;
   if (chunks * 16 > cap) return nullptr;
   const uint4 *g = (const uint4 *)(a - (uintptr_t)shift);
-  for (int c = lane; c < chunks; c += 32) {
+  for (int c = tid; c < chunks; c += nthreads) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 16 * c);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g + c) : "memory");
   }
   return dst + shift;
 }
 
-// One warp per read, both flanks: exact search (span_locater.rs:10-12); on a miss the WFA fallback
-// (:14-25) through the seed filter + banded pass + cone trace of wfa_core.h, all from the staged copy
-// of the read.  Pairs the banded path cannot settle are appended to `work` as 2*read+side for the
-// full-width kernels below.
-__global__ void __launch_bounds__(256, 3)
-k_flank_locate(WfaSrc src, uint32_t r_begin, uint32_t r_end, int band_budget, double min_flank_id_frac,
-               trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work, Counters *ctr) {
+// Phase A.  A CTA takes one locus at a time: it stages the two flank pieces and builds their 8-mer
+// indexes once, then each warp takes reads of the locus.  Per read, both flanks: exact search
+// (span_locater.rs:10-12) by index probes; on a miss the WFA fallback (:14-25) through the seed
+// filter + banded wavefront of wfa_core.h, all from the staged copy of the read.  Pairs the on-chip
+// path cannot settle are appended to `work` as 2*read+side for the full-width kernels below.
+__global__ void __launch_bounds__(FL_WARPS * 32, 3)
+k_flank_locate(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
+               int band_budget, double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits,
+               uint32_t *__restrict__ work, Counters *ctr) {
   extern __shared__ __align__(16) unsigned char smem_b[];
+  FlankCtaSmem &cs = *reinterpret_cast<FlankCtaSmem *>(smem_b);
   const WarpGroup g;
   const int lane = g.lane();
-  FlankWarpSmem &sm = reinterpret_cast<FlankWarpSmem *>(smem_b)[threadIdx.x >> 5];
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = r_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < r_end; r += warps) {
-    const WfaProb pl = wfa_prob_of(src, 2 * r), prr = wfa_prob_of(src, 2 * r + 1);
-    // stage read and pieces (cp.async, all requests in flight before the first wait)
-    const uint8_t *t_s = stage_bytes(pl.t, pl.T, sm.txt, FL_TXT, lane);
-    const uint8_t *lp_s = stage_bytes(pl.p, pl.P, sm.lp, FL_PIECE, lane);
-    const uint8_t *rp_s = stage_bytes(prr.p, prr.P, sm.rp, FL_PIECE, lane);
+  const int warp = (int)(threadIdx.x >> 5);
+  FlankWarpSmem &sm = cs.w[warp];
+  for (uint32_t l = l_begin + blockIdx.x; l < l_end; l += gridDim.x) {
+    const uint32_t r0 = locus_read_off[l], r1 = locus_read_off[l + 1];
+    if (r1 <= r0) continue;  // uniform over the CTA
+    __syncthreads();         // every warp is done with the previous locus' pieces and indexes
+    // pieces of this locus: staged and indexed once, shared by all of its reads
+    const uint8_t *pg[2];
+    int PL[2];
+    pg[0] = src.lp + src.lp_off[l]; PL[0] = (int)(src.lp_off[l + 1] - src.lp_off[l]);
+    pg[1] = src.rp + src.rp_off[l]; PL[1] = (int)(src.rp_off[l + 1] - src.rp_off[l]);
+    const uint8_t *ps[2];
+    ps[0] = stage_bytes(pg[0], PL[0], cs.piece[0], FL_PIECE, (int)threadIdx.x, (int)blockDim.x);
+    ps[1] = stage_bytes(pg[1], PL[1], cs.piece[1], FL_PIECE, (int)threadIdx.x, (int)blockDim.x);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncwarp();
-    for (uint32_t side = 0; side < 2; side++) {
-      WfaProb pr = side ? prr : pl;
-      const uint8_t *ps = side ? rp_s : lp_s;
-      if (t_s) pr.t = t_s;   // otherwise (very long read) straight from global memory
-      if (ps) pr.p = ps;
-      wfa_unband(pr);
-      trgt_flank_hit_t h;
-      h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
-      int deferred = 0;
-      if (pr.P > 0) {
-        const int pos = flank_scan(g, pr.p, pr.P, pr.t, pr.T);
-        if (pos >= 0) {
-          h.via = TRGT_VIA_EXACT; h.matches = pr.P; h.start = (uint32_t)pos; h.end = (uint32_t)(pos + pr.P);
-        } else {
-          FlankHit fh;
-          fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
-          deferred = band_budget > 0
-                         ? flank_locate_banded(g, pr, band_budget, min_flank_id_frac, sm.keys, sm.ws, FL_WS_INTS, &fh)
-                         : 1;
-          if (!deferred) {
-            h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
-            h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
+    __syncthreads();
+    bool indexed[2];
+    for (int side = 0; side < 2; side++) {
+      indexed[side] = ps[side] != nullptr && PL[side] >= 16 && PL[side] <= TRGT_KIDX_MAX_P;
+      if (indexed[side]) {
+        const BlockGroup bg(cs.scratch);
+        const KmerIndex idx{cs.key[side], cs.off[side]};
+        kidx_build(bg, idx, ps[side], PL[side]);
+      }
+    }
+    for (uint32_t r = r0 + (uint32_t)warp; r < r1; r += FL_WARPS) {
+      const uint8_t *tg = src.reads + src.read_off[r];
+      const int T = (int)(src.read_off[r + 1] - src.read_off[r]);
+      const uint8_t *t_s = stage_bytes(tg, T, sm.txt, FL_TXT, lane, 32);
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      __syncwarp();
+      for (int side = 0; side < 2; side++) {
+        WfaProb pr;
+        pr.x = src.x; pr.oe = src.oe; pr.e = src.e;
+        pr.p = ps[side] ? ps[side] : pg[side]; pr.P = PL[side];
+        pr.t = t_s ? t_s : tg; pr.T = T;       // very long reads: straight from global memory
+        pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;  // span_locater.rs:17
+        wfa_unband(pr);
+        const KmerIndex idx{cs.key[side], cs.off[side]};
+        trgt_flank_hit_t h;
+        h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
+        int deferred = 0;
+        if (pr.P > 0) {
+          int pos = indexed[side] ? flank_scan_indexed(g, idx, pr.p, pr.P, pr.t, pr.T, sm.cand) : -2;
+          if (pos == -2) pos = flank_scan(g, pr.p, pr.P, pr.t, pr.T);
+          if (pos >= 0) {
+            h.via = TRGT_VIA_EXACT; h.matches = pr.P; h.start = (uint32_t)pos; h.end = (uint32_t)(pos + pr.P);
+          } else {
+            FlankHit fh;
+            fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
+            deferred = band_budget > 0
+                           ? flank_locate_banded(g, pr, band_budget, min_flank_id_frac, sm.keys, sm.ws, FL_WS_INTS, &fh,
+                                                 indexed[side] ? &idx : nullptr, sm.cand)
+                           : 1;
+            if (!deferred) {
+              h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
+              h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
+            }
           }
         }
-      }
-      if (lane == 0) {
-        if (deferred) {
-          const unsigned int slot = atomicAdd(&ctr->n_work, 1u);
-          work[slot] = 2 * r + side;
+        if (lane == 0) {
+          if (deferred) {
+            const unsigned int slot = atomicAdd(&ctr->n_work, 1u);
+            work[slot] = 2 * r + (uint32_t)side;
+          }
+          hits[2 * r + side] = h;
         }
-        hits[2 * r + side] = h;
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
 }

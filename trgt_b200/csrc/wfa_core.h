@@ -655,6 +655,163 @@ TRGT_HD bool flank_seed_band(const G &g, const WfaProb &pr, int S, uint64_t *key
   return true;
 }
 
+// ---------------------------------------------------------------- 8-mer index of a flank piece ---
+
+// Open-addressing table of every 8-mer of one piece (key = its 8 bytes, value = its offset), built
+// once per locus and shared by all of the locus' reads.  With it, both the exact search and the seed
+// filter only look at a few *probe* positions of the read instead of every position: an occurrence
+// of a length-n pattern piece covers exactly one of the text positions (i+1)(n-7)-1, and the 8-mer
+// found there must be one of the piece's own.
+#define TRGT_KIDX_SLOTS 512u
+#define TRGT_KIDX_EMPTY 0xFFFFFFFFu
+#define TRGT_KIDX_MAX_P 400   // keeps the load factor below 0.77
+#define TRGT_CAND_CAP 64
+
+struct KmerIndex {
+  uint64_t *key;  // [TRGT_KIDX_SLOTS]
+  uint32_t *off;  // [TRGT_KIDX_SLOTS]
+};
+
+TRGT_HD uint32_t kidx_hash(uint64_t k) { return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 55); }
+
+TRGT_HD uint32_t kidx_cas(uint32_t *addr, uint32_t expect, uint32_t val) {
+#if defined(__CUDA_ARCH__)
+  return atomicCAS(addr, expect, val);
+#else
+  __atomic_compare_exchange_n(addr, &expect, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+  return expect;
+#endif
+}
+
+template <class G>
+TRGT_HD void kidx_build(const G &g, const KmerIndex &idx, const uint8_t *piece, int P) {
+  for (uint32_t i = (uint32_t)g.lane(); i < TRGT_KIDX_SLOTS; i += (uint32_t)g.size()) idx.off[i] = TRGT_KIDX_EMPTY;
+  g.sync();
+  for (int i = g.lane(); i + 8 <= P; i += g.size()) {
+    const uint64_t key = wfa_ld64u(piece + i);
+    uint32_t h = kidx_hash(key);
+    for (;;) {
+      if (kidx_cas(&idx.off[h], TRGT_KIDX_EMPTY, (uint32_t)i) == TRGT_KIDX_EMPTY) { idx.key[h] = key; break; }
+      h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u);
+    }
+  }
+  g.sync();
+}
+
+// first start s with t[s..s+P) == piece via the index; -1 none, -2 too many candidates (use flank_scan)
+// cand: TRGT_CAND_CAP + 1 ints of group scratch
+template <class G>
+TRGT_HD int flank_scan_indexed(const G &g, const KmerIndex &idx, const uint8_t *piece, int P, const uint8_t *t, int T,
+                               int *cand) {
+  const int n_starts = T - P + 1;
+  if (n_starts <= 0) return -1;
+  const int step = P - 7;
+  const int n_probes = (T - 7) / step;  // probes j_i = (i+1)*step - 1 with j_i + 8 <= T
+  for (int pb = 0; pb < n_probes; pb += g.size()) {
+    const int i = pb + g.lane();
+    const int j = (i + 1) * step - 1;
+    uint64_t key = 0;
+    int cnt = 0;
+    if (i < n_probes) {
+      key = wfa_ld64u(t + j);
+      for (uint32_t h = kidx_hash(key); idx.off[h] != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+        const int s = j - (int)idx.off[h];
+        if (idx.key[h] == key && s >= 0 && s < n_starts) cnt++;
+      }
+    }
+    for (;;) {  // probes in increasing order: their candidate ranges are disjoint and increasing
+      const int leader = g.min_i(cnt > 0 ? g.lane() : INT_MAX);
+      if (leader == INT_MAX) break;
+      if (g.lane() == leader) {
+        int n = 0;
+        for (uint32_t h = kidx_hash(key); idx.off[h] != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+          const int s = j - (int)idx.off[h];
+          if (idx.key[h] == key && s >= 0 && s < n_starts) { if (n < TRGT_CAND_CAP) cand[n] = s; n++; }
+        }
+        cand[TRGT_CAND_CAP] = n;
+        cnt = 0;
+      }
+      g.sync();
+      const int n = cand[TRGT_CAND_CAP];
+      int best = INT_MAX;
+      if (n <= TRGT_CAND_CAP)
+        for (int c = 0; c < n; c++) {
+          const int s = cand[c];
+          if (s < best && wfa_coop_match_len(g, piece, t + s, P) == P) best = s;
+        }
+      g.sync();
+      if (n > TRGT_CAND_CAP) return -2;
+      if (best != INT_MAX) return best;
+    }
+  }
+  return -1;
+}
+
+// flank_seed_band through the index: 1 band found, 0 no band can be given, -2 too many candidates
+template <class G>
+TRGT_HD int flank_seed_band_indexed(const G &g, const KmerIndex &idx, const WfaProb &pr, int S, int *cand, int *klo,
+                                    int *khi) {
+  const int emin = wfa_imin(pr.x, pr.oe);
+  const int nb = S / emin + 1;
+  if (nb > 32) return 0;
+  const int blen = pr.P / nb;
+  if (blen < 12 || pr.T < blen) return 0;
+  const int o = pr.oe - pr.e;
+  const int R = S > o ? (S - o) / pr.e : 0;
+  const int step = blen - 7;
+  const int n_probes = (pr.T - 7) / step;
+  int kmin = INT_MAX, kmax = INT_MIN;
+  for (int pb = 0; pb < n_probes; pb += g.size()) {
+    const int i = pb + g.lane();
+    const int j = (i + 1) * step - 1;
+    uint64_t key = 0;
+    int cnt = 0;
+    if (i < n_probes) {
+      key = wfa_ld64u(pr.t + j);
+      for (uint32_t h = kidx_hash(key); idx.off[h] != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+        if (idx.key[h] != key) continue;
+        const int d = (int)idx.off[h], b = d / blen, q = j - (d - b * blen);
+        if (b < nb && d - b * blen + 8 <= blen && q >= 0 && q + blen <= pr.T) cnt++;
+      }
+    }
+    for (;;) {
+      const int leader = g.min_i(cnt > 0 ? g.lane() : INT_MAX);
+      if (leader == INT_MAX) break;
+      if (g.lane() == leader) {
+        int n = 0;
+        for (uint32_t h = kidx_hash(key); idx.off[h] != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+          if (idx.key[h] != key) continue;
+          const int d = (int)idx.off[h], b = d / blen, q = j - (d - b * blen);
+          if (b < nb && d - b * blen + 8 <= blen && q >= 0 && q + blen <= pr.T) {
+            if (n < TRGT_CAND_CAP) cand[n] = (q << 5) | b;
+            n++;
+          }
+        }
+        cand[TRGT_CAND_CAP] = n;
+        cnt = 0;
+      }
+      g.sync();
+      const int n = cand[TRGT_CAND_CAP];
+      if (n <= TRGT_CAND_CAP)
+        for (int c = 0; c < n; c++) {
+          const int q = cand[c] >> 5, b = cand[c] & 31;
+          if (wfa_coop_match_len(g, pr.p + b * blen, pr.t + q, blen) == blen) {
+            const int k = q - b * blen;
+            kmin = wfa_imin(kmin, k);
+            kmax = wfa_imax(kmax, k);
+          }
+        }
+      g.sync();
+      if (n > TRGT_CAND_CAP) return -2;
+    }
+  }
+  if (kmin == INT_MAX) return 0;
+  *klo = wfa_imax(-pr.P, kmin - R);
+  *khi = wfa_imin(pr.T, kmax + R);
+  if (*khi + pr.P >= pr.T) return 0;  // see flank_seed_band
+  return 1;
+}
+
 struct FlankHit {
   int via;      // TRGT_VIA_* of include/trgt_engine.h: 2 accepted, 3 rejected
   int matches;  // count_matches
@@ -669,19 +826,34 @@ struct FlankHit {
 // ws: ws_ints ints of group scratch (on chip), keys: 32 uint64.  Returns 0 and fills *hit (lane 0's
 // copy is authoritative), or 1 if this pair needs the full-width path (no seed, cost > S, scratch
 // too small).
+// idx (optional): 8-mer index of pr.p with cand = TRGT_CAND_CAP + 1 ints of scratch; without it, or
+// when it overflows, the seed filter scans every text position.
 template <class G>
 TRGT_HD int flank_locate_banded(const G &g, const WfaProb &pr, int S, double min_flank_id_frac, uint64_t *keys,
-                                int *ws, size_t ws_ints, FlankHit *hit) {
+                                int *ws, size_t ws_ints, FlankHit *hit, const KmerIndex *idx = nullptr,
+                                int *cand = nullptr) {
   const int tier1 = wfa_imin(S, wfa_imax(pr.x, pr.oe));
   for (int tier = 0; tier < 2; tier++) {
     const int cap = tier == 0 ? tier1 : S;
     if (tier == 1 && S <= tier1) break;
     int klo, khi;
-    if (!flank_seed_band(g, pr, cap, keys, &klo, &khi)) continue;
+    int have = -2;
+    if (idx) have = flank_seed_band_indexed(g, *idx, pr, cap, cand, &klo, &khi);
+    if (have == -2) have = flank_seed_band(g, pr, cap, keys, &klo, &khi) ? 1 : 0;
+    if (!have) continue;
     WfaProb bp = pr;
     bp.blo = klo; bp.bhi = khi;
-    const WfaEnd end = wfa_forward_band_hist(g, bp, cap, ws, ws_ints);
+    WfaEnd end = wfa_forward_band_hist(g, bp, cap, ws, ws_ints);
     g.sync();
+    if (end.status == TRGT_WFA_OOM && wfa_ring_ints(bp) <= ws_ints) {
+      // the in-band history does not fit: score-only ring pass in the band, then the (smaller) cone
+      end = wfa_score_ring(g, bp, ws, cap);
+      g.sync();
+      if (end.status == TRGT_WFA_OK) {
+        if (wfa_trace_ints(pr, end.s) > ws_ints || wfa_trace_forward(g, pr, end.s, end.k, ws, ws_ints) != 0)
+          end.status = TRGT_WFA_OOM;
+      }
+    }
     if (end.status != TRGT_WFA_OK) continue;
     if (g.lane() == 0) {
       WfaFlankSink sink(pr.T);
