@@ -176,9 +176,8 @@ int emu_flank_indexed(const uint8_t *p_in, int P, const uint8_t *t_in, int T, in
   pr.p = pbuf.data(); pr.P = P; pr.t = tbuf.data(); pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
   pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;
   wfa_unband(pr);
-  std::vector<uint64_t> ikey(TRGT_KIDX_SLOTS);
-  std::vector<uint32_t> ioff(TRGT_KIDX_SLOTS);
-  KmerIndex idx{ikey.data(), ioff.data()};
+  std::vector<uint16_t> islot(TRGT_KIDX_SLOTS);
+  KmerIndex idx{islot.data()};
   std::vector<int> ws(ws_ints + 1, 0x7ead), cand(TRGT_CAND_CAP + 1);
   uint64_t keys[32];
   FlankHit hit = {0, 0, 0, 0, 0};

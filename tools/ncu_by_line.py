@@ -3,7 +3,7 @@ hottest source lines of one kernel.  Usage: ncu_by_line.py <report.ncu-rep> <ker
 import csv, io, os, re, subprocess, sys, tempfile, collections
 
 rep, kern = sys.argv[1], sys.argv[2]
-so = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "trgt_b200", "libtrgt_b200.so")
+so = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "trgt_b200", "libtrgt_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -44,5 +44,5 @@ for r in rows[h + 1:]:
 tot = sum(agg.values()) or 1
 tots = sum(samp.values()) or 1
 print(f"{n} SASS instructions, {len(line_of)} with line info, {tot} warp-instructions executed")
-for k, v in agg.most_common(45):
+for k, v in agg.most_common(100000 if '--all' in sys.argv else 45):
     print(f"{k[0]}:{k[1]:<5d} inst {100*v/tot:5.1f}%  samples {100*samp[k]/tots:5.1f}%")

@@ -544,13 +544,12 @@ int32_t trgt_flank_upload(trgt_engine_t *e, const trgt_seqs_t *left_pieces, cons
 
 static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src, uint32_t l0, uint32_t l1) {
   if (l1 <= l0) return 0;
-  const int block = FL_WARPS * 32;
-  const size_t smem = sizeof(FlankCtaSmem);
+  const int block = 32;  // one warp per CTA, one locus at a time per warp
   int grid = 0;
-  TRY(persistent_grid(e, k_flank_locate, block, smem, &grid));
+  TRY(persistent_grid(e, k_flank_locate, block, 0, &grid));
   if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
   LaunchScope ls(e, "k_flank_locate");
-  k_flank_locate<<<grid, block, smem, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
+  k_flank_locate<<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
                                                    b->frac, (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p,
                                                    (Counters *)b->ctr.p);
   return check_launch(e, "k_flank_locate");

@@ -81,24 +81,16 @@ __global__ void k_expand_offsets(const uint32_t *__restrict__ off, uint32_t n_gr
 
 // ------------------------------------------------------------------ phase A: flank location ---
 
-#define FL_WARPS 8         // warps per CTA; a CTA works on one locus at a time
-#define FL_TXT 1920        // bytes of staged read per warp (reads up to ~1.8 KB take the on-chip path)
+#define FL_TXT 1664        // bytes per staged read buffer (reads up to ~1.6 KB take the on-chip path)
 #define FL_PIECE 432       // bytes of staged flank piece (pieces up to TRGT_KIDX_MAX_P)
-#define FL_WS_INTS 1280    // WFA scratch per warp: banded history / ring, then the trace cone
+#define FL_WS_INTS 1280    // scratch: seed keys / candidates, banded history or ring, trace cone
 
+// one warp = one CTA = one locus at a time
 struct __align__(16) FlankWarpSmem {
-  uint8_t txt[FL_TXT];
-  uint64_t keys[32];
-  int cand[TRGT_CAND_CAP + 4];
-  int ws[FL_WS_INTS];
-};
-
-struct __align__(16) FlankCtaSmem {
-  uint64_t key[2][TRGT_KIDX_SLOTS];   // 8-mer index of the left / right piece
-  uint32_t off[2][TRGT_KIDX_SLOTS];
+  uint16_t slot[2][TRGT_KIDX_SLOTS];  // 8-mer index of the left / right piece
   uint8_t piece[2][FL_PIECE];
-  int scratch[40];                    // BlockGroup reductions
-  FlankWarpSmem w[FL_WARPS];
+  uint8_t txt[2][FL_TXT];             // double buffer: the next read lands while this one is worked on
+  int ws[FL_WS_INTS];
 };
 
 // copy `bytes` (+16 of slack) starting at global `src` into the 16-byte aligned staging buffer with
@@ -118,51 +110,58 @@ __device__ __forceinline__ const uint8_t *stage_bytes(const uint8_t *src, int by
   return dst + shift;
 }
 
-// Phase A.  A CTA takes one locus at a time: it stages the two flank pieces and builds their 8-mer
-// indexes once, then each warp takes reads of the locus.  Per read, both flanks: exact search
-// (span_locater.rs:10-12) by index probes; on a miss the WFA fallback (:14-25) through the seed
-// filter + banded wavefront of wfa_core.h, all from the staged copy of the read.  Pairs the on-chip
-// path cannot settle are appended to `work` as 2*read+side for the full-width kernels below.
-__global__ void __launch_bounds__(FL_WARPS * 32, 3)
+// Phase A.  A warp takes one locus at a time: it stages the two flank pieces and builds their 8-mer
+// indexes once, then walks the locus' reads with the next read's cp.async in flight.  Per read, both
+// flanks: exact search (span_locater.rs:10-12) by index probes; on a miss the WFA fallback (:14-25)
+// through the seed filter + banded wavefront of wfa_core.h, all from the staged copy of the read.
+// Pairs the on-chip path cannot settle are appended to `work` as 2*read+side for the full-width
+// kernels below.
+__global__ void __launch_bounds__(32)
 k_flank_locate(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
                int band_budget, double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits,
                uint32_t *__restrict__ work, Counters *ctr) {
-  extern __shared__ __align__(16) unsigned char smem_b[];
-  FlankCtaSmem &cs = *reinterpret_cast<FlankCtaSmem *>(smem_b);
+  __shared__ FlankWarpSmem sm;
   const WarpGroup g;
   const int lane = g.lane();
-  const int warp = (int)(threadIdx.x >> 5);
-  FlankWarpSmem &sm = cs.w[warp];
+  uint64_t *keys = reinterpret_cast<uint64_t *>(sm.ws);   // 32 seed keys (linear fallback only)
+  int *cand = sm.ws + 64;                                  // TRGT_CAND_CAP + 1 candidates
   for (uint32_t l = l_begin + blockIdx.x; l < l_end; l += gridDim.x) {
     const uint32_t r0 = locus_read_off[l], r1 = locus_read_off[l + 1];
-    if (r1 <= r0) continue;  // uniform over the CTA
-    __syncthreads();         // every warp is done with the previous locus' pieces and indexes
-    // pieces of this locus: staged and indexed once, shared by all of its reads
+    if (r1 <= r0) continue;
+    __syncwarp();
+    // pieces of this locus (staged and indexed once) and its first read
     const uint8_t *pg[2];
     int PL[2];
     pg[0] = src.lp + src.lp_off[l]; PL[0] = (int)(src.lp_off[l + 1] - src.lp_off[l]);
     pg[1] = src.rp + src.rp_off[l]; PL[1] = (int)(src.rp_off[l + 1] - src.rp_off[l]);
     const uint8_t *ps[2];
-    ps[0] = stage_bytes(pg[0], PL[0], cs.piece[0], FL_PIECE, (int)threadIdx.x, (int)blockDim.x);
-    ps[1] = stage_bytes(pg[1], PL[1], cs.piece[1], FL_PIECE, (int)threadIdx.x, (int)blockDim.x);
+    ps[0] = stage_bytes(pg[0], PL[0], sm.piece[0], FL_PIECE, lane, 32);
+    ps[1] = stage_bytes(pg[1], PL[1], sm.piece[1], FL_PIECE, lane, 32);
+    const uint8_t *tg = src.reads + src.read_off[r0];
+    int T = (int)(src.read_off[r0 + 1] - src.read_off[r0]);
+    const uint8_t *t_s = stage_bytes(tg, T, sm.txt[0], FL_TXT, lane, 32);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();
+    __syncwarp();
     bool indexed[2];
     for (int side = 0; side < 2; side++) {
       indexed[side] = ps[side] != nullptr && PL[side] >= 16 && PL[side] <= TRGT_KIDX_MAX_P;
-      if (indexed[side]) {
-        const BlockGroup bg(cs.scratch);
-        const KmerIndex idx{cs.key[side], cs.off[side]};
-        kidx_build(bg, idx, ps[side], PL[side]);
-      }
+      if (indexed[side]) kidx_build(g, KmerIndex{sm.slot[side]}, ps[side], PL[side]);
     }
-    for (uint32_t r = r0 + (uint32_t)warp; r < r1; r += FL_WARPS) {
-      const uint8_t *tg = src.reads + src.read_off[r];
-      const int T = (int)(src.read_off[r + 1] - src.read_off[r]);
-      const uint8_t *t_s = stage_bytes(tg, T, sm.txt, FL_TXT, lane, 32);
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    for (uint32_t r = r0; r < r1; r++) {
+      const int cur = (int)((r - r0) & 1u);
+      // prefetch the next read into the other buffer, then wait for this one
+      const uint8_t *tg_next = nullptr, *t_next = nullptr;
+      int T_next = 0;
+      if (r + 1 < r1) {
+        tg_next = src.reads + src.read_off[r + 1];
+        T_next = (int)(src.read_off[r + 2] - src.read_off[r + 1]);
+        t_next = stage_bytes(tg_next, T_next, sm.txt[cur ^ 1], FL_TXT, lane, 32);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      }
       __syncwarp();
       for (int side = 0; side < 2; side++) {
         WfaProb pr;
@@ -171,12 +170,12 @@ k_flank_locate(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t
         pr.t = t_s ? t_s : tg; pr.T = T;       // very long reads: straight from global memory
         pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;  // span_locater.rs:17
         wfa_unband(pr);
-        const KmerIndex idx{cs.key[side], cs.off[side]};
+        const KmerIndex idx{sm.slot[side]};
         trgt_flank_hit_t h;
         h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
         int deferred = 0;
         if (pr.P > 0) {
-          int pos = indexed[side] ? flank_scan_indexed(g, idx, pr.p, pr.P, pr.t, pr.T, sm.cand) : -2;
+          int pos = indexed[side] ? flank_scan_indexed(g, idx, pr.p, pr.P, pr.t, pr.T, cand) : -2;
           if (pos == -2) pos = flank_scan(g, pr.p, pr.P, pr.t, pr.T);
           if (pos >= 0) {
             h.via = TRGT_VIA_EXACT; h.matches = pr.P; h.start = (uint32_t)pos; h.end = (uint32_t)(pos + pr.P);
@@ -184,8 +183,8 @@ k_flank_locate(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t
             FlankHit fh;
             fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
             deferred = band_budget > 0
-                           ? flank_locate_banded(g, pr, band_budget, min_flank_id_frac, sm.keys, sm.ws, FL_WS_INTS, &fh,
-                                                 indexed[side] ? &idx : nullptr, sm.cand)
+                           ? flank_locate_banded(g, pr, band_budget, min_flank_id_frac, keys, sm.ws, FL_WS_INTS, &fh,
+                                                 indexed[side] ? &idx : nullptr, cand)
                            : 1;
             if (!deferred) {
               h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
@@ -202,6 +201,7 @@ k_flank_locate(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t
         }
         __syncwarp();
       }
+      tg = tg_next; T = T_next; t_s = t_next;
     }
   }
 }

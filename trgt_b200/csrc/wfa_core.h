@@ -663,37 +663,41 @@ TRGT_HD bool flank_seed_band(const G &g, const WfaProb &pr, int S, uint64_t *key
 // of a length-n pattern piece covers exactly one of the text positions (i+1)(n-7)-1, and the 8-mer
 // found there must be one of the piece's own.
 #define TRGT_KIDX_SLOTS 512u
-#define TRGT_KIDX_EMPTY 0xFFFFFFFFu
-#define TRGT_KIDX_MAX_P 400   // keeps the load factor below 0.77
+#define TRGT_KIDX_EMPTY 0xFFFFu
+#define TRGT_KIDX_MAX_P 400   // offsets fit 9 bits and the load factor stays below 0.77
 #define TRGT_CAND_CAP 64
 
+// slot (16 bits) = 7-bit fingerprint of the 8-mer << 9 | its offset in the piece: 1 KB per piece, so
+// every warp can afford its own pair of tables.  A fingerprint clash only costs a failed
+// verification: every candidate is compared byte for byte before it counts.  0x7F is never used as
+// a fingerprint, so no slot equals TRGT_KIDX_EMPTY.
 struct KmerIndex {
-  uint64_t *key;  // [TRGT_KIDX_SLOTS]
-  uint32_t *off;  // [TRGT_KIDX_SLOTS]
+  uint16_t *slot;  // [TRGT_KIDX_SLOTS]
 };
 
-TRGT_HD uint32_t kidx_hash(uint64_t k) { return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 55); }
+TRGT_HD uint64_t kidx_mix(uint64_t k) { return k * 0x9E3779B97F4A7C15ull; }
+TRGT_HD uint32_t kidx_home(uint64_t mixed) { return (uint32_t)(mixed >> 55); }
+TRGT_HD uint32_t kidx_fp(uint64_t mixed) { const uint32_t f = (uint32_t)(mixed >> 40) & 0x7Fu; return f == 0x7Fu ? 0x3Fu : f; }
 
-TRGT_HD uint32_t kidx_cas(uint32_t *addr, uint32_t expect, uint32_t val) {
+TRGT_HD uint32_t kidx_cas(uint16_t *addr, uint32_t expect, uint32_t val) {
 #if defined(__CUDA_ARCH__)
-  return atomicCAS(addr, expect, val);
+  return atomicCAS((unsigned short *)addr, (unsigned short)expect, (unsigned short)val);
 #else
-  __atomic_compare_exchange_n(addr, &expect, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
-  return expect;
+  uint16_t ex = (uint16_t)expect;
+  __atomic_compare_exchange_n(addr, &ex, (uint16_t)val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+  return ex;
 #endif
 }
 
 template <class G>
 TRGT_HD void kidx_build(const G &g, const KmerIndex &idx, const uint8_t *piece, int P) {
-  for (uint32_t i = (uint32_t)g.lane(); i < TRGT_KIDX_SLOTS; i += (uint32_t)g.size()) idx.off[i] = TRGT_KIDX_EMPTY;
+  for (uint32_t i = (uint32_t)g.lane(); i < TRGT_KIDX_SLOTS; i += (uint32_t)g.size()) idx.slot[i] = TRGT_KIDX_EMPTY;
   g.sync();
   for (int i = g.lane(); i + 8 <= P; i += g.size()) {
-    const uint64_t key = wfa_ld64u(piece + i);
-    uint32_t h = kidx_hash(key);
-    for (;;) {
-      if (kidx_cas(&idx.off[h], TRGT_KIDX_EMPTY, (uint32_t)i) == TRGT_KIDX_EMPTY) { idx.key[h] = key; break; }
-      h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u);
-    }
+    const uint64_t mixed = kidx_mix(wfa_ld64u(piece + i));
+    const uint32_t val = (kidx_fp(mixed) << 9) | (uint32_t)i;
+    uint32_t h = kidx_home(mixed);
+    while (kidx_cas(&idx.slot[h], TRGT_KIDX_EMPTY, val) != TRGT_KIDX_EMPTY) h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u);
   }
   g.sync();
 }
@@ -710,37 +714,44 @@ TRGT_HD int flank_scan_indexed(const G &g, const KmerIndex &idx, const uint8_t *
   for (int pb = 0; pb < n_probes; pb += g.size()) {
     const int i = pb + g.lane();
     const int j = (i + 1) * step - 1;
-    uint64_t key = 0;
-    int cnt = 0;
+    uint32_t home = 0, fp = 0;
+    int cnt = 0, c0 = 0;  // candidates of this lane's probe; c0 = the first one
     if (i < n_probes) {
-      key = wfa_ld64u(t + j);
-      for (uint32_t h = kidx_hash(key); idx.off[h] != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
-        const int s = j - (int)idx.off[h];
-        if (idx.key[h] == key && s >= 0 && s < n_starts) cnt++;
+      const uint64_t mixed = kidx_mix(wfa_ld64u(t + j));
+      home = kidx_home(mixed); fp = kidx_fp(mixed);
+      for (uint32_t h = home, v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+        const int s = j - (int)(v & 511u);
+        if ((v >> 9) == fp && s >= 0 && s < n_starts) { if (cnt == 0) c0 = s; cnt++; }
       }
     }
     for (;;) {  // probes in increasing order: their candidate ranges are disjoint and increasing
       const int leader = g.min_i(cnt > 0 ? g.lane() : INT_MAX);
       if (leader == INT_MAX) break;
-      if (g.lane() == leader) {
-        int n = 0;
-        for (uint32_t h = kidx_hash(key); idx.off[h] != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
-          const int s = j - (int)idx.off[h];
-          if (idx.key[h] == key && s >= 0 && s < n_starts) { if (n < TRGT_CAND_CAP) cand[n] = s; n++; }
-        }
-        cand[TRGT_CAND_CAP] = n;
-        cnt = 0;
-      }
-      g.sync();
-      const int n = cand[TRGT_CAND_CAP];
+      const int ln = g.bcast(cnt, leader);
       int best = INT_MAX;
-      if (n <= TRGT_CAND_CAP)
-        for (int c = 0; c < n; c++) {
-          const int s = cand[c];
-          if (s < best && wfa_coop_match_len(g, piece, t + s, P) == P) best = s;
+      if (ln == 1) {  // the usual case: one candidate, straight from the leader's register
+        const int s = g.bcast(c0, leader);
+        if (wfa_coop_match_len(g, piece, t + s, P) == P) best = s;
+      } else {
+        if (g.lane() == leader) {
+          int n = 0;
+          for (uint32_t h = home, v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+            const int s = j - (int)(v & 511u);
+            if ((v >> 9) == fp && s >= 0 && s < n_starts) { if (n < TRGT_CAND_CAP) cand[n] = s; n++; }
+          }
+          cand[TRGT_CAND_CAP] = n;
         }
-      g.sync();
-      if (n > TRGT_CAND_CAP) return -2;
+        g.sync();
+        const int n = cand[TRGT_CAND_CAP];
+        if (n <= TRGT_CAND_CAP)
+          for (int c = 0; c < n; c++) {
+            const int s = cand[c];
+            if (s < best && wfa_coop_match_len(g, piece, t + s, P) == P) best = s;
+          }
+        g.sync();
+        if (n > TRGT_CAND_CAP) return -2;
+      }
+      if (g.lane() == leader) cnt = 0;
       if (best != INT_MAX) return best;
     }
   }
@@ -764,45 +775,55 @@ TRGT_HD int flank_seed_band_indexed(const G &g, const KmerIndex &idx, const WfaP
   for (int pb = 0; pb < n_probes; pb += g.size()) {
     const int i = pb + g.lane();
     const int j = (i + 1) * step - 1;
-    uint64_t key = 0;
-    int cnt = 0;
+    uint32_t home = 0, fp = 0;
+    int cnt = 0, c0 = 0;  // candidate = block start in the text << 5 | block
     if (i < n_probes) {
-      key = wfa_ld64u(pr.t + j);
-      for (uint32_t h = kidx_hash(key); idx.off[h] != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
-        if (idx.key[h] != key) continue;
-        const int d = (int)idx.off[h], b = d / blen, q = j - (d - b * blen);
-        if (b < nb && d - b * blen + 8 <= blen && q >= 0 && q + blen <= pr.T) cnt++;
+      const uint64_t mixed = kidx_mix(wfa_ld64u(pr.t + j));
+      home = kidx_home(mixed); fp = kidx_fp(mixed);
+      for (uint32_t h = home, v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+        if ((v >> 9) != fp) continue;
+        const int d = (int)(v & 511u), b = d / blen, q = j - (d - b * blen);
+        if (b < nb && d - b * blen + 8 <= blen && q >= 0 && q + blen <= pr.T) { if (cnt == 0) c0 = (q << 5) | b; cnt++; }
       }
     }
     for (;;) {
       const int leader = g.min_i(cnt > 0 ? g.lane() : INT_MAX);
       if (leader == INT_MAX) break;
-      if (g.lane() == leader) {
-        int n = 0;
-        for (uint32_t h = kidx_hash(key); idx.off[h] != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
-          if (idx.key[h] != key) continue;
-          const int d = (int)idx.off[h], b = d / blen, q = j - (d - b * blen);
-          if (b < nb && d - b * blen + 8 <= blen && q >= 0 && q + blen <= pr.T) {
-            if (n < TRGT_CAND_CAP) cand[n] = (q << 5) | b;
-            n++;
-          }
+      const int ln = g.bcast(cnt, leader);
+      if (ln == 1) {
+        const int c = g.bcast(c0, leader);
+        const int q = c >> 5, b = c & 31;
+        if (wfa_coop_match_len(g, pr.p + b * blen, pr.t + q, blen) == blen) {
+          kmin = wfa_imin(kmin, q - b * blen);
+          kmax = wfa_imax(kmax, q - b * blen);
         }
-        cand[TRGT_CAND_CAP] = n;
-        cnt = 0;
+      } else {
+        if (g.lane() == leader) {
+          int n = 0;
+          for (uint32_t h = home, v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+            if ((v >> 9) != fp) continue;
+            const int d = (int)(v & 511u), b = d / blen, q = j - (d - b * blen);
+            if (b < nb && d - b * blen + 8 <= blen && q >= 0 && q + blen <= pr.T) {
+              if (n < TRGT_CAND_CAP) cand[n] = (q << 5) | b;
+              n++;
+            }
+          }
+          cand[TRGT_CAND_CAP] = n;
+        }
+        g.sync();
+        const int n = cand[TRGT_CAND_CAP];
+        if (n <= TRGT_CAND_CAP)
+          for (int c = 0; c < n; c++) {
+            const int q = cand[c] >> 5, b = cand[c] & 31;
+            if (wfa_coop_match_len(g, pr.p + b * blen, pr.t + q, blen) == blen) {
+              kmin = wfa_imin(kmin, q - b * blen);
+              kmax = wfa_imax(kmax, q - b * blen);
+            }
+          }
+        g.sync();
+        if (n > TRGT_CAND_CAP) return -2;
       }
-      g.sync();
-      const int n = cand[TRGT_CAND_CAP];
-      if (n <= TRGT_CAND_CAP)
-        for (int c = 0; c < n; c++) {
-          const int q = cand[c] >> 5, b = cand[c] & 31;
-          if (wfa_coop_match_len(g, pr.p + b * blen, pr.t + q, blen) == blen) {
-            const int k = q - b * blen;
-            kmin = wfa_imin(kmin, k);
-            kmax = wfa_imax(kmax, k);
-          }
-        }
-      g.sync();
-      if (n > TRGT_CAND_CAP) return -2;
+      if (g.lane() == leader) cnt = 0;
     }
   }
   if (kmin == INT_MAX) return 0;
