@@ -217,8 +217,7 @@ int check_launch(trgt_engine *e, const char *name) {
 
 template <class K>
 int persistent_grid(trgt_engine *e, K kernel, int block, size_t smem, int *grid_out) {
-  if (smem > 48 * 1024)
-    CU(e, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > (size_t)e->smem_optin) return fail(e, TRGT_ERR_INTERNAL, "kernel wants %zu bytes of shared memory", smem);
   int per_sm = 0;
   CU(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
   if (per_sm < 1) return fail(e, TRGT_ERR_INTERNAL, "kernel does not fit on an SM (smem %zu)", smem);
@@ -302,6 +301,20 @@ int32_t trgt_engine_create(int32_t device, trgt_engine_t **out) {
     g_create_error = std::string("engine setup failed: ") + cudaGetErrorString(err);
     delete e;
     return TRGT_ERR_CUDA;
+  }
+  // Dynamic shared memory limits are per-function process state: raise them once to the device
+  // maximum (never per launch, engines on other host threads may be launching concurrently).
+  {
+    const int mx = e->smem_optin;
+    if ((err = cudaFuncSetAttribute(k_wfa_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
+        (err = cudaFuncSetAttribute(k_wfa_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
+        (err = cudaFuncSetAttribute(k_wfa_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
+        (err = cudaFuncSetAttribute(k_hmm_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
+        (err = cudaFuncSetAttribute(k_hmm_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) {
+      g_create_error = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(err);
+      trgt_engine_destroy(e);
+      return TRGT_ERR_CUDA;
+    }
   }
   e->hmm_consts = hmm_make_consts();
   *out = e;

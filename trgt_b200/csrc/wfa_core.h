@@ -400,12 +400,87 @@ TRGT_HD int wfa_trace_forward(const G &g, const WfaProb &pr, int s_end, int k_en
 // satisfies the end condition.  Cells a band drops only ever lower the offsets of cells that are not
 // on a cost-optimal alignment inside the band, so when every optimal alignment is known to lie
 // inside the band (flank_seed_band) both the end cell and the back-trace equal the unbanded run's.
+// Narrow-band specialisation: when the band is at most one lane per diagonal and lies inside the
+// initial wavefront, every live wavefront spans exactly [blo, bhi].  Each lane then owns one diagonal
+// for the whole pass, rows have a fixed stride (no per-score bookkeeping to reload) and presence of a
+// score is one bit of a mask.  Writes the same history layout as the general routine.
+template <class G>
+TRGT_HD WfaEnd wfa_forward_band_hist_narrow(const G &g, const WfaProb &pr, int s_cap, int *ws, size_t cap_ints) {
+  WfaEnd out;
+  out.status = TRGT_WFA_OK; out.s = 0; out.k = 0; out.off = 0;
+  const int W = pr.bhi - pr.blo + 1;
+  const size_t hdr = (size_t)TRGT_WFA_META * ((size_t)s_cap + 1);
+  const int idx = g.lane();
+  const int k = pr.blo + idx;
+  const bool mine = idx < W;
+  unsigned long long present = 0;  // bit s: wavefront s is live
+  for (int s = 0; s <= s_cap; s++) {
+    const int sx = s - pr.x, so = s - pr.oe, se = s - pr.e;
+    const bool px = sx >= 0 && ((present >> sx) & 1ull), po = so >= 0 && ((present >> so) & 1ull);
+    const bool pe = se >= 1 && ((present >> se) & 1ull);  // score 0 has no I/D components
+    const bool live = s == 0 || px || po || pe;
+    const size_t base = hdr + (size_t)3 * W * s;
+    if (live && base + (size_t)3 * W > cap_ints) { out.status = TRGT_WFA_OOM; return out; }
+    if (g.lane() == 0) {
+      int *meta = ws + (size_t)TRGT_WFA_META * s;
+      meta[0] = meta[2] = live ? pr.blo : 1;
+      meta[1] = meta[3] = live ? pr.bhi : 0;
+      meta[4] = (int)(unsigned)(base & 0xffffffffu);
+      meta[5] = (int)(unsigned)(base >> 32);
+    }
+    if (!live) continue;
+    int mx = TRGT_WFA_NULL, more = 0;
+    if (mine) {
+      if (s == 0) {
+        mx = wfa_extend8(pr, k, k >= 0 ? k : 0, &more);
+      } else {
+        const int *mo = ws + hdr + (size_t)3 * W * (so > 0 ? so : 0);
+        const int *me = ws + hdr + (size_t)3 * W * (se > 0 ? se : 0);
+        const int *mxs = ws + hdr + (size_t)3 * W * (sx > 0 ? sx : 0);
+        const int o_l = (po && idx > 0) ? mo[idx - 1] : TRGT_WFA_NULL;
+        const int o_r = (po && idx + 1 < W) ? mo[idx + 1] : TRGT_WFA_NULL;
+        const int i_l = (pe && idx > 0) ? me[W + idx - 1] : TRGT_WFA_NULL;
+        const int d_r = (pe && idx + 1 < W) ? me[2 * W + idx + 1] : TRGT_WFA_NULL;
+        const int i1 = wfa_imax(o_l, i_l) + 1;
+        const int d1 = wfa_imax(o_r, d_r);
+        const int mm = (px ? mxs[idx] : TRGT_WFA_NULL) + 1;
+        mx = wfa_imax(mm, wfa_imax(i1, d1));
+        const int h = mx, v = mx - k;
+        if (mx < 0 || h > pr.T || v > pr.P || v < 0) mx = TRGT_WFA_NULL;
+        else mx = wfa_extend8(pr, k, mx, &more);
+        ws[base + W + idx] = i1;
+        ws[base + 2 * W + idx] = d1;
+      }
+    }
+    mx = wfa_extend_finish(g, pr, more, k, mx);
+    if (mine) ws[base + idx] = mx;
+    present |= 1ull << s;
+    // end condition, lowest diagonal first
+    int endk = INT_MAX;
+    if (mine && mx >= 0) {
+      const int h = mx, v = mx - k;
+      if (v >= 0 && v <= pr.P && h <= pr.T &&
+          ((h >= pr.T && pr.P - v <= pr.pef) || (v >= pr.P && pr.T - h <= pr.tef))) endk = k;
+    }
+    endk = g.min_i(endk);
+    g.sync();  // rows of this score are visible to every lane from here on
+    if (endk != INT_MAX) {
+      out.s = s; out.k = endk; out.off = ws[base + (endk - pr.blo)];
+      return out;
+    }
+  }
+  out.status = TRGT_WFA_MAX_STEPS;
+  return out;
+}
+
 template <class G>
 TRGT_HD WfaEnd wfa_forward_band_hist(const G &g, const WfaProb &pr, int s_cap, int *ws, size_t cap_ints) {
   WfaEnd out;
   out.status = TRGT_WFA_OK; out.s = 0; out.k = 0; out.off = 0;
   size_t top = (size_t)TRGT_WFA_META * ((size_t)s_cap + 1);
   if (top > cap_ints) { out.status = TRGT_WFA_OOM; return out; }
+  if (pr.bhi - pr.blo + 1 <= g.size() && g.size() > 1 && pr.blo >= -pr.pbf && pr.bhi <= pr.tbf && s_cap < 64)
+    return wfa_forward_band_hist_narrow(g, pr, s_cap, ws, cap_ints);
   for (int s = 0; s <= s_cap; s++) {
     int lo, hi;
     bool live;
