@@ -176,7 +176,7 @@ def kernel_bytes(name: str, w, hp, res) -> float | None:
     P = 250
     n_reads = w.n_reads
     read_bytes = float(w.reads.data.nbytes)
-    if name == "k_flank_locate":
+    if name == "k_flank_exact":
         return read_bytes + 2.0 * P * w.n_loci + 2 * 20.0 * n_reads + 8.0 * n_reads
     n_wfa = hp.n_wfa()
     mean_t = read_bytes / max(1, n_reads)

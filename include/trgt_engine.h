@@ -94,7 +94,7 @@ void trgt_engine_set_workspace_budget(trgt_engine_t *eng, size_t bytes);
 /* Phase A settles a (read, flank) pair that misses the exact search on chip when its alignment
  * cost is <= max_cost (seed filter + banded wavefront, results identical to the full-width
  * alignment); costlier pairs take the full-width path.  0 sends every miss down the full-width
- * path.  Default 20. */
+ * path.  Default 16. */
 void trgt_engine_set_flank_band_budget(trgt_engine_t *eng, int32_t max_cost);
 
 /* pinned host memory for the caller's packing buffers (DMA-direct H2D/D2H) */

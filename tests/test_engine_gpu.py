@@ -143,7 +143,7 @@ def test_flank_spans_synthetic_hifi(engine, oracle, band_budget):
         engine.set_flank_band_budget(20)
     n_wfa = _check_flanks(oracle, w, spans, hits, w.scoring, w.min_flank_id_frac)
     assert n_wfa > 20  # the WFA fallback was exercised
-    assert "k_flank_locate" in stats
+    assert "k_flank_exact" in stats
 
 
 def test_flank_spans_long_reads_and_repetitive_flanks(engine, oracle):

@@ -84,7 +84,7 @@ struct trgt_engine {
   trgt_hmm_batch_t *one_hmm = nullptr;
   DevBuf d_ed[6];
   size_t workspace_budget = (size_t)24 << 30;  // cap on back-pointer / trace workspace per wave
-  int band_budget = 20;  // cost cap of the banded flank fallback (0: always use the full-width path)
+  int band_budget = 16;  // cost cap of the banded flank fallback (0: always use the full-width path)
 };
 
 namespace {
@@ -558,14 +558,27 @@ int32_t trgt_flank_upload(trgt_engine_t *e, const trgt_seqs_t *left_pieces, cons
 static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src, uint32_t l0, uint32_t l1) {
   if (l1 <= l0) return 0;
   const int block = 32;  // one warp per CTA, one locus at a time per warp
-  int grid = 0;
-  TRY(persistent_grid(e, k_flank_locate, block, 0, &grid));
-  if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
-  LaunchScope ls(e, "k_flank_locate");
-  k_flank_locate<<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
-                                                   b->frac, (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p,
-                                                   (Counters *)b->ctr.p);
-  return check_launch(e, "k_flank_locate");
+  {
+    int grid = 0;
+    TRY(persistent_grid(e, k_flank_exact, block, 0, &grid));
+    if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
+    LaunchScope ls(e, "k_flank_exact");
+    k_flank_exact<<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
+                                                 (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p,
+                                                 (Counters *)b->ctr.p);
+    TRY(check_launch(e, "k_flank_exact"));
+  }
+  if (e->band_budget > 0) {
+    int grid = 0;
+    TRY(persistent_grid(e, k_flank_band, block, 0, &grid));
+    if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
+    LaunchScope ls(e, "k_flank_band");
+    k_flank_band<<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
+                                                b->frac, (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p,
+                                                (Counters *)b->ctr.p);
+    TRY(check_launch(e, "k_flank_band"));
+  }
+  return 0;
 }
 
 // pairs the on-chip path deferred: full-width score pass + cone trace; then the combine rule

@@ -1,6 +1,7 @@
 // kernels.cuh -- sm_100a kernels of the tandem-repeat DP engine (included by engine.cu only).
 //
-//   phase A  k_flank_locate    exact flank search + banded WFA fallback   span_locater.rs:7-30
+//   phase A  k_flank_exact     exact flank search by index probes          span_locater.rs:10-12
+//            k_flank_band      banded on-chip WFA fallback for the misses  span_locater.rs:14-25
 //            k_wfa_score       WFA pass 1 (ring, no history) wfaligner.rs:503-528 (flank), :489 (e2e)
 //            k_wfa_trace       WFA pass 2 (cone + back-trace) -> count_matches / span / SAM CIGAR
 //            k_flank_combine   find_tr_spans combine rule   span_locater.rs:53-67
@@ -110,26 +111,32 @@ __device__ __forceinline__ const uint8_t *stage_bytes(const uint8_t *src, int by
   return dst + shift;
 }
 
-// Phase A.  A warp takes one locus at a time: it stages the two flank pieces and builds their 8-mer
-// indexes once, then walks the locus' reads with the next read's cp.async in flight.  Per read, both
-// flanks: exact search (span_locater.rs:10-12) by index probes; on a miss the WFA fallback (:14-25)
-// through the seed filter + banded wavefront of wfa_core.h, all from the staged copy of the read.
-// Pairs the on-chip path cannot settle are appended to `work` as 2*read+side for the full-width
-// kernels below.
+#define TRGT_VIA_PENDING 4  // internal: missed the exact search, waiting for k_flank_band
+
+// smaller per-warp footprint of the exact-search kernel (no WFA scratch)
+struct __align__(16) FlankExactSmem {
+  uint16_t slot[2][TRGT_KIDX_SLOTS];
+  uint8_t piece[2][FL_PIECE];
+  uint8_t txt[2][FL_TXT];
+  int cand[TRGT_CAND_CAP + 4];
+};
+
+// Phase A, step 1.  A warp takes one locus at a time: it stages the two flank pieces and builds
+// their 8-mer indexes once, then walks the locus' reads with the next read's cp.async in flight and
+// runs the exact search (span_locater.rs:10-12) by index probes for both flanks.  Misses are marked
+// TRGT_VIA_PENDING for k_flank_band (or, with the banded path switched off, appended to `work`).
+// Kept separate from the fallback so that this loop -- all reads go through it -- stays a few
+// hundred instructions long and inside the instruction cache.
 __global__ void __launch_bounds__(32)
-k_flank_locate(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
-               int band_budget, double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits,
-               uint32_t *__restrict__ work, Counters *ctr) {
-  __shared__ FlankWarpSmem sm;
+k_flank_exact(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
+              int band_budget, trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work, Counters *ctr) {
+  __shared__ FlankExactSmem sm;
   const WarpGroup g;
   const int lane = g.lane();
-  uint64_t *keys = reinterpret_cast<uint64_t *>(sm.ws);   // 32 seed keys (linear fallback only)
-  int *cand = sm.ws + 64;                                  // TRGT_CAND_CAP + 1 candidates
   for (uint32_t l = l_begin + blockIdx.x; l < l_end; l += gridDim.x) {
     const uint32_t r0 = locus_read_off[l], r1 = locus_read_off[l + 1];
     if (r1 <= r0) continue;
     __syncwarp();
-    // pieces of this locus (staged and indexed once) and its first read
     const uint8_t *pg[2];
     int PL[2];
     pg[0] = src.lp + src.lp_off[l]; PL[0] = (int)(src.lp_off[l + 1] - src.lp_off[l]);
@@ -144,13 +151,14 @@ k_flank_locate(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncwarp();
     bool indexed[2];
+#pragma unroll 1
     for (int side = 0; side < 2; side++) {
       indexed[side] = ps[side] != nullptr && PL[side] >= 16 && PL[side] <= TRGT_KIDX_MAX_P;
       if (indexed[side]) kidx_build(g, KmerIndex{sm.slot[side]}, ps[side], PL[side]);
     }
+#pragma unroll 1
     for (uint32_t r = r0; r < r1; r++) {
       const int cur = (int)((r - r0) & 1u);
-      // prefetch the next read into the other buffer, then wait for this one
       const uint8_t *tg_next = nullptr, *t_next = nullptr;
       int T_next = 0;
       if (r + 1 < r1) {
@@ -163,45 +171,147 @@ k_flank_locate(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
       }
       __syncwarp();
+#pragma unroll 1
       for (int side = 0; side < 2; side++) {
-        WfaProb pr;
-        pr.x = src.x; pr.oe = src.oe; pr.e = src.e;
-        pr.p = ps[side] ? ps[side] : pg[side]; pr.P = PL[side];
-        pr.t = t_s ? t_s : tg; pr.T = T;       // very long reads: straight from global memory
-        pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;  // span_locater.rs:17
-        wfa_unband(pr);
-        const KmerIndex idx{sm.slot[side]};
+        const uint8_t *p = ps[side] ? ps[side] : pg[side];
+        const uint8_t *t = t_s ? t_s : tg;  // very long reads: straight from global memory
+        const int P = PL[side];
         trgt_flank_hit_t h;
         h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
-        int deferred = 0;
-        if (pr.P > 0) {
-          int pos = indexed[side] ? flank_scan_indexed(g, idx, pr.p, pr.P, pr.t, pr.T, cand) : -2;
-          if (pos == -2) pos = flank_scan(g, pr.p, pr.P, pr.t, pr.T);
+        if (P > 0) {
+          int pos = indexed[side] ? flank_scan_indexed(g, KmerIndex{sm.slot[side]}, p, P, t, T, sm.cand) : -2;
+          if (pos == -2) pos = flank_scan(g, p, P, t, T);
           if (pos >= 0) {
-            h.via = TRGT_VIA_EXACT; h.matches = pr.P; h.start = (uint32_t)pos; h.end = (uint32_t)(pos + pr.P);
-          } else {
-            FlankHit fh;
-            fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
-            deferred = band_budget > 0
-                           ? flank_locate_banded(g, pr, band_budget, min_flank_id_frac, keys, sm.ws, FL_WS_INTS, &fh,
-                                                 indexed[side] ? &idx : nullptr, cand)
-                           : 1;
-            if (!deferred) {
-              h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
-              h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
-            }
-          }
-        }
-        if (lane == 0) {
-          if (deferred) {
+            h.via = TRGT_VIA_EXACT; h.matches = P; h.start = (uint32_t)pos; h.end = (uint32_t)(pos + P);
+          } else if (band_budget > 0) {
+            h.via = TRGT_VIA_PENDING;
+          } else if (lane == 0) {
             const unsigned int slot = atomicAdd(&ctr->n_work, 1u);
             work[slot] = 2 * r + (uint32_t)side;
           }
-          hits[2 * r + side] = h;
         }
+        if (lane == 0) hits[2 * r + side] = h;
         __syncwarp();
       }
       tg = tg_next; T = T_next; t_s = t_next;
+    }
+  }
+}
+
+#define FL_LIST 256  // pending reads handled per pass over a locus
+
+struct __align__(16) FlankBandSmem {
+  uint16_t slot[2][TRGT_KIDX_SLOTS];
+  uint8_t piece[2][FL_PIECE];
+  uint8_t txt[2][FL_TXT];
+  uint16_t list[FL_LIST];  // (read - first read of the pass) << 2 | pending sides
+  int cand[TRGT_CAND_CAP + 4];
+  int ws[FL_WS_INTS];
+};
+
+// Phase A, step 2.  Again a warp per locus, but only the (read, flank) pairs left TRGT_VIA_PENDING:
+// the WFA fallback (span_locater.rs:14-25) through the index seed filter + narrow-band wavefront +
+// back-trace of wfa_core.h, from the staged copy of the read (next pending read in flight).  Pairs
+// this cannot settle (pieces that cannot be indexed, no seed, cost above the budget, reads too long
+// to stage) are appended to `work` as 2*read+side for the full-width kernels below.
+__global__ void __launch_bounds__(32)
+k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
+             int band_budget, double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits,
+             uint32_t *__restrict__ work, Counters *ctr) {
+  __shared__ FlankBandSmem sm;
+  const WarpGroup g;
+  const int lane = g.lane();
+  for (uint32_t l = l_begin + blockIdx.x; l < l_end; l += gridDim.x) {
+    const uint32_t r0 = locus_read_off[l], r1 = locus_read_off[l + 1];
+    bool have_index = false;
+    bool indexed[2] = {false, false};
+    const uint8_t *ps[2] = {nullptr, nullptr};
+    int PL[2] = {0, 0};
+#pragma unroll 1
+    for (uint32_t rb = r0; rb < r1; rb += FL_LIST) {
+      const uint32_t re = rb + FL_LIST < r1 ? rb + FL_LIST : r1;
+      // pending reads of this pass, in read order
+      __syncwarp();
+      int n_list = 0;
+      for (uint32_t base = rb; base < re; base += 32) {
+        const uint32_t r = base + (uint32_t)lane;
+        unsigned m = 0;
+        if (r < re) m = (hits[2 * r].via == TRGT_VIA_PENDING ? 1u : 0u) | (hits[2 * r + 1].via == TRGT_VIA_PENDING ? 2u : 0u);
+        const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
+        if (m) sm.list[n_list + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(((r - rb) << 2) | m);
+        n_list += __popc(bal);
+      }
+      __syncwarp();
+      if (n_list == 0) continue;
+      if (!have_index) {  // first pending pair of the locus: stage and index its pieces
+        have_index = true;
+        const uint8_t *pgl = src.lp + src.lp_off[l], *pgr = src.rp + src.rp_off[l];
+        PL[0] = (int)(src.lp_off[l + 1] - src.lp_off[l]);
+        PL[1] = (int)(src.rp_off[l + 1] - src.rp_off[l]);
+        ps[0] = stage_bytes(pgl, PL[0], sm.piece[0], FL_PIECE, lane, 32);
+        ps[1] = stage_bytes(pgr, PL[1], sm.piece[1], FL_PIECE, lane, 32);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+          indexed[side] = ps[side] != nullptr && PL[side] >= 16 && PL[side] <= TRGT_KIDX_MAX_P;
+          if (indexed[side]) kidx_build(g, KmerIndex{sm.slot[side]}, ps[side], PL[side]);
+        }
+      }
+      // first listed read in flight
+      uint32_t r = rb + (uint32_t)(sm.list[0] >> 2);
+      int T = (int)(src.read_off[r + 1] - src.read_off[r]);
+      const uint8_t *t_s = stage_bytes(src.reads + src.read_off[r], T, sm.txt[0], FL_TXT, lane, 32);
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+#pragma unroll 1
+      for (int i = 0; i < n_list; i++) {
+        const unsigned mask = sm.list[i] & 3u;
+        uint32_t r_next = 0;
+        int T_next = 0;
+        const uint8_t *t_next = nullptr;
+        if (i + 1 < n_list) {
+          r_next = rb + (uint32_t)(sm.list[i + 1] >> 2);
+          T_next = (int)(src.read_off[r_next + 1] - src.read_off[r_next]);
+          t_next = stage_bytes(src.reads + src.read_off[r_next], T_next, sm.txt[(i + 1) & 1], FL_TXT, lane, 32);
+          asm volatile("cp.async.commit_group;\n" ::: "memory");
+          asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+          if (!((mask >> side) & 1u)) continue;
+          int deferred = 1;
+          FlankHit fh;
+          fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
+          if (indexed[side] && t_s != nullptr) {
+            WfaProb pr;
+            pr.x = src.x; pr.oe = src.oe; pr.e = src.e;
+            pr.p = ps[side]; pr.P = PL[side];
+            pr.t = t_s; pr.T = T;
+            pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;  // span_locater.rs:17
+            wfa_unband(pr);
+            deferred = flank_locate_banded_lean(g, pr, band_budget, min_flank_id_frac, sm.ws, FL_WS_INTS, &fh,
+                                                KmerIndex{sm.slot[side]}, sm.cand);
+          }
+          if (lane == 0) {
+            trgt_flank_hit_t h;
+            h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
+            if (deferred) {
+              const unsigned int slot = atomicAdd(&ctr->n_work, 1u);
+              work[slot] = 2 * r + (uint32_t)side;
+            } else {
+              h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
+              h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
+            }
+            hits[2 * r + side] = h;
+          }
+          __syncwarp();
+        }
+        r = r_next; T = T_next; t_s = t_next;
+      }
     }
   }
 }

@@ -968,6 +968,45 @@ TRGT_HD int flank_locate_banded(const G &g, const WfaProb &pr, int S, double min
   return 1;
 }
 
+// Lean variant for k_flank_band: index-only seed filter and the narrow-band forward pass only; any
+// pair that would need the linear seed scan, a band wider than one lane per diagonal, or more
+// scratch is handed to the full-width path instead (returns 1).  Keeps the kernel's code small
+// enough to stay resident in the instruction cache.
+template <class G>
+TRGT_HD int flank_locate_banded_lean(const G &g, const WfaProb &pr, int S, double min_flank_id_frac, int *ws,
+                                     size_t ws_ints, FlankHit *hit, const KmerIndex &idx, int *cand) {
+  const int tier1 = wfa_imin(S, wfa_imax(pr.x, pr.oe));
+#pragma unroll 1
+  for (int tier = 0; tier < 2; tier++) {
+    const int cap = tier == 0 ? tier1 : S;
+    if (tier == 1 && S <= tier1) break;
+    int klo, khi;
+    if (flank_seed_band_indexed(g, idx, pr, cap, cand, &klo, &khi) != 1) continue;
+    WfaProb bp = pr;
+    bp.blo = klo; bp.bhi = khi;
+    if (khi - klo + 1 > g.size() || klo < -pr.pbf || khi > pr.tbf || cap >= 64 ||
+        (size_t)TRGT_WFA_META * ((size_t)cap + 1) > ws_ints)
+      continue;
+    const WfaEnd end = wfa_forward_band_hist_narrow(g, bp, cap, ws, ws_ints);
+    g.sync();
+    if (end.status != TRGT_WFA_OK) continue;
+    if (g.lane() == 0) {
+      WfaFlankSink sink(pr.T);
+      wfa_backtrace(pr, end.s, end.k, end.off, ws, sink);
+      hit->matches = sink.matches;
+      hit->score = -end.s;
+      if ((double)sink.matches >= (double)pr.P * min_flank_id_frac) {  // span_locater.rs:19-25, :46
+        hit->via = 2; hit->start = sink.ystart(); hit->end = sink.yend();
+      } else {
+        hit->via = 3; hit->start = 0; hit->end = 0;
+      }
+    }
+    g.sync();
+    return 0;
+  }
+  return 1;
+}
+
 // ---------------------------------------------------------------- unit-cost edit distance ------
 
 // Levenshtein distance, one lane per pair: bit-vector DP (Myers 1999, global variant of Hyyro 2003)
