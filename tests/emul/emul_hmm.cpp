@@ -83,11 +83,14 @@ long emu_hmm_annotate_lanes(const uint8_t *motifs, const uint64_t *moff, int nm,
   std::vector<uint32_t> mc_tmp(nm + 1, 0);
   std::vector<uint32_t> rev(path_cap ? path_cap : 1);
   uint64_t plen = 0;
-  HmmAnnot a = hmm_annotate(model, allele, L, bp.data(), 6, mc_tmp.data(), nullptr, 0, rev.data(),
+  // the walks use the table-free model, as the device's one-thread-per-allele kernels do
+  const HmmModelScan scan = hmm_model_scan(motifs, moff, nm);
+  if (scan.S != S) return -404;
+  HmmAnnot a = hmm_annotate(scan, allele, L, bp.data(), 6, mc_tmp.data(), nullptr, 0, rev.data(),
                             path_cap, 0, &plen);
   if (a.status < 0) return -402;
   if (a.n_spans > span_cap) return -2;
-  HmmAnnot b2 = hmm_annotate(model, allele, L, bp.data(), 6, mc, spans, a.n_spans, nullptr, 0, 0, nullptr);
+  HmmAnnot b2 = hmm_annotate(scan, allele, L, bp.data(), 6, mc, spans, a.n_spans, nullptr, 0, 0, nullptr);
   if (b2.n_spans != a.n_spans) return -403;
   *purity = a.purity;
   if (path_len) *path_len = plen;

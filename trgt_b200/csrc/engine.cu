@@ -309,8 +309,7 @@ int32_t trgt_engine_create(int32_t device, trgt_engine_t **out) {
     if ((err = cudaFuncSetAttribute(k_wfa_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_wfa_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_wfa_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
-        (err = cudaFuncSetAttribute(k_hmm_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
-        (err = cudaFuncSetAttribute(k_hmm_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) {
+        (err = cudaFuncSetAttribute(k_hmm_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) {
       g_create_error = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(err);
       trgt_engine_destroy(e);
       return TRGT_ERR_CUDA;
@@ -584,6 +583,14 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
 // pairs the on-chip path deferred: full-width score pass + cone trace; then the combine rule
 static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src) {
   Counters *ctr = (Counters *)b->ctr.p;
+  if (e->band_budget > 0) {
+    int grid = 0;
+    TRY(persistent_grid(e, k_flank_band_wide, 32, 0, &grid));
+    LaunchScope ls(e, "k_flank_band_wide");
+    k_flank_band_wide<<<grid, 32, 0, e->stream>>>(src, (uint32_t *)b->work.p, &ctr->n_work, b->frac,
+                                                  (trgt_flank_hit_t *)b->hits.p, ctr);
+    TRY(check_launch(e, "k_flank_band_wide"));
+  }
   {
     const int block = 128;
     const size_t bound = ring_ints_bound(src.x, src.oe, src.e, b->Pmax, b->Tmax);
@@ -609,7 +616,7 @@ static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src
   }
   CU(e, cudaMemcpyAsync(e->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaStreamSynchronize(e->stream));
-  b->last_n_work = e->h_ctr->n_work;
+  b->last_n_work = e->h_ctr->n_work - e->h_ctr->n_banded;  // pairs that needed the full-width kernels
   TRY(launch_trace(e, src, (const uint32_t *)b->work.p, &ctr->n_work, e->h_ctr->n_work, (const WfaEnd *)b->ends.p,
                    e->h_ctr->max_trace_ints, b->gws, b->frac, (trgt_flank_hit_t *)b->hits.p, nullptr, 0, nullptr,
                    nullptr, nullptr, ctr));
@@ -1187,22 +1194,27 @@ static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
   hb.warp_bytes = b->warp_bytes;
   const int block = 128, wpb = 4;
   const size_t smem = b->warp_bytes * wpb;
-  int grid_v = 0, grid_e = 0;
+  int grid_v = 0;
   TRY(persistent_grid(e, k_hmm_viterbi, block, smem, &grid_v));
-  TRY(persistent_grid(e, k_hmm_emit, block, smem, &grid_e));
   unsigned long long span_base = 0, path_base = 0;
   for (auto &w : b->waves) {
     const uint32_t a0 = w.first, a1 = w.second, cnt = a1 - a0;
     const uint32_t need = (cnt + wpb - 1) / wpb;
+    const uint32_t tgrid = (cnt + 127) / 128;  // one thread per allele for the walks
     const unsigned long long bp_base = b->h_bp_off[a0];
     {
       LaunchScope ls(e, "k_hmm_viterbi");
       const int grid = (uint32_t)grid_v > need ? (int)need : grid_v;
-      k_hmm_viterbi<<<grid, block, smem, e->stream>>>(hb, a0, a1, bp_base, (uint8_t *)b->bp.p, (uint32_t *)b->mc.p,
-                                                      (double *)b->purity.p, (uint32_t *)b->n_spans.p,
-                                                      b->want_paths ? (unsigned long long *)b->path_len.p : nullptr,
-                                                      (int32_t *)b->status.p);
+      k_hmm_viterbi<<<grid, block, smem, e->stream>>>(hb, a0, a1, bp_base, (uint8_t *)b->bp.p, (int32_t *)b->status.p);
       TRY(check_launch(e, "k_hmm_viterbi"));
+    }
+    {
+      LaunchScope ls(e, "k_hmm_walk");
+      k_hmm_walk<<<tgrid, 128, 0, e->stream>>>(hb, a0, a1, bp_base, (const uint8_t *)b->bp.p, (uint32_t *)b->mc.p,
+                                               (double *)b->purity.p, (uint32_t *)b->n_spans.p,
+                                               b->want_paths ? (unsigned long long *)b->path_len.p : nullptr,
+                                               (int32_t *)b->status.p);
+      TRY(check_launch(e, "k_hmm_walk"));
     }
     // span offsets of this wave: base + exclusive scan (n_spans[a1] is scratch and zeroed first)
     CU(e, cudaMemsetAsync((uint32_t *)b->n_spans.p + a1, 0, sizeof(uint32_t), e->stream));
@@ -1226,8 +1238,7 @@ static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
     if (b->want_paths) TRY(dev_reserve(e, b->paths, (size_t)(path_end + 1) * sizeof(uint32_t), true));
     if (span_end > span_base || path_end > path_base) {
       LaunchScope ls(e, "k_hmm_emit");
-      const int grid = (uint32_t)grid_e > need ? (int)need : grid_e;
-      k_hmm_emit<<<grid, block, smem, e->stream>>>(hb, a0, a1, bp_base, (const uint8_t *)b->bp.p,
+      k_hmm_emit<<<tgrid, 128, 0, e->stream>>>(hb, a0, a1, bp_base, (const uint8_t *)b->bp.p,
                                                    (const uint32_t *)b->n_spans.p,
                                                    (const unsigned long long *)b->span_off.p,
                                                    (trgt_motif_span_t *)b->spans.p,

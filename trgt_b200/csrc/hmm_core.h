@@ -49,51 +49,6 @@ struct HmmSpan {
   uint32_t motif_index, start, end;
 };
 
-// Block table of one locus' model.  Block b < nb-1 is motif b, block nb-1 is the skip block.
-struct HmmModel {
-  int S;                      // 7 + sum(3 n + 1)                      builder.rs:5-6
-  int nb;                     // motifs + 1
-  const uint8_t *motif_bytes; // sanitised motif bytes, concatenated
-  const uint32_t *blk_moff;   // [nb] offset of the motif's bytes
-  const uint32_t *blk_mmoff;  // [nb] offset of the motif's jump-in ln table (indexed by match index)
-  const uint16_t *blk_n;      // [nb] motif length (skip block: 0)
-  const uint16_t *blk_ms;     // [nb] state index of the block's ms
-  const uint16_t *st_blk;     // [S] block of each state (0xFFFF: start, rs, re, end)
-};
-
-enum HmmRoleKind {
-  HR_START = 0, HR_RS, HR_RE, HR_END, HR_MS, HR_MATCH, HR_INS, HR_DEL, HR_ME, HR_SKIP_MS, HR_SKIP, HR_SKIP_ME
-};
-
-struct HmmRole {
-  int kind, b, i, n, ms;
-};
-
-TRGT_HD HmmRole hmm_role(const HmmModel &m, int st) {
-  HmmRole r;
-  r.b = -1; r.i = 0; r.n = 0; r.ms = 0;
-  if (st == 0) { r.kind = HR_START; return r; }
-  if (st == 1) { r.kind = HR_RS; return r; }
-  if (st == m.S - 2) { r.kind = HR_RE; return r; }
-  if (st == m.S - 1) { r.kind = HR_END; return r; }
-  const int b = m.st_blk[st];
-  r.b = b;
-  r.ms = m.blk_ms[b];
-  const int off = st - r.ms;
-  if (b == m.nb - 1) {
-    r.kind = off == 0 ? HR_SKIP_MS : (off == 1 ? HR_SKIP : HR_SKIP_ME);
-    return r;
-  }
-  const int n = m.blk_n[b];
-  r.n = n;
-  if (off == 0) { r.kind = HR_MS; }
-  else if (off <= n) { r.kind = HR_MATCH; r.i = off - 1; }
-  else if (off <= 2 * n) { r.kind = HR_INS; r.i = off - n - 1; }
-  else if (off < 3 * n) { r.kind = HR_DEL; r.i = off - 2 * n - 1; }
-  else { r.kind = HR_ME; }
-  return r;
-}
-
 // replace_invalid_bases(seq, ATCG) for one base, utils.rs:29-42
 TRGT_HD uint8_t hmm_clean_base(uint8_t b, uint32_t index) {
   if (b == 'A' || b == 'T' || b == 'C' || b == 'G') return b;
@@ -108,6 +63,91 @@ TRGT_HD uint8_t hmm_clean_motif_base(uint8_t b, uint32_t index) {
 }
 // encode_base, hmm_model.rs:243-252 ('#' = 0 is produced by the column loop itself)
 TRGT_HD int hmm_symbol(uint8_t b) { return b == 'A' ? 1 : (b == 'T' ? 2 : (b == 'C' ? 3 : 4)); }
+
+// Block table of one locus' model.  Block b < nb-1 is motif b, block nb-1 is the skip block.
+struct HmmModel {
+  int S;                      // 7 + sum(3 n + 1)                      builder.rs:5-6
+  int nb;                     // motifs + 1
+  const uint8_t *motif_bytes; // sanitised motif bytes, concatenated
+  const uint32_t *blk_moff;   // [nb] offset of the motif's bytes
+  const uint32_t *blk_mmoff;  // [nb] offset of the motif's jump-in ln table (indexed by match index)
+  const uint16_t *blk_n;      // [nb] motif length (skip block: 0)
+  const uint16_t *blk_ms;     // [nb] state index of the block's ms
+  const uint16_t *st_blk;     // [S] block of each state (0xFFFF: start, rs, re, end)
+  // accessors shared with HmmModelScan (hmm_annotate is written against these)
+  TRGT_HD int block_of(int st) const { return st_blk[st]; }
+  TRGT_HD int block_ms(int b) const { return blk_ms[b]; }
+  TRGT_HD int block_n(int b) const { return blk_n[b]; }
+  TRGT_HD uint8_t motif_byte(int b, int i) const { return motif_bytes[blk_moff[b] + i]; }
+};
+
+// The same model addressed straight from the packed motif set, without any table: block geometry is
+// recomputed by scanning the locus' motif offsets.  For one thread per allele (back-pointer walks),
+// where per-thread tables would not fit on chip and loci have one or two motifs anyway.
+struct HmmModelScan {
+  int S, nb;
+  const uint8_t *motifs;    // raw motif bytes of the whole batch
+  const uint64_t *moff;     // offsets of this locus' motifs: moff[0..nb-1]
+  TRGT_HD int block_n(int b) const { return b == nb - 1 ? 0 : (int)(moff[b + 1] - moff[b]); }
+  TRGT_HD int block_ms(int b) const {
+    int ms = 2;
+    for (int i = 0; i < b; i++) ms += 3 * (int)(moff[i + 1] - moff[i]) + 1;
+    return ms;
+  }
+  TRGT_HD int block_of(int st) const {
+    int ms = 2;
+    for (int b = 0; b < nb - 1; b++) {
+      const int sz = 3 * (int)(moff[b + 1] - moff[b]) + 1;
+      if (st < ms + sz) return b;
+      ms += sz;
+    }
+    return nb - 1;
+  }
+  TRGT_HD uint8_t motif_byte(int b, int i) const { return hmm_clean_motif_base(motifs[moff[b] + i], (uint32_t)i); }
+};
+
+TRGT_HD HmmModelScan hmm_model_scan(const uint8_t *motifs, const uint64_t *moff, int nm) {
+  HmmModelScan m;
+  m.motifs = motifs; m.moff = moff; m.nb = nm + 1;
+  int S = 7;
+  for (int b = 0; b < nm; b++) S += 3 * (int)(moff[b + 1] - moff[b]) + 1;
+  m.S = S;
+  return m;
+}
+
+enum HmmRoleKind {
+  HR_START = 0, HR_RS, HR_RE, HR_END, HR_MS, HR_MATCH, HR_INS, HR_DEL, HR_ME, HR_SKIP_MS, HR_SKIP, HR_SKIP_ME
+};
+
+struct HmmRole {
+  int kind, b, i, n, ms;
+};
+
+template <class M>
+TRGT_HD HmmRole hmm_role(const M &m, int st) {
+  HmmRole r;
+  r.b = -1; r.i = 0; r.n = 0; r.ms = 0;
+  if (st == 0) { r.kind = HR_START; return r; }
+  if (st == 1) { r.kind = HR_RS; return r; }
+  if (st == m.S - 2) { r.kind = HR_RE; return r; }
+  if (st == m.S - 1) { r.kind = HR_END; return r; }
+  const int b = m.block_of(st);
+  r.b = b;
+  r.ms = m.block_ms(b);
+  const int off = st - r.ms;
+  if (b == m.nb - 1) {
+    r.kind = off == 0 ? HR_SKIP_MS : (off == 1 ? HR_SKIP : HR_SKIP_ME);
+    return r;
+  }
+  const int n = m.block_n(b);
+  r.n = n;
+  if (off == 0) { r.kind = HR_MS; }
+  else if (off <= n) { r.kind = HR_MATCH; r.i = off - 1; }
+  else if (off <= 2 * n) { r.kind = HR_INS; r.i = off - n - 1; }
+  else if (off < 3 * n) { r.kind = HR_DEL; r.i = off - 2 * n - 1; }
+  else { r.kind = HR_ME; }
+  return r;
+}
 
 // Fill the block table for one locus.  `motifs`/`moff` are the raw motif bytes and offsets of
 // this locus' nm motifs (moff[0..nm], absolute offsets into `motifs`).  mm_off[n] locates the
@@ -314,10 +354,11 @@ TRGT_HD void hmm_viterbi(const G &g, const HmmModel &m, const HmmConsts &c, cons
 }
 
 // predecessor of `st` through in-edge `e` (inverse of the enumeration order above)
-TRGT_HD int hmm_pred(const HmmModel &m, const HmmRole &r, int st, int e) {
+template <class M>
+TRGT_HD int hmm_pred(const M &m, const HmmRole &r, int st, int e) {
   switch (r.kind) {
     case HR_END: return m.S - 2;
-    case HR_RE: return m.blk_ms[e] + (e == m.nb - 1 ? 2 : 3 * (int)m.blk_n[e]);
+    case HR_RE: return m.block_ms(e) + (e == m.nb - 1 ? 2 : 3 * m.block_n(e));
     case HR_RS: return e == 0 ? 0 : m.S - 2;
     case HR_MS: return e == 0 ? 1 : r.ms + 3 * r.n;
     case HR_SKIP_MS: return e == 0 ? 1 : r.ms + 2;
@@ -345,7 +386,8 @@ struct HmmAnnot {
 // path_out (optional): receives the state path (Hmm::label).  With path_total == 0 it is written
 // in REVERSE order, up to path_cap entries; with path_total = the length found by a previous walk
 // it is written in forward order.  *path_len gets the full length.
-TRGT_HD HmmAnnot hmm_annotate(const HmmModel &m, const uint8_t *allele, int L, const uint8_t *bp,
+template <class M>
+TRGT_HD HmmAnnot hmm_annotate(const M &m, const uint8_t *allele, int L, const uint8_t *bp,
                               int max_motif_len, uint32_t *mc, HmmSpan *spans_out, uint32_t n_total,
                               uint32_t *path_out, uint64_t path_cap, uint64_t path_total,
                               uint64_t *path_len) {
@@ -380,7 +422,7 @@ TRGT_HD HmmAnnot hmm_annotate(const HmmModel &m, const uint8_t *allele, int L, c
               keep = false;
             } else {
               for (int i = 0; i < r.n; i++) {
-                const uint8_t expected = m.motif_bytes[m.blk_moff[r.b] + i];
+                const uint8_t expected = m.motif_byte(r.b, i);
                 const uint8_t observed = hmm_clean_base(allele[copy_start + i], (uint32_t)(copy_start + i));
                 if (expected != 'N' && observed != expected) keep = false;
               }
@@ -407,7 +449,7 @@ TRGT_HD HmmAnnot hmm_annotate(const HmmModel &m, const uint8_t *allele, int L, c
       }
       case HR_MATCH: {
         emits = true;
-        const uint8_t expected = m.motif_bytes[m.blk_moff[r.b] + r.i];
+        const uint8_t expected = m.motif_byte(r.b, r.i);
         const uint8_t base = hmm_clean_base(allele[col - 1], (uint32_t)(col - 1));
         if (base == expected || expected == 'N') n_match++; else n_mis++;
         break;

@@ -7,7 +7,7 @@
 //            k_flank_combine   find_tr_spans combine rule   span_locater.rs:53-67
 //   phase B  k_wfa_score / k_wfa_trace in end-to-end mode, k_cigar_gather   utils/align.rs:14-28
 //            k_edit_dist       get_dist_matrix              genotype_cluster.rs:236-286
-//   phase C  k_hmm_viterbi, k_hmm_emit                      src/hmm/*, tr.rs:454-492
+//   phase C  k_hmm_viterbi, k_hmm_walk, k_hmm_emit          src/hmm/*, tr.rs:454-492
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -316,6 +316,41 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
   }
 }
 
+// Phase A, step 3.  Second chance for the pairs k_flank_band deferred (band wider than a warp, cost
+// above its budget, scratch too small): one warp per pair with 32 KB of scratch and the general
+// banded routine (linear seed scan, any band width, history or ring + cone), budgets 24 then 36.
+// What it settles is struck from the work list (0xFFFFFFFF); only pairs without any usable seed are
+// left for the full-width kernels.
+#define FLW_WS_INTS 8192
+
+__global__ void __launch_bounds__(32)
+k_flank_band_wide(WfaSrc src, uint32_t *__restrict__ work, const unsigned int *n_work_ptr, double min_flank_id_frac,
+                  trgt_flank_hit_t *__restrict__ hits, Counters *ctr) {
+  __shared__ __align__(16) int ws[FLW_WS_INTS];
+  __shared__ uint64_t keys[32];
+  const WarpGroup g;
+  const uint32_t n = *n_work_ptr;
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint32_t id = work[i];
+    const WfaProb pr = wfa_prob_of(src, id);
+    int settled = 0;
+    FlankHit fh;
+    fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
+#pragma unroll 1
+    for (int S = 24; S <= 36 && !settled; S += 12)
+      settled = flank_locate_banded(g, pr, S, min_flank_id_frac, keys, ws, FLW_WS_INTS, &fh) == 0;
+    if (g.lane() == 0 && settled) {
+      trgt_flank_hit_t h;
+      h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
+      h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
+      hits[id] = h;
+      work[i] = 0xFFFFFFFFu;
+      atomicAdd(&ctr->n_banded, 1u);
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------ WFA pass 1 -------------
 
 // Persistent groups (a CTA when BLOCK, else a warp) pull items; ring on chip when it fits.
@@ -398,6 +433,10 @@ __global__ void k_wfa_score(WfaSrc src, const uint32_t *__restrict__ work, const
   }
   for (uint32_t i = slot; i < n; i += n_slots) {
     const uint32_t id = work ? work[i] : i;
+    if (id == 0xFFFFFFFFu) {  // settled by k_flank_band_wide
+      if (lane0) { WfaEnd done; done.status = 1; done.s = 0; done.k = 0; done.off = 0; ends[i] = done; }
+      continue;
+    }
     const WfaProb pr = wfa_prob_of(src, id);
     const size_t need = wfa_ring_ints(pr);
     int *ring = (need <= (size_t)smem_ring_ints) ? my_smem : (gring ? gring + (size_t)slot * gring_stride : nullptr);
@@ -454,6 +493,7 @@ k_wfa_trace(WfaSrc src, const uint32_t *__restrict__ work, const unsigned int *n
   int *my_smem = smem_i + (size_t)wib * smem_ws_ints;
   for (uint32_t i = slot; i < n; i += n_slots) {
     const uint32_t id = work[i];
+    if (id == 0xFFFFFFFFu) continue;  // settled by k_flank_band_wide
     const WfaProb pr = wfa_prob_of(src, id);
     const WfaEnd end = (src.mode == WFA_MODE_FLANK) ? ends[i] : ends[id];
     if (end.status != TRGT_WFA_OK) {
@@ -636,11 +676,10 @@ __device__ __forceinline__ HmmWarpMem hmm_carve(unsigned char *base, int S_max, 
   return w;
 }
 
-// One warp per allele: model build, Viterbi (back-pointers to HBM), counting walk.
+// One warp per allele: model build in shared memory, Viterbi, back-pointers to HBM.
 __global__ void __launch_bounds__(128)
 k_hmm_viterbi(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, uint8_t *__restrict__ bp,
-              uint32_t *__restrict__ mc, double *__restrict__ purity, uint32_t *__restrict__ n_spans,
-              unsigned long long *__restrict__ path_len, int32_t *__restrict__ status) {
+              int32_t *__restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_b[];
   const WarpGroup g;
   const uint32_t wib = threadIdx.x >> 5;
@@ -652,64 +691,66 @@ k_hmm_viterbi(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base,
     const int nm = (int)(hb.locus_motif_off[l + 1] - m0);
     const uint8_t *allele = hb.alleles + hb.allele_off[a];
     const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
-    uint32_t *my_mc = mc + hb.mc_off[a];
-    for (int b = g.lane(); b < nm; b += 32) my_mc[b] = 0;
     HmmModel model;
     const int S = hmm_model_build(g, hb.motifs, hb.motif_off + m0, nm, hb.mm_off, wm.bytes, wm.moff, wm.mmoff,
                                   wm.n, wm.ms, wm.stblk, &model);
-    if (S < 0 || L == 0) {
-      if (g.lane() == 0) {
-        purity[a] = nan("");  // purity.rs:7-9
-        n_spans[a] = 0;
-        if (path_len) path_len[a] = 0;
-        status[a] = S < 0 ? TRGT_ITEM_INVALID_BASE : 0;
-      }
-      __syncwarp();
-      continue;
-    }
-    uint8_t *my_bp = bp + (hb.bp_off[a] - bp_base);
-    hmm_viterbi(g, model, hb.c, hb.mm_lp, allele, L, wm.sc0, wm.sc1, my_bp);
-    __syncwarp();
-    if (g.lane() == 0) {
-      uint64_t plen = 0;
-      const HmmAnnot an = hmm_annotate(model, allele, L, my_bp, 6, my_mc, nullptr, 0, nullptr, 0, 0, &plen);
-      purity[a] = an.purity;
-      n_spans[a] = an.n_spans;
-      if (path_len) path_len[a] = plen;
-      status[a] = an.status < 0 ? TRGT_ERR_INTERNAL : 0;
-    }
+    if (g.lane() == 0) status[a] = S < 0 ? TRGT_ITEM_INVALID_BASE : 0;
+    if (S >= 0 && L > 0)
+      hmm_viterbi(g, model, hb.c, hb.mm_lp, allele, L, wm.sc0, wm.sc1, bp + (hb.bp_off[a] - bp_base));
     __syncwarp();
   }
 }
 
-// Second walk: writes the collapsed spans (and optionally the state path) at their CSR offsets.
+// One thread per allele: the counting walk over the back-pointers (purity, MC, number of collapsed
+// spans, optional path length).  Uses the table-free model (HmmModelScan).
+__global__ void __launch_bounds__(128)
+k_hmm_walk(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, const uint8_t *__restrict__ bp,
+           uint32_t *__restrict__ mc, double *__restrict__ purity, uint32_t *__restrict__ n_spans,
+           unsigned long long *__restrict__ path_len, int32_t *__restrict__ status) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t a = a0 + blockIdx.x * blockDim.x + threadIdx.x; a < a1; a += gsz) {
+    const uint32_t l = hb.allele_locus[a];
+    const uint32_t m0 = hb.locus_motif_off[l];
+    const int nm = (int)(hb.locus_motif_off[l + 1] - m0);
+    const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
+    uint32_t *my_mc = mc + hb.mc_off[a];
+    for (int b = 0; b < nm; b++) my_mc[b] = 0;
+    if (status[a] != 0 || L == 0) {
+      purity[a] = nan("");  // purity.rs:7-9
+      n_spans[a] = 0;
+      if (path_len) path_len[a] = 0;
+      continue;
+    }
+    const HmmModelScan model = hmm_model_scan(hb.motifs, hb.motif_off + m0, nm);
+    uint64_t plen = 0;
+    const HmmAnnot an = hmm_annotate(model, hb.alleles + hb.allele_off[a], L, bp + (hb.bp_off[a] - bp_base), 6, my_mc,
+                                     nullptr, 0, nullptr, 0, 0, &plen);
+    purity[a] = an.purity;
+    n_spans[a] = an.n_spans;
+    if (path_len) path_len[a] = plen;
+    if (an.status < 0) status[a] = TRGT_ERR_INTERNAL;
+  }
+}
+
+// One thread per allele: the second walk writes the collapsed spans (and optionally the state path)
+// at their CSR offsets.
 __global__ void __launch_bounds__(128)
 k_hmm_emit(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, const uint8_t *__restrict__ bp,
            const uint32_t *__restrict__ n_spans, const unsigned long long *__restrict__ span_off,
            trgt_motif_span_t *__restrict__ spans, const unsigned long long *__restrict__ path_off,
            uint32_t *__restrict__ paths, const int32_t *__restrict__ status) {
-  extern __shared__ __align__(16) unsigned char smem_b[];
-  const WarpGroup g;
-  const uint32_t wib = threadIdx.x >> 5;
-  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-  const HmmWarpMem wm = hmm_carve(smem_b + (size_t)wib * hb.warp_bytes, hb.S_max, hb.nb_max);
-  for (uint32_t a = a0 + blockIdx.x * (blockDim.x >> 5) + wib; a < a1; a += warps) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t a = a0 + blockIdx.x * blockDim.x + threadIdx.x; a < a1; a += gsz) {
     const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
     const uint32_t ns = n_spans[a];
     const unsigned long long plen = path_off ? path_off[a + 1] - path_off[a] : 0;
-    if (L == 0 || status[a] != 0 || (ns == 0 && plen == 0)) continue;  // warp-uniform
+    if (L == 0 || status[a] != 0 || (ns == 0 && plen == 0)) continue;
     const uint32_t l = hb.allele_locus[a];
     const uint32_t m0 = hb.locus_motif_off[l];
     const int nm = (int)(hb.locus_motif_off[l + 1] - m0);
-    HmmModel model;
-    hmm_model_build(g, hb.motifs, hb.motif_off + m0, nm, hb.mm_off, wm.bytes, wm.moff, wm.mmoff, wm.n, wm.ms,
-                    wm.stblk, &model);
-    if (g.lane() == 0) {
-      const uint8_t *allele = hb.alleles + hb.allele_off[a];
-      hmm_annotate(model, allele, L, bp + (hb.bp_off[a] - bp_base), 6, nullptr,
-                   (HmmSpan *)(spans + span_off[a]), ns, plen ? paths + path_off[a] : nullptr, plen, plen, nullptr);
-    }
-    __syncwarp();
+    const HmmModelScan model = hmm_model_scan(hb.motifs, hb.motif_off + m0, nm);
+    hmm_annotate(model, hb.alleles + hb.allele_off[a], L, bp + (hb.bp_off[a] - bp_base), 6, nullptr,
+                 (HmmSpan *)(spans + span_off[a]), ns, plen ? paths + path_off[a] : nullptr, plen, plen, nullptr);
   }
 }
 
