@@ -199,3 +199,32 @@ int emu_flank_indexed(const uint8_t *p_in, int P, const uint8_t *t_in, int T, in
 }
 
 }  // extern "C"
+
+extern "C" {
+
+// end-to-end pair through wfa_e2e_narrow + back-trace with `lanes` lock-step lanes.
+// out[0]=status out[1]=score out[2]=n_words
+int emu_e2e_narrow(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x, int o, int e, int S, int ws_ints,
+                   int *out, uint32_t *words, uint32_t words_cap, int lanes) {
+  std::vector<uint8_t> pbuf(P + 16, 0), tbuf(T + 16, 0);
+  memcpy(pbuf.data(), p_in, P);
+  memcpy(tbuf.data(), t_in, T);
+  WfaProb pr;
+  pr.p = pbuf.data(); pr.P = P; pr.t = tbuf.data(); pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
+  pr.pbf = pr.pef = pr.tbf = pr.tef = 0;
+  wfa_unband(pr);
+  std::vector<int> ws(ws_ints + 1, 0x7ead);
+  WfaEnd end{};
+  trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &g) {
+    const WfaEnd e2 = wfa_e2e_narrow(g, pr, S, ws.data(), (size_t)ws_ints);
+    if (g.lane() == 0) end = e2;
+  });
+  out[0] = end.status; out[1] = -end.s; out[2] = 0;
+  if (end.status != TRGT_WFA_OK) return end.status;
+  WfaCigarSink cs(words, words_cap);
+  wfa_backtrace(pr, end.s, end.k, end.off, ws.data(), cs);
+  out[2] = (int)cs.finish();
+  return 0;
+}
+
+}  // extern "C"

@@ -367,3 +367,27 @@ def test_flank_indexed_core(emul, oracle, lanes):
         else:
             seen["deferred"] += 1
     assert seen["exact"] > 10 and seen["resolved"] > 10
+
+
+def test_e2e_narrow_core(emul, oracle):
+    """Short consensus pairs: the [-R, R] band with cost cap S is the full computation (nothing is
+    reachable outside it), so its history back-traces to the reference's CIGAR."""
+    rng = random.Random(909)
+    resolved = 0
+    for _ in range(250):
+        unit = rnd(rng, rng.randint(2, 6))
+        p = unit * rng.randint(1, 25) if rng.random() < 0.7 else rnd(rng, rng.randint(1, 80))
+        r = rng.random()
+        t = (mutate(rng, p, rng.choice([0.02, 0.05, 0.15])) if r < 0.7 else
+             p + unit * rng.randint(1, 4) if r < 0.85 else p[:len(p) - len(unit) * rng.randint(0, 2)]) or b"A"
+        words, score = oracle.align_words(p, t)
+        out = (C.c_int * 3)()
+        cap = len(p) + len(t) + 8
+        w = (C.c_uint32 * cap)()
+        rc = emul.emu_e2e_narrow(p, len(p), t, len(t), 2, 5, 1, 16, 1280, out, w, cap, 32)
+        if rc == 0:
+            resolved += 1
+            assert out[1] == score and list(w[:out[2]]) == words
+        else:
+            assert -score > 16 or rc == -200
+    assert resolved > 100

@@ -846,6 +846,7 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
   CU(e, cudaMemsetAsync(b->cig_n.p, 0, ((size_t)n + 1) * sizeof(uint32_t), e->stream));
   CU(e, cudaMemsetAsync(b->status.p, 0, ((size_t)n + 1) * sizeof(int32_t), e->stream));
   const size_t bound = ring_ints_bound(src.x, src.oe, src.e, b->Pmax, b->Tmax);
+  unsigned long long pool_cap1 = 0;
   if ((size_t)b->Pmax + (size_t)b->Tmax > 4096) {
     // long alleles: a CTA per pair
     const int block = 128;
@@ -870,11 +871,13 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
   } else {
     const int block = 128, wpb = 4;
     const size_t cap_ints = 6 * 1024;  // 24 KB per warp
-    const int smem_ring_ints = (int)(bound < cap_ints ? bound : cap_ints);
+    size_t want = bound < cap_ints ? bound : cap_ints;
+    if (want < (size_t)(E2E_NARROW_INTS + E2E_NARROW_WORDS)) want = E2E_NARROW_INTS + E2E_NARROW_WORDS;
+    const int smem_ring_ints = (int)want;
     const size_t smem = (size_t)wpb * smem_ring_ints * sizeof(int);
     int grid = 0;
     TRY(persistent_grid(e, k_wfa_score<false>, block, smem, &grid));
-    const uint32_t need = (n + wpb - 1) / wpb;
+    const uint32_t need = (n + 32 * wpb - 1) / (32 * wpb);
     if ((uint32_t)grid > need) grid = (int)need;
     int *gring = nullptr;
     size_t stride = 0;
@@ -883,16 +886,21 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
       TRY(dev_reserve(e, b->gring, (size_t)grid * wpb * stride * sizeof(int)));
       gring = (int *)b->gring.p;
     }
+    // CIGAR pool of the one-pass path (pairs it cannot place fall through to the two-pass path)
+    pool_cap1 = 2ull * n + 65536ull;
+    TRY(dev_reserve(e, b->pool, (size_t)(pool_cap1 + 1) * sizeof(uint32_t)));
     LaunchScope ls(e, "k_wfa_score_warp");
     k_wfa_score<false><<<grid, block, smem, e->stream>>>(src, nullptr, nullptr, n, (WfaEnd *)b->ends.p, gring, stride,
                                                           smem_ring_ints, (uint32_t *)b->trace_work.p,
-                                                          (uint32_t *)b->cig_n.p, ctr);
+                                                          (uint32_t *)b->cig_n.p, ctr, (uint32_t *)b->pool.p, pool_cap1,
+                                                          (unsigned long long *)b->cig_off.p);
     TRY(check_launch(e, "k_wfa_score_warp"));
   }
   CU(e, cudaMemcpyAsync(e->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaStreamSynchronize(e->stream));
-  const unsigned long long words_bound = e->h_ctr->words_bound;
-  TRY(dev_reserve(e, b->pool, (size_t)(words_bound + 1) * sizeof(uint32_t)));
+  // pool = words the one-pass path already placed + room for everything the trace pass may emit
+  const unsigned long long words_bound = e->h_ctr->pool_used + e->h_ctr->words_bound;
+  TRY(dev_reserve(e, b->pool, (size_t)(words_bound + 1) * sizeof(uint32_t), /*keep=*/true));
   TRY(launch_trace(e, src, (const uint32_t *)b->trace_work.p, &ctr->n_trace, e->h_ctr->n_trace, (const WfaEnd *)b->ends.p,
                    e->h_ctr->max_trace_ints, b->gws, 0.0, nullptr, (uint32_t *)b->pool.p, words_bound,
                    (unsigned long long *)b->cig_off.p, (uint32_t *)b->cig_n.p, (int32_t *)b->status.p, ctr));

@@ -356,11 +356,16 @@ k_flank_band_wide(WfaSrc src, uint32_t *__restrict__ work, const unsigned int *n
 // Persistent groups (a CTA when BLOCK, else a warp) pull items; ring on chip when it fits.
 //   work == nullptr: items are 0..n_direct-1, else work[0..*n_work)
 //   ends[i]: result of the i-th item (position in the work list)
+#define E2E_NARROW_COST 16    // cost cap of the one-pass path for short consensus pairs
+#define E2E_NARROW_INTS 1280  // its history: 6*17 header + 3 * 23 diagonals * 17 scores
+#define E2E_NARROW_WORDS 48   // its CIGAR: at most 2 * cost + a few words
+
 template <bool BLOCK>
 __global__ void k_wfa_score(WfaSrc src, const uint32_t *__restrict__ work, const unsigned int *n_work_ptr,
                             uint32_t n_direct, WfaEnd *__restrict__ ends, int *gring, size_t gring_stride,
                             int smem_ring_ints, uint32_t *__restrict__ trace_work, uint32_t *__restrict__ cig_n,
-                            Counters *ctr) {
+                            Counters *ctr, uint32_t *__restrict__ pool = nullptr, unsigned long long pool_cap = 0,
+                            unsigned long long *__restrict__ cig_off = nullptr) {
   extern __shared__ int smem_i[];
   const uint32_t n = work ? *n_work_ptr : n_direct;
   uint32_t slot, n_slots;
@@ -402,13 +407,45 @@ __global__ void k_wfa_score(WfaSrc src, const uint32_t *__restrict__ work, const
         const uint32_t ii = base + src_lane;
         const uint32_t id = work ? work[ii] : ii;
         const WfaProb pr = wfa_prob_of(src, id);
+        const WarpGroup g;
+        WfaEnd end;
+        end.status = TRGT_WFA_OOM; end.s = 0; end.k = 0; end.off = 0;
+        // short, similar pair: one narrow-band pass with history, CIGAR straight from its back-trace
+        bool done = false;
+        if (smem_ring_ints >= E2E_NARROW_INTS + E2E_NARROW_WORDS && pool != nullptr) {
+          end = wfa_e2e_narrow(g, pr, E2E_NARROW_COST, my_smem, E2E_NARROW_INTS);
+          __syncwarp();
+          if (end.status == TRGT_WFA_OK) {
+            if (lane0) {
+              uint32_t *wbuf = (uint32_t *)(my_smem + E2E_NARROW_INTS);
+              WfaCigarSink sink(wbuf, E2E_NARROW_WORDS);
+              wfa_backtrace(pr, end.s, end.k, end.off, my_smem, sink);
+              const uint32_t nw = sink.finish();
+              unsigned long long off = 0;
+              bool ok = !sink.overflow;
+              if (ok && nw) {
+                off = atomicAdd(&ctr->pool_used, (unsigned long long)nw);
+                if (off + nw > pool_cap) ok = false;  // pool full: the generic path takes this pair
+              }
+              if (ok) {
+                for (uint32_t w = 0; w < nw; w++) pool[off + w] = wbuf[w];
+                cig_off[id] = off;
+                cig_n[id] = nw;
+                ends[ii] = end;
+              }
+              my_smem[0] = ok ? 1 : 0;
+            }
+            __syncwarp();
+            done = my_smem[0] != 0;
+            __syncwarp();
+          }
+        }
+        if (done) continue;
         const size_t need = wfa_ring_ints(pr);
         int *ring = (need <= (size_t)smem_ring_ints) ? my_smem : (gring ? gring + (size_t)slot * gring_stride : nullptr);
-        WfaEnd end;
         if (ring == nullptr || (ring != my_smem && need > gring_stride)) {
           end.status = TRGT_WFA_OOM; end.s = 0; end.k = 0; end.off = 0;
         } else {
-          const WarpGroup g;
           end = wfa_score_ring(g, pr, ring, wfa_score_cap(pr));
           __syncwarp();
         }

@@ -49,16 +49,16 @@ struct WfaProb {
 
 TRGT_HD void wfa_unband(WfaProb &pr) { pr.blo = -pr.P; pr.bhi = pr.T; }
 
-// 8 bytes starting at any byte address, assembled from the two aligned words that cover them.
-// May touch up to 15 bytes past `a`: every sequence buffer of the engine is padded by 16 bytes.
+// 8 bytes starting at any byte address, assembled from the three aligned 32-bit words that cover
+// them (two funnel shifts).  May touch up to 11 bytes past `a`: every sequence buffer of the engine
+// is padded by 16 bytes.
 TRGT_HD uint64_t wfa_ld64u(const uint8_t *a) {
 #if defined(__CUDA_ARCH__)
   const uintptr_t addr = (uintptr_t)a;
-  const uint64_t *w = (const uint64_t *)(addr & ~(uintptr_t)7);
-  const unsigned sh = (unsigned)(addr & 7u) * 8u;
-  const uint64_t lo = w[0];
-  if (sh == 0) return lo;
-  return (lo >> sh) | (w[1] << (64u - sh));
+  const uint32_t *w = (const uint32_t *)(addr & ~(uintptr_t)3);
+  const unsigned sh = (unsigned)(addr & 3u) * 8u;
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+  return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
 #else
   uint64_t v;
   memcpy(&v, a, 8);
@@ -400,10 +400,11 @@ TRGT_HD int wfa_trace_forward(const G &g, const WfaProb &pr, int s_end, int k_en
 // satisfies the end condition.  Cells a band drops only ever lower the offsets of cells that are not
 // on a cost-optimal alignment inside the band, so when every optimal alignment is known to lie
 // inside the band (flank_seed_band) both the end cell and the back-trace equal the unbanded run's.
-// Narrow-band specialisation: when the band is at most one lane per diagonal and lies inside the
-// initial wavefront, every live wavefront spans exactly [blo, bhi].  Each lane then owns one diagonal
-// for the whole pass, rows have a fixed stride (no per-score bookkeeping to reload) and presence of a
-// score is one bit of a mask.  Writes the same history layout as the general routine.
+// Narrow-band specialisation: the band is at most one lane per diagonal.  Each lane owns one
+// diagonal for the whole pass, rows have a fixed stride (no per-score bookkeeping to reload) and
+// presence of a score is one bit of a mask.  Every band cell is evaluated at every live score; cells
+// the general routine would leave outside a wavefront come out as (drifted) NULLs, which every
+// consumer treats as NULL.  Writes the same history layout as the general routine.
 template <class G>
 TRGT_HD WfaEnd wfa_forward_band_hist_narrow(const G &g, const WfaProb &pr, int s_cap, int *ws, size_t cap_ints) {
   WfaEnd out;
@@ -432,7 +433,7 @@ TRGT_HD WfaEnd wfa_forward_band_hist_narrow(const G &g, const WfaProb &pr, int s
     int mx = TRGT_WFA_NULL, more = 0;
     if (mine) {
       if (s == 0) {
-        mx = wfa_extend8(pr, k, k >= 0 ? k : 0, &more);
+        if (k >= -pr.pbf && k <= pr.tbf) mx = wfa_extend8(pr, k, k >= 0 ? k : 0, &more);
       } else {
         const int *mo = ws + hdr + (size_t)3 * W * (so > 0 ? so : 0);
         const int *me = ws + hdr + (size_t)3 * W * (se > 0 ? se : 0);
@@ -479,7 +480,7 @@ TRGT_HD WfaEnd wfa_forward_band_hist(const G &g, const WfaProb &pr, int s_cap, i
   out.status = TRGT_WFA_OK; out.s = 0; out.k = 0; out.off = 0;
   size_t top = (size_t)TRGT_WFA_META * ((size_t)s_cap + 1);
   if (top > cap_ints) { out.status = TRGT_WFA_OOM; return out; }
-  if (pr.bhi - pr.blo + 1 <= g.size() && g.size() > 1 && pr.blo >= -pr.pbf && pr.bhi <= pr.tbf && s_cap < 64)
+  if (pr.bhi - pr.blo + 1 <= g.size() && g.size() > 1 && s_cap < 64)
     return wfa_forward_band_hist_narrow(g, pr, s_cap, ws, cap_ints);
   for (int s = 0; s <= s_cap; s++) {
     int lo, hi;
@@ -580,6 +581,23 @@ TRGT_HD void wfa_backtrace(const WfaProb &pr, int s_end, int k_end, int off_end,
   }
   sink.op('D', v);
   sink.op('I', h);
+}
+
+// End-to-end alignment of a short pair in one pass: with cost cap S every cell the full computation
+// can reach lies on |k| <= R = (S - o) / e (a path's drift is its total gap length), so the band
+// [-R, R] loses nothing at all -- not even non-optimal cells -- and its history can be back-traced
+// directly.  Needs 2R+1 <= group size.  Returns status MAX_STEPS if the cost exceeds S.
+template <class G>
+TRGT_HD WfaEnd wfa_e2e_narrow(const G &g, const WfaProb &pr, int S, int *ws, size_t cap_ints) {
+  WfaEnd out;
+  out.status = TRGT_WFA_OOM; out.s = 0; out.k = 0; out.off = 0;
+  const int o = pr.oe - pr.e;
+  const int R = S > o ? (S - o) / pr.e : 0;
+  WfaProb bp = pr;
+  bp.blo = wfa_imax(-pr.P, -R);
+  bp.bhi = wfa_imin(pr.T, R);
+  if (bp.bhi - bp.blo + 1 > g.size() || S >= 64 || (size_t)TRGT_WFA_META * ((size_t)S + 1) > cap_ints) return out;
+  return wfa_forward_band_hist_narrow(g, bp, S, ws, cap_ints);
 }
 
 // count_matches (wfaligner.rs:988) and the text span of get_alignment_span (:864-908)
@@ -984,7 +1002,7 @@ TRGT_HD int flank_locate_banded_lean(const G &g, const WfaProb &pr, int S, doubl
     if (flank_seed_band_indexed(g, idx, pr, cap, cand, &klo, &khi) != 1) continue;
     WfaProb bp = pr;
     bp.blo = klo; bp.bhi = khi;
-    if (khi - klo + 1 > g.size() || klo < -pr.pbf || khi > pr.tbf || cap >= 64 ||
+    if (khi - klo + 1 > g.size() || cap >= 64 ||
         (size_t)TRGT_WFA_META * ((size_t)cap + 1) > ws_ints)
       continue;
     const WfaEnd end = wfa_forward_band_hist_narrow(g, bp, cap, ws, ws_ints);
