@@ -172,31 +172,32 @@ def run_reference(args):
 # ------------------------------------------------------------------ roofline -----------------
 
 def kernel_bytes(name: str, w, hp, res) -> float | None:
-    """Algorithmic bytes one launch of `name` must move for this workload ('Roofline')."""
-    P = 250
+    """Algorithmic bytes one launch of `name` must move for this workload."""
+    P = float(np.diff(w.left.offsets.astype(np.int64)).mean()) if len(w.left) else 250.0
     n_reads = w.n_reads
-    read_bytes = float(w.reads.data.nbytes)
-    if name == "k_flank_exact":
+    read_len = np.diff(w.reads.offsets.astype(np.int64)).astype(np.float64)
+    read_bytes = float(read_len.sum())
+    g = res.glue
+    if name == "k_flank_exact":   # every read base once, both pieces once per locus, one hit per (read, flank)
         return read_bytes + 2.0 * P * w.n_loci + 2 * 20.0 * n_reads + 8.0 * n_reads
-    n_wfa = hp.n_wfa()
-    mean_t = read_bytes / max(1, n_reads)
-    if name == "k_wfa_score_block":
-        return n_wfa * (P + mean_t + 16.0 + 4.0)
-    if name == "k_wfa_trace":
-        return n_wfa * (2.0 * P + 20.0 + 16.0 + 4.0) + (len(res.glue.seqs) * 0.0)
+    if name in ("k_flank_band", "k_flank_band_wide") and res.hits is not None:
+        via = res.hits["via"].reshape(-1, 2)
+        pend = (via >= 2)
+        pend_reads = pend.any(axis=1)
+        if name == "k_flank_band":  # hit records scanned, pending reads re-read once, pieces once per locus, hits rewritten
+            return float(40.0 * n_reads + read_len[pend_reads].sum() + 2.0 * P * w.n_loci + 20.0 * pend.sum())
+        return None
     if name == "k_hmm_viterbi":
-        a = res.annotations
-        L = np.diff(res.glue.backbones.offsets.astype(np.int64)).astype(np.float64)
-        nm = np.diff(w.locus_motif_off.astype(np.int64))[res.glue.group_locus]
+        L = np.diff(g.backbones.offsets.astype(np.int64)).astype(np.float64)
+        nm = np.diff(w.locus_motif_off.astype(np.int64))[g.group_locus]
         mlen = np.diff(w.motifs.offsets.astype(np.int64))
-        # one motif per locus in this catalog: S = 7 + 3n + 1
-        first = w.locus_motif_off[:-1][res.glue.group_locus]
-        S = 7.0 + 3.0 * mlen[first] + 1.0
-        return float(((L + 2) * (1.0 + S) + 3.0 * (L + 2) + 4.0 * nm + 8.0 + 12.0).sum())
-    if name in ("k_wfa_score_warp",):
-        g = res.glue
-        return float(g.seqs.data.nbytes + np.diff(g.backbones.offsets.astype(np.int64))[
-            np.repeat(np.arange(len(g.backbones)), np.diff(g.group_seq_off.astype(np.int64)))].sum() + 16.0 * len(g.seqs))
+        first = w.locus_motif_off[:-1][g.group_locus]
+        S = 7.0 + 3.0 * mlen[first] + 1.0          # one motif per locus in this catalog
+        return float(((L + 2) * (1.0 + S) + mlen[first] + 8.0 * nm).sum())
+    if name == "k_wfa_score_warp":
+        per_seq_bb = np.diff(g.backbones.offsets.astype(np.int64))[
+            np.repeat(np.arange(len(g.backbones)), np.diff(g.group_seq_off.astype(np.int64)))]
+        return float(g.seqs.data.nbytes + per_seq_bb.sum() + 16.0 * len(g.seqs) + 4.0 * res.cigars.words.size)
     return None
 
 
@@ -239,7 +240,7 @@ def run_b200(args):
     w = workload.generate(args.loci, args.depth, locus_begin=rank * args.loci, alloc_reads=eng.pinned_array,
                           name="genome-wide-synthetic")
     t_gen = time.perf_counter() - t_gen
-    hp = HotPath(eng, w, want_hits=False, pinned_outputs=True)
+    hp = HotPath(eng, w, want_hits=True, pinned_outputs=True)  # hits: to count the fallback pairs for the roofline
 
     # end-to-end driver: chunks of loci through `host_threads` engines on this GPU
     engines = [eng] + [trgt_b200.Engine(device=local_rank) for _ in range(max(1, args.host_threads) - 1)]
