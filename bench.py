@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk-loci", type=int, default=15625, help="loci per chunk of the end-to-end driver")
-    ap.add_argument("--host-threads", type=int, default=2, help="host threads (one engine each) of the e2e driver")
+    ap.add_argument("--host-threads", type=int, default=4, help="host threads (one engine each) of the e2e driver")
     return ap.parse_args()
 
 
@@ -244,7 +244,9 @@ def run_b200(args):
 
     # end-to-end driver: chunks of loci through `host_threads` engines on this GPU
     engines = [eng] + [trgt_b200.Engine(device=local_rank) for _ in range(max(1, args.host_threads) - 1)]
-    chp = ChunkedHotPath(engines, w, chunk_loci=args.chunk_loci)
+    # host cores are shared by all ranks of the box and all host threads of a rank
+    glue_threads = max(2, host_cores() // max(1, world * len(engines)))
+    chp = ChunkedHotPath(engines, w, chunk_loci=args.chunk_loci, glue_threads=glue_threads)
 
     # ---- warm-up: end-to-end passes (also builds the resident batches) ----
     res = None
@@ -297,12 +299,19 @@ def run_b200(args):
         return 0
 
     barrier()
+    tm0 = chp.timing()
+    t_gather = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         res = chp.run_e2e()
+        tg = time.perf_counter()
         gather_records(res)
+        t_gather += time.perf_counter() - tg
     barrier()
     e2e_s = (time.perf_counter() - t0) / max(1, args.steps)
+    tm1 = chp.timing()
+    e2e_phases = {k: (tm1[k] - tm0[k]) / max(1, args.steps) * 1e3 for k in tm1}  # ms per step, summed over host threads
+    e2e_phases["gather"] = t_gather / max(1, args.steps) * 1e3
     clk = clocks.stop()
     e2e_s = max_over_ranks(e2e_s)
     e2e_value = args.loci * world / e2e_s
@@ -373,7 +382,8 @@ def run_b200(args):
         "dtype": "int32 wavefront offsets + f64 Viterbi", "data": "synthetic",
         "config": workload_config(args, world), "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines)},
+                "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),
+                "glue_threads": glue_threads, "phase_ms_summed_over_host_threads": e2e_phases},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "kernels": kernels,
         "wfa_fallback_pairs": hp.n_wfa(), "workload_gen_s": t_gen,
     }

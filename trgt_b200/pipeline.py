@@ -14,6 +14,7 @@ import numpy as np
 
 from .engine import AnnotationBatch, CigarBatch, Engine, HIT_DTYPE, SPAN_DTYPE
 import threading
+import time
 
 from .workload import GenotypeGlue, GlueContext, Workload, genotype_glue
 
@@ -28,10 +29,13 @@ class HotPathResult:
 
 
 class HotPath:
-    def __init__(self, engine: Engine, w: Workload, want_hits: bool = False, pinned_outputs: bool = True):
+    def __init__(self, engine: Engine, w: Workload, want_hits: bool = False, pinned_outputs: bool = True,
+                 glue_threads: int = 0):
         self.eng = engine
         self.w = w
         self.want_hits = want_hits
+        self.glue_threads = glue_threads  # 0: all cores
+        self.timing = {"flank": 0.0, "glue": 0.0, "align": 0.0, "hmm": 0.0}
         n = w.n_reads
         if pinned_outputs:
             self._spans = engine.pinned_array(max(1, n) * SPAN_DTYPE.itemsize)[:n * SPAN_DTYPE.itemsize].view(SPAN_DTYPE)
@@ -66,12 +70,19 @@ class HotPath:
     def run_e2e(self, copy: bool = False) -> HotPathResult:
         """copy=False: results alias pinned buffers (the engine's, this object's) until the next pass."""
         w, eng = self.w, self.eng
+        t0 = time.perf_counter()
         spans, hits = eng.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring,
                                              w.min_flank_id_frac, want_hits=self.want_hits,
                                              spans_out=self._spans, hits_out=self._hits)
-        glue = genotype_glue(w, spans, ctx=self._glue_ctx)
+        t1 = time.perf_counter()
+        glue = genotype_glue(w, spans, threads=self.glue_threads, ctx=self._glue_ctx)
+        t2 = time.perf_counter()
         cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off, copy=copy)
+        t3 = time.perf_counter()
         ann = eng.hmm_label_packed(w.motifs, w.locus_motif_off, glue.backbones, glue.group_locus, copy=copy)
+        t4 = time.perf_counter()
+        for k, v in (("flank", t1 - t0), ("glue", t2 - t1), ("align", t3 - t2), ("hmm", t4 - t3)):
+            self.timing[k] += v
         return HotPathResult(spans, hits, glue, cigars, ann)
 
     # -- resident batches ---------------------------------------------------------------------
@@ -119,12 +130,20 @@ class ChunkedHotPath:
     runs phases A, glue, B, C per chunk through the blocking C ABI, so one chunk's PCIe transfers
     overlap another chunk's kernels and host glue."""
 
-    def __init__(self, engines, w: Workload, chunk_loci: int = 16384):
+    def __init__(self, engines, w: Workload, chunk_loci: int = 16384, glue_threads: int = 0):
         self.engines = list(engines)
         self.w = w
         self.bounds = [(l0, min(l0 + chunk_loci, w.n_loci)) for l0 in range(0, w.n_loci, chunk_loci)]
-        self.paths = [HotPath(self.engines[i % len(self.engines)], w.slice(l0, l1))
+        self.paths = [HotPath(self.engines[i % len(self.engines)], w.slice(l0, l1), glue_threads=glue_threads)
                       for i, (l0, l1) in enumerate(self.bounds)]
+
+    def timing(self) -> dict:
+        """Seconds spent per phase, summed over chunks and host threads since construction."""
+        out = {"flank": 0.0, "glue": 0.0, "align": 0.0, "hmm": 0.0}
+        for p in self.paths:
+            for k in out:
+                out[k] += p.timing[k]
+        return out
 
     def run_e2e(self):
         n_eng = len(self.engines)
