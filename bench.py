@@ -278,25 +278,17 @@ def run_b200(args):
     value = args.loci * world / (dev_ms * 1e-3)
 
     # ---- `e2e`: host buffers through the C ABI, host<->device copies and host glue inside ----
+    from trgt_b200.shard import RecordGather, record_parts
+    gatherer = RecordGather(dev)
+
     def gather_records(rs):
         if world == 1:
             return 0
-        payload = np.concatenate([x for r in rs for x in (
-            r.annotations.motif_counts.view(np.uint8), r.annotations.spans.reshape(-1).view(np.uint8),
-            r.annotations.purity.view(np.uint8), r.glue.backbones.data, r.glue.backbones.offsets.view(np.uint8))])
-        t = torch.from_numpy(payload).to(dev, non_blocking=False)
-        size = torch.tensor([t.numel()], dtype=torch.int64, device=dev)
-        sizes = [torch.zeros_like(size) for _ in range(world)]
-        dist.all_gather(sizes, size)
-        mx = int(max(int(s.item()) for s in sizes))
-        pad = torch.zeros(mx, dtype=torch.uint8, device=dev)
-        pad[:t.numel()] = t
-        out = [torch.empty(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, out, dst=0)
-        if rank == 0:
-            host = [o[:int(s.item())].cpu() for o, s in zip(out, sizes)]
-            return sum(h.numel() for h in host)
-        return 0
+        got = gatherer(record_parts(rs))
+        return sum(g.size for g in got) if got is not None else 0
+
+    for _ in range(2):   # warm-up: NCCL sets the collectives up lazily
+        gather_records(res)
 
     barrier()
     tm0 = chp.timing()
