@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--depth", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resident-only", action="store_true",
+                    help="profiling aid: skip the end-to-end driver so that every launch is a whole-shard launch")
     ap.add_argument("--chunk-loci", type=int, default=15625, help="loci per chunk of the end-to-end driver")
     ap.add_argument("--host-threads", type=int, default=4, help="host threads (one engine each) of the e2e driver")
     return ap.parse_args()
@@ -250,8 +252,9 @@ def run_b200(args):
 
     # ---- warm-up: end-to-end passes (also builds the resident batches) ----
     res = None
-    for _ in range(max(1, args.warmup)):
-        res = chp.run_e2e()
+    if not args.resident_only:
+        for _ in range(max(1, args.warmup)):
+            res = chp.run_e2e()
     hp.prepare_resident()
     for _ in range(max(1, args.warmup)):
         hp.run_resident()
@@ -278,6 +281,12 @@ def run_b200(args):
     value = args.loci * world / (dev_ms * 1e-3)
 
     # ---- `e2e`: host buffers through the C ABI, host<->device copies and host glue inside ----
+    if args.resident_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": dev_ms, "note": "resident-only profiling run", "e2e": None,
+                              "kernels": {k: {"launches": n, "ms": ms} for k, (n, ms) in stats.items()}}))
+        return
     from trgt_b200.shard import RecordGather, record_parts
     gatherer = RecordGather(dev)
 

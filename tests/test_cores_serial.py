@@ -299,7 +299,7 @@ def test_flank_locate_multilane(emul, oracle, lanes):
 def test_hmm_core_multilane(emul, oracle, lanes):
     emul.emu_hmm_annotate_lanes.restype = C.c_long
     rng = random.Random(300 + lanes)
-    for _ in range(60):
+    for _ in range(150):  # S <= 32 models take the one-state-per-lane variant when lanes == 32
         k = rng.choice([1, 1, 2, 5])
         motifs = [rnd(rng, rng.choice([1, 2, 3, 4, 6, 12]), "ACGTN" if rng.random() < 0.2 else "ACGT") for _ in range(k)]
         allele = noisy_repeat(rng, motifs) or b"A"

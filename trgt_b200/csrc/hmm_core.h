@@ -220,11 +220,19 @@ TRGT_HD int hmm_model_build(const G &g, const uint8_t *motifs, const uint64_t *m
     idx++;                                          \
   } while (0)
 
+template <class G>
+TRGT_HD void hmm_viterbi_small(const G &g, const HmmModel &m, const HmmConsts &c, const double *mm_lp,
+                               const uint8_t *allele, int L, double *sc0, double *sc1, uint8_t *bp);
+
 // Viterbi over '#' + allele + '#'.  sc0/sc1: two columns of S doubles (on-chip).  bp: (L+2)*S bytes.
 template <class G>
 TRGT_HD void hmm_viterbi(const G &g, const HmmModel &m, const HmmConsts &c, const double *mm_lp,
                          const uint8_t *allele, int L, double *sc0, double *sc1, uint8_t *bp) {
   const int S = m.S, nb = m.nb;
+  if (S <= g.size()) {  // one state per lane: the register-resident variant below
+    hmm_viterbi_small(g, m, c, mm_lp, allele, L, sc0, sc1, bp);
+    return;
+  }
   double *prev = sc0, *cur = sc1;
   const double NEG = -INFINITY;
   for (int col = 0; col <= L + 1; col++) {
@@ -344,6 +352,151 @@ TRGT_HD void hmm_viterbi(const G &g, const HmmModel &m, const HmmConsts &c, cons
         bpc[ms] = (uint8_t)arg;
       }
       if (b == 0) {
+        cur[S - 2] = re_sc; bpc[S - 2] = (uint8_t)re_arg;
+        cur[1] = rs_sc;     bpc[1] = (uint8_t)rs_arg;
+      }
+    }
+    g.sync();
+    double *t = prev; prev = cur; cur = t;
+  }
+}
+
+// The same recurrence for models with at most one state per lane (S <= group size; every locus of
+// the genome-wide catalog): each lane decodes its state's role, in-edges and ln terms ONCE, keeps
+// them in registers, and the column loop is just loads, adds and compares.  Candidate order, the
+// strict '>' and the left-to-right sums are those of hmm_viterbi, so results are bit-identical.
+template <class G>
+TRGT_HD void hmm_viterbi_small(const G &g, const HmmModel &m, const HmmConsts &c, const double *mm_lp,
+                               const uint8_t *allele, int L, double *sc0, double *sc1, uint8_t *bp) {
+  const int S = m.S, nb = m.nb;
+  const int st = g.lane();
+  const double NEG = -INFINITY;
+  // ---- per-lane constants: emitting state `st` ----
+  int kind = -1, nsrc = 0, base_sym = 0;  // base_sym: 1..4 match base, 5 = N / uniform, 0 = '#' only
+  int src0 = 0, src1 = 0, src2 = 0, src3 = 0;
+  double lp0 = 0, lp1 = 0, lp2 = 0, lp3 = 0;
+  if (st < S) {
+    const HmmRole r = hmm_role(m, st);
+    kind = r.kind;
+    switch (r.kind) {
+      case HR_END: nsrc = 1; src0 = S - 2; lp0 = c.lp_end; base_sym = 0; break;
+      case HR_MATCH: {
+        const uint8_t mb = m.motif_bytes[m.blk_moff[r.b] + r.i];
+        base_sym = mb == 'N' ? 5 : hmm_symbol(mb);
+        if (r.i == 0) { nsrc = 1; src0 = r.ms; lp0 = c.lp_match; }
+        else {
+          nsrc = r.i >= 2 ? 4 : 3;
+          src0 = st - 1; lp0 = c.lp_match;
+          src1 = r.ms; lp1 = mm_lp[m.blk_mmoff[r.b] + r.i];
+          src2 = r.ms + r.n + r.i; lp2 = c.lp_ins_exit;
+          src3 = r.ms + 2 * r.n + r.i - 1; lp3 = c.lp_half;
+        }
+        break;
+      }
+      case HR_INS: nsrc = 2; src0 = st; lp0 = c.lp_ins_loop; src1 = r.ms + 1 + r.i; lp1 = c.lp_indel_open; base_sym = 5; break;
+      case HR_SKIP: nsrc = 2; src0 = r.ms; lp0 = c.lp_one; src1 = st; lp1 = c.lp_half; base_sym = 5; break;
+      default: break;  // start, silent states
+    }
+  }
+  const bool emitting = kind == HR_START || kind == HR_END || kind == HR_MATCH || kind == HR_INS || kind == HR_SKIP;
+  // ---- per-lane constants: block `st` (lanes < nb also run the silent chain of one block) ----
+  const bool blk = st < nb;
+  int b_ms = 0, b_n = 0, b_me = 0;
+  if (blk) {
+    b_ms = m.blk_ms[st];
+    b_n = st == nb - 1 ? 0 : (int)m.blk_n[st];
+    b_me = b_ms + (st == nb - 1 ? 2 : 3 * b_n);
+  }
+  double *prev = sc0, *cur = sc1;
+  for (int col = 0; col <= L + 1; col++) {
+    const int sym = (col == 0 || col == L + 1)
+                        ? 0 : hmm_symbol(hmm_clean_base(allele[col - 1], (uint32_t)(col - 1)));
+    uint8_t *bpc = bp + (size_t)col * (size_t)S;
+    // (1) emitting states from the previous column
+    if (emitting) {
+      double best = NEG;
+      int arg = TRGT_HMM_NONE;
+      if (kind == HR_START) {
+        if (col == 0) { best = c.em_one; arg = 0; }
+      } else if (col > 0) {
+        double em;
+        if (base_sym == 0) em = sym == 0 ? c.em_one : NEG;
+        else if (sym == 0) em = NEG;
+        else if (base_sym == 5) em = c.em_quarter;
+        else em = base_sym == sym ? c.em_hi : c.em_lo;
+        if (em != NEG) {
+          int idx = 0;
+          TRGT_CAND(prev[src0], lp0);
+          if (nsrc > 1) TRGT_CAND(prev[src1], lp1);
+          if (nsrc > 2) TRGT_CAND(prev[src2], lp2);
+          if (nsrc > 3) TRGT_CAND(prev[src3], lp3);
+        }
+      }
+      cur[st] = best;
+      bpc[st] = (uint8_t)arg;
+    }
+    g.sync();
+    // (2) per block: del chain then me
+    if (blk) {
+      const double em = 0.0;
+      if (st == nb - 1) {
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        TRGT_CAND(cur[b_ms + 1], c.lp_half);
+        cur[b_ms + 2] = best;
+        bpc[b_ms + 2] = (uint8_t)arg;
+      } else {
+        const int m0 = b_ms + 1, i0 = b_ms + 1 + b_n, d0 = b_ms + 1 + 2 * b_n;
+        double dprev = NEG;
+        for (int i = 0; i + 1 < b_n; i++) {
+          double best = NEG;
+          int arg = TRGT_HMM_NONE, idx = 0;
+          TRGT_CAND(cur[m0 + i], c.lp_indel_open);
+          if (i > 0) TRGT_CAND(dprev, c.lp_half);
+          cur[d0 + i] = best;
+          bpc[d0 + i] = (uint8_t)arg;
+          dprev = best;
+        }
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        TRGT_CAND(cur[m0 + b_n - 1], c.lp_match);
+        TRGT_CAND(cur[i0 + b_n - 1], c.lp_ins_exit);
+        if (b_n > 1) TRGT_CAND(dprev, c.lp_one);
+        cur[b_me] = best;
+        bpc[b_me] = (uint8_t)arg;
+      }
+    }
+    g.sync();
+    // (3) re, rs, then every ms
+    if (blk) {
+      const double em = 0.0;
+      double re_sc, rs_sc;
+      int re_arg, rs_arg;
+      {
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        for (int bb = 0; bb < nb; bb++) {
+          const int me = m.blk_ms[bb] + (bb == nb - 1 ? 2 : 3 * (int)m.blk_n[bb]);
+          TRGT_CAND(cur[me], c.lp_half);
+        }
+        re_sc = best; re_arg = arg;
+      }
+      {
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        TRGT_CAND(cur[0], c.lp_one);
+        TRGT_CAND(re_sc, c.lp_one);
+        rs_sc = best; rs_arg = arg;
+      }
+      {
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        TRGT_CAND(rs_sc, c.lp_one);
+        TRGT_CAND(cur[b_me], c.lp_half);
+        cur[b_ms] = best;
+        bpc[b_ms] = (uint8_t)arg;
+      }
+      if (st == 0) {
         cur[S - 2] = re_sc; bpc[S - 2] = (uint8_t)re_arg;
         cur[1] = rs_sc;     bpc[1] = (uint8_t)rs_arg;
       }
