@@ -189,7 +189,7 @@ def kernel_bytes(name: str, w, hp, res) -> float | None:
         if name == "k_flank_band":  # hit records scanned, pending reads re-read once, pieces once per locus, hits rewritten
             return float(40.0 * n_reads + read_len[pend_reads].sum() + 2.0 * P * w.n_loci + 20.0 * pend.sum())
         return None
-    if name == "k_hmm_viterbi":
+    if name == "k_hmm_viterbi_thread":
         L = np.diff(g.backbones.offsets.astype(np.int64)).astype(np.float64)
         nm = np.diff(w.locus_motif_off.astype(np.int64))[g.group_locus]
         mlen = np.diff(w.motifs.offsets.astype(np.int64))

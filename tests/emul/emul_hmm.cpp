@@ -50,7 +50,7 @@ long emu_hmm_annotate_lanes(const uint8_t *motifs, const uint64_t *moff, int nm,
   HmmModel model;
   SerialGroup g;
   int S = 0;
-  if (lanes == 0) {
+  if (lanes <= 0) {
     S = hmm_model_build(g, motifs, moff, nm, jt.off.data(), o_bytes.data(), o_moff.data(), o_mmoff.data(),
                         o_n.data(), o_ms.data(), o_stblk.data(), &model);
   } else {
@@ -72,7 +72,12 @@ long emu_hmm_annotate_lanes(const uint8_t *motifs, const uint64_t *moff, int nm,
   }
   std::vector<double> sc0(S), sc1(S);
   std::vector<uint8_t> bp((size_t)(L + 2) * S, 0xEE);
-  if (lanes == 0) {
+  if (lanes == -1) {  // the one-thread-per-allele variant, with a stride as on the device
+    const int stride = 5;
+    std::vector<double> t0((size_t)S * stride, 0.0), t1((size_t)S * stride, 0.0);
+    const HmmModelScan scan0 = hmm_model_scan(motifs, moff, nm);
+    hmm_viterbi_thread(scan0, c, jt.off.data(), jt.lp.data(), allele, L, t0.data() + 2, t1.data() + 2, stride, bp.data());
+  } else if (lanes == 0) {
     hmm_viterbi(g, model, c, jt.lp.data(), allele, L, sc0.data(), sc1.data(), bp.data());
   } else {
     trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &lg) {

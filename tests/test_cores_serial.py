@@ -391,3 +391,39 @@ def test_e2e_narrow_core(emul, oracle):
         else:
             assert -score > 16 or rc == -200
     assert resolved > 100
+
+
+def test_hmm_core_thread_per_allele(emul, oracle):
+    """hmm_viterbi_thread (one lane does the whole allele, strided score columns, table-free model)
+    must give the oracle's state path, MC, MS and AP."""
+    emul.emu_hmm_annotate_lanes.restype = C.c_long
+    rng = random.Random(41)
+    for _ in range(700):
+        k = rng.choice([1, 1, 1, 2, 3, 5])
+        motifs = [rnd(rng, rng.choice([1, 2, 2, 3, 4, 5, 6, 7, 12]), "ACGTN" if rng.random() < 0.2 else "ACGT")
+                  for _ in range(k)]
+        allele = noisy_repeat(rng, motifs)
+        if rng.random() < 0.1:
+            allele = allele[:3] + b"N" + allele[3:] + b"X"
+        if not allele:
+            continue
+        h = oracle.Hmm([oracle.replace_invalid_bases(m, b"ATCGN") for m in motifs])
+        exp_mc, exp_sp, exp_pur = h.annotate(allele)
+        exp_path = h.label(oracle.replace_invalid_bases(allele, b"ATCG"))
+        data = b"".join(motifs)
+        offs = [0]
+        for m in motifs:
+            offs.append(offs[-1] + len(m))
+        moff = (C.c_uint64 * len(offs))(*offs)
+        mc = (C.c_uint32 * (len(motifs) + 1))()
+        cap = len(allele) + 2
+        spans = (_Span * cap)()
+        pur, plen, S = C.c_double(), C.c_uint64(), C.c_int()
+        pcap = (len(allele) + 2) * 64
+        path = (C.c_uint32 * pcap)()
+        n = emul.emu_hmm_annotate_lanes(data, moff, len(motifs), allele, len(allele), mc, spans, cap, C.byref(pur),
+                                        path, C.c_uint64(pcap), C.byref(plen), C.byref(S), -1)
+        assert n >= 0
+        assert list(path[:plen.value]) == exp_path
+        assert list(mc[:len(motifs)]) == exp_mc
+        assert [(spans[i].m, spans[i].s, spans[i].e) for i in range(n)] == exp_sp and pur.value == exp_pur

@@ -272,4 +272,4 @@ def test_kernels_actually_launched(engine):
     engine.reset_stats()
     engine.label_with_hmm([([b"CAG"], [b"CAGCAGCAG"])])
     stats = engine.kernel_stats()
-    assert stats["k_hmm_viterbi"][0] >= 1 and engine.launches() >= 2
+    assert stats["k_hmm_viterbi_thread"][0] >= 1 and engine.launches() >= 2

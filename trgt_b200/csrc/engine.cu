@@ -309,7 +309,8 @@ int32_t trgt_engine_create(int32_t device, trgt_engine_t **out) {
     if ((err = cudaFuncSetAttribute(k_wfa_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_wfa_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_wfa_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
-        (err = cudaFuncSetAttribute(k_hmm_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) {
+        (err = cudaFuncSetAttribute(k_hmm_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
+        (err = cudaFuncSetAttribute(k_hmm_viterbi_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) {
       g_create_error = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(err);
       trgt_engine_destroy(e);
       return TRGT_ERR_CUDA;
@@ -1210,10 +1211,20 @@ static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
     const uint32_t need = (cnt + wpb - 1) / wpb;
     const uint32_t tgrid = (cnt + 127) / 128;  // one thread per allele for the walks
     const unsigned long long bp_base = b->h_bp_off[a0];
-    {
+    {  // small models: one allele per thread
+      const size_t tsmem = (size_t)2 * HMM_THREAD_S * 128 * sizeof(double);
+      int grid = 0;
+      TRY(persistent_grid(e, k_hmm_viterbi_thread, 128, tsmem, &grid));
+      if ((uint32_t)grid > tgrid) grid = (int)tgrid;
+      LaunchScope ls(e, "k_hmm_viterbi_thread");
+      k_hmm_viterbi_thread<<<grid, 128, tsmem, e->stream>>>(hb, a0, a1, bp_base, (uint8_t *)b->bp.p,
+                                                             (int32_t *)b->status.p);
+      TRY(check_launch(e, "k_hmm_viterbi_thread"));
+    }
+    if (b->S_max > HMM_THREAD_S) {  // larger models: one allele per warp
       LaunchScope ls(e, "k_hmm_viterbi");
       const int grid = (uint32_t)grid_v > need ? (int)need : grid_v;
-      k_hmm_viterbi<<<grid, block, smem, e->stream>>>(hb, a0, a1, bp_base, (uint8_t *)b->bp.p, (int32_t *)b->status.p);
+      k_hmm_viterbi<<<grid, block, smem, e->stream>>>(hb, a0, a1, bp_base, (uint8_t *)b->bp.p, (int32_t *)b->status.p, 1);
       TRY(check_launch(e, "k_hmm_viterbi"));
     }
     {

@@ -506,6 +506,154 @@ TRGT_HD void hmm_viterbi_small(const G &g, const HmmModel &m, const HmmConsts &c
   }
 }
 
+// One lane does a whole allele: for the small models of a genome-wide catalog (S = 14..26) a warp per
+// allele leaves most lanes idle in the silent-state steps; with a thread per allele 32 alleles advance
+// per instruction.  Block geometry comes from HmmModelScan (no tables); score columns are strided
+// arrays (sc[state * stride]) so that neighbouring threads hit different shared-memory banks.
+// Candidate order, strict '>' and left-to-right sums as in hmm_viterbi: bit-identical results.
+TRGT_HD void hmm_viterbi_thread(const HmmModelScan &m, const HmmConsts &c, const uint32_t *mm_off, const double *mm_lp,
+                                const uint8_t *allele, int L, double *prev, double *cur, int stride, uint8_t *bp) {
+  const int S = m.S, nb = m.nb;
+  const double NEG = -INFINITY;
+#define SC(a, st) (a)[(size_t)(st) * (size_t)stride]
+  for (int col = 0; col <= L + 1; col++) {
+    const int sym = (col == 0 || col == L + 1)
+                        ? 0 : hmm_symbol(hmm_clean_base(allele[col - 1], (uint32_t)(col - 1)));
+    uint8_t *bpc = bp + (size_t)col * (size_t)S;
+    // ---- emitting states, from the previous column ----
+    SC(cur, 0) = col == 0 ? c.em_one : NEG;   // start (hmm_model.rs:91-94)
+    bpc[0] = col == 0 ? 0 : TRGT_HMM_NONE;
+    int ms = 2;
+    for (int b = 0; b < nb - 1; b++) {
+      const int n = m.block_n(b);
+      const double *jump = mm_lp + mm_off[n];
+      for (int i = 0; i < n; i++) {
+        {  // match_i
+          const int st = ms + 1 + i;
+          double best = NEG;
+          int arg = TRGT_HMM_NONE, idx = 0;
+          if (col > 0 && sym != 0) {
+            const uint8_t mb = m.motif_byte(b, i);
+            const double em = (mb == 'N') ? c.em_quarter : (hmm_symbol(mb) == sym ? c.em_hi : c.em_lo);
+            if (i == 0) {
+              TRGT_CAND(SC(prev, ms), c.lp_match);
+            } else {
+              TRGT_CAND(SC(prev, st - 1), c.lp_match);
+              TRGT_CAND(SC(prev, ms), jump[i]);
+              TRGT_CAND(SC(prev, ms + n + i), c.lp_ins_exit);
+              if (i >= 2) TRGT_CAND(SC(prev, ms + 2 * n + i - 1), c.lp_half);
+            }
+          }
+          SC(cur, st) = best;
+          bpc[st] = (uint8_t)arg;
+        }
+        {  // ins_i
+          const int st = ms + 1 + n + i;
+          double best = NEG;
+          int arg = TRGT_HMM_NONE, idx = 0;
+          if (col > 0 && sym != 0) {
+            const double em = c.em_quarter;
+            TRGT_CAND(SC(prev, st), c.lp_ins_loop);
+            TRGT_CAND(SC(prev, ms + 1 + i), c.lp_indel_open);
+          }
+          SC(cur, st) = best;
+          bpc[st] = (uint8_t)arg;
+        }
+      }
+      ms += 3 * n + 1;
+    }
+    const int sk = ms;  // skip block: ms_skip, skip, me_skip
+    {
+      double best = NEG;
+      int arg = TRGT_HMM_NONE, idx = 0;
+      if (col > 0 && sym != 0) {
+        const double em = c.em_quarter;
+        TRGT_CAND(SC(prev, sk), c.lp_one);
+        TRGT_CAND(SC(prev, sk + 1), c.lp_half);
+      }
+      SC(cur, sk + 1) = best;
+      bpc[sk + 1] = (uint8_t)arg;
+    }
+    {  // end
+      double best = NEG;
+      int arg = TRGT_HMM_NONE, idx = 0;
+      if (col > 0 && sym == 0) {
+        const double em = c.em_one;
+        TRGT_CAND(SC(prev, S - 2), c.lp_end);
+      }
+      SC(cur, S - 1) = best;
+      bpc[S - 1] = (uint8_t)arg;
+    }
+    // ---- silent states, same column: del chain and me per block, me_skip, re, rs, every ms ----
+    const double em = 0.0;
+    double re_sc = NEG;
+    int re_arg = TRGT_HMM_NONE, re_idx = 0;
+    ms = 2;
+    for (int b = 0; b < nb - 1; b++) {
+      const int n = m.block_n(b);
+      const int m0 = ms + 1, i0 = ms + 1 + n, d0 = ms + 1 + 2 * n, me = ms + 3 * n;
+      double dprev = NEG;
+      for (int i = 0; i + 1 < n; i++) {
+        double best = NEG;
+        int arg = TRGT_HMM_NONE, idx = 0;
+        TRGT_CAND(SC(cur, m0 + i), c.lp_indel_open);
+        if (i > 0) TRGT_CAND(dprev, c.lp_half);
+        SC(cur, d0 + i) = best;
+        bpc[d0 + i] = (uint8_t)arg;
+        dprev = best;
+      }
+      double best = NEG;
+      int arg = TRGT_HMM_NONE, idx = 0;
+      TRGT_CAND(SC(cur, m0 + n - 1), c.lp_match);
+      TRGT_CAND(SC(cur, i0 + n - 1), c.lp_ins_exit);
+      if (n > 1) TRGT_CAND(dprev, c.lp_one);
+      SC(cur, me) = best;
+      bpc[me] = (uint8_t)arg;
+      {  // this me as candidate `b` of re
+        const double sc_ = (best + c.lp_half) + em;
+        if (sc_ > re_sc) { re_sc = sc_; re_arg = re_idx; }
+        re_idx++;
+      }
+      ms += 3 * n + 1;
+    }
+    {  // me_skip, then its turn as the last candidate of re
+      double best = NEG;
+      int arg = TRGT_HMM_NONE, idx = 0;
+      TRGT_CAND(SC(cur, sk + 1), c.lp_half);
+      SC(cur, sk + 2) = best;
+      bpc[sk + 2] = (uint8_t)arg;
+      const double sc_ = (best + c.lp_half) + em;
+      if (sc_ > re_sc) { re_sc = sc_; re_arg = re_idx; }
+    }
+    SC(cur, S - 2) = re_sc;
+    bpc[S - 2] = (uint8_t)re_arg;
+    double rs_sc;
+    {
+      double best = NEG;
+      int arg = TRGT_HMM_NONE, idx = 0;
+      TRGT_CAND(SC(cur, 0), c.lp_one);
+      TRGT_CAND(re_sc, c.lp_one);
+      rs_sc = best;
+      SC(cur, 1) = best;
+      bpc[1] = (uint8_t)arg;
+    }
+    ms = 2;
+    for (int b = 0; b < nb; b++) {
+      const int n = m.block_n(b);
+      const int me = ms + (b == nb - 1 ? 2 : 3 * n);
+      double best = NEG;
+      int arg = TRGT_HMM_NONE, idx = 0;
+      TRGT_CAND(rs_sc, c.lp_one);
+      TRGT_CAND(SC(cur, me), c.lp_half);
+      SC(cur, ms) = best;
+      bpc[ms] = (uint8_t)arg;
+      ms += 3 * n + 1;
+    }
+    double *t = prev; prev = cur; cur = t;
+  }
+#undef SC
+}
+
 // predecessor of `st` through in-edge `e` (inverse of the enumeration order above)
 template <class M>
 TRGT_HD int hmm_pred(const M &m, const HmmRole &r, int st, int e) {

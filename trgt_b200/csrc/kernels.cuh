@@ -713,10 +713,41 @@ __device__ __forceinline__ HmmWarpMem hmm_carve(unsigned char *base, int S_max, 
   return w;
 }
 
-// One warp per allele: model build in shared memory, Viterbi, back-pointers to HBM.
+#define HMM_THREAD_S 32  // models up to this many states run one allele per thread
+
+// One THREAD per allele for small models (every locus of a genome-wide catalog: S = 14..26): 32
+// alleles advance per instruction.  Two score columns of HMM_THREAD_S doubles per thread, strided
+// over the CTA so that threads of a warp hit different banks.  Larger models are left to
+// k_hmm_viterbi.
+__global__ void __launch_bounds__(128)
+k_hmm_viterbi_thread(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, uint8_t *__restrict__ bp,
+                     int32_t *__restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_b[];
+  double *sc = reinterpret_cast<double *>(smem_b);  // [2][HMM_THREAD_S][128]
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t a = a0 + blockIdx.x * blockDim.x + threadIdx.x; a < a1; a += gsz) {
+    const uint32_t l = hb.allele_locus[a];
+    const uint32_t m0 = hb.locus_motif_off[l];
+    const int nm = (int)(hb.locus_motif_off[l + 1] - m0);
+    const uint64_t *moff = hb.motif_off + m0;
+    bool bad = false;
+    for (int b = 0; b < nm; b++) bad = bad || moff[b + 1] <= moff[b];
+    const HmmModelScan model = hmm_model_scan(hb.motifs, moff, nm);
+    if (bad) { status[a] = TRGT_ITEM_INVALID_BASE; continue; }
+    if (model.S > HMM_THREAD_S) continue;  // k_hmm_viterbi's
+    status[a] = 0;
+    const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
+    if (L == 0) continue;
+    hmm_viterbi_thread(model, hb.c, hb.mm_off, hb.mm_lp, hb.alleles + hb.allele_off[a], L, sc + threadIdx.x,
+                       sc + (size_t)HMM_THREAD_S * 128 + threadIdx.x, 128, bp + (hb.bp_off[a] - bp_base));
+  }
+}
+
+// One warp per allele (models larger than HMM_THREAD_S, or all of them when skip_small is 0): model
+// build in shared memory, Viterbi, back-pointers to HBM.
 __global__ void __launch_bounds__(128)
 k_hmm_viterbi(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, uint8_t *__restrict__ bp,
-              int32_t *__restrict__ status) {
+              int32_t *__restrict__ status, int skip_small) {
   extern __shared__ __align__(16) unsigned char smem_b[];
   const WarpGroup g;
   const uint32_t wib = threadIdx.x >> 5;
@@ -728,6 +759,16 @@ k_hmm_viterbi(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base,
     const int nm = (int)(hb.locus_motif_off[l + 1] - m0);
     const uint8_t *allele = hb.alleles + hb.allele_off[a];
     const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
+    if (skip_small) {  // small models were done by k_hmm_viterbi_thread
+      int Sq = 7;
+      bool bad = false;
+      for (int b = 0; b < nm; b++) {
+        const long long n = (long long)(hb.motif_off[m0 + b + 1] - hb.motif_off[m0 + b]);
+        bad = bad || n <= 0;
+        Sq += 3 * (int)n + 1;
+      }
+      if (bad || Sq <= HMM_THREAD_S) continue;
+    }
     HmmModel model;
     const int S = hmm_model_build(g, hb.motifs, hb.motif_off + m0, nm, hb.mm_off, wm.bytes, wm.moff, wm.mmoff,
                                   wm.n, wm.ms, wm.stblk, &model);
