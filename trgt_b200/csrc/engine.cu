@@ -570,6 +570,15 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
   }
   if (e->band_budget > 0) {
     int grid = 0;
+    TRY(persistent_grid(e, k_flank_band_thread, block, 0, &grid));
+    if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
+    LaunchScope ls(e, "k_flank_band_thread");
+    k_flank_band_thread<<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, b->frac,
+                                                       (trgt_flank_hit_t *)b->hits.p);
+    TRY(check_launch(e, "k_flank_band_thread"));
+  }
+  if (e->band_budget > 0) {
+    int grid = 0;
     TRY(persistent_grid(e, k_flank_band, block, 0, &grid));
     if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
     LaunchScope ls(e, "k_flank_band");
