@@ -228,29 +228,3 @@ int emu_e2e_narrow(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x
 }
 
 }  // extern "C"
-
-extern "C" {
-
-// the one-lane tier-1 path of k_flank_band_thread.  out[0]=rc out[1]=via out[2]=matches out[3]=score out[4]=start out[5]=end
-int emu_flank_tier1_serial(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x, int o, int e, double frac,
-                           int ws_ints, int *out) {
-  std::vector<uint8_t> pbuf(P + 16, 0), tbuf(T + 32, 0);
-  memcpy(pbuf.data(), p_in, P);
-  memcpy(tbuf.data(), t_in, T);
-  WfaProb pr;
-  pr.p = pbuf.data(); pr.P = P; pr.t = tbuf.data(); pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
-  pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;
-  wfa_unband(pr);
-  std::vector<uint16_t> islot(TRGT_KIDX_SLOTS);
-  KmerIndex idx{islot.data()};
-  SerialGroup g;
-  kidx_build(g, idx, pr.p, P);
-  std::vector<int> ws(ws_ints + 1, 0x7ead);
-  FlankHit hit = {0, 0, 0, 0, 0};
-  const int cap = x > o + e ? x : o + e;
-  out[0] = flank_locate_tier1_serial(pr, cap, frac, ws.data(), (size_t)ws_ints, &hit, idx);
-  out[1] = hit.via; out[2] = hit.matches; out[3] = hit.score; out[4] = hit.start; out[5] = hit.end;
-  return out[0];
-}
-
-}  // extern "C"

@@ -568,24 +568,26 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
                                                  (Counters *)b->ctr.p);
     TRY(check_launch(e, "k_flank_exact"));
   }
-  if (e->band_budget > 0) {
+  if (e->band_budget > 0) {  // first cost tier at high occupancy, then both tiers on what is left
     int grid = 0;
-    TRY(persistent_grid(e, k_flank_band_thread, block, 0, &grid));
+    TRY(persistent_grid(e, k_flank_band<true>, block, 0, &grid));
     if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
-    LaunchScope ls(e, "k_flank_band_thread");
-    k_flank_band_thread<<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, b->frac,
-                                                       (trgt_flank_hit_t *)b->hits.p);
-    TRY(check_launch(e, "k_flank_band_thread"));
-  }
-  if (e->band_budget > 0) {
-    int grid = 0;
-    TRY(persistent_grid(e, k_flank_band, block, 0, &grid));
+    {
+      LaunchScope ls(e, "k_flank_band_tier1");
+      k_flank_band<true><<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1,
+                                                        e->band_budget, b->frac, (trgt_flank_hit_t *)b->hits.p,
+                                                        (uint32_t *)b->work.p, (Counters *)b->ctr.p);
+      TRY(check_launch(e, "k_flank_band_tier1"));
+    }
+    TRY(persistent_grid(e, k_flank_band<false>, block, 0, &grid));
     if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
-    LaunchScope ls(e, "k_flank_band");
-    k_flank_band<<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
-                                                b->frac, (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p,
-                                                (Counters *)b->ctr.p);
-    TRY(check_launch(e, "k_flank_band"));
+    {
+      LaunchScope ls(e, "k_flank_band_tier2");
+      k_flank_band<false><<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1,
+                                                         e->band_budget, b->frac, (trgt_flank_hit_t *)b->hits.p,
+                                                         (uint32_t *)b->work.p, (Counters *)b->ctr.p);
+      TRY(check_launch(e, "k_flank_band_tier2"));
+    }
   }
   return 0;
 }

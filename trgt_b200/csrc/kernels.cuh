@@ -199,120 +199,35 @@ k_flank_exact(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t 
   }
 }
 
-#define FLT_WS_INTS 151   // per-thread scratch of k_flank_band_thread (odd: no bank conflicts between lanes)
-#define FLT_LIST 512      // pending pairs handled per pass over a locus
+#define FL_LIST 256       // pending reads handled per pass over a locus
+#define FL_WS1_INTS 304   // scratch of the first-tier kernel: cost <= o+e on a band of <= 12 diagonals
 
-struct __align__(16) FlankThreadSmem {
-  uint16_t slot[2][TRGT_KIDX_SLOTS];
-  uint8_t piece[2][FL_PIECE];
-  uint32_t list[FLT_LIST];          // (read - first read of the pass) << 1 | side
-  int ws[32][FLT_WS_INTS];
-};
-
-// Phase A, step 2a.  First cost tier (one mismatch or one 1-bp gap: most HiFi misses) with ONE THREAD
-// per pending pair: a warp takes a locus, builds the piece indexes together, then its 32 lanes each
-// settle a (read, flank) pair on their own -- index seed filter, serial band pass in 600 bytes of
-// shared memory, back-trace -- reading the read straight from global memory.  32 pairs advance per
-// instruction instead of one.  What a lane cannot settle becomes TRGT_VIA_PENDING2 for k_flank_band.
-__global__ void __launch_bounds__(32)
-k_flank_band_thread(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
-                    double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits) {
-  __shared__ FlankThreadSmem sm;
-  const WarpGroup g;
-  const int lane = g.lane();
-  const int tier1 = src.x > src.oe ? src.x : src.oe;
-  for (uint32_t l = l_begin + blockIdx.x; l < l_end; l += gridDim.x) {
-    const uint32_t r0 = locus_read_off[l], r1 = locus_read_off[l + 1];
-    bool have_index = false;
-    bool indexed[2] = {false, false};
-    const uint8_t *ps[2] = {nullptr, nullptr};
-    int PL[2] = {0, 0};
-#pragma unroll 1
-    for (uint32_t rb = r0; rb < r1; rb += FLT_LIST / 2) {
-      const uint32_t re = rb + FLT_LIST / 2 < r1 ? rb + FLT_LIST / 2 : r1;
-      __syncwarp();
-      int n_list = 0;
-      for (uint32_t base = 2 * rb; base < 2 * re; base += 32) {
-        const uint32_t i = base + (uint32_t)lane;
-        const bool pend = i < 2 * re && hits[i].via == TRGT_VIA_PENDING;
-        const unsigned bal = __ballot_sync(0xffffffffu, pend);
-        if (pend) sm.list[n_list + __popc(bal & ((1u << lane) - 1u))] = i - 2 * rb;
-        n_list += __popc(bal);
-      }
-      __syncwarp();
-      if (n_list == 0) continue;
-      if (!have_index) {
-        have_index = true;
-        const uint8_t *pgl = src.lp + src.lp_off[l], *pgr = src.rp + src.rp_off[l];
-        PL[0] = (int)(src.lp_off[l + 1] - src.lp_off[l]);
-        PL[1] = (int)(src.rp_off[l + 1] - src.rp_off[l]);
-        ps[0] = stage_bytes(pgl, PL[0], sm.piece[0], FL_PIECE, lane, 32);
-        ps[1] = stage_bytes(pgr, PL[1], sm.piece[1], FL_PIECE, lane, 32);
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        __syncwarp();
-#pragma unroll 1
-        for (int side = 0; side < 2; side++) {
-          indexed[side] = ps[side] != nullptr && PL[side] >= 16 && PL[side] <= TRGT_KIDX_MAX_P;
-          if (indexed[side]) kidx_build(g, KmerIndex{sm.slot[side]}, ps[side], PL[side]);
-        }
-      }
-#pragma unroll 1
-      for (int base = 0; base < n_list; base += 32) {
-        const int i = base + lane;
-        if (i < n_list) {
-          const uint32_t e = sm.list[i];
-          const uint32_t r = rb + (e >> 1);
-          const int side = (int)(e & 1u);
-          int rc = 1;
-          FlankHit fh;
-          fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
-          if (indexed[side]) {
-            WfaProb pr;
-            pr.x = src.x; pr.oe = src.oe; pr.e = src.e;
-            pr.p = ps[side]; pr.P = PL[side];
-            pr.t = src.reads + src.read_off[r];
-            pr.T = (int)(src.read_off[r + 1] - src.read_off[r]);
-            pr.pbf = 0; pr.pef = 0; pr.tbf = pr.T; pr.tef = pr.T;  // span_locater.rs:17
-            wfa_unband(pr);
-            rc = flank_locate_tier1_serial(pr, tier1, min_flank_id_frac, sm.ws[lane], FLT_WS_INTS, &fh,
-                                           KmerIndex{sm.slot[side]});
-          }
-          trgt_flank_hit_t h;
-          h.via = TRGT_VIA_PENDING2; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
-          if (rc == 0) {
-            h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
-            h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
-          }
-          hits[2 * r + (uint32_t)side] = h;
-        }
-        __syncwarp();
-      }
-    }
-  }
-}
-
-#define FL_LIST 256  // pending reads handled per pass over a locus
-
+// TIER1 = true : first cost tier only (one mismatch or one 1-bp gap: ~89 % of HiFi misses), small
+//                scratch, single read buffer -> twice the resident warps; failures become PENDING2.
+// TIER1 = false: both tiers with the full scratch, on whatever is still pending.
+template <bool TIER1>
 struct __align__(16) FlankBandSmem {
   uint16_t slot[2][TRGT_KIDX_SLOTS];
   uint8_t piece[2][FL_PIECE];
-  uint8_t txt[2][FL_TXT];
+  uint8_t txt[TIER1 ? 1 : 2][FL_TXT];
   uint16_t list[FL_LIST];  // (read - first read of the pass) << 4 | first-tier-done sides << 2 | pending sides
   int cand[TRGT_CAND_CAP + 4];
-  int ws[FL_WS_INTS];
+  int ws[TIER1 ? FL_WS1_INTS : FL_WS_INTS];
 };
 
-// Phase A, step 2.  Again a warp per locus, but only the (read, flank) pairs left TRGT_VIA_PENDING:
-// the WFA fallback (span_locater.rs:14-25) through the index seed filter + narrow-band wavefront +
-// back-trace of wfa_core.h, from the staged copy of the read (next pending read in flight).  Pairs
-// this cannot settle (pieces that cannot be indexed, no seed, cost above the budget, reads too long
-// to stage) are appended to `work` as 2*read+side for the full-width kernels below.
-__global__ void __launch_bounds__(32)
+// Phase A, step 2.  Again a warp per locus, but only the (read, flank) pairs still pending: the WFA
+// fallback (span_locater.rs:14-25) through the index seed filter + narrow-band wavefront +
+// back-trace of wfa_core.h, from the staged copy of the read.  Pairs this cannot settle (pieces that
+// cannot be indexed, no seed, cost above the budget, reads too long to stage) are appended to `work`
+// as 2*read+side for the kernels below.
+template <bool TIER1>
+__global__ void __launch_bounds__(32, TIER1 ? 28 : 16)
 k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
              int band_budget, double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits,
              uint32_t *__restrict__ work, Counters *ctr) {
-  __shared__ FlankBandSmem sm;
+  __shared__ FlankBandSmem<TIER1> sm;
+  constexpr int NBUF = TIER1 ? 1 : 2;
+  constexpr int WS = TIER1 ? FL_WS1_INTS : FL_WS_INTS;
   const WarpGroup g;
   const int lane = g.lane();
   for (uint32_t l = l_begin + blockIdx.x; l < l_end; l += gridDim.x) {
@@ -332,8 +247,13 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
         unsigned m = 0;
         if (r < re) {
           const int v0 = hits[2 * r].via, v1 = hits[2 * r + 1].via;
-          m = ((v0 == TRGT_VIA_PENDING || v0 == TRGT_VIA_PENDING2) ? 1u : 0u) | ((v1 == TRGT_VIA_PENDING || v1 == TRGT_VIA_PENDING2) ? 2u : 0u) |
-              (v0 == TRGT_VIA_PENDING2 ? 4u : 0u) | (v1 == TRGT_VIA_PENDING2 ? 8u : 0u);
+          if (TIER1) {
+            m = (v0 == TRGT_VIA_PENDING ? 1u : 0u) | (v1 == TRGT_VIA_PENDING ? 2u : 0u);
+          } else {
+            m = ((v0 == TRGT_VIA_PENDING || v0 == TRGT_VIA_PENDING2) ? 1u : 0u) |
+                ((v1 == TRGT_VIA_PENDING || v1 == TRGT_VIA_PENDING2) ? 2u : 0u) |
+                (v0 == TRGT_VIA_PENDING2 ? 4u : 0u) | (v1 == TRGT_VIA_PENDING2 ? 8u : 0u);
+          }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
         if (m) sm.list[n_list + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(((r - rb) << 4) | m);
@@ -368,10 +288,10 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
         uint32_t r_next = 0;
         int T_next = 0;
         const uint8_t *t_next = nullptr;
-        if (i + 1 < n_list) {
+        if (NBUF == 2 && i + 1 < n_list) {  // next pending read in flight while this one is worked on
           r_next = rb + (uint32_t)(sm.list[i + 1] >> 4);
           T_next = (int)(src.read_off[r_next + 1] - src.read_off[r_next]);
-          t_next = stage_bytes(src.reads + src.read_off[r_next], T_next, sm.txt[(i + 1) & 1], FL_TXT, lane, 32);
+          t_next = stage_bytes(src.reads + src.read_off[r_next], T_next, sm.txt[(i + 1) & (NBUF - 1)], FL_TXT, lane, 32);
           asm volatile("cp.async.commit_group;\n" ::: "memory");
           asm volatile("cp.async.wait_group 1;\n" ::: "memory");
         } else {
@@ -391,24 +311,34 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
             pr.t = t_s; pr.T = T;
             pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;  // span_locater.rs:17
             wfa_unband(pr);
-            deferred = flank_locate_banded_lean(g, pr, band_budget, min_flank_id_frac, sm.ws, FL_WS_INTS, &fh,
-                                                KmerIndex{sm.slot[side]}, sm.cand, (int)((mask >> (2 + side)) & 1u));
+            deferred = flank_locate_banded_lean(g, pr, band_budget, min_flank_id_frac, sm.ws, WS, &fh,
+                                                KmerIndex{sm.slot[side]}, sm.cand,
+                                                TIER1 ? 0 : (int)((mask >> (2 + side)) & 1u), TIER1 ? 0 : 1);
           }
           if (lane == 0) {
             trgt_flank_hit_t h;
             h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
-            if (deferred) {
-              const unsigned int slot = atomicAdd(&ctr->n_work, 1u);
-              work[slot] = 2 * r + (uint32_t)side;
-            } else {
+            if (!deferred) {
               h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
               h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
+            } else if (TIER1) {
+              h.via = TRGT_VIA_PENDING2;
+            } else {
+              const unsigned int slot = atomicAdd(&ctr->n_work, 1u);
+              work[slot] = 2 * r + (uint32_t)side;
             }
             hits[2 * r + side] = h;
           }
           __syncwarp();
         }
-        r = r_next; T = T_next; t_s = t_next;
+        if (NBUF == 2) {
+          r = r_next; T = T_next; t_s = t_next;
+        } else if (i + 1 < n_list) {  // single buffer: fetch the next pending read now
+          r = rb + (uint32_t)(sm.list[i + 1] >> 4);
+          T = (int)(src.read_off[r + 1] - src.read_off[r]);
+          t_s = stage_bytes(src.reads + src.read_off[r], T, sm.txt[0], FL_TXT, lane, 32);
+          asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
       }
     }
   }

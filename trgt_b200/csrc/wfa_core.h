@@ -987,97 +987,6 @@ TRGT_HD int flank_locate_banded(const G &g, const WfaProb &pr, int S, double min
   return 1;
 }
 
-// One lane, whole band: the narrow-band pass for a single thread (k_flank_band_thread runs 32 pairs
-// per warp this way).  Rows are allocated only for live scores -- with (2,5,1) every odd score is
-// empty -- so a cost-6 history of a 9-diagonal band is 150 ints.  Same history layout as the other
-// forward passes; extension is the plain 8-bytes-per-step loop.
-TRGT_HD WfaEnd wfa_forward_band_hist_serial(const WfaProb &pr, int s_cap, int *ws, size_t cap_ints) {
-  WfaEnd out;
-  out.status = TRGT_WFA_OK; out.s = 0; out.k = 0; out.off = 0;
-  const int W = pr.bhi - pr.blo + 1;
-  size_t top = (size_t)TRGT_WFA_META * ((size_t)s_cap + 1);
-  if (top > cap_ints || s_cap >= 64) { out.status = TRGT_WFA_OOM; return out; }
-  unsigned long long present = 0;
-  for (int s = 0; s <= s_cap; s++) {
-    const int sx = s - pr.x, so = s - pr.oe, se = s - pr.e;
-    const bool px = sx >= 0 && ((present >> sx) & 1ull), po = so >= 0 && ((present >> so) & 1ull);
-    const bool pe = se >= 1 && ((present >> se) & 1ull);
-    const bool live = s == 0 || px || po || pe;
-    int *meta = ws + (size_t)TRGT_WFA_META * s;
-    meta[0] = meta[2] = live ? pr.blo : 1;
-    meta[1] = meta[3] = live ? pr.bhi : 0;
-    meta[4] = (int)(unsigned)(top & 0xffffffffu);
-    meta[5] = 0;
-    if (!live) continue;
-    const size_t need = (size_t)W * (s == 0 ? 1 : 3);
-    if (top + need > cap_ints) { out.status = TRGT_WFA_OOM; return out; }
-    int *row = ws + top;
-    const int *mo = po ? ws + (unsigned)ws[TRGT_WFA_META * so + 4] : nullptr;
-    const int *me = pe ? ws + (unsigned)ws[TRGT_WFA_META * se + 4] : nullptr;
-    const int *mxs = px ? ws + (unsigned)ws[TRGT_WFA_META * sx + 4] : nullptr;
-    int endk = INT_MAX;
-    for (int idx = 0; idx < W; idx++) {
-      const int k = pr.blo + idx;
-      int mx;
-      if (s == 0) {
-        mx = (k >= -pr.pbf && k <= pr.tbf) ? (k >= 0 ? k : 0) : TRGT_WFA_NULL;
-      } else {
-        const int o_l = (mo && idx > 0) ? mo[idx - 1] : TRGT_WFA_NULL;
-        const int o_r = (mo && idx + 1 < W) ? mo[idx + 1] : TRGT_WFA_NULL;
-        const int i_l = (me && idx > 0) ? me[W + idx - 1] : TRGT_WFA_NULL;
-        const int d_r = (me && idx + 1 < W) ? me[2 * W + idx + 1] : TRGT_WFA_NULL;
-        const int i1 = wfa_imax(o_l, i_l) + 1;
-        const int d1 = wfa_imax(o_r, d_r);
-        const int mm = (mxs ? mxs[idx] : TRGT_WFA_NULL) + 1;
-        mx = wfa_imax(mm, wfa_imax(i1, d1));
-        row[W + idx] = i1;
-        row[2 * W + idx] = d1;
-      }
-      const int v0 = mx - k;
-      if (mx < 0 || mx > pr.T || v0 > pr.P || v0 < 0) {
-        mx = TRGT_WFA_NULL;
-      } else {
-        const int n = wfa_imin(pr.P - v0, pr.T - mx);
-        if (n > 0 && pr.p[v0] == pr.t[mx]) mx += wfa_match_len(pr.p + v0, pr.t + mx, n);
-        const int v = mx - k;
-        if (endk == INT_MAX && ((mx >= pr.T && pr.P - v <= pr.pef) || (v >= pr.P && pr.T - mx <= pr.tef))) endk = k;
-      }
-      row[idx] = mx;
-    }
-    present |= 1ull << s;
-    top += need;
-    if (endk != INT_MAX) {
-      out.s = s; out.k = endk; out.off = row[endk - pr.blo];
-      return out;
-    }
-  }
-  out.status = TRGT_WFA_MAX_STEPS;
-  return out;
-}
-
-// First cost tier of the flank fallback for ONE lane: index seed filter (single-candidate probes
-// only), serial band pass, back-trace.  0 = settled, 1 = leave it to the cooperative kernels.
-TRGT_HD int flank_locate_tier1_serial(const WfaProb &pr, int cap, double min_flank_id_frac, int *ws, size_t ws_ints,
-                                      FlankHit *hit, const KmerIndex &idx) {
-  const SerialGroup g;
-  int klo, khi;
-  if (flank_seed_band_indexed(g, idx, pr, cap, nullptr, &klo, &khi) != 1) return 1;
-  WfaProb bp = pr;
-  bp.blo = klo; bp.bhi = khi;
-  const WfaEnd end = wfa_forward_band_hist_serial(bp, cap, ws, ws_ints);
-  if (end.status != TRGT_WFA_OK) return 1;
-  WfaFlankSink sink(pr.T);
-  wfa_backtrace(pr, end.s, end.k, end.off, ws, sink);
-  hit->matches = sink.matches;
-  hit->score = -end.s;
-  if ((double)sink.matches >= (double)pr.P * min_flank_id_frac) {  // span_locater.rs:19-25, :46
-    hit->via = 2; hit->start = sink.ystart(); hit->end = sink.yend();
-  } else {
-    hit->via = 3; hit->start = 0; hit->end = 0;
-  }
-  return 0;
-}
-
 // Lean variant for k_flank_band: index-only seed filter and the narrow-band forward pass only; any
 // pair that would need the linear seed scan, a band wider than one lane per diagonal, or more
 // scratch is handed to the full-width path instead (returns 1).  Keeps the kernel's code small
@@ -1085,10 +994,10 @@ TRGT_HD int flank_locate_tier1_serial(const WfaProb &pr, int cap, double min_fla
 template <class G>
 TRGT_HD int flank_locate_banded_lean(const G &g, const WfaProb &pr, int S, double min_flank_id_frac, int *ws,
                                      size_t ws_ints, FlankHit *hit, const KmerIndex &idx, int *cand,
-                                     int first_tier = 0) {
+                                     int first_tier = 0, int last_tier = 1) {
   const int tier1 = wfa_imin(S, wfa_imax(pr.x, pr.oe));
 #pragma unroll 1
-  for (int tier = first_tier; tier < 2; tier++) {
+  for (int tier = first_tier; tier <= last_tier; tier++) {
     const int cap = tier == 0 ? tier1 : S;
     if (tier == 1 && S <= tier1) break;
     int klo, khi;
