@@ -182,11 +182,11 @@ def kernel_bytes(name: str, w, hp, res) -> float | None:
     g = res.glue
     if name == "k_flank_exact":   # every read base once, both pieces once per locus, one hit per (read, flank)
         return read_bytes + 2.0 * P * w.n_loci + 2 * 20.0 * n_reads + 8.0 * n_reads
-    if name in ("k_flank_band_tier1", "k_flank_band_tier2", "k_flank_band_wide") and res.hits is not None:
+    if name in ("k_flank_band", "k_flank_band2", "k_flank_band_wide") and res.hits is not None:
         via = res.hits["via"].reshape(-1, 2)
         pend = (via >= 2)
         pend_reads = pend.any(axis=1)
-        if name == "k_flank_band_tier1":  # hit records scanned, pending reads re-read once, pieces once per locus, hits rewritten
+        if name == "k_flank_band":  # hit records scanned, pending reads re-read once, pieces once per locus, hits rewritten
             return float(40.0 * n_reads + read_len[pend_reads].sum() + 2.0 * P * w.n_loci + 20.0 * pend.sum())
         return None
     if name == "k_hmm_viterbi_thread":

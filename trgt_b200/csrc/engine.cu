@@ -396,7 +396,7 @@ struct trgt_flank_batch {
   trgt_scoring_t scoring{2, 5, 1};
   double frac = 0.7;
   DevBuf reads, read_off, lp, lp_off, rp, rp_off, locus_read_off, read_locus;
-  DevBuf hits, spans, work, ends, ctr, gring, gws;
+  DevBuf hits, spans, work, work2, ends, ctr, gring, gws;
   uint32_t last_n_work = 0;
 };
 
@@ -482,7 +482,7 @@ void trgt_flank_free(trgt_engine_t *e, trgt_flank_batch_t *b) {
     if (e->one_flank == b) e->one_flank = nullptr;
   }
   DevBuf *all[] = {&b->reads, &b->read_off, &b->lp, &b->lp_off, &b->rp, &b->rp_off, &b->locus_read_off,
-                   &b->read_locus, &b->hits, &b->spans, &b->work, &b->ends, &b->ctr, &b->gring, &b->gws};
+                   &b->read_locus, &b->hits, &b->spans, &b->work, &b->work2, &b->ends, &b->ctr, &b->gring, &b->gws};
   for (auto *d : all) dev_free(*d);
   delete b;
 }
@@ -527,6 +527,7 @@ static int flank_upload_into(trgt_engine_t *e, trgt_flank_batch *b, const trgt_s
   TRY(dev_reserve(e, b->hits, ((size_t)b->n_reads * 2 + 1) * sizeof(trgt_flank_hit_t)));
   TRY(dev_reserve(e, b->spans, ((size_t)b->n_reads + 1) * sizeof(trgt_span_t)));
   TRY(dev_reserve(e, b->work, ((size_t)b->n_reads * 2 + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->work2, ((size_t)b->n_reads * 2 + 1) * sizeof(uint32_t)));
   TRY(dev_reserve(e, b->ends, ((size_t)b->n_reads * 2 + 1) * sizeof(WfaEnd)));
   TRY(dev_reserve(e, b->ctr, sizeof(Counters)));
   if (n_loci) {
@@ -568,26 +569,15 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
                                                  (Counters *)b->ctr.p);
     TRY(check_launch(e, "k_flank_exact"));
   }
-  if (e->band_budget > 0) {  // first cost tier at high occupancy, then both tiers on what is left
+  if (e->band_budget > 0) {  // first cost tier of the fallback, at high occupancy
     int grid = 0;
-    TRY(persistent_grid(e, k_flank_band<true>, block, 0, &grid));
+    TRY(persistent_grid(e, k_flank_band, block, 0, &grid));
     if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
-    {
-      LaunchScope ls(e, "k_flank_band_tier1");
-      k_flank_band<true><<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1,
-                                                        e->band_budget, b->frac, (trgt_flank_hit_t *)b->hits.p,
-                                                        (uint32_t *)b->work.p, (Counters *)b->ctr.p);
-      TRY(check_launch(e, "k_flank_band_tier1"));
-    }
-    TRY(persistent_grid(e, k_flank_band<false>, block, 0, &grid));
-    if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
-    {
-      LaunchScope ls(e, "k_flank_band_tier2");
-      k_flank_band<false><<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1,
-                                                         e->band_budget, b->frac, (trgt_flank_hit_t *)b->hits.p,
-                                                         (uint32_t *)b->work.p, (Counters *)b->ctr.p);
-      TRY(check_launch(e, "k_flank_band_tier2"));
-    }
+    LaunchScope ls(e, "k_flank_band");
+    k_flank_band<<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
+                                                b->frac, (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work2.p,
+                                                (Counters *)b->ctr.p);
+    TRY(check_launch(e, "k_flank_band"));
   }
   return 0;
 }
@@ -595,6 +585,14 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
 // pairs the on-chip path deferred: full-width score pass + cone trace; then the combine rule
 static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src) {
   Counters *ctr = (Counters *)b->ctr.p;
+  if (e->band_budget > 0) {  // second cost tier for what the first handed on, one warp per pair
+    int grid = 0;
+    TRY(persistent_grid(e, k_flank_band2, 32, 0, &grid));
+    LaunchScope ls(e, "k_flank_band2");
+    k_flank_band2<<<grid, 32, 0, e->stream>>>(src, (const uint32_t *)b->work2.p, &ctr->n_tier2, e->band_budget, b->frac,
+                                              (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p, ctr);
+    TRY(check_launch(e, "k_flank_band2"));
+  }
   if (e->band_budget > 0) {
     int grid = 0;
     TRY(persistent_grid(e, k_flank_band_wide, 32, 0, &grid));

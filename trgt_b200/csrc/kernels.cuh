@@ -28,7 +28,9 @@ struct Counters {
   unsigned long long words_bound;       // upper bound on CIGAR words pass 2 will emit
   unsigned long long pool_used;         // CIGAR words actually emitted by pass 2
   unsigned int n_failed;                // items that ended with a non-OK status
-  unsigned int n_banded;                // flank: pairs settled by the banded on-chip path
+  unsigned int n_banded;                // flank: pairs settled by k_flank_band_wide
+  unsigned int n_tier2;                 // flank: pairs the first cost tier handed to k_flank_band2
+  unsigned int pad2;
 };
 
 enum { WFA_MODE_FLANK = 0, WFA_MODE_E2E = 1 };
@@ -202,32 +204,25 @@ k_flank_exact(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t 
 #define FL_LIST 256       // pending reads handled per pass over a locus
 #define FL_WS1_INTS 304   // scratch of the first-tier kernel: cost <= o+e on a band of <= 12 diagonals
 
-// TIER1 = true : first cost tier only (one mismatch or one 1-bp gap: ~89 % of HiFi misses), small
-//                scratch, single read buffer -> twice the resident warps; failures become PENDING2.
-// TIER1 = false: both tiers with the full scratch, on whatever is still pending.
-template <bool TIER1>
 struct __align__(16) FlankBandSmem {
   uint16_t slot[2][TRGT_KIDX_SLOTS];
   uint8_t piece[2][FL_PIECE];
-  uint8_t txt[TIER1 ? 1 : 2][FL_TXT];
-  uint16_t list[FL_LIST];  // (read - first read of the pass) << 4 | first-tier-done sides << 2 | pending sides
+  uint8_t txt[FL_TXT];
+  uint16_t list[FL_LIST];  // (read - first read of the pass) << 2 | pending sides
   int cand[TRGT_CAND_CAP + 4];
-  int ws[TIER1 ? FL_WS1_INTS : FL_WS_INTS];
+  int ws[FL_WS1_INTS];
 };
 
-// Phase A, step 2.  Again a warp per locus, but only the (read, flank) pairs still pending: the WFA
-// fallback (span_locater.rs:14-25) through the index seed filter + narrow-band wavefront +
-// back-trace of wfa_core.h, from the staged copy of the read.  Pairs this cannot settle (pieces that
-// cannot be indexed, no seed, cost above the budget, reads too long to stage) are appended to `work`
-// as 2*read+side for the kernels below.
-template <bool TIER1>
-__global__ void __launch_bounds__(32, TIER1 ? 28 : 16)
+// Phase A, step 2.  Again a warp per locus, but only the (read, flank) pairs left pending, and only
+// the first cost tier of the WFA fallback (span_locater.rs:14-25): one mismatch or one 1-bp gap,
+// ~89 % of HiFi misses.  Index seed filter + narrow-band wavefront + back-trace of wfa_core.h from
+// the staged copy of the read, in 6.5 KB of shared memory per warp (28 resident warps per SM).
+// What it cannot settle goes to `work2` (2*read+side) for k_flank_band2.
+__global__ void __launch_bounds__(32, 28)
 k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
              int band_budget, double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits,
-             uint32_t *__restrict__ work, Counters *ctr) {
-  __shared__ FlankBandSmem<TIER1> sm;
-  constexpr int NBUF = TIER1 ? 1 : 2;
-  constexpr int WS = TIER1 ? FL_WS1_INTS : FL_WS_INTS;
+             uint32_t *__restrict__ work2, Counters *ctr) {
+  __shared__ FlankBandSmem sm;
   const WarpGroup g;
   const int lane = g.lane();
   for (uint32_t l = l_begin + blockIdx.x; l < l_end; l += gridDim.x) {
@@ -239,24 +234,14 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
 #pragma unroll 1
     for (uint32_t rb = r0; rb < r1; rb += FL_LIST) {
       const uint32_t re = rb + FL_LIST < r1 ? rb + FL_LIST : r1;
-      // pending reads of this pass, in read order
       __syncwarp();
       int n_list = 0;
-      for (uint32_t base = rb; base < re; base += 32) {
+      for (uint32_t base = rb; base < re; base += 32) {  // pending reads of this pass, in read order
         const uint32_t r = base + (uint32_t)lane;
         unsigned m = 0;
-        if (r < re) {
-          const int v0 = hits[2 * r].via, v1 = hits[2 * r + 1].via;
-          if (TIER1) {
-            m = (v0 == TRGT_VIA_PENDING ? 1u : 0u) | (v1 == TRGT_VIA_PENDING ? 2u : 0u);
-          } else {
-            m = ((v0 == TRGT_VIA_PENDING || v0 == TRGT_VIA_PENDING2) ? 1u : 0u) |
-                ((v1 == TRGT_VIA_PENDING || v1 == TRGT_VIA_PENDING2) ? 2u : 0u) |
-                (v0 == TRGT_VIA_PENDING2 ? 4u : 0u) | (v1 == TRGT_VIA_PENDING2 ? 8u : 0u);
-          }
-        }
+        if (r < re) m = (hits[2 * r].via == TRGT_VIA_PENDING ? 1u : 0u) | (hits[2 * r + 1].via == TRGT_VIA_PENDING ? 2u : 0u);
         const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
-        if (m) sm.list[n_list + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(((r - rb) << 4) | m);
+        if (m) sm.list[n_list + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(((r - rb) << 2) | m);
         n_list += __popc(bal);
       }
       __syncwarp();
@@ -277,26 +262,14 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
           if (indexed[side]) kidx_build(g, KmerIndex{sm.slot[side]}, ps[side], PL[side]);
         }
       }
-      // first listed read in flight
-      uint32_t r = rb + (uint32_t)(sm.list[0] >> 4);
-      int T = (int)(src.read_off[r + 1] - src.read_off[r]);
-      const uint8_t *t_s = stage_bytes(src.reads + src.read_off[r], T, sm.txt[0], FL_TXT, lane, 32);
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
 #pragma unroll 1
       for (int i = 0; i < n_list; i++) {
-        const unsigned mask = sm.list[i] & 15u;
-        uint32_t r_next = 0;
-        int T_next = 0;
-        const uint8_t *t_next = nullptr;
-        if (NBUF == 2 && i + 1 < n_list) {  // next pending read in flight while this one is worked on
-          r_next = rb + (uint32_t)(sm.list[i + 1] >> 4);
-          T_next = (int)(src.read_off[r_next + 1] - src.read_off[r_next]);
-          t_next = stage_bytes(src.reads + src.read_off[r_next], T_next, sm.txt[(i + 1) & (NBUF - 1)], FL_TXT, lane, 32);
-          asm volatile("cp.async.commit_group;\n" ::: "memory");
-          asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-        } else {
-          asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        }
+        const unsigned mask = sm.list[i] & 3u;
+        const uint32_t r = rb + (uint32_t)(sm.list[i] >> 2);
+        const int T = (int)(src.read_off[r + 1] - src.read_off[r]);
+        const uint8_t *t_s = stage_bytes(src.reads + src.read_off[r], T, sm.txt, FL_TXT, lane, 32);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncwarp();
 #pragma unroll 1
         for (int side = 0; side < 2; side++) {
@@ -311,9 +284,8 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
             pr.t = t_s; pr.T = T;
             pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;  // span_locater.rs:17
             wfa_unband(pr);
-            deferred = flank_locate_banded_lean(g, pr, band_budget, min_flank_id_frac, sm.ws, WS, &fh,
-                                                KmerIndex{sm.slot[side]}, sm.cand,
-                                                TIER1 ? 0 : (int)((mask >> (2 + side)) & 1u), TIER1 ? 0 : 1);
+            deferred = flank_locate_banded_lean(g, pr, band_budget, min_flank_id_frac, sm.ws, FL_WS1_INTS, &fh,
+                                                KmerIndex{sm.slot[side]}, sm.cand, 0, 0);
           }
           if (lane == 0) {
             trgt_flank_hit_t h;
@@ -321,26 +293,70 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
             if (!deferred) {
               h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
               h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
-            } else if (TIER1) {
-              h.via = TRGT_VIA_PENDING2;
             } else {
-              const unsigned int slot = atomicAdd(&ctr->n_work, 1u);
-              work[slot] = 2 * r + (uint32_t)side;
+              const unsigned int slot = atomicAdd(&ctr->n_tier2, 1u);
+              work2[slot] = 2 * r + (uint32_t)side;
             }
             hits[2 * r + side] = h;
           }
           __syncwarp();
         }
-        if (NBUF == 2) {
-          r = r_next; T = T_next; t_s = t_next;
-        } else if (i + 1 < n_list) {  // single buffer: fetch the next pending read now
-          r = rb + (uint32_t)(sm.list[i + 1] >> 4);
-          T = (int)(src.read_off[r + 1] - src.read_off[r]);
-          t_s = stage_bytes(src.reads + src.read_off[r], T, sm.txt[0], FL_TXT, lane, 32);
-          asm volatile("cp.async.commit_group;\n" ::: "memory");
-        }
+        __syncwarp();
       }
     }
+  }
+}
+
+struct __align__(16) FlankBand2Smem {
+  uint16_t slot[TRGT_KIDX_SLOTS];
+  uint8_t piece[FL_PIECE];
+  uint8_t txt[FL_TXT];
+  int cand[TRGT_CAND_CAP + 4];
+  int ws[FL_WS_INTS];
+};
+
+// Phase A, step 2b.  The pairs the first tier handed on (~11 %): one warp per pair, second cost tier
+// (budget) with the larger scratch; the piece is staged and indexed per pair.  Failures are
+// appended to `work` for k_flank_band_wide and the full-width kernels.
+__global__ void __launch_bounds__(32)
+k_flank_band2(WfaSrc src, const uint32_t *__restrict__ work2, const unsigned int *n_work2_ptr, int band_budget,
+              double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work,
+              Counters *ctr) {
+  __shared__ FlankBand2Smem sm;
+  const WarpGroup g;
+  const int lane = g.lane();
+  const uint32_t n = *n_work2_ptr;
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint32_t id = work2[i];
+    const WfaProb gp = wfa_prob_of(src, id);
+    __syncwarp();
+    const uint8_t *p_s = stage_bytes(gp.p, gp.P, sm.piece, FL_PIECE, lane, 32);
+    const uint8_t *t_s = stage_bytes(gp.t, gp.T, sm.txt, FL_TXT, lane, 32);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
+    int deferred = 1;
+    FlankHit fh;
+    fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
+    if (p_s != nullptr && t_s != nullptr && gp.P >= 16 && gp.P <= TRGT_KIDX_MAX_P) {
+      const KmerIndex idx{sm.slot};
+      kidx_build(g, idx, p_s, gp.P);
+      WfaProb pr = gp;
+      pr.p = p_s; pr.t = t_s;
+      deferred = flank_locate_banded_lean(g, pr, band_budget, min_flank_id_frac, sm.ws, FL_WS_INTS, &fh, idx, sm.cand, 1, 1);
+    }
+    if (lane == 0) {
+      if (!deferred) {
+        trgt_flank_hit_t h;
+        h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
+        h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
+        hits[id] = h;
+      } else {
+        const unsigned int slot = atomicAdd(&ctr->n_work, 1u);
+        work[slot] = id;
+      }
+    }
+    __syncwarp();
   }
 }
 
