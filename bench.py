@@ -386,7 +386,8 @@ def run_b200(args):
                 "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),
                 "glue_threads": glue_threads, "phase_ms_summed_over_host_threads": e2e_phases},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "kernels": kernels,
-        "wfa_fallback_pairs": hp.n_wfa(), "workload_gen_s": t_gen,
+        "wfa_fallback_pairs": hp.n_wfa(), "flank_fallback_counts": dict(zip(("second_tier", "wide_band", "full_width"), hp.fallback_counts())),
+        "workload_gen_s": t_gen,
     }
     print(json.dumps(out))
     hp.free_resident()

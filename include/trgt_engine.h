@@ -195,6 +195,9 @@ void trgt_flank_free(trgt_engine_t *eng, trgt_flank_batch_t *batch);
 int32_t trgt_flank_device_views(trgt_flank_batch_t *batch, const void **d_reads, const void **d_read_off,
                                 const void **d_spans, const void **d_hits, uint32_t *n_reads,
                                 uint32_t *n_wfa);
+/* how the last run settled the pairs that missed the exact search: out[0] = handed to the second cost
+ * tier, out[1] = handed to the wide-band kernel, out[2] = needed the full-width kernels */
+int32_t trgt_flank_fallback_counts(trgt_flank_batch_t *batch, uint32_t out[3]);
 
 typedef struct trgt_align_batch trgt_align_batch_t;
 int32_t trgt_align_upload(trgt_engine_t *eng, const trgt_seqs_t *backbones,

@@ -397,7 +397,7 @@ struct trgt_flank_batch {
   double frac = 0.7;
   DevBuf reads, read_off, lp, lp_off, rp, rp_off, locus_read_off, read_locus;
   DevBuf hits, spans, work, work2, ends, ctr, gring, gws;
-  uint32_t last_n_work = 0;
+  uint32_t last_n_work = 0, last_n_tier2 = 0, last_n_wide = 0;
 };
 
 namespace {
@@ -627,6 +627,8 @@ static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src
   CU(e, cudaMemcpyAsync(e->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaStreamSynchronize(e->stream));
   b->last_n_work = e->h_ctr->n_work - e->h_ctr->n_banded;  // pairs that needed the full-width kernels
+  b->last_n_tier2 = e->h_ctr->n_tier2;
+  b->last_n_wide = e->h_ctr->n_work;
   TRY(launch_trace(e, src, (const uint32_t *)b->work.p, &ctr->n_work, e->h_ctr->n_work, (const WfaEnd *)b->ends.p,
                    e->h_ctr->max_trace_ints, b->gws, b->frac, (trgt_flank_hit_t *)b->hits.p, nullptr, 0, nullptr,
                    nullptr, nullptr, ctr));
@@ -733,6 +735,14 @@ int32_t trgt_flank_device_views(trgt_flank_batch_t *b, const void **d_reads, con
   if (d_hits) *d_hits = b->hits.p;
   if (n_reads) *n_reads = b->n_reads;
   if (n_wfa) *n_wfa = b->last_n_work;
+  return 0;
+}
+
+/* how the last run settled the pairs that missed the exact search: out[0] = handed to the second cost
+ * tier, out[1] = handed to the wide-band kernel, out[2] = needed the full-width kernels */
+int32_t trgt_flank_fallback_counts(trgt_flank_batch_t *b, uint32_t out[3]) {
+  if (!b || !out) return TRGT_ERR_ARG;
+  out[0] = b->last_n_tier2; out[1] = b->last_n_wide; out[2] = b->last_n_work;
   return 0;
 }
 

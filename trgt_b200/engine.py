@@ -60,6 +60,7 @@ EXPORTS = [
     "trgt_host_alloc", "trgt_host_free",
     "trgt_flank_spans", "trgt_align_e2e", "trgt_edit_dist", "trgt_hmm_label",
     "trgt_flank_upload", "trgt_flank_run", "trgt_flank_download", "trgt_flank_free", "trgt_flank_device_views",
+    "trgt_flank_fallback_counts",
     "trgt_align_upload", "trgt_align_run", "trgt_align_download", "trgt_align_free",
     "trgt_hmm_upload", "trgt_hmm_run", "trgt_hmm_download", "trgt_hmm_free",
     "trgt_engine_set_profiling", "trgt_engine_reset_stats", "trgt_engine_kernel_count",
@@ -364,6 +365,13 @@ class Engine:
         n = C.c_uint32()
         self._L.trgt_flank_device_views(b, None, None, None, None, None, C.byref(n))
         return int(n.value)
+
+    def flank_fallback_counts(self, b):
+        """(pairs handed to the second cost tier, to the wide-band kernel, to the full-width kernels)"""
+        out = (C.c_uint32 * 3)()
+        self._L.trgt_flank_fallback_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        self._L.trgt_flank_fallback_counts(b, out)
+        return int(out[0]), int(out[1]), int(out[2])
 
     def align_upload(self, backbones: PackedSeqs, seqs: PackedSeqs, group_seq_offsets: np.ndarray):
         gso = np.ascontiguousarray(group_seq_offsets, dtype=np.uint32)

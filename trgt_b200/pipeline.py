@@ -111,6 +111,9 @@ class HotPath:
         spans, hits = eng.flank_download(self._fb, self.w.n_reads, want_hits=self.want_hits)
         return HotPathResult(spans, hits, self.glue, eng.align_download(self._ab), eng.hmm_download(self._hb))
 
+    def fallback_counts(self):
+        return self.eng.flank_fallback_counts(self._fb) if self._fb else (0, 0, 0)
+
     def n_wfa(self) -> int:
         return self.eng.flank_n_wfa(self._fb) if self._fb else 0
 
