@@ -47,20 +47,6 @@ struct WarpGroup {
   TRGT_D int bcast(int v, int src_lane) const { return __shfl_sync(0xffffffffu, v, src_lane); }
 };
 
-// 16 lanes: two independent groups per warp, each on its own item.  Collectives name only the
-// group's own half in their member mask, so the halves may run at different program points.
-struct HalfWarpGroup {
-  TRGT_D unsigned mask() const { return (threadIdx.x & 16u) ? 0xffff0000u : 0x0000ffffu; }
-  TRGT_D int lane() const { return (int)(threadIdx.x & 15u); }
-  TRGT_D int size() const { return 16; }
-  TRGT_D void sync() const { __syncwarp(mask()); }
-  TRGT_D int min_i(int v) const { return __reduce_min_sync(mask(), v); }
-  TRGT_D int max_i(int v) const { return __reduce_max_sync(mask(), v); }
-  TRGT_D int any(int p) const { return __any_sync(mask(), p); }
-  TRGT_D int bcast0(int v) const { return __shfl_sync(mask(), v, 0, 16); }
-  TRGT_D int bcast(int v, int src_lane) const { return __shfl_sync(mask(), v, src_lane, 16); }
-};
-
 // The whole CTA (blockDim.x threads, a multiple of 32, <= 1024) on one item.
 // `scratch` points at 33 ints of shared memory owned by the group.
 struct BlockGroup {

@@ -207,30 +207,24 @@ k_flank_exact(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t 
 struct __align__(16) FlankBandSmem {
   uint16_t slot[2][TRGT_KIDX_SLOTS];
   uint8_t piece[2][FL_PIECE];
+  uint8_t txt[FL_TXT];
   uint16_t list[FL_LIST];  // (read - first read of the pass) << 2 | pending sides
-  struct Half {            // one per half-warp: its staged read and scratch
-    uint8_t txt[FL_TXT];
-    int cand[TRGT_CAND_CAP + 4];
-    int ws[FL_WS1_INTS];
-  } h[2];
+  int cand[TRGT_CAND_CAP + 4];
+  int ws[FL_WS1_INTS];
 };
 
 // Phase A, step 2.  Again a warp per locus, but only the (read, flank) pairs left pending, and only
 // the first cost tier of the WFA fallback (span_locater.rs:14-25): one mismatch or one 1-bp gap,
 // ~89 % of HiFi misses.  Index seed filter + narrow-band wavefront + back-trace of wfa_core.h from
-// the staged copy of the read.  A first-tier band is at most 12 diagonals wide, so each HALF-warp
-// takes its own pending read: two pairs advance per warp.  The pieces' indexes are built once by
-// the whole warp.  What cannot be settled goes to `work2` (2*read+side) for k_flank_band2.
-__global__ void __launch_bounds__(32, 20)
+// the staged copy of the read, in 6.5 KB of shared memory per warp (28 resident warps per SM).
+// What it cannot settle goes to `work2` (2*read+side) for k_flank_band2.
+__global__ void __launch_bounds__(32, 28)
 k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
              int band_budget, double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits,
              uint32_t *__restrict__ work2, Counters *ctr) {
   __shared__ FlankBandSmem sm;
   const WarpGroup g;
-  const HalfWarpGroup hg;
   const int lane = g.lane();
-  const int half = lane >> 4, hl = hg.lane();
-  FlankBandSmem::Half &my = sm.h[half];
   for (uint32_t l = l_begin + blockIdx.x; l < l_end; l += gridDim.x) {
     const uint32_t r0 = locus_read_off[l], r1 = locus_read_off[l + 1];
     bool have_index = false;
@@ -252,7 +246,7 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
       }
       __syncwarp();
       if (n_list == 0) continue;
-      if (!have_index) {  // first pending pair of the locus: stage and index its pieces (whole warp)
+      if (!have_index) {  // first pending pair of the locus: stage and index its pieces
         have_index = true;
         const uint8_t *pgl = src.lp + src.lp_off[l], *pgr = src.rp + src.rp_off[l];
         PL[0] = (int)(src.lp_off[l + 1] - src.lp_off[l]);
@@ -268,16 +262,15 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
           if (indexed[side]) kidx_build(g, KmerIndex{sm.slot[side]}, ps[side], PL[side]);
         }
       }
-      // each half-warp takes every other pending read
 #pragma unroll 1
-      for (int i = half; i < n_list; i += 2) {
+      for (int i = 0; i < n_list; i++) {
         const unsigned mask = sm.list[i] & 3u;
         const uint32_t r = rb + (uint32_t)(sm.list[i] >> 2);
         const int T = (int)(src.read_off[r + 1] - src.read_off[r]);
-        const uint8_t *t_s = stage_bytes(src.reads + src.read_off[r], T, my.txt, FL_TXT, hl, 16);
+        const uint8_t *t_s = stage_bytes(src.reads + src.read_off[r], T, sm.txt, FL_TXT, lane, 32);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        hg.sync();
+        __syncwarp();
 #pragma unroll 1
         for (int side = 0; side < 2; side++) {
           if (!((mask >> side) & 1u)) continue;
@@ -291,10 +284,10 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
             pr.t = t_s; pr.T = T;
             pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;  // span_locater.rs:17
             wfa_unband(pr);
-            deferred = flank_locate_banded_lean(hg, pr, band_budget, min_flank_id_frac, my.ws, FL_WS1_INTS, &fh,
-                                                KmerIndex{sm.slot[side]}, my.cand, 0, 0);
+            deferred = flank_locate_banded_lean(g, pr, band_budget, min_flank_id_frac, sm.ws, FL_WS1_INTS, &fh,
+                                                KmerIndex{sm.slot[side]}, sm.cand, 0, 0);
           }
-          if (hl == 0) {
+          if (lane == 0) {
             trgt_flank_hit_t h;
             h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
             if (!deferred) {
@@ -306,11 +299,10 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
             }
             hits[2 * r + side] = h;
           }
-          hg.sync();
+          __syncwarp();
         }
-        hg.sync();
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
 }
