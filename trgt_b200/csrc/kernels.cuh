@@ -86,15 +86,7 @@ __global__ void k_expand_offsets(const uint32_t *__restrict__ off, uint32_t n_gr
 
 #define FL_TXT 1664        // bytes per staged read buffer (reads up to ~1.6 KB take the on-chip path)
 #define FL_PIECE 432       // bytes of staged flank piece (pieces up to TRGT_KIDX_MAX_P)
-#define FL_WS_INTS 1280    // scratch: seed keys / candidates, banded history or ring, trace cone
-
-// one warp = one CTA = one locus at a time
-struct __align__(16) FlankWarpSmem {
-  uint16_t slot[2][TRGT_KIDX_SLOTS];  // 8-mer index of the left / right piece
-  uint8_t piece[2][FL_PIECE];
-  uint8_t txt[2][FL_TXT];             // double buffer: the next read lands while this one is worked on
-  int ws[FL_WS_INTS];
-};
+#define FL_WS_INTS 1280    // scratch of the second cost tier: 6*17 header + 3 * 23 diagonals * 17 scores
 
 // copy `bytes` (+16 of slack) starting at global `src` into the 16-byte aligned staging buffer with
 // 16-byte cp.async issued by `nthreads` threads (this thread is `tid`); returns the staged address of
