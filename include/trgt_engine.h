@@ -136,6 +136,23 @@ typedef struct {
 int32_t trgt_align_e2e(trgt_engine_t *eng, const trgt_seqs_t *backbones, const trgt_seqs_t *seqs,
                        const uint32_t *group_seq_offsets, uint32_t n_groups, trgt_cigars_t *out);
 
+/* one sequence per group */
+typedef struct {
+  uint64_t n;
+  const uint64_t *offsets; /* [n+1] into data */
+  const uint8_t *data;
+  const int32_t *status;   /* per-group TRGT_ITEM_* */
+} trgt_seqs_out_t;
+
+/* utils::align followed by repair_consensus for many (backbone, seqs) groups, as every genotyper
+ * chains them (genotype_size.rs:35-36, genotype_cluster.rs:52-53, genotype_flank.rs:19-20):
+ * src/trgt/genotype/consensus.rs:5-72 (+ get_ins_consensus :94-111).  The CIGARs stay on the device;
+ * out receives one repaired consensus per group (engine-owned pinned memory, valid until the next
+ * align / consensus call on this engine).  A member base outside ACGT makes the reference panic
+ * (consensus.rs:81); here the group gets TRGT_ITEM_INVALID_BASE. */
+int32_t trgt_consensus(trgt_engine_t *eng, const trgt_seqs_t *backbones, const trgt_seqs_t *seqs,
+                       const uint32_t *group_seq_offsets, uint32_t n_groups, trgt_seqs_out_t *out);
+
 /* get_dist_matrix for many loci: src/trgt/genotype/genotype_cluster.rs:236-286.
  * locus_seq_offsets[n_loci+1] delimits each locus' TR sequences; dists_out receives, locus after
  * locus, the condensed upper triangles (index i*n - i(i+1)/2 + (j-i-1)), sqrt applied. */

@@ -116,6 +116,8 @@ def lib():
         L.tro_align_batch.argtypes = [vp] * 5 + [C.c_uint32, vp, C.POINTER(vp), vp, C.c_int]
         L.tro_hmm_batch.argtypes = [vp] * 3 + [C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, vp, C.POINTER(vp),
                                     vp, vp, C.c_int]
+        L.tro_repair_consensus.restype = C.c_int64
+        L.tro_repair_consensus.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, vp, C.c_uint32, vp, vp, vp, C.c_uint64]
         L.tro_free.argtypes = [vp]
         L.tro_free.restype = None
         _lib = L
@@ -411,3 +413,26 @@ def hmm_batch(motifs, locus_motif_off, alleles, allele_locus, n_threads: int = 1
     spans = np.ctypeslib.as_array(C.cast(sp, C.POINTER(C.c_uint32)), shape=(max(3 * tot, 1),))[:3 * tot].copy()
     lib().tro_free(sp)
     return mc_off, mc[:int(mc_off[n])], span_off, spans.reshape(-1, 3), purity[:n], status[:n]
+
+
+def repair_consensus(backbone: bytes, seqs: Sequence[bytes]) -> bytes:
+    """utils::align + repair_consensus (consensus.rs:5-72), as genotype_cluster.rs:52-53 chains them."""
+    np = _np()
+    offs = [0]
+    for s_ in seqs:
+        offs.append(offs[-1] + len(s_))
+    seq_off = np.array(offs, dtype=np.uint64)
+    words, woff = [], [0]
+    for s_ in seqs:
+        w, _ = align_words(backbone, s_)
+        words += w
+        woff.append(len(words))
+    warr = np.array(words if words else [0], dtype=np.uint32)
+    woffa = np.array(woff, dtype=np.uint64)
+    cap = len(backbone) + sum(len(s_) for s_ in seqs) + 8
+    out = np.zeros(cap, dtype=np.uint8)
+    n = lib().tro_repair_consensus(backbone, len(backbone), b"".join(seqs), seq_off.ctypes.data, len(seqs),
+                                   warr.ctypes.data, woffa.ctypes.data, out.ctypes.data, cap)
+    if n < 0:
+        raise ValueError(f"repair_consensus failed rc={n}")
+    return out[:n].tobytes()

@@ -151,6 +151,16 @@ int64_t tro_align_consensus(const uint8_t *backbone, int blen, const uint8_t *se
 /* get_dist: src/trgt/genotype/genotype_cluster.rs:236-248 */
 double tro_get_dist(const uint8_t *a, int alen, const uint8_t *b, int blen);
 
+/* ------------------------------------------------- next row: consensus -- */
+
+/* repair_consensus: src/trgt/genotype/consensus.rs:5-72 (get_ins_consensus :94-111).  words / word_off:
+ * run-length SAM CIGAR of every seq against the backbone (utils::align output).  Returns the consensus
+ * length, -1 on an unexpected base or op (the reference panics), -2 if cap is too small.
+ * PARITY UNPINNED: the reference's tests for it are commented out (consensus.rs:168-215). */
+int64_t tro_repair_consensus(const uint8_t *backbone, uint32_t blen, const uint8_t *seqs, const uint64_t *seq_off,
+                             uint32_t n_seqs, const uint32_t *words, const uint64_t *word_off, uint8_t *out,
+                             uint64_t cap);
+
 /* ------------------------------------------- batched CPU baseline path -- */
 
 /* Batched, multi-threaded drivers (batch_oracle.c) over the per-item functions above.  They take the

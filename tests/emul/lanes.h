@@ -47,6 +47,18 @@ struct LaneGroup {
     return r;
   }
   int bcast0(int v) const { return bcast(v, 0); }
+  int excl_scan_i(int v, int *total) const {
+    sh->slot[lane_] = v;
+    sync();
+    int before = 0, all = 0;
+    for (int i = 0; i < sh->n; i++) {
+      if (i < lane_) before += sh->slot[i];
+      all += sh->slot[i];
+    }
+    sync();
+    *total = all;
+    return before;
+  }
 };
 
 // run fn(group) on n lanes; returns when all are done

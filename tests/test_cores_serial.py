@@ -427,3 +427,34 @@ def test_hmm_core_thread_per_allele(emul, oracle):
         assert list(path[:plen.value]) == exp_path
         assert list(mc[:len(motifs)]) == exp_mc
         assert [(spans[i].m, spans[i].s, spans[i].e) for i in range(n)] == exp_sp and pur.value == exp_pur
+
+
+@pytest.mark.parametrize("lanes", [0, 4, 32])
+def test_consensus_core(emul, oracle, lanes):
+    """consensus_core.h (column vote + majority insertion) against the oracle's repair_consensus."""
+    import numpy as np
+    emul.emu_consensus.restype = C.c_long
+    emul.emu_consensus.argtypes = [C.c_int, C.c_char_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_uint64, C.c_int]
+    rng = random.Random(700 + lanes)
+    for _ in range(120 if lanes == 0 else 40):
+        unit = rnd(rng, rng.randint(2, 6))
+        truth = unit * rng.randint(2, 20)
+        pos = rng.randint(0, len(truth))
+        truth2 = truth[:pos] + rnd(rng, rng.randint(1, 4)) + truth[pos:]
+        seqs = [(mutate(rng, truth2 if rng.random() < 0.6 else truth, rng.choice([0, 0.02, 0.1])) or b"A")
+                for _ in range(rng.randint(1, 12))]
+        bb = rng.choice(seqs) if rng.random() < 0.7 else truth
+        offs, words, woff = [0], [], [0]
+        for s in seqs:
+            offs.append(offs[-1] + len(s))
+            w, _ = oracle.align_words(bb, s)
+            words += w
+            woff.append(len(words))
+        so, wa, wo = np.array(offs, dtype=np.uint64), np.array(words or [0], dtype=np.uint32), np.array(woff, dtype=np.uint64)
+        cap = len(bb) + sum(map(len, seqs)) + 8
+        out = np.zeros(cap, dtype=np.uint8)
+        n = emul.emu_consensus(len(bb), b"".join(seqs), so.ctypes.data, len(seqs), wa.ctypes.data, wo.ctypes.data,
+                               out.ctypes.data, cap, lanes)
+        assert n >= 0
+        assert out[:n].tobytes() == oracle.repair_consensus(bb, seqs)

@@ -238,6 +238,28 @@ def test_align_parity_long_and_scores(engine, oracle):
         assert res.cigar(i) == words and int(res.scores[i]) == score
 
 
+def test_consensus_parity(engine, oracle):
+    """next row (SURVEY 8f rank 1): utils::align + repair_consensus on the device vs the oracle."""
+    from trgt_b200 import TrgtError
+    rng = random.Random(53)
+    groups = []
+    for it in range(200):
+        unit = rnd(rng, rng.randint(2, 6))
+        truth = unit * rng.randint(2, 25 if it % 10 else 400)
+        pos = rng.randint(0, len(truth))
+        truth2 = truth[:pos] + rnd(rng, rng.randint(1, 4)) + truth[pos:]
+        seqs = [(mutate(rng, truth2 if rng.random() < 0.6 else truth, rng.choice([0, 0.02, 0.1])) or b"A")
+                for _ in range(rng.randint(1, 40))]
+        groups.append((rng.choice(seqs) if rng.random() < 0.7 else truth, seqs))
+    groups.append((b"ACGT", []))  # a group without members: every column ties at 0 -> '-' -> empty consensus
+    got = engine.repair_consensus(groups)
+    for (bb, seqs), g in zip(groups, got):
+        assert g == oracle.repair_consensus(bb, seqs)
+    assert engine.repair_consensus([]) == []
+    with pytest.raises(TrgtError):  # consensus.rs:81 panics on a base outside ACGT
+        engine.repair_consensus([(b"ACGT", [b"ACNT", b"ACGT"])])
+
+
 def test_edit_dist_parity(engine, oracle):
     rng = random.Random(41)
     loci = []

@@ -315,3 +315,23 @@ def test_find_span_exact_and_fallback(oracle):
     junk = bytes(rng.choice(b"ACGT") for _ in range(700))
     span, via, nm = oracle.find_span(flank, junk)
     assert span is None and via == 3 and nm < 175
+
+
+# ------------------------------------------------------------- consensus (next row) --
+
+def test_repair_consensus_reference_examples(oracle):
+    """src/trgt/genotype/consensus.rs:172-213 -- the reference's own examples for consensus repair.  They sit
+    in a commented-out test module written against an older API, so they pin nothing officially
+    (parity of this row stays 'unpinned'); the restatement reproduces all three expected strings."""
+    assert oracle.repair_consensus(b"CCCCACCCTCCC", [b"CCCCACCCGCCC", b"CCCCCCCCGCCC", b"CCCCCCCCCCCC"]) == b"CCCCCCCCGCCC"
+    assert oracle.repair_consensus(b"CCCCCCCCGCCC", [b"CCCCCCGCCC", b"CCCCCCGCCC", b"CCCCCCCCGCCC"]) == b"CCCCCCGCCC"
+    assert oracle.repair_consensus(b"CCCCCCCCGCCC", [b"CCCCCAAACCCGCCC", b"CCCCCAAACCCGCCC", b"CCCCCACCCGCAACC"]) == b"CCCCCAAACCCGCCC"
+
+
+def test_repair_consensus_tie_rules(oracle):
+    # column vote: Rust's max_by_key keeps the LAST maximum of [A,T,C,G,-] (consensus.rs:44-53)
+    assert oracle.repair_consensus(b"A", [b"A", b"G"]) == b"G"
+    assert oracle.repair_consensus(b"AC", [b"AC", b"C"]) in (b"C",)       # A vs '-' tie -> '-' wins
+    # insertion: needs more than half of the members and must outnumber members without one (:57, :106-110)
+    assert oracle.repair_consensus(b"ACGT", [b"ACTTGT", b"ACTTGT", b"ACGT"]) == b"ACTTGT"
+    assert oracle.repair_consensus(b"ACGT", [b"ACTTGT", b"ACGT"]) == b"ACGT"

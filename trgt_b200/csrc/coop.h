@@ -32,6 +32,8 @@ struct SerialGroup {
   TRGT_HD int any(int p) const { return p; }
   TRGT_HD int bcast0(int v) const { return v; }
   TRGT_HD int bcast(int v, int /*src_lane*/) const { return v; }
+  // exclusive prefix sum over the lanes; *total = sum over all lanes
+  TRGT_HD int excl_scan_i(int v, int *total) const { *total = v; return 0; }
 };
 
 #if defined(__CUDACC__)
@@ -45,6 +47,16 @@ struct WarpGroup {
   TRGT_D int any(int p) const { return __any_sync(0xffffffffu, p); }
   TRGT_D int bcast0(int v) const { return __shfl_sync(0xffffffffu, v, 0); }
   TRGT_D int bcast(int v, int src_lane) const { return __shfl_sync(0xffffffffu, v, src_lane); }
+  TRGT_D int excl_scan_i(int v, int *total) const {
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, d);
+      if ((int)(threadIdx.x & 31u) >= d) x += y;
+    }
+    *total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+  }
 };
 
 // The whole CTA (blockDim.x threads, a multiple of 32, <= 1024) on one item.

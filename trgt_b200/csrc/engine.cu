@@ -756,6 +756,8 @@ struct trgt_align_batch {
   DevBuf bb, bb_off, seqs, seq_off, group_off, seq_group;
   DevBuf ends, trace_work, cig_n, cig_off, pool, ctr, gring, gws;
   DevBuf out_off, out_words, scores, status;
+  DevBuf cons_counts, cons_recs, cons_len, cons_status, cons_off, cons_data;
+  PinBuf h_cons_off, h_cons_data, h_cons_status;
   // host copies handed out by download
   PinBuf h_off, h_words, h_scores, h_status;
   unsigned long long total_words = 0;
@@ -790,9 +792,11 @@ void trgt_align_free(trgt_engine_t *e, trgt_align_batch_t *b) {
   }
   DevBuf *all[] = {&b->bb, &b->bb_off, &b->seqs, &b->seq_off, &b->group_off, &b->seq_group, &b->ends, &b->trace_work,
                    &b->cig_n, &b->cig_off, &b->pool, &b->ctr, &b->gring, &b->gws, &b->out_off, &b->out_words,
-                   &b->scores, &b->status};
+                   &b->scores, &b->status, &b->cons_counts, &b->cons_recs, &b->cons_len, &b->cons_status,
+                   &b->cons_off, &b->cons_data};
   for (auto *d : all) dev_free(*d);
   pin_free(b->h_off); pin_free(b->h_words); pin_free(b->h_scores); pin_free(b->h_status);
+  pin_free(b->h_cons_off); pin_free(b->h_cons_data); pin_free(b->h_cons_status);
   delete b;
 }
 
@@ -989,6 +993,83 @@ int32_t trgt_align_e2e(trgt_engine_t *e, const trgt_seqs_t *backbones, const trg
   TRY(align_upload_into(e, e->one_align, backbones, seqs, group_seq_offsets, n_groups));
   TRY(align_run_locked(e, e->one_align));
   return align_download_locked(e, e->one_align, out);
+}
+
+// ------------------------------------------------------------------ consensus (next row) ------
+
+int32_t trgt_consensus(trgt_engine_t *e, const trgt_seqs_t *backbones, const trgt_seqs_t *seqs,
+                       const uint32_t *group_seq_offsets, uint32_t n_groups, trgt_seqs_out_t *out) {
+  if (!e || !out) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->one_align) e->one_align = new trgt_align_batch();
+  trgt_align_batch *b = e->one_align;
+  TRY(align_upload_into(e, b, backbones, seqs, group_seq_offsets, n_groups));
+  TRY(align_run_locked(e, b));  // CIGARs now sit in out_off / out_words on the device
+  const size_t ng = n_groups;
+  TRY(pin_reserve(e, b->h_cons_off, (ng + 1) * sizeof(uint64_t)));
+  TRY(pin_reserve(e, b->h_cons_status, (ng + 1) * sizeof(int32_t)));
+  b->h_cons_off.as<uint64_t>()[0] = 0;
+  out->n = ng;
+  out->offsets = b->h_cons_off.as<uint64_t>();
+  out->status = b->h_cons_status.as<int32_t>();
+  out->data = nullptr;
+  if (ng == 0) return 0;
+  const WfaSrc src = align_src(b);
+  TRY(dev_reserve(e, b->cons_len, (ng + 2) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->cons_status, (ng + 1) * sizeof(int32_t)));
+  TRY(dev_reserve(e, b->cons_off, (ng + 2) * sizeof(unsigned long long)));
+  // total CIGAR words bound the insertion records (one slot per word, plus one per group)
+  CU(e, cudaMemcpyAsync(&e->h_u64[2], (unsigned long long *)b->out_off.p + b->n_seqs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  const unsigned long long total_words = b->n_seqs ? e->h_u64[2] : 0;
+  TRY(dev_reserve(e, b->cons_recs, (size_t)(total_words + ng + 1) * sizeof(ConsRec)));
+  const int block = 128, wpb = 4;
+  int grid = 0;
+  TRY(persistent_grid(e, k_consensus_vote<false>, block, 0, &grid));
+  const uint32_t need = (uint32_t)((ng + wpb - 1) / wpb);
+  if ((uint32_t)grid > need) grid = (int)need;
+  const size_t stride = (size_t)6 * (size_t)(b->Pmax > 0 ? b->Pmax : 1);
+  // fewer resident warps when one column-count slot is large
+  {
+    const size_t budget_ints = e->workspace_budget / sizeof(int);
+    size_t slots = (size_t)grid * wpb;
+    if (stride > budget_ints) return fail(e, TRGT_ERR_INTERNAL, "consensus workspace exceeds the budget");
+    if (slots * stride > budget_ints) {
+      slots = budget_ints / stride;
+      grid = (int)(slots / wpb);
+      if (grid < 1) grid = 1;
+    }
+  }
+  TRY(dev_reserve(e, b->cons_counts, (size_t)grid * wpb * stride * sizeof(int)));
+  {
+    LaunchScope ls(e, "k_consensus_vote_count");
+    k_consensus_vote<false><<<grid, block, 0, e->stream>>>(
+        src, (const uint32_t *)b->group_off.p, n_groups, (const uint32_t *)b->out_words.p,
+        (const unsigned long long *)b->out_off.p, (const int32_t *)b->status.p, (int *)b->cons_counts.p, stride,
+        (ConsRec *)b->cons_recs.p, (uint32_t *)b->cons_len.p, (int32_t *)b->cons_status.p, nullptr, nullptr);
+    TRY(check_launch(e, "k_consensus_vote_count"));
+  }
+  CU(e, cudaMemsetAsync((uint32_t *)b->cons_len.p + ng, 0, sizeof(uint32_t), e->stream));
+  TRY(exclusive_scan_u32(e, (const uint32_t *)b->cons_len.p, (unsigned long long *)b->cons_off.p, ng + 1));
+  CU(e, cudaMemcpyAsync(b->h_cons_off.p, b->cons_off.p, (ng + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaMemcpyAsync(b->h_cons_status.p, b->cons_status.p, ng * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  const unsigned long long total = b->h_cons_off.as<uint64_t>()[ng];
+  TRY(dev_reserve(e, b->cons_data, (size_t)total + 16));
+  TRY(pin_reserve(e, b->h_cons_data, (size_t)total + 16));
+  if (total) {
+    LaunchScope ls(e, "k_consensus_vote_write");
+    k_consensus_vote<true><<<grid, block, 0, e->stream>>>(
+        src, (const uint32_t *)b->group_off.p, n_groups, (const uint32_t *)b->out_words.p,
+        (const unsigned long long *)b->out_off.p, (const int32_t *)b->status.p, (int *)b->cons_counts.p, stride,
+        (ConsRec *)b->cons_recs.p, (uint32_t *)b->cons_len.p, (int32_t *)b->cons_status.p,
+        (const unsigned long long *)b->cons_off.p, (uint8_t *)b->cons_data.p);
+    TRY(check_launch(e, "k_consensus_vote_write"));
+    CU(e, cudaMemcpyAsync(b->h_cons_data.p, b->cons_data.p, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+  }
+  out->data = b->h_cons_data.as<uint8_t>();
+  return 0;
 }
 
 // ------------------------------------------------------------------ phase B: edit distance ---

@@ -7,12 +7,14 @@
 //            k_flank_combine   find_tr_spans combine rule   span_locater.rs:53-67
 //   phase B  k_wfa_score / k_wfa_trace in end-to-end mode, k_cigar_gather   utils/align.rs:14-28
 //            k_edit_dist       get_dist_matrix              genotype_cluster.rs:236-286
+//            k_consensus_vote  repair_consensus behind the alignments (next row)  consensus.rs:5-111
 //   phase C  k_hmm_viterbi, k_hmm_walk, k_hmm_emit          src/hmm/*, tr.rs:454-492
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/trgt_engine.h"
+#include "consensus_core.h"
 #include "coop.h"
 #include "hmm_core.h"
 #include "wfa_core.h"
@@ -673,6 +675,48 @@ __global__ void k_cigar_gather(WfaSrc src, uint32_t n_seqs, const WfaEnd *__rest
       const unsigned long long po = cig_off[id];
       for (uint32_t w = 0; w < n; w++) out_words[o + w] = pool[po + w];
     }
+  }
+}
+
+// ------------------------------------------------------------------ consensus vote ----------
+
+// repair_consensus for many groups, one warp per group (consensus_core.h).  WRITE = false: counting
+// pass (lens[g] = consensus length, status[g]); WRITE = true: bytes at data + off[g].
+//   counts: per-warp slot of 6 * B_max ints; recs: one record slot per CIGAR word (indexed by the
+//   group's first word); align_status: per-sequence status of the alignment pass.
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_consensus_vote(WfaSrc src, const uint32_t *__restrict__ group_off, uint32_t n_groups,
+                 const uint32_t *__restrict__ words, const unsigned long long *__restrict__ word_off,
+                 const int32_t *__restrict__ align_status, int *counts, size_t counts_stride, ConsRec *recs,
+                 uint32_t *__restrict__ lens, int32_t *__restrict__ status, const unsigned long long *__restrict__ off,
+                 uint8_t *__restrict__ data) {
+  __shared__ int shared[4][2];
+  const WarpGroup g;
+  const uint32_t wib = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + wib, n_slots = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t gi = slot; gi < n_groups; gi += n_slots) {
+    ConsGroup gr;
+    gr.B = (int)(src.bb_off[gi + 1] - src.bb_off[gi]);
+    gr.s0 = group_off[gi];
+    gr.n = group_off[gi + 1] - gr.s0;
+    gr.seqs = src.seqs; gr.seq_off = src.seq_off; gr.words = words; gr.word_off = word_off;
+    int st = 0;
+    for (uint32_t m = (uint32_t)g.lane(); m < gr.n; m += 32)
+      if (align_status[gr.s0 + m] != 0) st = align_status[gr.s0 + m];
+    st = __reduce_min_sync(0xffffffffu, st);  // statuses are <= 0
+    if (WRITE && status[gi] != 0) continue;
+    long long len = 0;
+    if (st == 0) {
+      const uint32_t rec_cap = (uint32_t)(word_off[gr.s0 + gr.n] - word_off[gr.s0]) + 1u;
+      len = consensus_vote(g, gr, counts + (size_t)slot * counts_stride, recs + word_off[gr.s0] + gi, rec_cap,
+                           shared[wib], WRITE ? data + off[gi] : nullptr);
+    }
+    if (!WRITE && g.lane() == 0) {
+      status[gi] = st != 0 ? st : (len == -1 ? TRGT_ITEM_INVALID_BASE : (len < 0 ? TRGT_ITEM_OOM : 0));
+      lens[gi] = (st == 0 && len > 0) ? (uint32_t)len : 0u;
+    }
+    __syncwarp();
   }
 }
 

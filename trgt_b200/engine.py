@@ -40,6 +40,11 @@ class _Cigars(C.Structure):
                 ("scores", C.POINTER(C.c_int32)), ("status", C.POINTER(C.c_int32))]
 
 
+class _SeqsOut(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("offsets", C.POINTER(C.c_uint64)), ("data", C.POINTER(C.c_uint8)),
+                ("status", C.POINTER(C.c_int32))]
+
+
 class _Annotations(C.Structure):
     _fields_ = [("n", C.c_uint64), ("motif_count_offsets", C.POINTER(C.c_uint64)),
                 ("motif_counts", C.POINTER(C.c_uint32)), ("span_offsets", C.POINTER(C.c_uint64)),
@@ -58,7 +63,7 @@ EXPORTS = [
     "trgt_engine_stream", "trgt_engine_sm_count", "trgt_engine_sync", "trgt_engine_set_workspace_budget",
     "trgt_engine_set_flank_band_budget",
     "trgt_host_alloc", "trgt_host_free",
-    "trgt_flank_spans", "trgt_align_e2e", "trgt_edit_dist", "trgt_hmm_label",
+    "trgt_flank_spans", "trgt_align_e2e", "trgt_consensus", "trgt_edit_dist", "trgt_hmm_label",
     "trgt_flank_upload", "trgt_flank_run", "trgt_flank_download", "trgt_flank_free", "trgt_flank_device_views",
     "trgt_flank_fallback_counts",
     "trgt_align_upload", "trgt_align_run", "trgt_align_download", "trgt_align_free",
@@ -119,6 +124,7 @@ def load_library(build: bool = True):
     L.trgt_align_download.argtypes = [vp, vp, C.POINTER(_Cigars)]
     L.trgt_align_free.argtypes = [vp, vp]
     L.trgt_align_free.restype = None
+    L.trgt_consensus.argtypes = [vp, sp, sp, vp, u32, C.POINTER(_SeqsOut)]
     L.trgt_edit_dist.argtypes = [vp, sp, vp, u32, vp]
     L.trgt_hmm_label.argtypes = [vp, sp, vp, u32, sp, vp, i32, C.POINTER(_Annotations)]
     L.trgt_hmm_upload.argtypes = [vp, sp, vp, u32, sp, vp, i32, C.POINTER(vp)]
@@ -476,6 +482,27 @@ class Engine:
                 k += 1
             out.append(cur)
         return out
+
+    def consensus_packed(self, backbones: PackedSeqs, seqs: PackedSeqs, group_seq_offsets: np.ndarray):
+        """trgt_consensus -> (PackedSeqs of one repaired consensus per group, status int32[n_groups])"""
+        gso = np.ascontiguousarray(group_seq_offsets, dtype=np.uint32)
+        out = _SeqsOut()
+        rc = self._L.trgt_consensus(self._h, backbones.ref(), seqs.ref(), gso.ctypes.data, len(backbones), C.byref(out))
+        self._check(rc, "trgt_consensus")
+        n = int(out.n)
+        offs = _np_from(out.offsets, n + 1, np.uint64)
+        total = int(offs[n]) if n else 0
+        return PackedSeqs(_np_from(out.data, total, np.uint8), offs), _np_from(out.status, n, np.int32)
+
+    def repair_consensus(self, groups: Sequence[Tuple[bytes, Sequence[bytes]]]) -> List[bytes]:
+        """utils::align + repair_consensus (src/trgt/genotype/consensus.rs:5) for many (backbone, seqs) groups."""
+        bb = PackedSeqs.from_list([b for b, _ in groups])
+        sq = PackedSeqs.from_list([s for _, ss in groups for s in ss])
+        cons, status = self.consensus_packed(bb, sq, _group_offsets([ss for _, ss in groups]))
+        bad = np.nonzero(status)[0]
+        if bad.size:
+            raise TrgtError(f"trgt_consensus: group {int(bad[0])} failed with status {int(status[bad[0]])}")
+        return [cons.get(i) for i in range(len(groups))]
 
     def edit_dist_packed(self, seqs: PackedSeqs, locus_seq_offsets: np.ndarray) -> np.ndarray:
         lso = np.ascontiguousarray(locus_seq_offsets, dtype=np.uint32)
