@@ -377,6 +377,31 @@ def run_b200(args):
         compare_with_oracle(small.run_e2e(), ref)
         parity = {"checked_loci": n, "result": "bit-exact vs oracle (spans, CIGARs, scores, MC, MS, AP)"}
 
+    # ---- next row: consensus repair fused behind the alignments, timed on its own ----
+    consensus = None
+    if world == 1:
+        try:
+            g0 = hp.glue
+            eng.consensus_packed(g0.backbones, g0.seqs, g0.group_seq_off)  # warm-up
+            t0 = time.perf_counter()
+            cons, cstat = eng.consensus_packed(g0.backbones, g0.seqs, g0.group_seq_off)
+            dt = time.perf_counter() - t0
+            consensus = {"call": "trgt_consensus (utils::align + repair_consensus, host buffers in and out)",
+                         "groups": len(g0.backbones), "members": len(g0.seqs), "ms": dt * 1e3,
+                         "groups_per_s": len(g0.backbones) / dt, "failed_groups": int((cstat != 0).sum())}
+            if not args.no_cpu_baseline:
+                from oracle import oracle as orc
+                ng = min(len(g0.backbones), 2000)
+                t0 = time.perf_counter()
+                same = 0
+                for gi in range(ng):
+                    members = [g0.seqs.get(i) for i in range(int(g0.group_seq_off[gi]), int(g0.group_seq_off[gi + 1]))]
+                    same += orc.repair_consensus(g0.backbones.get(gi), members) == cons.get(gi)
+                consensus["parity"] = f"{same}/{ng} groups identical to the oracle"
+                consensus["cpu_port_groups_per_s_1_core_python_driver"] = ng / (time.perf_counter() - t0)
+        except Exception as exc:  # never let the extra row break the headline line
+            consensus = {"error": repr(exc)}
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -385,7 +410,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),
                 "glue_threads": glue_threads, "phase_ms_summed_over_host_threads": e2e_phases},
-        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "kernels": kernels,
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "kernels": kernels,
         "wfa_fallback_pairs": hp.n_wfa(), "flank_fallback_counts": dict(zip(("second_tier", "wide_band", "full_width"), hp.fallback_counts())),
         "workload_gen_s": t_gen,
     }
