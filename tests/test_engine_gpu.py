@@ -295,3 +295,45 @@ def test_kernels_actually_launched(engine):
     engine.label_with_hmm([([b"CAG"], [b"CAGCAGCAG"])])
     stats = engine.kernel_stats()
     assert stats["k_hmm_viterbi_thread"][0] >= 1 and engine.launches() >= 2
+
+
+# ------------------------------------------------------------------ whole pass, other BASELINE configs ---
+
+def _pass_and_compare(engine, oracle, w):
+    from trgt_b200.pipeline import HotPath, compare_with_oracle, oracle_pass
+    hp = HotPath(engine, w, want_hits=False, pinned_outputs=False)
+    res = hp.run_e2e(copy=True)
+    compare_with_oracle(res, oracle_pass(oracle, w, 4))
+    # the resident-batch interface must give the same answers
+    hp.prepare_resident()
+    hp.run_resident()
+    res2 = hp.download_resident()
+    hp.free_resident()
+    assert np.array_equal(res.spans, res2.spans) and np.array_equal(res.cigars.words, res2.cigars.words)
+    assert np.array_equal(res.annotations.spans, res2.annotations.spans)
+    assert np.array_equal(res.annotations.motif_counts, res2.annotations.motif_counts)
+    return res
+
+
+def test_pass_pathogenic_catalog_config2(engine, oracle):
+    """BASELINE config 2: the 56 loci of repeats/pathogenic_repeats.hg38.bed (motif sets from the committed
+    fixture; up to 10 motifs and 170 HMM states per locus, N in motifs), synthetic 30x HiFi."""
+    from trgt_b200 import workload
+    sets = workload.pathogenic_motif_sets()
+    w = workload.generate(len(sets), 30, motif_sets=sets, tr_len_median=60.0, seed=2)
+    res = _pass_and_compare(engine, oracle, w)
+    assert res.spans["found"].mean() > 0.9
+
+
+def test_pass_long_expansions_config5_shape(engine, oracle):
+    """BASELINE config 5 shape at test size: alleles of several kb (reads too long for the staged on-chip
+    path, consensus pairs through the CTA-per-pair kernels, Viterbi over thousands of columns)."""
+    from trgt_b200 import workload
+    w = workload.generate(5, 6, tr_len_median=3000.0, tr_len_sigma=0.5, tr_len_min=1500, tr_len_max=9000, seed=8)
+    assert int(np.diff(w.reads.offsets.astype(np.int64)).max()) > 4000
+    _pass_and_compare(engine, oracle, w)
+
+
+def test_hmm_locus_without_motifs_and_single_base_motif(engine, oracle):
+    loci = [([], [b"ACGTACGT", b"A"]), ([b"A"], [b"AAAAAAA", b"AAACAAA", b""]), ([b"N"], [b"ACGT"])]
+    _check_annotations(oracle, loci, engine.label_with_hmm(loci))
