@@ -337,3 +337,22 @@ def test_pass_long_expansions_config5_shape(engine, oracle):
 def test_hmm_locus_without_motifs_and_single_base_motif(engine, oracle):
     loci = [([], [b"ACGTACGT", b"A"]), ([b"A"], [b"AAAAAAA", b"AAACAAA", b""]), ([b"N"], [b"ACGT"])]
     _check_annotations(oracle, loci, engine.label_with_hmm(loci))
+
+
+@pytest.mark.parametrize("piece_len", [10, 40, 500])
+def test_flank_spans_unindexed_piece_lengths(engine, oracle, piece_len):
+    """Pieces too short or too long for the 8-mer index: linear exact scan, and misses go all the way
+    down to the wide-band / full-width kernels."""
+    rng = random.Random(piece_len)
+    loci = []
+    for _ in range(6):
+        lf, rf = rnd(rng, piece_len + 20), rnd(rng, piece_len + 20)
+        reads = []
+        for _ in range(8):
+            rate = rng.choice([0.0, 0.0, 0.01, 0.05])
+            reads.append(rnd(rng, rng.randint(0, 200)) + mutate(rng, lf[-piece_len:], rate) + b"CAG" * rng.randint(0, 30) +
+                         mutate(rng, rf[:piece_len], rate) + rnd(rng, rng.randint(piece_len + 10, 300)))
+        loci.append((lf, rf, reads))
+    got = engine.find_tr_spans(loci, search_flank_len=piece_len)
+    for (lf, rf, reads), g in zip(loci, got):
+        assert g == oracle.find_tr_spans(lf, rf, reads, search_flank_len=piece_len)
