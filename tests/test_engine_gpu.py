@@ -351,7 +351,7 @@ def test_flank_spans_unindexed_piece_lengths(engine, oracle, piece_len):
         for _ in range(8):
             rate = rng.choice([0.0, 0.0, 0.01, 0.05])
             reads.append(rnd(rng, rng.randint(0, 200)) + mutate(rng, lf[-piece_len:], rate) + b"CAG" * rng.randint(0, 30) +
-                         mutate(rng, rf[:piece_len], rate) + rnd(rng, rng.randint(piece_len + 10, 300)))
+                         mutate(rng, rf[:piece_len], rate) + rnd(rng, rng.randint(piece_len + 10, piece_len + 300)))
         loci.append((lf, rf, reads))
     got = engine.find_tr_spans(loci, search_flank_len=piece_len)
     for (lf, rf, reads), g in zip(loci, got):
