@@ -247,7 +247,7 @@ def run_b200(args):
     # end-to-end driver: chunks of loci through `host_threads` engines on this GPU
     engines = [eng] + [trgt_b200.Engine(device=local_rank) for _ in range(max(1, args.host_threads) - 1)]
     # host cores are shared by all ranks of the box and all host threads of a rank
-    glue_threads = max(2, host_cores() // max(1, world * len(engines)))
+    glue_threads = max(1, host_cores() // max(1, world * len(engines)))
     chp = ChunkedHotPath(engines, w, chunk_loci=args.chunk_loci, glue_threads=glue_threads)
 
     # ---- warm-up: end-to-end passes (also builds the resident batches) ----
