@@ -41,6 +41,7 @@ extern "C" {
 #define TRGT_ITEM_OOM (-200)
 #define TRGT_ITEM_UNATTAINABLE (-300)
 #define TRGT_ITEM_INVALID_BASE (-400) /* reference panics: hmm_model.rs:250, builder.rs:182 */
+#define TRGT_ITEM_INVALID_OP (-500)   /* reference panics: clip_region.rs:150,178 "Unexpected operation" */
 
 typedef struct trgt_engine trgt_engine_t;
 
@@ -101,6 +102,45 @@ void trgt_engine_set_flank_band_budget(trgt_engine_t *eng, int32_t max_cost);
 void *trgt_host_alloc(size_t bytes);
 void trgt_host_free(void *p);
 
+/* ---- producer of phase A's input: read clipping and BAM bases (next row, rank 2) ---- */
+
+/* clip_cigar plus the query range HiFiRead::clip_to_region copies
+ * (src/trgt/reads/clip_region.rs:19-38,105-186).  The clipped CIGAR is
+ * [first_word, ops[first_op+1 .. first_op+n_ops-2], last_word]; the clipped bases are
+ * bases[query_start .. query_end) of the record. */
+typedef struct {
+  int64_t ref_start;      /* clipped_ref_start */
+  uint64_t query_start;   /* clipped_query_start */
+  uint64_t query_end;
+  uint32_t first_op;      /* index in the read's ops of the first clipped op */
+  uint32_t n_ops;         /* number of clipped ops */
+  uint32_t first_word, last_word; /* BAM encoding (len<<4)|op after splitting; equal when n_ops == 1 */
+  int32_t status;         /* 1 = overlaps the region, 0 = None (read dropped by clip_reads),
+                             TRGT_ITEM_INVALID_OP = the reference panics */
+} trgt_clip_t;
+
+/* clip_reads for a chunk of loci: src/trgt/workflows/tr.rs:186-196 -> HiFiRead::clip_to_region.
+ *   cigar_ops: BAM-encoded CIGAR words ((len<<4)|op, op in MIDNSHP=X) of all reads, as bam_get_cigar
+ *   stores them; cigar_offsets[n_reads+1] delimits each read; ref_starts[n_reads] = rec.reference_start()
+ *   regions[2*n_loci] = (start, end) the reads of each locus are clipped to (locus region +- radius)
+ *   clips_out[n_reads] */
+int32_t trgt_clip_reads(trgt_engine_t *eng, const uint32_t *cigar_ops, const uint64_t *cigar_offsets,
+                        const int64_t *ref_starts, uint64_t n_reads, const int64_t *regions,
+                        const uint32_t *locus_read_offsets, uint32_t n_loci, trgt_clip_t *clips_out);
+
+/* Read bases as a BAM record stores them (htslib bam_get_seq / rust-htslib Seq::encoded: codes of
+ * "=ACMGRSVTWYHKDBN", two bases per byte, first base in the high nibble).  Read i is bases
+ * [starts[i], starts[i] + lengths[i]) of `data`, starts counted in bases (nibbles); starts must be
+ * non-decreasing.  The host copies the bytes covering bases[query_start..query_end) of each record
+ * (trgt_clip_t) into `data` -- no decoding, no shifting -- and sets starts[i] = 2*byte_offset + (query_start & 1). */
+typedef struct {
+  const uint8_t *data;
+  uint64_t data_bytes;
+  const uint64_t *starts;   /* [n] */
+  const uint32_t *lengths;  /* [n] */
+  uint64_t n;
+} trgt_seq4_t;
+
 /* ---- phase A: flank location (a1-a4) ------------------------------------ */
 
 /* find_tr_spans for a chunk of loci: src/trgt/genotype/span_locater.rs:32-68 (find_spans :7-30,
@@ -115,6 +155,21 @@ int32_t trgt_flank_spans(trgt_engine_t *eng, const trgt_seqs_t *left_pieces,
                          const uint32_t *locus_read_offsets, uint32_t n_loci,
                          trgt_scoring_t scoring, double min_flank_id_frac,
                          trgt_span_t *spans_out, trgt_flank_hit_t *hits_out);
+
+/* trgt_flank_spans on reads handed over as BAM 4-bit bases: replaces `rec.seq().as_bytes()`
+ * (src/trgt/reads/read.rs:104) + the copy of clip_to_region (clip_region.rs:29-31) + find_tr_spans.
+ * Half the bytes cross PCIe; the engine decodes to the ASCII reads of phase A in HBM (k_unpack_seq4).
+ * Spans are in bases of the clipped read, as in trgt_flank_spans. */
+int32_t trgt_flank_spans_seq4(trgt_engine_t *eng, const trgt_seqs_t *left_pieces,
+                              const trgt_seqs_t *right_pieces, const trgt_seq4_t *reads,
+                              const uint32_t *locus_read_offsets, uint32_t n_loci,
+                              trgt_scoring_t scoring, double min_flank_id_frac,
+                              trgt_span_t *spans_out, trgt_flank_hit_t *hits_out);
+
+/* decode only (for callers that want the clipped ASCII reads back, e.g. to cut allele sequences):
+ * ascii_out receives the reads back to back, ascii_offsets_out[n+1] their CSR offsets */
+int32_t trgt_seq4_decode(trgt_engine_t *eng, const trgt_seq4_t *reads, uint8_t *ascii_out,
+                         uint64_t *ascii_offsets_out);
 
 /* ---- phase B: consensus alignments (a5) and edit distances (a6) ---------- */
 
@@ -200,6 +255,12 @@ int32_t trgt_flank_upload(trgt_engine_t *eng, const trgt_seqs_t *left_pieces,
                           const uint32_t *locus_read_offsets, uint32_t n_loci,
                           trgt_scoring_t scoring, double min_flank_id_frac,
                           trgt_flank_batch_t **out);
+/* the same resident batch from BAM 4-bit reads (decoded on the device at upload) */
+int32_t trgt_flank_upload_seq4(trgt_engine_t *eng, const trgt_seqs_t *left_pieces,
+                               const trgt_seqs_t *right_pieces, const trgt_seq4_t *reads,
+                               const uint32_t *locus_read_offsets, uint32_t n_loci,
+                               trgt_scoring_t scoring, double min_flank_id_frac,
+                               trgt_flank_batch_t **out);
 /* the *_run calls enqueue on the engine stream; they synchronise internally where a later launch
  * is sized by an earlier one (work-list length, workspace), but results are only guaranteed in
  * place after the matching *_download (or trgt_engine_sync) */

@@ -54,6 +54,12 @@ class _OptSpan(C.Structure):
     _fields_ = [("found", C.c_int32), ("start", C.c_uint32), ("end", C.c_uint32)]
 
 
+class _Clip(C.Structure):
+    _fields_ = [("ref_start", C.c_int64), ("query_start", C.c_uint64), ("query_end", C.c_uint64),
+                ("first_op", C.c_uint32), ("n_ops", C.c_uint32), ("first_word", C.c_uint32),
+                ("last_word", C.c_uint32)]
+
+
 _lib = None
 
 
@@ -118,6 +124,9 @@ def lib():
                                     vp, vp, C.c_int]
         L.tro_repair_consensus.restype = C.c_int64
         L.tro_repair_consensus.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, vp, C.c_uint32, vp, vp, vp, C.c_uint64]
+        L.tro_clip_cigar.argtypes = [vp, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_Clip)]
+        L.tro_decode_seq4.argtypes = [vp, C.c_uint64, C.c_uint32, vp]
+        L.tro_decode_seq4.restype = None
         L.tro_free.argtypes = [vp]
         L.tro_free.restype = None
         _lib = L
@@ -436,3 +445,54 @@ def repair_consensus(backbone: bytes, seqs: Sequence[bytes]) -> bytes:
     if n < 0:
         raise ValueError(f"repair_consensus failed rc={n}")
     return out[:n].tobytes()
+
+
+# ------------------------------------------------------------------ next row: read clipping --
+
+BAM_OPS = "MIDNSHP=X"
+SEQ4_ALPHABET = b"=ACMGRSVTWYHKDBN"
+
+
+def encode_bam_cigar(text: str) -> List[int]:
+    """'3=2D5I' -> BAM words (len<<4)|op"""
+    import re
+    return [(int(n) << 4) | BAM_OPS.index(op) for n, op in re.findall(r"(\d+)([MIDNSHP=X])", text)]
+
+
+def clip_cigar(ops: Sequence[int], ref_pos: int, region: Tuple[int, int]):
+    """clip_cigar + the query range of clip_to_region (clip_region.rs:19-38,105-186).
+    None = no overlap; else (clipped_ref_start, query_start, query_end, clipped ops as BAM words)."""
+    np = _np()
+    arr = np.array(list(ops) if len(ops) else [0], dtype=np.uint32)
+    out = _Clip()
+    rc = lib().tro_clip_cigar(arr.ctypes.data, len(ops), ref_pos, region[0], region[1], C.byref(out))
+    if rc < 0:
+        raise ValueError("Unexpected operation")
+    if rc == 0:
+        return None
+    words = []
+    for i in range(out.n_ops):
+        if i == 0:
+            words.append(out.first_word)
+        elif i == out.n_ops - 1:
+            words.append(out.last_word)
+        else:
+            words.append(int(arr[out.first_op + i]))
+    return out.ref_start, out.query_start, out.query_end, words
+
+
+def encode_seq4(bases: bytes) -> bytes:
+    """ASCII -> BAM 4-bit (the inverse of rec.seq().as_bytes(); test helper)"""
+    codes = [SEQ4_ALPHABET.index(b) if b in SEQ4_ALPHABET else 15 for b in bases]
+    if len(codes) & 1:
+        codes.append(0)
+    return bytes((codes[i] << 4) | codes[i + 1] for i in range(0, len(codes), 2))
+
+
+def decode_seq4(packed: bytes, start: int, length: int) -> bytes:
+    """read.rs:104 for bases [start, start+length)"""
+    np = _np()
+    src = np.frombuffer(packed + b"\0", dtype=np.uint8)
+    out = np.zeros(max(1, length), dtype=np.uint8)
+    lib().tro_decode_seq4(src.ctypes.data, start, length, out.ctypes.data)
+    return out[:length].tobytes()

@@ -161,6 +161,27 @@ int64_t tro_repair_consensus(const uint8_t *backbone, uint32_t blen, const uint8
                              uint32_t n_seqs, const uint32_t *words, const uint64_t *word_off, uint8_t *out,
                              uint64_t cap);
 
+/* ------------------------------------------ next row: read clipping -- */
+
+/* Result of clip_cigar + the query range clip_to_region copies.  The clipped CIGAR is
+ * [first_word, ops[first_op+1 .. first_op+n_ops-2], last_word] (first_word == last_word if n_ops == 1). */
+typedef struct {
+  int64_t ref_start;       /* clipped_ref_start */
+  uint64_t query_start;    /* clipped_query_start */
+  uint64_t query_end;      /* query_start + sum of the clipped ops' query lengths */
+  uint32_t first_op;       /* index in ops of the first clipped op */
+  uint32_t n_ops;          /* number of clipped ops */
+  uint32_t first_word, last_word; /* BAM-encoded (len<<4)|op, after splitting */
+} tro_clip;
+
+/* clip_cigar: src/trgt/reads/clip_region.rs:105-186 (+ :19-38).  1 = overlap (out filled), 0 = None,
+ * -1 = the reference panics (split of an op without reference length). */
+int tro_clip_cigar(const uint32_t *ops, uint32_t n_ops, int64_t ref_start, int64_t region_start,
+                   int64_t region_end, tro_clip *out);
+
+/* rec.seq().as_bytes() (read.rs:104) for bases [start, start+len) of a BAM 4-bit sequence */
+void tro_decode_seq4(const uint8_t *packed, uint64_t start, uint32_t len, uint8_t *out);
+
 /* ------------------------------------------- batched CPU baseline path -- */
 
 /* Batched, multi-threaded drivers (batch_oracle.c) over the per-item functions above.  They take the

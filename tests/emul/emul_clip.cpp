@@ -1,0 +1,31 @@
+// emul_clip.cpp -- TEST INFRASTRUCTURE ONLY.  Serial / lock-step multi-lane run of
+// trgt_b200/csrc/clip_core.h.  Never linked into libtrgt_b200.so.
+#include <string.h>
+
+#include <vector>
+
+#include "../../trgt_b200/csrc/clip_core.h"
+#include "lanes.h"
+
+using namespace trgt;
+
+extern "C" {
+
+void emu_clip_cigar(const uint32_t *ops, uint32_t n_ops, long long ref_start, long long region_start,
+                    long long region_end, trgt_clip_t *out) {
+  *out = clip_cigar_one(ops, n_ops, ref_start, region_start, region_end);
+}
+
+// decode n reads into out (CSR offsets out_off[n+1] given); data must carry 16 bytes of padding on both
+// sides, as the engine's device buffer does; out must be 16-byte aligned
+void emu_seq4_unpack(const uint8_t *data, const uint64_t *starts, const uint32_t *lengths, const uint64_t *out_off,
+                     uint32_t n, uint8_t *out, int lanes) {
+  for (uint32_t r = 0; r < n; r++) {
+    if (lanes == 0) { SerialGroup g; seq4_unpack_read(g, data, starts[r], lengths[r], out, out_off[r]); }
+    else trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &g) {
+      seq4_unpack_read(g, data, starts[r], lengths[r], out, out_off[r]);
+    });
+  }
+}
+
+}  // extern "C"

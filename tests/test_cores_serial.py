@@ -458,3 +458,86 @@ def test_consensus_core(emul, oracle, lanes):
                                out.ctypes.data, cap, lanes)
         assert n >= 0
         assert out[:n].tobytes() == oracle.repair_consensus(bb, seqs)
+
+
+# ------------------------------------------------------------- producer row: clip + decode --
+
+class _Clip(C.Structure):
+    _fields_ = [("ref_start", C.c_int64), ("query_start", C.c_uint64), ("query_end", C.c_uint64),
+                ("first_op", C.c_uint32), ("n_ops", C.c_uint32), ("first_word", C.c_uint32),
+                ("last_word", C.c_uint32), ("status", C.c_int32)]
+
+
+def random_bam_cigar(rng, n_ops):
+    """HiFi-like CIGAR: optional soft clips at the ends, =/X/I/D/M/N inside"""
+    ops = []
+    if rng.random() < 0.3:
+        ops.append((rng.randint(1, 30) << 4) | 4)
+    for _ in range(n_ops):
+        op = rng.choice([7, 7, 7, 8, 1, 2, 0, 3])
+        ops.append((rng.randint(1, 40) << 4) | op)
+    if rng.random() < 0.3:
+        ops.append((rng.randint(1, 30) << 4) | 4)
+    if rng.random() < 0.05:
+        ops.insert(0, (5 << 4) | 5)
+    return ops
+
+
+def test_clip_core_random(emul, oracle):
+    import numpy as np
+    rng = random.Random(77)
+    for it in range(3000):
+        ops = random_bam_cigar(rng, rng.randint(0, 12))
+        ref_pos = rng.randint(0, 200)
+        a = rng.randint(0, 400)
+        region = (a, a + rng.randint(0, 300))
+        arr = np.array(ops if ops else [0], dtype=np.uint32)
+        got = _Clip()
+        emul.emu_clip_cigar(arr.ctypes.data_as(C.c_void_p), C.c_uint32(len(ops)), C.c_longlong(ref_pos),
+                            C.c_longlong(region[0]), C.c_longlong(region[1]), C.byref(got))
+        exp = oracle.clip_cigar(ops, ref_pos, region)
+        if exp is None:
+            assert got.status == 0, (it, ops, ref_pos, region)
+            continue
+        assert got.status == 1
+        words = [got.first_word if i == 0 else got.last_word if i == got.n_ops - 1 else ops[got.first_op + i]
+                 for i in range(got.n_ops)]
+        assert (got.ref_start, got.query_start, got.query_end, words) == exp, (it, ops, ref_pos, region)
+
+
+@pytest.mark.parametrize("lanes", [0, 4, 32])
+def test_seq4_unpack_core(emul, oracle, lanes):
+    import numpy as np
+    rng = random.Random(5 + lanes)
+    for it in range(40):
+        n = rng.randint(0, 12)
+        seqs = [rnd(rng, rng.choice([0, 1, 2, 15, 16, 17, 31, 33, rng.randint(0, 700)]), "ACGTN=MRSVWYHKDB")
+                for _ in range(n)]
+        packed = oracle.encode_seq4(b"")  # built below with arbitrary nibble starts
+        nibs, starts = [], []
+        for s_ in seqs:
+            nibs += [0] * rng.randint(0, 5)
+            starts.append(len(nibs))
+            nibs += [oracle.SEQ4_ALPHABET.index(c) for c in s_]
+        if len(nibs) & 1:
+            nibs.append(0)
+        packed = bytes((nibs[i] << 4) | nibs[i + 1] for i in range(0, len(nibs), 2))
+        buf = np.zeros(len(packed) + 48, dtype=np.uint8)
+        base = (-buf.ctypes.data) % 16 + 16      # 16 bytes of padding in front, data 16-byte aligned or not
+        base += rng.randint(0, 7)                # the packed buffer itself may sit at any address
+        buf[base:base + len(packed)] = np.frombuffer(packed, dtype=np.uint8)
+        lens = np.array([len(s_) for s_ in seqs] + [0], dtype=np.uint32)
+        st = np.array(starts + [0], dtype=np.uint64)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum(lens[:n], dtype=np.uint64)
+        out = np.zeros(int(offs[n]) + 64, dtype=np.uint8)
+        ob = (-out.ctypes.data) % 16
+        out[:] = 0x7E
+        emul.emu_seq4_unpack(C.c_void_p(buf.ctypes.data + base), st.ctypes.data_as(C.c_void_p),
+                             lens.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), C.c_uint32(n),
+                             C.c_void_p(out.ctypes.data + ob), C.c_int(lanes))
+        got = out[ob:ob + int(offs[n])].tobytes()
+        assert got == b"".join(seqs), (it, seqs)
+        assert (out[ob + int(offs[n]):ob + int(offs[n]) + 16] == 0x7E).all() and (out[:ob] == 0x7E).all()
+        for i, s_ in enumerate(seqs):
+            assert oracle.decode_seq4(packed, starts[i], len(s_)) == s_

@@ -356,3 +356,113 @@ def test_flank_spans_unindexed_piece_lengths(engine, oracle, piece_len):
     got = engine.find_tr_spans(loci, search_flank_len=piece_len)
     for (lf, rf, reads), g in zip(loci, got):
         assert g == oracle.find_tr_spans(lf, rf, reads, search_flank_len=piece_len)
+
+
+# ------------------------------------------------------------------ producer row: clip + BAM bases ---
+
+def test_clip_reads_reference_vectors(engine, oracle):
+    """src/trgt/reads/clip_region.rs:214-299 through trgt_clip_reads (one locus per region)"""
+    cases = [("3=2D2=1X2=5I3=", (0, 10)), ("3=2D2=1X2=5I3=", (23, 33)), ("5S3=2D2=1X2=5I3=10S", (9, 23)),
+             ("3=2D2=1X2=5I3=", (0, 15)), ("3=2D2=1X2=5I3=", (12, 17)), ("3=2D2=1X2=5I3=", (21, 22)),
+             ("3=2D2=1X2=5I3=", (0, 17))]
+    ops, offs = [], [0]
+    for cig, _ in cases:
+        ops += oracle.encode_bam_cigar(cig)
+        offs.append(len(ops))
+    clips = engine.clip_reads(np.array(ops, dtype=np.uint32), np.array(offs, dtype=np.uint64),
+                              np.full(len(cases), 10, dtype=np.int64),
+                              np.array([r for _, r in cases], dtype=np.int64),
+                              np.arange(len(cases) + 1, dtype=np.uint32))
+    exp = [None, None, (10, 0, 31, "5S3=2D2=1X2=5I3=10S"), (10, 0, 3, "3=2D"), (12, 2, 5, "1=2D2="),
+           (21, 15, 16, "1="), (10, 0, 5, "3=2D2=")]
+    for i, (c, e) in enumerate(zip(clips, exp)):
+        if e is None:
+            assert c["status"] == 0
+            continue
+        o0 = offs[i]
+        words = [int(c["first_word"]) if k == 0 else int(c["last_word"]) if k == c["n_ops"] - 1
+                 else ops[o0 + int(c["first_op"]) + k] for k in range(int(c["n_ops"]))]
+        text = "".join(f"{w >> 4}{oracle.BAM_OPS[w & 15]}" for w in words)
+        assert c["status"] == 1 and (int(c["ref_start"]), int(c["query_start"]), int(c["query_end"]), text) == e
+
+
+def test_clip_reads_random_parity(engine, oracle):
+    from tests.test_cores_serial import random_bam_cigar
+    rng = random.Random(123)
+    n_loci = 300
+    regions, lro, ops, offs, refs = [], [0], [], [0], []
+    for _ in range(n_loci):
+        a = rng.randint(0, 400)
+        regions.append((a, a + rng.randint(0, 300)))
+        for _ in range(rng.choice([0, 1, 5, 30])):
+            o = random_bam_cigar(rng, rng.randint(0, 40))
+            ops += o
+            offs.append(len(ops))
+            refs.append(rng.randint(0, 500))
+        lro.append(len(refs))
+    clips = engine.clip_reads(np.array(ops, dtype=np.uint32), np.array(offs, dtype=np.uint64),
+                              np.array(refs, dtype=np.int64), np.array(regions, dtype=np.int64),
+                              np.array(lro, dtype=np.uint32))
+    n_hit = 0
+    for l in range(n_loci):
+        for r in range(lro[l], lro[l + 1]):
+            o = ops[offs[r]:offs[r + 1]]
+            exp = oracle.clip_cigar(o, refs[r], regions[l])
+            c = clips[r]
+            if exp is None:
+                assert c["status"] == 0
+                continue
+            n_hit += 1
+            words = [int(c["first_word"]) if k == 0 else int(c["last_word"]) if k == c["n_ops"] - 1
+                     else o[int(c["first_op"]) + k] for k in range(int(c["n_ops"]))]
+            assert c["status"] == 1 and (int(c["ref_start"]), int(c["query_start"]), int(c["query_end"]), words) == exp
+    assert n_hit > 500
+    assert "k_clip_cigar" in engine.kernel_stats()
+
+
+def test_seq4_decode_parity(engine, oracle):
+    from trgt_b200 import PackedSeq4
+    rng = random.Random(9)
+    seqs = [rnd(rng, n, "ACGTN=MRSVWYHKDB") for n in
+            [0, 1, 2, 15, 16, 17, 31, 32, 33, 1024, 1023, 1025, 0, 5000] + [rng.randint(0, 1500) for _ in range(300)]]
+    for odd in (True, False):
+        p4 = PackedSeq4.from_ascii(seqs, odd_starts=odd)
+        got = engine.seq4_decode(p4)
+        assert [got.get(i) for i in range(len(seqs))] == seqs
+        for i in (0, 3, 9, 13, 50):
+            assert oracle.decode_seq4(p4.data.tobytes(), int(p4.starts[i]), int(p4.lengths[i])) == seqs[i]
+    empty = engine.seq4_decode(PackedSeq4.from_ascii([]))
+    assert len(empty) == 0
+    assert "k_unpack_seq4" in engine.kernel_stats()
+
+
+def test_flank_spans_seq4_matches_ascii_path(engine, oracle):
+    """BAM 4-bit input gives the ASCII path's result bit for bit (and hence the oracle's: the ASCII path is
+    checked against it above), one-shot and resident"""
+    from trgt_b200 import PackedSeq4, workload
+    w = workload.generate(60, 14, seed=31)
+    p4 = PackedSeq4.from_ascii([w.reads.get(r) for r in range(w.n_reads)])
+    spans_a, hits_a = engine.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+    spans_p, hits_p = engine.flank_spans_seq4(w.left, w.right, p4, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+    assert np.array_equal(spans_a, spans_p) and np.array_equal(hits_a, hits_p)
+    n_wfa = _check_flanks(oracle, w, spans_p, hits_p, w.scoring, w.min_flank_id_frac)
+    assert n_wfa > 20
+    b = engine.flank_upload_seq4(w.left, w.right, p4, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+    try:
+        engine.flank_run(b)
+        spans_r, hits_r = engine.flank_download(b, w.n_reads)
+    finally:
+        engine.flank_free(b)
+    assert np.array_equal(spans_a, spans_r) and np.array_equal(hits_a, hits_r)
+    # ragged: loci without reads, an empty batch
+    lro = np.array([0, 0, 3, 3, w.locus_read_off[1]], dtype=np.uint32)
+    from trgt_b200 import PackedSeqs
+    l4 = PackedSeqs.from_list([w.left.get(0)] * 4)
+    r4 = PackedSeqs.from_list([w.right.get(0)] * 4)
+    n0 = int(w.locus_read_off[1])
+    sub = PackedSeq4.from_ascii([w.reads.get(r) for r in range(n0)])
+    sp, _ = engine.flank_spans_seq4(l4, r4, sub, lro, w.scoring, w.min_flank_id_frac)
+    assert np.array_equal(sp, spans_a[:n0])
+    sp0, _ = engine.flank_spans_seq4(PackedSeqs.from_list([]), PackedSeqs.from_list([]), PackedSeq4.from_ascii([]),
+                                     np.zeros(1, dtype=np.uint32), w.scoring, w.min_flank_id_frac)
+    assert sp0.size == 0

@@ -335,3 +335,44 @@ def test_repair_consensus_tie_rules(oracle):
     # insertion: needs more than half of the members and must outnumber members without one (:57, :106-110)
     assert oracle.repair_consensus(b"ACGT", [b"ACTTGT", b"ACTTGT", b"ACGT"]) == b"ACTTGT"
     assert oracle.repair_consensus(b"ACGT", [b"ACTTGT", b"ACGT"]) == b"ACGT"
+
+
+# ------------------------------------------------------------- read clipping (next row) --
+
+_CLIP_READ = b"CGCTCGTTAAATCACG"
+_CLIP_CIGAR = "3=2D2=1X2=5I3="
+
+
+def _clip(oracle, bases, cigar, ref_pos, region):
+    """HiFiRead::clip_to_region on (bases, cigar): None or (bases, clipped ref_pos, clipped CIGAR text)"""
+    ops = oracle.encode_bam_cigar(cigar)
+    res = oracle.clip_cigar(ops, ref_pos, region)
+    if res is None:
+        return None
+    ref_start, qs, qe, words = res
+    packed = oracle.encode_seq4(bases)
+    text = "".join(f"{w >> 4}{oracle.BAM_OPS[w & 15]}" for w in words)
+    return oracle.decode_seq4(packed, qs, qe - qs), ref_start, text
+
+
+@pytest.mark.parametrize("bases,cigar,region,expect", [
+    (_CLIP_READ, _CLIP_CIGAR, (0, 10), None),                       # clip_region.rs:214-229
+    (_CLIP_READ, _CLIP_CIGAR, (23, 33), None),
+    (b"AAAAACGCTCGTTAAATCACGAAAAAAAAAA", "5S3=2D2=1X2=5I3=10S", (9, 23),   # :232-239: the original read
+     (b"AAAAACGCTCGTTAAATCACGAAAAAAAAAA", 10, "5S3=2D2=1X2=5I3=10S")),
+    (_CLIP_READ, _CLIP_CIGAR, (0, 15), (b"CGC", 10, "3=2D")),      # :242-254
+    (_CLIP_READ, _CLIP_CIGAR, (12, 17), (b"CTC", 12, "1=2D2=")),   # :257-269
+    (_CLIP_READ, _CLIP_CIGAR, (21, 22), (b"C", 21, "1=")),         # :272-284
+    (_CLIP_READ, _CLIP_CIGAR, (0, 17), (b"CGCTC", 10, "3=2D2=")),  # :287-299
+])
+def test_clip_to_region_reference_vectors(oracle, bases, cigar, region, expect):
+    assert _clip(oracle, bases, cigar, 10, region) == expect
+
+
+def test_seq4_alphabet(oracle):  # read.rs:104: htslib's "=ACMGRSVTWYHKDBN", first base in the high nibble
+    packed = bytes([0x12, 0x48, 0xF0])
+    assert oracle.decode_seq4(packed, 0, 5) == b"ACGTN"
+    assert oracle.decode_seq4(packed, 1, 4) == b"CGTN"
+    assert oracle.decode_seq4(bytes(range(256)), 0, 512) == bytes(
+        oracle.SEQ4_ALPHABET[(i >> 4) if j == 0 else (i & 15)] for i in range(256) for j in (0, 1))
+    assert oracle.decode_seq4(b"", 0, 0) == b""

@@ -5,10 +5,12 @@ include/trgt_engine.h), engine.py (ctypes binding and the host-side mirror of th
 find_tr_spans / align / get_dist_matrix / label_with_hmm), pipeline.py (the phase-structured pass
 bench.py times) and workload.py (synthetic HiFi inputs).  There is no CPU fallback.
 """
-from .engine import (Annotation, AnnotationBatch, CigarBatch, Engine, EXPORTS, PackedSeqs, TrgtError,
+from .engine import (Annotation, AnnotationBatch, CigarBatch, CLIP_DTYPE, Engine, EXPORTS, PackedSeq4, PackedSeqs,
+                     TrgtError,
                      decode_sam_cigar, load_library, HIT_DTYPE, SPAN_DTYPE, VIA_EXACT, VIA_NONE, VIA_WFA,
                      VIA_WFA_REJECTED)
 
-__all__ = ["Annotation", "AnnotationBatch", "CigarBatch", "Engine", "EXPORTS", "PackedSeqs", "TrgtError",
+__all__ = ["Annotation", "AnnotationBatch", "CigarBatch", "CLIP_DTYPE", "Engine", "EXPORTS", "PackedSeq4", "PackedSeqs",
+           "TrgtError",
            "decode_sam_cigar", "load_library", "HIT_DTYPE", "SPAN_DTYPE", "VIA_EXACT", "VIA_NONE", "VIA_WFA",
            "VIA_WFA_REJECTED"]

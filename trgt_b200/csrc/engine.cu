@@ -397,6 +397,7 @@ struct trgt_flank_batch {
   double frac = 0.7;
   DevBuf reads, read_off, lp, lp_off, rp, rp_off, locus_read_off, read_locus;
   DevBuf hits, spans, work, work2, ends, ctr, gring, gws;
+  DevBuf seq4, seq4_starts, seq4_len;  // BAM 4-bit input (trgt_flank_*_seq4): decoded into `reads` on the device
   uint32_t last_n_work = 0, last_n_tier2 = 0, last_n_wide = 0;
 };
 
@@ -482,7 +483,8 @@ void trgt_flank_free(trgt_engine_t *e, trgt_flank_batch_t *b) {
     if (e->one_flank == b) e->one_flank = nullptr;
   }
   DevBuf *all[] = {&b->reads, &b->read_off, &b->lp, &b->lp_off, &b->rp, &b->rp_off, &b->locus_read_off,
-                   &b->read_locus, &b->hits, &b->spans, &b->work, &b->work2, &b->ends, &b->ctr, &b->gring, &b->gws};
+                   &b->read_locus, &b->hits, &b->spans, &b->work, &b->work2, &b->ends, &b->ctr, &b->gring, &b->gws,
+                   &b->seq4, &b->seq4_starts, &b->seq4_len};
   for (auto *d : all) dev_free(*d);
   delete b;
 }
@@ -490,7 +492,8 @@ void trgt_flank_free(trgt_engine_t *e, trgt_flank_batch_t *b) {
 static int flank_upload_into(trgt_engine_t *e, trgt_flank_batch *b, const trgt_seqs_t *left_pieces,
                              const trgt_seqs_t *right_pieces, const trgt_seqs_t *reads,
                              const uint32_t *locus_read_offsets, uint32_t n_loci, trgt_scoring_t scoring,
-                             double min_flank_id_frac, bool defer_read_bytes = false) {
+                             double min_flank_id_frac, bool defer_read_bytes = false,
+                             bool skip_read_offsets = false) {
   TRY(check_seqs(e, left_pieces, "left_pieces"));
   TRY(check_seqs(e, right_pieces, "right_pieces"));
   TRY(check_seqs(e, reads, "reads"));
@@ -515,7 +518,8 @@ static int flank_upload_into(trgt_engine_t *e, trgt_flank_batch *b, const trgt_s
   if (defer_read_bytes) {  // the caller streams the read bytes in chunks (flank_oneshot_locked)
     static const uint64_t zero_off[1] = {0};
     TRY(dev_reserve(e, b->reads, (size_t)(reads->n ? reads->offsets[reads->n] : 0) + 16));
-    TRY(h2d(e, b->read_off, reads->n ? reads->offsets : zero_off, (size_t)(reads->n + 1) * sizeof(uint64_t)));
+    if (!skip_read_offsets)  // (seq4 input: the device derives the offsets from the read lengths)
+      TRY(h2d(e, b->read_off, reads->n ? reads->offsets : zero_off, (size_t)(reads->n + 1) * sizeof(uint64_t)));
   } else {
     TRY(upload_seqs(e, reads, b->reads, b->read_off));
   }
@@ -687,6 +691,153 @@ static int flank_oneshot_locked(trgt_engine_t *e, trgt_flank_batch *b, const trg
   return rc;
 }
 
+// ---- reads handed over as BAM 4-bit bases (trgt_seq4_t) ----
+
+#define SEQ4_PAD 16  // bytes of padding on both sides of the packed buffer (seq4_decode16 reads whole words)
+
+static int check_seq4(trgt_engine_t *e, const trgt_seq4_t *r, uint64_t *total_out, uint64_t *max_out) {
+  if (!r || (r->n && (!r->starts || !r->lengths))) return fail(e, TRGT_ERR_ARG, "reads: null seq4 set");
+  if (r->n > 0x7fffffffull) return fail(e, TRGT_ERR_ARG, "too many reads in one batch");
+  uint64_t total = 0, mx = 0, prev = 0;
+  for (uint64_t i = 0; i < r->n; i++) {
+    const uint64_t s0 = r->starts[i], len = r->lengths[i];
+    if (s0 < prev) return fail(e, TRGT_ERR_ARG, "reads: seq4 starts must be non-decreasing (read %llu)", (unsigned long long)i);
+    if (s0 + len > 2 * r->data_bytes) return fail(e, TRGT_ERR_ARG, "reads: seq4 read %llu runs past data_bytes", (unsigned long long)i);
+    prev = s0;
+    total += len;
+    if (len > mx) mx = len;
+  }
+  if (total && !r->data) return fail(e, TRGT_ERR_ARG, "reads: null data");
+  *total_out = total;
+  *max_out = mx;
+  return 0;
+}
+
+// device side of a seq4 read set: starts / lengths up, ASCII CSR offsets by a scan of the lengths;
+// the packed bytes themselves are copied by the caller (at once or in chunks)
+static int seq4_prepare(trgt_engine_t *e, const trgt_seq4_t *r, uint64_t total, DevBuf &d_seq4, DevBuf &d_starts,
+                        DevBuf &d_len, DevBuf &d_ascii, DevBuf &d_off) {
+  static const uint64_t zero64[1] = {0};
+  static const uint32_t zero32[1] = {0};
+  TRY(dev_reserve(e, d_seq4, (size_t)r->data_bytes + 2 * SEQ4_PAD));
+  TRY(h2d(e, d_starts, r->n ? r->starts : zero64, (size_t)(r->n ? r->n : 1) * sizeof(uint64_t)));
+  TRY(h2d(e, d_len, r->n ? r->lengths : zero32, (size_t)(r->n ? r->n : 1) * sizeof(uint32_t)));
+  CU(e, cudaMemsetAsync((uint8_t *)d_len.p + (size_t)r->n * sizeof(uint32_t), 0, sizeof(uint32_t), e->stream));
+  TRY(dev_reserve(e, d_ascii, (size_t)total + 16));
+  TRY(dev_reserve(e, d_off, (size_t)(r->n + 1) * sizeof(uint64_t) + 16));
+  TRY(exclusive_scan_u32(e, (const uint32_t *)d_len.p, (unsigned long long *)d_off.p, (size_t)r->n + 1));
+  return 0;
+}
+
+static int launch_unpack(trgt_engine_t *e, const DevBuf &d_seq4, const DevBuf &d_starts, const DevBuf &d_len,
+                         const DevBuf &d_off, DevBuf &d_ascii, uint32_t r0, uint32_t r1) {
+  if (r1 <= r0) return 0;
+  const int block = 256, wpb = block / 32;
+  int grid = 0;
+  TRY(persistent_grid(e, k_unpack_seq4, block, 0, &grid));
+  const uint32_t need = (r1 - r0 + wpb - 1) / wpb;
+  if ((uint32_t)grid > need) grid = (int)need;
+  LaunchScope ls(e, "k_unpack_seq4");
+  k_unpack_seq4<<<grid, block, 0, e->stream>>>((const uint8_t *)d_seq4.p + SEQ4_PAD, (const uint64_t *)d_starts.p,
+                                               (const uint32_t *)d_len.p, (const unsigned long long *)d_off.p, r0, r1,
+                                               (uint8_t *)d_ascii.p);
+  return check_launch(e, "k_unpack_seq4");
+}
+
+// upload of everything but the packed read bytes
+static int flank_upload_seq4_into(trgt_engine_t *e, trgt_flank_batch *b, const trgt_seqs_t *left_pieces,
+                                  const trgt_seqs_t *right_pieces, const trgt_seq4_t *reads,
+                                  const uint32_t *locus_read_offsets, uint32_t n_loci, trgt_scoring_t scoring,
+                                  double min_flank_id_frac) {
+  uint64_t total = 0, mx = 0;
+  TRY(check_seq4(e, reads, &total, &mx));
+  // flank_upload_into validates and sizes everything from a CSR view of the reads: build the ASCII
+  // offsets once on the host (never uploaded: the device derives its own by a scan of the lengths)
+  std::vector<uint64_t> offs((size_t)reads->n + 1);
+  offs[0] = 0;
+  for (uint64_t i = 0; i < reads->n; i++) offs[i + 1] = offs[i] + reads->lengths[i];
+  static const uint8_t dummy = 0;
+  trgt_seqs_t view;
+  view.data = &dummy; view.offsets = offs.data(); view.n = reads->n;
+  TRY(flank_upload_into(e, b, left_pieces, right_pieces, &view, locus_read_offsets, n_loci, scoring, min_flank_id_frac,
+                        /*defer_read_bytes=*/true, /*skip_read_offsets=*/true));
+  return seq4_prepare(e, reads, total, b->seq4, b->seq4_starts, b->seq4_len, b->reads, b->read_off);
+}
+
+int32_t trgt_flank_upload_seq4(trgt_engine_t *e, const trgt_seqs_t *left_pieces, const trgt_seqs_t *right_pieces,
+                               const trgt_seq4_t *reads, const uint32_t *locus_read_offsets, uint32_t n_loci,
+                               trgt_scoring_t scoring, double min_flank_id_frac, trgt_flank_batch_t **out) {
+  if (!e || !out) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  *out = nullptr;
+  trgt_flank_batch *b = new trgt_flank_batch();
+  int rc = flank_upload_seq4_into(e, b, left_pieces, right_pieces, reads, locus_read_offsets, n_loci, scoring,
+                                  min_flank_id_frac);
+  if (rc == 0 && reads->data_bytes) {
+    cudaError_t err = cudaMemcpyAsync((uint8_t *)b->seq4.p + SEQ4_PAD, reads->data, (size_t)reads->data_bytes,
+                                      cudaMemcpyHostToDevice, e->stream);
+    if (err != cudaSuccess) rc = fail(e, TRGT_ERR_CUDA, "seq4 upload failed: %s", cudaGetErrorString(err));
+  }
+  if (rc == 0) rc = launch_unpack(e, b->seq4, b->seq4_starts, b->seq4_len, b->read_off, b->reads, 0, b->n_reads);
+  if (rc == 0 && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(e, TRGT_ERR_CUDA, "seq4 decode failed");
+  if (rc != 0) {
+    trgt_flank_free(nullptr, b);
+    return rc;
+  }
+  *out = b;
+  return 0;
+}
+
+// One-shot phase A from BAM 4-bit reads: packed bytes go up in chunks of loci on the copy stream;
+// each chunk is decoded and searched as soon as it has landed.
+static int flank_oneshot_seq4_locked(trgt_engine_t *e, trgt_flank_batch *b, const trgt_seq4_t *reads,
+                                     const uint32_t *locus_read_offsets, uint32_t n_loci) {
+  CU(e, cudaSetDevice(e->device));
+  if (b->n_reads == 0) return 0;
+  const WfaSrc src = flank_src(b);
+  CU(e, cudaMemsetAsync(b->ctr.p, 0, sizeof(Counters), e->stream));
+  cudaEvent_t ready = get_event(e);
+  CU(e, cudaEventRecord(ready, e->stream));
+  CU(e, cudaStreamWaitEvent(e->copy_stream, ready, 0));
+  const uint64_t chunk_bytes = 96ull << 20;
+  std::vector<cudaEvent_t> evs;
+  // byte range of the packed buffer that reads [ra, rb) touch (starts are non-decreasing)
+  auto first_byte = [&](uint32_t r) { return r < b->n_reads ? reads->starts[r] >> 1 : reads->data_bytes; };
+  uint64_t sent = 0;  // bytes [0, sent) are queued
+  uint32_t l0 = 0;
+  while (l0 < n_loci) {
+    uint32_t l1 = l0 + 1;
+    const uint64_t b0 = first_byte(locus_read_offsets[l0]);
+    while (l1 < n_loci && first_byte(locus_read_offsets[l1 + 1]) - b0 <= chunk_bytes) l1++;
+    const uint32_t ra = locus_read_offsets[l0], rb = locus_read_offsets[l1];
+    // everything up to the end of the chunk's last read (a later read never starts before an earlier one,
+    // but an earlier read may end after a later one starts: take the maximum end)
+    uint64_t end = sent;
+    for (uint32_t r = ra; r < rb; r++) {
+      const uint64_t e_r = (reads->starts[r] + reads->lengths[r] + 1) >> 1;
+      if (e_r > end) end = e_r;
+    }
+    if (l1 == n_loci) end = reads->data_bytes > end ? reads->data_bytes : end;
+    if (end > reads->data_bytes) end = reads->data_bytes;
+    if (end > sent) {
+      CU(e, cudaMemcpyAsync((uint8_t *)b->seq4.p + SEQ4_PAD + sent, reads->data + sent, (size_t)(end - sent),
+                            cudaMemcpyHostToDevice, e->copy_stream));
+      sent = end;
+    }
+    cudaEvent_t ev = get_event(e);
+    evs.push_back(ev);
+    CU(e, cudaEventRecord(ev, e->copy_stream));
+    CU(e, cudaStreamWaitEvent(e->stream, ev, 0));
+    TRY(launch_unpack(e, b->seq4, b->seq4_starts, b->seq4_len, b->read_off, b->reads, ra, rb));
+    TRY(flank_launch_locate(e, b, src, l0, l1));
+    l0 = l1;
+  }
+  const int rc = flank_finish(e, b, src);
+  e->event_pool.push_back(ready);
+  for (auto ev : evs) e->event_pool.push_back(ev);
+  return rc;
+}
+
 int32_t trgt_flank_run(trgt_engine_t *e, trgt_flank_batch_t *b) {
   if (!e || !b) return TRGT_ERR_ARG;
   std::lock_guard<std::mutex> lk(e->mu);
@@ -723,6 +874,86 @@ int32_t trgt_flank_spans(trgt_engine_t *e, const trgt_seqs_t *left_pieces, const
                         min_flank_id_frac, /*defer_read_bytes=*/true));
   TRY(flank_oneshot_locked(e, e->one_flank, reads, locus_read_offsets, n_loci));
   return flank_download_locked(e, e->one_flank, spans_out, hits_out);
+}
+
+int32_t trgt_flank_spans_seq4(trgt_engine_t *e, const trgt_seqs_t *left_pieces, const trgt_seqs_t *right_pieces,
+                              const trgt_seq4_t *reads, const uint32_t *locus_read_offsets, uint32_t n_loci,
+                              trgt_scoring_t scoring, double min_flank_id_frac, trgt_span_t *spans_out,
+                              trgt_flank_hit_t *hits_out) {
+  if (!e) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->one_flank) e->one_flank = new trgt_flank_batch();
+  TRY(flank_upload_seq4_into(e, e->one_flank, left_pieces, right_pieces, reads, locus_read_offsets, n_loci, scoring,
+                             min_flank_id_frac));
+  TRY(flank_oneshot_seq4_locked(e, e->one_flank, reads, locus_read_offsets, n_loci));
+  return flank_download_locked(e, e->one_flank, spans_out, hits_out);
+}
+
+int32_t trgt_seq4_decode(trgt_engine_t *e, const trgt_seq4_t *reads, uint8_t *ascii_out, uint64_t *ascii_offsets_out) {
+  if (!e || !ascii_offsets_out) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(e, cudaSetDevice(e->device));
+  uint64_t total = 0, mx = 0;
+  TRY(check_seq4(e, reads, &total, &mx));
+  if (total && !ascii_out) return fail(e, TRGT_ERR_ARG, "ascii_out is null");
+  DevBuf *d = e->d_ed;  // scratch shared with trgt_edit_dist (calls on one engine serialise)
+  TRY(seq4_prepare(e, reads, total, d[0], d[1], d[2], d[3], d[4]));
+  if (reads->data_bytes)
+    CU(e, cudaMemcpyAsync((uint8_t *)d[0].p + SEQ4_PAD, reads->data, (size_t)reads->data_bytes, cudaMemcpyHostToDevice, e->stream));
+  TRY(launch_unpack(e, d[0], d[1], d[2], d[4], d[3], 0, (uint32_t)reads->n));
+  if (total) CU(e, cudaMemcpyAsync(ascii_out, d[3].p, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaMemcpyAsync(ascii_offsets_out, d[4].p, (size_t)(reads->n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int32_t trgt_clip_reads(trgt_engine_t *e, const uint32_t *cigar_ops, const uint64_t *cigar_offsets,
+                        const int64_t *ref_starts, uint64_t n_reads, const int64_t *regions,
+                        const uint32_t *locus_read_offsets, uint32_t n_loci, trgt_clip_t *clips_out) {
+  if (!e) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(e, cudaSetDevice(e->device));
+  if (n_reads == 0) return 0;
+  if (!cigar_offsets || !ref_starts || !regions || !locus_read_offsets || !clips_out || n_loci == 0)
+    return fail(e, TRGT_ERR_ARG, "trgt_clip_reads: null argument");
+  if (n_reads > 0x7fffffffull) return fail(e, TRGT_ERR_ARG, "too many reads in one batch");
+  for (uint64_t i = 0; i < n_reads; i++)
+    if (cigar_offsets[i + 1] < cigar_offsets[i]) return fail(e, TRGT_ERR_ARG, "cigar_offsets not monotone");
+  for (uint32_t l = 0; l < n_loci; l++)
+    if (locus_read_offsets[l + 1] < locus_read_offsets[l]) return fail(e, TRGT_ERR_ARG, "locus_read_offsets not monotone");
+  if (locus_read_offsets[0] != 0 || locus_read_offsets[n_loci] != n_reads)
+    return fail(e, TRGT_ERR_ARG, "locus_read_offsets must cover all reads");
+  const uint64_t n_ops = cigar_offsets[n_reads];
+  if (n_ops && !cigar_ops) return fail(e, TRGT_ERR_ARG, "cigar_ops is null");
+  DevBuf *d = e->d_ed;
+  TRY(h2d(e, d[0], cigar_ops, (size_t)n_ops * sizeof(uint32_t)));
+  TRY(h2d(e, d[1], cigar_offsets, (size_t)(n_reads + 1) * sizeof(uint64_t)));
+  TRY(h2d(e, d[2], ref_starts, (size_t)n_reads * sizeof(int64_t)));
+  TRY(h2d(e, d[3], regions, (size_t)n_loci * 2 * sizeof(int64_t)));
+  TRY(h2d(e, d[4], locus_read_offsets, ((size_t)n_loci + 1) * sizeof(uint32_t)));
+  // read -> locus map and the clips share one buffer: [n_reads] uint32 (padded to 16 B) then trgt_clip_t[n_reads]
+  const size_t map_bytes = (((size_t)n_reads + 1) * sizeof(uint32_t) + 15) & ~(size_t)15;
+  TRY(dev_reserve(e, d[5], map_bytes + (size_t)n_reads * sizeof(trgt_clip_t)));
+  uint32_t *d_map = (uint32_t *)d[5].p;
+  trgt_clip_t *d_clips = (trgt_clip_t *)((uint8_t *)d[5].p + map_bytes);
+  {
+    LaunchScope ls(e, "k_expand_offsets");
+    k_expand_offsets<<<(n_loci + 255) / 256, 256, 0, e->stream>>>((const uint32_t *)d[4].p, n_loci, d_map);
+    TRY(check_launch(e, "k_expand_offsets"));
+  }
+  {
+    int grid = 0;
+    TRY(persistent_grid(e, k_clip_cigar, 256, 0, &grid));
+    const uint32_t need = (uint32_t)((n_reads + 255) / 256);
+    if ((uint32_t)grid > need) grid = (int)need;
+    LaunchScope ls(e, "k_clip_cigar");
+    k_clip_cigar<<<grid, 256, 0, e->stream>>>((const uint32_t *)d[0].p, (const uint64_t *)d[1].p, (const long long *)d[2].p,
+                                              d_map, (const long long *)d[3].p, (uint32_t)n_reads, d_clips);
+    TRY(check_launch(e, "k_clip_cigar"));
+  }
+  CU(e, cudaMemcpyAsync(clips_out, d_clips, (size_t)n_reads * sizeof(trgt_clip_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  return 0;
 }
 
 /* device pointers of a resident flank batch (for device-side consumers such as the pipeline) */

@@ -1,5 +1,7 @@
 // kernels.cuh -- sm_100a kernels of the tandem-repeat DP engine (included by engine.cu only).
 //
+//   producer k_clip_cigar      clip_cigar + clip_to_region's query range    clip_region.rs:19-38,105-186
+//            k_unpack_seq4     BAM 4-bit bases -> the ASCII reads of phase A   read.rs:104
 //   phase A  k_flank_exact     exact flank search by index probes          span_locater.rs:10-12
 //            k_flank_band      banded on-chip WFA fallback for the misses  span_locater.rs:14-25
 //            k_wfa_score       WFA pass 1 (ring, no history) wfaligner.rs:503-528 (flank), :489 (e2e)
@@ -14,6 +16,7 @@
 #include <stdint.h>
 
 #include "../../include/trgt_engine.h"
+#include "clip_core.h"
 #include "consensus_core.h"
 #include "coop.h"
 #include "hmm_core.h"
@@ -82,6 +85,34 @@ __global__ void k_expand_offsets(const uint32_t *__restrict__ off, uint32_t n_gr
   const uint32_t gsz = gridDim.x * blockDim.x;
   for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gsz)
     for (uint32_t i = off[g]; i < off[g + 1]; i++) out[i] = g;
+}
+
+// ------------------------------------------------------------------ producer: clip + decode ---
+
+// clip_reads for a chunk of loci (tr.rs:186-196): one thread per read walks its CIGAR twice (reference
+// end, then the clip), a few dozen words.  Bytes per read: 4 * n_ops in, 48 out.
+__global__ void __launch_bounds__(256)
+k_clip_cigar(const uint32_t *__restrict__ ops, const uint64_t *__restrict__ op_off,
+             const long long *__restrict__ ref_starts, const uint32_t *__restrict__ read_locus,
+             const long long *__restrict__ regions, uint32_t n_reads, trgt_clip_t *__restrict__ out) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gsz) {
+    const uint32_t l = read_locus[r];
+    out[r] = clip_cigar_one(ops + op_off[r], (uint32_t)(op_off[r + 1] - op_off[r]), ref_starts[r], regions[2 * l],
+                            regions[2 * l + 1]);
+  }
+}
+
+// Reads r0..r1-1 from BAM 4-bit bases to ASCII, a warp per read: every lane turns 8-9 packed bytes
+// into one aligned 16-byte store (seq4_unpack_read).  HBM-bound: 0.5 B read + 1 B written per base.
+__global__ void __launch_bounds__(256)
+k_unpack_seq4(const uint8_t *__restrict__ data, const uint64_t *__restrict__ starts,
+              const uint32_t *__restrict__ lengths, const unsigned long long *__restrict__ out_off, uint32_t r0,
+              uint32_t r1, uint8_t *__restrict__ out) {
+  const WarpGroup g;
+  const uint32_t wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  for (uint32_t r = r0 + blockIdx.x * wpb + warp; r < r1; r += gridDim.x * wpb)
+    seq4_unpack_read(g, data, starts[r], lengths[r], out, (uint64_t)out_off[r]);
 }
 
 // ------------------------------------------------------------------ phase A: flank location ---

@@ -31,6 +31,11 @@ class _Seqs(C.Structure):
     _fields_ = [("data", C.c_void_p), ("offsets", C.c_void_p), ("n", C.c_uint64)]
 
 
+class _Seq4(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_bytes", C.c_uint64), ("starts", C.c_void_p), ("lengths", C.c_void_p),
+                ("n", C.c_uint64)]
+
+
 class _Scoring(C.Structure):
     _fields_ = [("mismatch", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32)]
 
@@ -53,6 +58,10 @@ class _Annotations(C.Structure):
                 ("paths", C.POINTER(C.c_uint32))]
 
 
+CLIP_DTYPE = np.dtype([("ref_start", np.int64), ("query_start", np.uint64), ("query_end", np.uint64),
+                       ("first_op", np.uint32), ("n_ops", np.uint32), ("first_word", np.uint32),
+                       ("last_word", np.uint32), ("status", np.int32)], align=True)
+SEQ4_ALPHABET = b"=ACMGRSVTWYHKDBN"
 SPAN_DTYPE = np.dtype([("found", np.int32), ("start", np.uint32), ("end", np.uint32)])
 HIT_DTYPE = np.dtype([("via", np.int32), ("matches", np.int32), ("score", np.int32),
                       ("start", np.uint32), ("end", np.uint32)])
@@ -63,6 +72,7 @@ EXPORTS = [
     "trgt_engine_stream", "trgt_engine_sm_count", "trgt_engine_sync", "trgt_engine_set_workspace_budget",
     "trgt_engine_set_flank_band_budget",
     "trgt_host_alloc", "trgt_host_free",
+    "trgt_clip_reads", "trgt_seq4_decode", "trgt_flank_spans_seq4", "trgt_flank_upload_seq4",
     "trgt_flank_spans", "trgt_align_e2e", "trgt_consensus", "trgt_edit_dist", "trgt_hmm_label",
     "trgt_flank_upload", "trgt_flank_run", "trgt_flank_download", "trgt_flank_free", "trgt_flank_device_views",
     "trgt_flank_fallback_counts",
@@ -112,6 +122,11 @@ def load_library(build: bool = True):
     sp = C.POINTER(_Seqs)
     L.trgt_flank_spans.argtypes = [vp, sp, sp, sp, vp, u32, _Scoring, C.c_double, vp, vp]
     L.trgt_flank_upload.argtypes = [vp, sp, sp, sp, vp, u32, _Scoring, C.c_double, C.POINTER(vp)]
+    s4 = C.POINTER(_Seq4)
+    L.trgt_flank_spans_seq4.argtypes = [vp, sp, sp, s4, vp, u32, _Scoring, C.c_double, vp, vp]
+    L.trgt_flank_upload_seq4.argtypes = [vp, sp, sp, s4, vp, u32, _Scoring, C.c_double, C.POINTER(vp)]
+    L.trgt_seq4_decode.argtypes = [vp, s4, vp, vp]
+    L.trgt_clip_reads.argtypes = [vp, vp, vp, vp, u64, vp, vp, u32, vp]
     L.trgt_flank_run.argtypes = [vp, vp]
     L.trgt_flank_download.argtypes = [vp, vp, vp, vp]
     L.trgt_flank_free.argtypes = [vp, vp]
@@ -169,6 +184,51 @@ class PackedSeqs:
 
     def get(self, i: int) -> bytes:
         return self.data[int(self.offsets[i]):int(self.offsets[i + 1])].tobytes()
+
+    def ref(self):
+        return C.byref(self._c)
+
+
+class PackedSeq4:
+    """Reads as BAM stores them (trgt_seq4_t): 4-bit codes of "=ACMGRSVTWYHKDBN", two bases per byte, first
+    base in the high nibble; read i = bases [starts[i], starts[i]+lengths[i]) of data."""
+
+    def __init__(self, data: np.ndarray, starts: np.ndarray, lengths: np.ndarray):
+        self.data = np.ascontiguousarray(data, dtype=np.uint8)
+        self.starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        self.lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
+        assert self.starts.shape == self.lengths.shape and self.starts.ndim == 1
+        self._c = _Seq4(self.data.ctypes.data if self.data.size else None, self.data.size,
+                        self.starts.ctypes.data if self.starts.size else None,
+                        self.lengths.ctypes.data if self.lengths.size else None, self.starts.size)
+
+    @classmethod
+    def from_ascii(cls, seqs: Sequence[bytes], odd_starts: bool = True) -> "PackedSeq4":
+        """Encode ASCII reads the way consecutive BAM records would hold them (test helper; unknown letters
+        become N).  With odd_starts every other read begins in the low nibble of a byte, as a clip at an
+        odd query position does."""
+        lut = np.full(256, 15, dtype=np.uint8)
+        for i, ch in enumerate(SEQ4_ALPHABET):
+            lut[ch] = i
+        nibs, starts, pos = [], [], 0
+        for k, s_ in enumerate(seqs):
+            if odd_starts and (k & 1) and (pos & 1) == 0:
+                nibs.append(np.zeros(1, dtype=np.uint8))
+                pos += 1
+            elif (not odd_starts or not (k & 1)) and (pos & 1):
+                nibs.append(np.zeros(1, dtype=np.uint8))
+                pos += 1
+            starts.append(pos)
+            nibs.append(lut[np.frombuffer(bytes(s_), dtype=np.uint8)])
+            pos += len(s_)
+        flat = np.concatenate(nibs) if nibs else np.zeros(0, dtype=np.uint8)
+        if flat.size & 1:
+            flat = np.concatenate([flat, np.zeros(1, dtype=np.uint8)])
+        data = ((flat[0::2] << 4) | flat[1::2]).astype(np.uint8)
+        return cls(data, np.array(starts, dtype=np.uint64), np.array([len(s_) for s_ in seqs], dtype=np.uint32))
+
+    def __len__(self):
+        return self.starts.size
 
     def ref(self):
         return C.byref(self._c)
@@ -324,6 +384,44 @@ class Engine:
         self._check(rc, "trgt_flank_spans")
         return spans, hits
 
+    def flank_spans_seq4(self, left: PackedSeqs, right: PackedSeqs, reads: PackedSeq4,
+                         locus_read_offsets: np.ndarray, scoring=(2, 5, 1), min_flank_id_frac: float = 0.7,
+                         want_hits: bool = True, spans_out: Optional[np.ndarray] = None,
+                         hits_out: Optional[np.ndarray] = None):
+        """trgt_flank_spans_seq4: the same on reads handed over as BAM 4-bit bases"""
+        lro = np.ascontiguousarray(locus_read_offsets, dtype=np.uint32)
+        n_reads = len(reads)
+        spans = spans_out if spans_out is not None else np.zeros(n_reads, dtype=SPAN_DTYPE)
+        hits = hits_out if hits_out is not None else (np.zeros(2 * n_reads, dtype=HIT_DTYPE) if want_hits else None)
+        rc = self._L.trgt_flank_spans_seq4(self._h, left.ref(), right.ref(), reads.ref(), lro.ctypes.data, len(left),
+                                           _Scoring(*scoring), float(min_flank_id_frac), spans.ctypes.data,
+                                           hits.ctypes.data if hits is not None else None)
+        self._check(rc, "trgt_flank_spans_seq4")
+        return spans, hits
+
+    def seq4_decode(self, reads: PackedSeq4) -> PackedSeqs:
+        """rec.seq().as_bytes() (read.rs:104) of the clipped bases, on the device"""
+        total = int(reads.lengths.sum(dtype=np.uint64))
+        out = np.zeros(max(1, total), dtype=np.uint8)
+        offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+        self._check(self._L.trgt_seq4_decode(self._h, reads.ref(), out.ctypes.data, offs.ctypes.data), "trgt_seq4_decode")
+        return PackedSeqs(out[:total], offs)
+
+    def clip_reads(self, cigar_ops: np.ndarray, cigar_offsets: np.ndarray, ref_starts: np.ndarray,
+                   regions: np.ndarray, locus_read_offsets: np.ndarray) -> np.ndarray:
+        """clip_reads (tr.rs:186-196 -> clip_region.rs:19-186) for a chunk of loci -> CLIP_DTYPE[n_reads]"""
+        ops = np.ascontiguousarray(cigar_ops, dtype=np.uint32)
+        offs = np.ascontiguousarray(cigar_offsets, dtype=np.uint64)
+        rs = np.ascontiguousarray(ref_starts, dtype=np.int64)
+        reg = np.ascontiguousarray(regions, dtype=np.int64).reshape(-1)
+        lro = np.ascontiguousarray(locus_read_offsets, dtype=np.uint32)
+        n = rs.size
+        out = np.zeros(max(1, n), dtype=CLIP_DTYPE)
+        self._check(self._L.trgt_clip_reads(self._h, ops.ctypes.data if ops.size else None, offs.ctypes.data,
+                                            rs.ctypes.data, n, reg.ctypes.data, lro.ctypes.data, lro.size - 1,
+                                            out.ctypes.data), "trgt_clip_reads")
+        return out[:n]
+
     def find_tr_spans(self, loci: Sequence[Tuple[bytes, bytes, Sequence[bytes]]], search_flank_len: int = 250,
                       min_flank_id_frac: float = 0.7, scoring=(2, 5, 1), return_hits: bool = False):
         """find_tr_spans (span_locater.rs:32-68) for many loci: loci = [(lf, rf, reads)].
@@ -352,6 +450,15 @@ class Engine:
                                               len(left), _Scoring(*scoring), float(min_flank_id_frac), C.byref(b)),
                     "trgt_flank_upload")
         self.sync()  # the host arrays may go away after this call
+        return b
+
+    def flank_upload_seq4(self, left: PackedSeqs, right: PackedSeqs, reads: PackedSeq4, locus_read_offsets: np.ndarray,
+                          scoring=(2, 5, 1), min_flank_id_frac: float = 0.7):
+        lro = np.ascontiguousarray(locus_read_offsets, dtype=np.uint32)
+        b = C.c_void_p()
+        self._check(self._L.trgt_flank_upload_seq4(self._h, left.ref(), right.ref(), reads.ref(), lro.ctypes.data,
+                                                   len(left), _Scoring(*scoring), float(min_flank_id_frac), C.byref(b)),
+                    "trgt_flank_upload_seq4")
         return b
 
     def flank_run(self, b):
