@@ -45,6 +45,8 @@ def parse_args():
                     help="profiling aid: skip the end-to-end driver so that every launch is a whole-shard launch")
     ap.add_argument("--chunk-loci", type=int, default=15625, help="loci per chunk of the end-to-end driver")
     ap.add_argument("--host-threads", type=int, default=4, help="host threads (one engine each) of the e2e driver")
+    ap.add_argument("--e2e-input", default="seq4", choices=["seq4", "ascii"],
+                    help="how the e2e driver hands reads to phase A: BAM 4-bit bases (trgt_flank_spans_seq4) or ASCII")
     return ap.parse_args()
 
 
@@ -180,7 +182,9 @@ def kernel_bytes(name: str, w, hp, res) -> float | None:
     read_len = np.diff(w.reads.offsets.astype(np.int64)).astype(np.float64)
     read_bytes = float(read_len.sum())
     g = res.glue
-    if name == "k_flank_exact":   # every read base once, both pieces once per locus, one hit per (read, flank)
+    if name == "k_unpack_seq4":   # half a byte in and one byte out per base, starts / lengths / offsets per read
+        return 1.5 * read_bytes + 28.0 * n_reads
+    if name in ("k_flank_exact", "k_flank_exact_t"):   # every read base once, both pieces once per locus, one hit per (read, flank)
         return read_bytes + 2.0 * P * w.n_loci + 2 * 20.0 * n_reads + 8.0 * n_reads
     if name in ("k_flank_band", "k_flank_band2", "k_flank_band_wide") and res.hits is not None:
         via = res.hits["via"].reshape(-1, 2)
@@ -242,13 +246,16 @@ def run_b200(args):
     w = workload.generate(args.loci, args.depth, locus_begin=rank * args.loci, alloc_reads=eng.pinned_array,
                           name="genome-wide-synthetic")
     t_gen = time.perf_counter() - t_gen
+    use_seq4 = args.e2e_input == "seq4"
+    if use_seq4:  # untimed set-up: the reads as BAM records hold them, in pinned memory
+        w.pack_seq4(alloc=eng.pinned_array)
     hp = HotPath(eng, w, want_hits=True, pinned_outputs=True)  # hits: to count the fallback pairs for the roofline
 
     # end-to-end driver: chunks of loci through `host_threads` engines on this GPU
     engines = [eng] + [trgt_b200.Engine(device=local_rank) for _ in range(max(1, args.host_threads) - 1)]
     # host cores are shared by all ranks of the box and all host threads of a rank
     glue_threads = max(1, host_cores() // max(1, world * len(engines)))
-    chp = ChunkedHotPath(engines, w, chunk_loci=args.chunk_loci, glue_threads=glue_threads)
+    chp = ChunkedHotPath(engines, w, chunk_loci=args.chunk_loci, glue_threads=glue_threads, use_seq4=use_seq4)
 
     # ---- warm-up: end-to-end passes (also builds the resident batches) ----
     res = None
@@ -275,6 +282,11 @@ def run_b200(args):
     dev_ms = ev0.elapsed_time(ev1) / max(1, args.steps)
     launches = (eng.launches() - launches0) // max(1, args.steps)
     stats = eng.kernel_stats()
+    unpack_stat = None
+    if use_seq4:  # outside the timed region: one whole-shard launch of the e2e path's decode kernel, for its roofline entry
+        fb4 = eng.flank_upload_seq4(w.left, w.right, w.reads4, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+        eng.flank_free(fb4)
+        unpack_stat = eng.kernel_stats().get("k_unpack_seq4")
     eng.set_profiling(False)
     res_resident = hp.download_resident()
     dev_ms = max_over_ranks(dev_ms)
@@ -349,6 +361,12 @@ def run_b200(args):
         kernels[name] = {"launches_per_step": n / max(1, args.steps), "ms_per_launch": per,
                          "share": None, "algorithmic_bytes": b,
                          "achieved_gbs": (b / (per * 1e-3) / 1e9) if (b and per > 0) else None}
+    if unpack_stat and unpack_stat[0]:  # not part of the resident step (launches_per_step 0): runs per chunk in the e2e pass
+        per = unpack_stat[1] / unpack_stat[0]
+        b = kernel_bytes("k_unpack_seq4", w, hp, res_resident)
+        kernels["k_unpack_seq4"] = {"launches_per_step": 0.0, "ms_per_launch": per, "share": None, "algorithmic_bytes": b,
+                                    "achieved_gbs": b / (per * 1e-3) / 1e9 if per > 0 else None,
+                                    "note": "e2e path only: one whole-shard launch timed outside the resident step"}
     tot_ms = sum(v["ms_per_launch"] * v["launches_per_step"] for v in kernels.values())
     for v in kernels.values():
         v["share"] = v["ms_per_launch"] * v["launches_per_step"] / tot_ms if tot_ms else None
@@ -373,7 +391,7 @@ def run_b200(args):
         rate, n, dt, ref = cpu_pass_rate(w, cores, args.cpu_seconds, args.loci)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {n} loci of the shard ({n * args.depth} reads), one pass in {dt:.1f} s, all host cores"}
-        small = HotPath(eng, w.head(n), want_hits=False, pinned_outputs=False)
+        small = HotPath(eng, w.head(n), want_hits=False, pinned_outputs=False, use_seq4=use_seq4)
         compare_with_oracle(small.run_e2e(), ref)
         parity = {"checked_loci": n, "result": "bit-exact vs oracle (spans, CIGARs, scores, MC, MS, AP)"}
 
@@ -409,6 +427,7 @@ def run_b200(args):
         "config": workload_config(args, world), "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),
+                "reads_in": "BAM 4-bit bases (trgt_flank_spans_seq4), decoded on the device" if use_seq4 else "ASCII (trgt_flank_spans)",
                 "glue_threads": glue_threads, "phase_ms_summed_over_host_threads": e2e_phases},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "kernels": kernels,
         "wfa_fallback_pairs": hp.n_wfa(), "flank_fallback_counts": dict(zip(("second_tier", "wide_band", "full_width"), hp.fallback_counts())),

@@ -227,4 +227,25 @@ int emu_e2e_narrow(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x
   return 0;
 }
 
+// exact search by one lane per pair (flank_exact_thread): copies and index built by `lanes` lanes;
+// text must carry 16 readable bytes on both sides
+int emu_flank_exact_thread(const uint8_t *p, int P, const uint8_t *t, int T, int lanes) {
+  std::vector<uint16_t> slot(TRGT_KIDX_SLOTS);
+  alignas(16) static thread_local uint8_t copies[FXT_COPIES * FXT_STRIDE];
+  memset(copies, 0xEE, sizeof copies);
+  const KmerIndex idx{slot.data()};
+  if (lanes == 0) {
+    SerialGroup g;
+    fxt_build_copies(g, p, P, copies);
+    kidx_build(g, idx, copies + 8, P);
+  } else {
+    uint8_t *cp = copies;
+    trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &g) {
+      fxt_build_copies(g, p, P, cp);
+      kidx_build(g, idx, cp + 8, P);
+    });
+  }
+  return flank_exact_thread(idx, copies, P, t, T);
+}
+
 }  // extern "C"

@@ -541,3 +541,42 @@ def test_seq4_unpack_core(emul, oracle, lanes):
         assert (out[ob + int(offs[n]):ob + int(offs[n]) + 16] == 0x7E).all() and (out[:ob] == 0x7E).all()
         for i, s_ in enumerate(seqs):
             assert oracle.decode_seq4(packed, starts[i], len(s_)) == s_
+
+
+@pytest.mark.parametrize("lanes", [0, 32])
+def test_flank_exact_thread_core(emul, lanes):
+    """Exact search with one lane per (read, flank) pair: shifted piece copies + aligned 16-byte compares,
+    at every text alignment, incl. repetitive pieces, several occurrences (the first one counts), an
+    occurrence at the very start / end of the read and near misses."""
+    import numpy as np
+    emul.emu_flank_exact_thread.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    rng = random.Random(900 + lanes)
+    hits = 0
+    for it in range(1200 if lanes == 0 else 150):
+        P = rng.choice([16, 17, 31, 60, 200, 250, 250, 250, 256])
+        kind = rng.random()
+        if kind < 0.3:
+            unit = rnd(rng, rng.randint(1, 9))
+            p = mutate(rng, (unit * (P // len(unit) + 1))[:P], rng.choice([0, 0.02]))[:P]
+            if len(p) < 16:
+                continue
+        else:
+            p = rnd(rng, P)
+        pre, suf = rnd(rng, rng.choice([0, 1, 7, rng.randint(0, 700)])), rnd(rng, rng.choice([0, 1, rng.randint(0, 700)]))
+        r = rng.random()
+        body = p if r < 0.6 else mutate(rng, p, 0.01) if r < 0.8 else p[:-1] + (b"A" if p[-1:] != b"A" else b"C")
+        if rng.random() < 0.15:
+            body += rnd(rng, rng.randint(0, 30)) + p
+        if kind < 0.3 and rng.random() < 0.5:
+            pre += p[len(p) // 2:]
+        t = pre + body + suf
+        if rng.random() < 0.05:
+            t = t[:rng.randint(1, len(t))]
+        pb = np.frombuffer(p + b"\0" * 16, dtype=np.uint8).copy()
+        buf = np.full(len(t) + 64, 0x23, dtype=np.uint8)
+        off = 16 + rng.randint(0, 15)
+        buf[off:off + len(t)] = np.frombuffer(t, dtype=np.uint8)
+        got = emul.emu_flank_exact_thread(pb.ctypes.data, len(p), buf.ctypes.data + off, len(t), lanes)
+        assert got == t.find(p), (it, P, len(t), off)
+        hits += got >= 0
+    assert hits > 50

@@ -122,9 +122,9 @@ TRGT_HD uint32_t seq4_decode4(uint32_t g) {
   const uint32_t sel = g & 0x7777u;
   const uint32_t lo = __byte_perm((uint32_t)TRGT_SEQ4_LO, (uint32_t)(TRGT_SEQ4_LO >> 32), sel);
   const uint32_t hi = __byte_perm((uint32_t)TRGT_SEQ4_HI, (uint32_t)(TRGT_SEQ4_HI >> 32), sel);
-  // bit 3 of code i -> sign bit of byte i -> whole byte (prmt sign replication)
-  const uint32_t x = ((g & 0x8u) << 4) | ((g & 0x80u) << 8) | ((g & 0x800u) << 12) | ((g & 0x8000u) << 16);
-  const uint32_t m = __byte_perm(x, 0u, 0xBA98u);
+  // bit 3 of code i -> bit 0 of byte i -> the whole byte (no carries: 1 * 0xFF fits a byte)
+  const uint32_t x = ((g & 0x8u) >> 3) | ((g & 0x80u) << 1) | ((g & 0x800u) << 5) | ((g & 0x8000u) << 9);
+  const uint32_t m = x * 0xFFu;
   return (lo & ~m) | (hi & m);
 #else
   return (uint32_t)seq4_letter(g & 15u) | ((uint32_t)seq4_letter((g >> 4) & 15u) << 8) |

@@ -392,7 +392,7 @@ uint64_t trgt_engine_launches(const trgt_engine_t *e) { return e ? e->launches :
 
 struct trgt_flank_batch {
   uint32_t n_loci = 0, n_reads = 0;
-  int Pmax = 0, Tmax = 0;
+  int Pmax = 0, Pmin = 0, Tmax = 0;
   trgt_scoring_t scoring{2, 5, 1};
   double frac = 0.7;
   DevBuf reads, read_off, lp, lp_off, rp, rp_off, locus_read_off, read_locus;
@@ -511,6 +511,16 @@ static int flank_upload_into(trgt_engine_t *e, trgt_flank_batch *b, const trgt_s
   b->n_loci = n_loci;
   b->n_reads = (uint32_t)reads->n;
   b->Pmax = (int)pm;
+  {
+    uint64_t mn = pm;
+    for (uint32_t l = 0; l < n_loci; l++) {
+      const uint64_t a = left_pieces->offsets[l + 1] - left_pieces->offsets[l];
+      const uint64_t c = right_pieces->offsets[l + 1] - right_pieces->offsets[l];
+      if (a < mn) mn = a;
+      if (c < mn) mn = c;
+    }
+    b->Pmin = (int)mn;
+  }
   b->Tmax = (int)tm;
   b->scoring = scoring;
   b->frac = min_flank_id_frac;
@@ -563,7 +573,18 @@ int32_t trgt_flank_upload(trgt_engine_t *e, const trgt_seqs_t *left_pieces, cons
 static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src, uint32_t l0, uint32_t l1) {
   if (l1 <= l0) return 0;
   const int block = 32;  // one warp per CTA, one locus at a time per warp
-  {
+  if (b->Pmin >= 16 && b->Pmax <= FXT_PMAX) {  // usual piece lengths: one lane per (read, flank) pair
+    const int tb = 32 * FXT_WARPS;
+    int grid = 0;
+    TRY(persistent_grid(e, k_flank_exact_t, tb, 0, &grid));
+    const uint32_t need = (l1 - l0 + FXT_WARPS - 1) / FXT_WARPS;
+    if ((uint32_t)grid > need) grid = (int)need;
+    LaunchScope ls(e, "k_flank_exact_t");
+    k_flank_exact_t<<<grid, tb, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
+                                                (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p,
+                                                (Counters *)b->ctr.p);
+    TRY(check_launch(e, "k_flank_exact_t"));
+  } else {
     int grid = 0;
     TRY(persistent_grid(e, k_flank_exact, block, 0, &grid));
     if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);

@@ -89,10 +89,61 @@ void glue_ctx_destroy(glue_ctx *c) {
   free(c);
 }
 
+// The reads as consecutive BAM records would hold them (trgt_seq4_t of include/trgt_engine.h): read r
+// starts in the high nibble of a byte when r is even and in the low nibble when r is odd, as clips at even
+// and odd query positions do.  Two calls: out == NULL returns the packed size in bytes.
+uint64_t seq4_pack(const uint8_t *reads, const uint64_t *read_off, uint64_t n_reads, uint8_t *out, uint64_t *starts,
+                   uint32_t *lengths, uint32_t threads) {
+  std::vector<uint64_t> boff((size_t)n_reads + 1, 0);
+  for (uint64_t r = 0; r < n_reads; r++) boff[r + 1] = boff[r] + ((r & 1u) + (read_off[r + 1] - read_off[r]) + 1) / 2;
+  if (!out) return boff[n_reads];
+  uint8_t code[256];
+  memset(code, 15, sizeof code);
+  const char *alphabet = "=ACMGRSVTWYHKDBN";
+  for (int i = 0; i < 16; i++) code[(uint8_t)alphabet[i]] = (uint8_t)i;
+  par_loci((uint32_t)n_reads, threads, [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t r = lo; r < hi; r++) {
+      const uint8_t *src = reads + read_off[r];
+      const uint64_t len = read_off[r + 1] - read_off[r];
+      const uint64_t par = r & 1u;
+      uint8_t *dst = out + boff[r];
+      memset(dst, 0, (size_t)(boff[r + 1] - boff[r]));
+      for (uint64_t i = 0; i < len; i++) {
+        const uint64_t nib = par + i;
+        dst[nib >> 1] |= (nib & 1u) ? code[src[i]] : (uint8_t)(code[src[i]] << 4);
+      }
+      starts[r] = 2 * boff[r] + par;
+      lengths[r] = (uint32_t)len;
+    }
+  });
+  return boff[n_reads];
+}
+
+namespace {
+// bases [pos, pos+len) of read r: from the ASCII reads, or decoded from the BAM 4-bit bases
+// (rec.seq().as_bytes(), read.rs:104, restricted to the repeat -- the host never decodes the flanks)
+struct ReadSource {
+  const uint8_t *reads; const uint64_t *read_off;
+  const uint8_t *seq4; const uint64_t *starts;
+  void copy(uint8_t *dst, uint32_t r, uint64_t pos, uint64_t len) const {
+    if (!seq4) { memcpy(dst, reads + read_off[r] + pos, len); return; }
+    static const char alphabet[] = "=ACMGRSVTWYHKDBN";
+    uint64_t nib = starts[r] + pos;
+    for (uint64_t i = 0; i < len; i++, nib++) {
+      const uint8_t b = seq4[nib >> 1];
+      dst[i] = (uint8_t)alphabet[(nib & 1u) ? (b & 15u) : (b >> 4)];
+    }
+  }
+};
+}  // namespace
+
 // ctx == NULL: plain malloc, release with glue_free; otherwise the outputs live in ctx's buffers and
-// stay valid until the next glue_build on that ctx.
+// stay valid until the next glue_build on that ctx.  seq4 != NULL: the reads are BAM 4-bit bases
+// (seq4, starts) and `reads` / `read_off` are ignored.
 int glue_build(const uint8_t *reads, const uint64_t *read_off, const uint32_t *locus_read_off, uint32_t n_loci,
-               const glue_span *spans, const uint8_t *read_hap, uint32_t threads, glue_ctx *ctx, glue_out *out) {
+               const glue_span *spans, const uint8_t *read_hap, uint32_t threads, glue_ctx *ctx, glue_out *out,
+               const uint8_t *seq4, const uint64_t *seq4_starts) {
+  const ReadSource rs{reads, read_off, seq4, seq4_starts};
   // pass 1: per-locus counts
   std::vector<uint32_t> g_cnt((size_t)n_loci + 1, 0), s_cnt((size_t)n_loci + 1, 0);
   std::vector<uint64_t> sb_cnt((size_t)n_loci + 1, 0), bb_cnt((size_t)n_loci + 1, 0);
@@ -145,19 +196,19 @@ int glue_build(const uint8_t *reads, const uint64_t *read_off, const uint32_t *l
         for (uint32_t r = locus_read_off[l]; r < locus_read_off[l + 1]; r++) {
           if (!spans[r].found || (read_hap[r] ? 1 : 0) != h) continue;
           const uint64_t len = spans[r].end - spans[r].start;
-          const uint8_t *src = reads + read_off[r] + spans[r].start;
           if (first) {
             first = false;
             out->bb_off[g] = bb;
             out->group_seq_off[g] = s;
             out->group_locus[g] = l;
-            memcpy(out->bb + bb, src, len);
+            rs.copy(out->bb + bb, r, spans[r].start, len);
             bb += len;
             g++;
           }
           out->seq_off[s] = sb;
           out->seq_read[s] = r;
-          memcpy(out->seqs + sb, src, len);
+          if (out->group_seq_off[g - 1] == s) memcpy(out->seqs + sb, out->bb + bb - len, len);  // the backbone is the first member
+          else rs.copy(out->seqs + sb, r, spans[r].start, len);
           sb += len;
           s++;
         }

@@ -226,6 +226,56 @@ k_flank_exact(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t 
   }
 }
 
+// Phase A, step 1, for the usual piece lengths (16 <= P <= FXT_PMAX on every locus): still a warp per
+// locus for the per-locus set-up (8-mer index + byte-shifted piece copies, 6.5 KB per warp), but then
+// ONE LANE PER (read, flank) PAIR: each lane walks its pair's probes and verifies candidates on its own
+// with aligned 16-byte loads of the read where it lies in HBM (flank_exact_thread).  No staging of the
+// reads, no warp collectives in the loop; only the sectors a probe or a verification touches are read.
+#define FXT_WARPS 4
+
+struct __align__(16) FlankExactTSmem {
+  uint16_t slot[2][TRGT_KIDX_SLOTS];
+  uint8_t copies[2][FXT_COPIES * FXT_STRIDE];
+};
+
+__global__ void __launch_bounds__(32 * FXT_WARPS)
+k_flank_exact_t(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
+                int band_budget, trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work, Counters *ctr) {
+  __shared__ FlankExactTSmem sm_all[FXT_WARPS];
+  FlankExactTSmem &sm = sm_all[threadIdx.x >> 5];
+  const WarpGroup g;
+  const int lane = g.lane();
+  for (uint32_t l = l_begin + blockIdx.x * FXT_WARPS + (threadIdx.x >> 5); l < l_end; l += gridDim.x * FXT_WARPS) {
+    const uint32_t r0 = locus_read_off[l], r1 = locus_read_off[l + 1];
+    if (r1 <= r0) continue;
+    __syncwarp();
+    const int P0 = (int)(src.lp_off[l + 1] - src.lp_off[l]), P1 = (int)(src.rp_off[l + 1] - src.rp_off[l]);
+    fxt_build_copies(g, src.lp + src.lp_off[l], P0, sm.copies[0]);
+    fxt_build_copies(g, src.rp + src.rp_off[l], P1, sm.copies[1]);
+    kidx_build(g, KmerIndex{sm.slot[0]}, sm.copies[0] + 8, P0);  // copy 0 holds the piece itself at byte 8
+    kidx_build(g, KmerIndex{sm.slot[1]}, sm.copies[1] + 8, P1);
+    const uint32_t n_pairs = 2u * (r1 - r0);
+    for (uint32_t p = (uint32_t)lane; p < n_pairs; p += 32u) {
+      const uint32_t r = r0 + (p >> 1), side = p & 1u;
+      const uint64_t o = src.read_off[r];
+      const int T = (int)(src.read_off[r + 1] - o);
+      const int P = side ? P1 : P0;
+      const int pos = flank_exact_thread(KmerIndex{sm.slot[side]}, sm.copies[side], P, src.reads + o, T);
+      trgt_flank_hit_t h;
+      h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
+      if (pos >= 0) {
+        h.via = TRGT_VIA_EXACT; h.matches = P; h.start = (uint32_t)pos; h.end = (uint32_t)(pos + P);
+      } else if (band_budget > 0) {
+        h.via = TRGT_VIA_PENDING;
+      } else {
+        const unsigned int slot = atomicAdd(&ctr->n_work, 1u);
+        work[slot] = 2 * r + side;
+      }
+      hits[2 * r + side] = h;
+    }
+  }
+}
+
 #define FL_LIST 256       // pending reads handled per pass over a locus
 #define FL_WS1_INTS 304   // scratch of the first-tier kernel: cost <= o+e on a band of <= 12 diagonals
 

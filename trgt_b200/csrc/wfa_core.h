@@ -851,6 +851,107 @@ TRGT_HD int flank_scan_indexed(const G &g, const KmerIndex &idx, const uint8_t *
   return -1;
 }
 
+// ---------------------------------------------------------------- exact search, one lane per pair ---
+
+// The exact search again, but a lane per (read, flank) pair instead of a group per pair: the probes of
+// flank_scan_indexed walked by one lane, and a candidate start verified by that lane alone against
+// the text where it lies (16 aligned bytes per load).  So that no byte ever has to be realigned, the
+// locus keeps FXT_COPIES copies of its piece on chip, copy k shifted by k bytes: byte 8 + k + i of
+// copy k is piece[i].  A candidate at text address A compares aligned text words with aligned words
+// of copy A & 7; the bytes outside [A, A + P) of the first and last word are masked.
+#define FXT_COPIES 8
+#define FXT_PMAX 256    // pieces this path takes
+#define FXT_STRIDE 288  // bytes per copy: 8 of front slack + 7 of shift + FXT_PMAX + 15 of tail, rounded to 16
+
+struct alignas(16) FxtU128 {
+  uint64_t lo, hi;
+};
+
+// valid-byte masks of a little-endian 8-byte word: bytes >= lo / bytes < hi
+TRGT_HD uint64_t fxt_mask_from(int lo) { return lo <= 0 ? ~0ull : (lo >= 8 ? 0ull : (~0ull << (8 * lo))); }
+TRGT_HD uint64_t fxt_mask_to(int hi) { return hi >= 8 ? ~0ull : (hi <= 0 ? 0ull : ((1ull << (8 * hi)) - 1ull)); }
+
+// the FXT_COPIES shifted copies of one piece (16 <= P <= FXT_PMAX), lanes stride over the words
+template <class G>
+TRGT_HD void fxt_build_copies(const G &g, const uint8_t *piece, int P, uint8_t *copies) {
+  const int W = FXT_STRIDE / 8;
+  for (int idx = g.lane(); idx < FXT_COPIES * W; idx += g.size()) {
+    const int k = idx / W, wd = idx - k * W;
+    const int i0 = 8 * wd - 8 - k;  // piece index of the word's first byte
+    uint64_t v = 0;
+    if (i0 >= 0 && i0 + 8 <= P) {
+      v = wfa_ld64u(piece + i0);
+    } else {
+      for (int b = 0; b < 8; b++)
+        if (i0 + b >= 0 && i0 + b < P) v |= (uint64_t)piece[i0 + b] << (8 * b);
+    }
+    *(uint64_t *)(copies + k * FXT_STRIDE + 8 * wd) = v;
+  }
+  g.sync();
+}
+
+// t[s .. s+P) == piece ?   a = t + s; reads whole 16-byte words around [a, a+P)
+TRGT_HD bool fxt_verify(const uint8_t *copies, int P, const uint8_t *a) {
+  const uintptr_t A = (uintptr_t)a;
+  const int a16 = (int)(A & 15u), k = a16 & 7, h = a16 >> 3;
+  const FxtU128 *tx = (const FxtU128 *)(A - (uintptr_t)a16);
+  const uint8_t *pc = copies + k * FXT_STRIDE + 8 - 8 * h;  // the copy's bytes that face tx[0]
+  const int C = (a16 + P + 15) >> 4;                        // 16-byte words touched
+  {  // first word: bytes below a16 do not belong to the candidate (nor, if C == 1, those from a16 + P on)
+    const FxtU128 tv = tx[0];
+    const uint64_t d0 = (tv.lo ^ *(const uint64_t *)pc) & fxt_mask_from(a16) & fxt_mask_to(a16 + P);
+    const uint64_t d1 = (tv.hi ^ *(const uint64_t *)(pc + 8)) & fxt_mask_from(a16 - 8) & fxt_mask_to(a16 + P - 8);
+    if (d0 | d1) return false;
+  }
+  if (C == 1) return true;
+  int c = 1;
+  for (; c + 4 <= C - 1; c += 4) {  // four words per step: the loads go out together
+    const FxtU128 t0 = tx[c], t1 = tx[c + 1], t2 = tx[c + 2], t3 = tx[c + 3];
+    const uint64_t *q = (const uint64_t *)(pc + 16 * c);
+    const uint64_t d = (t0.lo ^ q[0]) | (t0.hi ^ q[1]) | (t1.lo ^ q[2]) | (t1.hi ^ q[3]) | (t2.lo ^ q[4]) |
+                       (t2.hi ^ q[5]) | (t3.lo ^ q[6]) | (t3.hi ^ q[7]);
+    if (d) return false;
+  }
+  for (; c < C - 1; c++) {
+    const FxtU128 tv = tx[c];
+    const uint64_t *q = (const uint64_t *)(pc + 16 * c);
+    if ((tv.lo ^ q[0]) | (tv.hi ^ q[1])) return false;
+  }
+  {  // last word
+    const int end = a16 + P - 16 * (C - 1);  // valid bytes of it, 1..16
+    const FxtU128 tv = tx[C - 1];
+    const uint64_t *q = (const uint64_t *)(pc + 16 * (C - 1));
+    const uint64_t d0 = (tv.lo ^ q[0]) & fxt_mask_to(end);
+    const uint64_t d1 = (tv.hi ^ q[1]) & fxt_mask_to(end - 8);
+    if (d0 | d1) return false;
+  }
+  return true;
+}
+
+// first start s with t[s..s+P) == piece, or -1 (span_locater.rs:10-12), by ONE lane.
+// Probes in increasing order: their candidate ranges are disjoint and increasing, so the smallest
+// verified candidate of the first probe that has one is the first occurrence.
+TRGT_HD int flank_exact_thread(const KmerIndex &idx, const uint8_t *copies, int P, const uint8_t *t, int T) {
+  const int n_starts = T - P + 1;
+  if (n_starts <= 0) return -1;
+  const int step = P - 7;
+  const int n_probes = (T - 7) / step;
+  for (int i = 0; i < n_probes; i++) {
+    const int j = (i + 1) * step - 1;
+    const uint64_t mixed = kidx_mix(wfa_ld64u(t + j));
+    const uint32_t fp = kidx_fp(mixed);
+    int best = INT_MAX;
+    for (uint32_t h = kidx_home(mixed), v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+      if ((v >> 9) != fp) continue;
+      const int s = j - (int)(v & 511u);
+      if (s < 0 || s >= n_starts || s >= best) continue;
+      if (fxt_verify(copies, P, t + s)) best = s;
+    }
+    if (best != INT_MAX) return best;
+  }
+  return -1;
+}
+
 // flank_seed_band through the index: 1 band found, 0 no band can be given, -2 too many candidates
 template <class G>
 TRGT_HD int flank_seed_band_indexed(const G &g, const KmerIndex &idx, const WfaProb &pr, int S, int *cand, int *klo,

@@ -30,9 +30,11 @@ class HotPathResult:
 
 class HotPath:
     def __init__(self, engine: Engine, w: Workload, want_hits: bool = False, pinned_outputs: bool = True,
-                 glue_threads: int = 0):
+                 glue_threads: int = 0, use_seq4: bool = False):
         self.eng = engine
         self.w = w
+        # end-to-end input of phase A: the reads as BAM 4-bit bases (w.reads4) instead of ASCII
+        self.use_seq4 = bool(use_seq4 and w.reads4 is not None)
         self.want_hits = want_hits
         self.glue_threads = glue_threads  # 0: all cores
         self.timing = {"flank": 0.0, "glue": 0.0, "align": 0.0, "hmm": 0.0}
@@ -52,7 +54,11 @@ class HotPath:
     def h2d_bytes(self, glue: GenotypeGlue) -> int:
         w = self.w
         n = 0
-        for s in (w.reads, w.left, w.right, glue.backbones, glue.seqs, w.motifs):
+        if self.use_seq4:
+            n += w.reads4.data.nbytes + w.reads4.starts.nbytes + w.reads4.lengths.nbytes
+        else:
+            n += w.reads.data.nbytes + w.reads.offsets.nbytes
+        for s in (w.left, w.right, glue.backbones, glue.seqs, w.motifs):
             n += s.data.nbytes + s.offsets.nbytes
         n += glue.backbones.data.nbytes + glue.backbones.offsets.nbytes  # alleles = backbones, sent again for phase C
         n += w.locus_read_off.nbytes + glue.group_seq_off.nbytes + w.locus_motif_off.nbytes + glue.group_locus.nbytes
@@ -71,11 +77,16 @@ class HotPath:
         """copy=False: results alias pinned buffers (the engine's, this object's) until the next pass."""
         w, eng = self.w, self.eng
         t0 = time.perf_counter()
-        spans, hits = eng.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring,
-                                             w.min_flank_id_frac, want_hits=self.want_hits,
-                                             spans_out=self._spans, hits_out=self._hits)
+        if self.use_seq4:
+            spans, hits = eng.flank_spans_seq4(w.left, w.right, w.reads4, w.locus_read_off, w.scoring,
+                                               w.min_flank_id_frac, want_hits=self.want_hits,
+                                               spans_out=self._spans, hits_out=self._hits)
+        else:
+            spans, hits = eng.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring,
+                                                 w.min_flank_id_frac, want_hits=self.want_hits,
+                                                 spans_out=self._spans, hits_out=self._hits)
         t1 = time.perf_counter()
-        glue = genotype_glue(w, spans, threads=self.glue_threads, ctx=self._glue_ctx)
+        glue = genotype_glue(w, spans, threads=self.glue_threads, ctx=self._glue_ctx, from_seq4=self.use_seq4)
         t2 = time.perf_counter()
         cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off, copy=copy)
         t3 = time.perf_counter()
@@ -133,11 +144,12 @@ class ChunkedHotPath:
     runs phases A, glue, B, C per chunk through the blocking C ABI, so one chunk's PCIe transfers
     overlap another chunk's kernels and host glue."""
 
-    def __init__(self, engines, w: Workload, chunk_loci: int = 16384, glue_threads: int = 0):
+    def __init__(self, engines, w: Workload, chunk_loci: int = 16384, glue_threads: int = 0, use_seq4: bool = False):
         self.engines = list(engines)
         self.w = w
         self.bounds = [(l0, min(l0 + chunk_loci, w.n_loci)) for l0 in range(0, w.n_loci, chunk_loci)]
-        self.paths = [HotPath(self.engines[i % len(self.engines)], w.slice(l0, l1), glue_threads=glue_threads)
+        self.paths = [HotPath(self.engines[i % len(self.engines)], w.slice(l0, l1), glue_threads=glue_threads,
+                              use_seq4=use_seq4)
                       for i, (l0, l1) in enumerate(self.bounds)]
 
     def timing(self) -> dict:
