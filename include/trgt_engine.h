@@ -277,6 +277,13 @@ int32_t trgt_flank_device_views(trgt_flank_batch_t *batch, const void **d_reads,
  * tier, out[1] = handed to the wide-band kernel, out[2] = needed the full-width kernels */
 int32_t trgt_flank_fallback_counts(trgt_flank_batch_t *batch, uint32_t out[3]);
 
+/* The repeat sequences the genotypers work on, `trs` of src/trgt/workflows/tr.rs:58-62
+ * (read.bases[span.0..span.1] per spanning read), cut on the device from the reads of a flank batch
+ * (batch == NULL: the last trgt_flank_spans / trgt_flank_spans_seq4 call on this engine).  One sequence
+ * per read, empty for reads without a span; out->status is NULL.  out points into engine-owned pinned
+ * memory that stays valid until the next trgt_flank_trs on the same batch. */
+int32_t trgt_flank_trs(trgt_engine_t *eng, trgt_flank_batch_t *batch, trgt_seqs_out_t *out);
+
 typedef struct trgt_align_batch trgt_align_batch_t;
 int32_t trgt_align_upload(trgt_engine_t *eng, const trgt_seqs_t *backbones,
                           const trgt_seqs_t *seqs, const uint32_t *group_seq_offsets,

@@ -466,3 +466,40 @@ def test_flank_spans_seq4_matches_ascii_path(engine, oracle):
     sp0, _ = engine.flank_spans_seq4(PackedSeqs.from_list([]), PackedSeqs.from_list([]), PackedSeq4.from_ascii([]),
                                      np.zeros(1, dtype=np.uint32), w.scoring, w.min_flank_id_frac)
     assert sp0.size == 0
+
+
+def test_flank_trs_are_the_span_slices(engine, oracle):
+    """trgt_flank_trs = read.bases[span.0..span.1] per spanning read (tr.rs:58-62), for one-shot (ASCII and
+    BAM 4-bit input) and resident batches; and the host glue fed with them builds the same phase B/C input."""
+    from trgt_b200 import PackedSeq4, workload
+    w = workload.generate(50, 9, seed=77)
+    p4 = PackedSeq4.from_ascii([w.reads.get(r) for r in range(w.n_reads)])
+
+    def expect(spans):
+        return [w.reads.get(r)[int(s["start"]):int(s["end"])] if s["found"] else b"" for r, s in enumerate(spans)]
+
+    spans, _ = engine.flank_spans_seq4(w.left, w.right, p4, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+    trs = engine.flank_trs(copy=True)
+    assert [trs.get(r) for r in range(w.n_reads)] == expect(spans) and spans["found"].sum() > 300
+    g1 = workload.genotype_glue(w, spans)
+    g2 = workload.genotype_glue(w, spans, trs=trs)
+    for a, b in ((g1.seqs, g2.seqs), (g1.backbones, g2.backbones)):
+        assert np.array_equal(a.data, b.data) and np.array_equal(a.offsets, b.offsets)
+    assert np.array_equal(g1.seq_read, g2.seq_read) and np.array_equal(g1.group_locus, g2.group_locus)
+    spans2, _ = engine.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+    trs2 = engine.flank_trs(copy=True)
+    assert np.array_equal(trs2.data, trs.data) and np.array_equal(trs2.offsets, trs.offsets)
+    b = engine.flank_upload(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+    try:
+        engine.flank_run(b)
+        trs3 = engine.flank_trs(b, copy=True)
+    finally:
+        engine.flank_free(b)
+    assert np.array_equal(trs3.data, trs.data) and np.array_equal(trs3.offsets, trs.offsets)
+    # no spanning read at all / no reads
+    from trgt_b200 import PackedSeqs
+    junk = PackedSeqs.from_list([rnd(random.Random(1), 700) for _ in range(3)])
+    engine.flank_spans_packed(PackedSeqs.from_list([w.left.get(0)]), PackedSeqs.from_list([w.right.get(0)]), junk,
+                              np.array([0, 3], dtype=np.uint32), w.scoring, w.min_flank_id_frac)
+    t0 = engine.flank_trs(copy=True)
+    assert len(t0) == 3 and t0.data.size == 0

@@ -397,6 +397,8 @@ struct trgt_flank_batch {
   double frac = 0.7;
   DevBuf reads, read_off, lp, lp_off, rp, rp_off, locus_read_off, read_locus;
   DevBuf hits, spans, work, work2, ends, ctr, gring, gws;
+  DevBuf tr_len, tr_off, tr_data;      // trgt_flank_trs: repeat sequences of the spanning reads
+  PinBuf h_tr_off, h_tr_data;
   DevBuf seq4, seq4_starts, seq4_len;  // BAM 4-bit input (trgt_flank_*_seq4): decoded into `reads` on the device
   uint32_t last_n_work = 0, last_n_tier2 = 0, last_n_wide = 0;
 };
@@ -484,8 +486,10 @@ void trgt_flank_free(trgt_engine_t *e, trgt_flank_batch_t *b) {
   }
   DevBuf *all[] = {&b->reads, &b->read_off, &b->lp, &b->lp_off, &b->rp, &b->rp_off, &b->locus_read_off,
                    &b->read_locus, &b->hits, &b->spans, &b->work, &b->work2, &b->ends, &b->ctr, &b->gring, &b->gws,
-                   &b->seq4, &b->seq4_starts, &b->seq4_len};
+                   &b->seq4, &b->seq4_starts, &b->seq4_len, &b->tr_len, &b->tr_off, &b->tr_data};
   for (auto *d : all) dev_free(*d);
+  pin_free(b->h_tr_off);
+  pin_free(b->h_tr_data);
   delete b;
 }
 
@@ -974,6 +978,52 @@ int32_t trgt_clip_reads(trgt_engine_t *e, const uint32_t *cigar_ops, const uint6
   }
   CU(e, cudaMemcpyAsync(clips_out, d_clips, (size_t)n_reads * sizeof(trgt_clip_t), cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int32_t trgt_flank_trs(trgt_engine_t *e, trgt_flank_batch_t *b, trgt_seqs_out_t *out) {
+  if (!e || !out) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!b) b = e->one_flank;
+  if (!b) return fail(e, TRGT_ERR_ARG, "trgt_flank_trs: no flank batch has been run on this engine");
+  CU(e, cudaSetDevice(e->device));
+  memset(out, 0, sizeof *out);
+  const uint32_t n = b->n_reads;
+  TRY(pin_reserve(e, b->h_tr_off, ((size_t)n + 1) * sizeof(uint64_t)));
+  uint64_t *h_off = b->h_tr_off.as<uint64_t>();
+  h_off[0] = 0;
+  out->n = n;
+  out->offsets = h_off;
+  if (n == 0) return 0;
+  TRY(dev_reserve(e, b->tr_len, ((size_t)n + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->tr_off, ((size_t)n + 1) * sizeof(uint64_t)));
+  {
+    LaunchScope ls(e, "k_tr_len");
+    k_tr_len<<<(n + 256) / 256, 256, 0, e->stream>>>((const trgt_span_t *)b->spans.p, n, (uint32_t *)b->tr_len.p);
+    TRY(check_launch(e, "k_tr_len"));
+  }
+  TRY(exclusive_scan_u32(e, (const uint32_t *)b->tr_len.p, (unsigned long long *)b->tr_off.p, (size_t)n + 1));
+  CU(e, cudaMemcpyAsync(h_off, b->tr_off.p, ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  const uint64_t total = h_off[n];
+  TRY(dev_reserve(e, b->tr_data, (size_t)total + 16));
+  TRY(pin_reserve(e, b->h_tr_data, (size_t)total + 16));
+  if (total) {
+    int grid = 0;
+    TRY(persistent_grid(e, k_tr_gather, 256, 0, &grid));
+    const uint32_t need = (n + 7) / 8;
+    if ((uint32_t)grid > need) grid = (int)need;
+    {
+      LaunchScope ls(e, "k_tr_gather");
+      k_tr_gather<<<grid, 256, 0, e->stream>>>((const uint8_t *)b->reads.p, (const uint64_t *)b->read_off.p,
+                                               (const trgt_span_t *)b->spans.p, (const unsigned long long *)b->tr_off.p, n,
+                                               (uint8_t *)b->tr_data.p);
+      TRY(check_launch(e, "k_tr_gather"));
+    }
+    CU(e, cudaMemcpyAsync(b->h_tr_data.p, b->tr_data.p, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+  }
+  out->data = b->h_tr_data.as<uint8_t>();
   return 0;
 }
 

@@ -125,7 +125,9 @@ namespace {
 struct ReadSource {
   const uint8_t *reads; const uint64_t *read_off;
   const uint8_t *seq4; const uint64_t *starts;
+  bool trs;  // reads / read_off hold the repeat sequences themselves (trgt_flank_trs), not whole reads
   void copy(uint8_t *dst, uint32_t r, uint64_t pos, uint64_t len) const {
+    if (trs) { memcpy(dst, reads + read_off[r], len); return; }
     if (!seq4) { memcpy(dst, reads + read_off[r] + pos, len); return; }
     static const char alphabet[] = "=ACMGRSVTWYHKDBN";
     uint64_t nib = starts[r] + pos;
@@ -139,11 +141,12 @@ struct ReadSource {
 
 // ctx == NULL: plain malloc, release with glue_free; otherwise the outputs live in ctx's buffers and
 // stay valid until the next glue_build on that ctx.  seq4 != NULL: the reads are BAM 4-bit bases
-// (seq4, starts) and `reads` / `read_off` are ignored.
+// (seq4, starts) and `reads` / `read_off` are ignored.  trs_mode != 0: `reads` / `read_off` are the repeat
+// sequences of trgt_flank_trs (one per read, empty without a span).
 int glue_build(const uint8_t *reads, const uint64_t *read_off, const uint32_t *locus_read_off, uint32_t n_loci,
                const glue_span *spans, const uint8_t *read_hap, uint32_t threads, glue_ctx *ctx, glue_out *out,
-               const uint8_t *seq4, const uint64_t *seq4_starts) {
-  const ReadSource rs{reads, read_off, seq4, seq4_starts};
+               const uint8_t *seq4, const uint64_t *seq4_starts, int trs_mode) {
+  const ReadSource rs{reads, read_off, seq4, seq4_starts, trs_mode != 0};
   // pass 1: per-locus counts
   std::vector<uint32_t> g_cnt((size_t)n_loci + 1, 0), s_cnt((size_t)n_loci + 1, 0);
   std::vector<uint64_t> sb_cnt((size_t)n_loci + 1, 0), bb_cnt((size_t)n_loci + 1, 0);

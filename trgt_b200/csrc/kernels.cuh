@@ -470,6 +470,28 @@ k_flank_band_wide(WfaSrc src, uint32_t *__restrict__ work, const unsigned int *n
   }
 }
 
+// The repeat sequences read[span.start .. span.end) of the spanning reads (tr.rs:58-62), packed back to
+// back so that the host genotyper streams ~30 bytes per read instead of touching every ~1 KB read.
+__global__ void k_tr_len(const trgt_span_t *__restrict__ spans, uint32_t n_reads, uint32_t *__restrict__ len) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= n_reads; r += gsz)
+    len[r] = (r < n_reads && spans[r].found) ? spans[r].end - spans[r].start : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+k_tr_gather(const uint8_t *__restrict__ reads, const uint64_t *__restrict__ read_off,
+            const trgt_span_t *__restrict__ spans, const unsigned long long *__restrict__ off, uint32_t n_reads,
+            uint8_t *__restrict__ out) {
+  const uint32_t wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  for (uint32_t r = blockIdx.x * wpb + warp; r < n_reads; r += gridDim.x * wpb) {
+    const unsigned long long o = off[r];
+    const uint32_t n = (uint32_t)(off[r + 1] - o);
+    if (n == 0) continue;
+    const uint8_t *src = reads + read_off[r] + spans[r].start;
+    for (uint32_t i = lane; i < n; i += 32u) out[o + i] = src[i];
+  }
+}
+
 // ------------------------------------------------------------------ WFA pass 1 -------------
 
 // Persistent groups (a CTA when BLOCK, else a warp) pull items; ring on chip when it fits.

@@ -73,6 +73,7 @@ EXPORTS = [
     "trgt_engine_set_flank_band_budget",
     "trgt_host_alloc", "trgt_host_free",
     "trgt_clip_reads", "trgt_seq4_decode", "trgt_flank_spans_seq4", "trgt_flank_upload_seq4",
+    "trgt_flank_trs",
     "trgt_flank_spans", "trgt_align_e2e", "trgt_consensus", "trgt_edit_dist", "trgt_hmm_label",
     "trgt_flank_upload", "trgt_flank_run", "trgt_flank_download", "trgt_flank_free", "trgt_flank_device_views",
     "trgt_flank_fallback_counts",
@@ -127,6 +128,7 @@ def load_library(build: bool = True):
     L.trgt_flank_upload_seq4.argtypes = [vp, sp, sp, s4, vp, u32, _Scoring, C.c_double, C.POINTER(vp)]
     L.trgt_seq4_decode.argtypes = [vp, s4, vp, vp]
     L.trgt_clip_reads.argtypes = [vp, vp, vp, vp, u64, vp, vp, u32, vp]
+    L.trgt_flank_trs.argtypes = [vp, vp, C.POINTER(_SeqsOut)]
     L.trgt_flank_run.argtypes = [vp, vp]
     L.trgt_flank_download.argtypes = [vp, vp, vp, vp]
     L.trgt_flank_free.argtypes = [vp, vp]
@@ -460,6 +462,19 @@ class Engine:
                                                    len(left), _Scoring(*scoring), float(min_flank_id_frac), C.byref(b)),
                     "trgt_flank_upload_seq4")
         return b
+
+    def flank_trs(self, b=None, copy: bool = False) -> PackedSeqs:
+        """trs of tr.rs:58-62: read[span.start..span.end] per read (empty without a span), cut on the device
+        from batch b (None: the last one-shot flank call).  copy=False: views of the engine's pinned buffers."""
+        out = _SeqsOut()
+        self._check(self._L.trgt_flank_trs(self._h, b, C.byref(out)), "trgt_flank_trs")
+        n = int(out.n)
+        offs = np.ctypeslib.as_array(out.offsets, shape=(n + 1,))
+        total = int(offs[n])
+        data = np.ctypeslib.as_array(out.data, shape=(total,)) if total else np.zeros(0, dtype=np.uint8)
+        if copy:
+            offs, data = offs.copy(), data.copy()
+        return PackedSeqs(data, offs)
 
     def flank_run(self, b):
         self._check(self._L.trgt_flank_run(self._h, b), "trgt_flank_run")

@@ -67,6 +67,8 @@ class HotPath:
 
     def d2h_bytes(self, res: HotPathResult) -> int:
         n = res.spans.nbytes + (res.hits.nbytes if res.hits is not None else 0)
+        if self.use_seq4:  # trgt_flank_trs: offsets + bytes of the repeat sequences
+            n += 8 * (self.w.n_reads + 1) + int(res.glue.seqs.data.nbytes)
         c, a = res.cigars, res.annotations
         n += c.offsets.nbytes + c.words.nbytes + c.scores.nbytes + c.status.nbytes
         n += a.motif_counts.nbytes + a.span_offsets.nbytes + a.spans.nbytes + a.purity.nbytes + a.status.nbytes
@@ -85,8 +87,9 @@ class HotPath:
             spans, hits = eng.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring,
                                                  w.min_flank_id_frac, want_hits=self.want_hits,
                                                  spans_out=self._spans, hits_out=self._hits)
+        trs = eng.flank_trs() if self.use_seq4 else None  # the host holds no ASCII reads to cut them from
         t1 = time.perf_counter()
-        glue = genotype_glue(w, spans, threads=self.glue_threads, ctx=self._glue_ctx, from_seq4=self.use_seq4)
+        glue = genotype_glue(w, spans, threads=self.glue_threads, ctx=self._glue_ctx, trs=trs)
         t2 = time.perf_counter()
         cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off, copy=copy)
         t3 = time.perf_counter()
