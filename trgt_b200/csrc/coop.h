@@ -59,6 +59,28 @@ struct WarpGroup {
   }
 };
 
+// N consecutive lanes of a warp (N = 2, 4, 8, 16) on one item: a warp works on 32 / N items at once,
+// each tile following its own control flow (independent thread scheduling); every collective names
+// the tile's own lanes in its mask.  For items whose parallelism is a handful of diagonals.
+template <int N>
+struct TileGroup {
+  unsigned mask;
+  int l;
+  TRGT_D TileGroup() {
+    const unsigned lane = threadIdx.x & 31u;
+    l = (int)(lane & (unsigned)(N - 1));
+    mask = ((1u << N) - 1u) << (lane & ~(unsigned)(N - 1));
+  }
+  TRGT_D int lane() const { return l; }
+  TRGT_D int size() const { return N; }
+  TRGT_D void sync() const { __syncwarp(mask); }
+  TRGT_D int min_i(int v) const { return __reduce_min_sync(mask, v); }
+  TRGT_D int max_i(int v) const { return __reduce_max_sync(mask, v); }
+  TRGT_D int any(int p) const { return __any_sync(mask, p); }
+  TRGT_D int bcast0(int v) const { return __shfl_sync(mask, v, 0, N); }
+  TRGT_D int bcast(int v, int src_lane) const { return __shfl_sync(mask, v, src_lane, N); }
+};
+
 // The whole CTA (blockDim.x threads, a multiple of 32, <= 1024) on one item.
 // `scratch` points at 33 ints of shared memory owned by the group.
 struct BlockGroup {

@@ -276,30 +276,35 @@ k_flank_exact_t(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_
   }
 }
 
-#define FL_LIST 256       // pending reads handled per pass over a locus
-#define FL_WS1_INTS 304   // scratch of the first-tier kernel: cost <= o+e on a band of <= 12 diagonals
+#define FL_LIST 256       // pending pairs gathered per pass over a locus' reads
+#define FL_TILE 4         // lanes per pending pair in the first cost tier
+#define FL_TILES (32 / FL_TILE)
+#define FL_WS1_INTS 128   // per-tile scratch: 6*7 header + 3 * 4 diagonals * 7 scores (cost <= 6 on <= 4 diagonals)
 
 struct __align__(16) FlankBandSmem {
   uint16_t slot[2][TRGT_KIDX_SLOTS];
   uint8_t piece[2][FL_PIECE];
-  uint8_t txt[FL_TXT];
-  uint16_t list[FL_LIST];  // (read - first read of the pass) << 2 | pending sides
-  int cand[TRGT_CAND_CAP + 4];
-  int ws[FL_WS1_INTS];
+  uint16_t list[FL_LIST + 64];  // pending pairs of the pass: (read - first read of the pass) << 1 | side
+  int cand[FL_TILES][TRGT_CAND_CAP + 4];
+  int ws[FL_TILES][FL_WS1_INTS];
 };
 
 // Phase A, step 2.  Again a warp per locus, but only the (read, flank) pairs left pending, and only
 // the first cost tier of the WFA fallback (span_locater.rs:14-25): one mismatch or one 1-bp gap,
-// ~89 % of HiFi misses.  Index seed filter + narrow-band wavefront + back-trace of wfa_core.h from
-// the staged copy of the read, in 6.5 KB of shared memory per warp (28 resident warps per SM).
-// What it cannot settle goes to `work2` (2*read+side) for k_flank_band2.
-__global__ void __launch_bounds__(32, 28)
+// ~89 % of HiFi misses.  Such an alignment lives on 3-4 diagonals, so a pair gets a TILE OF 4 LANES
+// (one lane per diagonal in the narrow-band wavefront, 32 bytes per step in the match extensions) and
+// the warp works on 8 pending pairs at once: index seed filter + narrow-band wavefront + back-trace of
+// wfa_core.h, the read taken where it lies in HBM (L1 keeps the ~1 KB a pair touches).
+// What a tile cannot settle goes to `work2` (2*read+side) for k_flank_band2.
+__global__ void __launch_bounds__(32, 20)
 k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
              int band_budget, double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits,
              uint32_t *__restrict__ work2, Counters *ctr) {
   __shared__ FlankBandSmem sm;
   const WarpGroup g;
+  const TileGroup<FL_TILE> tg;
   const int lane = g.lane();
+  const int tile = lane / FL_TILE;
   for (uint32_t l = l_begin + blockIdx.x; l < l_end; l += gridDim.x) {
     const uint32_t r0 = locus_read_off[l], r1 = locus_read_off[l + 1];
     bool have_index = false;
@@ -307,18 +312,23 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
     const uint8_t *ps[2] = {nullptr, nullptr};
     int PL[2] = {0, 0};
 #pragma unroll 1
-    for (uint32_t rb = r0; rb < r1; rb += FL_LIST) {
-      const uint32_t re = rb + FL_LIST < r1 ? rb + FL_LIST : r1;
+    for (uint32_t rb = r0; rb < r1;) {
       __syncwarp();
       int n_list = 0;
-      for (uint32_t base = rb; base < re; base += 32) {  // pending reads of this pass, in read order
+      uint32_t base = rb;
+      for (; base < r1 && n_list < FL_LIST && base - rb < 16384u; base += 32) {  // pending pairs of this pass, in read order
         const uint32_t r = base + (uint32_t)lane;
         unsigned m = 0;
-        if (r < re) m = (hits[2 * r].via == TRGT_VIA_PENDING ? 1u : 0u) | (hits[2 * r + 1].via == TRGT_VIA_PENDING ? 2u : 0u);
-        const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
-        if (m) sm.list[n_list + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(((r - rb) << 2) | m);
-        n_list += __popc(bal);
+        if (r < r1) m = (hits[2 * r].via == TRGT_VIA_PENDING ? 1u : 0u) | (hits[2 * r + 1].via == TRGT_VIA_PENDING ? 2u : 0u);
+        const unsigned b0 = __ballot_sync(0xffffffffu, m & 1u), b1 = __ballot_sync(0xffffffffu, m & 2u);
+        const unsigned lt = (1u << lane) - 1u;
+        int pos = n_list + __popc(b0 & lt) + __popc(b1 & lt);
+        if (m & 1u) sm.list[pos++] = (uint16_t)(((r - rb) << 1) | 0u);
+        if (m & 2u) sm.list[pos] = (uint16_t)(((r - rb) << 1) | 1u);
+        n_list += __popc(b0) + __popc(b1);
       }
+      const uint32_t rb_pass = rb;
+      rb = base;
       __syncwarp();
       if (n_list == 0) continue;
       if (!have_index) {  // first pending pair of the locus: stage and index its pieces
@@ -338,46 +348,38 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
         }
       }
 #pragma unroll 1
-      for (int i = 0; i < n_list; i++) {
-        const unsigned mask = sm.list[i] & 3u;
-        const uint32_t r = rb + (uint32_t)(sm.list[i] >> 2);
-        const int T = (int)(src.read_off[r + 1] - src.read_off[r]);
-        const uint8_t *t_s = stage_bytes(src.reads + src.read_off[r], T, sm.txt, FL_TXT, lane, 32);
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        __syncwarp();
-#pragma unroll 1
-        for (int side = 0; side < 2; side++) {
-          if (!((mask >> side) & 1u)) continue;
-          int deferred = 1;
-          FlankHit fh;
-          fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
-          if (indexed[side] && t_s != nullptr) {
-            WfaProb pr;
-            pr.x = src.x; pr.oe = src.oe; pr.e = src.e;
-            pr.p = ps[side]; pr.P = PL[side];
-            pr.t = t_s; pr.T = T;
-            pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;  // span_locater.rs:17
-            wfa_unband(pr);
-            deferred = flank_locate_banded_lean(g, pr, band_budget, min_flank_id_frac, sm.ws, FL_WS1_INTS, &fh,
-                                                KmerIndex{sm.slot[side]}, sm.cand, 0, 0);
-          }
-          if (lane == 0) {
-            trgt_flank_hit_t h;
-            h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
-            if (!deferred) {
-              h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
-              h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
-            } else {
-              const unsigned int slot = atomicAdd(&ctr->n_tier2, 1u);
-              work2[slot] = 2 * r + (uint32_t)side;
-            }
-            hits[2 * r + side] = h;
-          }
-          __syncwarp();
+      for (int i = tile; i < n_list; i += FL_TILES) {  // one pending pair per tile
+        const int side = sm.list[i] & 1;
+        const uint32_t r = rb_pass + (uint32_t)(sm.list[i] >> 1);
+        int deferred = 1;
+        FlankHit fh;
+        fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
+        if (indexed[side]) {
+          WfaProb pr;
+          pr.x = src.x; pr.oe = src.oe; pr.e = src.e;
+          pr.p = ps[side]; pr.P = PL[side];
+          pr.t = src.reads + src.read_off[r];
+          pr.T = (int)(src.read_off[r + 1] - src.read_off[r]);
+          pr.pbf = 0; pr.pef = 0; pr.tbf = pr.T; pr.tef = pr.T;  // span_locater.rs:17
+          wfa_unband(pr);
+          deferred = flank_locate_banded_lean(tg, pr, band_budget, min_flank_id_frac, sm.ws[tile], FL_WS1_INTS, &fh,
+                                              KmerIndex{sm.slot[side]}, sm.cand[tile], 0, 0);
         }
-        __syncwarp();
+        if (tg.lane() == 0) {
+          trgt_flank_hit_t h;
+          h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
+          if (!deferred) {
+            h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
+            h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
+          } else {
+            const unsigned int slot = atomicAdd(&ctr->n_tier2, 1u);
+            work2[slot] = 2 * r + (uint32_t)side;
+          }
+          hits[2 * r + side] = h;
+        }
+        tg.sync();
       }
+      __syncwarp();
     }
   }
 }
