@@ -248,4 +248,27 @@ int emu_flank_exact_thread(const uint8_t *p, int P, const uint8_t *t, int T, int
   return flank_exact_thread(idx, copies, P, t, T);
 }
 
+// first cost tier by one lane (flank_locate_tier1_thread): out[0]=rc (0 settled, 1 handed on) out[1]=via
+// out[2]=matches out[3]=score out[4]=start out[5]=end
+int emu_flank_tier1_thread(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x, int o, int e, int S,
+                           double frac, int *out) {
+  std::vector<uint8_t> pbuf(P + 16, 0), tbuf(T + 32, 0);
+  memcpy(pbuf.data(), p_in, P);
+  memcpy(tbuf.data(), t_in, T);
+  WfaProb pr;
+  pr.p = pbuf.data(); pr.P = P; pr.t = tbuf.data(); pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
+  pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;
+  wfa_unband(pr);
+  std::vector<uint16_t> islot(TRGT_KIDX_SLOTS);
+  KmerIndex idx{islot.data()};
+  SerialGroup g;
+  kidx_build(g, idx, pr.p, P);
+  int ws[FT1_WS_INTS];
+  for (int i = 0; i < FT1_WS_INTS; i++) ws[i] = 0x7ead;
+  FlankHit hit = {0, 0, 0, 0, 0};
+  out[0] = flank_locate_tier1_thread(pr, S, frac, ws, &hit, idx);
+  out[1] = hit.via; out[2] = hit.matches; out[3] = hit.score; out[4] = hit.start; out[5] = hit.end;
+  return 0;
+}
+
 }  // extern "C"

@@ -580,3 +580,59 @@ def test_flank_exact_thread_core(emul, lanes):
         assert got == t.find(p), (it, P, len(t), off)
         hits += got >= 0
     assert hits > 50
+
+
+def test_flank_tier1_thread_core(emul, oracle):
+    """First cost tier of the flank fallback by one lane per pair: whatever it settles must be the
+    reference's answer (score, count_matches, span); what it hands on is checked by the other tiers' tests."""
+    emul.emu_flank_tier1_thread.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_double, C.POINTER(C.c_int)]
+    rng = random.Random(4242)
+    seen = {"settled": 0, "handed_on": 0, "gap": 0, "rejected": 0}
+    for it in range(2500):
+        x, o, e = rng.choice([(2, 5, 1), (2, 5, 1), (2, 5, 1), (1, 0, 1), (4, 6, 2), (3, 1, 1)])
+        P = rng.choice([60, 120, 200, 250, 250, 250, 380])
+        kind = rng.random()
+        if kind < 0.25:
+            unit = rnd(rng, rng.randint(1, 9))
+            p = mutate(rng, (unit * (P // len(unit) + 1))[:P], rng.choice([0, 0.02, 0.05]))[:P]
+            if len(p) < 16:
+                continue
+        else:
+            p = rnd(rng, P)
+        pre, suf = rnd(rng, rng.randint(0, 600)), rnd(rng, rng.randint(0, 600))
+        if kind < 0.25 and rng.random() < 0.5:
+            pre += p[:len(p) // 2]
+        r = rng.random()
+        if r < 0.5:      # exactly one edit: the bulk of what this tier is for
+            i = rng.randrange(len(p))
+            c = rng.random()
+            if c < 0.3:
+                body = p[:i] + bytes([rng.choice(b"ACGT")]) + p[i + 1:]
+            elif c < 0.65:
+                body = p[:i] + p[i + 1:]
+            else:
+                body = p[:i] + bytes([rng.choice(b"ACGT")]) + p[i:]
+            seen["gap"] += c >= 0.3
+        else:
+            body = mutate(rng, p, rng.choice([0.002, 0.004, 0.01, 0.03]))
+        if rng.random() < 0.1:
+            body += rnd(rng, 20) + p[:-1]
+        t = pre + body + suf
+        if rng.random() < 0.05:
+            t = t[:rng.randint(1, len(t))]
+        if t.find(p) >= 0:
+            continue  # exact hits never reach the fallback
+        frac = rng.choice([0.7, 0.7, 0.999])
+        out = (C.c_int * 6)()
+        emul.emu_flank_tier1_thread(p, len(p), t, len(t), x, o, e, 20, frac, out)
+        if out[0] != 0:
+            seen["handed_on"] += 1
+            continue
+        seen["settled"] += 1
+        exp, via, nm = oracle.find_span(p, t, (x, o, e), len(p) * frac)
+        assert (out[1], out[2]) == (via, nm), (it, x, o, e)
+        seen["rejected"] += via == 3
+        if exp is not None:
+            assert (out[4], out[5]) == exp, (it, x, o, e)
+    assert seen["settled"] > 700 and seen["handed_on"] > 50 and seen["rejected"] > 5, seen

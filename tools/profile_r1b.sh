@@ -1,0 +1,13 @@
+#!/bin/bash
+# Under gpurun (1 GPU): launch list of one full-size resident pass, then one `--set full` capture of the
+# kernels named on the command line (default: the ones changed late in round 1), whole-shard launches.
+mkdir -p gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_full.csv \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --resident-only > gpurun_out/ncu_bench_full.log 2>&1
+KERNELS=${@:-'k_flank_exact_t$ k_flank_band$ k_unpack_seq4$'}
+for k in $KERNELS; do
+  n=$(echo $k | tr -d '$')
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/full_$n \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --resident-only > gpurun_out/ncu_full_$n.log 2>&1
+done
+ls -la gpurun_out | tail -12

@@ -61,7 +61,7 @@ struct WarpGroup {
 
 // N consecutive lanes of a warp (N = 2, 4, 8, 16) on one item: a warp works on 32 / N items at once,
 // each tile following its own control flow (independent thread scheduling); every collective names
-// the tile's own lanes in its mask.  For items whose parallelism is a handful of diagonals.
+// the tile's own lanes in its mask.
 template <int N>
 struct TileGroup {
   unsigned mask;
@@ -79,6 +79,10 @@ struct TileGroup {
   TRGT_D int any(int p) const { return __any_sync(mask, p); }
   TRGT_D int bcast0(int v) const { return __shfl_sync(mask, v, 0, N); }
   TRGT_D int bcast(int v, int src_lane) const { return __shfl_sync(mask, v, src_lane, N); }
+  // bit i = predicate of the tile's lane i
+  TRGT_D unsigned ballot(int p) const {
+    return (__ballot_sync(mask, p) >> ((threadIdx.x & 31u) & ~(unsigned)(N - 1))) & (unsigned)((1ull << N) - 1ull);
+  }
 };
 
 // The whole CTA (blockDim.x threads, a multiple of 32, <= 1024) on one item.

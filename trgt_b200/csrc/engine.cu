@@ -397,6 +397,8 @@ struct trgt_flank_batch {
   double frac = 0.7;
   DevBuf reads, read_off, lp, lp_off, rp, rp_off, locus_read_off, read_locus;
   DevBuf hits, spans, work, work2, ends, ctr, gring, gws;
+  DevBuf kidx;                         // 8-mer indexes of both pieces of every locus (k_flank_exact_t -> k_flank_band)
+  bool kidx_valid = false;
   DevBuf tr_len, tr_off, tr_data;      // trgt_flank_trs: repeat sequences of the spanning reads
   PinBuf h_tr_off, h_tr_data;
   DevBuf seq4, seq4_starts, seq4_len;  // BAM 4-bit input (trgt_flank_*_seq4): decoded into `reads` on the device
@@ -486,7 +488,7 @@ void trgt_flank_free(trgt_engine_t *e, trgt_flank_batch_t *b) {
   }
   DevBuf *all[] = {&b->reads, &b->read_off, &b->lp, &b->lp_off, &b->rp, &b->rp_off, &b->locus_read_off,
                    &b->read_locus, &b->hits, &b->spans, &b->work, &b->work2, &b->ends, &b->ctr, &b->gring, &b->gws,
-                   &b->seq4, &b->seq4_starts, &b->seq4_len, &b->tr_len, &b->tr_off, &b->tr_data};
+                   &b->seq4, &b->seq4_starts, &b->seq4_len, &b->tr_len, &b->tr_off, &b->tr_data, &b->kidx};
   for (auto *d : all) dev_free(*d);
   pin_free(b->h_tr_off);
   pin_free(b->h_tr_data);
@@ -577,8 +579,13 @@ int32_t trgt_flank_upload(trgt_engine_t *e, const trgt_seqs_t *left_pieces, cons
 static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src, uint32_t l0, uint32_t l1) {
   if (l1 <= l0) return 0;
   const int block = 32;  // one warp per CTA, one locus at a time per warp
+  b->kidx_valid = false;
   if (b->Pmin >= 16 && b->Pmax <= FXT_PMAX) {  // usual piece lengths: one lane per (read, flank) pair
     const int tb = 32 * FXT_WARPS;
+    if (e->band_budget > 0) {
+      TRY(dev_reserve(e, b->kidx, (size_t)b->n_loci * 2 * TRGT_KIDX_SLOTS * sizeof(uint16_t) + 16));
+      b->kidx_valid = true;
+    }
     int grid = 0;
     TRY(persistent_grid(e, k_flank_exact_t, tb, 0, &grid));
     const uint32_t need = (l1 - l0 + FXT_WARPS - 1) / FXT_WARPS;
@@ -586,7 +593,7 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
     LaunchScope ls(e, "k_flank_exact_t");
     k_flank_exact_t<<<grid, tb, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
                                                 (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p,
-                                                (Counters *)b->ctr.p);
+                                                (Counters *)b->ctr.p, b->kidx_valid ? (uint16_t *)b->kidx.p : nullptr);
     TRY(check_launch(e, "k_flank_exact_t"));
   } else {
     int grid = 0;
@@ -600,12 +607,14 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
   }
   if (e->band_budget > 0) {  // first cost tier of the fallback, at high occupancy
     int grid = 0;
-    TRY(persistent_grid(e, k_flank_band, block, 0, &grid));
-    if ((uint32_t)grid > l1 - l0) grid = (int)(l1 - l0);
+    TRY(persistent_grid(e, k_flank_band, 128, 0, &grid));
+    const uint32_t need = (l1 - l0 + FB_LOCI - 1) / FB_LOCI;
+    if ((uint32_t)grid > need) grid = (int)need;
     LaunchScope ls(e, "k_flank_band");
-    k_flank_band<<<grid, block, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
+    k_flank_band<<<grid, 128, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
                                                 b->frac, (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work2.p,
-                                                (Counters *)b->ctr.p);
+                                                (Counters *)b->ctr.p,
+                                                b->kidx_valid ? (const uint16_t *)b->kidx.p : nullptr);
     TRY(check_launch(e, "k_flank_band"));
   }
   return 0;

@@ -240,7 +240,8 @@ struct __align__(16) FlankExactTSmem {
 
 __global__ void __launch_bounds__(32 * FXT_WARPS)
 k_flank_exact_t(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
-                int band_budget, trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work, Counters *ctr) {
+                int band_budget, trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work, Counters *ctr,
+                uint16_t *__restrict__ kidx_out) {
   __shared__ FlankExactTSmem sm_all[FXT_WARPS];
   FlankExactTSmem &sm = sm_all[threadIdx.x >> 5];
   const WarpGroup g;
@@ -254,6 +255,11 @@ k_flank_exact_t(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_
     fxt_build_copies(g, src.rp + src.rp_off[l], P1, sm.copies[1]);
     kidx_build(g, KmerIndex{sm.slot[0]}, sm.copies[0] + 8, P0);  // copy 0 holds the piece itself at byte 8
     kidx_build(g, KmerIndex{sm.slot[1]}, sm.copies[1] + 8, P1);
+    if (kidx_out) {  // both tables (2 KB) for the fallback kernels, which then need not rebuild them
+      uint4 *dst = (uint4 *)(kidx_out + (size_t)l * 2 * TRGT_KIDX_SLOTS);
+      const uint4 *s4 = (const uint4 *)&sm.slot[0][0];
+      for (int i = lane; i < (int)(2 * TRGT_KIDX_SLOTS * sizeof(uint16_t) / 16); i += 32) dst[i] = s4[i];
+    }
     const uint32_t n_pairs = 2u * (r1 - r0);
     for (uint32_t p = (uint32_t)lane; p < n_pairs; p += 32u) {
       const uint32_t r = r0 + (p >> 1), side = p & 1u;
@@ -276,36 +282,33 @@ k_flank_exact_t(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_
   }
 }
 
-#define FL_LIST 256       // pending pairs gathered per pass over a locus' reads
-#define FL_TILE 4         // lanes per pending pair in the first cost tier
-#define FL_TILES (32 / FL_TILE)
-#define FL_WS1_INTS 128   // per-tile scratch: 6*7 header + 3 * 4 diagonals * 7 scores (cost <= 6 on <= 4 diagonals)
+#define FB_LT 16          // lanes per locus in the first cost tier
+#define FB_LOCI (128 / FB_LT)  // loci in flight per CTA of 128 threads
+#define FB_LIST 64        // pending pairs gathered per pass over a locus' reads
 
 struct __align__(16) FlankBandSmem {
   uint16_t slot[2][TRGT_KIDX_SLOTS];
   uint8_t piece[2][FL_PIECE];
-  uint16_t list[FL_LIST + 64];  // pending pairs of the pass: (read - first read of the pass) << 1 | side
-  int cand[FL_TILES][TRGT_CAND_CAP + 4];
-  int ws[FL_TILES][FL_WS1_INTS];
+  uint16_t list[FB_LIST];  // pending pairs of the pass: (read - first read of the pass) << 1 | side
 };
 
-// Phase A, step 2.  Again a warp per locus, but only the (read, flank) pairs left pending, and only
-// the first cost tier of the WFA fallback (span_locater.rs:14-25): one mismatch or one 1-bp gap,
-// ~89 % of HiFi misses.  Such an alignment lives on 3-4 diagonals, so a pair gets a TILE OF 4 LANES
-// (one lane per diagonal in the narrow-band wavefront, 32 bytes per step in the match extensions) and
-// the warp works on 8 pending pairs at once: index seed filter + narrow-band wavefront + back-trace of
-// wfa_core.h, the read taken where it lies in HBM (L1 keeps the ~1 KB a pair touches).
-// What a tile cannot settle goes to `work2` (2*read+side) for k_flank_band2.
-__global__ void __launch_bounds__(32, 20)
+// Phase A, step 2.  Only the (read, flank) pairs left pending, and only the first cost tier of the WFA
+// fallback (span_locater.rs:14-25): one mismatch or one 1-bp gap, ~89 % of HiFi misses.  Such an
+// alignment lives on 3-4 diagonals -- no work for a warp -- so ONE LANE TAKES ONE PAIR
+// (flank_locate_tier1_thread: index seed filter + narrow-band wavefront + back-trace, no collectives,
+// history in the lane's local memory, the read taken where it lies in HBM).  A locus has ~13 pending
+// pairs at 30x, so a half-warp (FB_LT lanes) takes a locus: it stages and indexes the two pieces once
+// (3 KB of shared memory) and then its lanes each take a pending pair.
+// What a lane cannot settle goes to `work2` (2*read+side) for k_flank_band2.
+__global__ void __launch_bounds__(128, 4)
 k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
              int band_budget, double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits,
-             uint32_t *__restrict__ work2, Counters *ctr) {
-  __shared__ FlankBandSmem sm;
-  const WarpGroup g;
-  const TileGroup<FL_TILE> tg;
+             uint32_t *__restrict__ work2, Counters *ctr, const uint16_t *__restrict__ kidx_in) {
+  __shared__ FlankBandSmem sm_all[FB_LOCI];
+  const TileGroup<FB_LT> g;
+  FlankBandSmem &sm = sm_all[threadIdx.x / FB_LT];
   const int lane = g.lane();
-  const int tile = lane / FL_TILE;
-  for (uint32_t l = l_begin + blockIdx.x; l < l_end; l += gridDim.x) {
+  for (uint32_t l = l_begin + blockIdx.x * FB_LOCI + threadIdx.x / FB_LT; l < l_end; l += gridDim.x * FB_LOCI) {
     const uint32_t r0 = locus_read_off[l], r1 = locus_read_off[l + 1];
     bool have_index = false;
     bool indexed[2] = {false, false};
@@ -313,14 +316,14 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
     int PL[2] = {0, 0};
 #pragma unroll 1
     for (uint32_t rb = r0; rb < r1;) {
-      __syncwarp();
+      g.sync();
       int n_list = 0;
       uint32_t base = rb;
-      for (; base < r1 && n_list < FL_LIST && base - rb < 16384u; base += 32) {  // pending pairs of this pass, in read order
+      for (; base < r1 && n_list + 2 * FB_LT <= FB_LIST && base - rb < 16384u; base += FB_LT) {  // pending pairs, in read order
         const uint32_t r = base + (uint32_t)lane;
         unsigned m = 0;
         if (r < r1) m = (hits[2 * r].via == TRGT_VIA_PENDING ? 1u : 0u) | (hits[2 * r + 1].via == TRGT_VIA_PENDING ? 2u : 0u);
-        const unsigned b0 = __ballot_sync(0xffffffffu, m & 1u), b1 = __ballot_sync(0xffffffffu, m & 2u);
+        const unsigned b0 = g.ballot(m & 1u), b1 = g.ballot(m & 2u);
         const unsigned lt = (1u << lane) - 1u;
         int pos = n_list + __popc(b0 & lt) + __popc(b1 & lt);
         if (m & 1u) sm.list[pos++] = (uint16_t)(((r - rb) << 1) | 0u);
@@ -329,32 +332,46 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
       }
       const uint32_t rb_pass = rb;
       rb = base;
-      __syncwarp();
+      g.sync();
       if (n_list == 0) continue;
-      if (!have_index) {  // first pending pair of the locus: stage and index its pieces
+      for (int i = lane; i < n_list; i += FB_LT) {  // pull the pending reads towards the SM while the pieces are set up
+        const uint32_t r = rb_pass + (uint32_t)(sm.list[i] >> 1);
+        const uint8_t *t = src.reads + src.read_off[r];
+        const int T = (int)(src.read_off[r + 1] - src.read_off[r]);
+        for (int o = 0; o < T && o < 4096; o += 128) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(t + o));
+      }
+      if (!have_index) {  // first pending pair of the locus: stage its pieces, fetch or build their indexes
         have_index = true;
         const uint8_t *pgl = src.lp + src.lp_off[l], *pgr = src.rp + src.rp_off[l];
         PL[0] = (int)(src.lp_off[l + 1] - src.lp_off[l]);
         PL[1] = (int)(src.rp_off[l + 1] - src.rp_off[l]);
-        ps[0] = stage_bytes(pgl, PL[0], sm.piece[0], FL_PIECE, lane, 32);
-        ps[1] = stage_bytes(pgr, PL[1], sm.piece[1], FL_PIECE, lane, 32);
+        ps[0] = stage_bytes(pgl, PL[0], sm.piece[0], FL_PIECE, lane, FB_LT);
+        ps[1] = stage_bytes(pgr, PL[1], sm.piece[1], FL_PIECE, lane, FB_LT);
+        if (kidx_in) {  // k_flank_exact_t left both tables in HBM
+          const uint4 *s4 = (const uint4 *)(kidx_in + (size_t)l * 2 * TRGT_KIDX_SLOTS);
+          for (int i = lane; i < (int)(2 * TRGT_KIDX_SLOTS * sizeof(uint16_t) / 16); i += FB_LT) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared((uint4 *)&sm.slot[0][0] + i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(s4 + i) : "memory");
+          }
+        }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        __syncwarp();
+        g.sync();
 #pragma unroll 1
         for (int side = 0; side < 2; side++) {
           indexed[side] = ps[side] != nullptr && PL[side] >= 16 && PL[side] <= TRGT_KIDX_MAX_P;
-          if (indexed[side]) kidx_build(g, KmerIndex{sm.slot[side]}, ps[side], PL[side]);
+          if (indexed[side] && !kidx_in) kidx_build(g, KmerIndex{sm.slot[side]}, ps[side], PL[side]);
         }
       }
 #pragma unroll 1
-      for (int i = tile; i < n_list; i += FL_TILES) {  // one pending pair per tile
+      for (int i = lane; i < n_list; i += FB_LT) {  // one pending pair per lane
         const int side = sm.list[i] & 1;
         const uint32_t r = rb_pass + (uint32_t)(sm.list[i] >> 1);
         int deferred = 1;
         FlankHit fh;
         fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
         if (indexed[side]) {
+          int ws[FT1_WS_INTS];
           WfaProb pr;
           pr.x = src.x; pr.oe = src.oe; pr.e = src.e;
           pr.p = ps[side]; pr.P = PL[side];
@@ -362,24 +379,20 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
           pr.T = (int)(src.read_off[r + 1] - src.read_off[r]);
           pr.pbf = 0; pr.pef = 0; pr.tbf = pr.T; pr.tef = pr.T;  // span_locater.rs:17
           wfa_unband(pr);
-          deferred = flank_locate_banded_lean(tg, pr, band_budget, min_flank_id_frac, sm.ws[tile], FL_WS1_INTS, &fh,
-                                              KmerIndex{sm.slot[side]}, sm.cand[tile], 0, 0);
+          deferred = flank_locate_tier1_thread(pr, band_budget, min_flank_id_frac, ws, &fh, KmerIndex{sm.slot[side]});
         }
-        if (tg.lane() == 0) {
-          trgt_flank_hit_t h;
-          h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
-          if (!deferred) {
-            h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
-            h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
-          } else {
-            const unsigned int slot = atomicAdd(&ctr->n_tier2, 1u);
-            work2[slot] = 2 * r + (uint32_t)side;
-          }
-          hits[2 * r + side] = h;
+        trgt_flank_hit_t h;
+        h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
+        if (!deferred) {
+          h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
+          h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
+        } else {
+          const unsigned int slot = atomicAdd(&ctr->n_tier2, 1u);
+          work2[slot] = 2 * r + (uint32_t)side;
         }
-        tg.sync();
+        hits[2 * r + side] = h;
       }
-      __syncwarp();
+      g.sync();
     }
   }
 }

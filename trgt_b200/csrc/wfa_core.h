@@ -1128,6 +1128,148 @@ TRGT_HD int flank_locate_banded_lean(const G &g, const WfaProb &pr, int S, doubl
   return 1;
 }
 
+// ---------------------------------------------------------------- first cost tier, one lane per pair ---
+
+// The first cost tier of the fallback (cost <= max(x, o+e): one mismatch or one 1-bp gap, ~89 % of HiFi
+// misses) by ONE lane: such a pair lives on 3-4 diagonals, which is no work for a group, and one lane per
+// pair needs no collectives at all.  Same three steps as flank_locate_banded_lean -- index seed filter,
+// narrow-band forward pass with history, back-trace -- with the history (<= FT1_WS_INTS ints, same layout
+// as wfa_forward_band_hist_narrow so that wfa_backtrace runs on it unchanged) in the lane's own scratch.
+#define FT1_WMAX 4      // widest band taken
+#define FT1_SMAX 8      // highest cost cap taken
+#define FT1_WS_INTS (TRGT_WFA_META * (FT1_SMAX + 1) + 3 * FT1_WMAX * (FT1_SMAX + 1))
+
+// flank_seed_band_indexed by one lane.  Two loops, so that the lanes of a warp (each on its own pair)
+// stay together: first every probe's candidates are collected, then they are verified.
+#define FT1_CANDS 12  // candidates a lane keeps; more (repetitive pieces) hands the pair on
+TRGT_HD int flank_seed_band_thread(const KmerIndex &idx, const WfaProb &pr, int S, int *klo, int *khi) {
+  const int emin = wfa_imin(pr.x, pr.oe);
+  const int nb = S / emin + 1;
+  if (nb > 32) return 0;
+  const int blen = pr.P / nb;
+  if (blen < 12 || pr.T < blen) return 0;
+  const int o = pr.oe - pr.e;
+  const int R = S > o ? (S - o) / pr.e : 0;
+  const int step = blen - 7;
+  const int n_probes = (pr.T - 7) / step;
+  int cand[FT1_CANDS];  // block start in the text << 5 | block
+  int n = 0;
+  for (int i = 0; i < n_probes; i++) {
+    const int j = (i + 1) * step - 1;
+    const uint64_t mixed = kidx_mix(wfa_ld64u(pr.t + j));
+    const uint32_t fp = kidx_fp(mixed);
+    for (uint32_t h = kidx_home(mixed), v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+      if ((v >> 9) != fp) continue;
+      const int d = (int)(v & 511u), b = d / blen, q = j - (d - b * blen);
+      if (b >= nb || d - b * blen + 8 > blen || q < 0 || q + blen > pr.T) continue;
+      if (n == FT1_CANDS) return -2;
+      cand[n++] = (q << 5) | b;
+    }
+  }
+  int kmin = INT_MAX, kmax = INT_MIN;
+  for (int c = 0; c < n; c++) {
+    const int q = cand[c] >> 5, b = cand[c] & 31, k = q - b * blen;
+    if (k >= kmin && k <= kmax) continue;  // would not move the band
+    if (wfa_match_len(pr.p + b * blen, pr.t + q, blen) == blen) {
+      kmin = wfa_imin(kmin, k);
+      kmax = wfa_imax(kmax, k);
+    }
+  }
+  if (kmin == INT_MAX) return 0;
+  *klo = wfa_imax(-pr.P, kmin - R);
+  *khi = wfa_imin(pr.T, kmax + R);
+  if (*khi + pr.P >= pr.T) return 0;  // see flank_seed_band
+  return 1;
+}
+
+// wfa_forward_band_hist_narrow by one lane (it walks the band's diagonals itself)
+TRGT_HD WfaEnd wfa_forward_band_hist_narrow_thread(const WfaProb &pr, int s_cap, int *ws, size_t cap_ints) {
+  WfaEnd out;
+  out.status = TRGT_WFA_OK; out.s = 0; out.k = 0; out.off = 0;
+  const int W = pr.bhi - pr.blo + 1;
+  const size_t hdr = (size_t)TRGT_WFA_META * ((size_t)s_cap + 1);
+  unsigned long long present = 0;
+  for (int s = 0; s <= s_cap; s++) {
+    const int sx = s - pr.x, so = s - pr.oe, se = s - pr.e;
+    const bool px = sx >= 0 && ((present >> sx) & 1ull), po = so >= 0 && ((present >> so) & 1ull);
+    const bool pe = se >= 1 && ((present >> se) & 1ull);
+    const bool live = s == 0 || px || po || pe;
+    const size_t base = hdr + (size_t)3 * W * s;
+    if (live && base + (size_t)3 * W > cap_ints) { out.status = TRGT_WFA_OOM; return out; }
+    int *meta = ws + (size_t)TRGT_WFA_META * s;
+    meta[0] = meta[2] = live ? pr.blo : 1;
+    meta[1] = meta[3] = live ? pr.bhi : 0;
+    meta[4] = (int)(unsigned)(base & 0xffffffffu);
+    meta[5] = (int)(unsigned)(base >> 32);
+    if (!live) continue;
+    const int *mo = ws + hdr + (size_t)3 * W * (so > 0 ? so : 0);
+    const int *me = ws + hdr + (size_t)3 * W * (se > 0 ? se : 0);
+    const int *mxs = ws + hdr + (size_t)3 * W * (sx > 0 ? sx : 0);
+    int endk = INT_MAX;
+    for (int idx = 0; idx < W; idx++) {
+      const int k = pr.blo + idx;
+      int mx = TRGT_WFA_NULL;
+      if (s == 0) {
+        if (k >= -pr.pbf && k <= pr.tbf) mx = k >= 0 ? k : 0;
+      } else {
+        const int o_l = (po && idx > 0) ? mo[idx - 1] : TRGT_WFA_NULL;
+        const int o_r = (po && idx + 1 < W) ? mo[idx + 1] : TRGT_WFA_NULL;
+        const int i_l = (pe && idx > 0) ? me[W + idx - 1] : TRGT_WFA_NULL;
+        const int d_r = (pe && idx + 1 < W) ? me[2 * W + idx + 1] : TRGT_WFA_NULL;
+        const int i1 = wfa_imax(o_l, i_l) + 1;
+        const int d1 = wfa_imax(o_r, d_r);
+        const int mm = (px ? mxs[idx] : TRGT_WFA_NULL) + 1;
+        mx = wfa_imax(mm, wfa_imax(i1, d1));
+        const int h = mx, v = mx - k;
+        if (mx < 0 || h > pr.T || v > pr.P || v < 0) mx = TRGT_WFA_NULL;
+        ws[base + W + idx] = i1;
+        ws[base + 2 * W + idx] = d1;
+      }
+      if (mx >= 0) {  // match extension along the diagonal
+        const int v = mx - k, n = wfa_imin(pr.P - v, pr.T - mx);
+        if (n > 0) mx += wfa_match_len(pr.p + v, pr.t + mx, n);
+      }
+      ws[base + idx] = mx;
+      if (endk == INT_MAX && mx >= 0) {  // end condition, lowest diagonal first
+        const int h = mx, v = mx - k;
+        if (v >= 0 && v <= pr.P && h <= pr.T &&
+            ((h >= pr.T && pr.P - v <= pr.pef) || (v >= pr.P && pr.T - h <= pr.tef))) endk = k;
+      }
+    }
+    present |= 1ull << s;
+    if (endk != INT_MAX) {
+      out.s = s; out.k = endk; out.off = ws[base + (endk - pr.blo)];
+      return out;
+    }
+  }
+  out.status = TRGT_WFA_MAX_STEPS;
+  return out;
+}
+
+// 0 and *hit filled, or 1 if the pair has to go on to the next tier.  ws: FT1_WS_INTS ints of the lane.
+TRGT_HD int flank_locate_tier1_thread(const WfaProb &pr, int S, double min_flank_id_frac, int *ws, FlankHit *hit,
+                                      const KmerIndex &idx) {
+  const int cap = wfa_imin(S, wfa_imax(pr.x, pr.oe));
+  if (cap > FT1_SMAX) return 1;
+  int klo, khi;
+  if (flank_seed_band_thread(idx, pr, cap, &klo, &khi) != 1) return 1;
+  if (khi - klo + 1 > FT1_WMAX) return 1;
+  WfaProb bp = pr;
+  bp.blo = klo; bp.bhi = khi;
+  const WfaEnd end = wfa_forward_band_hist_narrow_thread(bp, cap, ws, FT1_WS_INTS);
+  if (end.status != TRGT_WFA_OK) return 1;
+  WfaFlankSink sink(pr.T);
+  wfa_backtrace(pr, end.s, end.k, end.off, ws, sink);
+  hit->matches = sink.matches;
+  hit->score = -end.s;
+  if ((double)sink.matches >= (double)pr.P * min_flank_id_frac) {  // span_locater.rs:19-25, :46
+    hit->via = 2; hit->start = sink.ystart(); hit->end = sink.yend();
+  } else {
+    hit->via = 3; hit->start = 0; hit->end = 0;
+  }
+  return 0;
+}
+
 // ---------------------------------------------------------------- unit-cost edit distance ------
 
 // Levenshtein distance, one lane per pair: bit-vector DP (Myers 1999, global variant of Hyyro 2003)
