@@ -628,7 +628,8 @@ static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src
     TRY(persistent_grid(e, k_flank_band2, 32, 0, &grid));
     LaunchScope ls(e, "k_flank_band2");
     k_flank_band2<<<grid, 32, 0, e->stream>>>(src, (const uint32_t *)b->work2.p, &ctr->n_tier2, e->band_budget, b->frac,
-                                              (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p, ctr);
+                                              (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work.p, ctr,
+                                              b->kidx_valid ? (const uint16_t *)b->kidx.p : nullptr);
     TRY(check_launch(e, "k_flank_band2"));
   }
   if (e->band_budget > 0) {
@@ -1065,7 +1066,7 @@ struct trgt_align_batch {
   uint32_t n_groups = 0, n_seqs = 0;
   int Pmax = 0, Tmax = 0;
   DevBuf bb, bb_off, seqs, seq_off, group_off, seq_group;
-  DevBuf ends, trace_work, cig_n, cig_off, pool, ctr, gring, gws;
+  DevBuf ends, trace_work, resid, cig_n, cig_off, pool, ctr, gring, gws;
   DevBuf out_off, out_words, scores, status;
   DevBuf cons_counts, cons_recs, cons_len, cons_status, cons_off, cons_data;
   PinBuf h_cons_off, h_cons_data, h_cons_status;
@@ -1104,7 +1105,7 @@ void trgt_align_free(trgt_engine_t *e, trgt_align_batch_t *b) {
   DevBuf *all[] = {&b->bb, &b->bb_off, &b->seqs, &b->seq_off, &b->group_off, &b->seq_group, &b->ends, &b->trace_work,
                    &b->cig_n, &b->cig_off, &b->pool, &b->ctr, &b->gring, &b->gws, &b->out_off, &b->out_words,
                    &b->scores, &b->status, &b->cons_counts, &b->cons_recs, &b->cons_len, &b->cons_status,
-                   &b->cons_off, &b->cons_data};
+                   &b->cons_off, &b->cons_data, &b->resid};
   for (auto *d : all) dev_free(*d);
   pin_free(b->h_off); pin_free(b->h_words); pin_free(b->h_scores); pin_free(b->h_status);
   pin_free(b->h_cons_off); pin_free(b->h_cons_data); pin_free(b->h_cons_status);
@@ -1224,8 +1225,21 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
     // CIGAR pool of the one-pass path (pairs it cannot place fall through to the two-pass path)
     pool_cap1 = 2ull * n + 65536ull;
     TRY(dev_reserve(e, b->pool, (size_t)(pool_cap1 + 1) * sizeof(uint32_t)));
+    // one lane per pair first: identical members and cheap alignments end there
+    TRY(dev_reserve(e, b->resid, ((size_t)n + 1) * sizeof(uint32_t)));
+    {
+      int tgrid = 0;
+      TRY(persistent_grid(e, k_e2e_thread, 128, 0, &tgrid));
+      const uint32_t tneed = (n + 127) / 128;
+      if ((uint32_t)tgrid > tneed) tgrid = (int)tneed;
+      LaunchScope ls(e, "k_e2e_thread");
+      k_e2e_thread<<<tgrid, 128, 0, e->stream>>>(src, n, (WfaEnd *)b->ends.p, (uint32_t *)b->cig_n.p,
+                                                 (unsigned long long *)b->cig_off.p, (uint32_t *)b->pool.p, pool_cap1,
+                                                 (uint32_t *)b->resid.p, ctr);
+      TRY(check_launch(e, "k_e2e_thread"));
+    }
     LaunchScope ls(e, "k_wfa_score_warp");
-    k_wfa_score<false><<<grid, block, smem, e->stream>>>(src, nullptr, nullptr, n, (WfaEnd *)b->ends.p, gring, stride,
+    k_wfa_score<false><<<grid, block, smem, e->stream>>>(src, (const uint32_t *)b->resid.p, &ctr->n_resid, 0, (WfaEnd *)b->ends.p, gring, stride,
                                                           smem_ring_ints, (uint32_t *)b->trace_work.p,
                                                           (uint32_t *)b->cig_n.p, ctr, (uint32_t *)b->pool.p, pool_cap1,
                                                           (unsigned long long *)b->cig_off.p);

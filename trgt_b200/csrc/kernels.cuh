@@ -35,7 +35,7 @@ struct Counters {
   unsigned int n_failed;                // items that ended with a non-OK status
   unsigned int n_banded;                // flank: pairs settled by k_flank_band_wide
   unsigned int n_tier2;                 // flank: pairs the first cost tier handed to k_flank_band2
-  unsigned int pad2;
+  unsigned int n_resid;                 // e2e: pairs k_e2e_thread handed to the warp kernel
 };
 
 enum { WFA_MODE_FLANK = 0, WFA_MODE_E2E = 1 };
@@ -411,7 +411,7 @@ struct __align__(16) FlankBand2Smem {
 __global__ void __launch_bounds__(32)
 k_flank_band2(WfaSrc src, const uint32_t *__restrict__ work2, const unsigned int *n_work2_ptr, int band_budget,
               double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits, uint32_t *__restrict__ work,
-              Counters *ctr) {
+              Counters *ctr, const uint16_t *__restrict__ kidx_in) {
   __shared__ FlankBand2Smem sm;
   const WarpGroup g;
   const int lane = g.lane();
@@ -422,6 +422,13 @@ k_flank_band2(WfaSrc src, const uint32_t *__restrict__ work2, const unsigned int
     __syncwarp();
     const uint8_t *p_s = stage_bytes(gp.p, gp.P, sm.piece, FL_PIECE, lane, 32);
     const uint8_t *t_s = stage_bytes(gp.t, gp.T, sm.txt, FL_TXT, lane, 32);
+    if (kidx_in) {  // the piece's table as k_flank_exact_t left it in HBM (1 KB)
+      const uint4 *s4 = (const uint4 *)(kidx_in + ((size_t)src.read_locus[id >> 1] * 2 + (id & 1u)) * TRGT_KIDX_SLOTS);
+      for (int i = lane; i < (int)(TRGT_KIDX_SLOTS * sizeof(uint16_t) / 16); i += 32) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared((uint4 *)&sm.slot[0] + i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(s4 + i) : "memory");
+      }
+    }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncwarp();
@@ -430,7 +437,7 @@ k_flank_band2(WfaSrc src, const uint32_t *__restrict__ work2, const unsigned int
     fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
     if (p_s != nullptr && t_s != nullptr && gp.P >= 16 && gp.P <= TRGT_KIDX_MAX_P) {
       const KmerIndex idx{sm.slot};
-      kidx_build(g, idx, p_s, gp.P);
+      if (!kidx_in) kidx_build(g, idx, p_s, gp.P);
       WfaProb pr = gp;
       pr.p = p_s; pr.t = t_s;
       deferred = flank_locate_banded_lean(g, pr, band_budget, min_flank_id_frac, sm.ws, FL_WS_INTS, &fh, idx, sm.cand, 1, 1);
@@ -516,6 +523,66 @@ k_tr_gather(const uint8_t *__restrict__ reads, const uint64_t *__restrict__ read
 #define E2E_NARROW_INTS 1280  // its history: 6*17 header + 3 * 23 diagonals * 17 scores
 #define E2E_NARROW_WORDS 48   // its CIGAR: at most 2 * cost + a few words
 
+// Phase B, first step for short repeat sequences: ONE LANE PER (backbone, member) PAIR.  A member equal
+// to its backbone (92 % on HiFi) is a single '=' run; otherwise the lane runs the end-to-end alignment
+// itself with cost cap E2T_COST: every cell the full computation can reach then lies on
+// |k| <= (E2T_COST - o) / e, so the band of <= E2T_W diagonals IS the full computation (wfa_e2e_narrow's
+// argument), its history sits in the lane's local memory and the CIGAR comes straight from the
+// back-trace.  Costlier pairs are appended to `resid` for the warp kernel.
+#define E2T_COST 8
+#define E2T_W 7
+#define E2T_WS_INTS (TRGT_WFA_META * (E2T_COST + 1) + 3 * E2T_W * (E2T_COST + 1))
+#define E2T_WORDS 32
+
+__global__ void __launch_bounds__(128)
+k_e2e_thread(WfaSrc src, uint32_t n, WfaEnd *__restrict__ ends, uint32_t *__restrict__ cig_n,
+             unsigned long long *__restrict__ cig_off, uint32_t *__restrict__ pool, unsigned long long pool_cap,
+             uint32_t *__restrict__ resid, Counters *ctr) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gsz) {
+    const WfaProb pr = wfa_prob_of(src, id);
+    WfaEnd end;
+    if (pr.P == pr.T && (pr.P == 0 || wfa_match_len(pr.p, pr.t, pr.P) == pr.P)) {
+      end.status = TRGT_WFA_OK; end.s = 0; end.k = 0; end.off = pr.T;
+      ends[id] = end;
+      cig_n[id] = pr.P > 0 ? 1u : 0u;
+      continue;
+    }
+    bool done = false;
+    const int o = pr.oe - pr.e;
+    const int R = E2T_COST > o ? (E2T_COST - o) / pr.e : 0;
+    WfaProb bp = pr;
+    bp.blo = wfa_imax(-pr.P, -R);
+    bp.bhi = wfa_imin(pr.T, R);
+    if (bp.bhi - bp.blo + 1 <= E2T_W) {
+      int ws[E2T_WS_INTS];
+      end = wfa_forward_band_hist_narrow_thread(bp, E2T_COST, ws, E2T_WS_INTS);
+      if (end.status == TRGT_WFA_OK) {
+        uint32_t wbuf[E2T_WORDS];
+        WfaCigarSink sink(wbuf, E2T_WORDS);
+        wfa_backtrace(pr, end.s, end.k, end.off, ws, sink);
+        const uint32_t nw = sink.finish();
+        if (!sink.overflow) {
+          unsigned long long off = 0;
+          bool ok = true;
+          if (nw) {
+            off = atomicAdd(&ctr->pool_used, (unsigned long long)nw);
+            if (off + nw > pool_cap) ok = false;  // pool full: the warp kernel's generic path takes the pair
+          }
+          if (ok) {
+            for (uint32_t w = 0; w < nw; w++) pool[off + w] = wbuf[w];
+            cig_off[id] = off;
+            cig_n[id] = nw;
+            ends[id] = end;
+            done = true;
+          }
+        }
+      }
+    }
+    if (!done) resid[atomicAdd(&ctr->n_resid, 1u)] = id;
+  }
+}
+
 template <bool BLOCK>
 __global__ void k_wfa_score(WfaSrc src, const uint32_t *__restrict__ work, const unsigned int *n_work_ptr,
                             uint32_t n_direct, WfaEnd *__restrict__ ends, int *gring, size_t gring_stride,
@@ -550,7 +617,7 @@ __global__ void k_wfa_score(WfaSrc src, const uint32_t *__restrict__ work, const
         if (pr.P == pr.T && (pr.P == 0 || wfa_match_len(pr.p, pr.t, pr.P) == pr.P)) {
           WfaEnd end;
           end.status = TRGT_WFA_OK; end.s = 0; end.k = 0; end.off = pr.T;
-          ends[i] = end;
+          ends[id] = end;  // e2e mode: results are indexed by sequence
           cig_n[id] = pr.P > 0 ? 1u : 0u;  // a single '=' run
         } else {
           pending = true;
@@ -587,7 +654,7 @@ __global__ void k_wfa_score(WfaSrc src, const uint32_t *__restrict__ work, const
                 for (uint32_t w = 0; w < nw; w++) pool[off + w] = wbuf[w];
                 cig_off[id] = off;
                 cig_n[id] = nw;
-                ends[ii] = end;
+                ends[id] = end;
               }
               my_smem[0] = ok ? 1 : 0;
             }
@@ -606,7 +673,7 @@ __global__ void k_wfa_score(WfaSrc src, const uint32_t *__restrict__ work, const
           __syncwarp();
         }
         if (lane0) {
-          ends[ii] = end;
+          ends[id] = end;
           if (end.status != TRGT_WFA_OK) {
             atomicAdd(&ctr->n_failed, 1u);
             cig_n[id] = 0;
