@@ -43,8 +43,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident-only", action="store_true",
                     help="profiling aid: skip the end-to-end driver so that every launch is a whole-shard launch")
-    ap.add_argument("--chunk-loci", type=int, default=15625, help="loci per chunk of the end-to-end driver")
-    ap.add_argument("--host-threads", type=int, default=4, help="host threads (one engine each) of the e2e driver")
+    ap.add_argument("--chunk-loci", type=int, default=0,
+                    help="loci per chunk of the end-to-end driver (0: two chunks per host thread)")
+    ap.add_argument("--host-threads", type=int, default=0,
+                    help="host threads (one engine each) of the e2e driver (0: host cores / ranks, between 2 and 8)")
     ap.add_argument("--e2e-input", default="seq4", choices=["seq4", "ascii"],
                     help="how the e2e driver hands reads to phase A: BAM 4-bit bases (trgt_flank_spans_seq4) or ASCII")
     return ap.parse_args()
@@ -252,6 +254,10 @@ def run_b200(args):
     hp = HotPath(eng, w, want_hits=True, pinned_outputs=True)  # hits: to count the fallback pairs for the roofline
 
     # end-to-end driver: chunks of loci through `host_threads` engines on this GPU
+    if args.host_threads <= 0:
+        args.host_threads = max(2, min(8, host_cores() // max(1, world)))
+    if args.chunk_loci <= 0:
+        args.chunk_loci = -(-args.loci // (2 * args.host_threads))
     engines = [eng] + [trgt_b200.Engine(device=local_rank) for _ in range(max(1, args.host_threads) - 1)]
     # host cores are shared by all ranks of the box and all host threads of a rank
     glue_threads = max(1, host_cores() // max(1, world * len(engines)))
