@@ -426,6 +426,35 @@ def run_b200(args):
         except Exception as exc:  # never let the extra row break the headline line
             consensus = {"error": repr(exc)}
 
+    # ---- next row: VCF sample fields encoded behind phase C, timed on its own ----
+    vcf = None
+    if world == 1:
+        try:
+            eng.vcf_fields(hp._hb)  # warm-up
+            t0 = time.perf_counter()
+            fields = eng.vcf_fields(hp._hb)
+            dt = time.perf_counter() - t0
+            vcf = {"call": "trgt_vcf_fields (AL / MC / MS / AP of write_vcf.rs:267-343, device buffers in, host strings out)",
+                   "records": len(fields), "ms": dt * 1e3, "records_per_s": len(fields) / dt,
+                   "bytes": int(sum(len(x) for f in fields for x in f))}
+            if not args.no_cpu_baseline:
+                from oracle import oracle as orc
+                a = res_resident.annotations
+                nchk = min(len(fields), 2000)
+                same = 0
+                gl = hp.glue.group_locus  # alleles = backbones, grouped by locus
+                lo = np.searchsorted(gl, np.arange(nchk), side="left")
+                hi = np.searchsorted(gl, np.arange(nchk), side="right")
+                for li in range(nchk):
+                    als = []
+                    for ai in range(int(lo[li]), int(hi[li])):
+                        x = a.annotation(ai)
+                        als.append((len(hp.glue.backbones.get(ai)), x.motif_counts, x.labels, x.purity))
+                    same += fields[li] == orc.vcf_fields(als)
+                vcf["parity"] = f"{same}/{nchk} records identical to the oracle"
+        except Exception as exc:  # never let the extra row break the headline line
+            vcf = {"error": repr(exc)}
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -435,7 +464,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),
                 "reads_in": "BAM 4-bit bases (trgt_flank_spans_seq4), decoded on the device" if use_seq4 else "ASCII (trgt_flank_spans)",
                 "glue_threads": glue_threads, "phase_ms_summed_over_host_threads": e2e_phases},
-        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "kernels": kernels,
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "vcf_row": vcf, "kernels": kernels,
         "wfa_fallback_pairs": hp.n_wfa(), "flank_fallback_counts": dict(zip(("second_tier", "wide_band", "full_width"), hp.fallback_counts())),
         "workload_gen_s": t_gen,
     }

@@ -301,6 +301,19 @@ int32_t trgt_hmm_run(trgt_engine_t *eng, trgt_hmm_batch_t *batch);
 int32_t trgt_hmm_download(trgt_engine_t *eng, trgt_hmm_batch_t *batch, trgt_annotations_t *out);
 void trgt_hmm_free(trgt_engine_t *eng, trgt_hmm_batch_t *batch);
 
+/* ---- VCF sample fields behind phase C (next row, rank 4) --------------------- */
+
+/* The sample fields the engine's results determine, as the reference's writer encodes them
+ * (src/trgt/writers/write_vcf.rs: encode_al :267-277, encode_mc :286-299, encode_ms :307-323,
+ * encode_ap :332-343), for every locus of an HMM batch that has been run (batch == NULL: the last
+ * trgt_hmm_label call).  The alleles of a locus must be consecutive in the batch, in genotype order.
+ * out->n = 4 * n_loci strings, locus after locus in the order AL, MC, MS, AP ("33,33", "11,11",
+ * "0(0-33),0(0-33)", "1.000000,1.000000" for the tutorial locus, docs/tutorial.md:44); a locus without
+ * alleles gets four empty strings; out->status is NULL.  `{:.6}` is rounded half to even on the exact
+ * binary value, as Rust prints it.  out points into engine-owned pinned memory valid until the next
+ * trgt_vcf_fields on the same batch.  GT, ALLR, SD and AM come from the host genotyper. */
+int32_t trgt_vcf_fields(trgt_engine_t *eng, trgt_hmm_batch_t *batch, trgt_seqs_out_t *out);
+
 /* ---- instrumentation ------------------------------------------------------ */
 
 /* When enabled, every kernel launch is bracketed by CUDA events on the engine stream. */

@@ -127,6 +127,8 @@ def lib():
         L.tro_clip_cigar.argtypes = [vp, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_Clip)]
         L.tro_decode_seq4.argtypes = [vp, C.c_uint64, C.c_uint32, vp]
         L.tro_decode_seq4.restype = None
+        L.tro_vcf_field.restype = C.c_size_t
+        L.tro_vcf_field.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_char_p, C.c_size_t]
         L.tro_free.argtypes = [vp]
         L.tro_free.restype = None
         _lib = L
@@ -496,3 +498,32 @@ def decode_seq4(packed: bytes, start: int, length: int) -> bytes:
     out = np.zeros(max(1, length), dtype=np.uint8)
     lib().tro_decode_seq4(src.ctypes.data, start, length, out.ctypes.data)
     return out[:length].tobytes()
+
+
+# ------------------------------------------------------------------ next row: VCF sample fields --
+
+def vcf_fields(alleles):
+    """(AL, MC, MS, AP) of one locus (write_vcf.rs:267-343).  alleles = [(allele_len, motif_counts,
+    spans or None, purity)] in genotype order, spans = [(motif_index, start, end)]."""
+    np = _np()
+    n = len(alleles)
+    lens = np.array([a[0] for a in alleles] + [0], dtype=np.uint64)
+    mc_off = np.zeros(n + 1, dtype=np.uint64)
+    sp_off = np.zeros(n + 1, dtype=np.uint64)
+    mc, sp = [], []
+    for i, (_, counts, spans, _) in enumerate(alleles):
+        mc += list(counts)
+        sp += [x for s_ in (spans or []) for x in s_]
+        mc_off[i + 1] = len(mc)
+        sp_off[i + 1] = len(sp) // 3
+    mca = np.array(mc + [0], dtype=np.uint32)
+    spa = np.array(sp + [0], dtype=np.uint32)
+    pur = np.array([a[3] for a in alleles] + [0.0], dtype=np.float64)
+    out = []
+    for f in range(4):
+        buf = C.create_string_buffer(1 << 16)
+        ln = lib().tro_vcf_field(f, n, lens.ctypes.data, mc_off.ctypes.data, mca.ctypes.data, sp_off.ctypes.data,
+                                 spa.ctypes.data, pur.ctypes.data, buf, len(buf))
+        assert ln <= len(buf)
+        out.append(buf.raw[:ln])
+    return tuple(out)

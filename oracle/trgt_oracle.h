@@ -182,6 +182,14 @@ int tro_clip_cigar(const uint32_t *ops, uint32_t n_ops, int64_t ref_start, int64
 /* rec.seq().as_bytes() (read.rs:104) for bases [start, start+len) of a BAM 4-bit sequence */
 void tro_decode_seq4(const uint8_t *packed, uint64_t start, uint32_t len, uint8_t *out);
 
+/* ------------------------------------------ next row: VCF sample fields -- */
+
+/* One field (0 AL, 1 MC, 2 MS, 3 AP) of one locus: src/trgt/writers/write_vcf.rs:267-343.  Returns the
+ * field's length; the bytes are written when they fit cap. */
+size_t tro_vcf_field(int field, uint32_t n_alleles, const uint64_t *allele_len, const uint64_t *mc_off,
+                     const uint32_t *mc, const uint64_t *span_off, const tro_span *spans, const double *purity,
+                     char *out, size_t cap);
+
 /* ------------------------------------------- batched CPU baseline path -- */
 
 /* Batched, multi-threaded drivers (batch_oracle.c) over the per-item functions above.  They take the

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "../../trgt_b200/csrc/clip_core.h"
+#include "../../trgt_b200/csrc/vcf_core.h"
 #include "lanes.h"
 
 using namespace trgt;
@@ -26,6 +27,14 @@ void emu_seq4_unpack(const uint8_t *data, const uint64_t *starts, const uint32_t
       seq4_unpack_read(g, data, starts[r], lengths[r], out, out_off[r]);
     });
   }
+}
+
+// format!("{:.6}", v) of vcf_core.h into out (cap >= 40); returns the length, -1 if the value is not taken
+int emu_vcf_fixed6(double v, char *out) {
+  VcfWriter w;
+  w.out = (uint8_t *)out; w.n = 0;
+  if (!vcf_put_fixed6(w, v)) return -1;
+  return (int)w.n;
 }
 
 }  // extern "C"

@@ -636,3 +636,29 @@ def test_flank_tier1_thread_core(emul, oracle):
         if exp is not None:
             assert (out[4], out[5]) == exp, (it, x, o, e)
     assert seen["settled"] > 700 and seen["handed_on"] > 50 and seen["rejected"] > 5, seen
+
+
+def test_vcf_fixed6_core(emul):
+    """{:.6} of the VCF writer (write_vcf.rs:339) by exact 128-bit integer arithmetic: identical to the
+    correctly rounded decimal (Python's format, itself exact, ties to even) on purity-like ratios, on exact
+    ties such as 1 - 1/128 and on random doubles"""
+    import struct
+    emul.emu_vcf_fixed6.argtypes = [C.c_double, C.c_char_p]
+    rng = random.Random(6)
+    vals = [0.0, 1.0, 0.5, 1 - 1 / 128, 1 / 128, 3 / 128, 0.9921875, 0.0078125, 1e-7, 4.9999995e-7, 5e-7, 0.1, 0.85,
+            17 / 20, 18 / 26, 11 / 12, 123456.7890125, 2.5e-6 / 2, 1 - 2 ** -53, 2 ** -1074, 7.0, 999999.9999995,
+            -0.5, -1e-9, 4503599627370495.5 / 1e6]
+    vals += [a / b for b in range(1, 140) for a in range(0, b + 1, max(1, b // 7))]
+    vals += [rng.random() for _ in range(3000)]
+    vals += [struct.unpack("<d", struct.pack("<Q", rng.getrandbits(62) % (0x433 << 52)))[0] for _ in range(3000)]
+    vals += [(2 * k + 1) / 2 ** rng.randint(7, 20) for k in range(400)]   # dyadic: exact decimal ties occur
+    n = 0
+    for v in vals:
+        buf = C.create_string_buffer(64)
+        ln = emul.emu_vcf_fixed6(v, buf)
+        if ln < 0:
+            assert abs(v) * 1e6 >= 2 ** 62
+            continue
+        assert buf.raw[:ln].decode() == format(v, ".6f"), v
+        n += 1
+    assert n > 6000

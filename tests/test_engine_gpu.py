@@ -503,3 +503,42 @@ def test_flank_trs_are_the_span_slices(engine, oracle):
                               np.array([0, 3], dtype=np.uint32), w.scoring, w.min_flank_id_frac)
     t0 = engine.flank_trs(copy=True)
     assert len(t0) == 3 and t0.data.size == 0
+
+
+# ------------------------------------------------------------------ VCF sample fields (next row) ---
+
+def test_vcf_fields_tutorial_and_random_parity(engine, oracle):
+    """trgt_vcf_fields behind phase C against the oracle's restatement of write_vcf.rs:267-343; the tutorial
+    locus must give the record of docs/tutorial.md:44"""
+    rng = random.Random(88)
+    loci = [([b"CAG"], [b"CAG" * 11, b"CAG" * 11])]
+    for _ in range(300):
+        k = rng.choice([1, 1, 2, 3])
+        motifs = [rnd(rng, rng.choice([2, 3, 4, 5, 6, 9])) for _ in range(k)]
+        alleles = [noisy_repeat(rng, motifs, rng.choice([1, 6, 30])) for _ in range(rng.choice([0, 1, 2, 2, 3]))]
+        if rng.random() < 0.1 and alleles:
+            alleles[0] = b""
+        loci.append((motifs, alleles))
+    ann = engine.label_with_hmm(loci)
+    got = engine.vcf_fields()
+    assert len(got) == len(loci)
+    assert got[0] == (b"33,33", b"11,11", b"0(0-33),0(0-33)", b"1.000000,1.000000")
+    n_none = 0
+    for (motifs, alleles), a, g in zip(loci, ann, got):
+        exp = oracle.vcf_fields([(len(s), x.motif_counts, x.labels, x.purity) for s, x in zip(alleles, a)])
+        assert g == exp, (motifs, alleles)
+        n_none += b"." in g[2].split(b",")
+    assert n_none > 5
+    stats = engine.kernel_stats()
+    assert "k_vcf_fields_count" in stats and "k_vcf_fields_write" in stats
+    # an invalid base: the reference panics; the allele's MC / MS / AP read '.'
+    engine.label_with_hmm([([b"CAG"], [b"CAGCAG", b"CAGXAG"])])
+    bad = engine.vcf_fields()
+    assert bad[0][0] == b"6,6" and bad[0][1].count(b",") == 1
+    # alleles not grouped by locus -> argument error, not a wrong answer
+    from trgt_b200 import PackedSeqs, TrgtError
+    m = PackedSeqs.from_list([b"CAG", b"AT"])
+    al = PackedSeqs.from_list([b"CAGCAG", b"ATAT", b"CAGCAGCAG"])
+    engine.hmm_label_packed(m, np.array([0, 1, 2], dtype=np.uint32), al, np.array([0, 1, 0], dtype=np.uint32))
+    with pytest.raises(TrgtError):
+        engine.vcf_fields()

@@ -376,3 +376,23 @@ def test_seq4_alphabet(oracle):  # read.rs:104: htslib's "=ACMGRSVTWYHKDBN", fir
     assert oracle.decode_seq4(bytes(range(256)), 0, 512) == bytes(
         oracle.SEQ4_ALPHABET[(i >> 4) if j == 0 else (i & 15)] for i in range(256) for j in (0, 1))
     assert oracle.decode_seq4(b"", 0, 0) == b""
+
+
+# ------------------------------------------------------------- VCF sample fields (next row) --
+
+def test_vcf_fields_tutorial_record(oracle):
+    """docs/tutorial.md:44: AL 33,33  MC 11,11  MS 0(0-33),0(0-33)  AP 1.000000,1.000000, from the oracle's own
+    annotation of the two CAG x 11 alleles"""
+    h = oracle.Hmm([b"CAG"])
+    alleles = []
+    for seq in (b"CAG" * 11, b"CAG" * 11):
+        mc, spans, pur = h.annotate(seq)
+        alleles.append((len(seq), mc, spans, pur))
+    assert oracle.vcf_fields(alleles) == (b"33,33", b"11,11", b"0(0-33),0(0-33)", b"1.000000,1.000000")
+
+
+def test_vcf_fields_shapes(oracle):  # write_vcf.rs:286-343: '_' within an allele, ',' between, '.' for None / NaN
+    got = oracle.vcf_fields([(17, [4, 5], [(0, 0, 12), (1, 12, 17)], 1.0), (0, [0, 0], None, float("nan")),
+                             (20, [3, 0], [(0, 2, 11)], 17 / 20)])
+    assert got == (b"17,0,20", b"4_5,0_0,3_0", b"0(0-12)_1(12-17),.,0(2-11)", b"1.000000,.,0.850000")
+    assert oracle.vcf_fields([]) == (b"", b"", b"", b"")

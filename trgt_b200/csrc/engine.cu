@@ -1448,6 +1448,9 @@ struct trgt_hmm_batch {
   DevBuf motifs, motif_off, locus_motif_off, alleles, allele_off, allele_locus, bp_off, mc_off;
   DevBuf bp, mc, purity, n_spans, span_off, spans, path_len, path_off, paths, status;
   std::vector<unsigned long long> h_bp_off, h_mc_off;
+  std::vector<uint32_t> h_locus_allele_off;  // [n_loci+1] when the alleles are grouped by locus, else empty
+  DevBuf locus_allele_off, vcf_len, vcf_off, vcf_data;
+  PinBuf r_vcf_off, r_vcf_data;
   std::vector<std::pair<uint32_t, uint32_t>> waves;
   // host results
   PinBuf r_mc, r_span_off, r_spans, r_purity, r_status, r_path_off, r_paths;
@@ -1466,9 +1469,11 @@ void trgt_hmm_free(trgt_engine_t *e, trgt_hmm_batch_t *b) {
   }
   DevBuf *all[] = {&b->motifs, &b->motif_off, &b->locus_motif_off, &b->alleles, &b->allele_off, &b->allele_locus,
                    &b->bp_off, &b->mc_off, &b->bp, &b->mc, &b->purity, &b->n_spans, &b->span_off, &b->spans,
-                   &b->path_len, &b->path_off, &b->paths, &b->status};
+                   &b->path_len, &b->path_off, &b->paths, &b->status, &b->locus_allele_off, &b->vcf_len, &b->vcf_off,
+                   &b->vcf_data};
   for (auto *d : all) dev_free(*d);
-  PinBuf *pins[] = {&b->r_mc, &b->r_span_off, &b->r_spans, &b->r_purity, &b->r_status, &b->r_path_off, &b->r_paths};
+  PinBuf *pins[] = {&b->r_mc, &b->r_span_off, &b->r_spans, &b->r_purity, &b->r_status, &b->r_path_off, &b->r_paths,
+                    &b->r_vcf_off, &b->r_vcf_data};
   for (auto *q : pins) pin_free(*q);
   delete b;
 }
@@ -1514,6 +1519,16 @@ static int hmm_upload_into(trgt_engine_t *e, trgt_hmm_batch *b, const trgt_seqs_
     if (L > 0x3ffffff0ull) return fail(e, TRGT_ERR_ARG, "allele too long");
     b->h_bp_off[a + 1] = b->h_bp_off[a] + (L ? (L + 2) * (unsigned long long)locus_S[l] : 0);
     b->h_mc_off[a + 1] = b->h_mc_off[a] + (locus_motif_offsets[l + 1] - locus_motif_offsets[l]);
+  }
+  {  // allele range of every locus, if the alleles come grouped by locus (trgt_vcf_fields needs that)
+    bool sorted = true;
+    for (size_t a = 1; a < n && sorted; a++) sorted = allele_locus[a] >= allele_locus[a - 1];
+    b->h_locus_allele_off.clear();
+    if (sorted) {
+      b->h_locus_allele_off.assign((size_t)n_loci + 1, 0);
+      for (size_t a = 0; a < n; a++) b->h_locus_allele_off[allele_locus[a] + 1]++;
+      for (uint32_t l = 0; l < n_loci; l++) b->h_locus_allele_off[l + 1] += b->h_locus_allele_off[l];
+    }
   }
   b->n_loci = n_loci;
   b->n_alleles = (uint32_t)n;
@@ -1744,6 +1759,60 @@ static int hmm_download_locked(trgt_engine_t *e, trgt_hmm_batch *b, trgt_annotat
   out->status = b->r_status.as<int32_t>();
   out->path_offsets = b->want_paths ? b->r_path_off.as<uint64_t>() : nullptr;
   out->paths = b->want_paths ? b->r_paths.as<uint32_t>() : nullptr;
+  return 0;
+}
+
+int32_t trgt_vcf_fields(trgt_engine_t *e, trgt_hmm_batch_t *b, trgt_seqs_out_t *out) {
+  if (!e || !out) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!b) b = e->one_hmm;
+  if (!b || !b->ran) return fail(e, TRGT_ERR_ARG, "trgt_vcf_fields: no HMM batch has been run");
+  if (b->h_locus_allele_off.empty() && b->n_alleles)
+    return fail(e, TRGT_ERR_ARG, "trgt_vcf_fields: the alleles of a locus must be consecutive (allele_locus non-decreasing)");
+  CU(e, cudaSetDevice(e->device));
+  memset(out, 0, sizeof *out);
+  const size_t nf = 4 * (size_t)b->n_loci;
+  TRY(pin_reserve(e, b->r_vcf_off, (nf + 1) * sizeof(uint64_t)));
+  uint64_t *h_off = b->r_vcf_off.as<uint64_t>();
+  h_off[0] = 0;
+  out->n = nf;
+  out->offsets = h_off;
+  if (nf == 0) return 0;
+  if (nf + 1 > 0x7fffffffull) return fail(e, TRGT_ERR_ARG, "too many loci in one batch");
+  if (b->h_locus_allele_off.empty()) b->h_locus_allele_off.assign((size_t)b->n_loci + 1, 0);
+  TRY(h2d(e, b->locus_allele_off, b->h_locus_allele_off.data(), ((size_t)b->n_loci + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->vcf_len, (nf + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->vcf_off, (nf + 1) * sizeof(uint64_t)));
+  CU(e, cudaMemsetAsync((uint32_t *)b->vcf_len.p + nf, 0, sizeof(uint32_t), e->stream));
+  int grid = 0;
+  TRY(persistent_grid(e, k_vcf_fields<false>, 128, 0, &grid));
+  const uint32_t need = (b->n_loci + 127) / 128;
+  if ((uint32_t)grid > need) grid = (int)need;
+#define VCF_ARGS(outp)                                                                                                \
+  b->n_loci, (const uint32_t *)b->locus_allele_off.p, (const uint64_t *)b->allele_off.p,                              \
+      (const unsigned long long *)b->mc_off.p, (const uint32_t *)b->mc.p, (const unsigned long long *)b->span_off.p,  \
+      (const trgt_motif_span_t *)b->spans.p, (const double *)b->purity.p, (const int32_t *)b->status.p,               \
+      (uint32_t *)b->vcf_len.p, (const unsigned long long *)b->vcf_off.p, (outp)
+  {
+    LaunchScope ls(e, "k_vcf_fields_count");
+    k_vcf_fields<false><<<grid, 128, 0, e->stream>>>(VCF_ARGS((uint8_t *)nullptr));
+    TRY(check_launch(e, "k_vcf_fields_count"));
+  }
+  TRY(exclusive_scan_u32(e, (const uint32_t *)b->vcf_len.p, (unsigned long long *)b->vcf_off.p, nf + 1));
+  CU(e, cudaMemcpyAsync(h_off, b->vcf_off.p, (nf + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  const uint64_t total = h_off[nf];
+  TRY(dev_reserve(e, b->vcf_data, (size_t)total + 16));
+  TRY(pin_reserve(e, b->r_vcf_data, (size_t)total + 16));
+  {
+    LaunchScope ls(e, "k_vcf_fields_write");
+    k_vcf_fields<true><<<grid, 128, 0, e->stream>>>(VCF_ARGS((uint8_t *)b->vcf_data.p));
+    TRY(check_launch(e, "k_vcf_fields_write"));
+  }
+#undef VCF_ARGS
+  if (total) CU(e, cudaMemcpyAsync(b->r_vcf_data.p, b->vcf_data.p, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  out->data = b->r_vcf_data.as<uint8_t>();
   return 0;
 }
 

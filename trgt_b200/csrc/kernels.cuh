@@ -11,6 +11,7 @@
 //            k_edit_dist       get_dist_matrix              genotype_cluster.rs:236-286
 //            k_consensus_vote  repair_consensus behind the alignments (next row)  consensus.rs:5-111
 //   phase C  k_hmm_viterbi, k_hmm_walk, k_hmm_emit          src/hmm/*, tr.rs:454-492
+//            k_vcf_fields      AL / MC / MS / AP sample fields (next row)  write_vcf.rs:267-343
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,6 +21,7 @@
 #include "consensus_core.h"
 #include "coop.h"
 #include "hmm_core.h"
+#include "vcf_core.h"
 #include "wfa_core.h"
 
 namespace trgt {
@@ -1094,6 +1096,33 @@ k_hmm_emit(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, co
     const HmmModelScan model = hmm_model_scan(hb.motifs, hb.motif_off + m0, nm);
     hmm_annotate(model, hb.alleles + hb.allele_off[a], L, bp + (hb.bp_off[a] - bp_base), 6, nullptr,
                  (HmmSpan *)(spans + span_off[a]), ns, plen ? paths + path_off[a] : nullptr, plen, plen, nullptr);
+  }
+}
+
+// ------------------------------------------------------------------ VCF sample fields ---------
+
+// AL, MC, MS, AP of every locus (write_vcf.rs:267-343): one lane per locus.  WRITE = false fills
+// len[4*l + field]; WRITE = true stores the bytes at off[4*l + field].
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_vcf_fields(uint32_t n_loci, const uint32_t *__restrict__ locus_allele_off, const uint64_t *__restrict__ allele_off,
+             const unsigned long long *__restrict__ mc_off, const uint32_t *__restrict__ mc,
+             const unsigned long long *__restrict__ span_off, const trgt_motif_span_t *__restrict__ spans,
+             const double *__restrict__ purity, const int32_t *__restrict__ status, uint32_t *__restrict__ len,
+             const unsigned long long *__restrict__ off, uint8_t *__restrict__ out) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < n_loci; l += gsz) {
+    VcfLocus L;
+    L.a0 = locus_allele_off[l]; L.a1 = locus_allele_off[l + 1];
+    L.allele_off = allele_off; L.mc_off = mc_off; L.mc = mc; L.span_off = span_off; L.spans = spans;
+    L.purity = purity; L.status = status;
+    for (int f = 0; f < 4; f++) {
+      VcfWriter w;
+      w.out = WRITE ? out + off[4 * (size_t)l + f] : nullptr;
+      w.n = 0;
+      vcf_encode_field(L, f, w);
+      if (!WRITE) len[4 * (size_t)l + f] = (uint32_t)w.n;
+    }
   }
 }
 

@@ -73,7 +73,7 @@ EXPORTS = [
     "trgt_engine_set_flank_band_budget",
     "trgt_host_alloc", "trgt_host_free",
     "trgt_clip_reads", "trgt_seq4_decode", "trgt_flank_spans_seq4", "trgt_flank_upload_seq4",
-    "trgt_flank_trs",
+    "trgt_flank_trs", "trgt_vcf_fields",
     "trgt_flank_spans", "trgt_align_e2e", "trgt_consensus", "trgt_edit_dist", "trgt_hmm_label",
     "trgt_flank_upload", "trgt_flank_run", "trgt_flank_download", "trgt_flank_free", "trgt_flank_device_views",
     "trgt_flank_fallback_counts",
@@ -129,6 +129,7 @@ def load_library(build: bool = True):
     L.trgt_seq4_decode.argtypes = [vp, s4, vp, vp]
     L.trgt_clip_reads.argtypes = [vp, vp, vp, vp, u64, vp, vp, u32, vp]
     L.trgt_flank_trs.argtypes = [vp, vp, C.POINTER(_SeqsOut)]
+    L.trgt_vcf_fields.argtypes = [vp, vp, C.POINTER(_SeqsOut)]
     L.trgt_flank_run.argtypes = [vp, vp]
     L.trgt_flank_download.argtypes = [vp, vp, vp, vp]
     L.trgt_flank_free.argtypes = [vp, vp]
@@ -538,6 +539,20 @@ class Engine:
         out = _Annotations()
         self._check(self._L.trgt_hmm_download(self._h, b, C.byref(out)), "trgt_hmm_download")
         return self._annotations(out, want_paths)
+
+    def vcf_fields(self, b=None):
+        """AL / MC / MS / AP sample fields of every locus of HMM batch b (None: the last hmm_label call), as
+        write_vcf.rs:267-343 encodes them -> list of (AL, MC, MS, AP) byte strings per locus"""
+        out = _SeqsOut()
+        self._check(self._L.trgt_vcf_fields(self._h, b, C.byref(out)), "trgt_vcf_fields")
+        n = int(out.n)
+        if n == 0:
+            return []
+        offs = np.ctypeslib.as_array(out.offsets, shape=(n + 1,))
+        total = int(offs[n])
+        data = np.ctypeslib.as_array(out.data, shape=(max(1, total),))[:total].tobytes()
+        f = [data[int(offs[i]):int(offs[i + 1])] for i in range(n)]
+        return [tuple(f[4 * l:4 * l + 4]) for l in range(n // 4)]
 
     def hmm_free(self, b):
         self._L.trgt_hmm_free(self._h, b)
