@@ -302,7 +302,7 @@ struct __align__(16) FlankBandSmem {
 // pairs at 30x, so a half-warp (FB_LT lanes) takes a locus: it stages and indexes the two pieces once
 // (3 KB of shared memory) and then its lanes each take a pending pair.
 // What a lane cannot settle goes to `work2` (2*read+side) for k_flank_band2.
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 8)
 k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
              int band_budget, double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits,
              uint32_t *__restrict__ work2, Counters *ctr, const uint16_t *__restrict__ kidx_in) {

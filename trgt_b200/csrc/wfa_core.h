@@ -772,6 +772,33 @@ TRGT_HD uint64_t kidx_mix(uint64_t k) { return k * 0x9E3779B97F4A7C15ull; }
 TRGT_HD uint32_t kidx_home(uint64_t mixed) { return (uint32_t)(mixed >> 55); }
 TRGT_HD uint32_t kidx_fp(uint64_t mixed) { const uint32_t f = (uint32_t)(mixed >> 40) & 0x7Fu; return f == 0x7Fu ? 0x3Fu : f; }
 
+// claim the first free slot at or after `h` for `val` (linear probing).  Occupied slots are skipped
+// with plain loads; only a slot that looks free costs an atomic, on the 32-bit word that holds it.
+TRGT_HD void kidx_insert(uint16_t *slot, uint32_t h, uint32_t val) {
+#if defined(__CUDA_ARCH__)
+  for (;;) {
+    unsigned int *w = (unsigned int *)slot + (h >> 1);
+    const unsigned sh = (h & 1u) * 16u;
+    unsigned int cur = *(volatile unsigned int *)w;
+    bool placed = false;
+    while (((cur >> sh) & 0xFFFFu) == TRGT_KIDX_EMPTY) {
+      const unsigned int nv = (cur & ~(0xFFFFu << sh)) | (val << sh);
+      const unsigned int prev = atomicCAS(w, cur, nv);
+      if (prev == cur) { placed = true; break; }
+      cur = prev;
+    }
+    if (placed) return;
+    h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u);
+  }
+#else
+  for (;;) {
+    uint16_t ex = (uint16_t)TRGT_KIDX_EMPTY;
+    if (__atomic_compare_exchange_n(&slot[h], &ex, (uint16_t)val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) return;
+    h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u);
+  }
+#endif
+}
+
 TRGT_HD uint32_t kidx_cas(uint16_t *addr, uint32_t expect, uint32_t val) {
 #if defined(__CUDA_ARCH__)
   return atomicCAS((unsigned short *)addr, (unsigned short)expect, (unsigned short)val);
@@ -789,8 +816,7 @@ TRGT_HD void kidx_build(const G &g, const KmerIndex &idx, const uint8_t *piece, 
   for (int i = g.lane(); i + 8 <= P; i += g.size()) {
     const uint64_t mixed = kidx_mix(wfa_ld64u(piece + i));
     const uint32_t val = (kidx_fp(mixed) << 9) | (uint32_t)i;
-    uint32_t h = kidx_home(mixed);
-    while (kidx_cas(&idx.slot[h], TRGT_KIDX_EMPTY, val) != TRGT_KIDX_EMPTY) h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u);
+    kidx_insert(idx.slot, kidx_home(mixed), val);
   }
   g.sync();
 }
@@ -881,10 +907,10 @@ TRGT_HD void fxt_build_copies(const G &g, const uint8_t *piece, int P, uint8_t *
     uint64_t v = 0;
     if (i0 >= 0 && i0 + 8 <= P) {
       v = wfa_ld64u(piece + i0);
-    } else {
+    } else if (i0 + 8 > 0 && i0 < P) {  // the two words that straddle an end of the piece
       for (int b = 0; b < 8; b++)
         if (i0 + b >= 0 && i0 + b < P) v |= (uint64_t)piece[i0 + b] << (8 * b);
-    }
+    }  // words wholly outside the piece are never compared unmasked
     *(uint64_t *)(copies + k * FXT_STRIDE + 8 * wd) = v;
   }
   g.sync();
@@ -936,6 +962,43 @@ TRGT_HD int flank_exact_thread(const KmerIndex &idx, const uint8_t *copies, int 
   if (n_starts <= 0) return -1;
   const int step = P - 7;
   const int n_probes = (T - 7) / step;
+  // Two loops, so that the lanes of a warp (each on its own pair) stay together: the probes' candidates
+  // are collected first (in increasing order of probe, hence of candidate range), then verified.
+  int c0 = -1, c1 = -1, c2 = -1, c3 = -1;  // candidate starts, probe index in the top bits
+  int n = 0;
+  bool many = false;
+  for (int ib = 0; ib < n_probes && !many; ib += 4) {  // four probes per step: their loads go out together
+    uint64_t key[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) key[u] = ib + u < n_probes ? wfa_ld64u(t + (ib + u + 1) * step - 1) : 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (ib + u >= n_probes) break;
+      const int j = (ib + u + 1) * step - 1;
+      const uint64_t mixed = kidx_mix(key[u]);
+      const uint32_t fp = kidx_fp(mixed);
+      for (uint32_t h = kidx_home(mixed), v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+        if ((v >> 9) != fp) continue;
+        const int s = j - (int)(v & 511u);
+        if (s < 0 || s >= n_starts) continue;
+        if (n == 0) c0 = s; else if (n == 1) c1 = s; else if (n == 2) c2 = s; else if (n == 3) c3 = s; else many = true;
+        n++;
+      }
+    }
+  }
+  if (!many) {
+    // candidates of probe i lie in [i * step, (i + 1) * step): the first occurrence is the smallest verified
+    // candidate within the first probe range that has one
+    int best = INT_MAX, best_range = INT_MAX;
+    for (int c = 0; c < n; c++) {
+      const int s = c == 0 ? c0 : c == 1 ? c1 : c == 2 ? c2 : c3;
+      const int range = s / step;  // index of the probe whose range holds s
+      if (range > best_range || s >= best) continue;
+      if (fxt_verify(copies, P, t + s)) { best = s; best_range = range; }
+    }
+    return best == INT_MAX ? -1 : best;
+  }
+  // many candidates (repetitive piece): probe by probe
   for (int i = 0; i < n_probes; i++) {
     const int j = (i + 1) * step - 1;
     const uint64_t mixed = kidx_mix(wfa_ld64u(t + j));
@@ -1154,16 +1217,23 @@ TRGT_HD int flank_seed_band_thread(const KmerIndex &idx, const WfaProb &pr, int 
   const int n_probes = (pr.T - 7) / step;
   int cand[FT1_CANDS];  // block start in the text << 5 | block
   int n = 0;
-  for (int i = 0; i < n_probes; i++) {
-    const int j = (i + 1) * step - 1;
-    const uint64_t mixed = kidx_mix(wfa_ld64u(pr.t + j));
-    const uint32_t fp = kidx_fp(mixed);
-    for (uint32_t h = kidx_home(mixed), v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
-      if ((v >> 9) != fp) continue;
-      const int d = (int)(v & 511u), b = d / blen, q = j - (d - b * blen);
-      if (b >= nb || d - b * blen + 8 > blen || q < 0 || q + blen > pr.T) continue;
-      if (n == FT1_CANDS) return -2;
-      cand[n++] = (q << 5) | b;
+  for (int ib = 0; ib < n_probes; ib += 4) {  // four probes per step: their loads go out together
+    uint64_t key[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) key[u] = ib + u < n_probes ? wfa_ld64u(pr.t + (ib + u + 1) * step - 1) : 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (ib + u >= n_probes) break;
+      const int j = (ib + u + 1) * step - 1;
+      const uint64_t mixed = kidx_mix(key[u]);
+      const uint32_t fp = kidx_fp(mixed);
+      for (uint32_t h = kidx_home(mixed), v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+        if ((v >> 9) != fp) continue;
+        const int d = (int)(v & 511u), b = d / blen, q = j - (d - b * blen);
+        if (b >= nb || d - b * blen + 8 > blen || q < 0 || q + blen > pr.T) continue;
+        if (n == FT1_CANDS) return -2;
+        cand[n++] = (q << 5) | b;
+      }
     }
   }
   int kmin = INT_MAX, kmax = INT_MIN;

@@ -540,16 +540,18 @@ class Engine:
         self._check(self._L.trgt_hmm_download(self._h, b, C.byref(out)), "trgt_hmm_download")
         return self._annotations(out, want_paths)
 
-    def vcf_fields(self, b=None):
+    def vcf_fields(self, b=None, raw: bool = False):
         """AL / MC / MS / AP sample fields of every locus of HMM batch b (None: the last hmm_label call), as
         write_vcf.rs:267-343 encodes them -> list of (AL, MC, MS, AP) byte strings per locus"""
         out = _SeqsOut()
         self._check(self._L.trgt_vcf_fields(self._h, b, C.byref(out)), "trgt_vcf_fields")
         n = int(out.n)
         if n == 0:
-            return []
+            return (np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint8)) if raw else []
         offs = np.ctypeslib.as_array(out.offsets, shape=(n + 1,))
         total = int(offs[n])
+        if raw:  # views of the engine's pinned buffers: offsets[4 * n_loci + 1], bytes
+            return offs, np.ctypeslib.as_array(out.data, shape=(max(1, total),))[:total]
         data = np.ctypeslib.as_array(out.data, shape=(max(1, total),))[:total].tobytes()
         f = [data[int(offs[i]):int(offs[i + 1])] for i in range(n)]
         return [tuple(f[4 * l:4 * l + 4]) for l in range(n // 4)]
