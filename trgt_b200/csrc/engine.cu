@@ -1652,13 +1652,14 @@ static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
     const uint32_t tgrid = (cnt + 127) / 128;  // one thread per allele for the walks
     const unsigned long long bp_base = b->h_bp_off[a0];
     {  // small models: one allele per thread
-      const size_t tsmem = (size_t)2 * HMM_THREAD_S * 128 * sizeof(double);
+      const int s_cap = b->S_max < HMM_THREAD_S ? b->S_max : HMM_THREAD_S;  // two score columns per thread
+      const size_t tsmem = (size_t)2 * s_cap * 128 * sizeof(double);
       int grid = 0;
       TRY(persistent_grid(e, k_hmm_viterbi_thread, 128, tsmem, &grid));
       if ((uint32_t)grid > tgrid) grid = (int)tgrid;
       LaunchScope ls(e, "k_hmm_viterbi_thread");
       k_hmm_viterbi_thread<<<grid, 128, tsmem, e->stream>>>(hb, a0, a1, bp_base, (uint8_t *)b->bp.p,
-                                                             (int32_t *)b->status.p);
+                                                             (int32_t *)b->status.p, s_cap);
       TRY(check_launch(e, "k_hmm_viterbi_thread"));
     }
     if (b->S_max > HMM_THREAD_S) {  // larger models: one allele per warp

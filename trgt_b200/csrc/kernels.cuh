@@ -988,9 +988,9 @@ __device__ __forceinline__ HmmWarpMem hmm_carve(unsigned char *base, int S_max, 
 // k_hmm_viterbi.
 __global__ void __launch_bounds__(128)
 k_hmm_viterbi_thread(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, uint8_t *__restrict__ bp,
-                     int32_t *__restrict__ status) {
+                     int32_t *__restrict__ status, int s_cap) {
   extern __shared__ __align__(16) unsigned char smem_b[];
-  double *sc = reinterpret_cast<double *>(smem_b);  // [2][HMM_THREAD_S][128]
+  double *sc = reinterpret_cast<double *>(smem_b);  // [2][s_cap][128], s_cap = min(HMM_THREAD_S, largest model of the batch)
   const uint32_t gsz = gridDim.x * blockDim.x;
   for (uint32_t a = a0 + blockIdx.x * blockDim.x + threadIdx.x; a < a1; a += gsz) {
     const uint32_t l = hb.allele_locus[a];
@@ -1006,7 +1006,7 @@ k_hmm_viterbi_thread(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long b
     const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
     if (L == 0) continue;
     hmm_viterbi_thread(model, hb.c, hb.mm_off, hb.mm_lp, hb.alleles + hb.allele_off[a], L, sc + threadIdx.x,
-                       sc + (size_t)HMM_THREAD_S * 128 + threadIdx.x, 128, bp + (hb.bp_off[a] - bp_base));
+                       sc + (size_t)s_cap * 128 + threadIdx.x, 128, bp + (hb.bp_off[a] - bp_base));
   }
 }
 
