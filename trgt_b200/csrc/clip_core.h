@@ -148,27 +148,31 @@ TRGT_HD void seq4_decode16(const uint8_t *data, long long nib, uint32_t out[4]) 
   out[3] = seq4_decode4((uint32_t)(v >> 48) & 0xFFFFu);
 }
 
-// One read: bases [start, start+len) of `data` -> out[o .. o+len), written as aligned 16-byte words
-// where a word lies inside the read and byte by byte at its two ends.  Lanes of the group stride
-// over the aligned words of the output range.
+// One read: bases [start, start+len) of `data` -> out[o .. o+len).  The aligned 16-byte words that lie
+// wholly inside the read are written one per lane and step (no divergence); the < 32 bytes left at the
+// two ends are then written one byte per lane.
 template <class G>
 TRGT_HD void seq4_unpack_read(const G &g, const uint8_t *data, uint64_t start, uint32_t len, uint8_t *out_base,
                               uint64_t o) {
   if (len == 0) return;
-  const uint64_t c0 = o >> 4, c1 = (o + len - 1) >> 4;
-  for (uint64_t c = c0 + (uint64_t)g.lane(); c <= c1; c += (uint64_t)g.size()) {
-    const long long j0 = (long long)(16 * c) - (long long)o;  // base index of the word's first byte
+  const uint32_t head = (uint32_t)((16u - (uint32_t)(o & 15u)) & 15u);  // bytes before the first aligned word
+  const uint32_t nfull = len > head ? (len - head) >> 4 : 0;           // aligned words wholly inside
+  uint8_t *dst = out_base + o + head;                                   // 16-byte aligned
+  const long long nib0 = (long long)start + head;
+  for (uint32_t c = (uint32_t)g.lane(); c < nfull; c += (uint32_t)g.size()) {
     uint32_t q[4];
-    seq4_decode16(data, (long long)start + j0, q);
-    uint8_t *dst = out_base + 16 * c;
-    if (j0 >= 0 && j0 + 16 <= (long long)len) {
-      Seq4Word v;
-      v.x = q[0]; v.y = q[1]; v.z = q[2]; v.w = q[3];
-      *(Seq4Word *)dst = v;
-    } else {
-      for (int k = 0; k < 16; k++)
-        if (j0 + k >= 0 && j0 + k < (long long)len) dst[k] = (uint8_t)(q[k >> 2] >> (8 * (k & 3)));
-    }
+    seq4_decode16(data, nib0 + 16ll * c, q);
+    Seq4Word v;
+    v.x = q[0]; v.y = q[1]; v.z = q[2]; v.w = q[3];
+    *(Seq4Word *)(dst + 16u * c) = v;
+  }
+  // ends: bases [0, head) and [head + 16 * nfull, len)
+  const uint32_t h = head < len ? head : len;
+  const uint32_t tail0 = head + 16u * nfull;
+  const uint32_t ntail = len > tail0 ? len - tail0 : 0;
+  for (uint32_t k = (uint32_t)g.lane(); k < h + ntail; k += (uint32_t)g.size()) {
+    const uint32_t i = k < h ? k : tail0 + (k - h);
+    out_base[o + i] = seq4_letter(seq4_code_at(data, (long long)start + i));
   }
 }
 
