@@ -614,7 +614,8 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
     k_flank_band<<<grid, 128, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
                                                 b->frac, (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work2.p,
                                                 (Counters *)b->ctr.p,
-                                                b->kidx_valid ? (const uint16_t *)b->kidx.p : nullptr);
+                                                b->kidx_valid ? (const uint16_t *)b->kidx.p : nullptr,
+                                                /*prefetch=*/1);
     TRY(check_launch(e, "k_flank_band"));
   }
   return 0;

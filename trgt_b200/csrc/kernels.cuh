@@ -305,7 +305,7 @@ struct __align__(16) FlankBandSmem {
 __global__ void __launch_bounds__(128, 8)
 k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
              int band_budget, double min_flank_id_frac, trgt_flank_hit_t *__restrict__ hits,
-             uint32_t *__restrict__ work2, Counters *ctr, const uint16_t *__restrict__ kidx_in) {
+             uint32_t *__restrict__ work2, Counters *ctr, const uint16_t *__restrict__ kidx_in, int prefetch) {
   __shared__ FlankBandSmem sm_all[FB_LOCI];
   const TileGroup<FB_LT> g;
   FlankBandSmem &sm = sm_all[threadIdx.x / FB_LT];
@@ -336,7 +336,7 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
       rb = base;
       g.sync();
       if (n_list == 0) continue;
-      for (int i = lane; i < n_list; i += FB_LT) {  // pull the pending reads towards the SM while the pieces are set up
+      for (int i = lane; prefetch && i < n_list; i += FB_LT) {  // pull the pending reads towards the SM while the pieces are set up
         const uint32_t r = rb_pass + (uint32_t)(sm.list[i] >> 1);
         const uint8_t *t = src.reads + src.read_off[r];
         const int T = (int)(src.read_off[r + 1] - src.read_off[r]);
