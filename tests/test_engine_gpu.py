@@ -303,7 +303,13 @@ def _pass_and_compare(engine, oracle, w):
     from trgt_b200.pipeline import HotPath, compare_with_oracle, oracle_pass
     hp = HotPath(engine, w, want_hits=False, pinned_outputs=False)
     res = hp.run_e2e(copy=True)
-    compare_with_oracle(res, oracle_pass(oracle, w, 4))
+    ref = oracle_pass(oracle, w, 4)
+    compare_with_oracle(res, ref)
+    # the same pass with the reads handed over as BAM 4-bit bases and the repeat sequences cut on the device
+    w.pack_seq4()
+    hp4 = HotPath(engine, w, want_hits=False, pinned_outputs=False, use_seq4=True)
+    assert hp4.use_seq4
+    compare_with_oracle(hp4.run_e2e(copy=True), ref)
     # the resident-batch interface must give the same answers
     hp.prepare_resident()
     hp.run_resident()
@@ -542,3 +548,18 @@ def test_vcf_fields_tutorial_and_random_parity(engine, oracle):
     engine.hmm_label_packed(m, np.array([0, 1, 2], dtype=np.uint32), al, np.array([0, 1, 0], dtype=np.uint32))
     with pytest.raises(TrgtError):
         engine.vcf_fields()
+
+
+def test_results_before_run_are_refused(engine):
+    from trgt_b200 import TrgtError, workload
+    w = workload.generate(3, 4, seed=1)
+    b = engine.flank_upload(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+    try:
+        with pytest.raises(TrgtError):
+            engine.flank_download(b, w.n_reads)
+        with pytest.raises(TrgtError):
+            engine.flank_trs(b)
+        engine.flank_run(b)
+        assert len(engine.flank_trs(b, copy=True)) == w.n_reads
+    finally:
+        engine.flank_free(b)

@@ -399,6 +399,7 @@ struct trgt_flank_batch {
   DevBuf hits, spans, work, work2, ends, ctr, gring, gws;
   DevBuf kidx;                         // 8-mer indexes of both pieces of every locus (k_flank_exact_t -> k_flank_band)
   bool kidx_valid = false;
+  bool ran = false;                    // spans / hits hold results
   DevBuf tr_len, tr_off, tr_data;      // trgt_flank_trs: repeat sequences of the spanning reads
   PinBuf h_tr_off, h_tr_data;
   DevBuf seq4, seq4_starts, seq4_len;  // BAM 4-bit input (trgt_flank_*_seq4): decoded into `reads` on the device
@@ -516,6 +517,7 @@ static int flank_upload_into(trgt_engine_t *e, trgt_flank_batch *b, const trgt_s
   if (pm + tm > 0x3fffffffull) return fail(e, TRGT_ERR_ARG, "sequence too long");
   b->n_loci = n_loci;
   b->n_reads = (uint32_t)reads->n;
+  b->ran = false;
   b->Pmax = (int)pm;
   {
     uint64_t mn = pm;
@@ -678,6 +680,7 @@ static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src
     k_flank_combine<<<grid, 256, 0, e->stream>>>((const trgt_flank_hit_t *)b->hits.p, b->n_reads, (trgt_span_t *)b->spans.p);
     TRY(check_launch(e, "k_flank_combine"));
   }
+  b->ran = true;
   return 0;
 }
 
@@ -882,6 +885,7 @@ int32_t trgt_flank_run(trgt_engine_t *e, trgt_flank_batch_t *b) {
 
 static int flank_download_locked(trgt_engine_t *e, trgt_flank_batch *b, trgt_span_t *spans_out,
                                  trgt_flank_hit_t *hits_out) {
+  if (b->n_reads && !b->ran) return fail(e, TRGT_ERR_ARG, "trgt_flank_download before trgt_flank_run");
   CU(e, cudaSetDevice(e->device));
   if (b->n_reads) {
     if (spans_out)
@@ -996,7 +1000,7 @@ int32_t trgt_flank_trs(trgt_engine_t *e, trgt_flank_batch_t *b, trgt_seqs_out_t 
   if (!e || !out) return TRGT_ERR_ARG;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!b) b = e->one_flank;
-  if (!b) return fail(e, TRGT_ERR_ARG, "trgt_flank_trs: no flank batch has been run on this engine");
+  if (!b || (b->n_reads && !b->ran)) return fail(e, TRGT_ERR_ARG, "trgt_flank_trs: the flank batch has not been run");
   CU(e, cudaSetDevice(e->device));
   memset(out, 0, sizeof *out);
   const uint32_t n = b->n_reads;

@@ -799,16 +799,6 @@ TRGT_HD void kidx_insert(uint16_t *slot, uint32_t h, uint32_t val) {
 #endif
 }
 
-TRGT_HD uint32_t kidx_cas(uint16_t *addr, uint32_t expect, uint32_t val) {
-#if defined(__CUDA_ARCH__)
-  return atomicCAS((unsigned short *)addr, (unsigned short)expect, (unsigned short)val);
-#else
-  uint16_t ex = (uint16_t)expect;
-  __atomic_compare_exchange_n(addr, &ex, (uint16_t)val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
-  return ex;
-#endif
-}
-
 template <class G>
 TRGT_HD void kidx_build(const G &g, const KmerIndex &idx, const uint8_t *piece, int P) {
   for (uint32_t i = (uint32_t)g.lane(); i < TRGT_KIDX_SLOTS; i += (uint32_t)g.size()) idx.slot[i] = TRGT_KIDX_EMPTY;
