@@ -202,7 +202,7 @@ def kernel_bytes(name: str, w, hp, res) -> float | None:
         first = w.locus_motif_off[:-1][g.group_locus]
         S = 7.0 + 3.0 * mlen[first] + 1.0          # one motif per locus in this catalog
         return float(((L + 2) * (1.0 + S) + mlen[first] + 8.0 * nm).sum())
-    if name == "k_e2e_thread":  # every member and its backbone once, one end record and its CIGAR words per member
+    if name == "k_e2e_identity":  # every member and its backbone once, one end record and its CIGAR words per member
         per_seq_bb = np.diff(g.backbones.offsets.astype(np.int64))[
             np.repeat(np.arange(len(g.backbones)), np.diff(g.group_seq_off.astype(np.int64)))]
         return float(g.seqs.data.nbytes + per_seq_bb.sum() + 16.0 * len(g.seqs) + 4.0 * res.cigars.words.size)

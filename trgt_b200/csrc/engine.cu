@@ -1071,7 +1071,7 @@ struct trgt_align_batch {
   uint32_t n_groups = 0, n_seqs = 0;
   int Pmax = 0, Tmax = 0;
   DevBuf bb, bb_off, seqs, seq_off, group_off, seq_group;
-  DevBuf ends, trace_work, resid, cig_n, cig_off, pool, ctr, gring, gws;
+  DevBuf ends, trace_work, resid, diff, cig_n, cig_off, pool, ctr, gring, gws;
   DevBuf out_off, out_words, scores, status;
   DevBuf cons_counts, cons_recs, cons_len, cons_status, cons_off, cons_data;
   PinBuf h_cons_off, h_cons_data, h_cons_status;
@@ -1110,7 +1110,7 @@ void trgt_align_free(trgt_engine_t *e, trgt_align_batch_t *b) {
   DevBuf *all[] = {&b->bb, &b->bb_off, &b->seqs, &b->seq_off, &b->group_off, &b->seq_group, &b->ends, &b->trace_work,
                    &b->cig_n, &b->cig_off, &b->pool, &b->ctr, &b->gring, &b->gws, &b->out_off, &b->out_words,
                    &b->scores, &b->status, &b->cons_counts, &b->cons_recs, &b->cons_len, &b->cons_status,
-                   &b->cons_off, &b->cons_data, &b->resid};
+                   &b->cons_off, &b->cons_data, &b->resid, &b->diff};
   for (auto *d : all) dev_free(*d);
   pin_free(b->h_off); pin_free(b->h_words); pin_free(b->h_scores); pin_free(b->h_status);
   pin_free(b->h_cons_off); pin_free(b->h_cons_data); pin_free(b->h_cons_status);
@@ -1232,15 +1232,26 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
     TRY(dev_reserve(e, b->pool, (size_t)(pool_cap1 + 1) * sizeof(uint32_t)));
     // one lane per pair first: identical members and cheap alignments end there
     TRY(dev_reserve(e, b->resid, ((size_t)n + 1) * sizeof(uint32_t)));
+    TRY(dev_reserve(e, b->diff, ((size_t)n + 1) * sizeof(uint32_t)));
+    {
+      int igrid = 0;
+      TRY(persistent_grid(e, k_e2e_identity, 256, 0, &igrid));
+      const uint32_t ineed = (n + 255) / 256;
+      if ((uint32_t)igrid > ineed) igrid = (int)ineed;
+      LaunchScope ls(e, "k_e2e_identity");
+      k_e2e_identity<<<igrid, 256, 0, e->stream>>>(src, n, (WfaEnd *)b->ends.p, (uint32_t *)b->cig_n.p,
+                                                   (uint32_t *)b->diff.p, ctr);
+      TRY(check_launch(e, "k_e2e_identity"));
+    }
     {
       int tgrid = 0;
       TRY(persistent_grid(e, k_e2e_thread, 128, 0, &tgrid));
       const uint32_t tneed = (n + 127) / 128;
       if ((uint32_t)tgrid > tneed) tgrid = (int)tneed;
       LaunchScope ls(e, "k_e2e_thread");
-      k_e2e_thread<<<tgrid, 128, 0, e->stream>>>(src, n, (WfaEnd *)b->ends.p, (uint32_t *)b->cig_n.p,
-                                                 (unsigned long long *)b->cig_off.p, (uint32_t *)b->pool.p, pool_cap1,
-                                                 (uint32_t *)b->resid.p, ctr);
+      k_e2e_thread<<<tgrid, 128, 0, e->stream>>>(src, (const uint32_t *)b->diff.p, &ctr->n_diff, (WfaEnd *)b->ends.p,
+                                                 (uint32_t *)b->cig_n.p, (unsigned long long *)b->cig_off.p,
+                                                 (uint32_t *)b->pool.p, pool_cap1, (uint32_t *)b->resid.p, ctr);
       TRY(check_launch(e, "k_e2e_thread"));
     }
     LaunchScope ls(e, "k_wfa_score_warp");

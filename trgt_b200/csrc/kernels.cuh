@@ -38,6 +38,8 @@ struct Counters {
   unsigned int n_banded;                // flank: pairs settled by k_flank_band_wide
   unsigned int n_tier2;                 // flank: pairs the first cost tier handed to k_flank_band2
   unsigned int n_resid;                 // e2e: pairs k_e2e_thread handed to the warp kernel
+  unsigned int n_diff;                  // e2e: members that differ from their backbone (k_e2e_identity)
+  unsigned int pad3;
 };
 
 enum { WFA_MODE_FLANK = 0, WFA_MODE_E2E = 1 };
@@ -525,9 +527,10 @@ k_tr_gather(const uint8_t *__restrict__ reads, const uint64_t *__restrict__ read
 #define E2E_NARROW_INTS 1280  // its history: 6*17 header + 3 * 23 diagonals * 17 scores
 #define E2E_NARROW_WORDS 48   // its CIGAR: at most 2 * cost + a few words
 
-// Phase B, first step for short repeat sequences: ONE LANE PER (backbone, member) PAIR.  A member equal
-// to its backbone (92 % on HiFi) is a single '=' run; otherwise the lane runs the end-to-end alignment
-// itself with cost cap E2T_COST: every cell the full computation can reach then lies on
+// Phase B, first steps for short repeat sequences: ONE LANE PER (backbone, member) PAIR.  A member equal
+// to its backbone (92 % on HiFi) is a single '=' run (k_e2e_identity, which compacts the others into a
+// list); a lane of k_e2e_thread then runs the end-to-end alignment of one listed member itself with cost
+// cap E2T_COST: every cell the full computation can reach then lies on
 // |k| <= (E2T_COST - o) / e, so the band of <= E2T_W diagonals IS the full computation (wfa_e2e_narrow's
 // argument), its history sits in the lane's local memory and the CIGAR comes straight from the
 // back-trace.  Costlier pairs are appended to `resid` for the warp kernel.
@@ -536,20 +539,47 @@ k_tr_gather(const uint8_t *__restrict__ reads, const uint64_t *__restrict__ read
 #define E2T_WS_INTS (TRGT_WFA_META * (E2T_COST + 1) + 3 * E2T_W * (E2T_COST + 1))
 #define E2T_WORDS 32
 
-__global__ void __launch_bounds__(128)
-k_e2e_thread(WfaSrc src, uint32_t n, WfaEnd *__restrict__ ends, uint32_t *__restrict__ cig_n,
-             unsigned long long *__restrict__ cig_off, uint32_t *__restrict__ pool, unsigned long long pool_cap,
-             uint32_t *__restrict__ resid, Counters *ctr) {
+// step 1: identity test, one lane per member; the ones that differ are compacted into `diff`
+__global__ void __launch_bounds__(256)
+k_e2e_identity(WfaSrc src, uint32_t n, WfaEnd *__restrict__ ends, uint32_t *__restrict__ cig_n,
+               uint32_t *__restrict__ diff, Counters *ctr) {
   const uint32_t gsz = gridDim.x * blockDim.x;
-  for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gsz) {
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gsz) {
+    const uint32_t id = base + lane;
+    bool differs = false;
+    if (id < n) {
+      const WfaProb pr = wfa_prob_of(src, id);
+      if (pr.P == pr.T && (pr.P == 0 || wfa_match_len(pr.p, pr.t, pr.P) == pr.P)) {
+        WfaEnd end;
+        end.status = TRGT_WFA_OK; end.s = 0; end.k = 0; end.off = pr.T;
+        ends[id] = end;
+        cig_n[id] = pr.P > 0 ? 1u : 0u;  // a single '=' run
+      } else {
+        differs = true;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, differs);
+    if (bal) {
+      unsigned int slot = 0;
+      if (lane == 0) slot = atomicAdd(&ctr->n_diff, (unsigned int)__popc(bal));
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (differs) diff[slot + __popc(bal & ((1u << lane) - 1u))] = id;
+    }
+  }
+}
+
+// step 2: one lane per member that differs (all lanes of a warp busy)
+__global__ void __launch_bounds__(128)
+k_e2e_thread(WfaSrc src, const uint32_t *__restrict__ diff, const unsigned int *n_diff_ptr, WfaEnd *__restrict__ ends,
+             uint32_t *__restrict__ cig_n, unsigned long long *__restrict__ cig_off, uint32_t *__restrict__ pool,
+             unsigned long long pool_cap, uint32_t *__restrict__ resid, Counters *ctr) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  const uint32_t n = *n_diff_ptr;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gsz) {
+    const uint32_t id = diff[i];
     const WfaProb pr = wfa_prob_of(src, id);
     WfaEnd end;
-    if (pr.P == pr.T && (pr.P == 0 || wfa_match_len(pr.p, pr.t, pr.P) == pr.P)) {
-      end.status = TRGT_WFA_OK; end.s = 0; end.k = 0; end.off = pr.T;
-      ends[id] = end;
-      cig_n[id] = pr.P > 0 ? 1u : 0u;
-      continue;
-    }
     bool done = false;
     const int o = pr.oe - pr.e;
     const int R = E2T_COST > o ? (E2T_COST - o) / pr.e : 0;
