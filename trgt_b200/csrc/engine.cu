@@ -1463,7 +1463,8 @@ struct trgt_hmm_batch {
   size_t warp_bytes = 0;
   DevBuf motifs, motif_off, locus_motif_off, alleles, allele_off, allele_locus, bp_off, mc_off;
   DevBuf bp, mc, purity, n_spans, span_off, spans, path_len, path_off, paths, status;
-  std::vector<unsigned long long> h_bp_off, h_mc_off;
+  std::vector<unsigned long long> h_bp_off, h_mc_off, h_al_off;
+  DevBuf span_scratch;
   std::vector<uint32_t> h_locus_allele_off;  // [n_loci+1] when the alleles are grouped by locus, else empty
   DevBuf locus_allele_off, vcf_len, vcf_off, vcf_data;
   PinBuf r_vcf_off, r_vcf_data;
@@ -1486,7 +1487,7 @@ void trgt_hmm_free(trgt_engine_t *e, trgt_hmm_batch_t *b) {
   DevBuf *all[] = {&b->motifs, &b->motif_off, &b->locus_motif_off, &b->alleles, &b->allele_off, &b->allele_locus,
                    &b->bp_off, &b->mc_off, &b->bp, &b->mc, &b->purity, &b->n_spans, &b->span_off, &b->spans,
                    &b->path_len, &b->path_off, &b->paths, &b->status, &b->locus_allele_off, &b->vcf_len, &b->vcf_off,
-                   &b->vcf_data};
+                   &b->vcf_data, &b->span_scratch};
   for (auto *d : all) dev_free(*d);
   PinBuf *pins[] = {&b->r_mc, &b->r_span_off, &b->r_spans, &b->r_purity, &b->r_status, &b->r_path_off, &b->r_paths,
                     &b->r_vcf_off, &b->r_vcf_data};
@@ -1528,6 +1529,7 @@ static int hmm_upload_into(trgt_engine_t *e, trgt_hmm_batch *b, const trgt_seqs_
   const size_t n = alleles->n;
   b->h_bp_off.assign(n + 1, 0);
   b->h_mc_off.assign(n + 1, 0);
+  b->h_al_off.assign(alleles->offsets, alleles->offsets + n + 1);
   for (size_t a = 0; a < n; a++) {
     const uint32_t l = allele_locus[a];
     if (l >= n_loci) return fail(e, TRGT_ERR_ARG, "allele %zu: locus %u out of range", a, l);
@@ -1684,12 +1686,18 @@ static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
       k_hmm_viterbi<<<grid, block, smem, e->stream>>>(hb, a0, a1, bp_base, (uint8_t *)b->bp.p, (int32_t *)b->status.p, 1);
       TRY(check_launch(e, "k_hmm_viterbi"));
     }
+    // without state paths the walk leaves the spans in scratch slots and a copy kernel places them;
+    // with state paths a second walk (k_hmm_emit) writes spans and paths at their offsets
+    const bool one_walk = !b->want_paths;
+    if (one_walk)
+      TRY(dev_reserve(e, b->span_scratch, (size_t)(b->h_al_off[a1] - b->h_al_off[a0] + 1) * sizeof(trgt_motif_span_t)));
     {
       LaunchScope ls(e, "k_hmm_walk");
       k_hmm_walk<<<tgrid, 128, 0, e->stream>>>(hb, a0, a1, bp_base, (const uint8_t *)b->bp.p, (uint32_t *)b->mc.p,
                                                (double *)b->purity.p, (uint32_t *)b->n_spans.p,
                                                b->want_paths ? (unsigned long long *)b->path_len.p : nullptr,
-                                               (int32_t *)b->status.p);
+                                               (int32_t *)b->status.p,
+                                               one_walk ? (trgt_motif_span_t *)b->span_scratch.p : nullptr);
       TRY(check_launch(e, "k_hmm_walk"));
     }
     // span offsets of this wave: base + exclusive scan (n_spans[a1] is scratch and zeroed first)
@@ -1712,7 +1720,16 @@ static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
     const unsigned long long path_end = b->want_paths ? e->h_u64[1] : 0;
     TRY(dev_reserve(e, b->spans, (size_t)(span_end + 1) * sizeof(trgt_motif_span_t), true));
     if (b->want_paths) TRY(dev_reserve(e, b->paths, (size_t)(path_end + 1) * sizeof(uint32_t), true));
-    if (span_end > span_base || path_end > path_base) {
+    if (one_walk) {
+      if (span_end > span_base) {
+        LaunchScope ls(e, "k_hmm_spans");
+        k_hmm_spans<<<tgrid, 128, 0, e->stream>>>(hb, a0, a1, (const trgt_motif_span_t *)b->span_scratch.p,
+                                                  (const uint32_t *)b->n_spans.p,
+                                                  (const unsigned long long *)b->span_off.p,
+                                                  (trgt_motif_span_t *)b->spans.p);
+        TRY(check_launch(e, "k_hmm_spans"));
+      }
+    } else if (span_end > span_base || path_end > path_base) {
       LaunchScope ls(e, "k_hmm_emit");
       k_hmm_emit<<<tgrid, 128, 0, e->stream>>>(hb, a0, a1, bp_base, (const uint8_t *)b->bp.p,
                                                    (const uint32_t *)b->n_spans.p,

@@ -682,8 +682,9 @@ struct HmmAnnot {
 };
 
 // One reverse walk from (end, L+1) to start.  mc[nb-1] must be zeroed by the caller when non-null.
-// When spans_out is non-null the collapsed spans are written in forward order given their total
-// count n_total from a previous counting walk.  max_motif_len: tr.rs:468 passes 6.
+// When spans_out is non-null the collapsed spans are written in forward order into the LAST n_spans of
+// its n_total slots: n_total is either the count from a previous counting walk or any upper bound (a
+// collapsed span covers at least one base, so L is one).  max_motif_len: tr.rs:468 passes 6.
 // path_out (optional): receives the state path (Hmm::label).  With path_total == 0 it is written
 // in REVERSE order, up to path_cap entries; with path_total = the length found by a previous walk
 // it is written in forward order.  *path_len gets the full length.
@@ -735,7 +736,7 @@ TRGT_HD HmmAnnot hmm_annotate(const M &m, const uint8_t *allele, int L, const ui
               p_start = (uint32_t)copy_start;
             } else {
               if (have_p) {
-                if (spans_out) {
+                if (spans_out && emitted < n_total) {
                   HmmSpan s; s.motif_index = p_motif; s.start = p_start; s.end = p_end;
                   spans_out[n_total - 1 - emitted] = s;
                 }
@@ -771,7 +772,7 @@ TRGT_HD HmmAnnot hmm_annotate(const M &m, const uint8_t *allele, int L, const ui
   plen++;
   if (path_len) *path_len = plen;
   if (have_p) {
-    if (spans_out) {
+    if (spans_out && emitted < n_total) {
       HmmSpan s; s.motif_index = p_motif; s.start = p_start; s.end = p_end;
       spans_out[n_total - 1 - emitted] = s;
     }

@@ -1081,7 +1081,8 @@ k_hmm_viterbi(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base,
 __global__ void __launch_bounds__(128)
 k_hmm_walk(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, const uint8_t *__restrict__ bp,
            uint32_t *__restrict__ mc, double *__restrict__ purity, uint32_t *__restrict__ n_spans,
-           unsigned long long *__restrict__ path_len, int32_t *__restrict__ status) {
+           unsigned long long *__restrict__ path_len, int32_t *__restrict__ status,
+           trgt_motif_span_t *__restrict__ span_scratch) {
   const uint32_t gsz = gridDim.x * blockDim.x;
   for (uint32_t a = a0 + blockIdx.x * blockDim.x + threadIdx.x; a < a1; a += gsz) {
     const uint32_t l = hb.allele_locus[a];
@@ -1098,12 +1099,31 @@ k_hmm_walk(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, co
     }
     const HmmModelScan model = hmm_model_scan(hb.motifs, hb.motif_off + m0, nm);
     uint64_t plen = 0;
+    // span_scratch: one slot per base of the wave's alleles (a collapsed span covers at least one base); the
+    // walk fills the allele's slots from the back, so its spans end up in the last n_spans of them, in order
+    HmmSpan *sp = span_scratch ? (HmmSpan *)(span_scratch + (hb.allele_off[a] - hb.allele_off[a0])) : nullptr;
     const HmmAnnot an = hmm_annotate(model, hb.alleles + hb.allele_off[a], L, bp + (hb.bp_off[a] - bp_base), 6, my_mc,
-                                     nullptr, 0, nullptr, 0, 0, &plen);
+                                     sp, (uint32_t)L, nullptr, 0, 0, &plen);
     purity[a] = an.purity;
     n_spans[a] = an.n_spans;
     if (path_len) path_len[a] = plen;
     if (an.status < 0) status[a] = TRGT_ERR_INTERNAL;
+  }
+}
+
+// spans of the wave's alleles from the walk's scratch slots to their CSR offsets, one thread per allele
+__global__ void __launch_bounds__(128)
+k_hmm_spans(HmmBatch hb, uint32_t a0, uint32_t a1, const trgt_motif_span_t *__restrict__ span_scratch,
+            const uint32_t *__restrict__ n_spans, const unsigned long long *__restrict__ span_off,
+            trgt_motif_span_t *__restrict__ spans) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t a = a0 + blockIdx.x * blockDim.x + threadIdx.x; a < a1; a += gsz) {
+    const uint32_t ns = n_spans[a];
+    if (ns == 0) continue;
+    const uint64_t L = hb.allele_off[a + 1] - hb.allele_off[a];
+    const trgt_motif_span_t *src = span_scratch + (hb.allele_off[a] - hb.allele_off[a0]) + (L - ns);
+    trgt_motif_span_t *dst = spans + span_off[a];
+    for (uint32_t i = 0; i < ns; i++) dst[i] = src[i];
   }
 }
 
