@@ -640,7 +640,8 @@ static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src
     TRY(persistent_grid(e, k_flank_band_wide, 32, 0, &grid));
     LaunchScope ls(e, "k_flank_band_wide");
     k_flank_band_wide<<<grid, 32, 0, e->stream>>>(src, (uint32_t *)b->work.p, &ctr->n_work, b->frac,
-                                                  (trgt_flank_hit_t *)b->hits.p, ctr);
+                                                  (trgt_flank_hit_t *)b->hits.p, ctr,
+                                                  b->kidx_valid ? (const uint16_t *)b->kidx.p : nullptr);
     TRY(check_launch(e, "k_flank_band_wide"));
   }
   {

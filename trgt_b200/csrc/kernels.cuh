@@ -463,28 +463,42 @@ k_flank_band2(WfaSrc src, const uint32_t *__restrict__ work2, const unsigned int
 
 // Phase A, step 3.  Second chance for the pairs k_flank_band deferred (band wider than a warp, cost
 // above its budget, scratch too small): one warp per pair with 32 KB of scratch and the general
-// banded routine (linear seed scan, any band width, history or ring + cone), budgets 24 then 36.
+// banded routine (index or linear seed scan, any band width, history or ring + cone), budgets 24 then 36.
 // What it settles is struck from the work list (0xFFFFFFFF); only pairs without any usable seed are
 // left for the full-width kernels.
 #define FLW_WS_INTS 8192
 
 __global__ void __launch_bounds__(32)
 k_flank_band_wide(WfaSrc src, uint32_t *__restrict__ work, const unsigned int *n_work_ptr, double min_flank_id_frac,
-                  trgt_flank_hit_t *__restrict__ hits, Counters *ctr) {
+                  trgt_flank_hit_t *__restrict__ hits, Counters *ctr, const uint16_t *__restrict__ kidx_in) {
   __shared__ __align__(16) int ws[FLW_WS_INTS];
   __shared__ uint64_t keys[32];
+  __shared__ __align__(16) uint16_t slot[TRGT_KIDX_SLOTS];
+  __shared__ int cand[TRGT_CAND_CAP + 4];
   const WarpGroup g;
+  const int lane = g.lane();
   const uint32_t n = *n_work_ptr;
   for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
     const uint32_t id = work[i];
     const WfaProb pr = wfa_prob_of(src, id);
+    __syncwarp();
+    // the piece's 8-mer table as k_flank_exact_t left it (seed filter by probes instead of a scan of every
+    // text position); pieces it does not cover are scanned
+    const bool indexed = kidx_in != nullptr && pr.P >= 16 && pr.P <= TRGT_KIDX_MAX_P;
+    if (indexed) {
+      const uint4 *s4 = (const uint4 *)(kidx_in + ((size_t)src.read_locus[id >> 1] * 2 + (id & 1u)) * TRGT_KIDX_SLOTS);
+      for (int c = lane; c < (int)(TRGT_KIDX_SLOTS * sizeof(uint16_t) / 16); c += 32) ((uint4 *)slot)[c] = s4[c];
+      __syncwarp();
+    }
+    const KmerIndex idx{slot};
     int settled = 0;
     FlankHit fh;
     fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
 #pragma unroll 1
     for (int S = 24; S <= 36 && !settled; S += 12)
-      settled = flank_locate_banded(g, pr, S, min_flank_id_frac, keys, ws, FLW_WS_INTS, &fh) == 0;
-    if (g.lane() == 0 && settled) {
+      settled = flank_locate_banded(g, pr, S, min_flank_id_frac, keys, ws, FLW_WS_INTS, &fh, indexed ? &idx : nullptr,
+                                    cand) == 0;
+    if (lane == 0 && settled) {
       trgt_flank_hit_t h;
       h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
       h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
