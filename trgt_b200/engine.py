@@ -290,13 +290,22 @@ class AnnotationBatch:
         return self.paths[int(self.path_offsets[i]):int(self.path_offsets[i + 1])].tolist()
 
 
+_memcpy = C.CDLL(None).memcpy
+_memcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+_memcpy.restype = C.c_void_p
+
+
 def _np_from(ptr, n, dtype, copy=True):
     """numpy view of n elements at a ctypes pointer; copy=False aliases the engine's pinned result
     buffer, which stays valid until the next call of the same kind on that engine."""
     if n == 0:
         return np.zeros(0, dtype=dtype)
     a = np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype)
-    return a.copy() if copy else a
+    if not copy:
+        return a
+    out = np.empty(n, dtype=dtype)
+    _memcpy(out.ctypes.data, a.ctypes.data, out.nbytes)  # a foreign call: the copy runs without the GIL
+    return out
 
 
 class Engine:

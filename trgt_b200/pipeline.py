@@ -151,8 +151,11 @@ class ChunkedHotPath:
         self.engines = list(engines)
         self.w = w
         self.bounds = [(l0, min(l0 + chunk_loci, w.n_loci)) for l0 in range(0, w.n_loci, chunk_loci)]
-        self.paths = [HotPath(self.engines[i % len(self.engines)], w.slice(l0, l1), glue_threads=glue_threads,
-                              use_seq4=use_seq4)
+        # every chunk's arrays (the rebased offsets are fresh copies) in pinned memory, as a host that packs into
+        # trgt_host_alloc buffers has them
+        self.paths = [HotPath(self.engines[i % len(self.engines)],
+                              w.slice(l0, l1).pinned(self.engines[i % len(self.engines)].pinned_array),
+                              glue_threads=glue_threads, use_seq4=use_seq4)
                       for i, (l0, l1) in enumerate(self.bounds)]
 
     def timing(self) -> dict:
