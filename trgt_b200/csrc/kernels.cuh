@@ -265,12 +265,15 @@ k_flank_exact_t(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_
       for (int i = lane; i < (int)(2 * TRGT_KIDX_SLOTS * sizeof(uint16_t) / 16); i += 32) dst[i] = s4[i];
     }
     const uint32_t n_pairs = 2u * (r1 - r0);
-    for (uint32_t p = (uint32_t)lane; p < n_pairs; p += 32u) {
+    for (uint32_t pb = 0; pb < n_pairs; pb += 32u) {
+      const uint32_t p = pb + (uint32_t)lane;
+      const unsigned lanes = __ballot_sync(0xffffffffu, p < n_pairs);  // the lanes that search side by side
+      if (p >= n_pairs) continue;
       const uint32_t r = r0 + (p >> 1), side = p & 1u;
       const uint64_t o = src.read_off[r];
       const int T = (int)(src.read_off[r + 1] - o);
       const int P = side ? P1 : P0;
-      const int pos = flank_exact_thread(KmerIndex{sm.slot[side]}, sm.copies[side], P, src.reads + o, T);
+      const int pos = flank_exact_thread(KmerIndex{sm.slot[side]}, sm.copies[side], P, src.reads + o, T, lanes);
       trgt_flank_hit_t h;
       h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
       if (pos >= 0) {

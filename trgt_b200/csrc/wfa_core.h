@@ -801,7 +801,8 @@ TRGT_HD void kidx_insert(uint16_t *slot, uint32_t h, uint32_t val) {
 
 template <class G>
 TRGT_HD void kidx_build(const G &g, const KmerIndex &idx, const uint8_t *piece, int P) {
-  for (uint32_t i = (uint32_t)g.lane(); i < TRGT_KIDX_SLOTS; i += (uint32_t)g.size()) idx.slot[i] = TRGT_KIDX_EMPTY;
+  for (uint32_t i = (uint32_t)g.lane(); i < TRGT_KIDX_SLOTS / 4; i += (uint32_t)g.size())  // tables are 8-byte aligned
+    ((uint64_t *)idx.slot)[i] = 0xFFFFFFFFFFFFFFFFull;  // four TRGT_KIDX_EMPTY
   g.sync();
   for (int i = g.lane(); i + 8 <= P; i += g.size()) {
     const uint64_t mixed = kidx_mix(wfa_ld64u(piece + i));
@@ -895,12 +896,13 @@ TRGT_HD void fxt_build_copies(const G &g, const uint8_t *piece, int P, uint8_t *
     const int k = idx / W, wd = idx - k * W;
     const int i0 = 8 * wd - 8 - k;  // piece index of the word's first byte
     uint64_t v = 0;
-    if (i0 >= 0 && i0 + 8 <= P) {
-      v = wfa_ld64u(piece + i0);
-    } else if (i0 + 8 > 0 && i0 < P) {  // the two words that straddle an end of the piece
-      for (int b = 0; b < 8; b++)
-        if (i0 + b >= 0 && i0 + b < P) v |= (uint64_t)piece[i0 + b] << (8 * b);
-    }  // words wholly outside the piece are never compared unmasked
+    if (i0 + 8 > 0 && i0 < P) {  // (words wholly outside the piece are never compared unmasked)
+      // a word that straddles an end of the piece comes from the piece's first / last 8 bytes, shifted
+      const int lo = i0 < 0 ? -i0 : 0, hi = i0 + 8 > P ? i0 + 8 - P : 0;  // bytes missing at its low / high end
+      v = wfa_ld64u(piece + (lo ? 0 : hi ? P - 8 : i0));
+      if (lo) v <<= 8 * lo;
+      if (hi) v >>= 8 * hi;
+    }
     *(uint64_t *)(copies + k * FXT_STRIDE + 8 * wd) = v;
   }
   g.sync();
@@ -947,14 +949,24 @@ TRGT_HD bool fxt_verify(const uint8_t *copies, int P, const uint8_t *a) {
 // first start s with t[s..s+P) == piece, or -1 (span_locater.rs:10-12), by ONE lane.
 // Probes in increasing order: their candidate ranges are disjoint and increasing, so the smallest
 // verified candidate of the first probe that has one is the first occurrence.
-TRGT_HD int flank_exact_thread(const KmerIndex &idx, const uint8_t *copies, int P, const uint8_t *t, int T) {
+// Lanes that run a per-lane routine side by side drift apart in its data-dependent loops and are not
+// brought back together until the routine returns.  `lanes` names the lanes of the warp that entered the
+// routine together; at a few points they all pass they wait for each other, so that the expensive stretches
+// (a verification's sixteen-byte compares) run with the whole warp.  0 (and the CPU test build): no-op.
+#if defined(__CUDA_ARCH__)
+#define TRGT_CONVERGE(lanes) do { if (lanes) __syncwarp(lanes); } while (0)
+#else
+#define TRGT_CONVERGE(lanes) do { (void)(lanes); } while (0)
+#endif
+
+TRGT_HD int flank_exact_thread(const KmerIndex &idx, const uint8_t *copies, int P, const uint8_t *t, int T,
+                               unsigned lanes = 0) {
   const int n_starts = T - P + 1;
-  if (n_starts <= 0) return -1;
   const int step = P - 7;
-  const int n_probes = (T - 7) / step;
+  const int n_probes = n_starts > 0 ? (T - 7) / step : 0;
   // Two loops, so that the lanes of a warp (each on its own pair) stay together: the probes' candidates
   // are collected first (in increasing order of probe, hence of candidate range), then verified.
-  int c0 = -1, c1 = -1, c2 = -1, c3 = -1;  // candidate starts, probe index in the top bits
+  int c0 = -1, c1 = -1, c2 = -1, c3 = -1;  // candidate starts
   int n = 0;
   bool many = false;
   for (int ib = 0; ib < n_probes && !many; ib += 4) {  // four probes per step: their loads go out together
@@ -976,31 +988,33 @@ TRGT_HD int flank_exact_thread(const KmerIndex &idx, const uint8_t *copies, int 
       }
     }
   }
-  if (!many) {
-    // candidates of probe i lie in [i * step, (i + 1) * step): the first occurrence is the smallest verified
-    // candidate within the first probe range that has one
-    int best = INT_MAX, best_range = INT_MAX;
-    for (int c = 0; c < n; c++) {
-      const int s = c == 0 ? c0 : c == 1 ? c1 : c == 2 ? c2 : c3;
-      const int range = s / step;  // index of the probe whose range holds s
-      if (range > best_range || s >= best) continue;
-      if (fxt_verify(copies, P, t + s)) { best = s; best_range = range; }
-    }
-    return best == INT_MAX ? -1 : best;
+  // candidates of probe i lie in [i * step, (i + 1) * step): the first occurrence is the smallest verified
+  // candidate within the first probe range that has one.  Four rounds for everybody, one candidate per round.
+  int best = INT_MAX, best_range = INT_MAX;
+#pragma unroll 1
+  for (int c = 0; c < 4; c++) {
+    TRGT_CONVERGE(lanes);
+    if (many || c >= n) continue;
+    const int s = c == 0 ? c0 : c == 1 ? c1 : c == 2 ? c2 : c3;
+    const int range = s / step;  // index of the probe whose range holds s
+    if (range > best_range || s >= best) continue;
+    if (fxt_verify(copies, P, t + s)) { best = s; best_range = range; }
   }
+  TRGT_CONVERGE(lanes);
+  if (!many) return best == INT_MAX ? -1 : best;
   // many candidates (repetitive piece): probe by probe
   for (int i = 0; i < n_probes; i++) {
     const int j = (i + 1) * step - 1;
     const uint64_t mixed = kidx_mix(wfa_ld64u(t + j));
     const uint32_t fp = kidx_fp(mixed);
-    int best = INT_MAX;
+    int pbest = INT_MAX;
     for (uint32_t h = kidx_home(mixed), v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
       if ((v >> 9) != fp) continue;
       const int s = j - (int)(v & 511u);
-      if (s < 0 || s >= n_starts || s >= best) continue;
-      if (fxt_verify(copies, P, t + s)) best = s;
+      if (s < 0 || s >= n_starts || s >= pbest) continue;
+      if (fxt_verify(copies, P, t + s)) pbest = s;
     }
-    if (best != INT_MAX) return best;
+    if (pbest != INT_MAX) return pbest;
   }
   return -1;
 }
