@@ -456,6 +456,48 @@ def run_b200(args):
         except Exception as exc:  # never let the extra row break the headline line
             vcf = {"error": repr(exc)}
 
+    # ---- next row (first half): read clipping on synthetic BAM CIGARs, timed on its own ----
+    clip = None
+    if world == 1:
+        try:
+            rng = np.random.default_rng(7)
+            n_cl, ops_per = 1_000_000, 40   # a 15 kb HiFi alignment has a few dozen CIGAR ops
+            codes = rng.choice(np.array([7, 7, 7, 8, 1, 2], dtype=np.uint32), size=n_cl * ops_per)
+            lens = np.where(codes == 7, rng.integers(50, 700, size=codes.size), rng.integers(1, 4, size=codes.size)).astype(np.uint32)
+            ops = (lens << 4) | codes
+            offs = (np.arange(n_cl + 1, dtype=np.uint64) * ops_per)
+            n_loc = n_cl // 30
+            lro = np.minimum(np.arange(n_loc + 1, dtype=np.uint64) * 30, n_cl).astype(np.uint32)
+            lro[-1] = n_cl
+            centre = rng.integers(4000, 9000, size=n_loc).astype(np.int64)
+            regions = np.stack([centre - 500, centre + 530], axis=1)
+            refs = rng.integers(0, 3000, size=n_cl).astype(np.int64)
+            eng.clip_reads(ops, offs, refs, regions, lro)  # warm-up
+            t0 = time.perf_counter()
+            clips = eng.clip_reads(ops, offs, refs, regions, lro)
+            dt = time.perf_counter() - t0
+            clip = {"call": "trgt_clip_reads (clip_cigar of clip_region.rs:105-186, host buffers in and out)", "reads": n_cl,
+                    "cigar_ops_per_read": ops_per, "ms": dt * 1e3, "reads_per_s": n_cl / dt,
+                    "overlapping": int((clips["status"] == 1).sum())}
+            if not args.no_cpu_baseline:
+                from oracle import oracle as orc
+                same = 0
+                nchk = 2000
+                read_locus = np.repeat(np.arange(n_loc), np.diff(lro.astype(np.int64)))
+                for r in range(nchk):
+                    o = ops[r * ops_per:(r + 1) * ops_per].tolist()
+                    exp = orc.clip_cigar(o, int(refs[r]), (int(regions[read_locus[r], 0]), int(regions[read_locus[r], 1])))
+                    c = clips[r]
+                    if exp is None:
+                        same += c["status"] == 0
+                    else:
+                        same += (c["status"] == 1 and (int(c["ref_start"]), int(c["query_start"]), int(c["query_end"])) == exp[:3]
+                                 and int(c["n_ops"]) == len(exp[3]) and int(c["first_word"]) == exp[3][0]
+                                 and int(c["last_word"]) == exp[3][-1])
+                clip["parity"] = f"{int(same)}/{nchk} reads identical to the oracle"
+        except Exception as exc:  # never let the extra row break the headline line
+            clip = {"error": repr(exc)}
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -465,7 +507,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),
                 "reads_in": "BAM 4-bit bases (trgt_flank_spans_seq4), decoded on the device" if use_seq4 else "ASCII (trgt_flank_spans)",
                 "glue_threads": glue_threads, "phase_ms_summed_over_host_threads": e2e_phases},
-        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "vcf_row": vcf, "kernels": kernels,
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "clip_row": clip, "vcf_row": vcf, "kernels": kernels,
         "wfa_fallback_pairs": hp.n_wfa(), "flank_fallback_counts": dict(zip(("second_tier", "wide_band", "full_width"), hp.fallback_counts())),
         "workload_gen_s": t_gen,
     }
