@@ -657,10 +657,14 @@ __global__ void k_wfa_score(WfaSrc src, const uint32_t *__restrict__ work, const
   // haplotype equal their backbone), then the warp aligns the remaining ones one at a time
   if (!BLOCK && src.mode == WFA_MODE_E2E) {
     const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t base = slot * 32u; base < n; base += n_slots * 32u) {
+    // direct mode: 32 members per warp and round (identity test by lane, then the warp aligns the ones that
+    // differ one at a time); list mode (members already known to differ): one member per warp and round, so
+    // that a short list spreads over all warps instead of queueing 32 deep behind a few
+    const uint32_t G = work ? 1u : 32u;
+    for (uint32_t base = slot * G; base < n; base += n_slots * G) {
       const uint32_t i = base + lane;
       bool pending = false;
-      if (i < n) {
+      if (lane < G && i < n) {
         const uint32_t id = work ? work[i] : i;
         const WfaProb pr = wfa_prob_of(src, id);
         if (pr.P == pr.T && (pr.P == 0 || wfa_match_len(pr.p, pr.t, pr.P) == pr.P)) {
