@@ -76,7 +76,11 @@ long emu_hmm_annotate_lanes(const uint8_t *motifs, const uint64_t *moff, int nm,
     const int stride = 5;
     std::vector<double> t0((size_t)S * stride, 0.0), t1((size_t)S * stride, 0.0);
     const HmmModelScan scan0 = hmm_model_scan(motifs, moff, nm);
-    hmm_viterbi_thread(scan0, c, jt.off.data(), jt.lp.data(), allele, L, t0.data() + 2, t1.data() + 2, stride, bp.data());
+    if (scan0.S <= HMM_THREAD_S)  // as on the device: the whole model in registers
+      hmm_viterbi_thread(hmm_model_pack(scan0), c, jt.off.data(), jt.lp.data(), allele, L, t0.data() + 2, t1.data() + 2,
+                         stride, bp.data());
+    else
+      hmm_viterbi_thread(scan0, c, jt.off.data(), jt.lp.data(), allele, L, t0.data() + 2, t1.data() + 2, stride, bp.data());
   } else if (lanes == 0) {
     hmm_viterbi(g, model, c, jt.lp.data(), allele, L, sc0.data(), sc1.data(), bp.data());
   } else {
@@ -95,7 +99,10 @@ long emu_hmm_annotate_lanes(const uint8_t *motifs, const uint64_t *moff, int nm,
                             path_cap, 0, &plen);
   if (a.status < 0) return -402;
   if (a.n_spans > span_cap) return -2;
-  HmmAnnot b2 = hmm_annotate(scan, allele, L, bp.data(), 6, mc, spans, a.n_spans, nullptr, 0, 0, nullptr);
+  // the writing walk through the register-packed model where the device uses it (small models, thread variant)
+  HmmAnnot b2 = (lanes == -1 && scan.S <= HMM_THREAD_S)
+                    ? hmm_annotate(hmm_model_pack(scan), allele, L, bp.data(), 6, mc, spans, a.n_spans, nullptr, 0, 0, nullptr)
+                    : hmm_annotate(scan, allele, L, bp.data(), 6, mc, spans, a.n_spans, nullptr, 0, 0, nullptr);
   if (b2.n_spans != a.n_spans) return -403;
   *purity = a.purity;
   if (path_len) *path_len = plen;

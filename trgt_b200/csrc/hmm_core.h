@@ -115,6 +115,51 @@ TRGT_HD HmmModelScan hmm_model_scan(const uint8_t *motifs, const uint64_t *moff,
   return m;
 }
 
+#define HMM_THREAD_S 32  // models up to this many states run one allele per lane (k_hmm_viterbi_thread)
+
+// The same again with the whole model in two registers, for the models one lane handles on its own
+// (S <= HMM_THREAD_S = 32, i.e. at most 8 motif bases in at most 6 blocks): block lengths as nibbles, the
+// sanitised motif bytes concatenated.  Nothing of the model is re-read from memory inside the DP loops.
+struct HmmModelPacked {
+  int S, nb;
+  uint64_t lens;   // nibble b = length of motif block b
+  uint64_t offs;   // nibble b = offset of block b's first byte in `bytes`
+  uint64_t bytes;  // sanitised motif bytes
+  TRGT_HD int block_n(int b) const { return b == nb - 1 ? 0 : (int)((lens >> (4 * b)) & 15u); }
+  TRGT_HD int block_ms(int b) const {
+    int ms = 2;
+    for (int i = 0; i < b; i++) ms += 3 * (int)((lens >> (4 * i)) & 15u) + 1;
+    return ms;
+  }
+  TRGT_HD int block_of(int st) const {
+    int ms = 2;
+    for (int b = 0; b < nb - 1; b++) {
+      const int sz = 3 * (int)((lens >> (4 * b)) & 15u) + 1;
+      if (st < ms + sz) return b;
+      ms += sz;
+    }
+    return nb - 1;
+  }
+  TRGT_HD uint8_t motif_byte(int b, int i) const {
+    return (uint8_t)(bytes >> (8 * ((int)((offs >> (4 * b)) & 15u) + i)));
+  }
+};
+
+// only for models with S <= 32 (checked by the caller)
+TRGT_HD HmmModelPacked hmm_model_pack(const HmmModelScan &m) {
+  HmmModelPacked p;
+  p.S = m.S; p.nb = m.nb; p.lens = 0; p.offs = 0; p.bytes = 0;
+  int o = 0;
+  for (int b = 0; b < m.nb - 1; b++) {
+    const int n = m.block_n(b);
+    p.lens |= (uint64_t)n << (4 * b);
+    p.offs |= (uint64_t)o << (4 * b);
+    for (int i = 0; i < n; i++) p.bytes |= (uint64_t)m.motif_byte(b, i) << (8 * (o + i));
+    o += n;
+  }
+  return p;
+}
+
 enum HmmRoleKind {
   HR_START = 0, HR_RS, HR_RE, HR_END, HR_MS, HR_MATCH, HR_INS, HR_DEL, HR_ME, HR_SKIP_MS, HR_SKIP, HR_SKIP_ME
 };
@@ -511,7 +556,8 @@ TRGT_HD void hmm_viterbi_small(const G &g, const HmmModel &m, const HmmConsts &c
 // per instruction.  Block geometry comes from HmmModelScan (no tables); score columns are strided
 // arrays (sc[state * stride]) so that neighbouring threads hit different shared-memory banks.
 // Candidate order, strict '>' and left-to-right sums as in hmm_viterbi: bit-identical results.
-TRGT_HD void hmm_viterbi_thread(const HmmModelScan &m, const HmmConsts &c, const uint32_t *mm_off, const double *mm_lp,
+template <class M>
+TRGT_HD void hmm_viterbi_thread(const M &m, const HmmConsts &c, const uint32_t *mm_off, const double *mm_lp,
                                 const uint8_t *allele, int L, double *prev, double *cur, int stride, uint8_t *bp) {
   const int S = m.S, nb = m.nb;
   const double NEG = -INFINITY;

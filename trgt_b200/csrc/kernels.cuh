@@ -1031,7 +1031,6 @@ __device__ __forceinline__ HmmWarpMem hmm_carve(unsigned char *base, int S_max, 
   return w;
 }
 
-#define HMM_THREAD_S 32  // models up to this many states run one allele per thread
 
 // One THREAD per allele for small models (every locus of a genome-wide catalog: S = 14..26): 32
 // alleles advance per instruction.  Two score columns of HMM_THREAD_S doubles per thread, strided
@@ -1056,7 +1055,7 @@ k_hmm_viterbi_thread(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long b
     status[a] = 0;
     const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
     if (L == 0) continue;
-    hmm_viterbi_thread(model, hb.c, hb.mm_off, hb.mm_lp, hb.alleles + hb.allele_off[a], L, sc + threadIdx.x,
+    hmm_viterbi_thread(hmm_model_pack(model), hb.c, hb.mm_off, hb.mm_lp, hb.alleles + hb.allele_off[a], L, sc + threadIdx.x,
                        sc + (size_t)s_cap * 128 + threadIdx.x, 128, bp + (hb.bp_off[a] - bp_base));
   }
 }
@@ -1123,8 +1122,11 @@ k_hmm_walk(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, co
     // span_scratch: one slot per base of the wave's alleles (a collapsed span covers at least one base); the
     // walk fills the allele's slots from the back, so its spans end up in the last n_spans of them, in order
     HmmSpan *sp = span_scratch ? (HmmSpan *)(span_scratch + (hb.allele_off[a] - hb.allele_off[a0])) : nullptr;
-    const HmmAnnot an = hmm_annotate(model, hb.alleles + hb.allele_off[a], L, bp + (hb.bp_off[a] - bp_base), 6, my_mc,
-                                     sp, (uint32_t)L, nullptr, 0, 0, &plen);
+    const HmmAnnot an = model.S <= HMM_THREAD_S
+                            ? hmm_annotate(hmm_model_pack(model), hb.alleles + hb.allele_off[a], L,
+                                           bp + (hb.bp_off[a] - bp_base), 6, my_mc, sp, (uint32_t)L, nullptr, 0, 0, &plen)
+                            : hmm_annotate(model, hb.alleles + hb.allele_off[a], L, bp + (hb.bp_off[a] - bp_base), 6, my_mc,
+                                           sp, (uint32_t)L, nullptr, 0, 0, &plen);
     purity[a] = an.purity;
     n_spans[a] = an.n_spans;
     if (path_len) path_len[a] = plen;
