@@ -77,7 +77,7 @@ long emu_hmm_annotate_lanes(const uint8_t *motifs, const uint64_t *moff, int nm,
     std::vector<double> t0((size_t)S * stride, 0.0), t1((size_t)S * stride, 0.0);
     const HmmModelScan scan0 = hmm_model_scan(motifs, moff, nm);
     if (scan0.S <= HMM_THREAD_S)  // as on the device: the whole model in registers
-      hmm_viterbi_thread(hmm_model_pack(scan0), c, jt.off.data(), jt.lp.data(), allele, L, t0.data() + 2, t1.data() + 2,
+      hmm_viterbi_thread(hmm_model_pack(scan0, jt.off.data()), c, jt.off.data(), jt.lp.data(), allele, L, t0.data() + 2, t1.data() + 2,
                          stride, bp.data());
     else
       hmm_viterbi_thread(scan0, c, jt.off.data(), jt.lp.data(), allele, L, t0.data() + 2, t1.data() + 2, stride, bp.data());

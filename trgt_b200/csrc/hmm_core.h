@@ -104,6 +104,7 @@ struct HmmModelScan {
     return nb - 1;
   }
   TRGT_HD uint8_t motif_byte(int b, int i) const { return hmm_clean_motif_base(motifs[moff[b] + i], (uint32_t)i); }
+  TRGT_HD uint32_t jump_off(int b, const uint32_t *mm_off) const { return mm_off[block_n(b)]; }
 };
 
 TRGT_HD HmmModelScan hmm_model_scan(const uint8_t *motifs, const uint64_t *moff, int nm) {
@@ -125,6 +126,8 @@ struct HmmModelPacked {
   uint64_t lens;   // nibble b = length of motif block b
   uint64_t offs;   // nibble b = offset of block b's first byte in `bytes`
   uint64_t bytes;  // sanitised motif bytes
+  uint64_t joffs;  // byte b = where block b's jump-in ln table starts (mm_off[length])
+  TRGT_HD uint32_t jump_off(int b, const uint32_t *) const { return (uint32_t)(joffs >> (8 * b)) & 255u; }
   TRGT_HD int block_n(int b) const { return b == nb - 1 ? 0 : (int)((lens >> (4 * b)) & 15u); }
   TRGT_HD int block_ms(int b) const {
     int ms = 2;
@@ -146,14 +149,15 @@ struct HmmModelPacked {
 };
 
 // only for models with S <= 32 (checked by the caller)
-TRGT_HD HmmModelPacked hmm_model_pack(const HmmModelScan &m) {
+TRGT_HD HmmModelPacked hmm_model_pack(const HmmModelScan &m, const uint32_t *mm_off = nullptr) {
   HmmModelPacked p;
-  p.S = m.S; p.nb = m.nb; p.lens = 0; p.offs = 0; p.bytes = 0;
+  p.S = m.S; p.nb = m.nb; p.lens = 0; p.offs = 0; p.bytes = 0; p.joffs = 0;
   int o = 0;
   for (int b = 0; b < m.nb - 1; b++) {
     const int n = m.block_n(b);
     p.lens |= (uint64_t)n << (4 * b);
     p.offs |= (uint64_t)o << (4 * b);
+    if (mm_off) p.joffs |= (uint64_t)(mm_off[n] & 255u) << (8 * b);  // n <= 8: the offset is below 37
     for (int i = 0; i < n; i++) p.bytes |= (uint64_t)m.motif_byte(b, i) << (8 * (o + i));
     o += n;
   }
@@ -562,9 +566,12 @@ TRGT_HD void hmm_viterbi_thread(const M &m, const HmmConsts &c, const uint32_t *
   const int S = m.S, nb = m.nb;
   const double NEG = -INFINITY;
 #define SC(a, st) (a)[(size_t)(st) * (size_t)stride]
+  uint8_t base_next = L > 0 ? allele[0] : 0;  // the base of column col + 1, loaded one column ahead
   for (int col = 0; col <= L + 1; col++) {
+    const uint8_t base_cur = base_next;
+    if (col + 1 <= L) base_next = allele[col];
     const int sym = (col == 0 || col == L + 1)
-                        ? 0 : hmm_symbol(hmm_clean_base(allele[col - 1], (uint32_t)(col - 1)));
+                        ? 0 : hmm_symbol(hmm_clean_base(base_cur, (uint32_t)(col - 1)));
     uint8_t *bpc = bp + (size_t)col * (size_t)S;
     // ---- emitting states, from the previous column ----
     SC(cur, 0) = col == 0 ? c.em_one : NEG;   // start (hmm_model.rs:91-94)
@@ -572,7 +579,7 @@ TRGT_HD void hmm_viterbi_thread(const M &m, const HmmConsts &c, const uint32_t *
     int ms = 2;
     for (int b = 0; b < nb - 1; b++) {
       const int n = m.block_n(b);
-      const double *jump = mm_lp + mm_off[n];
+      const double *jump = mm_lp + m.jump_off(b, mm_off);
       for (int i = 0; i < n; i++) {
         {  // match_i
           const int st = ms + 1 + i;

@@ -1055,7 +1055,7 @@ k_hmm_viterbi_thread(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long b
     status[a] = 0;
     const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
     if (L == 0) continue;
-    hmm_viterbi_thread(hmm_model_pack(model), hb.c, hb.mm_off, hb.mm_lp, hb.alleles + hb.allele_off[a], L, sc + threadIdx.x,
+    hmm_viterbi_thread(hmm_model_pack(model, hb.mm_off), hb.c, hb.mm_off, hb.mm_lp, hb.alleles + hb.allele_off[a], L, sc + threadIdx.x,
                        sc + (size_t)s_cap * 128 + threadIdx.x, 128, bp + (hb.bp_off[a] - bp_base));
   }
 }
