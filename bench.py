@@ -286,7 +286,8 @@ def run_b200(args):
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1) / max(1, args.steps)
-    launches = (eng.launches() - launches0) // max(1, args.steps)
+    launches_total = eng.launches() - launches0                 # kernels of this engine inside the timed region
+    launches = launches_total // max(1, args.steps)
     stats = eng.kernel_stats()
     unpack_stat = None
     if use_seq4:  # outside the timed region: one whole-shard launch of the e2e path's decode kernel, for its roofline entry
@@ -502,7 +503,8 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32 wavefront offsets + f64 Viterbi", "data": "synthetic",
-        "config": workload_config(args, world), "clocks": clk, "gpu_launches": int(launches),
+        "config": workload_config(args, world), "clocks": clk, "gpu_launches": int(launches_total),
+        "gpu_launches_per_step": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),
                 "reads_in": "BAM 4-bit bases (trgt_flank_spans_seq4), decoded on the device" if use_seq4 else "ASCII (trgt_flank_spans)",
