@@ -240,6 +240,45 @@ def test_flank_banded_core(emul, oracle):
     assert resolved > 300
 
 
+def test_flank_banded_straddling_gaps(emul, oracle):
+    """A scoring with a cheap gap open (3,3,1): two-base gaps that straddle block boundaries damage two seed
+    blocks for o+2e < 2*min(x,o+e), so the block count of the seed filter must account for them
+    (flank_seed_blocks); a decoy copy with one intact block must not capture the band."""
+    emul.emu_flank_banded.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_double, C.c_int, C.POINTER(C.c_int)]
+    rng = random.Random(5)
+    x, o, e, S, P = 3, 3, 1, 24, 250
+    nb_naive = S // min(x, o + e) + 1
+    blen = P // nb_naive
+    resolved = 0
+    for _ in range(200):
+        p = rnd(rng, P)
+        true = bytearray(p)
+        cuts = sorted(rng.sample(range(1, nb_naive), 4), reverse=True)
+        touched = set()
+        for b in cuts:
+            touched |= {b - 1, b}
+        mb = [b for b in range(nb_naive) if b not in touched][0]
+        pos = mb * blen + blen // 2
+        true[pos] = ord("A") if true[pos] != ord("A") else ord("C")
+        for b in cuts:
+            del true[b * blen - 1: b * blen + 1]
+        decoy = bytearray(p)
+        for b in range(8):
+            q = b * blen + blen // 2
+            decoy[q] = ord("A") if decoy[q] != ord("A") else ord("C")
+        t = rnd(rng, 200) + bytes(true) + rnd(rng, 400) + bytes(decoy) + rnd(rng, 300)
+        exp, via, nm = oracle.find_span(p, t, (x, o, e), P * 0.7)
+        out = (C.c_int * 6)()
+        rc = emul.emu_flank_banded(p, P, t, len(t), x, o, e, S, 0.7, 65536, out)
+        if rc == 0:
+            resolved += 1
+            assert (out[1], out[2]) == (via, nm)
+            if exp is not None:
+                assert (out[4], out[5]) == exp
+    assert resolved > 50
+
+
 # ---- the same cores with several lock-step host lanes (tests/emul/lanes.h): leader election,
 # ---- broadcasts and barrier placement are exercised, not just the index arithmetic --------------
 

@@ -225,6 +225,19 @@ int persistent_grid(trgt_engine *e, K kernel, int block, size_t smem, int *grid_
   return 0;
 }
 
+// A persistent kernel whose every slot (CTA, or warp when slots_per_block > 1) owns `stride_ints` ints of global
+// scratch: shrink the grid until the scratch fits the engine's workspace budget (fewer slots, same result).
+int cap_grid_to_budget(trgt_engine *e, int *grid, int slots_per_block, size_t stride_ints, const char *what) {
+  if (stride_ints == 0) return 0;
+  const size_t budget_ints = e->workspace_budget / sizeof(int);
+  const size_t per_block = stride_ints * (size_t)slots_per_block;
+  if (per_block > budget_ints)
+    return fail(e, TRGT_ERR_INTERNAL, "%s: one scratch slot of %zu ints exceeds the workspace budget", what, stride_ints);
+  const size_t fit = budget_ints / per_block;
+  if ((size_t)*grid > fit) *grid = (int)fit;
+  return 0;
+}
+
 int check_seqs(trgt_engine *e, const trgt_seqs_t *s, const char *what) {
   if (!s || (s->n && (!s->offsets))) return fail(e, TRGT_ERR_ARG, "%s: null sequence set", what);
   for (uint64_t i = 0; i < s->n; i++)
@@ -568,8 +581,11 @@ int32_t trgt_flank_upload(trgt_engine_t *e, const trgt_seqs_t *left_pieces, cons
   std::lock_guard<std::mutex> lk(e->mu);
   *out = nullptr;
   trgt_flank_batch *b = new trgt_flank_batch();
-  const int rc = flank_upload_into(e, b, left_pieces, right_pieces, reads, locus_read_offsets, n_loci, scoring,
-                                   min_flank_id_frac);
+  int rc = flank_upload_into(e, b, left_pieces, right_pieces, reads, locus_read_offsets, n_loci, scoring,
+                             min_flank_id_frac);
+  // the copies were queued from the caller's buffers: with pinned sources they are asynchronous to the host, and
+  // the header promises that no pointer is retained after return
+  if (rc == 0 && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(e, TRGT_ERR_CUDA, "flank upload failed");
   if (rc != 0) {
     trgt_flank_free(nullptr, b);
     return rc;
@@ -658,6 +674,7 @@ static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src
     size_t stride = 0;
     if (bound > (size_t)smem_ring_ints) {
       stride = bound;
+      TRY(cap_grid_to_budget(e, &grid, 1, stride, "flank ring"));
       TRY(dev_reserve(e, b->gring, (size_t)grid * stride * sizeof(int)));
       gring = (int *)b->gring.p;
     }
@@ -1167,7 +1184,9 @@ int32_t trgt_align_upload(trgt_engine_t *e, const trgt_seqs_t *backbones, const 
   std::lock_guard<std::mutex> lk(e->mu);
   *out = nullptr;
   trgt_align_batch *b = new trgt_align_batch();
-  const int rc = align_upload_into(e, b, backbones, seqs, group_seq_offsets, n_groups);
+  int rc = align_upload_into(e, b, backbones, seqs, group_seq_offsets, n_groups);
+  // as trgt_flank_upload: the caller's buffers are free again when this returns
+  if (rc == 0 && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(e, TRGT_ERR_CUDA, "align upload failed");
   if (rc != 0) {
     trgt_align_free(nullptr, b);
     return rc;
@@ -1202,6 +1221,7 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
     size_t stride = 0;
     if (bound > (size_t)smem_ring_ints) {
       stride = bound;
+      TRY(cap_grid_to_budget(e, &grid, 1, stride, "align ring"));
       TRY(dev_reserve(e, b->gring, (size_t)grid * stride * sizeof(int)));
       gring = (int *)b->gring.p;
     }
@@ -1225,6 +1245,7 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
     size_t stride = 0;
     if (bound > (size_t)smem_ring_ints) {
       stride = bound;
+      TRY(cap_grid_to_budget(e, &grid, wpb, stride, "align ring"));
       TRY(dev_reserve(e, b->gring, (size_t)grid * wpb * stride * sizeof(int)));
       gring = (int *)b->gring.p;
     }

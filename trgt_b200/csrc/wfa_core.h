@@ -695,6 +695,25 @@ TRGT_HD int flank_scan(const G &g, const uint8_t *piece, int P, const uint8_t *t
 
 // ---------------------------------------------------------------- seed filter ----------------
 
+// Number of disjoint pattern blocks the seed filter cuts the piece into for cost cap S: one more than the
+// blocks an alignment of cost <= S can damage, so that one block survives verbatim.  A mismatch damages one
+// block for x, a one-base gap one block for o+e; a longer gap can straddle block boundaries: g deleted
+// bases touch at most 1 + ceil((g-1)/blen) blocks, and blen >= TRGT_SEED_BLEN_MIN is enforced by every
+// caller, so j+1 blocks cost at least o + (TRGT_SEED_BLEN_MIN*(j-1) + 2) e.  The bound is the best ratio
+// blocks/cost over the events that fit the cap at all.  (For the presets 2,5,1 and 1,0,1 this equals
+// S / min(x, o+e) + 1; scorings with a cheap gap open, e.g. 3,3,1, need more blocks.)
+#define TRGT_SEED_BLEN_MIN 12
+TRGT_HD int flank_seed_blocks(const WfaProb &pr, int S) {
+  const int o = pr.oe - pr.e;
+  int d = S / wfa_imin(pr.x, pr.oe);
+  for (int j = 1; j < 16; j++) {
+    const int cost = o + (TRGT_SEED_BLEN_MIN * (j - 1) + 2) * pr.e;
+    if (cost > S) break;
+    d = wfa_imax(d, S * (j + 1) / cost);
+  }
+  return d + 1;
+}
+
 // Diagonal band that provably contains every alignment of the whole pattern with cost <= S.
 // Such an alignment has at most S / min(x, o+e) mismatches and gaps, so of nb = that + 1
 // disjoint pattern blocks one is copied without any edit and shows up as an exact occurrence in the
@@ -704,11 +723,10 @@ TRGT_HD int flank_scan(const G &g, const uint8_t *piece, int P, const uint8_t *t
 // occurrence, blocks too short to be selective).
 template <class G>
 TRGT_HD bool flank_seed_band(const G &g, const WfaProb &pr, int S, uint64_t *keys, int *klo, int *khi) {
-  const int emin = wfa_imin(pr.x, pr.oe);
-  const int nb = S / emin + 1;
+  const int nb = flank_seed_blocks(pr, S);
   if (nb > 32) return false;
   const int blen = pr.P / nb;
-  if (blen < 12 || pr.T < blen) return false;
+  if (blen < TRGT_SEED_BLEN_MIN || pr.T < blen) return false;
   const int o = pr.oe - pr.e;
   const int R = S > o ? (S - o) / pr.e : 0;
   for (int b = g.lane(); b < nb; b += g.size()) keys[b] = wfa_ld64u(pr.p + b * blen);
@@ -1023,11 +1041,10 @@ TRGT_HD int flank_exact_thread(const KmerIndex &idx, const uint8_t *copies, int 
 template <class G>
 TRGT_HD int flank_seed_band_indexed(const G &g, const KmerIndex &idx, const WfaProb &pr, int S, int *cand, int *klo,
                                     int *khi) {
-  const int emin = wfa_imin(pr.x, pr.oe);
-  const int nb = S / emin + 1;
+  const int nb = flank_seed_blocks(pr, S);
   if (nb > 32) return 0;
   const int blen = pr.P / nb;
-  if (blen < 12 || pr.T < blen) return 0;
+  if (blen < TRGT_SEED_BLEN_MIN || pr.T < blen) return 0;
   const int o = pr.oe - pr.e;
   const int R = S > o ? (S - o) / pr.e : 0;
   const int step = blen - 7;
@@ -1210,11 +1227,10 @@ TRGT_HD int flank_locate_banded_lean(const G &g, const WfaProb &pr, int S, doubl
 // stay together: first every probe's candidates are collected, then they are verified.
 #define FT1_CANDS 12  // candidates a lane keeps; more (repetitive pieces) hands the pair on
 TRGT_HD int flank_seed_band_thread(const KmerIndex &idx, const WfaProb &pr, int S, int *klo, int *khi) {
-  const int emin = wfa_imin(pr.x, pr.oe);
-  const int nb = S / emin + 1;
+  const int nb = flank_seed_blocks(pr, S);
   if (nb > 32) return 0;
   const int blen = pr.P / nb;
-  if (blen < 12 || pr.T < blen) return 0;
+  if (blen < TRGT_SEED_BLEN_MIN || pr.T < blen) return 0;
   const int o = pr.oe - pr.e;
   const int R = S > o ? (S - o) / pr.e : 0;
   const int step = blen - 7;

@@ -39,9 +39,15 @@ class RecordGather:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
 
+    def _drain(self):
+        """Wait for the previous call's staging copy and gather: they read self.pin / self.dev asynchronously."""
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+
     def _ensure(self, n: int):
         if n <= self.cap:
             return
+        self._drain()  # earlier operations may still use the buffers that are about to be replaced
         self.cap = int(n * 1.5) + (1 << 16)
         cuda = self.device.type == "cuda"
         self.pin = torch.empty(self.cap, dtype=torch.uint8, pin_memory=cuda)
@@ -65,12 +71,14 @@ class RecordGather:
         sizes = [int(v) for v in sizes_t.cpu().tolist()]
         mx = max(sizes)
         self._ensure(mx)
+        self._drain()  # the staging buffer is rewritten below
         if parts:
             np.concatenate(parts, out=self.pin_np[:n])
         if self.dev is not self.pin:
             self.dev[:n].copy_(self.pin[:n], non_blocking=True)
         dist.gather(self.dev[:mx], [t[:mx] for t in self.recv] if self.rank == 0 else None, dst=0)
         if self.rank != 0:
+            self._drain()  # the caller may re-enter (or drop its arrays) as soon as this returns
             return None
         out, o = [], 0
         for t, sz in zip(self.recv, sizes):
