@@ -98,6 +98,12 @@ void trgt_engine_set_workspace_budget(trgt_engine_t *eng, size_t bytes);
  * path.  Default 16. */
 void trgt_engine_set_flank_band_budget(trgt_engine_t *eng, int32_t max_cost);
 
+/* Phase C runs the alleles of single-motif loci (one motif of 1..8 bases: every locus of a genome-wide catalog)
+ * through kernels specialised per motif length (one lane per allele, score column in registers, one packed
+ * back-pointer word per column); all other loci take the generic kernels.  Results are identical either way;
+ * 0 sends every allele down the generic path (diagnostic).  Default on.  Applies to batches uploaded afterwards. */
+void trgt_engine_set_hmm_lane_path(trgt_engine_t *eng, int32_t on);
+
 /* pinned host memory for the caller's packing buffers (DMA-direct H2D/D2H) */
 void *trgt_host_alloc(size_t bytes);
 void trgt_host_free(void *p);

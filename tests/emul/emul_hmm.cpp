@@ -70,6 +70,55 @@ long emu_hmm_annotate_lanes(const uint8_t *motifs, const uint64_t *moff, int nm,
     if (path_len) *path_len = 0;
     return 0;
   }
+  if (lanes == -2) {  // single-motif fast path: registers + one packed word per column (hmm_viterbi_lane)
+    const int n = nm == 1 ? (int)(moff[1] - moff[0]) : 0;
+    if (n < 1 || n > HMM_LANE_NMAX) return -405;
+    const int stride = 3;  // any stride: the device uses 32
+    std::vector<uint32_t> words((size_t)L * stride + 1, 0xEEEEEEEEu);
+    const uint64_t mb = hmm_pack_motif(motifs + moff[0], n);
+    const double *jump = jt.lp.data() + jt.off[n];
+    HmmAnnot a1, a2;
+    uint64_t plen = 0;
+    std::vector<uint32_t> rev(path_cap ? path_cap : 1);
+#define EMU_LANE(N)                                                                                              \
+  case N: {                                                                                                      \
+    hmm_viterbi_lane<N>(c, jump, mb, allele, L, words.data(), stride);                                           \
+    const HmmModelSingle<N> m1{mb};                                                                              \
+    HmmBpWords<N> bw(words.data(), stride, L);                                                             \
+    std::vector<uint32_t> mc_tmp(2, 0);                                                                          \
+    a1 = hmm_annotate_bp(m1, allele, L, bw, 6, mc_tmp.data(), HmmSpanArray{nullptr}, 0, rev.data(), path_cap, 0, &plen); \
+    if (a1.status < 0) return -402;                                                                              \
+    if (a1.n_spans > span_cap) return -2;                                                                        \
+    a2 = hmm_annotate_bp(m1, allele, L, bw, 6, mc, HmmSpanArray{spans}, a1.n_spans, (uint32_t *)nullptr, 0, 0, (uint64_t *)nullptr); \
+    {  /* the table-driven walk the device uses for counting and spans must agree with it */                     \
+      std::vector<HmmLaneEntry> tab(32);                                                                         \
+      for (int st_ = 0; st_ < 32; st_++) tab[st_] = hmm_lane_table_entry(N, st_);                                \
+      std::vector<uint32_t> mc3(2, 0);                                                                           \
+      std::vector<HmmSpan> sp3(a1.n_spans + 1);                                                                  \
+      uint64_t plen3 = 0;                                                                                        \
+      const HmmAnnot a3 = hmm_walk_table(tab.data(), N, mb, allele, L, words.data(), stride, 6, mc3.data(),      \
+                                         HmmSpanArray{sp3.data()}, a1.n_spans, &plen3);                          \
+      if (a3.status != 0 || a3.n_spans != a1.n_spans || plen3 != plen || mc3[0] != mc[0]) return -406;           \
+      if (!(a3.purity == a1.purity || (a3.purity != a3.purity && a1.purity != a1.purity))) return -407;          \
+      for (uint32_t q_ = 0; q_ < a1.n_spans; q_++)                                                               \
+        if (sp3[q_].motif_index != spans[q_].motif_index || sp3[q_].start != spans[q_].start || sp3[q_].end != spans[q_].end) return -408; \
+    }                                                                                                            \
+    break;                                                                                                       \
+  }
+    switch (n) {
+      EMU_LANE(1) EMU_LANE(2) EMU_LANE(3) EMU_LANE(4) EMU_LANE(5) EMU_LANE(6) EMU_LANE(7) EMU_LANE(8)
+      default: return -405;
+    }
+#undef EMU_LANE
+    if (a2.n_spans != a1.n_spans) return -403;
+    *purity = a1.purity;
+    if (path_len) *path_len = plen;
+    if (path_out) {
+      const uint64_t np = plen < path_cap ? plen : path_cap;
+      for (uint64_t i = 0; i < np; i++) path_out[i] = rev[np - 1 - i];
+    }
+    return (long)a1.n_spans;
+  }
   std::vector<double> sc0(S), sc1(S);
   std::vector<uint8_t> bp((size_t)(L + 2) * S, 0xEE);
   if (lanes == -1) {  // the one-thread-per-allele variant, with a stride as on the device

@@ -468,6 +468,52 @@ def test_hmm_core_thread_per_allele(emul, oracle):
         assert [(spans[i].m, spans[i].s, spans[i].e) for i in range(n)] == exp_sp and pur.value == exp_pur
 
 
+def test_hmm_core_single_motif_lane(emul, oracle):
+    """hmm_viterbi_lane<N> (single-motif loci: score column in registers, one packed back-pointer word per
+    column, ms / skip_ms / rs folded into re) + the walk over the packed words must give the oracle's state
+    path, MC, MS and AP for every motif length the fast path takes (1..8), 'N' motif bases, invalid allele
+    bases, interruptions, and long alleles."""
+    emul.emu_hmm_annotate_lanes.restype = C.c_long
+    rng = random.Random(4242)
+    seen = set()
+    for it in range(1500):
+        n = rng.choice([1, 2, 2, 2, 3, 3, 4, 4, 5, 6, 6, 7, 8])
+        motif = rnd(rng, n, "ACGTN" if rng.random() < 0.15 else "ACGT")
+        r = rng.random()
+        if r < 0.75:
+            allele = noisy_repeat(rng, [motif], max_units=rng.choice([3, 12, 40]))
+        elif r < 0.85:   # unrelated sequence: the skip block carries it
+            allele = rnd(rng, rng.randint(1, 60))
+        else:            # repeat - interruption - repeat
+            unit = oracle.replace_invalid_bases(motif, b"ATCG") if b"N" in motif else motif
+            allele = unit * rng.randint(1, 9) + rnd(rng, rng.randint(1, 9)) + unit * rng.randint(1, 9)
+        if rng.random() < 0.1:
+            allele = allele[:3] + b"N" + allele[3:] + b"X"
+        if it % 300 == 299:
+            allele = (allele or b"A") * 40  # a few long ones
+        if not allele:
+            continue
+        seen.add(n)
+        h = oracle.Hmm([oracle.replace_invalid_bases(motif, b"ATCGN")])
+        exp_mc, exp_sp, exp_pur = h.annotate(allele)
+        exp_path = h.label(oracle.replace_invalid_bases(allele, b"ATCG"))
+        moff = (C.c_uint64 * 2)(0, n)
+        mc = (C.c_uint32 * 2)()
+        cap = len(allele) + 2
+        spans = (_Span * cap)()
+        pur, plen, S = C.c_double(), C.c_uint64(), C.c_int()
+        pcap = (len(allele) + 2) * 8 + 64
+        path = (C.c_uint32 * pcap)()
+        got = emul.emu_hmm_annotate_lanes(motif, moff, 1, allele, len(allele), mc, spans, cap, C.byref(pur),
+                                          path, C.c_uint64(pcap), C.byref(plen), C.byref(S), -2)
+        assert got >= 0, got
+        assert list(path[:plen.value]) == exp_path
+        assert list(mc[:1]) == exp_mc
+        assert [(spans[i].m, spans[i].s, spans[i].e) for i in range(got)] == exp_sp
+        assert pur.value == exp_pur or (math.isnan(pur.value) and math.isnan(exp_pur))
+    assert seen == set(range(1, 9))
+
+
 @pytest.mark.parametrize("lanes", [0, 4, 32])
 def test_consensus_core(emul, oracle, lanes):
     """consensus_core.h (column vote + majority insertion) against the oracle's repair_consensus."""

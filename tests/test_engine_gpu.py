@@ -100,6 +100,58 @@ def test_hmm_long_allele_and_waves(engine, oracle):
     _check_annotations(oracle, loci, got)
 
 
+def test_hmm_lane_path_single_motif_loci(engine, oracle):
+    """Single-motif loci (motif of 1..8 bases) run through k_hmm_lane_* (score column in registers, one packed
+    back-pointer word per column, slots sorted by motif and allele length): MC / MS / AP and the state paths
+    must be the oracle's, with the lane path on and off, in one wave and in several, mixed with loci the
+    generic kernels take (several motifs, 12-base motifs, empty alleles)."""
+    from trgt_b200 import PackedSeqs
+    rng = random.Random(2026)
+    loci = []
+    for it in range(900):
+        if rng.random() < 0.85:
+            motifs = [rnd(rng, rng.choice([1, 2, 2, 2, 3, 4, 4, 5, 6, 7, 8]), "ACGTN" if rng.random() < 0.1 else "ACGT")]
+        else:
+            motifs = [rnd(rng, rng.choice([2, 3, 12])) for _ in range(rng.choice([1, 2, 3]))]
+        alleles = []
+        for _ in range(rng.randint(1, 3)):
+            a = noisy_repeat(rng, motifs, rng.choice([4, 12, 40]))
+            if rng.random() < 0.1:
+                a = a[:3] + b"N" + a[3:] + b"X"
+            if rng.random() < 0.03:
+                a = b""
+            if it % 150 == 0:
+                a = (a or b"AC") * 60   # long alleles: the last length bin, sorted by length
+            alleles.append(a)
+        loci.append((motifs, alleles))
+    motifs = PackedSeqs.from_list([m for ms, _ in loci for m in ms])
+    lmo = np.cumsum([0] + [len(ms) for ms, _ in loci]).astype(np.uint32)
+    alleles = PackedSeqs.from_list([a for _, als in loci for a in als])
+    al = np.array([i for i, (_, als) in enumerate(loci) for _ in als], dtype=np.uint32)
+    results = {}
+    try:
+        for lane in (True, False):
+            engine.set_hmm_lane_path(lane)
+            engine.reset_stats()
+            got = engine.label_with_hmm(loci)
+            stats = engine.kernel_stats()
+            assert ("k_hmm_lane_viterbi" in stats) == lane and "k_hmm_viterbi_thread" in stats and "k_hmm_viterbi" in stats
+            res = engine.hmm_label_packed(motifs, lmo, alleles, al, want_paths=True)
+            paths = [res.path(i) for i in range(len(alleles))]
+            _check_annotations(oracle, loci, got, paths)
+            results[lane] = res
+        engine.set_hmm_lane_path(True)
+        engine.set_workspace_budget(1 << 20)
+        small = [l for l in loci if sum(len(a) for a in l[1]) < 400][:600] + [([b"AT"], [b"AT" * 90000, b"AT" * 7])]
+        _check_annotations(oracle, small, engine.label_with_hmm(small))
+    finally:
+        engine.set_hmm_lane_path(True)
+        engine.set_workspace_budget(24 << 30)
+    a, b = results[True], results[False]
+    assert np.array_equal(a.motif_counts, b.motif_counts) and np.array_equal(a.spans, b.spans)
+    assert np.array_equal(a.purity, b.purity, equal_nan=True) and np.array_equal(a.paths, b.paths)
+
+
 # ------------------------------------------------------------------ phase A: flanks --------
 
 def _check_flanks(oracle, w, spans, hits, scoring, frac):
@@ -294,7 +346,7 @@ def test_kernels_actually_launched(engine):
     engine.reset_stats()
     engine.label_with_hmm([([b"CAG"], [b"CAGCAGCAG"])])
     stats = engine.kernel_stats()
-    assert stats["k_hmm_viterbi_thread"][0] >= 1 and engine.launches() >= 2
+    assert stats["k_hmm_lane_viterbi"][0] >= 1 and stats["k_hmm_lane_walk"][0] >= 1 and engine.launches() >= 2
 
 
 # ------------------------------------------------------------------ whole pass, other BASELINE configs ---

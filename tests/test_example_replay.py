@@ -68,7 +68,7 @@ def test_example_replay_engine():
         for a, b in zip(res.annotations, ref.annotations):
             assert list(a[0]) == list(b[0]) and (a[1] or None) == (b[1] or None) and a[2] == b[2]
         stats = eng.kernel_stats()
-        for k in ("k_clip_cigar", "k_unpack_seq4", "k_flank_exact_t", "k_hmm_viterbi_thread", "k_vcf_fields_write"):
+        for k in ("k_clip_cigar", "k_unpack_seq4", "k_flank_exact_t", "k_hmm_lane_viterbi", "k_vcf_fields_write"):
             assert k in stats, (k, sorted(stats))
     finally:
         eng.close()

@@ -10,6 +10,7 @@
 
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -85,6 +86,7 @@ struct trgt_engine {
   DevBuf d_ed[6];
   size_t workspace_budget = (size_t)24 << 30;  // cap on back-pointer / trace workspace per wave
   int band_budget = 16;  // cost cap of the banded flank fallback (0: always use the full-width path)
+  bool hmm_lane = true;  // single-motif loci take the register / packed-word HMM kernels (k_hmm_lane_*)
 };
 
 namespace {
@@ -1485,8 +1487,17 @@ struct trgt_hmm_batch {
   size_t warp_bytes = 0;
   DevBuf motifs, motif_off, locus_motif_off, alleles, allele_off, allele_locus, bp_off, mc_off;
   DevBuf bp, mc, purity, n_spans, span_off, spans, path_len, path_off, paths, status;
-  std::vector<unsigned long long> h_bp_off, h_mc_off, h_al_off;
+  std::vector<unsigned long long> h_bp_off, h_mc_off, h_scr_off;
   DevBuf span_scratch;
+  // the alleles the generic kernels take (those the lane kernels do not): h_bp_off / h_scr_off index this list
+  std::vector<uint32_t> h_list;
+  DevBuf list, scr_off;
+  // single-motif loci: slots sorted by (motif length, allele length), 32 slots = one group = one warp
+  std::vector<uint32_t> h_slots;
+  std::vector<unsigned long long> h_group_off;   // [n_groups+1] words
+  std::vector<uint8_t> h_group_n;                // motif length of each group
+  std::vector<std::pair<uint32_t, uint32_t>> lane_waves;  // group ranges whose packed words fit the budget
+  DevBuf slots, group_off, group_n, lane_bp, lane_scratch;
   std::vector<uint32_t> h_locus_allele_off;  // [n_loci+1] when the alleles are grouped by locus, else empty
   DevBuf locus_allele_off, vcf_len, vcf_off, vcf_data;
   PinBuf r_vcf_off, r_vcf_data;
@@ -1509,7 +1520,8 @@ void trgt_hmm_free(trgt_engine_t *e, trgt_hmm_batch_t *b) {
   DevBuf *all[] = {&b->motifs, &b->motif_off, &b->locus_motif_off, &b->alleles, &b->allele_off, &b->allele_locus,
                    &b->bp_off, &b->mc_off, &b->bp, &b->mc, &b->purity, &b->n_spans, &b->span_off, &b->spans,
                    &b->path_len, &b->path_off, &b->paths, &b->status, &b->locus_allele_off, &b->vcf_len, &b->vcf_off,
-                   &b->vcf_data, &b->span_scratch};
+                   &b->vcf_data, &b->span_scratch, &b->list, &b->scr_off, &b->slots, &b->group_off, &b->group_n, &b->lane_bp,
+                   &b->lane_scratch};
   for (auto *d : all) dev_free(*d);
   PinBuf *pins[] = {&b->r_mc, &b->r_span_off, &b->r_spans, &b->r_purity, &b->r_status, &b->r_path_off, &b->r_paths,
                     &b->r_vcf_off, &b->r_vcf_data};
@@ -1549,16 +1561,75 @@ static int hmm_upload_into(trgt_engine_t *e, trgt_hmm_batch *b, const trgt_seqs_
     if ((int)mb > mb_max) mb_max = (int)mb;
   }
   const size_t n = alleles->n;
-  b->h_bp_off.assign(n + 1, 0);
   b->h_mc_off.assign(n + 1, 0);
-  b->h_al_off.assign(alleles->offsets, alleles->offsets + n + 1);
+  // Two classes of alleles.  Single-motif loci with a motif of 1..HMM_LANE_NMAX bases (every locus of a genome-wide
+  // catalog) take the lane kernels: counting sort by (motif length, allele length) into slots, 32 slots = one warp.
+  // Everything else (several motifs, long motifs, empty alleles) is listed for the generic kernels.
+  const uint32_t LB = 1024;  // alleles of LB-1 bases and more share the last bin of their motif length (sorted below)
+  std::vector<uint32_t> bin_of(n, 0xFFFFFFFFu);
+  std::vector<uint32_t> bin_cnt((size_t)(HMM_LANE_NMAX + 1) * LB + 1, 0);
+  b->h_list.clear();
   for (size_t a = 0; a < n; a++) {
     const uint32_t l = allele_locus[a];
     if (l >= n_loci) return fail(e, TRGT_ERR_ARG, "allele %zu: locus %u out of range", a, l);
     const uint64_t L = alleles->offsets[a + 1] - alleles->offsets[a];
     if (L > 0x3ffffff0ull) return fail(e, TRGT_ERR_ARG, "allele too long");
-    b->h_bp_off[a + 1] = b->h_bp_off[a] + (L ? (L + 2) * (unsigned long long)locus_S[l] : 0);
-    b->h_mc_off[a + 1] = b->h_mc_off[a] + (locus_motif_offsets[l + 1] - locus_motif_offsets[l]);
+    const uint32_t nm = locus_motif_offsets[l + 1] - locus_motif_offsets[l];
+    b->h_mc_off[a + 1] = b->h_mc_off[a] + nm;
+    const uint64_t n1 = nm == 1 ? motifs->offsets[locus_motif_offsets[l] + 1] - motifs->offsets[locus_motif_offsets[l]] : 0;
+    if (e->hmm_lane && n1 >= 1 && n1 <= HMM_LANE_NMAX && L > 0 && L < (1ull << 26)) {  // (32-bit event counters)
+      bin_of[a] = (uint32_t)n1 * LB + (uint32_t)(L < LB - 1 ? L : LB - 1);
+      bin_cnt[bin_of[a] + 1]++;
+    } else {
+      b->h_list.push_back((uint32_t)a);
+    }
+  }
+  const size_t n_gen = b->h_list.size(), n_lane = n - n_gen;
+  b->h_slots.clear();
+  b->h_group_off.assign(1, 0);
+  b->h_group_n.clear();
+  if (n_lane) {
+    for (size_t k = 1; k < bin_cnt.size(); k++) bin_cnt[k] += bin_cnt[k - 1];  // bin_cnt[k] = first position of bin k
+    std::vector<uint32_t> sorted(n_lane);
+    {
+      std::vector<uint32_t> pos(bin_cnt.begin(), bin_cnt.end() - 1);
+      for (size_t a = 0; a < n; a++)
+        if (bin_of[a] != 0xFFFFFFFFu) sorted[pos[bin_of[a]]++] = (uint32_t)a;
+    }
+    auto len_of = [&](uint32_t a) { return alleles->offsets[a + 1] - alleles->offsets[a]; };
+    struct Group { uint64_t lmax; uint32_t first, count, n1; };
+    std::vector<Group> groups;
+    for (uint32_t n1 = 1; n1 <= HMM_LANE_NMAX; n1++) {
+      const size_t s0 = bin_cnt[(size_t)n1 * LB], s1 = bin_cnt[(size_t)(n1 + 1) * LB];
+      const size_t t0 = bin_cnt[(size_t)n1 * LB + LB - 1];  // the long ones of this motif length, by length
+      std::sort(sorted.begin() + t0, sorted.begin() + s1, [&](uint32_t x, uint32_t y) {
+        const uint64_t lx = len_of(x), ly = len_of(y);
+        return lx != ly ? lx < ly : x < y;
+      });
+      for (size_t k = s0; k < s1; k += 32) {  // one group: its columns are as many as its longest allele has bases
+        const uint32_t cnt = (uint32_t)(s1 - k < 32 ? s1 - k : 32);
+        uint64_t lmax = 0;
+        for (uint32_t j = 0; j < cnt; j++) lmax = len_of(sorted[k + j]) > lmax ? len_of(sorted[k + j]) : lmax;
+        groups.push_back(Group{lmax, (uint32_t)k, cnt, n1});
+      }
+    }
+    // longest first: a lane walks its columns one after the other, so the long alleles should start first
+    std::stable_sort(groups.begin(), groups.end(), [](const Group &x, const Group &y) { return x.lmax > y.lmax; });
+    b->h_slots.reserve(groups.size() * 32);
+    for (const Group &g : groups) {
+      for (uint32_t j = 0; j < 32; j++) b->h_slots.push_back(j < g.count ? sorted[g.first + j] : 0xFFFFFFFFu);
+      b->h_group_off.push_back(b->h_group_off.back() + 32ull * g.lmax);
+      b->h_group_n.push_back((uint8_t)g.n1);
+    }
+  }
+  // back-pointer bytes and span scratch slots of the generic alleles, indexed by their position in the list
+  b->h_bp_off.assign(n_gen + 1, 0);
+  b->h_scr_off.assign(n_gen + 1, 0);
+  for (size_t i = 0; i < n_gen; i++) {
+    const uint32_t a = b->h_list[i];
+    const uint64_t L = alleles->offsets[a + 1] - alleles->offsets[a];
+    b->h_bp_off[i + 1] = b->h_bp_off[i] + (L ? (L + 2) * (unsigned long long)locus_S[allele_locus[a]] : 0);
+    b->h_scr_off[i + 1] = b->h_scr_off[i] + L;
   }
   {  // allele range of every locus, if the alleles come grouped by locus (trgt_vcf_fields needs that)
     bool sorted = true;
@@ -1579,20 +1650,30 @@ static int hmm_upload_into(trgt_engine_t *e, trgt_hmm_batch *b, const trgt_seqs_
   b->warp_bytes = hmm_onchip_bytes(S_max, nb_max, mb_max);
   b->ran = false;
   if (b->warp_bytes * 4 > (size_t)e->smem_optin) return fail(e, TRGT_ERR_ARG, "HMM with %d states does not fit in shared memory", S_max);
-  // waves: consecutive alleles whose back-pointers fit the workspace budget
+  // waves: consecutive listed alleles / groups whose back-pointers fit the workspace budget (state paths are
+  // written by a second walk after all offsets are known, which needs every back-pointer: one wave then)
   b->waves.clear();
+  b->lane_waves.clear();
   {
     size_t a0 = 0;
-    while (a0 < n) {
+    while (a0 < n_gen) {
       size_t a1 = a0 + 1;
-      while (a1 < n && b->h_bp_off[a1 + 1] - b->h_bp_off[a0] <= e->workspace_budget) a1++;
+      while (a1 < n_gen && (want_paths || b->h_bp_off[a1 + 1] - b->h_bp_off[a0] <= e->workspace_budget)) a1++;
       b->waves.push_back({(uint32_t)a0, (uint32_t)a1});
       a0 = a1;
+    }
+    const size_t n_groups = b->h_group_off.size() - 1;
+    size_t g0 = 0;
+    while (g0 < n_groups) {
+      size_t g1 = g0 + 1;
+      while (g1 < n_groups && (want_paths || (b->h_group_off[g1 + 1] - b->h_group_off[g0]) * sizeof(uint32_t) <= e->workspace_budget)) g1++;
+      b->lane_waves.push_back({(uint32_t)g0, (uint32_t)g1});
+      g0 = g1;
     }
   }
   CU(e, cudaSetDevice(e->device));
   // jump-in ln table
-  e->jump.ensure((int)len_max);
+  e->jump.ensure((int)(len_max > HMM_LANE_NMAX ? len_max : HMM_LANE_NMAX));
   if (e->jump_uploaded_len != e->jump.lp.size() || !e->d_mm_lp.p) {
     TRY(h2d(e, e->d_mm_off, e->jump.off.data(), e->jump.off.size() * sizeof(uint32_t)));
     TRY(h2d(e, e->d_mm_lp, e->jump.lp.data(), e->jump.lp.size() * sizeof(double)));
@@ -1604,7 +1685,16 @@ static int hmm_upload_into(trgt_engine_t *e, trgt_hmm_batch *b, const trgt_seqs_
   static const uint32_t zero32[1] = {0};
   TRY(h2d(e, b->locus_motif_off, n_loci ? locus_motif_offsets : zero32, ((size_t)n_loci + 1) * sizeof(uint32_t)));
   TRY(h2d(e, b->allele_locus, allele_locus, n * sizeof(uint32_t)));
-  TRY(h2d(e, b->bp_off, b->h_bp_off.data(), (n + 1) * sizeof(unsigned long long)));
+  if (n_gen) {
+    TRY(h2d(e, b->bp_off, b->h_bp_off.data(), (n_gen + 1) * sizeof(unsigned long long)));
+    TRY(h2d(e, b->scr_off, b->h_scr_off.data(), (n_gen + 1) * sizeof(unsigned long long)));
+    if (n_gen != n) TRY(h2d(e, b->list, b->h_list.data(), n_gen * sizeof(uint32_t)));  // (all of them: identity)
+  }
+  if (n_lane) {
+    TRY(h2d(e, b->slots, b->h_slots.data(), b->h_slots.size() * sizeof(uint32_t)));
+    TRY(h2d(e, b->group_off, b->h_group_off.data(), b->h_group_off.size() * sizeof(unsigned long long)));
+    TRY(h2d(e, b->group_n, b->h_group_n.data(), b->h_group_n.size()));
+  }
   TRY(h2d(e, b->mc_off, b->h_mc_off.data(), (n + 1) * sizeof(unsigned long long)));
   CU(e, cudaStreamSynchronize(e->stream));  // h_* vectors may be reallocated by the next upload
   TRY(dev_reserve(e, b->mc, (size_t)(b->h_mc_off[n] + 1) * sizeof(uint32_t)));
@@ -1616,12 +1706,20 @@ static int hmm_upload_into(trgt_engine_t *e, trgt_hmm_batch *b, const trgt_seqs_
     TRY(dev_reserve(e, b->path_len, (n + 2) * sizeof(unsigned long long)));
     TRY(dev_reserve(e, b->path_off, (n + 2) * sizeof(unsigned long long)));
   }
-  size_t bp_need = 0;
+  size_t bp_need = 0, lane_need = 0;
   for (auto &w : b->waves) {
     const size_t bytes = (size_t)(b->h_bp_off[w.second] - b->h_bp_off[w.first]);
     if (bytes > bp_need) bp_need = bytes;
   }
+  for (auto &w : b->lane_waves) {
+    const size_t bytes = (size_t)(b->h_group_off[w.second] - b->h_group_off[w.first]) * sizeof(uint32_t);
+    if (bytes > lane_need) lane_need = bytes;
+  }
   TRY(dev_reserve(e, b->bp, bp_need + 16));
+  TRY(dev_reserve(e, b->lane_bp, lane_need + 16));
+  // span scratch of the whole batch: one slot per base (generic alleles) / per packed word (lane groups)
+  if (!want_paths) TRY(dev_reserve(e, b->span_scratch, (size_t)(b->h_scr_off[n_gen] + 1) * sizeof(trgt_motif_span_t)));
+  TRY(dev_reserve(e, b->lane_scratch, (size_t)(b->h_group_off.back() + 1) * sizeof(trgt_motif_span_t)));
   return 0;
 }
 
@@ -1665,6 +1763,8 @@ static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
   b->total_spans = 0;
   b->total_path = 0;
   if (b->n_alleles == 0) return 0;
+  const uint32_t n = b->n_alleles, n_gen = (uint32_t)b->h_list.size();
+  const uint32_t n_groups = (uint32_t)(b->h_group_off.size() - 1);
   HmmBatch hb;
   hb.motifs = (const uint8_t *)b->motifs.p;
   hb.motif_off = (const uint64_t *)b->motif_off.p;
@@ -1672,7 +1772,9 @@ static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
   hb.alleles = (const uint8_t *)b->alleles.p;
   hb.allele_off = (const uint64_t *)b->allele_off.p;
   hb.allele_locus = (const uint32_t *)b->allele_locus.p;
+  hb.list = n_gen != n ? (const uint32_t *)b->list.p : nullptr;
   hb.bp_off = (const unsigned long long *)b->bp_off.p;
+  hb.scr_off = (const unsigned long long *)b->scr_off.p;
   hb.mc_off = (const unsigned long long *)b->mc_off.p;
   hb.mm_off = (const uint32_t *)e->d_mm_off.p;
   hb.mm_lp = (const double *)e->d_mm_lp.p;
@@ -1681,11 +1783,23 @@ static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
   hb.nb_max = b->nb_max;
   hb.mbytes_max = b->mbytes_max;
   hb.warp_bytes = b->warp_bytes;
+  HmmLaneBatch lb;
+  lb.motifs = hb.motifs; lb.motif_off = hb.motif_off; lb.locus_motif_off = hb.locus_motif_off;
+  lb.alleles = hb.alleles; lb.allele_off = hb.allele_off; lb.allele_locus = hb.allele_locus;
+  lb.mc_off = hb.mc_off;
+  lb.slots = (const uint32_t *)b->slots.p;
+  lb.group_off = (const unsigned long long *)b->group_off.p;
+  lb.group_n = (const uint8_t *)b->group_n.p;
+  lb.c = e->hmm_consts;
+  for (int n1 = 0; n1 <= HMM_LANE_NMAX; n1++)
+    for (int i = 0; i < HMM_LANE_NMAX; i++)
+      lb.jump[n1][i] = (n1 >= 1 && i < n1) ? e->jump.lp[e->jump.off[n1] + i] : 0.0;
+  unsigned long long *path_len = b->want_paths ? (unsigned long long *)b->path_len.p : nullptr;
+  // ---- generic alleles: Viterbi (a lane or a warp per allele) and the counting walk, wave by wave ----
   const int block = 128, wpb = 4;
   const size_t smem = b->warp_bytes * wpb;
   int grid_v = 0;
-  TRY(persistent_grid(e, k_hmm_viterbi, block, smem, &grid_v));
-  unsigned long long span_base = 0, path_base = 0;
+  if (n_gen) TRY(persistent_grid(e, k_hmm_viterbi, block, smem, &grid_v));
   for (auto &w : b->waves) {
     const uint32_t a0 = w.first, a1 = w.second, cnt = a1 - a0;
     const uint32_t need = (cnt + wpb - 1) / wpb;
@@ -1710,63 +1824,85 @@ static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
     }
     // without state paths the walk leaves the spans in scratch slots and a copy kernel places them;
     // with state paths a second walk (k_hmm_emit) writes spans and paths at their offsets
-    const bool one_walk = !b->want_paths;
-    if (one_walk)
-      TRY(dev_reserve(e, b->span_scratch, (size_t)(b->h_al_off[a1] - b->h_al_off[a0] + 1) * sizeof(trgt_motif_span_t)));
     {
       LaunchScope ls(e, "k_hmm_walk");
       k_hmm_walk<<<tgrid, 128, 0, e->stream>>>(hb, a0, a1, bp_base, (const uint8_t *)b->bp.p, (uint32_t *)b->mc.p,
-                                               (double *)b->purity.p, (uint32_t *)b->n_spans.p,
-                                               b->want_paths ? (unsigned long long *)b->path_len.p : nullptr,
+                                               (double *)b->purity.p, (uint32_t *)b->n_spans.p, path_len,
                                                (int32_t *)b->status.p,
-                                               one_walk ? (trgt_motif_span_t *)b->span_scratch.p : nullptr);
+                                               b->want_paths ? nullptr : (trgt_motif_span_t *)b->span_scratch.p);
       TRY(check_launch(e, "k_hmm_walk"));
     }
-    // span offsets of this wave: base + exclusive scan (n_spans[a1] is scratch and zeroed first)
-    CU(e, cudaMemsetAsync((uint32_t *)b->n_spans.p + a1, 0, sizeof(uint32_t), e->stream));
-    TRY(exclusive_scan_u32(e, (const uint32_t *)b->n_spans.p + a0, (unsigned long long *)b->span_off.p + a0, (size_t)cnt + 1));
-    if (span_base) {
-      LaunchScope ls(e, "k_add_base_u64");
-      k_add_base_u64<<<(cnt + 256) / 256, 256, 0, e->stream>>>((unsigned long long *)b->span_off.p, a0, a1, span_base);
-      TRY(check_launch(e, "k_add_base_u64"));
-    }
-    CU(e, cudaMemcpyAsync(&e->h_u64[0], (unsigned long long *)b->span_off.p + a1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
-    if (b->want_paths) {
-      LaunchScope ls(e, "k_scan_u64_serial");
-      k_scan_u64_serial<<<1, 32, 0, e->stream>>>((const unsigned long long *)b->path_len.p, (unsigned long long *)b->path_off.p, a0, a1, path_base);
-      TRY(check_launch(e, "k_scan_u64_serial"));
-      CU(e, cudaMemcpyAsync(&e->h_u64[1], (unsigned long long *)b->path_off.p + a1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
-    }
-    CU(e, cudaStreamSynchronize(e->stream));
-    const unsigned long long span_end = e->h_u64[0];
-    const unsigned long long path_end = b->want_paths ? e->h_u64[1] : 0;
-    TRY(dev_reserve(e, b->spans, (size_t)(span_end + 1) * sizeof(trgt_motif_span_t), true));
-    if (b->want_paths) TRY(dev_reserve(e, b->paths, (size_t)(path_end + 1) * sizeof(uint32_t), true));
-    if (one_walk) {
-      if (span_end > span_base) {
-        LaunchScope ls(e, "k_hmm_spans");
-        k_hmm_spans<<<tgrid, 128, 0, e->stream>>>(hb, a0, a1, (const trgt_motif_span_t *)b->span_scratch.p,
-                                                  (const uint32_t *)b->n_spans.p,
-                                                  (const unsigned long long *)b->span_off.p,
-                                                  (trgt_motif_span_t *)b->spans.p);
-        TRY(check_launch(e, "k_hmm_spans"));
-      }
-    } else if (span_end > span_base || path_end > path_base) {
-      LaunchScope ls(e, "k_hmm_emit");
-      k_hmm_emit<<<tgrid, 128, 0, e->stream>>>(hb, a0, a1, bp_base, (const uint8_t *)b->bp.p,
-                                                   (const uint32_t *)b->n_spans.p,
-                                                   (const unsigned long long *)b->span_off.p,
-                                                   (trgt_motif_span_t *)b->spans.p,
-                                                   b->want_paths ? (const unsigned long long *)b->path_off.p : nullptr,
-                                                   b->want_paths ? (uint32_t *)b->paths.p : nullptr,
-                                                   (const int32_t *)b->status.p);
-      TRY(check_launch(e, "k_hmm_emit"));
-    }
-    span_base = span_end;
-    path_base = path_end;
   }
-  b->total_spans = span_base;
-  b->total_path = path_base;
+  // ---- single-motif loci: lane kernels per motif length, wave by wave ----
+  for (auto &w : b->lane_waves) {
+    const unsigned long long word_base = b->h_group_off[w.first];
+    const uint32_t lgrid = (w.second - w.first + 3) / 4;
+    {
+      LaunchScope ls(e, "k_hmm_lane_viterbi");
+      k_hmm_lane_viterbi<<<lgrid, 128, 0, e->stream>>>(lb, w.first, w.second, word_base, (uint32_t *)b->lane_bp.p,
+                                                       (int32_t *)b->status.p);
+      TRY(check_launch(e, "k_hmm_lane_viterbi"));
+    }
+    {
+      LaunchScope ls(e, "k_hmm_lane_walk");
+      k_hmm_lane_walk<<<lgrid, 128, 0, e->stream>>>(lb, w.first, w.second, word_base, (const uint32_t *)b->lane_bp.p,
+                                                    (uint32_t *)b->mc.p, (double *)b->purity.p, (uint32_t *)b->n_spans.p,
+                                                    path_len, (int32_t *)b->status.p,
+                                                    (trgt_motif_span_t *)b->lane_scratch.p);
+      TRY(check_launch(e, "k_hmm_lane_walk"));
+    }
+  }
+  // ---- span (and path) offsets of the whole batch ----
+  CU(e, cudaMemsetAsync((uint32_t *)b->n_spans.p + n, 0, sizeof(uint32_t), e->stream));
+  TRY(exclusive_scan_u32(e, (const uint32_t *)b->n_spans.p, (unsigned long long *)b->span_off.p, (size_t)n + 1));
+  CU(e, cudaMemcpyAsync(&e->h_u64[0], (unsigned long long *)b->span_off.p + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  if (b->want_paths) {
+    LaunchScope ls(e, "k_scan_u64_serial");
+    k_scan_u64_serial<<<1, 32, 0, e->stream>>>((const unsigned long long *)b->path_len.p, (unsigned long long *)b->path_off.p, 0, n, 0);
+    TRY(check_launch(e, "k_scan_u64_serial"));
+    CU(e, cudaMemcpyAsync(&e->h_u64[1], (unsigned long long *)b->path_off.p + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  }
+  CU(e, cudaStreamSynchronize(e->stream));
+  const unsigned long long span_end = e->h_u64[0];
+  const unsigned long long path_end = b->want_paths ? e->h_u64[1] : 0;
+  TRY(dev_reserve(e, b->spans, (size_t)(span_end + 1) * sizeof(trgt_motif_span_t)));
+  if (b->want_paths) TRY(dev_reserve(e, b->paths, (size_t)(path_end + 1) * sizeof(uint32_t)));
+  // ---- spans to their CSR offsets; state paths by a second walk ----
+  if (n_gen && !b->want_paths && span_end) {
+    LaunchScope ls(e, "k_hmm_spans");
+    k_hmm_spans<<<(n_gen + 127) / 128, 128, 0, e->stream>>>(hb, 0, n_gen, (const trgt_motif_span_t *)b->span_scratch.p,
+                                                            (const uint32_t *)b->n_spans.p,
+                                                            (const unsigned long long *)b->span_off.p,
+                                                            (trgt_motif_span_t *)b->spans.p);
+    TRY(check_launch(e, "k_hmm_spans"));
+  }
+  if (n_gen && b->want_paths && (span_end || path_end)) {  // (one wave: every back-pointer is still in place)
+    LaunchScope ls(e, "k_hmm_emit");
+    k_hmm_emit<<<(n_gen + 127) / 128, 128, 0, e->stream>>>(hb, 0, n_gen, 0, (const uint8_t *)b->bp.p,
+                                                           (const uint32_t *)b->n_spans.p,
+                                                           (const unsigned long long *)b->span_off.p,
+                                                           (trgt_motif_span_t *)b->spans.p,
+                                                           (const unsigned long long *)b->path_off.p,
+                                                           (uint32_t *)b->paths.p, (const int32_t *)b->status.p);
+    TRY(check_launch(e, "k_hmm_emit"));
+  }
+  if (n_groups && span_end) {
+    LaunchScope ls(e, "k_hmm_lane_spans");
+    k_hmm_lane_spans<<<(n_groups + 3) / 4, 128, 0, e->stream>>>(lb, 0, n_groups, (const trgt_motif_span_t *)b->lane_scratch.p,
+                                                                (const uint32_t *)b->n_spans.p,
+                                                                (const unsigned long long *)b->span_off.p,
+                                                                (trgt_motif_span_t *)b->spans.p);
+    TRY(check_launch(e, "k_hmm_lane_spans"));
+  }
+  if (n_groups && b->want_paths && path_end) {
+    LaunchScope ls(e, "k_hmm_lane_emit");
+    k_hmm_lane_emit<<<(n_groups + 3) / 4, 128, 0, e->stream>>>(lb, 0, n_groups, 0ull, (const uint32_t *)b->lane_bp.p,
+                                                               (const unsigned long long *)b->path_off.p,
+                                                               (uint32_t *)b->paths.p, (const int32_t *)b->status.p);
+    TRY(check_launch(e, "k_hmm_lane_emit"));
+  }
+  b->total_spans = span_end;
+  b->total_path = path_end;
   return 0;
 }
 
@@ -1891,6 +2027,10 @@ int32_t trgt_hmm_label(trgt_engine_t *e, const trgt_seqs_t *motifs, const uint32
 
 void trgt_engine_set_workspace_budget(trgt_engine_t *e, size_t bytes) {
   if (e && bytes >= ((size_t)1 << 20)) e->workspace_budget = bytes;
+}
+
+void trgt_engine_set_hmm_lane_path(trgt_engine_t *e, int32_t on) {
+  if (e) e->hmm_lane = on != 0;
 }
 
 void trgt_engine_set_flank_band_budget(trgt_engine_t *e, int32_t max_cost) {

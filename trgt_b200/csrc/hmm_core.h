@@ -741,11 +741,48 @@ struct HmmAnnot {
 // path_out (optional): receives the state path (Hmm::label).  With path_total == 0 it is written
 // in REVERSE order, up to path_cap entries; with path_total = the length found by a previous walk
 // it is written in forward order.  *path_len gets the full length.
+// how the walk reads a back-pointer: S bytes per column (hmm_viterbi, hmm_viterbi_thread) ...
+struct HmmBpBytes {
+  const uint8_t *bp;
+  int S;
+  TRGT_HD int get(int col, int st, const HmmRole &) const { return bp[(size_t)col * (size_t)S + (size_t)st]; }
+};
+
+// where the walk leaves collapsed span `idx`: a plain array ...
+struct HmmSpanArray {
+  HmmSpan *p;
+  TRGT_HD bool on() const { return p != nullptr; }
+  TRGT_HD void put(uint32_t idx, const HmmSpan &s) const { p[idx] = s; }
+};
+// ... or slots `stride` apart (the lanes of a warp share a block of scratch, slot j of lane l at j * 32 + l)
+struct HmmSpanStrided {
+  HmmSpan *p;
+  uint32_t stride;
+  TRGT_HD bool on() const { return p != nullptr; }
+  TRGT_HD void put(uint32_t idx, const HmmSpan &s) const { p[(size_t)idx * stride] = s; }
+};
+
+template <class M, class BP, class SP>
+TRGT_HD HmmAnnot hmm_annotate_bp(const M &m, const uint8_t *allele, int L, BP &bpr,
+                                 int max_motif_len, uint32_t *mc, const SP &spans_out, uint32_t n_total,
+                                 uint32_t *path_out, uint64_t path_cap, uint64_t path_total,
+                                 uint64_t *path_len);
+
 template <class M>
 TRGT_HD HmmAnnot hmm_annotate(const M &m, const uint8_t *allele, int L, const uint8_t *bp,
                               int max_motif_len, uint32_t *mc, HmmSpan *spans_out, uint32_t n_total,
                               uint32_t *path_out, uint64_t path_cap, uint64_t path_total,
                               uint64_t *path_len) {
+  HmmBpBytes bpr{bp, m.S};
+  return hmm_annotate_bp(m, allele, L, bpr, max_motif_len, mc, HmmSpanArray{spans_out}, n_total, path_out, path_cap,
+                         path_total, path_len);
+}
+
+template <class M, class BP, class SP>
+TRGT_HD HmmAnnot hmm_annotate_bp(const M &m, const uint8_t *allele, int L, BP &bpr,
+                                 int max_motif_len, uint32_t *mc, const SP &spans_out, uint32_t n_total,
+                                 uint32_t *path_out, uint64_t path_cap, uint64_t path_total,
+                                 uint64_t *path_len) {
   HmmAnnot out;
   out.purity = 0.0; out.n_spans = 0; out.status = 0;
   const int S = m.S;
@@ -789,9 +826,9 @@ TRGT_HD HmmAnnot hmm_annotate(const M &m, const uint8_t *allele, int L, const ui
               p_start = (uint32_t)copy_start;
             } else {
               if (have_p) {
-                if (spans_out && emitted < n_total) {
+                if (spans_out.on() && emitted < n_total) {
                   HmmSpan s; s.motif_index = p_motif; s.start = p_start; s.end = p_end;
-                  spans_out[n_total - 1 - emitted] = s;
+                  spans_out.put(n_total - 1 - emitted, s);
                 }
                 emitted++;
               }
@@ -814,7 +851,7 @@ TRGT_HD HmmAnnot hmm_annotate(const M &m, const uint8_t *allele, int L, const ui
       case HR_SKIP: emits = true; n_skip++; break;
       default: break;  // rs, re
     }
-    const int e = bp[(size_t)col * (size_t)S + (size_t)st];
+    const int e = bpr.get(col, st, r);
     if (e == TRGT_HMM_NONE) { out.status = -1; break; }
     const int p = hmm_pred(m, r, st, e);
     if (emits) col -= 1;
@@ -825,9 +862,9 @@ TRGT_HD HmmAnnot hmm_annotate(const M &m, const uint8_t *allele, int L, const ui
   plen++;
   if (path_len) *path_len = plen;
   if (have_p) {
-    if (spans_out && emitted < n_total) {
+    if (spans_out.on() && emitted < n_total) {
       HmmSpan s; s.motif_index = p_motif; s.start = p_start; s.end = p_end;
-      spans_out[n_total - 1 - emitted] = s;
+      spans_out.put(n_total - 1 - emitted, s);
     }
     emitted++;
   }
@@ -835,6 +872,333 @@ TRGT_HD HmmAnnot hmm_annotate(const M &m, const uint8_t *allele, int L, const ui
   // purity.rs:11-40
   const double edit = (double)(n_del + n_ins + n_mis + n_skip);
   const uint64_t ref_len = n_match + n_mis + n_del + n_skip;
+  const double max_dist = (double)(ref_len > (uint64_t)L ? ref_len : (uint64_t)L);
+  out.purity = (max_dist - edit) / max_dist;
+  return out;
+}
+
+// ---------------------------------------------------------------- single-motif loci, one lane per allele ---
+//
+// Every locus of a genome-wide catalog has ONE motif of 2..6 bases (S = 3n + 8 = 14..26).  For those
+// the recurrence is written out per motif length N (template), with the live score column -- ms, match[N],
+// ins[N], del[N-1], skip, re -- in the lane's REGISTERS and every loop unrolled, and the back-pointers of one
+// column packed into ONE 32-bit word per allele (4N bits) instead of S bytes:
+//   * a state with a single in-edge needs no bits (match_0, del_0, skip_me, end; start);
+//   * rs: in-edge 1 (re) in every column but column 0, where it is in-edge 0 (start);
+//   * ms and skip_ms always take in-edge 0 (rs): their other candidate me + ln(1/2) is one of the candidates
+//     re = rs was maximised over, so it can never be strictly greater (hmm_model.rs:84) -- this also makes
+//     ms = skip_ms = rs = re one carried value;
+//   * columns 0 and L+1 need no word at all: in column 0 only start, rs, ms, skip_ms are finite (in-edges 0),
+//     in column L+1 only `end` (one in-edge).
+// Adding ln(1.0) = +0.0 (lp_one, em_one, the emission of a silent state) leaves every score bit for bit as it
+// is -- no score is ever -0.0 -- so those additions are not issued; all other sums are the reference's
+// left-to-right `(prev + ln(trans)) + ln(emit)` (hmm_model.rs:79-88), candidates in the reference's in-edge
+// order with strict '>'.
+template <int N>
+struct HmmLaneBits {
+  static constexpr int I0 = 0;                               // ins_i: bit i
+  static constexpr int M0 = N;                               // match_i, i >= 1: two bits at M0 + 2 (i - 1)
+  static constexpr int D0 = 3 * N - 2;                       // del_i, i >= 1: bit D0 + (i - 1)
+  static constexpr int SKIP = D0 + (N >= 2 ? N - 2 : 0);
+  static constexpr int ME = SKIP + 1;                        // two bits
+  static constexpr int RE = ME + 2;
+  static constexpr int BITS = RE + 1;                        // 4 N for N >= 2
+};
+#define HMM_LANE_NMAX 8  // 4 N <= 32
+
+// first maximum, strict '>': `arg` of the reference's argmax whenever one candidate is finite
+#define TRGT_LANE_MAX2(a0, a1, best, arg)        \
+  do {                                           \
+    const bool g_ = (a1) > (a0);                 \
+    best = g_ ? (a1) : (a0);                     \
+    arg = g_ ? 1u : 0u;                          \
+  } while (0)
+
+// The table-free model of a single-motif locus, for the walk (same accessors as HmmModelScan)
+template <int N>
+struct HmmModelSingle {
+  static constexpr int S = 3 * N + 8;
+  static constexpr int nb = 2;
+  uint64_t bytes;  // sanitised motif bytes
+  TRGT_HD int block_n(int b) const { return b == 0 ? N : 0; }
+  TRGT_HD int block_ms(int b) const { return b == 0 ? 2 : 3 + 3 * N; }
+  TRGT_HD int block_of(int st) const { return st <= 2 + 3 * N ? 0 : 1; }
+  TRGT_HD uint8_t motif_byte(int, int i) const { return (uint8_t)(bytes >> (8 * i)); }
+};
+
+TRGT_HD uint64_t hmm_pack_motif(const uint8_t *motif, int n) {
+  uint64_t v = 0;
+  for (int i = 0; i < n; i++) v |= (uint64_t)hmm_clean_motif_base(motif[i], (uint32_t)i) << (8 * i);
+  return v;
+}
+
+// Viterbi of one allele by one lane.  jump[i] = ln(seed (N - i)), i in 1..N-1 (builder.rs:93-111).
+// bp: one word per column 1..L at bp[(col - 1) * stride] (stride = 32: the lanes of a warp write one line).
+template <int N>
+TRGT_HD void hmm_viterbi_lane(const HmmConsts &c, const double *jump, uint64_t mbytes, const uint8_t *allele, int L,
+                              uint32_t *bp, int stride) {
+  typedef HmmLaneBits<N> B;
+  const double NEG = -INFINITY;
+  double M[N], I[N], D[N > 1 ? N - 1 : 1];
+#pragma unroll
+  for (int i = 0; i < N; i++) { M[i] = NEG; I[i] = NEG; }
+#pragma unroll
+  for (int i = 0; i + 1 < N; i++) D[i] = NEG;
+  double skip = NEG;
+  double r = c.em_one;  // column 0: start = ln(1); rs, ms, skip_ms follow through ln(1) edges; re is -inf but never read
+  uint8_t base_next = L > 0 ? allele[0] : 0;  // loaded a column ahead
+  for (int col = 1; col <= L; col++) {
+    const uint8_t base = hmm_clean_base(base_next, (uint32_t)(col - 1));
+    if (col < L) base_next = allele[col];
+    uint32_t w = 0;
+    const double em_q = c.em_quarter;
+    double nM[N], nI[N];
+    // ---- emitting states, from the previous column ----
+#pragma unroll
+    for (int i = 0; i < N; i++) {  // ins_i: [ins_i, match_i]
+      const double a0 = (I[i] + c.lp_ins_loop) + em_q;
+      const double a1 = (M[i] + c.lp_indel_open) + em_q;
+      unsigned arg;
+      TRGT_LANE_MAX2(a0, a1, nI[i], arg);
+      w |= arg << (B::I0 + i);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {  // match_i: [match_{i-1}, ms, ins_{i-1}, del_{i-2}]
+      const uint8_t mb = (uint8_t)(mbytes >> (8 * i));
+      const double em = (mb == 'N') ? c.em_quarter : (mb == base ? c.em_hi : c.em_lo);
+      if (i == 0) {
+        nM[0] = (r + c.lp_match) + em;
+      } else {
+        const double a0 = (M[i - 1] + c.lp_match) + em;
+        const double a1 = (r + jump[i]) + em;
+        const double a2 = (I[i - 1] + c.lp_ins_exit) + em;
+        double best;
+        unsigned arg;
+        TRGT_LANE_MAX2(a0, a1, best, arg);
+        if (a2 > best) { best = a2; arg = 2u; }
+        if (i >= 2) {
+          const double a3 = (D[i >= 2 ? i - 2 : 0] + c.lp_half) + em;
+          if (a3 > best) { best = a3; arg = 3u; }
+        }
+        nM[i] = best;
+        w |= arg << (B::M0 + 2 * (i - 1));
+      }
+    }
+    {  // skip: [skip_ms, skip]
+      const double a0 = r + em_q;  // (skip_ms + ln 1) + em
+      const double a1 = (skip + c.lp_half) + em_q;
+      unsigned arg;
+      TRGT_LANE_MAX2(a0, a1, skip, arg);
+      w |= arg << B::SKIP;
+    }
+    // ---- silent states of this column ----
+#pragma unroll
+    for (int i = 0; i < N; i++) { M[i] = nM[i]; I[i] = nI[i]; }
+#pragma unroll
+    for (int i = 0; i + 1 < N; i++) {  // del_i: [match_i, del_{i-1}]
+      const double a0 = M[i] + c.lp_indel_open;
+      if (i == 0) {
+        D[0] = a0;
+      } else {
+        const double a1 = D[i - 1] + c.lp_half;
+        unsigned arg;
+        TRGT_LANE_MAX2(a0, a1, D[i], arg);
+        w |= arg << (B::D0 + (i - 1));
+      }
+    }
+    double me;
+    {  // me: [match_{N-1}, ins_{N-1}, del_{N-2}]
+      const double a0 = M[N - 1] + c.lp_match;
+      const double a1 = I[N - 1] + c.lp_ins_exit;
+      unsigned arg;
+      TRGT_LANE_MAX2(a0, a1, me, arg);
+      if (N > 1) {
+        const double a2 = D[N > 1 ? N - 2 : 0];  // + ln 1
+        if (a2 > me) { me = a2; arg = 2u; }
+      }
+      w |= arg << B::ME;
+    }
+    {  // re: [me, skip_me]; rs = re (its other in-edge, start, is -inf here); ms = skip_ms = rs
+      const double a0 = me + c.lp_half;
+      const double a1 = (skip + c.lp_half) + c.lp_half;  // skip_me = skip + ln(1/2)
+      unsigned arg;
+      TRGT_LANE_MAX2(a0, a1, r, arg);
+      w |= arg << B::RE;
+    }
+    bp[(size_t)(col - 1) * (size_t)stride] = w;
+  }
+}
+
+// ... or one packed word per column (hmm_viterbi_lane).  The walk visits the columns in decreasing order, several
+// states per column: the word of the current column is kept, and the line a few columns further down is asked for
+// ahead of time (the 32 lanes of a warp share every line).
+#define HMM_LANE_PREFETCH 6
+template <int N>
+struct HmmBpWords {
+  const uint32_t *w;
+  int stride, L;
+  int cur_col;
+  uint32_t cur_w;
+  TRGT_HD HmmBpWords(const uint32_t *w_, int stride_, int L_) : w(w_), stride(stride_), L(L_), cur_col(-1), cur_w(0) {}
+  TRGT_HD int get(int col, int st, const HmmRole &r) {
+    typedef HmmLaneBits<N> B;
+    (void)st;
+    if (col <= 0) return 0;          // column 0: rs <- start, ms / skip_ms <- rs
+    if (col > L) return 0;           // column L + 1: end <- re
+    if (col != cur_col) {
+      cur_col = col;
+      cur_w = w[(size_t)(col - 1) * (size_t)stride];
+#if defined(__CUDA_ARCH__)
+      if (col > HMM_LANE_PREFETCH)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(w + (size_t)(col - 1 - HMM_LANE_PREFETCH) * (size_t)stride));
+#endif
+    }
+    const uint32_t v = cur_w;
+    switch (r.kind) {
+      case HR_INS: return (int)((v >> (B::I0 + r.i)) & 1u);
+      case HR_MATCH: return r.i == 0 ? 0 : (int)((v >> (B::M0 + 2 * (r.i - 1))) & 3u);
+      case HR_DEL: return r.i == 0 ? 0 : (int)((v >> (B::D0 + (r.i - 1))) & 1u);
+      case HR_SKIP: return (int)((v >> B::SKIP) & 1u);
+      case HR_ME: return (int)((v >> B::ME) & 3u);
+      case HR_RE: return (int)((v >> B::RE) & 1u);
+      case HR_RS: return 1;
+      default: return 0;             // ms, skip_ms, skip_me, end
+    }
+  }
+};
+
+// ---- the walk of a single-motif allele, table driven ---------------------------------------------------------
+// hmm_annotate_bp decodes a state's role and its predecessor arithmetically at every step; for the lane kernels
+// that is most of the walk.  Here everything a step needs about state `st` of the model of motif length n is one
+// 8-byte table entry, built once per CTA from that same arithmetic (hmm_role / hmm_pred / HmmLaneBits):
+//   x = the four predecessors (one byte each, indexed by in-edge);
+//   y = shift | mask << 8 | kind << 16 | i << 24   (where the in-edge sits in the column's packed word).
+struct HmmModelSingleRt {  // HmmModelSingle with the motif length at run time (only for building tables)
+  int n, S, nb;
+  TRGT_HD explicit HmmModelSingleRt(int n_) : n(n_), S(3 * n_ + 8), nb(2) {}
+  TRGT_HD int block_n(int b) const { return b == 0 ? n : 0; }
+  TRGT_HD int block_ms(int b) const { return b == 0 ? 2 : 3 + 3 * n; }
+  TRGT_HD int block_of(int st) const { return st <= 2 + 3 * n ? 0 : 1; }
+};
+
+struct HmmLaneEntry {
+  uint32_t x, y;
+};
+
+TRGT_HD HmmLaneEntry hmm_lane_table_entry(int n, int st) {
+  const HmmModelSingleRt m(n);
+  HmmLaneEntry t;
+  t.x = 0; t.y = 0;
+  if (st >= m.S) return t;
+  const HmmRole r = hmm_role(m, st);
+  for (int e = 0; e < 4; e++) t.x |= ((uint32_t)hmm_pred(m, r, st, e) & 255u) << (8 * e);
+  const int M0 = n, D0 = 3 * n - 2, SKIP = D0 + (n >= 2 ? n - 2 : 0), ME = SKIP + 1, RE = ME + 2;  // HmmLaneBits<n>
+  uint32_t shift = 0, mask = 0;
+  switch (r.kind) {
+    case HR_INS: shift = (uint32_t)r.i; mask = 1; break;
+    case HR_MATCH: if (r.i > 0) { shift = (uint32_t)(M0 + 2 * (r.i - 1)); mask = 3; } break;
+    case HR_DEL: if (r.i > 0) { shift = (uint32_t)(D0 + r.i - 1); mask = 1; } break;
+    case HR_SKIP: shift = (uint32_t)SKIP; mask = 1; break;
+    case HR_ME: shift = (uint32_t)ME; mask = 3; break;
+    case HR_RE: shift = (uint32_t)RE; mask = 1; break;
+    default: break;  // one in-edge, or rs / ms / skip_ms (see HmmLaneBits)
+  }
+  t.y = shift | (mask << 8) | ((uint32_t)r.kind << 16) | ((uint32_t)r.i << 24);
+  return t;
+}
+
+// hmm_annotate_bp for one allele of a single-motif locus over its packed words, driven by `tab` (the 3 n + 8
+// entries of motif length n).  Same walk, same results: purity, MC, collapsed spans (into the last n_spans of the
+// n_total slots of spans_out).  words: column c at words[(c - 1) * stride].
+template <class SP>
+TRGT_HD HmmAnnot hmm_walk_table(const HmmLaneEntry *tab, int n, uint64_t mbytes, const uint8_t *allele, int L,
+                                const uint32_t *words, int stride, int max_motif_len, uint32_t *mc,
+                                const SP &spans_out, uint32_t n_total, uint64_t *path_len) {
+  HmmAnnot out;
+  out.purity = 0.0; out.n_spans = 0; out.status = 0;
+  const int S = 3 * n + 8;
+  uint32_t n_match = 0, n_mis = 0, n_ins = 0, n_del = 0, n_skip = 0;
+  int st = S - 1, col = L + 1, last = -1;
+  int copy_end = 0;
+  bool have_p = false;
+  uint32_t p_motif = 0, p_start = 0, p_end = 0, emitted = 0;
+  uint64_t plen = 0;
+  const uint64_t max_steps = ((uint64_t)L + 2) * (uint64_t)S + 2;
+  // words of column col and of the one below it (asked for one column ahead of its use)
+  uint32_t w_cur = 0, w_nxt = L >= 1 ? words[(size_t)(L - 1) * (size_t)stride] : 0u;
+  while (st != 0) {
+    if (++plen > max_steps) { out.status = -1; break; }
+    const HmmLaneEntry t = tab[st];
+    const int kind = (int)((t.y >> 16) & 255u), i = (int)(t.y >> 24);
+    const bool emits = kind == HR_END || kind == HR_MATCH || kind == HR_INS || kind == HR_SKIP;
+    if (kind == HR_MATCH) {
+      const uint8_t expected = (uint8_t)(mbytes >> (8 * i));
+      const uint8_t base = hmm_clean_base(allele[col - 1], (uint32_t)(col - 1));
+      if (base == expected || expected == 'N') n_match++; else n_mis++;
+    }
+    n_ins += kind == HR_INS ? 1u : 0u;
+    n_skip += kind == HR_SKIP ? 1u : 0u;
+    n_del += kind == HR_DEL ? 1u : 0u;
+    if (kind == HR_ME || kind == HR_SKIP_ME) copy_end = col;
+    if (kind == HR_MS || kind == HR_SKIP_MS) {
+      const int copy_start = col;
+      n_del += (uint32_t)(last - st - 1);  // jump-in to match_i counts i deletions, events.rs:44-46
+      if (kind == HR_MS) {
+        bool keep = true;  // operations.rs:46-62
+        if (n <= max_motif_len) {
+          if (copy_end - copy_start < n) {
+            keep = false;
+          } else {
+            for (int k = 0; k < n; k++) {
+              const uint8_t expected = (uint8_t)(mbytes >> (8 * k));
+              const uint8_t observed = hmm_clean_base(allele[copy_start + k], (uint32_t)(copy_start + k));
+              if (expected != 'N' && observed != expected) keep = false;
+            }
+          }
+        }
+        if (keep) {
+          if (mc) mc[0]++;
+          if (have_p && p_motif == 0u && p_start == (uint32_t)copy_end) {
+            p_start = (uint32_t)copy_start;
+          } else {
+            if (have_p) {
+              if (spans_out.on() && emitted < n_total) {
+                HmmSpan sp; sp.motif_index = p_motif; sp.start = p_start; sp.end = p_end;
+                spans_out.put(n_total - 1 - emitted, sp);
+              }
+              emitted++;
+            }
+            have_p = true;
+            p_motif = 0u; p_start = (uint32_t)copy_start; p_end = (uint32_t)copy_end;
+          }
+        }
+      }
+    }
+    // in-edge taken into this state: from the column's word, except where it is implied (HmmLaneBits)
+    uint32_t arg = (col >= 1 && col <= L) ? ((w_cur >> (t.y & 255u)) & ((t.y >> 8) & 255u)) : 0u;
+    if (kind == HR_RS) arg = col > 0 ? 1u : 0u;
+    const int p = (int)((t.x >> (8 * arg)) & 255u);
+    if (emits) {
+      col -= 1;
+      w_cur = w_nxt;
+      if (col >= 2) w_nxt = words[(size_t)(col - 2) * (size_t)stride];
+    }
+    last = st;
+    st = p;
+  }
+  plen++;  // the start state
+  if (path_len) *path_len = plen;
+  if (have_p) {
+    if (spans_out.on() && emitted < n_total) {
+      HmmSpan sp; sp.motif_index = p_motif; sp.start = p_start; sp.end = p_end;
+      spans_out.put(n_total - 1 - emitted, sp);
+    }
+    emitted++;
+  }
+  out.n_spans = emitted;
+  // purity.rs:11-40
+  const double edit = (double)((uint64_t)n_del + n_ins + n_mis + n_skip);
+  const uint64_t ref_len = (uint64_t)n_match + n_mis + n_del + n_skip;
   const double max_dist = (double)(ref_len > (uint64_t)L ? ref_len : (uint64_t)L);
   out.purity = (max_dist - edit) / max_dist;
   return out;

@@ -1003,7 +1003,10 @@ struct HmmBatch {
   const uint32_t *locus_motif_off;                     // [n_loci+1]
   const uint8_t *alleles; const uint64_t *allele_off; // [n_alleles+1]
   const uint32_t *allele_locus;
-  const unsigned long long *bp_off;                    // [n_alleles+1] into bp (relative to wave base)
+  const uint32_t *list;                                // alleles these kernels take (nullptr: every allele); the
+                                                       // kernels' ranges and bp_off / scr_off index this list
+  const unsigned long long *bp_off;                    // [n_list+1] into bp (relative to wave base)
+  const unsigned long long *scr_off;                   // [n_list+1] into the span scratch (one slot per base)
   const unsigned long long *mc_off;                    // [n_alleles+1] into mc
   const uint32_t *mm_off; const double *mm_lp;         // jump-in ln table
   HmmConsts c;
@@ -1042,7 +1045,8 @@ k_hmm_viterbi_thread(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long b
   extern __shared__ __align__(16) unsigned char smem_b[];
   double *sc = reinterpret_cast<double *>(smem_b);  // [2][s_cap][128], s_cap = min(HMM_THREAD_S, largest model of the batch)
   const uint32_t gsz = gridDim.x * blockDim.x;
-  for (uint32_t a = a0 + blockIdx.x * blockDim.x + threadIdx.x; a < a1; a += gsz) {
+  for (uint32_t ai = a0 + blockIdx.x * blockDim.x + threadIdx.x; ai < a1; ai += gsz) {
+    const uint32_t a = hb.list ? hb.list[ai] : ai;
     const uint32_t l = hb.allele_locus[a];
     const uint32_t m0 = hb.locus_motif_off[l];
     const int nm = (int)(hb.locus_motif_off[l + 1] - m0);
@@ -1056,7 +1060,7 @@ k_hmm_viterbi_thread(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long b
     const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
     if (L == 0) continue;
     hmm_viterbi_thread(hmm_model_pack(model, hb.mm_off), hb.c, hb.mm_off, hb.mm_lp, hb.alleles + hb.allele_off[a], L, sc + threadIdx.x,
-                       sc + (size_t)s_cap * 128 + threadIdx.x, 128, bp + (hb.bp_off[a] - bp_base));
+                       sc + (size_t)s_cap * 128 + threadIdx.x, 128, bp + (hb.bp_off[ai] - bp_base));
   }
 }
 
@@ -1070,7 +1074,8 @@ k_hmm_viterbi(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base,
   const uint32_t wib = threadIdx.x >> 5;
   const uint32_t warps = gridDim.x * (blockDim.x >> 5);
   const HmmWarpMem wm = hmm_carve(smem_b + (size_t)wib * hb.warp_bytes, hb.S_max, hb.nb_max);
-  for (uint32_t a = a0 + blockIdx.x * (blockDim.x >> 5) + wib; a < a1; a += warps) {
+  for (uint32_t ai = a0 + blockIdx.x * (blockDim.x >> 5) + wib; ai < a1; ai += warps) {
+    const uint32_t a = hb.list ? hb.list[ai] : ai;
     const uint32_t l = hb.allele_locus[a];
     const uint32_t m0 = hb.locus_motif_off[l];
     const int nm = (int)(hb.locus_motif_off[l + 1] - m0);
@@ -1091,7 +1096,7 @@ k_hmm_viterbi(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base,
                                   wm.n, wm.ms, wm.stblk, &model);
     if (g.lane() == 0) status[a] = S < 0 ? TRGT_ITEM_INVALID_BASE : 0;
     if (S >= 0 && L > 0)
-      hmm_viterbi(g, model, hb.c, hb.mm_lp, allele, L, wm.sc0, wm.sc1, bp + (hb.bp_off[a] - bp_base));
+      hmm_viterbi(g, model, hb.c, hb.mm_lp, allele, L, wm.sc0, wm.sc1, bp + (hb.bp_off[ai] - bp_base));
     __syncwarp();
   }
 }
@@ -1104,7 +1109,8 @@ k_hmm_walk(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, co
            unsigned long long *__restrict__ path_len, int32_t *__restrict__ status,
            trgt_motif_span_t *__restrict__ span_scratch) {
   const uint32_t gsz = gridDim.x * blockDim.x;
-  for (uint32_t a = a0 + blockIdx.x * blockDim.x + threadIdx.x; a < a1; a += gsz) {
+  for (uint32_t ai = a0 + blockIdx.x * blockDim.x + threadIdx.x; ai < a1; ai += gsz) {
+    const uint32_t a = hb.list ? hb.list[ai] : ai;
     const uint32_t l = hb.allele_locus[a];
     const uint32_t m0 = hb.locus_motif_off[l];
     const int nm = (int)(hb.locus_motif_off[l + 1] - m0);
@@ -1119,13 +1125,13 @@ k_hmm_walk(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, co
     }
     const HmmModelScan model = hmm_model_scan(hb.motifs, hb.motif_off + m0, nm);
     uint64_t plen = 0;
-    // span_scratch: one slot per base of the wave's alleles (a collapsed span covers at least one base); the
+    // span_scratch: one slot per base of the batch's alleles (a collapsed span covers at least one base); the
     // walk fills the allele's slots from the back, so its spans end up in the last n_spans of them, in order
-    HmmSpan *sp = span_scratch ? (HmmSpan *)(span_scratch + (hb.allele_off[a] - hb.allele_off[a0])) : nullptr;
+    HmmSpan *sp = span_scratch ? (HmmSpan *)(span_scratch + hb.scr_off[ai]) : nullptr;
     const HmmAnnot an = model.S <= HMM_THREAD_S
                             ? hmm_annotate(hmm_model_pack(model), hb.alleles + hb.allele_off[a], L,
-                                           bp + (hb.bp_off[a] - bp_base), 6, my_mc, sp, (uint32_t)L, nullptr, 0, 0, &plen)
-                            : hmm_annotate(model, hb.alleles + hb.allele_off[a], L, bp + (hb.bp_off[a] - bp_base), 6, my_mc,
+                                           bp + (hb.bp_off[ai] - bp_base), 6, my_mc, sp, (uint32_t)L, nullptr, 0, 0, &plen)
+                            : hmm_annotate(model, hb.alleles + hb.allele_off[a], L, bp + (hb.bp_off[ai] - bp_base), 6, my_mc,
                                            sp, (uint32_t)L, nullptr, 0, 0, &plen);
     purity[a] = an.purity;
     n_spans[a] = an.n_spans;
@@ -1140,11 +1146,12 @@ k_hmm_spans(HmmBatch hb, uint32_t a0, uint32_t a1, const trgt_motif_span_t *__re
             const uint32_t *__restrict__ n_spans, const unsigned long long *__restrict__ span_off,
             trgt_motif_span_t *__restrict__ spans) {
   const uint32_t gsz = gridDim.x * blockDim.x;
-  for (uint32_t a = a0 + blockIdx.x * blockDim.x + threadIdx.x; a < a1; a += gsz) {
+  for (uint32_t ai = a0 + blockIdx.x * blockDim.x + threadIdx.x; ai < a1; ai += gsz) {
+    const uint32_t a = hb.list ? hb.list[ai] : ai;
     const uint32_t ns = n_spans[a];
     if (ns == 0) continue;
     const uint64_t L = hb.allele_off[a + 1] - hb.allele_off[a];
-    const trgt_motif_span_t *src = span_scratch + (hb.allele_off[a] - hb.allele_off[a0]) + (L - ns);
+    const trgt_motif_span_t *src = span_scratch + hb.scr_off[ai] + (L - ns);
     trgt_motif_span_t *dst = spans + span_off[a];
     for (uint32_t i = 0; i < ns; i++) dst[i] = src[i];
   }
@@ -1158,7 +1165,8 @@ k_hmm_emit(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, co
            trgt_motif_span_t *__restrict__ spans, const unsigned long long *__restrict__ path_off,
            uint32_t *__restrict__ paths, const int32_t *__restrict__ status) {
   const uint32_t gsz = gridDim.x * blockDim.x;
-  for (uint32_t a = a0 + blockIdx.x * blockDim.x + threadIdx.x; a < a1; a += gsz) {
+  for (uint32_t ai = a0 + blockIdx.x * blockDim.x + threadIdx.x; ai < a1; ai += gsz) {
+    const uint32_t a = hb.list ? hb.list[ai] : ai;
     const int L = (int)(hb.allele_off[a + 1] - hb.allele_off[a]);
     const uint32_t ns = n_spans[a];
     const unsigned long long plen = path_off ? path_off[a + 1] - path_off[a] : 0;
@@ -1167,9 +1175,141 @@ k_hmm_emit(HmmBatch hb, uint32_t a0, uint32_t a1, unsigned long long bp_base, co
     const uint32_t m0 = hb.locus_motif_off[l];
     const int nm = (int)(hb.locus_motif_off[l + 1] - m0);
     const HmmModelScan model = hmm_model_scan(hb.motifs, hb.motif_off + m0, nm);
-    hmm_annotate(model, hb.alleles + hb.allele_off[a], L, bp + (hb.bp_off[a] - bp_base), 6, nullptr,
+    hmm_annotate(model, hb.alleles + hb.allele_off[a], L, bp + (hb.bp_off[ai] - bp_base), 6, nullptr,
                  (HmmSpan *)(spans + span_off[a]), ns, plen ? paths + path_off[a] : nullptr, plen, plen, nullptr);
   }
+}
+
+// ---- single-motif loci (every locus of a genome-wide catalog): one lane per allele, score column in registers,
+// ---- one packed back-pointer word per column (hmm_core.h, hmm_viterbi_lane) -------------------------------
+
+// The engine sorts these alleles by (motif length, allele length) into `slots`; 32 consecutive slots form a
+// group = one warp: same motif length (groups never straddle two lengths: the tail of a length is padded with
+// empty slots), similar allele lengths, so the lanes of a warp run the same unrolled code for about the same
+// number of columns.  Groups are ordered by their longest allele, longest first, so that the long alleles --
+// a lane walks its columns one after the other -- start first and the short ones fill in behind them.
+// Column c of lane l of group g is word group_off[g] + (c - 1) * 32 + l: a warp writes one 128-byte line per column.
+struct HmmLaneBatch {
+  const uint8_t *motifs; const uint64_t *motif_off; const uint32_t *locus_motif_off;
+  const uint8_t *alleles; const uint64_t *allele_off; const uint32_t *allele_locus;
+  const unsigned long long *mc_off;
+  const uint32_t *slots;                  // allele of each slot, 0xFFFFFFFF = padding
+  const uint8_t *group_n;                 // motif length of each group
+  const unsigned long long *group_off;    // [n_groups+1] first word of each group (absolute; waves subtract their base)
+  HmmConsts c;
+  double jump[HMM_LANE_NMAX + 1][HMM_LANE_NMAX];  // jump[n][i] = ln(seed (n - i)), builder.rs:93-111
+};
+
+#define HMM_LANE_SWITCH(n, F) \
+  switch (n) {                \
+    case 1: F(1); break;      \
+    case 2: F(2); break;      \
+    case 3: F(3); break;      \
+    case 4: F(4); break;      \
+    case 5: F(5); break;      \
+    case 6: F(6); break;      \
+    case 7: F(7); break;      \
+    case 8: F(8); break;      \
+    default: break;           \
+  }
+
+__global__ void __launch_bounds__(128)
+k_hmm_lane_viterbi(HmmLaneBatch lb, uint32_t g0, uint32_t g1, unsigned long long word_base, uint32_t *__restrict__ bp,
+                   int32_t *__restrict__ status) {
+  const uint32_t g = g0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= g1) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t a = lb.slots[(size_t)g * 32 + lane];
+  if (a == 0xFFFFFFFFu) return;
+  const uint32_t l = lb.allele_locus[a];
+  const uint8_t *motif = lb.motifs + lb.motif_off[lb.locus_motif_off[l]];
+  const int L = (int)(lb.allele_off[a + 1] - lb.allele_off[a]);
+  status[a] = 0;
+  uint32_t *my_bp = bp + (lb.group_off[g] - word_base) + lane;
+  const uint8_t *allele = lb.alleles + lb.allele_off[a];
+#define F(N) hmm_viterbi_lane<N>(lb.c, lb.jump[N], hmm_pack_motif(motif, N), allele, L, my_bp, 32)
+  HMM_LANE_SWITCH(lb.group_n[g], F)
+#undef F
+}
+
+// The reverse walk of the same alleles over the packed words: purity, MC, collapsed spans (left in the group's
+// scratch slots, slot j of lane l at group_off[g] + j * 32 + l, filled from the back) and, optionally, the
+// length of the state path.  Table driven (hmm_walk_table): the CTA first builds the 32-entry state table of
+// every motif length in shared memory (2 KB), from the same arithmetic the generic walk evaluates per step.
+__global__ void __launch_bounds__(128)
+k_hmm_lane_walk(HmmLaneBatch lb, uint32_t g0, uint32_t g1, unsigned long long word_base, const uint32_t *__restrict__ bp,
+                uint32_t *__restrict__ mc, double *__restrict__ purity, uint32_t *__restrict__ n_spans,
+                unsigned long long *__restrict__ path_len, int32_t *__restrict__ status,
+                trgt_motif_span_t *__restrict__ span_scratch) {
+  __shared__ HmmLaneEntry tab[HMM_LANE_NMAX + 1][32];
+  for (int q = threadIdx.x; q < (HMM_LANE_NMAX + 1) * 32; q += blockDim.x)
+    tab[q >> 5][q & 31] = (q >> 5) >= 1 ? hmm_lane_table_entry(q >> 5, q & 31) : HmmLaneEntry{0u, 0u};
+  __syncthreads();
+  const uint32_t g = g0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= g1) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t a = lb.slots[(size_t)g * 32 + lane];
+  if (a == 0xFFFFFFFFu) return;
+  const uint32_t l = lb.allele_locus[a];
+  const uint8_t *motif = lb.motifs + lb.motif_off[lb.locus_motif_off[l]];
+  const int L = (int)(lb.allele_off[a + 1] - lb.allele_off[a]);
+  const int n = lb.group_n[g];
+  uint32_t *my_mc = mc + lb.mc_off[a];
+  my_mc[0] = 0;
+  const HmmSpanStrided sp{span_scratch ? (HmmSpan *)(span_scratch + lb.group_off[g] + lane) : nullptr, 32u};
+  uint64_t plen = 0;
+  const HmmAnnot an = hmm_walk_table(tab[n], n, hmm_pack_motif(motif, n), lb.alleles + lb.allele_off[a], L,
+                                     bp + (lb.group_off[g] - word_base) + lane, 32, 6, my_mc, sp, (uint32_t)L, &plen);
+  purity[a] = an.purity;
+  n_spans[a] = an.n_spans;
+  if (path_len) path_len[a] = plen;
+  if (an.status < 0) status[a] = TRGT_ERR_INTERNAL;
+}
+
+// spans of the lane alleles from their groups' scratch slots to their CSR offsets
+__global__ void __launch_bounds__(128)
+k_hmm_lane_spans(HmmLaneBatch lb, uint32_t g0, uint32_t g1, const trgt_motif_span_t *__restrict__ span_scratch,
+                 const uint32_t *__restrict__ n_spans, const unsigned long long *__restrict__ span_off,
+                 trgt_motif_span_t *__restrict__ spans) {
+  const uint32_t g = g0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= g1) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t a = lb.slots[(size_t)g * 32 + lane];
+  if (a == 0xFFFFFFFFu) return;
+  const uint32_t ns = n_spans[a];
+  if (ns == 0) return;
+  const uint64_t L = lb.allele_off[a + 1] - lb.allele_off[a];
+  const trgt_motif_span_t *src = span_scratch + lb.group_off[g] + lane;
+  trgt_motif_span_t *dst = spans + span_off[a];
+  for (uint32_t i = 0; i < ns; i++) dst[i] = src[(size_t)(L - ns + i) * 32];
+}
+
+// second walk, only when state paths (Hmm::label) are asked for: the path at its CSR offset, forward order
+__global__ void __launch_bounds__(128)
+k_hmm_lane_emit(HmmLaneBatch lb, uint32_t g0, uint32_t g1, unsigned long long word_base, const uint32_t *__restrict__ bp,
+                const unsigned long long *__restrict__ path_off, uint32_t *__restrict__ paths,
+                const int32_t *__restrict__ status) {
+  const uint32_t g = g0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= g1) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t a = lb.slots[(size_t)g * 32 + lane];
+  if (a == 0xFFFFFFFFu || status[a] != 0) return;
+  const unsigned long long plen = path_off[a + 1] - path_off[a];
+  if (plen == 0) return;
+  const uint32_t l = lb.allele_locus[a];
+  const uint8_t *motif = lb.motifs + lb.motif_off[lb.locus_motif_off[l]];
+  const int L = (int)(lb.allele_off[a + 1] - lb.allele_off[a]);
+  const uint32_t *my_bp = bp + (lb.group_off[g] - word_base) + lane;
+  const uint8_t *allele = lb.alleles + lb.allele_off[a];
+#define F(N)                                                                                              \
+  {                                                                                                       \
+    const HmmModelSingle<N> model{hmm_pack_motif(motif, N)};                                              \
+    HmmBpWords<N> words(my_bp, 32, L);                                                                    \
+    hmm_annotate_bp(model, allele, L, words, 6, (uint32_t *)nullptr, HmmSpanArray{nullptr}, 0, paths + path_off[a], \
+                    plen, plen, (uint64_t *)nullptr);                                                     \
+  }
+  HMM_LANE_SWITCH(lb.group_n[g], F)
+#undef F
 }
 
 // ------------------------------------------------------------------ VCF sample fields ---------

@@ -70,7 +70,7 @@ HIT_DTYPE = np.dtype([("via", np.int32), ("matches", np.int32), ("score", np.int
 EXPORTS = [
     "trgt_engine_create", "trgt_engine_destroy", "trgt_engine_last_error", "trgt_last_create_error",
     "trgt_engine_stream", "trgt_engine_sm_count", "trgt_engine_sync", "trgt_engine_set_workspace_budget",
-    "trgt_engine_set_flank_band_budget",
+    "trgt_engine_set_flank_band_budget", "trgt_engine_set_hmm_lane_path",
     "trgt_host_alloc", "trgt_host_free",
     "trgt_clip_reads", "trgt_seq4_decode", "trgt_flank_spans_seq4", "trgt_flank_upload_seq4",
     "trgt_flank_trs", "trgt_vcf_fields",
@@ -358,6 +358,10 @@ class Engine:
 
     def set_workspace_budget(self, nbytes: int):
         self._L.trgt_engine_set_workspace_budget(self._h, nbytes)
+
+    def set_hmm_lane_path(self, on: bool):
+        """single-motif loci through the per-motif-length lane kernels (default) or the generic ones (diagnostic)"""
+        self._L.trgt_engine_set_hmm_lane_path(self._h, int(bool(on)))
 
     def set_flank_band_budget(self, max_cost: int):
         self._L.trgt_engine_set_flank_band_budget(self._h, max_cost)
