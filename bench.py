@@ -37,8 +37,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--loci", type=int, default=125000, help="loci per GPU (125000 x 8 = the 1M-locus catalog)")
-    ap.add_argument("--depth", type=int, default=30)
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4],
+                    help="BASELINE.json config: 2 = pathogenic catalog (56 loci, 30x), 3 = 100k-locus catalog, uniform 2-6 bp "
+                         "motifs, 20x (strong scaling: the catalog is split over the GPUs), 4 = Adotto-scale catalog, 30x "
+                         "(125000 loci per GPU; the metric's config, default)")
+    ap.add_argument("--loci", type=int, default=0, help="override the config's locus count (per GPU for config 4, total otherwise)")
+    ap.add_argument("--depth", type=int, default=0, help="override the config's depth")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident-only", action="store_true",
@@ -59,15 +63,63 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def workload_config(args, n_gpus: int) -> dict:
-    return {
-        "workload": f"Adotto-scale genome-wide synthetic catalog shard (BASELINE config 4): {args.loci} loci/GPU x "
-                    f"{n_gpus} GPU, {args.depth}x HiFi, clipped reads = 500 bp + allele + 500 bp, 250-bp flank pieces, "
-                    "2-6 bp motifs (57/8/25/7/2 %), TR length median 24 bp; sub/ins/del 2e-4/4e-4/4e-4 per base",
-        "loci_per_gpu": args.loci, "depth": args.depth, "scoring": [2, 5, 1], "min_flank_id_frac": 0.7,
-        "parallelism": f"locus shards x{n_gpus}, no data-path collective; one gather of per-locus records per e2e step",
-        "l2": "inputs (~3.9 GB of reads per GPU) are larger than the 126 MB L2; no explicit flush",
-    }
+class Spec:
+    """What one rank processes under --config, and how the catalog grows with the GPU count."""
+
+    def __init__(self, args, world: int):
+        self.config = args.config
+        c = args.config
+        self.depth = args.depth or {2: 30, 3: 20, 4: 30}[c]
+        self.gen = {}
+        self.motif_sets = None
+        if c == 4:     # weak scaling: 125 000 loci per GPU, 1 M at 8 GPUs
+            self.loci_per_rank = args.loci or 125000
+            self.total = self.loci_per_rank * world
+            self.scaling = "weak"
+            self.name = "Adotto-scale genome-wide synthetic catalog shard (BASELINE config 4)"
+            self.detail = "2-6 bp motifs (57/8/25/7/2 %), TR length median 24 bp"
+        elif c == 3:   # strong scaling: one 100k-locus catalog split over the GPUs
+            self.total = args.loci or 100000
+            self.loci_per_rank = -(-self.total // world)
+            self.scaling = "strong"
+            self.gen = {"motif_mix": "uniform"}
+            self.name = "100k-locus synthetic catalog (BASELINE config 3)"
+            self.detail = "2-6 bp motifs (uniform), TR length median 24 bp"
+        else:          # the 56 loci of repeats/pathogenic_repeats.hg38.bed, split over the GPUs
+            from harness import workload
+            self.motif_sets = workload.pathogenic_motif_sets()
+            self.total = args.loci or len(self.motif_sets)
+            self.loci_per_rank = -(-self.total // world)
+            self.scaling = "strong"
+            self.gen = {"tr_len_median": 60.0}
+            self.name = "pathogenic catalog (BASELINE config 2: motif sets of repeats/pathogenic_repeats.hg38.bed)"
+            self.detail = "1-10 motifs per locus, up to 170 HMM states, TR length median 60 bp"
+
+    def rank_range(self, rank: int):
+        if self.scaling == "weak":
+            return rank * self.loci_per_rank, self.loci_per_rank
+        lo = min(self.total, rank * self.loci_per_rank)
+        return lo, min(self.total, lo + self.loci_per_rank) - lo
+
+    def generate(self, rank: int, n_loci=None, **kw):
+        from harness import workload
+        lo, cnt = self.rank_range(rank)
+        return workload.generate(cnt if n_loci is None else min(n_loci, cnt), self.depth, locus_begin=lo,
+                                 motif_sets=self.motif_sets, name=self.name, **self.gen, **kw)
+
+    def describe(self, n_gpus: int) -> dict:
+        per = f"{self.loci_per_rank} loci/GPU x {n_gpus} GPU" if self.scaling == "weak" else \
+            f"{self.total} loci split over {n_gpus} GPU"
+        return {
+            "workload": f"{self.name}: {per}, {self.depth}x HiFi, clipped reads = 500 bp + allele + 500 bp, 250-bp "
+                        f"flank pieces, {self.detail}; sub/ins/del 2e-4/4e-4/4e-4 per base",
+            "baseline_config": self.config, "loci_per_gpu": self.loci_per_rank, "loci_total": self.total,
+            "depth": self.depth, "scoring": [2, 5, 1], "min_flank_id_frac": 0.7,
+            "parallelism": f"locus shards x{n_gpus}, no data-path collective; one gather of per-locus records per e2e step",
+            "l2": "inputs (~1 KB per read; 3.9 GB of reads per GPU at config 4) are larger than the 126 MB L2 for configs 3 "
+                  "and 4; no explicit flush" if self.config != 2 else
+                  "inputs (1.9 MB of reads) fit the L2: a 256 MB buffer is overwritten between timed steps",
+        }
 
 
 # ------------------------------------------------------------------ clocks -----------------
@@ -125,7 +177,7 @@ class ClockSampler:
 def cpu_pass_rate(w, n_threads: int, seconds: float, max_loci: int):
     """Time the oracle pass on a bounded head of the workload sized for ~`seconds`.  -> (loci/s, n, dt)"""
     from oracle import oracle as orc
-    from trgt_b200.pipeline import oracle_pass
+    from harness.pipeline import oracle_pass
     probe = min(max_loci, max(64, 16 * n_threads))
     t0 = time.perf_counter()
     oracle_pass(orc, w.head(probe), n_threads)
@@ -143,18 +195,19 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as orc
-    from trgt_b200 import workload
-    from trgt_b200.pipeline import oracle_pass
+    from harness.pipeline import oracle_pass
     cores = host_cores()
+    spec = Spec(args, max(1, args.gpus))
     total = max(1, args.steps + args.warmup)
     per_step = max(1.0, min(8.0, 150.0 / total))
     # size the per-step sample with a probe
-    w0 = workload.generate(min(args.loci, max(64, 16 * cores)), args.depth)
+    w0 = spec.generate(0, max(64, 16 * cores))
     t0 = time.perf_counter()
     oracle_pass(orc, w0, cores)
     rate = w0.n_loci / (time.perf_counter() - t0)
-    n = int(min(args.loci, max(w0.n_loci, rate * per_step)))
-    w = workload.generate(n, args.depth)
+    n = int(min(spec.loci_per_rank, max(w0.n_loci, rate * per_step)))
+    w = spec.generate(0, n)
+    n = w.n_loci
     for _ in range(args.warmup):
         oracle_pass(orc, w, cores)
     t0 = time.perf_counter()
@@ -162,11 +215,11 @@ def run_reference(args):
         oracle_pass(orc, w, cores)
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     value = n / dt
-    cfg = workload_config(args, args.gpus)
-    sample = f"first {n} loci of the shard per step ({n * args.depth} reads), all host cores"
+    cfg = spec.describe(args.gpus)
+    sample = f"first {n} loci of the shard per step ({w.n_reads} reads), all host cores"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": spec.scaling,
         "vs_baseline": None, "dtype": "int32 wavefront offsets + f64 Viterbi", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -225,8 +278,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
 
     import trgt_b200
-    from trgt_b200 import workload
-    from trgt_b200.pipeline import ChunkedHotPath, HotPath, compare_with_oracle, concat_results
+    from harness import workload
+    from harness.pipeline import ChunkedHotPath, HotPath, compare_with_oracle, concat_results
 
     eng = trgt_b200.Engine(device=local_rank)  # fails loudly without the CUDA library / a GPU
     stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
@@ -244,9 +297,10 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    spec = Spec(args, world)
+    args.loci = spec.rank_range(rank)[1]   # loci of this rank
     t_gen = time.perf_counter()
-    w = workload.generate(args.loci, args.depth, locus_begin=rank * args.loci, alloc_reads=eng.pinned_array,
-                          name="genome-wide-synthetic")
+    w = spec.generate(rank, alloc_reads=eng.pinned_array)
     t_gen = time.perf_counter() - t_gen
     use_seq4 = args.e2e_input == "seq4"
     if use_seq4:  # untimed set-up: the reads as BAM records hold them, in pinned memory
@@ -279,13 +333,28 @@ def run_b200(args):
     barrier()
     clocks.start()
     launches0 = eng.launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        hp.run_resident(sync=False)
-    ev1.record(stream)
-    barrier()
-    dev_ms = ev0.elapsed_time(ev1) / max(1, args.steps)
+    small = w.reads.data.nbytes < (256 << 20)   # inputs that fit the 126 MB L2: flush it between timed steps
+    if small:
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        pairs = []
+        with torch.cuda.stream(stream):
+            for _ in range(args.steps):
+                flush_buf.zero_()               # untimed: overwrites the L2 with 256 MB
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                hp.run_resident(sync=False)
+                b_.record(stream)
+                pairs.append((a, b_))
+        barrier()
+        dev_ms = sum(a.elapsed_time(b_) for a, b_ in pairs) / max(1, args.steps)
+    else:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            hp.run_resident(sync=False)
+        ev1.record(stream)
+        barrier()
+        dev_ms = ev0.elapsed_time(ev1) / max(1, args.steps)
     launches_total = eng.launches() - launches0                 # kernels of this engine inside the timed region
     launches = launches_total // max(1, args.steps)
     stats = eng.kernel_stats()
@@ -297,7 +366,8 @@ def run_b200(args):
     eng.set_profiling(False)
     res_resident = hp.download_resident()
     dev_ms = max_over_ranks(dev_ms)
-    value = args.loci * world / (dev_ms * 1e-3)
+    total_loci = spec.total   # loci all ranks process per step
+    value = total_loci / (dev_ms * 1e-3)
 
     # ---- `e2e`: host buffers through the C ABI, host<->device copies and host glue inside ----
     if args.resident_only:
@@ -334,7 +404,7 @@ def run_b200(args):
     e2e_phases["gather"] = t_gather / max(1, args.steps) * 1e3
     clk = clocks.stop()
     e2e_s = max_over_ranks(e2e_s)
-    e2e_value = args.loci * world / e2e_s
+    e2e_value = total_loci / e2e_s
     h2d = chp.h2d_bytes(res)
     d2h = chp.d2h_bytes(res)
 
@@ -397,7 +467,7 @@ def run_b200(args):
         cores = host_cores()
         rate, n, dt, ref = cpu_pass_rate(w, cores, args.cpu_seconds, args.loci)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {n} loci of the shard ({n * args.depth} reads), one pass in {dt:.1f} s, all host cores"}
+               "sample": f"first {n} loci of the shard ({n * spec.depth} reads), one pass in {dt:.1f} s, all host cores"}
         small = HotPath(eng, w.head(n), want_hits=False, pinned_outputs=False, use_seq4=use_seq4)
         compare_with_oracle(small.run_e2e(), ref)
         parity = {"checked_loci": n, "result": "bit-exact vs oracle (spans, CIGARs, scores, MC, MS, AP)"}
@@ -501,9 +571,9 @@ def run_b200(args):
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": spec.scaling, "vs_baseline": None,
         "dtype": "int32 wavefront offsets + f64 Viterbi", "data": "synthetic",
-        "config": workload_config(args, world), "clocks": clk, "gpu_launches": int(launches_total),
+        "config": spec.describe(world), "clocks": clk, "gpu_launches": int(launches_total),
         "gpu_launches_per_step": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),

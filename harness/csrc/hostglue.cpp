@@ -1,5 +1,5 @@
 // hostglue.cpp -- host-side stand-in for the reference's genotyper between the GPU phases (part of
-// libtrgt_host.so, used identically by the GPU arm and the CPU reference arm of bench.py).
+// libtrgt_harness.so, used identically by the GPU arm and the CPU reference arm of bench.py).
 //
 // In the reference the scalar genotype logic (src/trgt/genotype/*) sits between span location and
 // consensus alignment / HMM annotation and is out of scope here.  For synthetic reads whose

@@ -59,6 +59,8 @@ typedef struct {
   const uint8_t *motifs; const uint64_t *motif_off; const uint32_t *locus_motif_off;
   uint32_t n_catalog_loci;  // number of loci the fixed motif sets describe (cycled if n_loci is larger)
   uint32_t threads;
+  uint32_t motif_mix;       // 0: motif length mix of the genome-wide catalog (57/8/25/7/2 % for 2..6 bp); 1: uniform 2..6 bp
+  uint32_t tr_len_dist;     // 0: lognormal(median, sigma) clipped to [min, max]; 1: log-uniform on [min, max]
 } synth_params;
 
 typedef struct {
@@ -94,7 +96,8 @@ void make_locus(const synth_params &p, uint32_t gl, LocusDesc &d) {
       d.motifs.emplace_back(p.motifs + p.motif_off[m], p.motifs + p.motif_off[m + 1]);
   } else {
     const double u = r.uni();  // motif length mix of repeats/repeat_catalog.hg38.bed
-    const int n = u < 0.57 ? 2 : (u < 0.65 ? 3 : (u < 0.90 ? 4 : (u < 0.97 ? 5 : 6)));
+    const int n = p.motif_mix == 1 ? 2 + (int)(u * 5.0)
+                                   : (u < 0.57 ? 2 : (u < 0.65 ? 3 : (u < 0.90 ? 4 : (u < 0.97 ? 5 : 6))));
     std::vector<uint8_t> m(n);
     for (;;) {
       for (int i = 0; i < n; i++) m[i] = r.base();
@@ -105,7 +108,9 @@ void make_locus(const synth_params &p, uint32_t gl, LocusDesc &d) {
     d.motifs.push_back(m);
   }
   // repeat tract: copies of the motifs (N in a catalog motif becomes a concrete base)
-  double len = p.tr_len_median * exp(p.tr_len_sigma * r.gauss());
+  double len = p.tr_len_dist == 1
+                   ? exp(log((double)p.tr_len_min) + r.uni() * (log((double)p.tr_len_max) - log((double)p.tr_len_min)))
+                   : p.tr_len_median * exp(p.tr_len_sigma * r.gauss());
   if (len < p.tr_len_min) len = p.tr_len_min;
   if (len > p.tr_len_max) len = p.tr_len_max;
   const size_t nm = d.motifs.size();

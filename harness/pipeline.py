@@ -12,7 +12,7 @@ from typing import Optional
 
 import numpy as np
 
-from .engine import AnnotationBatch, CigarBatch, Engine, HIT_DTYPE, SPAN_DTYPE
+from trgt_b200.engine import AnnotationBatch, CigarBatch, Engine, HIT_DTYPE, SPAN_DTYPE
 import threading
 import time
 

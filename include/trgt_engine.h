@@ -44,6 +44,10 @@ extern "C" {
 #define TRGT_ITEM_INVALID_OP (-500)   /* reference panics: clip_region.rs:150,178 "Unexpected operation" */
 
 typedef struct trgt_engine trgt_engine_t;
+/* inputs of one phase kept resident in HBM (resident-batch interface below) */
+typedef struct trgt_flank_batch trgt_flank_batch_t;
+typedef struct trgt_align_batch trgt_align_batch_t;
+typedef struct trgt_hmm_batch trgt_hmm_batch_t;
 
 /* CSR set of byte sequences */
 typedef struct {
@@ -98,7 +102,7 @@ void trgt_engine_set_workspace_budget(trgt_engine_t *eng, size_t bytes);
  * path.  Default 16. */
 void trgt_engine_set_flank_band_budget(trgt_engine_t *eng, int32_t max_cost);
 
-/* Phase C runs the alleles of single-motif loci (one motif of 1..8 bases: every locus of a genome-wide catalog)
+/* Phase C runs the alleles of single-motif loci (one motif of 1..7 bases: every locus of a genome-wide catalog)
  * through kernels specialised per motif length (one lane per allele, score column in registers, one packed
  * back-pointer word per column); all other loci take the generic kernels.  Results are identical either way;
  * 0 sends every allele down the generic path (diagnostic).  Default on.  Applies to batches uploaded afterwards. */
@@ -220,6 +224,38 @@ int32_t trgt_consensus(trgt_engine_t *eng, const trgt_seqs_t *backbones, const t
 int32_t trgt_edit_dist(trgt_engine_t *eng, const trgt_seqs_t *seqs,
                        const uint32_t *locus_seq_offsets, uint32_t n_loci, double *dists_out);
 
+/* ---- cluster-genotyper glue between get_dist_matrix and make_consensus (next row, rank 3) ---- */
+
+/* For many loci: get_dist_matrix (genotype_cluster.rs:250-286), then cluster() (:154-227: Ward linkage of
+ * kodama::linkage on the distance matrix, the dendrogram cut that leaves both sides at least
+ * max(2, round(n / 100)) sequences, alternate split when there is none), the choice of the two largest groups
+ * (:64-69: stable sort by size, the last two) and central_read (:12-39) of each -- what genotype() needs to call
+ * make_consensus (:41-55) twice.
+ *   group_out[n_seqs]: 0 = member of group1 (the largest group), 1 = group2, 2 = neither (an outlier that
+ *     genotype() assigns to the closer consensus afterwards, :125-142)
+ *   central_out[2 * n_loci]: index within the locus of the backbone of group1 / group2, 0xFFFFFFFF when the locus
+ *     has no such group (fewer than two sequences)
+ *   n_groups_out[n_loci] (may be NULL): number of groups cluster() returned
+ * kodama (0.3.0) is not part of the reference tree: see DESIGN.md for what pins this row. */
+int32_t trgt_cluster(trgt_engine_t *eng, const trgt_seqs_t *seqs, const uint32_t *locus_seq_offsets, uint32_t n_loci,
+                     int32_t *group_out, uint32_t *central_out, uint32_t *n_groups_out);
+
+/* The same on the repeat sequences of a flank batch that has been run (batch == NULL: the last one-shot call),
+ * read where they lie in HBM: reads[locus_offsets[l] .. locus_offsets[l+1]) are the read indices (within the
+ * batch) of locus l's spanning reads in genotyping order (tr.rs:138-165: margin filter, stable sort by repeat
+ * length, down-sampling -- host logic on the spans).  Indices in group_out / central_out are positions in that
+ * per-locus list.  Nothing but the index lists crosses PCIe. */
+int32_t trgt_cluster_trs(trgt_engine_t *eng, trgt_flank_batch_t *batch, const uint32_t *reads,
+                         const uint32_t *locus_offsets, uint32_t n_loci, int32_t *group_out, uint32_t *central_out,
+                         uint32_t *n_groups_out);
+
+/* trgt_consensus with backbones and members named by read index of a flank batch (make_consensus :41-55 for many
+ * groups): the repeat sequences are gathered on the device, aligned and voted on; only the repaired consensuses
+ * come back. */
+int32_t trgt_consensus_trs(trgt_engine_t *eng, trgt_flank_batch_t *batch, const uint32_t *backbone_reads,
+                           const uint32_t *member_reads, const uint32_t *group_offsets, uint32_t n_groups,
+                           trgt_seqs_out_t *out);
+
 /* ---- phase C: motif HMM (a7-a13) ---------------------------------------- */
 
 typedef struct {
@@ -255,7 +291,6 @@ int32_t trgt_hmm_label(trgt_engine_t *eng, const trgt_seqs_t *motifs,
 /* ---- resident-batch interface (same phases, inputs kept in HBM) ---------- */
 
 /* upload once, run many times: lets a caller (and bench.py) separate PCIe from kernel time */
-typedef struct trgt_flank_batch trgt_flank_batch_t;
 int32_t trgt_flank_upload(trgt_engine_t *eng, const trgt_seqs_t *left_pieces,
                           const trgt_seqs_t *right_pieces, const trgt_seqs_t *reads,
                           const uint32_t *locus_read_offsets, uint32_t n_loci,
@@ -290,7 +325,6 @@ int32_t trgt_flank_fallback_counts(trgt_flank_batch_t *batch, uint32_t out[3]);
  * memory that stays valid until the next trgt_flank_trs on the same batch. */
 int32_t trgt_flank_trs(trgt_engine_t *eng, trgt_flank_batch_t *batch, trgt_seqs_out_t *out);
 
-typedef struct trgt_align_batch trgt_align_batch_t;
 int32_t trgt_align_upload(trgt_engine_t *eng, const trgt_seqs_t *backbones,
                           const trgt_seqs_t *seqs, const uint32_t *group_seq_offsets,
                           uint32_t n_groups, trgt_align_batch_t **out);
@@ -298,7 +332,6 @@ int32_t trgt_align_run(trgt_engine_t *eng, trgt_align_batch_t *batch);
 int32_t trgt_align_download(trgt_engine_t *eng, trgt_align_batch_t *batch, trgt_cigars_t *out);
 void trgt_align_free(trgt_engine_t *eng, trgt_align_batch_t *batch);
 
-typedef struct trgt_hmm_batch trgt_hmm_batch_t;
 int32_t trgt_hmm_upload(trgt_engine_t *eng, const trgt_seqs_t *motifs,
                         const uint32_t *locus_motif_offsets, uint32_t n_loci,
                         const trgt_seqs_t *alleles, const uint32_t *allele_locus,

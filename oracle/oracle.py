@@ -359,6 +359,41 @@ def get_dist_matrix(trs: Sequence[bytes]) -> List[float]:
     return [get_dist(trs[i], trs[j]) for i in range(n) for j in range(i + 1, n)]
 
 
+# ------------------------------------------------- next row: cluster-genotyper glue --
+
+class _LinkStep(C.Structure):
+    _fields_ = [("cluster1", C.c_uint32), ("cluster2", C.c_uint32), ("dissimilarity", C.c_double), ("size", C.c_uint32)]
+
+
+def ward_linkage(dists: Sequence[float], n: int):
+    """kodama::linkage(dists, n, Method::Ward) (genotype_cluster.rs:161)
+    -> ([(cluster1, cluster2, dissimilarity, size)], the condensed matrix as the call leaves it)"""
+    np = _np()
+    d = np.array(list(dists) + [0.0], dtype=np.float64)
+    steps = (_LinkStep * max(1, n - 1))()
+    L = lib()
+    L.tro_ward_linkage.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    if L.tro_ward_linkage(d.ctypes.data, n, steps) != 0:
+        raise MemoryError
+    return ([(steps[i].cluster1, steps[i].cluster2, steps[i].dissimilarity, steps[i].size) for i in range(max(0, n - 1))],
+            d[:-1])
+
+
+def cluster_locus(dists: Sequence[float], n: int):
+    """genotype() of genotype_cluster.rs:57-72 up to the make_consensus calls -> (sel[n]: 0 group1, 1 group2,
+    2 other; (central_read of group1, of group2 or None), number of groups)"""
+    np = _np()
+    d = np.array(list(dists) + [0.0], dtype=np.float64)
+    sel = np.zeros(max(1, n), dtype=np.uint8)
+    central = (C.c_uint32 * 2)()
+    L = lib()
+    L.tro_cluster_locus.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    ng = L.tro_cluster_locus(n, d.ctypes.data, sel.ctypes.data, central)
+    if ng < 0:
+        raise MemoryError
+    return sel[:n].tolist(), tuple(None if c == 0xFFFFFFFF else int(c) for c in central), ng
+
+
 # ------------------------------------------------- batched drivers (numpy) --
 
 def _np():

@@ -223,6 +223,23 @@ int tro_hmm_batch(const uint8_t *motifs, const uint64_t *motif_off, const uint32
 
 void tro_free(void *p);
 
+/* ---------------------------------------------- next row: cluster-genotyper glue (cluster_oracle.c) -- */
+
+typedef struct {
+  uint32_t cluster1, cluster2; /* cluster1 < cluster2; observations are 0..n-1, step i creates cluster n+i */
+  double dissimilarity;
+  uint32_t size;
+} tro_linkage_step;
+
+/* kodama::linkage(dists, n, Method::Ward) as called at genotype_cluster.rs:161; dists is modified in place */
+int tro_ward_linkage(double *dists, uint32_t n, tro_linkage_step *steps_out);
+/* cluster(): genotype_cluster.rs:154-227 -> number of groups, group_out[n] */
+int tro_cluster(uint32_t n, double *dists, uint32_t *group_out);
+/* central_read(): genotype_cluster.rs:12-39 */
+uint32_t tro_central_read(uint32_t num_seqs, const uint32_t *group, uint32_t group_size, const double *dists);
+/* genotype() :57-72 up to the make_consensus calls: group1 / group2 / others and their central reads */
+int tro_cluster_locus(uint32_t n, double *dists, uint8_t *sel_out, uint32_t *central_out);
+
 #ifdef __cplusplus
 }
 #endif

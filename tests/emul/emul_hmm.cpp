@@ -96,7 +96,7 @@ long emu_hmm_annotate_lanes(const uint8_t *motifs, const uint64_t *moff, int nm,
       std::vector<uint32_t> mc3(2, 0);                                                                           \
       std::vector<HmmSpan> sp3(a1.n_spans + 1);                                                                  \
       uint64_t plen3 = 0;                                                                                        \
-      const HmmAnnot a3 = hmm_walk_table(tab.data(), N, mb, allele, L, words.data(), stride, 6, mc3.data(),      \
+      const HmmAnnot a3 = hmm_walk_table(tab.data(), N, mb, L, words.data(), stride, 6, mc3.data(),      \
                                          HmmSpanArray{sp3.data()}, a1.n_spans, &plen3);                          \
       if (a3.status != 0 || a3.n_spans != a1.n_spans || plen3 != plen || mc3[0] != mc[0]) return -406;           \
       if (!(a3.purity == a1.purity || (a3.purity != a3.purity && a1.purity != a1.purity))) return -407;          \
@@ -106,7 +106,7 @@ long emu_hmm_annotate_lanes(const uint8_t *motifs, const uint64_t *moff, int nm,
     break;                                                                                                       \
   }
     switch (n) {
-      EMU_LANE(1) EMU_LANE(2) EMU_LANE(3) EMU_LANE(4) EMU_LANE(5) EMU_LANE(6) EMU_LANE(7) EMU_LANE(8)
+      EMU_LANE(1) EMU_LANE(2) EMU_LANE(3) EMU_LANE(4) EMU_LANE(5) EMU_LANE(6) EMU_LANE(7)
       default: return -405;
     }
 #undef EMU_LANE

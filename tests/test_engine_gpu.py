@@ -76,7 +76,7 @@ def test_hmm_random_parity_with_paths(engine, oracle):
 def test_hmm_pathogenic_catalog_shapes(engine, oracle):
     """BASELINE config 2 shapes: the 56 motif sets of repeats/pathogenic_repeats.hg38.bed (up to 10
     motifs, 170 states, N allowed)."""
-    from trgt_b200 import workload
+    from harness import workload
     sets = workload.pathogenic_motif_sets()
     w = workload.generate(len(sets), 4, motif_sets=sets, tr_len_median=60.0)
     rng = random.Random(5)
@@ -101,7 +101,7 @@ def test_hmm_long_allele_and_waves(engine, oracle):
 
 
 def test_hmm_lane_path_single_motif_loci(engine, oracle):
-    """Single-motif loci (motif of 1..8 bases) run through k_hmm_lane_* (score column in registers, one packed
+    """Single-motif loci (motif of 1..7 bases) run through k_hmm_lane_* (score column in registers, one packed
     back-pointer word per column, slots sorted by motif and allele length): MC / MS / AP and the state paths
     must be the oracle's, with the lane path on and off, in one wave and in several, mixed with loci the
     generic kernels take (several motifs, 12-base motifs, empty alleles)."""
@@ -152,6 +152,41 @@ def test_hmm_lane_path_single_motif_loci(engine, oracle):
     assert np.array_equal(a.purity, b.purity, equal_nan=True) and np.array_equal(a.paths, b.paths)
 
 
+# ------------------------------------------------------------------ cluster-genotyper glue ----
+
+def test_cluster_matches_oracle(engine, oracle):
+    """trgt_cluster (get_dist_matrix -> Ward linkage -> cluster() -> group1 / group2 -> central_read) against the
+    oracle on short repeat sequences (real edit distances, many ties), on long alleles (sqrt of the length
+    difference, BASELINE config 5 shape), on tiny loci and at max_depth (250 sequences)."""
+    rng = random.Random(97)
+    loci = []
+    for it in range(160):
+        kind = rng.random()
+        if kind < 0.5:      # two haplotypes of a short repeat, noisy copies
+            unit = rnd(rng, rng.randint(2, 6))
+            a, b = unit * rng.randint(3, 12), unit * rng.randint(3, 12)
+            n = rng.choice([1, 2, 3, 5, 12, 30, 40])
+            trs = [mutate(rng, a if rng.random() < 0.5 else b, rng.choice([0.0, 0.02, 0.08])) or b"A" for _ in range(n)]
+        elif kind < 0.9:    # long alleles: no alignment at all (len1 * len2 > 10000)
+            la, lb = rng.randint(300, 3000), rng.randint(300, 3000)
+            n = rng.choice([4, 20, 40, 41])
+            trs = [rnd(rng, (la if rng.random() < 0.6 else lb) + rng.randint(-6, 6)) for _ in range(n)]
+        else:
+            trs = [rnd(rng, rng.randint(1, 30)) for _ in range(rng.choice([100, 250]))]
+        loci.append(trs)
+    loci.append([])
+    got = engine.cluster(loci)
+    for trs, (sel, central, ng) in zip(loci, got):
+        n = len(trs)
+        if n == 0:
+            assert (sel, central, ng) == ([], (None, None), 0)
+            continue
+        d = oracle.get_dist_matrix(trs) if n >= 2 else []
+        exp = oracle.cluster_locus(d, n)
+        assert (sel, central, ng) == exp, (n, [len(t) for t in trs])
+    assert "k_cluster_ward" in engine.kernel_stats()
+
+
 # ------------------------------------------------------------------ phase A: flanks --------
 
 def _check_flanks(oracle, w, spans, hits, scoring, frac):
@@ -183,7 +218,7 @@ def _check_flanks(oracle, w, spans, hits, scoring, frac):
 def test_flank_spans_synthetic_hifi(engine, oracle, band_budget):
     """band_budget 20: misses settled by the on-chip banded path; 0: all by the full-width kernels;
     6: a mix.  All three must give the reference's answer."""
-    from trgt_b200 import workload
+    from harness import workload
     w = workload.generate(40, 12, seed=99)
     engine.set_flank_band_budget(band_budget)
     try:
@@ -223,7 +258,7 @@ def test_flank_spans_long_reads_and_repetitive_flanks(engine, oracle):
 def test_flank_spans_noisy_targeted_scoring(engine, oracle):
     """--preset targeted scoring (1,0,1), 0.8 identity, 200-bp pieces (cli.rs:271-302); noisy reads so
     that accepted, rejected and discordant cases all occur."""
-    from trgt_b200 import workload
+    from harness import workload
     w = workload.generate(24, 10, seed=5, context=260, piece=200, sub_rate=0.1, ins_rate=0.1, del_rate=0.1)
     spans, hits = engine.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, (1, 0, 1), 0.8)
     _check_flanks(oracle, w, spans, hits, (1, 0, 1), 0.8)
@@ -352,7 +387,7 @@ def test_kernels_actually_launched(engine):
 # ------------------------------------------------------------------ whole pass, other BASELINE configs ---
 
 def _pass_and_compare(engine, oracle, w):
-    from trgt_b200.pipeline import HotPath, compare_with_oracle, oracle_pass
+    from harness.pipeline import HotPath, compare_with_oracle, oracle_pass
     hp = HotPath(engine, w, want_hits=False, pinned_outputs=False)
     res = hp.run_e2e(copy=True)
     ref = oracle_pass(oracle, w, 4)
@@ -376,7 +411,7 @@ def _pass_and_compare(engine, oracle, w):
 def test_pass_pathogenic_catalog_config2(engine, oracle):
     """BASELINE config 2: the 56 loci of repeats/pathogenic_repeats.hg38.bed (motif sets from the committed
     fixture; up to 10 motifs and 170 HMM states per locus, N in motifs), synthetic 30x HiFi."""
-    from trgt_b200 import workload
+    from harness import workload
     sets = workload.pathogenic_motif_sets()
     w = workload.generate(len(sets), 30, motif_sets=sets, tr_len_median=60.0, seed=2)
     res = _pass_and_compare(engine, oracle, w)
@@ -386,7 +421,7 @@ def test_pass_pathogenic_catalog_config2(engine, oracle):
 def test_pass_long_expansions_config5_shape(engine, oracle):
     """BASELINE config 5 shape at test size: alleles of several kb (reads too long for the staged on-chip
     path, consensus pairs through the CTA-per-pair kernels, Viterbi over thousands of columns)."""
-    from trgt_b200 import workload
+    from harness import workload
     w = workload.generate(5, 6, tr_len_median=3000.0, tr_len_sigma=0.5, tr_len_min=1500, tr_len_max=9000, seed=8)
     assert int(np.diff(w.reads.offsets.astype(np.int64)).max()) > 4000
     _pass_and_compare(engine, oracle, w)
@@ -497,7 +532,8 @@ def test_seq4_decode_parity(engine, oracle):
 def test_flank_spans_seq4_matches_ascii_path(engine, oracle):
     """BAM 4-bit input gives the ASCII path's result bit for bit (and hence the oracle's: the ASCII path is
     checked against it above), one-shot and resident"""
-    from trgt_b200 import PackedSeq4, workload
+    from trgt_b200 import PackedSeq4
+    from harness import workload
     w = workload.generate(60, 14, seed=31)
     p4 = PackedSeq4.from_ascii([w.reads.get(r) for r in range(w.n_reads)])
     spans_a, hits_a = engine.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
@@ -529,7 +565,8 @@ def test_flank_spans_seq4_matches_ascii_path(engine, oracle):
 def test_flank_trs_are_the_span_slices(engine, oracle):
     """trgt_flank_trs = read.bases[span.0..span.1] per spanning read (tr.rs:58-62), for one-shot (ASCII and
     BAM 4-bit input) and resident batches; and the host glue fed with them builds the same phase B/C input."""
-    from trgt_b200 import PackedSeq4, workload
+    from trgt_b200 import PackedSeq4
+    from harness import workload
     w = workload.generate(50, 9, seed=77)
     p4 = PackedSeq4.from_ascii([w.reads.get(r) for r in range(w.n_reads)])
 
@@ -603,7 +640,8 @@ def test_vcf_fields_tutorial_and_random_parity(engine, oracle):
 
 
 def test_results_before_run_are_refused(engine):
-    from trgt_b200 import TrgtError, workload
+    from trgt_b200 import TrgtError
+    from harness import workload
     w = workload.generate(3, 4, seed=1)
     b = engine.flank_upload(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
     try:

@@ -33,8 +33,8 @@ class _Res:
 
 def _payload(n_loci, begin, count):
     from oracle import oracle as orc
-    from trgt_b200 import workload
-    from trgt_b200.pipeline import oracle_pass
+    from harness import workload
+    from harness.pipeline import oracle_pass
     from trgt_b200.shard import record_parts
     w = workload.generate(count, 8, locus_begin=begin, seed=31337)
     return np.concatenate(record_parts([_Res(oracle_pass(orc, w, 2))]))
@@ -76,7 +76,7 @@ def test_two_rank_gather_equals_single_process(tmp_path):
     expect = np.concatenate([_payload(n_loci, b[r], b[r + 1] - b[r]) for r in range(world)])
     assert np.array_equal(gathered, expect)
     # shards regenerate the catalog exactly: rank 1's first locus is locus b[1] of a single-process run
-    from trgt_b200 import workload
+    from harness import workload
     whole = workload.generate(n_loci, 8, seed=31337)
     part = workload.generate(b[2] - b[1], 8, locus_begin=b[1], seed=31337)
     assert part.reads.get(0) == whole.reads.get(b[1] * 8) and part.left.get(3) == whole.left.get(b[1] + 3)

@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import trgt_b200
-from trgt_b200 import workload
+from harness import workload
 from oracle import oracle as orc
 
 n_loci = int(sys.argv[1]) if len(sys.argv) > 1 else 20000

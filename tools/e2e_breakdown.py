@@ -4,9 +4,9 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import trgt_b200
-from trgt_b200 import workload
-from trgt_b200.pipeline import HotPath
-from trgt_b200.workload import GlueContext, genotype_glue
+from harness import workload
+from harness.pipeline import HotPath
+from harness.workload import GlueContext, genotype_glue
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 7813
 eng = trgt_b200.Engine(0)

@@ -2,8 +2,9 @@
 
 The package holds only what that path needs: csrc/ (hand-written sm_100a kernels + the C ABI of
 include/trgt_engine.h), engine.py (ctypes binding and the host-side mirror of the reference's
-find_tr_spans / align / get_dist_matrix / label_with_hmm), pipeline.py (the phase-structured pass
-bench.py times) and workload.py (synthetic HiFi inputs).  There is no CPU fallback.
+find_tr_spans / align / get_dist_matrix / label_with_hmm) and shard.py (locus shards and the record gather).
+Bench and test support (workloads, the phase pipeline, the stand-in host glue) lives in harness/.  There is no
+CPU fallback.
 """
 from .engine import (Annotation, AnnotationBatch, CigarBatch, CLIP_DTYPE, Engine, EXPORTS, PackedSeq4, PackedSeqs,
                      TrgtError,

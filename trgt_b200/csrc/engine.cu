@@ -84,6 +84,7 @@ struct trgt_engine {
   trgt_align_batch_t *one_align = nullptr;
   trgt_hmm_batch_t *one_hmm = nullptr;
   DevBuf d_ed[6];
+  DevBuf d_cl[5];  // cluster glue: scratch slots, group ids, central reads, group counts, read index
   size_t workspace_budget = (size_t)24 << 30;  // cap on back-pointer / trace workspace per wave
   int band_budget = 16;  // cost cap of the banded flank fallback (0: always use the full-width path)
   bool hmm_lane = true;  // single-motif loci take the register / packed-word HMM kernels (k_hmm_lane_*)
@@ -349,6 +350,7 @@ void trgt_engine_destroy(trgt_engine_t *e) {
   dev_free(e->d_mm_lp);
   dev_free(e->d_scan_tmp);
   for (auto &b : e->d_ed) dev_free(b);
+  for (auto &b : e->d_cl) dev_free(b);
   if (e->h_ctr) cudaFreeHost(e->h_ctr);
   if (e->h_u64) cudaFreeHost(e->h_u64);
   cudaStreamDestroy(e->stream);
@@ -1137,6 +1139,9 @@ void trgt_align_free(trgt_engine_t *e, trgt_align_batch_t *b) {
   delete b;
 }
 
+static int align_prepare(trgt_engine_t *e, trgt_align_batch *b, const uint32_t *group_seq_offsets, uint32_t n_groups,
+                         uint32_t n_seqs, int pm, int tm);
+
 static int align_upload_into(trgt_engine_t *e, trgt_align_batch *b, const trgt_seqs_t *backbones,
                              const trgt_seqs_t *seqs, const uint32_t *group_seq_offsets, uint32_t n_groups) {
   TRY(check_seqs(e, backbones, "backbones"));
@@ -1151,14 +1156,20 @@ static int align_upload_into(trgt_engine_t *e, trgt_align_batch *b, const trgt_s
   if (!n_groups && seqs->n) return fail(e, TRGT_ERR_ARG, "sequences without groups");
   const uint64_t pm = max_len(backbones), tm = max_len(seqs);
   if (pm + tm > 0x0fffffffull) return fail(e, TRGT_ERR_ARG, "sequence too long");
-  b->n_groups = n_groups;
-  b->n_seqs = (uint32_t)seqs->n;
-  b->Pmax = (int)pm;
-  b->Tmax = (int)tm;
-  b->ran = false;
   CU(e, cudaSetDevice(e->device));
   TRY(upload_seqs(e, backbones, b->bb, b->bb_off));
   TRY(upload_seqs(e, seqs, b->seqs, b->seq_off));
+  return align_prepare(e, b, group_seq_offsets, n_groups, (uint32_t)seqs->n, (int)pm, (int)tm);
+}
+
+// the rest of an align batch once backbones and member sequences are on the device (uploaded, or gathered there)
+static int align_prepare(trgt_engine_t *e, trgt_align_batch *b, const uint32_t *group_seq_offsets, uint32_t n_groups,
+                         uint32_t n_seqs, int pm, int tm) {
+  b->n_groups = n_groups;
+  b->n_seqs = n_seqs;
+  b->Pmax = pm;
+  b->Tmax = tm;
+  b->ran = false;
   static const uint32_t zero32[1] = {0};
   TRY(h2d(e, b->group_off, n_groups ? group_seq_offsets : zero32, ((size_t)n_groups + 1) * sizeof(uint32_t)));
   const size_t n = b->n_seqs;
@@ -1362,6 +1373,8 @@ int32_t trgt_align_e2e(trgt_engine_t *e, const trgt_seqs_t *backbones, const trg
 
 // ------------------------------------------------------------------ consensus (next row) ------
 
+static int consensus_run_locked(trgt_engine_t *e, trgt_align_batch *b, trgt_seqs_out_t *out);
+
 int32_t trgt_consensus(trgt_engine_t *e, const trgt_seqs_t *backbones, const trgt_seqs_t *seqs,
                        const uint32_t *group_seq_offsets, uint32_t n_groups, trgt_seqs_out_t *out) {
   if (!e || !out) return TRGT_ERR_ARG;
@@ -1369,6 +1382,12 @@ int32_t trgt_consensus(trgt_engine_t *e, const trgt_seqs_t *backbones, const trg
   if (!e->one_align) e->one_align = new trgt_align_batch();
   trgt_align_batch *b = e->one_align;
   TRY(align_upload_into(e, b, backbones, seqs, group_seq_offsets, n_groups));
+  return consensus_run_locked(e, b, out);
+}
+
+// utils::align + repair_consensus on an align batch whose sequences are in place
+static int consensus_run_locked(trgt_engine_t *e, trgt_align_batch *b, trgt_seqs_out_t *out) {
+  const uint32_t n_groups = b->n_groups;
   TRY(align_run_locked(e, b));  // CIGARs now sit in out_off / out_words on the device
   const size_t ng = n_groups;
   TRY(pin_reserve(e, b->h_cons_off, (ng + 1) * sizeof(uint64_t)));
@@ -1439,6 +1458,38 @@ int32_t trgt_consensus(trgt_engine_t *e, const trgt_seqs_t *backbones, const trg
 
 // ------------------------------------------------------------------ phase B: edit distance ---
 
+// get_dist_matrix of every locus into d_ed[4] (condensed, locus after locus at pair_off).  Sequences: d_seqs /
+// d_seq_off as a CSR set, or -- with d_index and d_spans -- the repeat sequences of a flank batch read in place.
+static int edit_dist_device(trgt_engine_t *e, const uint8_t *d_seqs, const uint64_t *d_seq_off, const uint32_t *d_index,
+                            const trgt_span_t *d_spans, const uint32_t *locus_seq_offsets, uint32_t n_loci, uint64_t n_seqs,
+                            unsigned long long *total_out, uint32_t *n_max_out) {
+  if (locus_seq_offsets[0] != 0 || locus_seq_offsets[n_loci] != n_seqs) return fail(e, TRGT_ERR_ARG, "locus_seq_offsets must cover all sequences");
+  std::vector<unsigned long long> pair_off((size_t)n_loci + 1, 0);
+  uint32_t n_max = 0;
+  for (uint32_t l = 0; l < n_loci; l++) {
+    if (locus_seq_offsets[l + 1] < locus_seq_offsets[l]) return fail(e, TRGT_ERR_ARG, "locus_seq_offsets not monotone");
+    const unsigned long long n = locus_seq_offsets[l + 1] - locus_seq_offsets[l];
+    pair_off[l + 1] = pair_off[l] + (n < 2 ? 0 : n * (n - 1) / 2);
+    if (n > n_max) n_max = (uint32_t)n;
+  }
+  const unsigned long long total = pair_off[n_loci];
+  *total_out = total;
+  if (n_max_out) *n_max_out = n_max;
+  TRY(h2d(e, e->d_ed[2], locus_seq_offsets, ((size_t)n_loci + 1) * sizeof(uint32_t)));
+  TRY(h2d(e, e->d_ed[3], pair_off.data(), pair_off.size() * sizeof(unsigned long long)));
+  TRY(dev_reserve(e, e->d_ed[4], (size_t)(total + 1) * sizeof(double)));
+  CU(e, cudaStreamSynchronize(e->stream));  // pair_off is a local
+  if (total == 0) return 0;
+  int grid = 0;
+  TRY(persistent_grid(e, k_edit_dist, 128, 0, &grid));
+  if ((uint32_t)grid > n_loci) grid = (int)n_loci;
+  LaunchScope ls(e, "k_edit_dist");
+  k_edit_dist<<<grid, 128, 0, e->stream>>>(d_seqs, d_seq_off, (const uint32_t *)e->d_ed[2].p,
+                                           (const unsigned long long *)e->d_ed[3].p, n_loci, (double *)e->d_ed[4].p,
+                                           d_index, d_spans);
+  return check_launch(e, "k_edit_dist");
+}
+
 int32_t trgt_edit_dist(trgt_engine_t *e, const trgt_seqs_t *seqs, const uint32_t *locus_seq_offsets, uint32_t n_loci,
                        double *dists_out) {
   if (!e) return TRGT_ERR_ARG;
@@ -1446,34 +1497,150 @@ int32_t trgt_edit_dist(trgt_engine_t *e, const trgt_seqs_t *seqs, const uint32_t
   TRY(check_seqs(e, seqs, "seqs"));
   if (n_loci && !locus_seq_offsets) return fail(e, TRGT_ERR_ARG, "locus_seq_offsets is null");
   if (n_loci == 0) return 0;
-  if (locus_seq_offsets[0] != 0 || locus_seq_offsets[n_loci] != seqs->n) return fail(e, TRGT_ERR_ARG, "locus_seq_offsets must cover all sequences");
-  std::vector<unsigned long long> pair_off((size_t)n_loci + 1, 0);
-  for (uint32_t l = 0; l < n_loci; l++) {
-    if (locus_seq_offsets[l + 1] < locus_seq_offsets[l]) return fail(e, TRGT_ERR_ARG, "locus_seq_offsets not monotone");
-    const unsigned long long n = locus_seq_offsets[l + 1] - locus_seq_offsets[l];
-    pair_off[l + 1] = pair_off[l] + (n < 2 ? 0 : n * (n - 1) / 2);
-  }
-  const unsigned long long total = pair_off[n_loci];
-  if (total == 0) return 0;
-  if (!dists_out) return fail(e, TRGT_ERR_ARG, "dists_out is null");
   CU(e, cudaSetDevice(e->device));
   TRY(upload_seqs(e, seqs, e->d_ed[0], e->d_ed[1]));
-  TRY(h2d(e, e->d_ed[2], locus_seq_offsets, ((size_t)n_loci + 1) * sizeof(uint32_t)));
-  TRY(h2d(e, e->d_ed[3], pair_off.data(), pair_off.size() * sizeof(unsigned long long)));
-  TRY(dev_reserve(e, e->d_ed[4], (size_t)total * sizeof(double)));
-  {
-    int grid = 0;
-    TRY(persistent_grid(e, k_edit_dist, 128, 0, &grid));
-    if ((uint32_t)grid > n_loci) grid = (int)n_loci;
-    LaunchScope ls(e, "k_edit_dist");
-    k_edit_dist<<<grid, 128, 0, e->stream>>>((const uint8_t *)e->d_ed[0].p, (const uint64_t *)e->d_ed[1].p,
-                                             (const uint32_t *)e->d_ed[2].p, (const unsigned long long *)e->d_ed[3].p,
-                                             n_loci, (double *)e->d_ed[4].p);
-    TRY(check_launch(e, "k_edit_dist"));
-  }
+  unsigned long long total = 0;
+  TRY(edit_dist_device(e, (const uint8_t *)e->d_ed[0].p, (const uint64_t *)e->d_ed[1].p, nullptr, nullptr,
+                       locus_seq_offsets, n_loci, seqs->n, &total, nullptr));
+  if (total == 0) return 0;
+  if (!dists_out) return fail(e, TRGT_ERR_ARG, "dists_out is null");
   CU(e, cudaMemcpyAsync(dists_out, e->d_ed[4].p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaStreamSynchronize(e->stream));
   return 0;
+}
+
+// ------------------------------------------------------------------ cluster-genotyper glue (next row, rank 3) ---
+
+// cluster() + group1 / group2 + central_read on the matrices edit_dist_device left in d_ed[4]
+static int cluster_device(trgt_engine_t *e, uint32_t n_loci, uint64_t n_seqs, uint32_t n_max, int32_t *group_out,
+                          uint32_t *central_out, uint32_t *n_groups_out) {
+  const int block = 128, wpb = 4;
+  int grid = 0;
+  TRY(persistent_grid(e, k_cluster_ward, block, 0, &grid));
+  const uint32_t need = (n_loci + wpb - 1) / wpb;
+  if ((uint32_t)grid > need) grid = (int)need;
+  const size_t stride = (cl_ws_bytes(n_max) + 15) & ~(size_t)15;
+  TRY(dev_reserve(e, e->d_cl[0], (size_t)grid * wpb * stride));
+  TRY(dev_reserve(e, e->d_cl[1], (size_t)(n_seqs + 1) * sizeof(int32_t)));
+  TRY(dev_reserve(e, e->d_cl[2], ((size_t)n_loci * 2 + 2) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, e->d_cl[3], ((size_t)n_loci + 1) * sizeof(uint32_t)));
+  {
+    LaunchScope ls(e, "k_cluster_ward");
+    k_cluster_ward<<<grid, block, 0, e->stream>>>((const uint32_t *)e->d_ed[2].p, (const unsigned long long *)e->d_ed[3].p,
+                                                  n_loci, (double *)e->d_ed[4].p, (unsigned char *)e->d_cl[0].p, stride,
+                                                  (int32_t *)e->d_cl[1].p, (uint32_t *)e->d_cl[2].p, (uint32_t *)e->d_cl[3].p);
+    TRY(check_launch(e, "k_cluster_ward"));
+  }
+  if (n_seqs) CU(e, cudaMemcpyAsync(group_out, e->d_cl[1].p, (size_t)n_seqs * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaMemcpyAsync(central_out, e->d_cl[2].p, (size_t)n_loci * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  if (n_groups_out) CU(e, cudaMemcpyAsync(n_groups_out, e->d_cl[3].p, (size_t)n_loci * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int32_t trgt_cluster(trgt_engine_t *e, const trgt_seqs_t *seqs, const uint32_t *locus_seq_offsets, uint32_t n_loci,
+                     int32_t *group_out, uint32_t *central_out, uint32_t *n_groups_out) {
+  if (!e) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  TRY(check_seqs(e, seqs, "seqs"));
+  if (n_loci && !locus_seq_offsets) return fail(e, TRGT_ERR_ARG, "locus_seq_offsets is null");
+  if (n_loci == 0) return 0;
+  if (!central_out || (seqs->n && !group_out)) return fail(e, TRGT_ERR_ARG, "trgt_cluster: null output");
+  CU(e, cudaSetDevice(e->device));
+  TRY(upload_seqs(e, seqs, e->d_ed[0], e->d_ed[1]));
+  unsigned long long total = 0;
+  uint32_t n_max = 0;
+  TRY(edit_dist_device(e, (const uint8_t *)e->d_ed[0].p, (const uint64_t *)e->d_ed[1].p, nullptr, nullptr,
+                       locus_seq_offsets, n_loci, seqs->n, &total, &n_max));
+  return cluster_device(e, n_loci, seqs->n, n_max, group_out, central_out, n_groups_out);
+}
+
+// read indices of a flank batch handed in by the caller: all in range
+static int check_read_index(trgt_engine_t *e, const trgt_flank_batch *b, const uint32_t *reads, uint64_t n, const char *what) {
+  if (n && !reads) return fail(e, TRGT_ERR_ARG, "%s: null read index", what);
+  for (uint64_t i = 0; i < n; i++)
+    if (reads[i] >= b->n_reads) return fail(e, TRGT_ERR_ARG, "%s: read %u out of range", what, reads[i]);
+  return 0;
+}
+
+int32_t trgt_cluster_trs(trgt_engine_t *e, trgt_flank_batch_t *b, const uint32_t *reads, const uint32_t *locus_offsets,
+                         uint32_t n_loci, int32_t *group_out, uint32_t *central_out, uint32_t *n_groups_out) {
+  if (!e) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!b) b = e->one_flank;
+  if (!b || (b->n_reads && !b->ran)) return fail(e, TRGT_ERR_ARG, "trgt_cluster_trs: the flank batch has not been run");
+  if (n_loci == 0) return 0;
+  if (!locus_offsets || !central_out) return fail(e, TRGT_ERR_ARG, "trgt_cluster_trs: null argument");
+  const uint64_t n_sel = locus_offsets[n_loci];
+  if (n_sel && !group_out) return fail(e, TRGT_ERR_ARG, "trgt_cluster_trs: null output");
+  TRY(check_read_index(e, b, reads, n_sel, "trgt_cluster_trs"));
+  CU(e, cudaSetDevice(e->device));
+  static const uint32_t zero32[1] = {0};
+  TRY(h2d(e, e->d_cl[4], n_sel ? reads : zero32, (size_t)(n_sel ? n_sel : 1) * sizeof(uint32_t)));
+  unsigned long long total = 0;
+  uint32_t n_max = 0;
+  TRY(edit_dist_device(e, (const uint8_t *)b->reads.p, (const uint64_t *)b->read_off.p, (const uint32_t *)e->d_cl[4].p,
+                       (const trgt_span_t *)b->spans.p, locus_offsets, n_loci, n_sel, &total, &n_max));
+  return cluster_device(e, n_loci, n_sel, n_max, group_out, central_out, n_groups_out);
+}
+
+int32_t trgt_consensus_trs(trgt_engine_t *e, trgt_flank_batch_t *fb, const uint32_t *backbone_reads,
+                           const uint32_t *member_reads, const uint32_t *group_offsets, uint32_t n_groups,
+                           trgt_seqs_out_t *out) {
+  if (!e || !out) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!fb) fb = e->one_flank;
+  if (!fb || (fb->n_reads && !fb->ran)) return fail(e, TRGT_ERR_ARG, "trgt_consensus_trs: the flank batch has not been run");
+  if (n_groups && (!group_offsets || !backbone_reads)) return fail(e, TRGT_ERR_ARG, "trgt_consensus_trs: null argument");
+  const uint32_t n_seqs = n_groups ? group_offsets[n_groups] : 0;
+  if (n_groups && group_offsets[0] != 0) return fail(e, TRGT_ERR_ARG, "group_offsets must start at 0");
+  for (uint32_t g = 0; g < n_groups; g++)
+    if (group_offsets[g + 1] < group_offsets[g]) return fail(e, TRGT_ERR_ARG, "group_offsets not monotone");
+  TRY(check_read_index(e, fb, backbone_reads, n_groups, "trgt_consensus_trs"));
+  TRY(check_read_index(e, fb, member_reads, n_seqs, "trgt_consensus_trs"));
+  CU(e, cudaSetDevice(e->device));
+  if (!e->one_align) e->one_align = new trgt_align_batch();
+  trgt_align_batch *b = e->one_align;
+  // Backbones and members are gathered on the device from the reads of the flank batch: index, lengths, scan, bytes.
+  // The two longest sequences size the wavefront rings: read back from the scans' inputs.
+  struct Part { const uint32_t *idx; uint32_t n; DevBuf *data, *off; int *mx; } parts[2] = {
+      {backbone_reads, n_groups, &b->bb, &b->bb_off, &b->Pmax}, {member_reads, n_seqs, &b->seqs, &b->seq_off, &b->Tmax}};
+  std::vector<trgt_span_t> h_spans(fb->n_reads ? fb->n_reads : 1);
+  if (fb->n_reads)
+    CU(e, cudaMemcpyAsync(h_spans.data(), fb->spans.p, (size_t)fb->n_reads * sizeof(trgt_span_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  int pm = 0, tm = 0;
+  for (int k = 0; k < 2; k++) {
+    Part &p = parts[k];
+    std::vector<unsigned long long> off((size_t)p.n + 1, 0);
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i < p.n; i++) {
+      const trgt_span_t sp = h_spans[p.idx[i]];
+      const uint32_t len = sp.found ? sp.end - sp.start : 0u;
+      off[i + 1] = off[i] + len;
+      if (len > mx) mx = len;
+    }
+    (k == 0 ? pm : tm) = (int)mx;
+    static const uint32_t zero32[1] = {0};
+    TRY(h2d(e, e->d_cl[4], p.n ? p.idx : zero32, (size_t)(p.n ? p.n : 1) * sizeof(uint32_t)));
+    TRY(h2d(e, *p.off, off.data(), off.size() * sizeof(unsigned long long)));
+    TRY(dev_reserve(e, *p.data, (size_t)off[p.n] + 16));
+    if (off[p.n]) {
+      int grid = 0;
+      TRY(persistent_grid(e, k_trs_gather, 256, 0, &grid));
+      const uint32_t need = (p.n + 7) / 8;
+      if ((uint32_t)grid > need) grid = (int)need;
+      LaunchScope ls(e, "k_trs_gather");
+      k_trs_gather<<<grid, 256, 0, e->stream>>>((const uint8_t *)fb->reads.p, (const uint64_t *)fb->read_off.p,
+                                                (const trgt_span_t *)fb->spans.p, (const uint32_t *)e->d_cl[4].p,
+                                                (const unsigned long long *)p.off->p, p.n, (uint8_t *)p.data->p);
+      TRY(check_launch(e, "k_trs_gather"));
+    }
+    CU(e, cudaStreamSynchronize(e->stream));  // `off` and the index buffer are reused by the next part
+  }
+  if ((uint64_t)pm + (uint64_t)tm > 0x0fffffffull) return fail(e, TRGT_ERR_ARG, "sequence too long");
+  TRY(align_prepare(e, b, group_offsets, n_groups, n_seqs, pm, tm));
+  return consensus_run_locked(e, b, out);
 }
 
 }  // extern "C"

@@ -888,6 +888,7 @@ TRGT_HD HmmAnnot hmm_annotate_bp(const M &m, const uint8_t *allele, int L, BP &b
 //   * ms and skip_ms always take in-edge 0 (rs): their other candidate me + ln(1/2) is one of the candidates
 //     re = rs was maximised over, so it can never be strictly greater (hmm_model.rs:84) -- this also makes
 //     ms = skip_ms = rs = re one carried value;
+//   * bits 30-31 of the word carry the column's base, so that the walk never reads the allele;
 //   * columns 0 and L+1 need no word at all: in column 0 only start, rs, ms, skip_ms are finite (in-edges 0),
 //     in column L+1 only `end` (one in-edge).
 // Adding ln(1.0) = +0.0 (lp_one, em_one, the emission of a silent state) leaves every score bit for bit as it
@@ -904,7 +905,9 @@ struct HmmLaneBits {
   static constexpr int RE = ME + 2;
   static constexpr int BITS = RE + 1;                        // 4 N for N >= 2
 };
-#define HMM_LANE_NMAX 8  // 4 N <= 32
+#define HMM_LANE_BASE 30  // two-bit code of the (sanitised) base the column emits, for the walk: it never reads the allele
+TRGT_HD uint32_t hmm_base_code(uint8_t b) { return ((uint32_t)b >> 1) & 3u; }  // A 0, C 1, T 2, G 3
+#define HMM_LANE_NMAX 7  // 4 N <= 28: bits 30-31 of a column's word carry the column's base (HMM_LANE_BASE)
 
 // first maximum, strict '>': `arg` of the reference's argmax whenever one candidate is finite
 #define TRGT_LANE_MAX2(a0, a1, best, arg)        \
@@ -950,7 +953,7 @@ TRGT_HD void hmm_viterbi_lane(const HmmConsts &c, const double *jump, uint64_t m
   for (int col = 1; col <= L; col++) {
     const uint8_t base = hmm_clean_base(base_next, (uint32_t)(col - 1));
     if (col < L) base_next = allele[col];
-    uint32_t w = 0;
+    uint32_t w = hmm_base_code(base) << HMM_LANE_BASE;
     const double em_q = c.em_quarter;
     double nM[N], nI[N];
     // ---- emitting states, from the previous column ----
@@ -1032,7 +1035,7 @@ TRGT_HD void hmm_viterbi_lane(const HmmConsts &c, const double *jump, uint64_t m
 // ... or one packed word per column (hmm_viterbi_lane).  The walk visits the columns in decreasing order, several
 // states per column: the word of the current column is kept, and the line a few columns further down is asked for
 // ahead of time (the 32 lanes of a warp share every line).
-#define HMM_LANE_PREFETCH 6
+#define HMM_LANE_PREFETCH 8
 template <int N>
 struct HmmBpWords {
   const uint32_t *w;
@@ -1111,30 +1114,44 @@ TRGT_HD HmmLaneEntry hmm_lane_table_entry(int n, int st) {
 // entries of motif length n).  Same walk, same results: purity, MC, collapsed spans (into the last n_spans of the
 // n_total slots of spans_out).  words: column c at words[(c - 1) * stride].
 template <class SP>
-TRGT_HD HmmAnnot hmm_walk_table(const HmmLaneEntry *tab, int n, uint64_t mbytes, const uint8_t *allele, int L,
-                                const uint32_t *words, int stride, int max_motif_len, uint32_t *mc,
-                                const SP &spans_out, uint32_t n_total, uint64_t *path_len) {
+TRGT_HD HmmAnnot hmm_walk_table(const HmmLaneEntry *tab, int n, uint64_t mbytes, int L, const uint32_t *words,
+                                int stride, int max_motif_len, uint32_t *mc, const SP &spans_out, uint32_t n_total,
+                                uint64_t *path_len) {
   HmmAnnot out;
   out.purity = 0.0; out.n_spans = 0; out.status = 0;
   const int S = 3 * n + 8;
-  uint32_t n_match = 0, n_mis = 0, n_ins = 0, n_del = 0, n_skip = 0;
+  // the motif as two-bit codes (bases i at bits 2 i), 'N' positions as a mask of the same shape
+  uint32_t mcodes = 0, nmask = 0;
+  for (int k = 0; k < n; k++) {
+    const uint8_t mb = (uint8_t)(mbytes >> (8 * k));
+    mcodes |= hmm_base_code(mb) << (2 * k);
+    if (mb == 'N') nmask |= 3u << (2 * k);
+  }
+  const uint32_t copy_mask = n < 16 ? (1u << (2 * n)) - 1u : ~0u;
+  uint32_t n_match = 0, n_mis = 0, n_ins = 0, n_del = 0, n_skip = 0, n_copies = 0;
   int st = S - 1, col = L + 1, last = -1;
   int copy_end = 0;
   bool have_p = false;
-  uint32_t p_motif = 0, p_start = 0, p_end = 0, emitted = 0;
+  uint32_t p_start = 0, p_end = 0, emitted = 0;
+  uint32_t recent = 0;  // the bases of the columns just left, newest at bits 0-1: at `ms` the copy's first bases
   uint64_t plen = 0;
   const uint64_t max_steps = ((uint64_t)L + 2) * (uint64_t)S + 2;
-  // words of column col and of the one below it (asked for one column ahead of its use)
+  // Words of column col and of the one below it.  A column is often left after a single step, so a load issued
+  // one column ahead would still be waited for at full latency: the lines further down (a warp's lanes share
+  // them) are pulled into L1 HMM_LANE_PREFETCH columns ahead of the walk.
+#if defined(__CUDA_ARCH__)
+  for (int c = L; c >= 1 && c > L - HMM_LANE_PREFETCH; c--)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(words + (size_t)(c - 1) * (size_t)stride));
+#endif
   uint32_t w_cur = 0, w_nxt = L >= 1 ? words[(size_t)(L - 1) * (size_t)stride] : 0u;
   while (st != 0) {
     if (++plen > max_steps) { out.status = -1; break; }
     const HmmLaneEntry t = tab[st];
     const int kind = (int)((t.y >> 16) & 255u), i = (int)(t.y >> 24);
     const bool emits = kind == HR_END || kind == HR_MATCH || kind == HR_INS || kind == HR_SKIP;
-    if (kind == HR_MATCH) {
-      const uint8_t expected = (uint8_t)(mbytes >> (8 * i));
-      const uint8_t base = hmm_clean_base(allele[col - 1], (uint32_t)(col - 1));
-      if (base == expected || expected == 'N') n_match++; else n_mis++;
+    if (kind == HR_MATCH) {  // base == expected || expected == 'N'  (events.rs:88-117)
+      const uint32_t d = (((w_cur >> HMM_LANE_BASE) ^ (mcodes >> (2 * i))) & ~(nmask >> (2 * i))) & 3u;
+      if (d == 0) n_match++; else n_mis++;
     }
     n_ins += kind == HR_INS ? 1u : 0u;
     n_skip += kind == HR_SKIP ? 1u : 0u;
@@ -1144,32 +1161,23 @@ TRGT_HD HmmAnnot hmm_walk_table(const HmmLaneEntry *tab, int n, uint64_t mbytes,
       const int copy_start = col;
       n_del += (uint32_t)(last - st - 1);  // jump-in to match_i counts i deletions, events.rs:44-46
       if (kind == HR_MS) {
-        bool keep = true;  // operations.rs:46-62
-        if (n <= max_motif_len) {
-          if (copy_end - copy_start < n) {
-            keep = false;
-          } else {
-            for (int k = 0; k < n; k++) {
-              const uint8_t expected = (uint8_t)(mbytes >> (8 * k));
-              const uint8_t observed = hmm_clean_base(allele[copy_start + k], (uint32_t)(copy_start + k));
-              if (expected != 'N' && observed != expected) keep = false;
-            }
-          }
-        }
+        // operations.rs:46-62: a copy of a short motif is kept only if its first n observed bases spell the motif
+        bool keep = true;
+        if (n <= max_motif_len) keep = copy_end - copy_start >= n && ((recent ^ mcodes) & ~nmask & copy_mask) == 0;
         if (keep) {
-          if (mc) mc[0]++;
-          if (have_p && p_motif == 0u && p_start == (uint32_t)copy_end) {
+          n_copies++;
+          if (have_p && p_start == (uint32_t)copy_end) {
             p_start = (uint32_t)copy_start;
           } else {
             if (have_p) {
               if (spans_out.on() && emitted < n_total) {
-                HmmSpan sp; sp.motif_index = p_motif; sp.start = p_start; sp.end = p_end;
+                HmmSpan sp; sp.motif_index = 0; sp.start = p_start; sp.end = p_end;
                 spans_out.put(n_total - 1 - emitted, sp);
               }
               emitted++;
             }
             have_p = true;
-            p_motif = 0u; p_start = (uint32_t)copy_start; p_end = (uint32_t)copy_end;
+            p_start = (uint32_t)copy_start; p_end = (uint32_t)copy_end;
           }
         }
       }
@@ -1179,18 +1187,24 @@ TRGT_HD HmmAnnot hmm_walk_table(const HmmLaneEntry *tab, int n, uint64_t mbytes,
     if (kind == HR_RS) arg = col > 0 ? 1u : 0u;
     const int p = (int)((t.x >> (8 * arg)) & 255u);
     if (emits) {
+      if (col <= L) recent = (recent << 2) | (w_cur >> HMM_LANE_BASE);
       col -= 1;
       w_cur = w_nxt;
       if (col >= 2) w_nxt = words[(size_t)(col - 2) * (size_t)stride];
+#if defined(__CUDA_ARCH__)
+      if (col > HMM_LANE_PREFETCH)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(words + (size_t)(col - 1 - HMM_LANE_PREFETCH) * (size_t)stride));
+#endif
     }
     last = st;
     st = p;
   }
   plen++;  // the start state
   if (path_len) *path_len = plen;
+  if (mc) mc[0] = n_copies;  // count_motifs (hmm/utils.rs:3-9): one motif
   if (have_p) {
     if (spans_out.on() && emitted < n_total) {
-      HmmSpan sp; sp.motif_index = p_motif; sp.start = p_start; sp.end = p_end;
+      HmmSpan sp; sp.motif_index = 0; sp.start = p_start; sp.end = p_end;
       spans_out.put(n_total - 1 - emitted, sp);
     }
     emitted++;

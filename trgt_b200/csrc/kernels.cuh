@@ -18,6 +18,7 @@
 
 #include "../../include/trgt_engine.h"
 #include "clip_core.h"
+#include "cluster_core.h"
 #include "consensus_core.h"
 #include "coop.h"
 #include "hmm_core.h"
@@ -961,10 +962,13 @@ k_consensus_vote(WfaSrc src, const uint32_t *__restrict__ group_off, uint32_t n_
 // ------------------------------------------------------------------ edit distance ---------
 
 // get_dist_matrix: one CTA per locus, threads stride the condensed pair index.
+// Sequence s of the batch is seqs[seq_off[s] .. seq_off[s+1]) -- or, with `index` and `spans` (the repeat
+// sequences of a resident flank batch, read in place), bytes [span.start, span.end) of read index[s].
 __global__ void __launch_bounds__(128)
 k_edit_dist(const uint8_t *__restrict__ seqs, const uint64_t *__restrict__ seq_off,
             const uint32_t *__restrict__ locus_seq_off, const unsigned long long *__restrict__ pair_off,
-            uint32_t n_loci, double *__restrict__ dists) {
+            uint32_t n_loci, double *__restrict__ dists, const uint32_t *__restrict__ index,
+            const trgt_span_t *__restrict__ spans) {
   for (uint32_t l = blockIdx.x; l < n_loci; l += gridDim.x) {
     const uint32_t s0 = locus_seq_off[l];
     const uint32_t n = locus_seq_off[l + 1] - s0;
@@ -981,10 +985,16 @@ k_edit_dist(const uint8_t *__restrict__ seqs, const uint64_t *__restrict__ seq_o
       while ((unsigned long long)(i + 1) * n - (unsigned long long)(i + 1) * (i + 2) / 2 <= q) i++;
       const unsigned long long row0 = (unsigned long long)i * n - (unsigned long long)i * (i + 1) / 2;
       const uint32_t j = (uint32_t)(i + 1 + (long long)(q - row0));
-      const uint8_t *a = seqs + seq_off[s0 + i];
-      const uint8_t *b = seqs + seq_off[s0 + j];
-      const int la = (int)(seq_off[s0 + i + 1] - seq_off[s0 + i]);
-      const int lb = (int)(seq_off[s0 + j + 1] - seq_off[s0 + j]);
+      const uint8_t *a, *b;
+      int la, lb;
+      if (index) {
+        const uint32_t ra = index[s0 + i], rb = index[s0 + j];
+        a = seqs + seq_off[ra] + spans[ra].start; la = (int)(spans[ra].end - spans[ra].start);
+        b = seqs + seq_off[rb] + spans[rb].start; lb = (int)(spans[rb].end - spans[rb].start);
+      } else {
+        a = seqs + seq_off[s0 + i]; la = (int)(seq_off[s0 + i + 1] - seq_off[s0 + i]);
+        b = seqs + seq_off[s0 + j]; lb = (int)(seq_off[s0 + j + 1] - seq_off[s0 + j]);
+      }
       int d;
       if ((unsigned long long)la * (unsigned long long)lb > 10000ull) {  // MAX_OPS, genotype_cluster.rs:237-243
         d = la > lb ? la - lb : lb - la;
@@ -993,6 +1003,52 @@ k_edit_dist(const uint8_t *__restrict__ seqs, const uint64_t *__restrict__ seq_o
       }
       dists[base + q] = sqrt((double)d);
     }
+  }
+}
+
+// cluster() + the choice of the two largest groups + central_read (genotype_cluster.rs:12-39,57-72,154-227) on the
+// distance matrices k_edit_dist left in HBM: one warp per locus (cluster_core.h), its scratch in a global slot.
+__global__ void __launch_bounds__(128)
+k_cluster_ward(const uint32_t *__restrict__ locus_seq_off, const unsigned long long *__restrict__ pair_off,
+               uint32_t n_loci, double *__restrict__ dists, unsigned char *__restrict__ ws, size_t ws_stride,
+               int32_t *__restrict__ group_out, uint32_t *__restrict__ central_out, uint32_t *__restrict__ n_groups_out) {
+  const WarpGroup g;
+  const uint32_t wib = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + wib, n_slots = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t l = slot; l < n_loci; l += n_slots) {
+    const uint32_t s0 = locus_seq_off[l];
+    const uint32_t n = locus_seq_off[l + 1] - s0;
+    const ClusterWs w = cl_carve(ws + (size_t)slot * ws_stride, n);
+    const int ng = cl_cluster_locus(g, dists + pair_off[l], n, w, group_out + s0, central_out + 2 * (size_t)l);
+    if (g.lane() == 0 && n_groups_out) n_groups_out[l] = (uint32_t)ng;
+    __syncwarp();
+  }
+}
+
+// The repeat sequences of selected reads of a flank batch as one CSR set (lengths first, then the bytes): what
+// the align / consensus kernels take, built without a trip through the host.
+__global__ void k_trs_len(const trgt_span_t *__restrict__ spans, const uint32_t *__restrict__ index, uint32_t n,
+                          uint32_t *__restrict__ len) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gsz) {
+    uint32_t v = 0;
+    if (i < n) { const trgt_span_t s = spans[index[i]]; v = s.found ? s.end - s.start : 0u; }
+    len[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_trs_gather(const uint8_t *__restrict__ reads, const uint64_t *__restrict__ read_off,
+             const trgt_span_t *__restrict__ spans, const uint32_t *__restrict__ index,
+             const unsigned long long *__restrict__ off, uint32_t n, uint8_t *__restrict__ out) {
+  const uint32_t wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  for (uint32_t i = blockIdx.x * wpb + warp; i < n; i += gridDim.x * wpb) {
+    const unsigned long long o = off[i];
+    const uint32_t len = (uint32_t)(off[i + 1] - o);
+    if (len == 0) continue;
+    const uint32_t r = index[i];
+    const uint8_t *src = reads + read_off[r] + spans[r].start;
+    for (uint32_t k = lane; k < len; k += 32u) out[o + k] = src[k];
   }
 }
 
@@ -1209,7 +1265,6 @@ struct HmmLaneBatch {
     case 5: F(5); break;      \
     case 6: F(6); break;      \
     case 7: F(7); break;      \
-    case 8: F(8); break;      \
     default: break;           \
   }
 
@@ -1258,7 +1313,7 @@ k_hmm_lane_walk(HmmLaneBatch lb, uint32_t g0, uint32_t g1, unsigned long long wo
   my_mc[0] = 0;
   const HmmSpanStrided sp{span_scratch ? (HmmSpan *)(span_scratch + lb.group_off[g] + lane) : nullptr, 32u};
   uint64_t plen = 0;
-  const HmmAnnot an = hmm_walk_table(tab[n], n, hmm_pack_motif(motif, n), lb.alleles + lb.allele_off[a], L,
+  const HmmAnnot an = hmm_walk_table(tab[n], n, hmm_pack_motif(motif, n), L,
                                      bp + (lb.group_off[g] - word_base) + lane, 32, 6, my_mc, sp, (uint32_t)L, &plen);
   purity[a] = an.purity;
   n_spans[a] = an.n_spans;

@@ -75,6 +75,7 @@ EXPORTS = [
     "trgt_clip_reads", "trgt_seq4_decode", "trgt_flank_spans_seq4", "trgt_flank_upload_seq4",
     "trgt_flank_trs", "trgt_vcf_fields",
     "trgt_flank_spans", "trgt_align_e2e", "trgt_consensus", "trgt_edit_dist", "trgt_hmm_label",
+    "trgt_cluster", "trgt_cluster_trs", "trgt_consensus_trs",
     "trgt_flank_upload", "trgt_flank_run", "trgt_flank_download", "trgt_flank_free", "trgt_flank_device_views",
     "trgt_flank_fallback_counts",
     "trgt_align_upload", "trgt_align_run", "trgt_align_download", "trgt_align_free",
@@ -116,6 +117,8 @@ def load_library(build: bool = True):
     L.trgt_engine_set_workspace_budget.restype = None
     L.trgt_engine_set_flank_band_budget.argtypes = [vp, i32]
     L.trgt_engine_set_flank_band_budget.restype = None
+    L.trgt_engine_set_hmm_lane_path.argtypes = [vp, i32]
+    L.trgt_engine_set_hmm_lane_path.restype = None
     L.trgt_host_alloc.argtypes = [C.c_size_t]
     L.trgt_host_alloc.restype = vp
     L.trgt_host_free.argtypes = [vp]
@@ -144,6 +147,9 @@ def load_library(build: bool = True):
     L.trgt_align_free.restype = None
     L.trgt_consensus.argtypes = [vp, sp, sp, vp, u32, C.POINTER(_SeqsOut)]
     L.trgt_edit_dist.argtypes = [vp, sp, vp, u32, vp]
+    L.trgt_cluster.argtypes = [vp, sp, vp, u32, vp, vp, vp]
+    L.trgt_cluster_trs.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
+    L.trgt_consensus_trs.argtypes = [vp, vp, vp, vp, vp, u32, C.POINTER(_SeqsOut)]
     L.trgt_hmm_label.argtypes = [vp, sp, vp, u32, sp, vp, i32, C.POINTER(_Annotations)]
     L.trgt_hmm_upload.argtypes = [vp, sp, vp, u32, sp, vp, i32, C.POINTER(vp)]
     L.trgt_hmm_run.argtypes = [vp, vp]
@@ -676,6 +682,60 @@ class Engine:
             out.append(flat[k:k + m].tolist())
             k += m
         return out
+
+    # -- cluster-genotyper glue (next row, rank 3) ------------------------------------------
+    def cluster_packed(self, seqs: PackedSeqs, locus_seq_offsets: np.ndarray):
+        """trgt_cluster -> (group int32[n_seqs]: 0 group1, 1 group2, 2 neither; central uint32[n_loci, 2];
+        n_groups uint32[n_loci])"""
+        lso = np.ascontiguousarray(locus_seq_offsets, dtype=np.uint32)
+        n_loci = lso.size - 1
+        group = np.zeros(max(1, len(seqs)), dtype=np.int32)
+        central = np.zeros((max(1, n_loci), 2), dtype=np.uint32)
+        ng = np.zeros(max(1, n_loci), dtype=np.uint32)
+        rc = self._L.trgt_cluster(self._h, seqs.ref(), lso.ctypes.data, n_loci, group.ctypes.data, central.ctypes.data,
+                                  ng.ctypes.data)
+        self._check(rc, "trgt_cluster")
+        return group[:len(seqs)], central[:n_loci], ng[:n_loci]
+
+    def cluster(self, loci_trs: Sequence[Sequence[bytes]]):
+        """cluster() + group1 / group2 + central_read (genotype_cluster.rs:12-39,57-72,154-227) for many loci
+        -> per locus (sel list, (central1, central2 or None), n_groups)"""
+        sq = PackedSeqs.from_list([s for trs in loci_trs for s in trs])
+        lso = _group_offsets(loci_trs)
+        group, central, ng = self.cluster_packed(sq, lso)
+        out = []
+        for l, trs in enumerate(loci_trs):
+            a, b = int(lso[l]), int(lso[l + 1])
+            out.append((group[a:b].tolist(), tuple(None if c == 0xFFFFFFFF else int(c) for c in central[l]), int(ng[l])))
+        return out
+
+    def cluster_trs(self, b, reads: np.ndarray, locus_offsets: np.ndarray):
+        """trgt_cluster_trs: the same on the repeat sequences of flank batch b (None: the last one-shot call),
+        named by read index"""
+        rd = np.ascontiguousarray(reads, dtype=np.uint32)
+        lo = np.ascontiguousarray(locus_offsets, dtype=np.uint32)
+        n_loci = lo.size - 1
+        group = np.zeros(max(1, rd.size), dtype=np.int32)
+        central = np.zeros((max(1, n_loci), 2), dtype=np.uint32)
+        ng = np.zeros(max(1, n_loci), dtype=np.uint32)
+        rc = self._L.trgt_cluster_trs(self._h, b, rd.ctypes.data if rd.size else None, lo.ctypes.data, n_loci,
+                                      group.ctypes.data, central.ctypes.data, ng.ctypes.data)
+        self._check(rc, "trgt_cluster_trs")
+        return group[:rd.size], central[:n_loci], ng[:n_loci]
+
+    def consensus_trs(self, b, backbone_reads: np.ndarray, member_reads: np.ndarray, group_offsets: np.ndarray):
+        """trgt_consensus_trs -> (PackedSeqs of one repaired consensus per group, status int32[n_groups])"""
+        bb = np.ascontiguousarray(backbone_reads, dtype=np.uint32)
+        mr = np.ascontiguousarray(member_reads, dtype=np.uint32)
+        go = np.ascontiguousarray(group_offsets, dtype=np.uint32)
+        out = _SeqsOut()
+        rc = self._L.trgt_consensus_trs(self._h, b, bb.ctypes.data if bb.size else None, mr.ctypes.data if mr.size else None,
+                                        go.ctypes.data, bb.size, C.byref(out))
+        self._check(rc, "trgt_consensus_trs")
+        n = int(out.n)
+        offs = _np_from(out.offsets, n + 1, np.uint64)
+        total = int(offs[n]) if n else 0
+        return PackedSeqs(_np_from(out.data, total, np.uint8), offs), _np_from(out.status, n, np.int32)
 
     # -- phase C ---------------------------------------------------------------------------
     def hmm_label_packed(self, motifs: PackedSeqs, locus_motif_offsets: np.ndarray, alleles: PackedSeqs,
