@@ -37,10 +37,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4],
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 2 = pathogenic catalog (56 loci, 30x), 3 = 100k-locus catalog, uniform 2-6 bp "
                          "motifs, 20x (strong scaling: the catalog is split over the GPUs), 4 = Adotto-scale catalog, 30x "
-                         "(125000 loci per GPU; the metric's config, default)")
+                         "(125000 loci per GPU; the metric's config, default), 5 = long expansions: alleles of 5-50 kb, 40x, cluster "
+                         "genotyper pass (1024 loci per GPU by default; --loci 10000 for the full catalog)")
     ap.add_argument("--loci", type=int, default=0, help="override the config's locus count (per GPU for config 4, total otherwise)")
     ap.add_argument("--depth", type=int, default=0, help="override the config's depth")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
@@ -69,7 +70,7 @@ class Spec:
     def __init__(self, args, world: int):
         self.config = args.config
         c = args.config
-        self.depth = args.depth or {2: 30, 3: 20, 4: 30}[c]
+        self.depth = args.depth or {2: 30, 3: 20, 4: 30, 5: 40}[c]
         self.gen = {}
         self.motif_sets = None
         if c == 4:     # weak scaling: 125 000 loci per GPU, 1 M at 8 GPUs
@@ -78,6 +79,13 @@ class Spec:
             self.scaling = "weak"
             self.name = "Adotto-scale genome-wide synthetic catalog shard (BASELINE config 4)"
             self.detail = "2-6 bp motifs (57/8/25/7/2 %), TR length median 24 bp"
+        elif c == 5:   # weak scaling like config 4; the cluster-genotyper pass (harness/cluster_pass.py)
+            self.loci_per_rank = args.loci or 1024
+            self.total = self.loci_per_rank * world
+            self.scaling = "weak"
+            self.gen = {"tr_len_dist": "loguniform", "tr_len_min": 5000, "tr_len_max": 50000, "het_independent": True}
+            self.name = "long-expansion stress catalog (BASELINE config 5), --genotyper cluster pass"
+            self.detail = "2-6 bp motifs, allele lengths log-uniform on 5-50 kb (heterozygous loci draw two lengths)"
         elif c == 3:   # strong scaling: one 100k-locus catalog split over the GPUs
             self.total = args.loci or 100000
             self.loci_per_rank = -(-self.total // world)
@@ -591,9 +599,176 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ config 5: the cluster-genotyper pass ----
+
+def run_cluster(args):
+    """BASELINE config 5.  One step = flank spans on 6-51 kb reads, spanning order, distance matrices + Ward clusters
+    + central reads, consensus of both groups, HMM on the 5-50 kb alleles (harness/cluster_pass.py).  `value`: reads
+    resident in HBM, CUDA events around the whole pass (the numpy glue between the phases included); `e2e`: the same
+    pass from host buffers (BAM 4-bit bases uploaded inside the timed region).  The reference arm runs the pass on
+    the oracle."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    spec = Spec(args, world if args.impl != "reference" else max(1, args.gpus))
+    cores = host_cores()
+    from harness.cluster_pass import compare_cluster_pass, engine_cluster_pass, oracle_cluster_pass
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import oracle as orc
+        n = max(4, min(spec.loci_per_rank, 2 * cores))
+        w = spec.generate(0, n)
+        for _ in range(args.warmup):
+            oracle_cluster_pass(orc, w, cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oracle_cluster_pass(orc, w, cores)
+        dt = (time.perf_counter() - t0) / max(1, args.steps)
+        value = w.n_loci / dt
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": spec.scaling,
+            "vs_baseline": None, "dtype": "int32 wavefront offsets + f64 Viterbi", "data": "synthetic",
+            "config": spec.describe(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"first {w.n_loci} loci of the shard per step ({w.n_reads} reads), all host cores"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import trgt_b200
+    from oracle import oracle as orc
+    eng = trgt_b200.Engine(device=local_rank)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.sync()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    w = spec.generate(rank, alloc_reads=eng.pinned_array)
+    w.pack_seq4(alloc=eng.pinned_array)
+    fb = eng.flank_upload(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+
+    def resident_pass():
+        return engine_cluster_pass(eng, w, orc_for_redo=orc, resident_batch=fb)
+
+    for _ in range(max(1, args.warmup)):
+        res = resident_pass()
+    eng.reset_stats()
+    eng.set_profiling(True)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    launches0 = eng.launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        res = resident_pass()
+    ev1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1) / max(1, args.steps))
+    launches_total = eng.launches() - launches0
+    stats = eng.kernel_stats()
+    eng.set_profiling(False)
+    eng.flank_free(fb)
+    # e2e: reads go up as BAM 4-bit bases inside the timed region
+    engine_cluster_pass(eng, w, orc_for_redo=orc, use_seq4=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_e2e = engine_cluster_pass(eng, w, orc_for_redo=orc, use_seq4=True)
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / max(1, args.steps))
+    clk = clocks.stop()
+    assert np.array_equal(res_e2e.alleles.data, res.alleles.data), "e2e and resident alleles differ"
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = spec.total / (dev_ms * 1e-3)
+    h2d = int(w.reads4.data.nbytes + w.reads4.starts.nbytes + w.reads4.lengths.nbytes + w.left.data.nbytes +
+              w.right.data.nbytes + 4 * res.sel_reads.size * 2 + res.alleles.data.nbytes)
+    d2h = int(res.spans.nbytes + 4 * res.sel_reads.size + res.alleles.data.nbytes + res.annotations.spans.nbytes)
+    # roofline of the dominant kernel: bytes it must move (every pair's two sequences once for the aligner, a read
+    # once for the flank search, a base and its back-pointer word once for the lane Viterbi)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    tr_len = (res.spans["end"].astype(np.int64) - res.spans["start"].astype(np.int64))
+    sel_len = tr_len[res.sel_reads]
+    allele_len = np.diff(res.alleles.offsets.astype(np.int64))
+    bytes_of = {
+        "k_wfa_score_block": float(2 * sel_len.sum() + 16 * sel_len.size),
+        "k_wfa_trace": float(2 * sel_len.sum()),
+        "k_flank_exact_t": float(w.reads.data.nbytes + 80.0 * w.n_reads),
+        "k_hmm_lane_viterbi": float(5 * allele_len.sum()),
+        "k_hmm_lane_walk": float(4 * allele_len.sum()),
+        "k_trs_gather": float(2 * sel_len.sum()),
+    }
+    kernels = {}
+    tot = sum(ms for _, ms in stats.values())
+    for name, (n, ms) in stats.items():
+        per = ms / max(1, n)
+        b = bytes_of.get(name)
+        kernels[name] = {"launches_per_step": n / max(1, args.steps), "ms_per_launch": per, "share": ms / tot if tot else None,
+                         "algorithmic_bytes": b, "achieved_gbs": (b / (per * 1e-3) / 1e9) if (b and per > 0) else None}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches_per_step"])
+    d = kernels[dom]
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": (d["achieved_gbs"] / peak) if d["achieved_gbs"] else None, "traffic": None,
+                "ms_per_launch": d["ms_per_launch"], "share_of_step": d["share"],
+                "algorithmic_bytes_per_launch": d["algorithmic_bytes"],
+                "note": "wavefront alignment of ~20 kb pairs is compute / latency bound (O(L s) cells on a few hundred "
+                        "diagonals); the byte figure is what the kernel must read"}
+    cpu = parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        n = max(4, min(w.n_loci, 2 * cores))
+        ws = w.head(n)
+        t0 = time.perf_counter()
+        ref = oracle_cluster_pass(orc, ws, cores)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {n} loci of the shard ({ws.n_reads} reads), one pass in {dt:.1f} s, all host cores"}
+        compare_cluster_pass(engine_cluster_pass(eng, ws, orc_for_redo=orc, use_seq4=True), ref)
+        parity = {"checked_loci": n, "result": "bit-exact vs oracle (spans, clusters, central reads, alleles, MC, MS, AP)"}
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": spec.scaling, "vs_baseline": None,
+        "dtype": "int32 wavefront offsets + f64 Viterbi", "data": "synthetic", "config": spec.describe(world),
+        "clocks": clk, "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches_total // max(1, args.steps)),
+        "e2e": {"value": spec.total / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "reads_in": "BAM 4-bit bases (trgt_flank_upload_seq4), decoded on the device"},
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "kernels": kernels,
+        "outlier_redo_loci": int(res.redone.size)}))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
-    if args.impl == "reference":
+    if args.config == 5:
+        run_cluster(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -61,6 +61,7 @@ typedef struct {
   uint32_t threads;
   uint32_t motif_mix;       // 0: motif length mix of the genome-wide catalog (57/8/25/7/2 % for 2..6 bp); 1: uniform 2..6 bp
   uint32_t tr_len_dist;     // 0: lognormal(median, sigma) clipped to [min, max]; 1: log-uniform on [min, max]
+  uint32_t het_independent; // 1: the second haplotype of a heterozygous locus draws its own tract length (expansions)
 } synth_params;
 
 typedef struct {
@@ -108,22 +109,31 @@ void make_locus(const synth_params &p, uint32_t gl, LocusDesc &d) {
     d.motifs.push_back(m);
   }
   // repeat tract: copies of the motifs (N in a catalog motif becomes a concrete base)
-  double len = p.tr_len_dist == 1
-                   ? exp(log((double)p.tr_len_min) + r.uni() * (log((double)p.tr_len_max) - log((double)p.tr_len_min)))
-                   : p.tr_len_median * exp(p.tr_len_sigma * r.gauss());
-  if (len < p.tr_len_min) len = p.tr_len_min;
-  if (len > p.tr_len_max) len = p.tr_len_max;
+  auto draw_len = [&]() {
+    double len = p.tr_len_dist == 1
+                     ? exp(log((double)p.tr_len_min) + r.uni() * (log((double)p.tr_len_max) - log((double)p.tr_len_min)))
+                     : p.tr_len_median * exp(p.tr_len_sigma * r.gauss());
+    if (len < p.tr_len_min) len = p.tr_len_min;
+    if (len > p.tr_len_max) len = p.tr_len_max;
+    return len;
+  };
   const size_t nm = d.motifs.size();
-  std::vector<uint32_t> copies(nm);
-  for (size_t m = 0; m < nm; m++) {
-    const double share = len / (double)nm;
-    uint32_t c = (uint32_t)(share / (double)d.motifs[m].size() + 0.5);
-    copies[m] = c < 2 ? 2 : c;
-  }
+  auto copies_of = [&](double len) {
+    std::vector<uint32_t> copies(nm);
+    for (size_t m = 0; m < nm; m++) {
+      const double share = len / (double)nm;
+      uint32_t c = (uint32_t)(share / (double)d.motifs[m].size() + 0.5);
+      copies[m] = c < 2 ? 2 : c;
+    }
+    return copies;
+  };
+  const std::vector<uint32_t> copies = copies_of(draw_len());
   const bool het = r.uni() < p.het_frac;
   for (int h = 0; h < 2; h++) {
     std::vector<uint32_t> c = copies;
-    if (h == 1 && het) {
+    if (h == 1 && het && p.het_independent) {
+      c = copies_of(draw_len());
+    } else if (h == 1 && het) {
       const size_t m = r.below((uint32_t)nm);
       const int k = 1 + (int)r.below(3);
       if (r.uni() < 0.5 && c[m] > (uint32_t)k + 1) c[m] -= k; else c[m] += k;

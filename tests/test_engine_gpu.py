@@ -427,6 +427,51 @@ def test_pass_long_expansions_config5_shape(engine, oracle):
     _pass_and_compare(engine, oracle, w)
 
 
+def test_pass_long_expansions_config5_at_size(engine, oracle):
+    """BASELINE config 5 at its own sizes: 16 loci, 40x, alleles of 20-50 kb (heterozygous loci draw two
+    independent lengths), the cluster-genotyper pass -- flank spans on 21-51 kb reads, spanning order, distance
+    matrices + Ward clusters + central reads, consensus of both groups (20 alignments of ~35 kb each, repaired),
+    HMM on 20-50 kb alleles -- against the same pass on the oracle.  Run twice: reads resident from ASCII with the
+    lane HMM kernels, and from BAM 4-bit bases with the generic HMM kernels in several back-pointer waves."""
+    from harness import workload
+    from harness.cluster_pass import compare_cluster_pass, engine_cluster_pass, oracle_cluster_pass
+    w = workload.generate(16, 40, seed=505, tr_len_dist="loguniform", tr_len_min=20000, tr_len_max=50000,
+                          het_independent=True)
+    assert int(np.diff(w.alleles.offsets.astype(np.int64)).min()) >= 19000
+    ref = oracle_cluster_pass(oracle, w, n_threads=os.cpu_count() or 1)
+    assert ref.sel_off[-1] > 0.8 * w.n_reads and len(ref.alleles) == 32
+    engine.reset_stats()
+    compare_cluster_pass(engine_cluster_pass(engine, w, orc_for_redo=oracle), ref)
+    stats = engine.kernel_stats()
+    for k in ("k_cluster_ward", "k_trs_gather", "k_wfa_score_block", "k_wfa_trace", "k_consensus_vote_write", "k_hmm_lane_viterbi"):
+        assert k in stats, (k, sorted(stats))
+    w.pack_seq4()
+    engine.set_hmm_lane_path(False)
+    engine.set_workspace_budget(8 << 20)   # one wavefront ring of a 50 kb pair is 4.3 MB; the back-pointers are 19 MB
+    try:
+        engine.reset_stats()
+        compare_cluster_pass(engine_cluster_pass(engine, w, orc_for_redo=oracle, use_seq4=True), ref)
+        stats = engine.kernel_stats()
+        assert stats["k_hmm_viterbi_thread"][0] >= 3 and "k_unpack_seq4" in stats
+    finally:
+        engine.set_hmm_lane_path(True)
+        engine.set_workspace_budget(24 << 30)
+
+
+def test_cluster_pass_outlier_rule_and_small_loci(engine, oracle):
+    """the cluster pass on short repeats at low depth: loci with 0 / 1 / 2 spanning reads, real edit distances,
+    and the outlier rule (a group 4x smaller and within 100 bp -> alternate split, genotype_cluster.rs:84-111)"""
+    from harness import workload
+    from harness.cluster_pass import compare_cluster_pass, engine_cluster_pass, oracle_cluster_pass
+    seen_redo = 0
+    for seed, depth in ((3, 1), (4, 2), (5, 3), (6, 12), (7, 30)):
+        w = workload.generate(48, depth, seed=seed, tr_len_median=30.0, unit_indel_rate=0.05, sub_rate=0.004)
+        ref = oracle_cluster_pass(oracle, w, n_threads=4)
+        compare_cluster_pass(engine_cluster_pass(engine, w, orc_for_redo=oracle), ref)
+        seen_redo += ref.redone.size
+    assert seen_redo > 0
+
+
 def test_hmm_locus_without_motifs_and_single_base_motif(engine, oracle):
     loci = [([], [b"ACGTACGT", b"A"]), ([b"A"], [b"AAAAAAA", b"AAACAAA", b""]), ([b"N"], [b"ACGT"])]
     _check_annotations(oracle, loci, engine.label_with_hmm(loci))
