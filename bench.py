@@ -255,14 +255,34 @@ def kernel_bytes(name: str, w, hp, res) -> float | None:
         pend_reads = pend.any(axis=1)
         if name == "k_flank_band":  # hit records scanned, pending reads re-read once, pieces once per locus, hits rewritten
             return float(40.0 * n_reads + read_len[pend_reads].sum() + 2.0 * P * w.n_loci + 20.0 * pend.sum())
-        return None
-    if name == "k_hmm_viterbi_thread":
+        n_pairs = {"k_flank_band2": hp.fallback_counts()[0], "k_flank_band_wide": hp.fallback_counts()[1]}[name]
+        # per pair handed on: its read and piece once, the piece's 8-mer table (1 KB), the work-list entry, the hit
+        return float(n_pairs * (read_len.mean() + P + 1024.0 + 4.0 + 20.0))
+    if name in ("k_hmm_viterbi_thread", "k_hmm_viterbi"):
         L = np.diff(g.backbones.offsets.astype(np.int64)).astype(np.float64)
         nm = np.diff(w.locus_motif_off.astype(np.int64))[g.group_locus]
         mlen = np.diff(w.motifs.offsets.astype(np.int64))
         first = w.locus_motif_off[:-1][g.group_locus]
         S = 7.0 + 3.0 * mlen[first] + 1.0          # one motif per locus in this catalog
         return float(((L + 2) * (1.0 + S) + mlen[first] + 8.0 * nm).sum())
+    if name in ("k_hmm_lane_viterbi", "k_hmm_lane_walk", "k_hmm_lane_spans"):
+        L = np.diff(g.backbones.offsets.astype(np.int64)).astype(np.float64)
+        a = res.annotations
+        if name == "k_hmm_lane_viterbi":   # every base once, one packed back-pointer word per column, motif + slot + status
+            return float((L * (1.0 + 4.0)).sum() + 24.0 * L.size)
+        if name == "k_hmm_lane_walk":      # the words once, MC / purity / span count / scratch spans out
+            return float((4.0 * L).sum() + (4.0 + 8.0 + 4.0 + 8.0) * L.size + 12.0 * a.spans.shape[0])
+        return float(24.0 * a.spans.shape[0] + 16.0 * L.size)
+    if name in ("k_e2e_thread", "k_wfa_score_warp", "k_cigar_gather") and res.cigars is not None:
+        c = res.cigars
+        slen = np.diff(g.seqs.offsets.astype(np.int64)).astype(np.float64)
+        blen = np.diff(g.backbones.offsets.astype(np.int64)).astype(np.float64)[
+            np.repeat(np.arange(len(g.backbones)), np.diff(g.group_seq_off.astype(np.int64)))]
+        nw = np.diff(c.offsets.astype(np.int64)).astype(np.float64)
+        if name == "k_cigar_gather":       # every CIGAR word read from the pool and written in CSR order, end / offsets / score / status
+            return float(8.0 * nw.sum() + (16.0 + 8.0 + 8.0 + 8.0) * nw.size)
+        sel = (c.scores != 0) if name == "k_e2e_thread" else (c.scores < -8)   # members that differ / cost above the lane cap
+        return float((slen[sel] + blen[sel] + 4.0 * nw[sel] + 16.0 + 4.0).sum())
     if name == "k_e2e_identity":  # every member and its backbone once, one end record and its CIGAR words per member
         per_seq_bb = np.diff(g.backbones.offsets.astype(np.int64))[
             np.repeat(np.arange(len(g.backbones)), np.diff(g.group_seq_off.astype(np.int64)))]
@@ -505,6 +525,35 @@ def run_b200(args):
         except Exception as exc:  # never let the extra row break the headline line
             consensus = {"error": repr(exc)}
 
+    # ---- a14 (filter_impure_trs, tr.rs:400-452): the HMM on every spanning READ's repeat sequence, timed on its own ----
+    a14 = None
+    if world == 1:
+        try:
+            trs = eng.flank_trs(hp._fb, copy=True)
+            read_locus = np.repeat(np.arange(w.n_loci, dtype=np.uint32), np.diff(w.locus_read_off.astype(np.int64)))
+            eng.hmm_label_packed(w.motifs, w.locus_motif_off, trs, read_locus, copy=False)  # warm-up
+            eng.reset_stats()
+            eng.set_profiling(True)
+            t0 = time.perf_counter()
+            ann = eng.hmm_label_packed(w.motifs, w.locus_motif_off, trs, read_locus, copy=False)
+            dt = time.perf_counter() - t0
+            st = eng.kernel_stats()
+            eng.set_profiling(False)
+            a14 = {"call": "trgt_hmm_label on the repeat sequence of every read (D x per-read HMM of the targeted preset), "
+                           "host buffers in and out", "sequences": len(trs), "ms": dt * 1e3, "sequences_per_s": len(trs) / dt,
+                   "kernel_ms": {k: v[1] for k, v in st.items() if k.startswith("k_hmm")}}
+            if not args.no_cpu_baseline:
+                from oracle import oracle as orc
+                nchk, same = 3000, 0
+                pur = np.array(ann.purity[:nchk])
+                for r in range(nchk):
+                    h = orc.Hmm([orc.replace_invalid_bases(m, b"ATCGN") for m in w.locus_motifs(int(read_locus[r]))])
+                    e_p = h.annotate(trs.get(r))[2]
+                    same += (pur[r] == e_p) or (np.isnan(pur[r]) and np.isnan(e_p))
+                a14["parity"] = f"{int(same)}/{nchk} purities identical to the oracle"
+        except Exception as exc:  # never let the extra row break the headline line
+            a14 = {"error": repr(exc)}
+
     # ---- next row: VCF sample fields encoded behind phase C, timed on its own ----
     vcf = None
     if world == 1:
@@ -587,7 +636,8 @@ def run_b200(args):
                 "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),
                 "reads_in": "BAM 4-bit bases (trgt_flank_spans_seq4), decoded on the device" if use_seq4 else "ASCII (trgt_flank_spans)",
                 "glue_threads": glue_threads, "phase_ms_summed_over_host_threads": e2e_phases},
-        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "clip_row": clip, "vcf_row": vcf, "kernels": kernels,
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "clip_row": clip, "vcf_row": vcf,
+        "a14_row": a14, "kernels": kernels,
         "wfa_fallback_pairs": hp.n_wfa(), "flank_fallback_counts": dict(zip(("second_tier", "wide_band", "full_width"), hp.fallback_counts())),
         "workload_gen_s": t_gen,
     }

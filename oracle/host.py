@@ -441,6 +441,30 @@ def genotype_flank(reads: List[HiFiRead], trs: List[bytes], backend):
     return gt, alleles, assign
 
 
+def filter_impure_trs(purities: Sequence[float], read_quals: Sequence[Optional[float]], rq_cutoff: float = 0.9,
+                      purity_cutoff: float = 0.9) -> List[int]:
+    """filter_impure_trs (tr.rs:400-452), the part after the HMM: purities[i] is calc_purity of read i's repeat
+    sequence (only looked at for reads with rq < rq_cutoff or without rq; the others count as 1.0).  Returns the
+    indices of the reads that are kept, in the order the reference returns them (sorted by purity, total_cmp,
+    stable); at most max(1, round(0.1 n)) reads below the cutoff are dropped, the least pure first."""
+    n = len(purities)
+    max_filter = max(1, int(math.floor(0.1 * n + 0.5)))
+    eff = [1.0 if (rq is not None and rq >= rq_cutoff) else p for p, rq in zip(purities, read_quals)]
+
+    def total_key(x: float):  # f64::total_cmp: -NaN < -inf < ... < +inf < +NaN
+        bits = struct.unpack("<q", struct.pack("<d", x))[0]
+        return bits ^ (((bits >> 63) & 0xFFFFFFFFFFFFFFFF) >> 1) if bits < 0 else bits
+
+    order = sorted(range(n), key=lambda i: total_key(eff[i]))
+    kept, filtered = [], 0
+    for i in order:
+        if eff[i] >= purity_cutoff or filtered >= max_filter:
+            kept.append(i)
+        else:
+            filtered += 1
+    return kept
+
+
 # ------------------------------------------------------------------ the per-locus worker ----------
 
 @dataclass

@@ -17,15 +17,37 @@ _LIB_PATH = os.path.join(_HERE, "libtrgt_oracle.so")
 INDEL, EDIT, LINEAR, AFFINE, AFFINE2P = 0, 1, 2, 3, 4
 
 
+def _cpu_stamp() -> str:
+    """identifies the host CPU: the library is compiled with -march=native (CPU baseline of bench.py)"""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force: bool = False) -> str:
-    """Compile oracle/*.c into libtrgt_oracle.so (gcc via oracle/Makefile)."""
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    """Compile oracle/*.c into libtrgt_oracle.so (gcc via oracle/Makefile, -O3 -march=native): rebuilt when a source
+    is newer or when the library was built on a different CPU (it travels to the GPU box with the snapshot)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
+    stamp_path = os.path.join(_HERE, ".build_cpu")
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
     )
-    if force or stale:
+    try:
+        with open(stamp_path) as f:
+            built_for = f.read().strip()
+    except OSError:
+        built_for = ""
+    if force or stale or built_for != _cpu_stamp():
         subprocess.run(["make", "-C", _HERE, "-B", "libtrgt_oracle.so"], check=True,
                        stdout=subprocess.DEVNULL)
+        with open(stamp_path, "w") as f:
+            f.write(_cpu_stamp())
     return _LIB_PATH
 
 

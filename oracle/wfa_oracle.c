@@ -48,6 +48,45 @@ static inline int wf_present(const wf_hist *H, int s, int c) {
 static inline int imax(int a, int b) { return a > b ? a : b; }
 static inline int imin(int a, int b) { return a < b ? a : b; }
 
+/* Wavefront offsets come from a per-thread slab that is reused from one alignment to the next (as WFA2-lib's
+ * mm_allocator does), not from one malloc per wavefront component. */
+typedef struct slab_chunk {
+  struct slab_chunk *next;
+  size_t cap, used;
+} slab_chunk;
+static __thread slab_chunk *tl_slab = NULL;    /* chunks of this thread, the first one is the current one */
+static __thread slab_chunk *tl_slab_free = NULL;
+
+static int *slab_ints(size_t n) {
+  const size_t bytes = (n * sizeof(int) + 15) & ~(size_t)15;
+  if (!tl_slab || tl_slab->used + bytes > tl_slab->cap) {
+    slab_chunk *c = NULL, **pp = &tl_slab_free;
+    while (*pp && (*pp)->cap < bytes) pp = &(*pp)->next;
+    if (*pp) {
+      c = *pp;
+      *pp = c->next;
+    } else {
+      const size_t cap = bytes > ((size_t)4 << 20) ? bytes : ((size_t)4 << 20);
+      c = (slab_chunk *)malloc(sizeof(slab_chunk) + cap);
+      c->cap = cap;
+    }
+    c->used = 0;
+    c->next = tl_slab;
+    tl_slab = c;
+  }
+  int *p = (int *)((char *)(tl_slab + 1) + tl_slab->used);
+  tl_slab->used += bytes;
+  return p;
+}
+static void slab_reset(void) { /* everything back to the free list; the memory stays with the thread */
+  while (tl_slab) {
+    slab_chunk *c = tl_slab;
+    tl_slab = c->next;
+    c->next = tl_slab_free;
+    tl_slab_free = c;
+  }
+}
+
 static wf_t *hist_push(wf_hist *H) {
   if (H->n == H->cap) {
     H->cap = H->cap ? H->cap * 2 : 64;
@@ -60,8 +99,7 @@ static wf_t *hist_push(wf_hist *H) {
   return w;
 }
 static void hist_free(wf_hist *H) {
-  for (int s = 0; s < H->n; s++)
-    for (int c = 0; c < N_COMP; c++) free(H->wf[s].off[c]);
+  slab_reset();
   free(H->wf);
 }
 
@@ -70,10 +108,25 @@ static void extend(wf_t *w, const uint8_t *p, int P, const uint8_t *t, int T) {
     int h = w->off[C_M][k - w->lo];
     if (h < 0) continue;
     int v = h - k;
+    while (v + 8 <= P && h + 8 <= T) { /* eight bases per step, as WFA2-lib's extend kernel compares blocks */
+      uint64_t a, b;
+      memcpy(&a, p + v, 8);
+      memcpy(&b, t + h, 8);
+      const uint64_t d = a ^ b;
+      if (d) {
+        const int m = __builtin_ctzll(d) >> 3;
+        v += m;
+        h += m;
+        goto done;
+      }
+      v += 8;
+      h += 8;
+    }
     while (v < P && h < T && p[v] == t[h]) {
       v++;
       h++;
     }
+  done:
     w->off[C_M][k - w->lo] = h;
   }
 }
@@ -159,7 +212,7 @@ int tro_wfa_align(const tro_wfa_params *prm, const uint8_t *p, int P, const uint
       w->lo = 0;
       w->hi = 0;
     }
-    w->off[C_M] = (int *)malloc(sizeof(int) * (size_t)(w->hi - w->lo + 1));
+    w->off[C_M] = slab_ints((size_t)(w->hi - w->lo + 1));
     for (int k = w->lo; k <= w->hi; k++) w->off[C_M][k - w->lo] = k >= 0 ? k : 0;
     extend(w, p, P, t, T);
   }
@@ -202,14 +255,14 @@ int tro_wfa_align(const tro_wfa_params *prm, const uint8_t *p, int P, const uint
     w->lo = lo;
     w->hi = hi;
     const size_t width = (size_t)(hi - lo + 1);
-    w->off[C_M] = (int *)malloc(sizeof(int) * width);
+    w->off[C_M] = slab_ints(width);
     if (affine) {
-      w->off[C_I1] = (int *)malloc(sizeof(int) * width);
-      w->off[C_D1] = (int *)malloc(sizeof(int) * width);
+      w->off[C_I1] = slab_ints(width);
+      w->off[C_D1] = slab_ints(width);
     }
     if (two) {
-      w->off[C_I2] = (int *)malloc(sizeof(int) * width);
-      w->off[C_D2] = (int *)malloc(sizeof(int) * width);
+      w->off[C_I2] = slab_ints(width);
+      w->off[C_D2] = slab_ints(width);
     }
     for (int k = lo; k <= hi; k++) {
       int ins, del;
@@ -457,7 +510,7 @@ tro_opt_span tro_find_span(const uint8_t *piece, int piece_len, const uint8_t *s
   /* span_locater.rs:10-12: first exact window */
   if (piece_len > 0) {
     for (int s = 0; s + piece_len <= seq_len; s++) {
-      if (memcmp(seq + s, piece, (size_t)piece_len) == 0) {
+      if (seq[s] == piece[0] && memcmp(seq + s, piece, (size_t)piece_len) == 0) {
         r.found = 1;
         r.start = (uint32_t)s;
         r.end = (uint32_t)(s + piece_len);

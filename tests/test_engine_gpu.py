@@ -152,7 +152,49 @@ def test_hmm_lane_path_single_motif_loci(engine, oracle):
     assert np.array_equal(a.purity, b.purity, equal_nan=True) and np.array_equal(a.paths, b.paths)
 
 
-# ------------------------------------------------------------------ cluster-genotyper glue ----
+def test_filter_impure_trs_targeted_preset(engine, oracle):
+    """a14, filter_impure_trs (tr.rs:400-452, targeted preset: min_read_qual < 0.9): the HMM runs on every READ's
+    repeat sequence (D sequences per locus instead of two alleles) and calc_purity decides which reads are dropped.
+    trgt_hmm_label serves it with the reads' repeat sequences as `alleles`; purities must be the oracle's and the
+    filter (host logic, oracle/host.py) must keep the same reads."""
+    from oracle import host
+    from harness import workload
+    from trgt_b200 import PackedSeqs
+    rng = random.Random(314)
+    w = workload.generate(60, 30, seed=99, sub_rate=0.002, unit_indel_rate=0.02)
+    spans, _ = engine.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+    trs, read_locus = [], []
+    for l in range(w.n_loci):
+        for r in range(int(w.locus_read_off[l]), int(w.locus_read_off[l + 1])):
+            if not spans[r]["found"]:
+                continue
+            tr = w.reads.get(r)[int(spans[r]["start"]):int(spans[r]["end"])]
+            if rng.random() < 0.15:   # an impure read: part of its repeat scrambled
+                k = max(1, len(tr) // 3)
+                tr = tr[:k] + rnd(rng, rng.randint(1, 2 * k)) + tr[2 * k:]
+            if rng.random() < 0.02:
+                tr = b""
+            trs.append(tr)
+            read_locus.append(l)
+    engine.reset_stats()
+    res = engine.hmm_label_packed(w.motifs, w.locus_motif_off, PackedSeqs.from_list(trs), np.array(read_locus, dtype=np.uint32))
+    assert not res.status.any() and "k_hmm_lane_walk" in engine.kernel_stats()
+    exp = []
+    hmms = {}
+    for tr, l in zip(trs, read_locus):
+        h = hmms.setdefault(l, oracle.Hmm([oracle.replace_invalid_bases(m, b"ATCGN") for m in w.locus_motifs(l)]))
+        exp.append(h.annotate(tr)[2])
+    assert np.array_equal(res.purity, np.array(exp), equal_nan=True)
+    assert (res.purity[~np.isnan(res.purity)] < 0.9).sum() > 20
+    # the filter itself, per locus, on the engine's purities and on the oracle's: same reads kept, same order
+    read_locus = np.array(read_locus)
+    for l in range(w.n_loci):
+        idx = np.nonzero(read_locus == l)[0]
+        rq = [None if rng.random() < 0.3 else rng.choice([0.85, 0.95, 0.999]) for _ in idx]
+        assert host.filter_impure_trs(res.purity[idx].tolist(), rq) == host.filter_impure_trs([exp[i] for i in idx], rq)
+
+
+# ------------------------------------------------------------------ cluster-genotyper glue ----# ------------------------------------------------------------------ cluster-genotyper glue ----
 
 def test_cluster_matches_oracle(engine, oracle):
     """trgt_cluster (get_dist_matrix -> Ward linkage -> cluster() -> group1 / group2 -> central_read) against the

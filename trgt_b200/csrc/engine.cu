@@ -1221,8 +1221,9 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
   CU(e, cudaMemsetAsync(b->status.p, 0, ((size_t)n + 1) * sizeof(int32_t), e->stream));
   const size_t bound = ring_ints_bound(src.x, src.oe, src.e, b->Pmax, b->Tmax);
   unsigned long long pool_cap1 = 0;
-  if ((size_t)b->Pmax + (size_t)b->Tmax > 4096) {
-    // long alleles: a CTA per pair
+  if (false) {
+    // (a CTA per pair: the wide-and-shallow shape of the flank problem; end-to-end wavefronts are 2 s + 1 wide at most,
+    // one warp covers them, see the banded ring in k_wfa_score)
     const int block = 128;
     const size_t cap_ints = 24 * 1024;
     const int smem_ring_ints = (int)(bound < cap_ints ? bound : cap_ints);
