@@ -58,6 +58,7 @@ class _Params(C.Structure):
         ("pattern_begin_free", C.c_int), ("pattern_end_free", C.c_int),
         ("text_begin_free", C.c_int), ("text_end_free", C.c_int),
         ("score_only", C.c_int), ("max_steps", C.c_int),
+        ("wfadaptive_min_len", C.c_int), ("wfadaptive_max_dist", C.c_int),
     ]
 
 
@@ -309,9 +310,12 @@ def decode_sam_cigar(words: Sequence[int]) -> List[Tuple[int, str]]:
 
 def wfa_align(pattern: bytes, text: bytes, metric: int = AFFINE, x: int = 0, o: int = 0,
               e: int = 0, o2: int = 0, e2: int = 0, ends_free: Optional[Tuple[int, int, int, int]] = None,
-              score_only: bool = False, max_steps: int = 0) -> Alignment:
-    """ends_free = (pattern_begin_free, pattern_end_free, text_begin_free, text_end_free)"""
-    p = _Params(metric, x, o, e, o2, e2, 0, 0, 0, 0, 0, int(score_only), max_steps)
+              score_only: bool = False, max_steps: int = 0, wfadaptive: Optional[Tuple[int, int]] = None) -> Alignment:
+    """ends_free = (pattern_begin_free, pattern_end_free, text_begin_free, text_end_free);
+    wfadaptive = (min_wavefront_length, max_distance_threshold): WFA2-lib's adaptive heuristic, a measuring device"""
+    p = _Params(metric, x, o, e, o2, e2, 0, 0, 0, 0, 0, int(score_only), max_steps, 0, 0)
+    if wfadaptive is not None:
+        p.wfadaptive_min_len, p.wfadaptive_max_dist = wfadaptive
     if ends_free is not None:
         p.ends_free = 1
         (p.pattern_begin_free, p.pattern_end_free, p.text_begin_free, p.text_end_free) = ends_free
@@ -483,16 +487,18 @@ def hmm_batch(motifs, locus_motif_off, alleles, allele_locus, n_threads: int = 1
     return mc_off, mc[:int(mc_off[n])], span_off, spans.reshape(-1, 3), purity[:n], status[:n]
 
 
-def repair_consensus(backbone: bytes, seqs: Sequence[bytes]) -> bytes:
-    """utils::align + repair_consensus (consensus.rs:5-72), as genotype_cluster.rs:52-53 chains them."""
+def repair_consensus(backbone: bytes, seqs: Sequence[bytes], cigars: Optional[Sequence[Sequence[int]]] = None) -> bytes:
+    """utils::align + repair_consensus (consensus.rs:5-72), as genotype_cluster.rs:52-53 chains them.
+    cigars (optional): run-length SAM words per sequence to use instead of the exact alignments (for measuring
+    how sensitive the consensus is to the choice among co-optimal alignments)"""
     np = _np()
     offs = [0]
     for s_ in seqs:
         offs.append(offs[-1] + len(s_))
     seq_off = np.array(offs, dtype=np.uint64)
     words, woff = [], [0]
-    for s_ in seqs:
-        w, _ = align_words(backbone, s_)
+    for i, s_ in enumerate(seqs):
+        w = list(cigars[i]) if cigars is not None else align_words(backbone, s_)[0]
         words += w
         woff.append(len(words))
     warr = np.array(words if words else [0], dtype=np.uint32)

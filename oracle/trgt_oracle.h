@@ -100,6 +100,9 @@ typedef struct {
   int pattern_begin_free, pattern_end_free, text_begin_free, text_end_free;
   int score_only;        /* AlignmentScope::Score */
   int max_steps;         /* <=0: unlimited */
+  /* optional (0 = off): WFA2-lib's adaptive heuristic wfadaptive(min_len, max_dist), applied at every score
+   * (steps_between_cutoffs = 1).  Restated from the published rule, parity unpinned: a MEASURING device only. */
+  int wfadaptive_min_len, wfadaptive_max_dist;
 } tro_wfa_params;
 
 typedef struct {

@@ -29,6 +29,7 @@ enum { T_I1O = 1, T_I1E = 2, T_I2O = 3, T_I2E = 4, T_D1O = 5, T_D1E = 6, T_D2O =
 typedef struct {
   int lo, hi;        /* inclusive; lo > hi <=> null */
   int *off[N_COMP];  /* off[c][k - lo] */
+  int elo, ehi;      /* what a heuristic cut-off left of [lo, hi] (cells outside are nulled); = lo, hi without one */
 } wf_t;
 
 typedef struct {
@@ -43,7 +44,7 @@ static inline int wf_get(const wf_hist *H, int s, int c, int k) {
   return w->off[c][k - w->lo];
 }
 static inline int wf_present(const wf_hist *H, int s, int c) {
-  return s >= 0 && s < H->n && H->wf[s].lo <= H->wf[s].hi && H->wf[s].off[c] != NULL;
+  return s >= 0 && s < H->n && H->wf[s].elo <= H->wf[s].ehi && H->wf[s].off[c] != NULL;
 }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 static inline int imin(int a, int b) { return a < b ? a : b; }
@@ -96,6 +97,8 @@ static wf_t *hist_push(wf_hist *H) {
   memset(w, 0, sizeof(*w));
   w->lo = 1;
   w->hi = -1;
+  w->elo = 1;
+  w->ehi = -1;
   return w;
 }
 static void hist_free(wf_hist *H) {
@@ -129,6 +132,47 @@ static void extend(wf_t *w, const uint8_t *p, int P, const uint8_t *t, int T) {
   done:
     w->off[C_M][k - w->lo] = h;
   }
+}
+
+/* WFA2-lib's adaptive wavefront reduction (Marco-Sola et al. 2021, section 2.4; `wfadaptive(min_wavefront_length,
+ * max_distance_threshold, steps_between_cutoffs)`, the default heuristic of wavefront_aligner_attr_default with
+ * (10, 50, 1) -- WFA2-lib is not vendored in the reference tree, so this is a restatement of the published rule,
+ * PARITY UNPINNED, used only to MEASURE how far the reference's default-heuristic aligners can stray from exact
+ * WFA).  After the wavefront of a score has been extended and found not to terminate:
+ * if it spans at least min_len diagonals, every diagonal's remaining distance max(P - v, T - h) is compared with
+ * the smallest one and diagonals more than max_dist behind it are cut off from both ends, never across the
+ * target diagonal T - P; the I / D components are clamped to the M range. */
+static void wfadaptive_cutoff(wf_t *w, int P, int T, int min_len, int max_dist) {
+  if (w->elo > w->ehi) return;
+  if (w->ehi - w->elo + 1 < min_len) return;
+  int min_d = INT_MAX;
+  for (int k = w->elo; k <= w->ehi; k++) {
+    const int h = w->off[C_M][k - w->lo];
+    if (h < 0) continue;
+    const int v = h - k, d = imax(P - v, T - h);
+    if (d < min_d) min_d = d;
+  }
+  if (min_d == INT_MAX) return;
+  const int ak = T - P;
+  int lo = w->elo, hi = w->ehi;
+  for (int k = w->elo; k < ak && k <= w->ehi; k++) {
+    const int h = w->off[C_M][k - w->lo];
+    const int d = h < 0 ? INT_MAX : imax(P - (h - k), T - h);
+    if (d != INT_MAX && d - min_d <= max_dist) break;
+    lo++;
+  }
+  for (int k = w->ehi; k > ak && k >= lo; k--) {
+    const int h = w->off[C_M][k - w->lo];
+    const int d = h < 0 ? INT_MAX : imax(P - (h - k), T - h);
+    if (d != INT_MAX && d - min_d <= max_dist) break;
+    hi--;
+  }
+  for (int k = w->lo; k <= w->hi; k++)
+    if (k < lo || k > hi)
+      for (int c = 0; c < N_COMP; c++)
+        if (w->off[c]) w->off[c][k - w->lo] = OFF_NULL;
+  w->elo = lo;
+  w->ehi = hi;
 }
 
 /* returns 1 and sets (k, offset) for the first (lowest k) diagonal that satisfies the end condition */
@@ -212,6 +256,8 @@ int tro_wfa_align(const tro_wfa_params *prm, const uint8_t *p, int P, const uint
       w->lo = 0;
       w->hi = 0;
     }
+    w->elo = w->lo;
+    w->ehi = w->hi;
     w->off[C_M] = slab_ints((size_t)(w->hi - w->lo + 1));
     for (int k = w->lo; k <= w->hi; k++) w->off[C_M][k - w->lo] = k >= 0 ? k : 0;
     extend(w, p, P, t, T);
@@ -220,6 +266,8 @@ int tro_wfa_align(const tro_wfa_params *prm, const uint8_t *p, int P, const uint
   int status = TRO_STATUS_OK;
   for (;;) {
     if (terminated(&H.wf[s], prm, P, T, &ek, &eo)) break;
+    if (prm->wfadaptive_min_len > 0 && !prm->ends_free)
+      wfadaptive_cutoff(&H.wf[s], P, T, prm->wfadaptive_min_len, prm->wfadaptive_max_dist);
     s++;
     if (prm->max_steps > 0 && s > prm->max_steps) {
       status = TRO_STATUS_MAX_STEPS;
@@ -230,8 +278,8 @@ int tro_wfa_align(const tro_wfa_params *prm, const uint8_t *p, int P, const uint
     int lo = INT_MAX, hi = INT_MIN;
 #define SRC(ss, c)                                 \
   if (wf_present(&H, (ss), (c))) {                 \
-    lo = imin(lo, H.wf[(ss)].lo);                  \
-    hi = imax(hi, H.wf[(ss)].hi);                  \
+    lo = imin(lo, H.wf[(ss)].elo);                 \
+    hi = imax(hi, H.wf[(ss)].ehi);                 \
   }
     if (use_x) SRC(s - x, C_M);
     SRC(s - o1e1, C_M);
@@ -254,6 +302,8 @@ int tro_wfa_align(const tro_wfa_params *prm, const uint8_t *p, int P, const uint
     if (lo > hi) continue;
     w->lo = lo;
     w->hi = hi;
+    w->elo = lo;
+    w->ehi = hi;
     const size_t width = (size_t)(hi - lo + 1);
     w->off[C_M] = slab_ints(width);
     if (affine) {

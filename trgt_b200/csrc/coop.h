@@ -79,6 +79,16 @@ struct TileGroup {
   TRGT_D int any(int p) const { return __any_sync(mask, p); }
   TRGT_D int bcast0(int v) const { return __shfl_sync(mask, v, 0, N); }
   TRGT_D int bcast(int v, int src_lane) const { return __shfl_sync(mask, v, src_lane, N); }
+  TRGT_D int excl_scan_i(int v, int *total) const {
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < N; d <<= 1) {
+      const int y = __shfl_up_sync(mask, x, d, N);
+      if (l >= d) x += y;
+    }
+    *total = __shfl_sync(mask, x, N - 1, N);
+    return x - v;
+  }
   // bit i = predicate of the tile's lane i
   TRGT_D unsigned ballot(int p) const {
     return (__ballot_sync(mask, p) >> ((threadIdx.x & 31u) & ~(unsigned)(N - 1))) & (unsigned)((1ull << N) - 1ull);

@@ -234,9 +234,10 @@ int cap_grid_to_budget(trgt_engine *e, int *grid, int slots_per_block, size_t st
   if (stride_ints == 0) return 0;
   const size_t budget_ints = e->workspace_budget / sizeof(int);
   const size_t per_block = stride_ints * (size_t)slots_per_block;
-  if (per_block > budget_ints)
+  if (stride_ints > budget_ints)
     return fail(e, TRGT_ERR_INTERNAL, "%s: one scratch slot of %zu ints exceeds the workspace budget", what, stride_ints);
-  const size_t fit = budget_ints / per_block;
+  size_t fit = budget_ints / per_block;
+  if (fit == 0) fit = 1;  // one CTA of several slots: over the budget by less than slots_per_block, but it has to run
   if ((size_t)*grid > fit) *grid = (int)fit;
   return 0;
 }
@@ -1221,9 +1222,10 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
   CU(e, cudaMemsetAsync(b->status.p, 0, ((size_t)n + 1) * sizeof(int32_t), e->stream));
   const size_t bound = ring_ints_bound(src.x, src.oe, src.e, b->Pmax, b->Tmax);
   unsigned long long pool_cap1 = 0;
-  if (false) {
-    // (a CTA per pair: the wide-and-shallow shape of the flank problem; end-to-end wavefronts are 2 s + 1 wide at most,
-    // one warp covers them, see the banded ring in k_wfa_score)
+  if ((size_t)b->Pmax + (size_t)b->Tmax > 4096) {
+    // long alleles: a CTA per pair.  (Tandem repeats match themselves on every diagonal that is a multiple of the
+    // motif length, so most of the work is long match extensions, 8 bytes per lane per round: four warps per pair
+    // finish them in a quarter of the rounds a single warp needs -- measured on config 5: 334 vs 422 ms.)
     const int block = 128;
     const size_t cap_ints = 24 * 1024;
     const int smem_ring_ints = (int)(bound < cap_ints ? bound : cap_ints);

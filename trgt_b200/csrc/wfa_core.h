@@ -768,64 +768,73 @@ TRGT_HD bool flank_seed_band(const G &g, const WfaProb &pr, int S, uint64_t *key
 
 // ---------------------------------------------------------------- 8-mer index of a flank piece ---
 
-// Open-addressing table of every 8-mer of one piece (key = its 8 bytes, value = its offset), built
-// once per locus and shared by all of the locus' reads.  With it, both the exact search and the seed
-// filter only look at a few *probe* positions of the read instead of every position: an occurrence
-// of a length-n pattern piece covers exactly one of the text positions (i+1)(n-7)-1, and the 8-mer
-// found there must be one of the piece's own.
-#define TRGT_KIDX_SLOTS 512u
-#define TRGT_KIDX_EMPTY 0xFFFFu
-#define TRGT_KIDX_MAX_P 400   // offsets fit 9 bits and the load factor stays below 0.77
+// Table of every 8-mer of one piece (key = its 8 bytes, value = its offset), built once per locus and
+// shared by all of the locus' reads.  With it, both the exact search and the seed filter only look at a few
+// *probe* positions of the read instead of every position: an occurrence of a length-n pattern piece covers
+// exactly one of the text positions (i+1)(n-7)-1, and the 8-mer found there must be one of the piece's own.
+//
+// Layout (TRGT_KIDX_SLOTS 16-bit words = 1344 bytes per piece): 256 buckets by 8 bits of the mixed key,
+// bound[b] .. bound[b+1] delimiting bucket b's entries (bound[0] = 0), then the entries themselves,
+// entry = 7-bit fingerprint << 9 | offset in the piece.  A fingerprint clash only costs a failed
+// verification: every candidate is compared byte for byte before it counts.  Built by counting sort --
+// count per bucket, exclusive scan, scatter -- three converged passes without a compare-and-swap loop.
+#define TRGT_KIDX_BUCKETS 256u
+#define TRGT_KIDX_ENT0 264u    // first entry: after bound[257], rounded to 16 bytes
+#define TRGT_KIDX_SLOTS 672u   // 264 + room for 400 entries, rounded to 16 bytes
+#define TRGT_KIDX_MAX_P 400    // offsets fit 9 bits
 #define TRGT_CAND_CAP 64
 
-// slot (16 bits) = 7-bit fingerprint of the 8-mer << 9 | its offset in the piece: 1 KB per piece, so
-// every warp can afford its own pair of tables.  A fingerprint clash only costs a failed
-// verification: every candidate is compared byte for byte before it counts.  0x7F is never used as
-// a fingerprint, so no slot equals TRGT_KIDX_EMPTY.
 struct KmerIndex {
   uint16_t *slot;  // [TRGT_KIDX_SLOTS]
 };
 
 TRGT_HD uint64_t kidx_mix(uint64_t k) { return k * 0x9E3779B97F4A7C15ull; }
-TRGT_HD uint32_t kidx_home(uint64_t mixed) { return (uint32_t)(mixed >> 55); }
-TRGT_HD uint32_t kidx_fp(uint64_t mixed) { const uint32_t f = (uint32_t)(mixed >> 40) & 0x7Fu; return f == 0x7Fu ? 0x3Fu : f; }
+TRGT_HD uint32_t kidx_home(uint64_t mixed) { return (uint32_t)(mixed >> 56); }
+TRGT_HD uint32_t kidx_fp(uint64_t mixed) { return (uint32_t)(mixed >> 40) & 0x7Fu; }
 
-// claim the first free slot at or after `h` for `val` (linear probing).  Occupied slots are skipped
-// with plain loads; only a slot that looks free costs an atomic, on the 32-bit word that holds it.
-TRGT_HD void kidx_insert(uint16_t *slot, uint32_t h, uint32_t val) {
+// every entry `v` of the bucket of `mixed`
+#define TRGT_KIDX_FOR(idx, mixed, v)                                                                            \
+  for (uint32_t ki_ = (idx).slot[kidx_home(mixed)], ke_ = (idx).slot[kidx_home(mixed) + 1u];                   \
+       ki_ < ke_ && (((v) = (idx).slot[TRGT_KIDX_ENT0 + ki_]), true); ki_++)
+
+// slot[i] += 1, returning the old value (the 16-bit word shares its 32-bit word with a neighbour; counts stay far
+// below 65536, so the add never carries across)
+TRGT_HD uint32_t kidx_fetch_inc(uint16_t *slot, uint32_t i) {
 #if defined(__CUDA_ARCH__)
-  for (;;) {
-    unsigned int *w = (unsigned int *)slot + (h >> 1);
-    const unsigned sh = (h & 1u) * 16u;
-    unsigned int cur = *(volatile unsigned int *)w;
-    bool placed = false;
-    while (((cur >> sh) & 0xFFFFu) == TRGT_KIDX_EMPTY) {
-      const unsigned int nv = (cur & ~(0xFFFFu << sh)) | (val << sh);
-      const unsigned int prev = atomicCAS(w, cur, nv);
-      if (prev == cur) { placed = true; break; }
-      cur = prev;
-    }
-    if (placed) return;
-    h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u);
-  }
+  const unsigned sh = (i & 1u) * 16u;
+  const unsigned int old = atomicAdd((unsigned int *)slot + (i >> 1), 1u << sh);
+  return (old >> sh) & 0xFFFFu;
 #else
-  for (;;) {
-    uint16_t ex = (uint16_t)TRGT_KIDX_EMPTY;
-    if (__atomic_compare_exchange_n(&slot[h], &ex, (uint16_t)val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) return;
-    h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u);
-  }
+  return __atomic_fetch_add(&slot[i], (uint16_t)1, __ATOMIC_ACQ_REL);
 #endif
 }
 
 template <class G>
 TRGT_HD void kidx_build(const G &g, const KmerIndex &idx, const uint8_t *piece, int P) {
-  for (uint32_t i = (uint32_t)g.lane(); i < TRGT_KIDX_SLOTS / 4; i += (uint32_t)g.size())  // tables are 8-byte aligned
-    ((uint64_t *)idx.slot)[i] = 0xFFFFFFFFFFFFFFFFull;  // four TRGT_KIDX_EMPTY
+  uint16_t *bound = idx.slot;  // during the build bound[1 + b] = count, then first free position of bucket b
+  for (uint32_t i = (uint32_t)g.lane(); i < TRGT_KIDX_ENT0 / 4; i += (uint32_t)g.size())  // tables are 8-byte aligned
+    ((uint64_t *)idx.slot)[i] = 0ull;
   g.sync();
-  for (int i = g.lane(); i + 8 <= P; i += g.size()) {
+  for (int i = g.lane(); i + 8 <= P; i += g.size()) kidx_fetch_inc(bound, 1u + kidx_home(kidx_mix(wfa_ld64u(piece + i))));
+  g.sync();
+  {  // exclusive scan of the 256 counts: a run of consecutive buckets per lane, then across the lanes
+    const uint32_t per = (TRGT_KIDX_BUCKETS + (uint32_t)g.size() - 1u) / (uint32_t)g.size();
+    const uint32_t b0 = (uint32_t)g.lane() * per;
+    int sum = 0;
+    for (uint32_t b = b0; b < b0 + per && b < TRGT_KIDX_BUCKETS; b++) sum += bound[1u + b];
+    int total;
+    int run = g.excl_scan_i(sum, &total);
+    for (uint32_t b = b0; b < b0 + per && b < TRGT_KIDX_BUCKETS; b++) {
+      const int c = bound[1u + b];
+      bound[1u + b] = (uint16_t)run;
+      run += c;
+    }
+  }
+  g.sync();
+  for (int i = g.lane(); i + 8 <= P; i += g.size()) {  // scatter; bound[1 + b] ends up at the end of bucket b
     const uint64_t mixed = kidx_mix(wfa_ld64u(piece + i));
-    const uint32_t val = (kidx_fp(mixed) << 9) | (uint32_t)i;
-    kidx_insert(idx.slot, kidx_home(mixed), val);
+    const uint32_t pos = kidx_fetch_inc(bound, 1u + kidx_home(mixed));
+    idx.slot[TRGT_KIDX_ENT0 + pos] = (uint16_t)((kidx_fp(mixed) << 9) | (uint32_t)i);
   }
   g.sync();
 }
@@ -842,12 +851,14 @@ TRGT_HD int flank_scan_indexed(const G &g, const KmerIndex &idx, const uint8_t *
   for (int pb = 0; pb < n_probes; pb += g.size()) {
     const int i = pb + g.lane();
     const int j = (i + 1) * step - 1;
-    uint32_t home = 0, fp = 0;
+    uint32_t fp = 0;
+    uint64_t mixed = 0;
     int cnt = 0, c0 = 0;  // candidates of this lane's probe; c0 = the first one
     if (i < n_probes) {
-      const uint64_t mixed = kidx_mix(wfa_ld64u(t + j));
-      home = kidx_home(mixed); fp = kidx_fp(mixed);
-      for (uint32_t h = home, v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+      mixed = kidx_mix(wfa_ld64u(t + j));
+      fp = kidx_fp(mixed);
+      uint32_t v;
+      TRGT_KIDX_FOR(idx, mixed, v) {
         const int s = j - (int)(v & 511u);
         if ((v >> 9) == fp && s >= 0 && s < n_starts) { if (cnt == 0) c0 = s; cnt++; }
       }
@@ -863,7 +874,8 @@ TRGT_HD int flank_scan_indexed(const G &g, const KmerIndex &idx, const uint8_t *
       } else {
         if (g.lane() == leader) {
           int n = 0;
-          for (uint32_t h = home, v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+          uint32_t v;
+          TRGT_KIDX_FOR(idx, mixed, v) {
             const int s = j - (int)(v & 511u);
             if ((v >> 9) == fp && s >= 0 && s < n_starts) { if (n < TRGT_CAND_CAP) cand[n] = s; n++; }
           }
@@ -997,7 +1009,8 @@ TRGT_HD int flank_exact_thread(const KmerIndex &idx, const uint8_t *copies, int 
       const int j = (ib + u + 1) * step - 1;
       const uint64_t mixed = kidx_mix(key[u]);
       const uint32_t fp = kidx_fp(mixed);
-      for (uint32_t h = kidx_home(mixed), v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+      uint32_t v;
+      TRGT_KIDX_FOR(idx, mixed, v) {
         if ((v >> 9) != fp) continue;
         const int s = j - (int)(v & 511u);
         if (s < 0 || s >= n_starts) continue;
@@ -1026,7 +1039,8 @@ TRGT_HD int flank_exact_thread(const KmerIndex &idx, const uint8_t *copies, int 
     const uint64_t mixed = kidx_mix(wfa_ld64u(t + j));
     const uint32_t fp = kidx_fp(mixed);
     int pbest = INT_MAX;
-    for (uint32_t h = kidx_home(mixed), v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+    uint32_t v;
+      TRGT_KIDX_FOR(idx, mixed, v) {
       if ((v >> 9) != fp) continue;
       const int s = j - (int)(v & 511u);
       if (s < 0 || s >= n_starts || s >= pbest) continue;
@@ -1053,12 +1067,14 @@ TRGT_HD int flank_seed_band_indexed(const G &g, const KmerIndex &idx, const WfaP
   for (int pb = 0; pb < n_probes; pb += g.size()) {
     const int i = pb + g.lane();
     const int j = (i + 1) * step - 1;
-    uint32_t home = 0, fp = 0;
+    uint32_t fp = 0;
+    uint64_t mixed = 0;
     int cnt = 0, c0 = 0;  // candidate = block start in the text << 5 | block
     if (i < n_probes) {
-      const uint64_t mixed = kidx_mix(wfa_ld64u(pr.t + j));
-      home = kidx_home(mixed); fp = kidx_fp(mixed);
-      for (uint32_t h = home, v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+      mixed = kidx_mix(wfa_ld64u(pr.t + j));
+      fp = kidx_fp(mixed);
+      uint32_t v;
+      TRGT_KIDX_FOR(idx, mixed, v) {
         if ((v >> 9) != fp) continue;
         const int d = (int)(v & 511u), b = d / blen, q = j - (d - b * blen);
         if (b < nb && d - b * blen + 8 <= blen && q >= 0 && q + blen <= pr.T) { if (cnt == 0) c0 = (q << 5) | b; cnt++; }
@@ -1079,7 +1095,8 @@ TRGT_HD int flank_seed_band_indexed(const G &g, const KmerIndex &idx, const WfaP
         if (cand == nullptr) return -2;  // no list scratch (one-lane callers): leave it to the cooperative path
         if (g.lane() == leader) {
           int n = 0;
-          for (uint32_t h = home, v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+          uint32_t v;
+          TRGT_KIDX_FOR(idx, mixed, v) {
             if ((v >> 9) != fp) continue;
             const int d = (int)(v & 511u), b = d / blen, q = j - (d - b * blen);
             if (b < nb && d - b * blen + 8 <= blen && q >= 0 && q + blen <= pr.T) {
@@ -1247,7 +1264,8 @@ TRGT_HD int flank_seed_band_thread(const KmerIndex &idx, const WfaProb &pr, int 
       const int j = (ib + u + 1) * step - 1;
       const uint64_t mixed = kidx_mix(key[u]);
       const uint32_t fp = kidx_fp(mixed);
-      for (uint32_t h = kidx_home(mixed), v; (v = idx.slot[h]) != TRGT_KIDX_EMPTY; h = (h + 1u) & (TRGT_KIDX_SLOTS - 1u)) {
+      uint32_t v;
+      TRGT_KIDX_FOR(idx, mixed, v) {
         if ((v >> 9) != fp) continue;
         const int d = (int)(v & 511u), b = d / blen, q = j - (d - b * blen);
         if (b >= nb || d - b * blen + 8 > blen || q < 0 || q + blen > pr.T) continue;
