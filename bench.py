@@ -249,10 +249,18 @@ def kernel_bytes(name: str, w, hp, res) -> float | None:
         return 1.5 * read_bytes + 28.0 * n_reads
     if name in ("k_flank_exact", "k_flank_exact_t"):   # every read base once, both pieces once per locus, one hit per (read, flank)
         return read_bytes + 2.0 * P * w.n_loci + 2 * 20.0 * n_reads + 8.0 * n_reads
-    if name in ("k_flank_band", "k_flank_band2", "k_flank_band_wide") and res.hits is not None:
+    if name in ("k_flank_band", "k_flank_seed", "k_flank_band1", "k_flank_band2", "k_flank_band_wide") and res.hits is not None:
         via = res.hits["via"].reshape(-1, 2)
         pend = (via >= 2)
         pend_reads = pend.any(axis=1)
+        if name == "k_flank_seed":   # hit records scanned, both 8-mer tables per locus with a pending pair, the probes of
+            # every pending pair (one 32-byte sector each, a probe every P/4 - 7 bases), one list entry per pair
+            loci_pend = np.add.reduceat(pend_reads.astype(np.int64), w.locus_read_off[:-1].astype(np.int64)) > 0
+            step = max(1.0, P / 4.0 - 7.0)
+            n_probe_sectors = float((np.repeat(read_len / step, 2).reshape(-1, 2) * pend).sum())
+            return float(40.0 * n_reads + 2.0 * 1344.0 * loci_pend.sum() + 32.0 * n_probe_sectors + 8.0 * pend.sum())
+        if name == "k_flank_band1":  # per listed pair: list entry, the text window its band can touch, its piece, the hit
+            return float(pend.sum() * (8.0 + (P + 16.0 + 12.0) + P + 20.0))
         if name == "k_flank_band":  # hit records scanned, pending reads re-read once, pieces once per locus, hits rewritten
             return float(40.0 * n_reads + read_len[pend_reads].sum() + 2.0 * P * w.n_loci + 20.0 * pend.sum())
         n_pairs = {"k_flank_band2": hp.fallback_counts()[0], "k_flank_band_wide": hp.fallback_counts()[1]}[name]

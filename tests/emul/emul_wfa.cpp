@@ -271,4 +271,41 @@ int emu_flank_tier1_thread(const uint8_t *p_in, int P, const uint8_t *t_in, int 
   return 0;
 }
 
+// first cost tier in two passes (flank_tier1_seed_thread + flank_tier1_band_thread on a staged window with the
+// 16-bit on-chip history): same outputs as emu_flank_tier1_thread; `slack` (0..15) = how far the window starts
+// before the first byte the band can touch (on the device: the distance to the previous 16-byte boundary)
+int emu_flank_tier1_split(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x, int o, int e, int S,
+                          double frac, int slack, int *out) {
+  std::vector<uint8_t> pbuf(P + 16, 0), tbuf(T + 32, 0);
+  memcpy(pbuf.data(), p_in, P);
+  memcpy(tbuf.data(), t_in, T);
+  WfaProb pr;
+  pr.p = pbuf.data(); pr.P = P; pr.t = tbuf.data(); pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
+  pr.pbf = 0; pr.pef = 0; pr.tbf = T; pr.tef = T;
+  wfa_unband(pr);
+  std::vector<uint16_t> islot(TRGT_KIDX_SLOTS);
+  KmerIndex idx{islot.data()};
+  SerialGroup g;
+  kidx_build(g, idx, pr.p, P);
+  FlankHit hit = {0, 0, 0, 0, 0};
+  out[0] = 1; out[1] = out[2] = out[3] = out[4] = out[5] = 0;
+  int klo = 0, khi = 0;
+  if (P > FT1_PMAX || flank_tier1_seed_thread(idx, pr, S, &klo, &khi) != 1) return 0;
+  const int first = klo > 0 ? klo : 0;
+  const int a0 = first - slack;  // may be negative: bytes before the text are never read
+  uint8_t win[FT1_WIN_BYTES];
+  memset(win, 0xEE, sizeof win);
+  for (int i = 0; i < FT1_WIN_BYTES; i++) {
+    const int h = a0 + i;
+    if (h >= 0 && h < T + 16) win[i] = tbuf[h];  // the sequence buffers of the engine carry 16 bytes of padding
+  }
+  int16_t hist[FT1_HIST_HALFS];
+  for (int i = 0; i < FT1_HIST_HALFS; i++) hist[i] = 0x7ead;
+  WfaProb q = pr;
+  q.t = nullptr;  // must not be read
+  out[0] = flank_tier1_band_thread<1>(q, klo, khi, S, frac, win, a0, hist, &hit);
+  out[1] = hit.via; out[2] = hit.matches; out[3] = hit.score; out[4] = hit.start; out[5] = hit.end;
+  return 0;
+}
+
 }  // extern "C"

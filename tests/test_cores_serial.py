@@ -723,6 +723,74 @@ def test_flank_tier1_thread_core(emul, oracle):
     assert seen["settled"] > 700 and seen["handed_on"] > 50 and seen["rejected"] > 5, seen
 
 
+def test_flank_tier1_split_core(emul, oracle):
+    """First cost tier in two passes (seed pass: hull of ALL index hits, unverified; band pass: staged text
+    window + 16-bit on-chip history): whatever it settles is the reference's answer, and it settles at least
+    every pair the one-pass routine settles with the same result.  Decoys (a second copy of a block elsewhere
+    in the read, repetitive pieces) force the verifying path; windows start at every 16-byte phase."""
+    emul.emu_flank_tier1_thread.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_double, C.POINTER(C.c_int)]
+    emul.emu_flank_tier1_split.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int)]
+    rng = random.Random(777)
+    seen = {"settled": 0, "handed_on": 0, "rejected": 0, "decoy_settled": 0, "negative_k": 0}
+    for it in range(4000):
+        x, o, e = rng.choice([(2, 5, 1), (2, 5, 1), (2, 5, 1), (1, 0, 1), (4, 6, 2), (3, 1, 1), (3, 3, 1)])
+        P = rng.choice([16, 60, 120, 200, 250, 250, 250, 256])
+        kind = rng.random()
+        if kind < 0.2:
+            unit = rnd(rng, rng.randint(1, 9))
+            p = mutate(rng, (unit * (P // len(unit) + 1))[:P], rng.choice([0, 0.02, 0.05]))[:P]
+            if len(p) < 16:
+                continue
+        else:
+            p = rnd(rng, P)
+        pre, suf = rnd(rng, rng.choice([0, 0, 1, 3, rng.randint(0, 600)])), rnd(rng, rng.randint(0, 600))
+        r = rng.random()
+        if r < 0.6:
+            i = rng.randrange(len(p))
+            c = rng.random()
+            if c < 0.3:
+                body = p[:i] + bytes([rng.choice(b"ACGT")]) + p[i + 1:]
+            elif c < 0.65:
+                body = p[:i] + p[i + 1:]
+            else:
+                body = p[:i] + bytes([rng.choice(b"ACGT")]) + p[i:]
+        else:
+            body = mutate(rng, p, rng.choice([0.002, 0.004, 0.01, 0.03]))
+        decoy = rng.random() < 0.25
+        if decoy:   # a verbatim stretch of the piece somewhere else in the read: an index hit off the alignment
+            a = rng.randrange(max(1, len(p) - 20))
+            piece_bit = p[a:a + rng.choice([8, 12, 30, 70])]
+            if rng.random() < 0.5:
+                suf = suf + piece_bit + rnd(rng, rng.randint(0, 50))
+            else:
+                pre = piece_bit + rnd(rng, rng.randint(0, 50)) + pre
+        t = pre + body + suf
+        if rng.random() < 0.05:
+            t = t[:rng.randint(1, len(t))]
+        if t.find(p) >= 0:
+            continue
+        frac = rng.choice([0.7, 0.7, 0.999])
+        one, two = (C.c_int * 6)(), (C.c_int * 6)()
+        emul.emu_flank_tier1_thread(p, len(p), t, len(t), x, o, e, 20, frac, one)
+        emul.emu_flank_tier1_split(p, len(p), t, len(t), x, o, e, 20, frac, it % 16, two)
+        if one[0] == 0:
+            assert two[0] == 0 and list(two) == list(one), (it, list(one), list(two))
+        if two[0] != 0:
+            seen["handed_on"] += 1
+            continue
+        seen["settled"] += 1
+        seen["decoy_settled"] += decoy
+        exp, via, nm = oracle.find_span(p, t, (x, o, e), len(p) * frac)
+        assert (two[1], two[2]) == (via, nm), (it, x, o, e)
+        seen["rejected"] += via == 3
+        if exp is not None:
+            assert (two[4], two[5]) == exp, (it, x, o, e)
+            seen["negative_k"] += exp[0] == 0
+    assert seen["settled"] > 1200 and seen["handed_on"] > 50 and seen["rejected"] > 5 and seen["decoy_settled"] > 100, seen
+
+
 def test_vcf_fixed6_core(emul):
     """{:.6} of the VCF writer (write_vcf.rs:339) by exact 128-bit integer arithmetic: identical to the
     correctly rounded decimal (Python's format, itself exact, ties to even) on purity-like ratios, on exact

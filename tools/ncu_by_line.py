@@ -3,7 +3,7 @@ hottest source lines of one kernel.  Usage: ncu_by_line.py <report.ncu-rep> <ker
 import csv, io, os, re, subprocess, sys, tempfile, collections
 
 rep, kern = sys.argv[1], sys.argv[2]
-so = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "trgt_b200", "libtrgt_b200.so")
+so = os.path.abspath(sys.argv[3]) if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "trgt_b200", "libtrgt_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]

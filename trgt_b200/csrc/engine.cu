@@ -414,7 +414,7 @@ struct trgt_flank_batch {
   trgt_scoring_t scoring{2, 5, 1};
   double frac = 0.7;
   DevBuf reads, read_off, lp, lp_off, rp, rp_off, locus_read_off, read_locus;
-  DevBuf hits, spans, work, work2, ends, ctr, gring, gws;
+  DevBuf hits, spans, work, work2, list1, ends, ctr, gring, gws;
   DevBuf kidx;                         // 8-mer indexes of both pieces of every locus (k_flank_exact_t -> k_flank_band)
   bool kidx_valid = false;
   bool ran = false;                    // spans / hits hold results
@@ -506,7 +506,7 @@ void trgt_flank_free(trgt_engine_t *e, trgt_flank_batch_t *b) {
     if (e->one_flank == b) e->one_flank = nullptr;
   }
   DevBuf *all[] = {&b->reads, &b->read_off, &b->lp, &b->lp_off, &b->rp, &b->rp_off, &b->locus_read_off,
-                   &b->read_locus, &b->hits, &b->spans, &b->work, &b->work2, &b->ends, &b->ctr, &b->gring, &b->gws,
+                   &b->read_locus, &b->hits, &b->spans, &b->work, &b->work2, &b->list1, &b->ends, &b->ctr, &b->gring, &b->gws,
                    &b->seq4, &b->seq4_starts, &b->seq4_len, &b->tr_len, &b->tr_off, &b->tr_data, &b->kidx};
   for (auto *d : all) dev_free(*d);
   pin_free(b->h_tr_off);
@@ -568,6 +568,7 @@ static int flank_upload_into(trgt_engine_t *e, trgt_flank_batch *b, const trgt_s
   TRY(dev_reserve(e, b->spans, ((size_t)b->n_reads + 1) * sizeof(trgt_span_t)));
   TRY(dev_reserve(e, b->work, ((size_t)b->n_reads * 2 + 1) * sizeof(uint32_t)));
   TRY(dev_reserve(e, b->work2, ((size_t)b->n_reads * 2 + 1) * sizeof(uint32_t)));
+  TRY(dev_reserve(e, b->list1, ((size_t)b->n_reads * 2 + 1) * sizeof(uint2)));
   TRY(dev_reserve(e, b->ends, ((size_t)b->n_reads * 2 + 1) * sizeof(WfaEnd)));
   TRY(dev_reserve(e, b->ctr, sizeof(Counters)));
   if (n_loci) {
@@ -628,7 +629,17 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
                                                  (Counters *)b->ctr.p);
     TRY(check_launch(e, "k_flank_exact"));
   }
-  if (e->band_budget > 0) {  // first cost tier of the fallback, at high occupancy
+  if (e->band_budget > 0 && b->kidx_valid) {  // first cost tier of the fallback, seed pass (the band pass runs in flank_finish)
+    int grid = 0;
+    TRY(persistent_grid(e, k_flank_seed, 128, 0, &grid));
+    const uint32_t need = (l1 - l0 + FB_LOCI - 1) / FB_LOCI;
+    if ((uint32_t)grid > need) grid = (int)need;
+    LaunchScope ls(e, "k_flank_seed");
+    k_flank_seed<<<grid, 128, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
+                                              (trgt_flank_hit_t *)b->hits.p, (uint2 *)b->list1.p, (uint32_t *)b->work2.p,
+                                              (Counters *)b->ctr.p, (const uint16_t *)b->kidx.p);
+    TRY(check_launch(e, "k_flank_seed"));
+  } else if (e->band_budget > 0) {  // unusual piece lengths: the one-pass first tier
     int grid = 0;
     TRY(persistent_grid(e, k_flank_band, 128, 0, &grid));
     const uint32_t need = (l1 - l0 + FB_LOCI - 1) / FB_LOCI;
@@ -636,9 +647,7 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
     LaunchScope ls(e, "k_flank_band");
     k_flank_band<<<grid, 128, 0, e->stream>>>(src, (const uint32_t *)b->locus_read_off.p, l0, l1, e->band_budget,
                                                 b->frac, (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work2.p,
-                                                (Counters *)b->ctr.p,
-                                                b->kidx_valid ? (const uint16_t *)b->kidx.p : nullptr,
-                                                /*prefetch=*/1);
+                                                (Counters *)b->ctr.p, nullptr, /*prefetch=*/1);
     TRY(check_launch(e, "k_flank_band"));
   }
   return 0;
@@ -647,6 +656,21 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
 // pairs the on-chip path deferred: full-width score pass + cone trace; then the combine rule
 static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src) {
   Counters *ctr = (Counters *)b->ctr.p;
+  if (e->band_budget > 0 && b->kidx_valid) {  // band pass of the first cost tier over the pairs the seed pass listed
+    static bool attr_set = false;
+    const size_t smem = sizeof(FlankBand1Smem);
+    if (!attr_set) {
+      CU(e, cudaFuncSetAttribute(k_flank_band1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    int grid = 0;
+    TRY(persistent_grid(e, k_flank_band1, FB1_THREADS, smem, &grid));
+    LaunchScope ls(e, "k_flank_band1");
+    k_flank_band1<<<grid, FB1_THREADS, smem, e->stream>>>(src, (const uint2 *)b->list1.p, &ctr->n_list1, e->band_budget,
+                                                          b->frac, src.reads + b->reads.cap,
+                                                          (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work2.p, ctr);
+    TRY(check_launch(e, "k_flank_band1"));
+  }
   if (e->band_budget > 0) {  // second cost tier for what the first handed on, one warp per pair
     int grid = 0;
     TRY(persistent_grid(e, k_flank_band2, 32, 0, &grid));

@@ -40,7 +40,7 @@ struct Counters {
   unsigned int n_tier2;                 // flank: pairs the first cost tier handed to k_flank_band2
   unsigned int n_resid;                 // e2e: pairs k_e2e_thread handed to the warp kernel
   unsigned int n_diff;                  // e2e: members that differ from their backbone (k_e2e_identity)
-  unsigned int pad3;
+  unsigned int n_list1;                // flank: pairs the seed pass listed for the band pass (k_flank_seed -> k_flank_band1)
 };
 
 enum { WFA_MODE_FLANK = 0, WFA_MODE_E2E = 1 };
@@ -401,6 +401,218 @@ k_flank_band(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
         hits[2 * r + side] = h;
       }
       g.sync();
+    }
+  }
+}
+
+// ---- bulk copies (TMA, 1-D) and their completion barriers ----
+// cp.async.bulk moves a 16-byte aligned run of global memory into shared memory with ONE instruction of ONE
+// thread and reports the bytes to an mbarrier; nobody holds registers for the data in flight.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+// this thread's arrival, announcing `bytes` of bulk copies that complete on the barrier
+__device__ __forceinline__ void mbar_arrive_expect(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+struct __align__(16) FlankSeedSmem {
+  uint16_t slot[2][TRGT_KIDX_SLOTS];  // both tables of the locus as k_flank_exact_t left them: one bulk copy
+  uint16_t list[FB_LIST];             // pending pairs of the pass: (read - first read of the pass) << 1 | side
+  unsigned long long bar;             // completion of the table copy
+};
+
+// Phase A, step 2a (seed pass of the first cost tier, see flank_tier1_seed_thread).  A half-warp per locus scans the
+// hit records of its reads; for every pending pair ONE LANE loads all probes of the read up front and takes the hull
+// of the diagonals of all index hits: `list1` (2 * read + side, klo << 3 | width - 1) for k_flank_band1, or `work2`
+// for k_flank_band2 if the pair is not for this tier.  Two global round trips per pair: hit records, probes.
+__global__ void __launch_bounds__(128, 8)
+k_flank_seed(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l_begin, uint32_t l_end,
+             int band_budget, trgt_flank_hit_t *__restrict__ hits, uint2 *__restrict__ list1,
+             uint32_t *__restrict__ work2, Counters *ctr, const uint16_t *__restrict__ kidx_in) {
+  __shared__ FlankSeedSmem sm_all[FB_LOCI];
+  const TileGroup<FB_LT> g;
+  FlankSeedSmem &sm = sm_all[threadIdx.x / FB_LT];
+  const int lane = g.lane();
+  if (lane == 0) mbar_init(&sm.bar, 1);
+  mbar_init_fence();
+  __syncthreads();
+  unsigned parity = 0;
+  for (uint32_t l = l_begin + blockIdx.x * FB_LOCI + threadIdx.x / FB_LT; l < l_end; l += gridDim.x * FB_LOCI) {
+    const uint32_t r0 = locus_read_off[l], r1 = locus_read_off[l + 1];
+    bool have_index = false;
+    const int P0 = (int)(src.lp_off[l + 1] - src.lp_off[l]), P1 = (int)(src.rp_off[l + 1] - src.rp_off[l]);
+    const uint8_t *pg0 = src.lp + src.lp_off[l], *pg1 = src.rp + src.rp_off[l];
+#pragma unroll 1
+    for (uint32_t rb = r0; rb < r1;) {
+      g.sync();
+      int n_list = 0;
+      uint32_t base = rb;
+      for (; base < r1 && n_list + 2 * FB_LT <= FB_LIST && base - rb < 16384u; base += FB_LT) {  // pending pairs, in read order
+        const uint32_t r = base + (uint32_t)lane;
+        unsigned m = 0;
+        if (r < r1) m = (hits[2 * r].via == TRGT_VIA_PENDING ? 1u : 0u) | (hits[2 * r + 1].via == TRGT_VIA_PENDING ? 2u : 0u);
+        const unsigned b0 = g.ballot(m & 1u), b1 = g.ballot(m & 2u);
+        const unsigned lt = (1u << lane) - 1u;
+        int pos = n_list + __popc(b0 & lt) + __popc(b1 & lt);
+        if (m & 1u) sm.list[pos++] = (uint16_t)(((r - rb) << 1) | 0u);
+        if (m & 2u) sm.list[pos] = (uint16_t)(((r - rb) << 1) | 1u);
+        n_list += __popc(b0) + __popc(b1);
+      }
+      const uint32_t rb_pass = rb;
+      rb = base;
+      g.sync();
+      if (n_list == 0) continue;
+      if (!have_index) {  // first pending pair of the locus: fetch both tables (2.6 KB, contiguous) in one bulk copy
+        have_index = true;
+        if (lane == 0) {
+          mbar_arrive_expect(&sm.bar, (unsigned)sizeof(sm.slot));
+          bulk_g2s(&sm.slot[0][0], kidx_in + (size_t)l * 2 * TRGT_KIDX_SLOTS, (unsigned)sizeof(sm.slot), &sm.bar);
+        }
+        mbar_wait(&sm.bar, parity);
+        parity ^= 1u;
+      }
+#pragma unroll 1
+      for (int ib = 0; ib < n_list; ib += FB_LT) {  // one pending pair per lane
+        const int i = ib + lane;
+        int listed = 0, deferred = 0;
+        uint32_t id = 0;
+        int klo = 0, khi = 0;
+        if (i < n_list) {
+          const int side = sm.list[i] & 1;
+          const uint32_t r = rb_pass + (uint32_t)(sm.list[i] >> 1);
+          id = 2 * r + (uint32_t)side;
+          WfaProb pr;
+          pr.x = src.x; pr.oe = src.oe; pr.e = src.e;
+          pr.p = side ? pg1 : pg0; pr.P = side ? P1 : P0;
+          pr.t = src.reads + src.read_off[r];
+          pr.T = (int)(src.read_off[r + 1] - src.read_off[r]);
+          pr.pbf = 0; pr.pef = 0; pr.tbf = pr.T; pr.tef = pr.T;  // span_locater.rs:17
+          wfa_unband(pr);
+          listed = pr.P >= 16 && pr.P <= FT1_PMAX &&
+                   flank_tier1_seed_thread(KmerIndex{sm.slot[side]}, pr, band_budget, &klo, &khi) == 1;
+          deferred = !listed;
+        }
+        const unsigned bl = g.ballot(listed), bd = g.ballot(deferred);
+        unsigned base1 = 0, base2 = 0;
+        if (lane == 0) {
+          if (bl) base1 = atomicAdd(&ctr->n_list1, (unsigned)__popc(bl));
+          if (bd) base2 = atomicAdd(&ctr->n_tier2, (unsigned)__popc(bd));
+        }
+        base1 = (unsigned)g.bcast0((int)base1);
+        base2 = (unsigned)g.bcast0((int)base2);
+        const unsigned lt = (1u << lane) - 1u;
+        if (listed) list1[base1 + __popc(bl & lt)] = make_uint2(id, (uint32_t)((klo * 8) | (khi - klo)));
+        if (deferred) {
+          work2[base2 + __popc(bd & lt)] = id;
+          trgt_flank_hit_t h;
+          h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
+          hits[id] = h;
+        }
+      }
+      g.sync();
+    }
+  }
+}
+
+#define FB1_THREADS 128
+
+struct __align__(16) FlankBand1Smem {
+  uint8_t win[FB1_THREADS][FT1_WIN_BYTES];               // a lane's text window, filled by its own bulk copy
+  int16_t hist[FB1_THREADS / 32][FT1_HIST_HALFS][32];    // 16-bit wavefront history, the lanes of a warp interleaved
+  unsigned long long bar[FB1_THREADS];                   // a lane's copy-complete barrier
+};
+
+// Phase A, step 2b (band pass of the first cost tier, see flank_tier1_band_thread).  ONE LANE PER LISTED PAIR, dense
+// warps: the lane fetches the <= 304 bytes of the read its band can touch with one bulk copy into its own window
+// and then runs the narrow-band wavefronts, their history and the back-trace entirely on chip; only the piece is
+// read through L1 (the ~13 pending pairs of a locus sit next to each other in the list).  Writes the hit, or hands
+// the pair on to `work2` (cost above this tier's cap).
+__global__ void __launch_bounds__(FB1_THREADS, 3)
+k_flank_band1(WfaSrc src, const uint2 *__restrict__ list1, const unsigned int *n_list1_ptr, int band_budget,
+              double min_flank_id_frac, const uint8_t *reads_end, trgt_flank_hit_t *__restrict__ hits,
+              uint32_t *__restrict__ work2, Counters *ctr) {
+  extern __shared__ __align__(16) unsigned char fb1_raw[];
+  FlankBand1Smem &sm = *reinterpret_cast<FlankBand1Smem *>(fb1_raw);
+  const int tid = threadIdx.x;
+  uint8_t *win = sm.win[tid];
+  int16_t *hist = &sm.hist[tid >> 5][0][tid & 31];
+  unsigned long long *bar = &sm.bar[tid];
+  mbar_init(bar, 1);
+  mbar_init_fence();
+  __syncthreads();
+  unsigned parity = 0;
+  const uint32_t n = *n_list1_ptr;
+  // whole warps walk the list (a lane past its end keeps company): the wavefront loop runs warp-uniform
+  for (uint32_t base = blockIdx.x * FB1_THREADS + (uint32_t)(tid & ~31); base < n; base += gridDim.x * FB1_THREADS) {
+    const uint32_t i = base + (uint32_t)(tid & 31);
+    const bool have = i < n;
+    uint32_t id = 0;
+    int klo = 0, khi = 0, a0 = 0;
+    WfaProb pr;
+    pr.p = nullptr; pr.t = nullptr; pr.P = 0; pr.T = 0; pr.x = src.x; pr.oe = src.oe; pr.e = src.e;
+    pr.pbf = pr.pef = pr.tbf = pr.tef = 0; pr.blo = 0; pr.bhi = 0;
+    if (have) {
+      const uint2 ent = list1[i];
+      id = ent.x;
+      klo = ((int)ent.y) >> 3;
+      khi = klo + (int)(ent.y & 7u);
+      pr = wfa_prob_of(src, id);
+      // the text the band can touch: offsets [first, last) of the read, from the 16-byte boundary below `first`
+      const int first = klo > 0 ? klo : 0;
+      const int last = wfa_imin(pr.T, khi + pr.P) + 12;
+      const uint8_t *a = pr.t + first;
+      const int slack = (int)((uintptr_t)a & 15u);
+      const uint8_t *a_al = a - slack;
+      a0 = first - slack;
+      unsigned bytes = (unsigned)(slack + (last - first) + 15) & ~15u;
+      if (bytes > FT1_WIN_BYTES) bytes = FT1_WIN_BYTES;
+      const size_t room = (size_t)(reads_end - a_al) & ~(size_t)15;  // never past the padded end of the read buffer
+      if ((size_t)bytes > room) bytes = (unsigned)room;
+      mbar_arrive_expect(bar, bytes);
+      bulk_g2s(win, a_al, bytes, bar);
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+    }
+    __syncwarp();
+    FlankHit fh;
+    fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
+    const int deferred = flank_tier1_band_thread<32>(pr, klo, khi, band_budget, min_flank_id_frac, win, a0, hist, &fh,
+                                                     0xffffffffu, !have);
+    __syncwarp();
+    if (have) {
+      trgt_flank_hit_t h;
+      h.via = TRGT_VIA_NONE; h.matches = 0; h.score = 0; h.start = 0; h.end = 0;
+      if (!deferred) {
+        h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
+        h.start = (uint32_t)fh.start; h.end = (uint32_t)fh.end;
+      } else {
+        const unsigned int slot = atomicAdd(&ctr->n_tier2, 1u);
+        work2[slot] = id;
+      }
+      hits[id] = h;
     }
   }
 }

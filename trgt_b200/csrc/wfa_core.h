@@ -523,10 +523,19 @@ TRGT_HD WfaEnd wfa_forward_band_hist(const G &g, const WfaProb &pr, int s_cap, i
   return out;
 }
 
-// Back-trace from (s_end, k_end) through the history in ws; ops are handed to the sink from the
-// LAST operation to the first.  One lane.
-template <class Sink>
-TRGT_HD void wfa_backtrace(const WfaProb &pr, int s_end, int k_end, int off_end, int *ws, Sink &sink) {
+// The wavefront history as wfa_trace_forward / wfa_forward_band_hist* leave it in `ws`, read cell by cell
+// (TRGT_WFA_NULL for a cell that is not stored).
+struct WfaWsHist {
+  int *ws;
+  TRGT_HD int m(int s, int k) const { const WfaView v = wfa_hist_view(ws, s); return wfa_at(v.m, v, k); }
+  TRGT_HD int i(int s, int k) const { const WfaView v = wfa_hist_view(ws, s); return wfa_at(v.i, v, k); }
+  TRGT_HD int d(int s, int k) const { const WfaView v = wfa_hist_view(ws, s); return wfa_at(v.d, v, k); }
+};
+
+// Back-trace from (s_end, k_end) through a wavefront history (any type with m / i / d readers, see
+// WfaWsHist); ops are handed to the sink from the LAST operation to the first.  One lane.
+template <class Hist, class Sink>
+TRGT_HD void wfa_backtrace_h(const WfaProb &pr, int s_end, int k_end, int off_end, const Hist &hist, Sink &sink) {
   enum { T_I1O = 1, T_I1E = 2, T_D1O = 5, T_D1E = 6, T_M = 9 };
   enum { C_M = 0, C_I = 1, C_D = 2 };
   int k = k_end, off = off_end;
@@ -537,12 +546,11 @@ TRGT_HD void wfa_backtrace(const WfaProb &pr, int s_end, int k_end, int off_end,
 #define TRGT_PG(o, tag) ((o) < 0 ? (long long)TRGT_WFA_NULL : ((((long long)(o)) << 4) | (tag)))
   while (v > 0 && h > 0 && sc > 0) {
     const int sx = sc - pr.x, so = sc - pr.oe, se = sc - pr.e;
-    const WfaView vx = wfa_hist_view(ws, sx), vo = wfa_hist_view(ws, so), ve = wfa_hist_view(ws, se);
-    const long long c_m = TRGT_PG(wfa_at(vx.m, vx, k) + 1, T_M);
-    const long long c_io = TRGT_PG(wfa_at(vo.m, vo, k - 1) + 1, T_I1O);
-    const long long c_ie = TRGT_PG(wfa_at(ve.i, ve, k - 1) + 1, T_I1E);
-    const long long c_do = TRGT_PG(wfa_at(vo.m, vo, k + 1), T_D1O);
-    const long long c_de = TRGT_PG(wfa_at(ve.d, ve, k + 1), T_D1E);
+    const long long c_m = TRGT_PG(hist.m(sx, k) + 1, T_M);
+    const long long c_io = TRGT_PG(hist.m(so, k - 1) + 1, T_I1O);
+    const long long c_ie = TRGT_PG(hist.i(se, k - 1) + 1, T_I1E);
+    const long long c_do = TRGT_PG(hist.m(so, k + 1), T_D1O);
+    const long long c_de = TRGT_PG(hist.d(se, k + 1), T_D1E);
     long long mx;
     if (mt == C_M) {
       mx = c_m;
@@ -581,6 +589,12 @@ TRGT_HD void wfa_backtrace(const WfaProb &pr, int s_end, int k_end, int off_end,
   }
   sink.op('D', v);
   sink.op('I', h);
+}
+
+template <class Sink>
+TRGT_HD void wfa_backtrace(const WfaProb &pr, int s_end, int k_end, int off_end, int *ws, Sink &sink) {
+  const WfaWsHist hist{ws};
+  wfa_backtrace_h(pr, s_end, k_end, off_end, hist, sink);
 }
 
 // End-to-end alignment of a short pair in one pass: with cost cap S every cell the full computation
@@ -985,8 +999,10 @@ TRGT_HD bool fxt_verify(const uint8_t *copies, int P, const uint8_t *a) {
 // (a verification's sixteen-byte compares) run with the whole warp.  0 (and the CPU test build): no-op.
 #if defined(__CUDA_ARCH__)
 #define TRGT_CONVERGE(lanes) do { if (lanes) __syncwarp(lanes); } while (0)
+#define TRGT_ANY(lanes, p) ((lanes) ? __any_sync((lanes), (p)) : (p))
 #else
 #define TRGT_CONVERGE(lanes) do { (void)(lanes); } while (0)
+#define TRGT_ANY(lanes, p) ((void)(lanes), (p))
 #endif
 
 TRGT_HD int flank_exact_thread(const KmerIndex &idx, const uint8_t *copies, int P, const uint8_t *t, int T,
@@ -1368,6 +1384,265 @@ TRGT_HD int flank_locate_tier1_thread(const WfaProb &pr, int S, double min_flank
   if (end.status != TRGT_WFA_OK) return 1;
   WfaFlankSink sink(pr.T);
   wfa_backtrace(pr, end.s, end.k, end.off, ws, sink);
+  hit->matches = sink.matches;
+  hit->score = -end.s;
+  if ((double)sink.matches >= (double)pr.P * min_flank_id_frac) {  // span_locater.rs:19-25, :46
+    hit->via = 2; hit->start = sink.ystart(); hit->end = sink.yend();
+  } else {
+    hit->via = 3; hit->start = 0; hit->end = 0;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- first cost tier in two passes ---
+//
+// flank_locate_tier1_thread above walks a chain of dependent loads per pair: probe -> table -> block
+// verification (8-byte steps over the read in HBM) -> match extensions (the same) -> history in local memory.
+// The two routines below do the same computation with two global round trips per pair:
+//   seed pass   every probe is loaded up front; the band is the hull of the diagonals of ALL index hits
+//               (checked on 16 bases only, not on the whole block).  Every alignment of cost <= S contains an intact block, that block's 8-mer
+//               at its probe is in the table, so the hull of all hits contains the hull of the true block
+//               occurrences: a superset band, and the banded computation equals the full one on any band
+//               that contains every alignment of cost <= S (see flank_seed_band).  A chance hit elsewhere
+//               only makes the hull too wide for this tier; those pairs take the verifying filter.
+//   band pass   the text window the band can touch ([klo, khi + P], <= 304 bytes) is staged on chip in one
+//               bulk copy, the history lives on chip as 16-bit offsets relative to the band's lowest
+//               diagonal, and the back-trace reads it through the same routine as every other path.
+
+TRGT_HD int ft1_ld(int16_t v, int blo) { return v < 0 ? TRGT_WFA_NULL : (int)v + blo; }
+
+// wfa_ld64u with the address space spelled out: the piece through the read-only path, the window from shared memory
+TRGT_HD uint64_t ft1_ld64_piece(const uint8_t *a) {
+#if defined(__CUDA_ARCH__)
+  const uintptr_t addr = (uintptr_t)a;
+  const uint32_t *w = (const uint32_t *)(addr & ~(uintptr_t)3);
+  const unsigned sh = (unsigned)(addr & 3u) * 8u;
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+  return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+#else
+  return wfa_ld64u(a);
+#endif
+}
+TRGT_HD uint64_t ft1_ld64_win(const uint8_t *a) {
+#if defined(__CUDA_ARCH__)
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(a);
+  const unsigned base = addr & ~3u, sh = (addr & 3u) * 8u;
+  uint32_t w0, w1, w2;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(base));
+  asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(base));
+  asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(base));
+  return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+#else
+  return wfa_ld64u(a);
+#endif
+}
+// wfa_match_len(piece, window, n)
+TRGT_HD int ft1_match_len(const uint8_t *p, const uint8_t *w, int n) {
+  int i = 0;
+  while (i < n) {
+    const uint64_t x = ft1_ld64_piece(p + i) ^ ft1_ld64_win(w + i);
+    if (x) {
+      i += wfa_ctz64(x) >> 3;
+      return i < n ? i : n;
+    }
+    i += 8;
+  }
+  return n;
+}
+
+// floor(d / blen) for d < 512 by multiplication: inv = ceil(2^20 / blen)
+TRGT_HD uint32_t ft1_div_magic(int blen) { return ((1u << 20) + (uint32_t)blen - 1u) / (uint32_t)blen; }
+
+// 1 and [klo, khi] (hull of every index hit +- R), or 0 if there is no hit
+TRGT_HD int flank_seed_hull_thread(const KmerIndex &idx, const WfaProb &pr, int S, int *klo, int *khi) {
+  const int nb = flank_seed_blocks(pr, S);
+  if (nb > 32) return 0;
+  const int blen = pr.P / nb;
+  if (blen < TRGT_SEED_BLEN_MIN || pr.T < blen) return 0;
+  const int o = pr.oe - pr.e;
+  const int R = S > o ? (S - o) / pr.e : 0;
+  const int step = blen - 7;
+  const int n_probes = (pr.T - 7) / step;
+  const uint32_t inv = ft1_div_magic(blen);
+  int kmin = INT_MAX, kmax = INT_MIN;
+  for (int ib = 0; ib < n_probes; ib += 6) {  // six probes per step: their loads go out together
+    uint64_t key[6];
+#pragma unroll
+    for (int u = 0; u < 6; u++) key[u] = ib + u < n_probes ? wfa_ld64u(pr.t + (ib + u + 1) * step - 1) : 0;
+#pragma unroll
+    for (int u = 0; u < 6; u++) {
+      if (ib + u >= n_probes) break;
+      const int j = (ib + u + 1) * step - 1;
+      const uint64_t mixed = kidx_mix(key[u]);
+      const uint32_t fp = kidx_fp(mixed);
+      uint32_t v;
+      TRGT_KIDX_FOR(idx, mixed, v) {
+        if ((v >> 9) != fp) continue;
+        const int d = (int)(v & 511u), b = (int)(((uint32_t)d * inv) >> 20), r = d - b * blen, q = j - r;
+        if (b >= nb || r + 8 > blen || q < 0 || q + blen > pr.T) continue;
+        // a fingerprint clash or a chance 8-mer would push the pair onto the verifying path: compare the 8-mer itself
+        // and eight more bases of the block (a true block occurrence passes both)
+        if (wfa_ld64u(pr.p + d) != key[u]) continue;
+        if (r + 16 <= blen) { if (wfa_ld64u(pr.p + d + 8) != wfa_ld64u(pr.t + j + 8)) continue; }
+        else if (r >= 8) { if (wfa_ld64u(pr.p + d - 8) != wfa_ld64u(pr.t + j - 8)) continue; }
+        const int k = j - d;
+        kmin = wfa_imin(kmin, k);
+        kmax = wfa_imax(kmax, k);
+      }
+    }
+  }
+  if (kmin == INT_MAX) return 0;
+  *klo = wfa_imax(-pr.P, kmin - R);
+  *khi = wfa_imin(pr.T, kmax + R);
+  return 1;
+}
+
+// Seed pass of one pair: 1 and the band if the band pass can take it, 0 if the pair goes to the next tier.
+// pr.p must be readable (only the rare verifying path reads it).
+TRGT_HD int flank_tier1_seed_thread(const KmerIndex &idx, const WfaProb &pr, int S, int *klo, int *khi) {
+  const int cap = wfa_imin(S, wfa_imax(pr.x, pr.oe));
+  if (cap > FT1_SMAX) return 0;
+  if (flank_seed_hull_thread(idx, pr, cap, klo, khi) != 1) return 0;  // no hit at all: no verified one either
+  if (*khi - *klo + 1 <= FT1_WMAX && *khi + pr.P < pr.T) return 1;  // (the text-end rule of flank_seed_band)
+  if (flank_seed_band_thread(idx, pr, cap, klo, khi) != 1) return 0;  // a hit off the alignment: verify them
+  return *khi - *klo + 1 <= FT1_WMAX ? 1 : 0;
+}
+
+#define FT1_WIN_BYTES 304  // text window of a pair: <= 256 of piece + band + 15 of alignment + 11 of over-read, in 16-byte chunks
+#define FT1_PMAX 256       // longest piece the band pass takes
+#define FT1_HIST_HALFS ((FT1_SMAX + 1) * 3 * FT1_WMAX)  // 16-bit cells of one pair's history (216 bytes)
+
+// History of the band pass: cell (s, component, k) at h[((s * 3 + c) * FT1_WMAX + k - blo) * LS] as offset - blo
+// (never negative for a reachable cell), -1 = null.  LS = distance between a lane's consecutive cells (cells of
+// the lanes of a warp interleaved: every lane of a converged access hits its own bank).
+template <int LS>
+struct Ft1Hist {
+  int16_t *h;
+  int blo, W;
+  unsigned present;  // bit s: score s has a wavefront
+  TRGT_HD int cell(int s, int c, int k) const {
+    if (s < 0 || !((present >> s) & 1u) || k < blo || k >= blo + W) return TRGT_WFA_NULL;
+    const int v = h[((s * 3 + c) * FT1_WMAX + (k - blo)) * LS];
+    return v < 0 ? TRGT_WFA_NULL : v + blo;
+  }
+  TRGT_HD int m(int s, int k) const { return cell(s, 0, k); }
+  TRGT_HD int i(int s, int k) const { return s < 1 ? TRGT_WFA_NULL : cell(s, 1, k); }
+  TRGT_HD int d(int s, int k) const { return s < 1 ? TRGT_WFA_NULL : cell(s, 2, k); }
+};
+
+// wfa_forward_band_hist_narrow_thread on the staged window: text offset h lives at win[h - a0].
+// Written as ONE loop whose iteration is "one 8-byte step of the match extension in progress, then -- if that
+// extension is over -- record the cell and start the next one": the lanes of a warp, each on its own pair, have
+// their long extensions in different cells, and with a loop per cell every cell would cost the warp its longest
+// extension among 32 pairs.  This way a lane's trip count is (cells + 8-byte steps), nearly the same for all.
+// lanes: the lanes of the warp that call this together (they leave the loop together, so that the hardware keeps
+// them on one instruction stream; 0 = a lane on its own); idle: this lane has no pair and only keeps company.
+template <int LS>
+TRGT_HD WfaEnd ft1_forward(const WfaProb &pr, int s_cap, const uint8_t *win, int a0, int16_t *hist, unsigned *present_out,
+                           unsigned lanes, bool idle) {
+  WfaEnd out;
+  out.status = TRGT_WFA_OK; out.s = 0; out.k = 0; out.off = 0;
+  const int W = pr.bhi - pr.blo + 1;
+  unsigned present = 0;       // bit s: score s has a wavefront with some cell that is not null (an all-null wavefront
+                              // reads exactly like an absent one, so it is neither computed nor stored)
+  unsigned present_gap = 0;   // bit s: some I or D cell of score s is not null
+  bool row_m = false, row_gap = false;
+#define FT1_LD(s_, c_, i_) ft1_ld(hist[(((s_) * 3 + (c_)) * FT1_WMAX + (i_)) * LS], pr.blo)
+#define FT1_ST(s_, c_, i_, val) hist[(((s_) * 3 + (c_)) * FT1_WMAX + (i_)) * LS] = (int16_t)((val) < 0 ? -1 : (val) - pr.blo)
+  int s = 0, idx = -1;       // the cell in progress (idx = -1: none yet)
+  int cur = TRGT_WFA_NULL;   // its offset so far
+  int n_rem = 0;             // bases its extension may still cover
+  int endk = INT_MAX, endoff = 0;
+  bool px = false, po = false, pe = false;
+  bool done = idle;
+  while (TRGT_ANY(lanes, !done)) {
+    if (!done && n_rem > 0) {  // one step of the match extension along the diagonal
+      const int v = cur - (pr.blo + idx);
+      const uint64_t x = ft1_ld64_piece(pr.p + v) ^ ft1_ld64_win(win + (cur - a0));
+      int adv = x ? (wfa_ctz64(x) >> 3) : 8;
+      if (adv > n_rem) adv = n_rem;
+      cur += adv;
+      n_rem = x ? 0 : n_rem - adv;
+    }
+    if (!done && n_rem == 0) {
+      if (idx >= 0) {  // the cell is complete
+        FT1_ST(s, 0, idx, cur);
+        row_m |= cur >= 0;
+        if (endk == INT_MAX && cur >= 0) {  // end condition, lowest diagonal first
+          const int h = cur, v = cur - (pr.blo + idx);
+          if (v >= 0 && v <= pr.P && h <= pr.T &&
+              ((h >= pr.T && pr.P - v <= pr.pef) || (v >= pr.P && pr.T - h <= pr.tef))) { endk = pr.blo + idx; endoff = cur; }
+        }
+      }
+      idx++;
+      if (idx == W) {  // the wavefront of score s is complete
+        if (row_m || row_gap) present |= 1u << s;
+        if (row_gap) present_gap |= 1u << s;
+        row_m = row_gap = false;
+        if (endk != INT_MAX) {
+          out.s = s; out.k = endk; out.off = endoff;
+          done = true;
+        }
+        bool live = done;
+        while (!live && ++s <= s_cap) {
+          const int sx = s - pr.x, so = s - pr.oe, se = s - pr.e;
+          px = sx >= 0 && ((present >> sx) & 1u);
+          po = so >= 0 && ((present >> so) & 1u);
+          pe = se >= 1 && ((present_gap >> se) & 1u);
+          live = px || po || pe;
+        }
+        if (!live) { out.status = TRGT_WFA_MAX_STEPS; done = true; }
+        idx = 0;
+      }
+      // start of cell (s, idx)
+      const int k = pr.blo + idx;
+      int mx = TRGT_WFA_NULL;
+      if (done) {
+      } else if (s == 0) {
+        if (k >= -pr.pbf && k <= pr.tbf) mx = k >= 0 ? k : 0;
+      } else {
+        const int sx = s - pr.x, so = s - pr.oe, se = s - pr.e;
+        const int o_l = (po && idx > 0) ? FT1_LD(so, 0, idx - 1) : TRGT_WFA_NULL;
+        const int o_r = (po && idx + 1 < W) ? FT1_LD(so, 0, idx + 1) : TRGT_WFA_NULL;
+        const int i_l = (pe && idx > 0) ? FT1_LD(se, 1, idx - 1) : TRGT_WFA_NULL;
+        const int d_r = (pe && idx + 1 < W) ? FT1_LD(se, 2, idx + 1) : TRGT_WFA_NULL;
+        const int i1 = wfa_imax(o_l, i_l) + 1;
+        const int d1 = wfa_imax(o_r, d_r);
+        const int mm = (px ? FT1_LD(sx, 0, idx) : TRGT_WFA_NULL) + 1;
+        mx = wfa_imax(mm, wfa_imax(i1, d1));
+        const int h = mx, v = mx - k;
+        if (mx < 0 || h > pr.T || v > pr.P || v < 0) mx = TRGT_WFA_NULL;
+        FT1_ST(s, 1, idx, i1);
+        FT1_ST(s, 2, idx, d1);
+        row_gap |= i1 >= 0 || d1 >= 0;
+      }
+      cur = mx;
+      n_rem = mx >= 0 ? wfa_imax(0, wfa_imin(pr.P - (mx - k), pr.T - mx)) : 0;
+    }
+  }
+#undef FT1_LD
+#undef FT1_ST
+  *present_out = present;
+  return out;
+}
+
+// Band pass of one pair the seed pass listed with band [klo, khi]: 0 and *hit filled, or 1 if the pair goes to
+// the next tier.  pr: the pair as the reference poses it (pr.t is not dereferenced: the text is read from the
+// window, win[h - a0] = text[h] for every h in [max(klo, 0), min(T, khi + P) + 11]).
+template <int LS>
+TRGT_HD int flank_tier1_band_thread(const WfaProb &pr, int klo, int khi, int S, double min_flank_id_frac,
+                                    const uint8_t *win, int a0, int16_t *hist, FlankHit *hit, unsigned lanes = 0,
+                                    bool idle = false) {
+  const int cap = wfa_imin(S, wfa_imax(pr.x, pr.oe));
+  const bool skip = idle || cap > FT1_SMAX || khi - klo + 1 > FT1_WMAX;
+  WfaProb bp = pr;
+  bp.blo = klo; bp.bhi = khi;
+  unsigned present = 0;
+  const WfaEnd end = ft1_forward<LS>(bp, cap, win, a0, hist, &present, lanes, skip);
+  if (skip || end.status != TRGT_WFA_OK) return 1;
+  const Ft1Hist<LS> H{hist, klo, khi - klo + 1, present};
+  WfaFlankSink sink(pr.T);
+  wfa_backtrace_h(pr, end.s, end.k, end.off, H, sink);
   hit->matches = sink.matches;
   hit->score = -end.s;
   if ((double)sink.matches >= (double)pr.P * min_flank_id_frac) {  // span_locater.rs:19-25, :46
