@@ -181,6 +181,38 @@ int32_t trgt_flank_spans_seq4(trgt_engine_t *eng, const trgt_seqs_t *left_pieces
 int32_t trgt_seq4_decode(trgt_engine_t *eng, const trgt_seq4_t *reads, uint8_t *ascii_out,
                          uint64_t *ascii_offsets_out);
 
+/* ---- consumer of phase A's output: the reads of the BAMlet (next row, rank 4) ---- */
+
+#define TRGT_BAMLET_SKIPPED 0   /* no span, or "unexpectedly short flanks" (write_bam.rs:80-83, :88-91): no record */
+#define TRGT_BAMLET_WRITE 1
+
+/* HiFiRead::clip_bases (src/trgt/reads/clip_bases.rs:9-119) as BamWriter::write asks for it
+ * (src/trgt/writers/write_bam.rs:72-92: flank_len bases either side of the repeat span): the record's bases and
+ * quals are [base_start, base_end) of the clipped read, its methylation profile entries [meth_start, meth_end)
+ * (one entry per "CG" of the read, clip_bases.rs:23-44), its CIGAR
+ * [first_word, ops[first_op+1 .. first_op+n_ops-2], last_word] at ref_pos (n_ops == 0 for a read without CIGAR:
+ * the writer marks it unmapped at the locus start, write_bam.rs:108-112).  The record itself (rust-htslib
+ * Record::set / push_aux, :95-140) stays with the host's BAM writer. */
+typedef struct {
+  int64_t ref_pos;
+  uint32_t base_start, base_end;
+  uint32_t meth_start, meth_end;
+  uint32_t first_op, n_ops;
+  uint32_t first_word, last_word;
+  int32_t status;   /* TRGT_BAMLET_WRITE, TRGT_BAMLET_SKIPPED, TRGT_ITEM_INVALID_OP where the reference panics / exits
+                       (clip_bases.rs:61,80,106) */
+  uint32_t pad;
+} trgt_bamlet_clip_t;
+
+/* clip_bases for every read of a resident phase-A batch that has run (the clipped reads and their spans are in
+ * HBM already: only the CIGARs go up and 48 bytes per read come back).
+ *   cigar_ops / cigar_offsets[n_reads+1]: the reads' CIGARs after clip_to_region, BAM words (len<<4)|op; a read
+ *   without CIGAR has an empty range; ref_starts[n_reads] = cigar.ref_pos; clips_out[n_reads];
+ *   batch == NULL: the batch of the last one-shot trgt_flank_spans / trgt_flank_spans_seq4 call on this engine */
+int32_t trgt_bamlet_clip(trgt_engine_t *eng, trgt_flank_batch_t *batch, const uint32_t *cigar_ops,
+                         const uint64_t *cigar_offsets, const int64_t *ref_starts, uint32_t flank_len,
+                         trgt_bamlet_clip_t *clips_out);
+
 /* ---- phase B: consensus alignments (a5) and edit distances (a6) ---------- */
 
 typedef struct {

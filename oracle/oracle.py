@@ -77,6 +77,12 @@ class _OptSpan(C.Structure):
     _fields_ = [("found", C.c_int32), ("start", C.c_uint32), ("end", C.c_uint32)]
 
 
+class _BamletClip(C.Structure):
+    _fields_ = [("ref_pos", C.c_int64), ("base_start", C.c_uint64), ("base_end", C.c_uint64),
+                ("meth_start", C.c_uint32), ("meth_end", C.c_uint32), ("first_op", C.c_uint32), ("n_ops", C.c_uint32),
+                ("first_word", C.c_uint32), ("last_word", C.c_uint32), ("has_cigar", C.c_int32), ("pad", C.c_int32)]
+
+
 class _Clip(C.Structure):
     _fields_ = [("ref_start", C.c_int64), ("query_start", C.c_uint64), ("query_end", C.c_uint64),
                 ("first_op", C.c_uint32), ("n_ops", C.c_uint32), ("first_word", C.c_uint32),
@@ -149,6 +155,12 @@ def lib():
         L.tro_repair_consensus.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, vp, C.c_uint32, vp, vp, vp, C.c_uint64]
         L.tro_clip_cigar.argtypes = [vp, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_Clip)]
         L.tro_decode_seq4.argtypes = [vp, C.c_uint64, C.c_uint32, vp]
+        L.tro_meth_range.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.tro_meth_range.restype = None
+        L.tro_clip_bases.argtypes = [vp, C.c_uint32, C.c_int64, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                     C.POINTER(_BamletClip)]
+        L.tro_bamlet_clip.argtypes = [vp, C.c_uint32, C.c_int64, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                      C.c_uint64, C.POINTER(_BamletClip)]
         L.tro_decode_seq4.restype = None
         L.tro_vcf_field.restype = C.c_size_t
         L.tro_vcf_field.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_char_p, C.c_size_t]
@@ -544,6 +556,56 @@ def clip_cigar(ops: Sequence[int], ref_pos: int, region: Tuple[int, int]):
         else:
             words.append(int(arr[out.first_op + i]))
     return out.ref_start, out.query_start, out.query_end, words
+
+
+def meth_range(bases: bytes, start: int, end: int) -> Tuple[int, int]:
+    """which methylation entries a clip to bases [start, end) keeps (clip_region.rs:40-58, clip_bases.rs:23-44)"""
+    m0, m1 = C.c_uint32(), C.c_uint32()
+    lib().tro_meth_range(bases, len(bases), start, end, C.byref(m0), C.byref(m1))
+    return m0.value, m1.value
+
+
+def _bamlet_words(out, arr):
+    words = []
+    for i in range(out.n_ops):
+        if i == 0:
+            words.append(out.first_word)
+        elif i == out.n_ops - 1:
+            words.append(out.last_word)
+        else:
+            words.append(int(arr[out.first_op + i]))
+    return words
+
+
+def clip_bases(bases: bytes, ops: Optional[Sequence[int]], ref_pos: int, left_len: int, right_len: int):
+    """HiFiRead::clip_bases (clip_bases.rs:9-119).  None, or (base_start, base_end, meth_start, meth_end,
+    cigar) with cigar = None for a read without one, else (ref_pos, BAM words)."""
+    np = _np()
+    arr = np.array(list(ops) if ops else [0], dtype=np.uint32)
+    out = _BamletClip()
+    rc = lib().tro_clip_bases(arr.ctypes.data, len(ops) if ops else 0, ref_pos, bases, len(bases), left_len, right_len,
+                              C.byref(out))
+    if rc < 0:
+        raise ValueError("clip_bases: the reference panics")
+    if rc == 0:
+        return None
+    cigar = (out.ref_pos, _bamlet_words(out, arr)) if out.has_cigar else None
+    return out.base_start, out.base_end, out.meth_start, out.meth_end, cigar
+
+
+def bamlet_clip(bases: bytes, ops: Optional[Sequence[int]], ref_pos: int, span: Tuple[int, int], flank_len: int):
+    """the clip BamWriter::write asks for (write_bam.rs:80-92); None = skipped"""
+    np = _np()
+    arr = np.array(list(ops) if ops else [0], dtype=np.uint32)
+    out = _BamletClip()
+    rc = lib().tro_bamlet_clip(arr.ctypes.data, len(ops) if ops else 0, ref_pos, bases, len(bases), span[0], span[1],
+                               flank_len, C.byref(out))
+    if rc < 0:
+        raise ValueError("clip_bases: the reference panics")
+    if rc == 0:
+        return None
+    cigar = (out.ref_pos, _bamlet_words(out, arr)) if out.has_cigar else None
+    return out.base_start, out.base_end, out.meth_start, out.meth_end, cigar
 
 
 def encode_seq4(bases: bytes) -> bytes:

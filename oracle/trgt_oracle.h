@@ -185,6 +185,30 @@ int tro_clip_cigar(const uint32_t *ops, uint32_t n_ops, int64_t ref_start, int64
 /* rec.seq().as_bytes() (read.rs:104) for bases [start, start+len) of a BAM 4-bit sequence */
 void tro_decode_seq4(const uint8_t *packed, uint64_t start, uint32_t len, uint8_t *out);
 
+/* ------------------------------------------ next row: BAMlet clipping -- */
+
+/* Result of HiFiRead::clip_bases (clip_bases.rs:9-56): bases / quals [base_start, base_end), methylation entries
+ * [meth_start, meth_end), and -- if the read has a CIGAR -- its clipped form
+ * [first_word, ops[first_op+1 .. first_op+n_ops-2], last_word] at reference position ref_pos. */
+typedef struct {
+  int64_t ref_pos;
+  uint64_t base_start, base_end;
+  uint32_t meth_start, meth_end;
+  uint32_t first_op, n_ops;
+  uint32_t first_word, last_word;
+  int32_t has_cigar;
+  int32_t pad;
+} tro_bclip;
+
+/* which methylation entries a clip to bases [start, end) keeps: clip_region.rs:40-58, clip_bases.rs:23-44 */
+void tro_meth_range(const uint8_t *bases, uint64_t len, uint64_t start, uint64_t end, uint32_t *m0, uint32_t *m1);
+/* clip_bases.rs:9-119.  1 = Some, 0 = None, -1 = the reference panics */
+int tro_clip_bases(const uint32_t *ops, uint32_t n_ops, int64_t ref_pos, const uint8_t *bases, uint64_t len,
+                   uint64_t left_len, uint64_t right_len, tro_bclip *out);
+/* the clip of BamWriter::write, write_bam.rs:80-92.  1 = written, 0 = skipped (short flanks / None), -1 = panic */
+int tro_bamlet_clip(const uint32_t *ops, uint32_t n_ops, int64_t ref_pos, const uint8_t *bases, uint64_t len,
+                    uint64_t span_start, uint64_t span_end, uint64_t flank_len, tro_bclip *out);
+
 /* ------------------------------------------ next row: VCF sample fields -- */
 
 /* One field (0 AL, 1 MC, 2 MS, 3 AP) of one locus: src/trgt/writers/write_vcf.rs:267-343.  Returns the

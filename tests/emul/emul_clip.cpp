@@ -37,4 +37,19 @@ int emu_vcf_fixed6(double v, char *out) {
   return (int)w.n;
 }
 
+// clip_bases for the BAMlet (bamlet_clip_read) by `lanes` lanes (0 = one serial lane)
+void emu_bamlet_clip(const uint8_t *bases, uint32_t len, int found, uint32_t span_start, uint32_t span_end,
+                     uint32_t flank_len, const uint32_t *ops, uint32_t n_ops, long long ref_pos, int lanes,
+                     trgt_bamlet_clip_t *out) {
+  if (lanes == 0) {
+    SerialGroup g;
+    *out = bamlet_clip_read(g, bases, len, found != 0, span_start, span_end, flank_len, ops, n_ops, ref_pos);
+  } else {
+    trgt_test::run_lanes(lanes, [&](const trgt_test::LaneGroup &g) {
+      const trgt_bamlet_clip_t c = bamlet_clip_read(g, bases, len, found != 0, span_start, span_end, flank_len, ops, n_ops, ref_pos);
+      if (g.lane() == 0) *out = c;
+    });
+  }
+}
+
 }  // extern "C"

@@ -7,6 +7,8 @@ import math
 import os
 import random
 
+import numpy as np
+
 import pytest
 
 from tests.emul import build as emul_build
@@ -789,6 +791,101 @@ def test_flank_tier1_split_core(emul, oracle):
             assert (two[4], two[5]) == exp, (it, x, o, e)
             seen["negative_k"] += exp[0] == 0
     assert seen["settled"] > 1200 and seen["handed_on"] > 50 and seen["rejected"] > 5 and seen["decoy_settled"] > 100, seen
+
+
+def _bamlet_expect(oracle, bases, ops, ref_pos, span, flank_len):
+    """oracle.bamlet_clip -> the fields of trgt_bamlet_clip_t (status, base range, methylation range, ref_pos, words)"""
+    if span is None:
+        return (0,)
+    try:
+        res = oracle.bamlet_clip(bases, ops, ref_pos, span, flank_len)
+    except ValueError:
+        return (-500,)
+    if res is None:
+        return (0,)
+    b0, b1, m0, m1, cig = res
+    return (1, b0, b1, m0, m1) + ((cig[0], cig[1]) if cig is not None else (None, []))
+
+
+def bamlet_got(c, ops):
+    """trgt_bamlet_clip_t (numpy record or ctypes struct fields by name) -> the same tuple"""
+    st = int(c["status"])
+    if st != 1:
+        return (st,)
+    n = int(c["n_ops"])
+    words = [int(c["first_word"]) if k == 0 else int(c["last_word"]) if k == n - 1 else int(ops[int(c["first_op"]) + k])
+             for k in range(n)]
+    has_cigar = len(ops) > 0
+    return (1, int(c["base_start"]), int(c["base_end"]), int(c["meth_start"]), int(c["meth_end"]),
+            int(c["ref_pos"]) if has_cigar else None, words)
+
+
+def random_bamlet_case(rng):
+    """a clipped read with a CIGAR whose query length is the read's, a span and a flank length"""
+    n = rng.choice([2, 5, 31, 200, 1100])
+    bases = bytes(rng.choice(b"ACGT" if rng.random() < 0.7 else b"CG") for _ in range(n))
+    ops = []
+    if rng.random() < 0.85:
+        left = n
+        if rng.random() < 0.5:
+            k = rng.randint(1, max(1, min(20, left)))
+            ops.append((k << 4) | 4); left -= k
+        while left > 0:
+            op = rng.choice([7, 7, 7, 8, 1, 2, 0, 3])
+            k = rng.randint(1, max(1, min(60, left))) if op not in (2, 3) else rng.randint(1, 9)
+            ops.append((k << 4) | op)
+            if op not in (2, 3):
+                left -= k
+        if rng.random() < 0.3 and (ops[-1] & 15) in (7, 0):   # a soft clip at the end
+            k = ops[-1] >> 4
+            cut = rng.randint(1, k)
+            ops[-1] = ((k - cut) << 4) | (ops[-1] & 15) if k > cut else (cut << 4) | 4
+            if k > cut:
+                ops.append((cut << 4) | 4)
+        if rng.random() < 0.05:
+            ops.append((3 << 4) | 7)    # alignment longer than the read: still fine for clip_bases
+        if rng.random() < 0.05 and len(ops) > 1:
+            ops = ops[:-1]               # alignment shorter than the read: the assert fires for long clips
+    a = rng.randint(0, n)
+    b = rng.randint(a, n)
+    span = None if rng.random() < 0.1 else (a, b)
+    flank = rng.choice([0, 1, 3, 50, 250, n // 3])
+    return bases, ops, rng.randint(0, 10 ** 6), span, flank
+
+
+@pytest.mark.parametrize("lanes", [0, 7, 32])
+def test_bamlet_clip_core(emul, oracle, lanes):
+    """clip_bases for the BAMlet (write_bam.rs:72-92, clip_bases.rs:9-119) by a group of lanes: the reference's own
+    vectors (clip_bases.rs:147-230, with the span / flank length that asks for each clip) and random reads"""
+    from trgt_b200 import BAMLET_CLIP_DTYPE
+    emul.emu_bamlet_clip.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                     C.c_uint32, C.c_longlong, C.c_int, C.c_void_p]
+    emul.emu_bamlet_clip.restype = None
+
+    def run(bases, ops, ref_pos, span, flank):
+        arr = np.array(ops if ops else [0], dtype=np.uint32)
+        out = np.zeros(1, dtype=BAMLET_CLIP_DTYPE)
+        emul.emu_bamlet_clip(bases, len(bases), span is not None, span[0] if span else 0, span[1] if span else 0, flank,
+                             arr.ctypes.data, len(ops), ref_pos, lanes, out.ctypes.data)
+        return bamlet_got(out[0], ops)
+
+    read, cigar = b"AAAAACGCTCGTTAAATCACGAAAAAAAAAA", oracle.encode_bam_cigar("5S3=2D2=1X2=5I3=10S")
+    text = lambda words: "".join(f"{w >> 4}{oracle.BAM_OPS[w & 15]}" for w in words)
+    for (left, right), exp in [((3, 0), (3, 31, 0, 3, 10, "2S3=2D2=1X2=5I3=10S")), ((10, 0), (10, 31, 2, 3, 17, "1X2=5I3=10S")),
+                               ((0, 15), (0, 16, 0, 2, 10, "5S3=2D2=1X2=3I")), ((8, 11), (8, 20, 1, 3, 13, "2D2=1X2=5I2=")),
+                               ((13, 13), (13, 18, 2, 2, 20, "5I"))]:
+        # span and flank length with span.0 - flank = left and len - span.1 - flank = right
+        flank = 0
+        got = run(read, cigar, 10, (left + flank, len(read) - right - flank), flank)
+        assert got[:6] + (text(got[6]),) == (1,) + exp
+    rng = random.Random(31 + lanes)
+    seen = {1: 0, 0: 0, -500: 0}
+    for _ in range(1500 if lanes == 0 else 150):
+        bases, ops, ref_pos, span, flank = random_bamlet_case(rng)
+        exp = _bamlet_expect(oracle, bases, ops, ref_pos, span, flank)
+        assert run(bases, ops, ref_pos, span, flank) == exp
+        seen[exp[0]] += 1
+    assert seen[1] > 30 and seen[0] > 30, seen
 
 
 def test_vcf_fixed6_core(emul):

@@ -600,6 +600,48 @@ def test_clip_reads_random_parity(engine, oracle):
     assert "k_clip_cigar" in engine.kernel_stats()
 
 
+def test_bamlet_clip_parity(engine, oracle):
+    """trgt_bamlet_clip (write_bam.rs:72-92 -> clip_bases.rs:9-119) on the resident reads and spans of a phase-A
+    pass: every read against the oracle, with CIGARs of the read's query length, reads without CIGAR, alignments
+    that are too short (the reference's assert) and flank lengths from 0 to longer than the flanks"""
+    from harness import workload
+    from tests.test_cores_serial import _bamlet_expect, bamlet_got
+    rng = random.Random(77)
+    w = workload.generate(60, 12, seed=99)
+    spans, _ = engine.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+    for flank in (0, 50, 250, 600):
+        ops, offs, refs, per_read = [], [0], [], []
+        for r in range(w.n_reads):
+            n = len(w.reads.get(r))
+            o = []
+            if rng.random() < 0.9:
+                left = n
+                if rng.random() < 0.4:
+                    k = rng.randint(1, 30); o.append((k << 4) | 4); left -= k
+                while left > 0:
+                    op = rng.choice([7, 7, 7, 8, 1, 2, 0])
+                    k = rng.randint(1, min(120, left)) if op != 2 else rng.randint(1, 9)
+                    o.append((k << 4) | op)
+                    if op != 2:
+                        left -= k
+                if rng.random() < 0.03 and len(o) > 1:
+                    o = o[:-1]
+            ops += o
+            offs.append(len(ops))
+            refs.append(rng.randint(0, 10 ** 7))
+            per_read.append(o)
+        clips = engine.bamlet_clip(None, np.array(ops, dtype=np.uint32), np.array(offs, dtype=np.uint64),
+                                   np.array(refs, dtype=np.int64), flank)
+        seen = {1: 0, 0: 0, -500: 0}
+        for r in range(w.n_reads):
+            span = (int(spans[r]["start"]), int(spans[r]["end"])) if spans[r]["found"] else None
+            exp = _bamlet_expect(oracle, w.reads.get(r), per_read[r], refs[r], span, flank)
+            assert bamlet_got(clips[r], per_read[r]) == exp, (flank, r)
+            seen[exp[0]] += 1
+        assert seen[1 if flank <= 250 else 0] > 300, (flank, seen)
+    assert "k_bamlet_clip" in engine.kernel_stats()
+
+
 def test_seq4_decode_parity(engine, oracle):
     from trgt_b200 import PackedSeq4
     rng = random.Random(9)

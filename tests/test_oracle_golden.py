@@ -369,6 +369,61 @@ def test_clip_to_region_reference_vectors(oracle, bases, cigar, region, expect):
     assert _clip(oracle, bases, cigar, 10, region) == expect
 
 
+@pytest.mark.parametrize("bases,cigar,region,meth", [   # the methylation side of the same six tests
+    (b"AAAAACGCTCGTTAAATCACGAAAAAAAAAA", "5S3=2D2=1X2=5I3=10S", (9, 23), [10, 20, 30]),   # clip_region.rs:232-239
+    (_CLIP_READ, _CLIP_CIGAR, (0, 15), [10]),          # :242-254
+    (_CLIP_READ, _CLIP_CIGAR, (12, 17), [20]),         # :257-269
+    (_CLIP_READ, _CLIP_CIGAR, (21, 22), [30]),         # :272-284
+    (_CLIP_READ, _CLIP_CIGAR, (0, 17), [10, 20]),      # :287-299
+])
+def test_clip_to_region_methylation_vectors(oracle, bases, cigar, region, meth):
+    _, qs, qe, _ = oracle.clip_cigar(oracle.encode_bam_cigar(cigar), 10, region)
+    m0, m1 = oracle.meth_range(bases, qs, qe)
+    assert [10, 20, 30][m0:m1] == meth
+
+
+_CB_READ = b"AAAAACGCTCGTTAAATCACGAAAAAAAAAA"
+_CB_CIGAR = "5S3=2D2=1X2=5I3=10S"
+
+
+def _clip_bases(oracle, bases, cigar, left, right):
+    """HiFiRead::clip_bases -> None or (bases, methylation of [10, 20, 30], ref_pos, CIGAR text)"""
+    res = oracle.clip_bases(bases, oracle.encode_bam_cigar(cigar), 10, left, right)
+    if res is None:
+        return None
+    b0, b1, m0, m1, (ref_pos, words) = res
+    return bases[b0:b1], [10, 20, 30][m0:m1], ref_pos, "".join(f"{w >> 4}{oracle.BAM_OPS[w & 15]}" for w in words)
+
+
+@pytest.mark.parametrize("bases,cigar,left,right,expect", [
+    (b"CGCTCGTTAAATCACG", "3=2D2=1X2=5I3=", 16, 0, None),     # clip_bases.rs:147-159 get_none_if_clip_whole_query
+    (b"CGCTCGTTAAATCACG", "3=2D2=1X2=5I3=", 0, 16, None),
+    (b"CGCTCGTTAAATCACG", "3=2D2=1X2=5I3=", 12, 4, None),
+    (_CB_READ, _CB_CIGAR, 3, 0, (b"AACGCTCGTTAAATCACGAAAAAAAAAA", [10, 20, 30], 10, "2S3=2D2=1X2=5I3=10S")),   # :162-177
+    (_CB_READ, _CB_CIGAR, 5, 0, (b"CGCTCGTTAAATCACGAAAAAAAAAA", [10, 20, 30], 10, "3=2D2=1X2=5I3=10S")),
+    (_CB_READ, _CB_CIGAR, 10, 0, (b"GTTAAATCACGAAAAAAAAAA", [30], 17, "1X2=5I3=10S")),
+    (_CB_READ, _CB_CIGAR, 0, 5, (b"AAAAACGCTCGTTAAATCACGAAAAA", [10, 20, 30], 10, "5S3=2D2=1X2=5I3=5S")),     # :180-195
+    (_CB_READ, _CB_CIGAR, 0, 10, (b"AAAAACGCTCGTTAAATCACG", [10, 20, 30], 10, "5S3=2D2=1X2=5I3=")),
+    (_CB_READ, _CB_CIGAR, 0, 15, (b"AAAAACGCTCGTTAAA", [10, 20], 10, "5S3=2D2=1X2=3I")),
+    (_CB_READ, _CB_CIGAR, 5, 5, (b"CGCTCGTTAAATCACGAAAAA", [10, 20, 30], 10, "3=2D2=1X2=5I3=5S")),            # :198-209
+    (_CB_READ, _CB_CIGAR, 8, 11, (b"TCGTTAAATCAC", [20, 30], 13, "2D2=1X2=5I2=")),
+    (_CB_READ, _CB_CIGAR, 31, 0, None),                                                                       # :212-219
+    (_CB_READ, _CB_CIGAR, 0, 31, None),
+    (_CB_READ, _CB_CIGAR, 30, 30, None),
+    (_CB_READ, _CB_CIGAR, 13, 13, (b"AAATC", [], 20, "5I")),                                                  # :222-230
+])
+def test_clip_bases_reference_vectors(oracle, bases, cigar, left, right, expect):
+    assert _clip_bases(oracle, bases, cigar, left, right) == expect
+
+
+def test_bamlet_clip_rule(oracle):  # write_bam.rs:80-92: flank_len either side of the span, else the read is skipped
+    ops = oracle.encode_bam_cigar(_CB_CIGAR)
+    assert oracle.bamlet_clip(_CB_READ, ops, 10, (10, 16), 5) == oracle.clip_bases(_CB_READ, ops, 10, 5, 10)
+    assert oracle.bamlet_clip(_CB_READ, ops, 10, (4, 16), 5) is None          # span.0 < flank_len
+    assert oracle.bamlet_clip(_CB_READ, ops, 10, (10, 27), 5) is None         # bases.len() < span.1 + flank_len
+    assert oracle.bamlet_clip(_CB_READ, None, 0, (10, 16), 5) == (5, 21, 0, 3, None)   # unmapped read: no CIGAR
+
+
 def test_seq4_alphabet(oracle):  # read.rs:104: htslib's "=ACMGRSVTWYHKDBN", first base in the high nibble
     packed = bytes([0x12, 0x48, 0xF0])
     assert oracle.decode_seq4(packed, 0, 5) == b"ACGTN"

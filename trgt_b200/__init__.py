@@ -6,12 +6,12 @@ find_tr_spans / align / get_dist_matrix / label_with_hmm) and shard.py (locus sh
 Bench and test support (workloads, the phase pipeline, the stand-in host glue) lives in harness/.  There is no
 CPU fallback.
 """
-from .engine import (Annotation, AnnotationBatch, CigarBatch, CLIP_DTYPE, Engine, EXPORTS, PackedSeq4, PackedSeqs,
+from .engine import (Annotation, AnnotationBatch, CigarBatch, BAMLET_CLIP_DTYPE, CLIP_DTYPE, Engine, EXPORTS, PackedSeq4, PackedSeqs,
                      TrgtError,
                      decode_sam_cigar, load_library, HIT_DTYPE, SPAN_DTYPE, VIA_EXACT, VIA_NONE, VIA_WFA,
                      VIA_WFA_REJECTED)
 
-__all__ = ["Annotation", "AnnotationBatch", "CigarBatch", "CLIP_DTYPE", "Engine", "EXPORTS", "PackedSeq4", "PackedSeqs",
+__all__ = ["Annotation", "AnnotationBatch", "CigarBatch", "BAMLET_CLIP_DTYPE", "CLIP_DTYPE", "Engine", "EXPORTS", "PackedSeq4", "PackedSeqs",
            "TrgtError",
            "decode_sam_cigar", "load_library", "HIT_DTYPE", "SPAN_DTYPE", "VIA_EXACT", "VIA_NONE", "VIA_WFA",
            "VIA_WFA_REJECTED"]

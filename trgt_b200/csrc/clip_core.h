@@ -176,4 +176,91 @@ TRGT_HD void seq4_unpack_read(const G &g, const uint8_t *data, uint64_t start, u
   }
 }
 
+// ---------------------------------------------------------------- BAMlet output: clip_bases ---
+//
+// HiFiRead::clip_bases (src/trgt/reads/clip_bases.rs:9-119) for the clip BamWriter::write asks for
+// (src/trgt/writers/write_bam.rs:72-92).  The clipped reads and their spans are resident after phase A, so only
+// the CIGAR walk (one lane) and the count of "CG" dinucleotides left of / inside the kept bases (the whole
+// group: entry i of the methylation profile belongs to the read's i-th CG, clip_bases.rs:23-44) are computed.
+
+TRGT_HD bool bamlet_query_kind(uint32_t w) {  // clip_bases.rs:73-81, 98-106: Match Diff Ins Equal SoftClip
+  return ((0x193u >> (w & 15u)) & 1u) != 0;
+}
+
+// clip_cigar of clip_bases.rs:59-119 on one read; fills ref_pos / first_op / n_ops / first_word / last_word,
+// returns false where the reference panics or exits
+TRGT_HD bool bamlet_clip_cigar(const uint32_t *ops, uint32_t n_ops, long long ref_pos, unsigned long long left,
+                               unsigned long long right, trgt_bamlet_clip_t *c) {
+  unsigned long long qlen = 0;
+  for (uint32_t i = 0; i < n_ops; i++) qlen += (unsigned long long)clip_query_len(ops[i]);
+  if (qlen < left + right) return false;  // assert :61
+  unsigned long long keep = qlen - left - right;
+  uint32_t cur = 0, w = ops[0];
+  while (left != 0) {  // :68-92
+    if (cur >= n_ops) return false;
+    const unsigned long long q = (unsigned long long)clip_query_len(w);
+    if (q > left) {  // split the operation
+      if (!bamlet_query_kind(w)) return false;
+      w = ((uint32_t)(q - left) << 4) | (w & 15u);
+      if (clip_ref_len(w) != 0) ref_pos += (long long)left;
+      left = 0;
+    } else {
+      left -= q;
+      ref_pos += clip_ref_len(w);
+      cur++;
+      w = cur < n_ops ? ops[cur] : 0u;
+    }
+  }
+  uint32_t n = 0;
+  c->first_op = cur;
+  while (cur < n_ops && keep != 0) {  // :94-113
+    const unsigned long long q = (unsigned long long)clip_query_len(w);
+    uint32_t word;
+    if (q > keep) {
+      if (!bamlet_query_kind(w)) return false;
+      word = ((uint32_t)keep << 4) | (w & 15u);
+      keep = 0;
+    } else {
+      keep -= q;
+      word = w;
+      cur++;
+      w = cur < n_ops ? ops[cur] : 0u;
+    }
+    if (n == 0) c->first_word = word;
+    c->last_word = word;
+    n++;
+  }
+  c->n_ops = n;
+  c->ref_pos = ref_pos;
+  return true;
+}
+
+// One read by one group of lanes.  found / span: the read's repeat span from phase A.
+template <class G>
+TRGT_HD trgt_bamlet_clip_t bamlet_clip_read(const G &g, const uint8_t *bases, uint32_t len, bool found, uint32_t span_start,
+                                            uint32_t span_end, uint32_t flank_len, const uint32_t *ops, uint32_t n_ops,
+                                            long long ref_pos) {
+  trgt_bamlet_clip_t c;
+  c.ref_pos = 0; c.base_start = 0; c.base_end = 0; c.meth_start = 0; c.meth_end = 0; c.first_op = 0; c.n_ops = 0;
+  c.first_word = 0; c.last_word = 0; c.status = TRGT_BAMLET_SKIPPED; c.pad = 0;
+  if (!found || span_start < flank_len || (unsigned long long)len < (unsigned long long)span_end + flank_len) return c;  // write_bam.rs:80-83
+  const uint32_t left = span_start - flank_len, right = len - span_end - flank_len;
+  if ((unsigned long long)left + right >= len) return c;  // clip_bases.rs:10-12 -> None -> :88-91
+  c.base_start = left;
+  c.base_end = len - right;
+  int before = 0, inside = 0;  // "CG" whose C lies left of / inside [base_start, base_end)
+  for (uint32_t i = (uint32_t)g.lane(); i + 1 < len; i += (uint32_t)g.size()) {
+    const int cg = bases[i] == 'C' && bases[i + 1] == 'G';
+    before += cg && i < c.base_start;
+    inside += cg && i >= c.base_start && i < c.base_end;
+  }
+  { int tot; g.excl_scan_i(before, &tot); before = tot; }
+  { int tot; g.excl_scan_i(inside, &tot); inside = tot; }
+  c.meth_start = (uint32_t)before;
+  c.meth_end = (uint32_t)(before + inside);
+  c.status = TRGT_BAMLET_WRITE;
+  if (n_ops != 0 && !bamlet_clip_cigar(ops, n_ops, ref_pos, left, right, &c)) c.status = TRGT_ITEM_INVALID_OP;
+  return c;
+}
+
 }  // namespace trgt

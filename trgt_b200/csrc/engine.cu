@@ -657,17 +657,19 @@ static int flank_launch_locate(trgt_engine_t *e, trgt_flank_batch *b, const WfaS
 static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src) {
   Counters *ctr = (Counters *)b->ctr.p;
   if (e->band_budget > 0 && b->kidx_valid) {  // band pass of the first cost tier over the pairs the seed pass listed
-    static bool attr_set = false;
-    const size_t smem = sizeof(FlankBand1Smem);
-    if (!attr_set) {
-      CU(e, cudaFuncSetAttribute(k_flank_band1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
+    const int cap1 = e->band_budget < (src.x > src.oe ? src.x : src.oe) ? e->band_budget : (src.x > src.oe ? src.x : src.oe);
+    int rows = 1;
+    if (cap1 <= FT1_SMAX) {
+      const unsigned live = ft1_live_scores(src.x, src.oe, src.e, cap1, nullptr);
+      rows = __builtin_popcount(live);
     }
+    const size_t smem = fb1_smem_bytes(rows);
+    CU(e, cudaFuncSetAttribute(k_flank_band1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb1_smem_bytes(FT1_SMAX + 1)));
     int grid = 0;
     TRY(persistent_grid(e, k_flank_band1, FB1_THREADS, smem, &grid));
     LaunchScope ls(e, "k_flank_band1");
     k_flank_band1<<<grid, FB1_THREADS, smem, e->stream>>>(src, (const uint2 *)b->list1.p, &ctr->n_list1, e->band_budget,
-                                                          b->frac, src.reads + b->reads.cap,
+                                                          b->frac, src.reads + b->reads.cap, rows,
                                                           (trgt_flank_hit_t *)b->hits.p, (uint32_t *)b->work2.p, ctr);
     TRY(check_launch(e, "k_flank_band1"));
   }
@@ -990,6 +992,43 @@ int32_t trgt_seq4_decode(trgt_engine_t *e, const trgt_seq4_t *reads, uint8_t *as
   TRY(launch_unpack(e, d[0], d[1], d[2], d[4], d[3], 0, (uint32_t)reads->n));
   if (total) CU(e, cudaMemcpyAsync(ascii_out, d[3].p, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaMemcpyAsync(ascii_offsets_out, d[4].p, (size_t)(reads->n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int32_t trgt_bamlet_clip(trgt_engine_t *e, trgt_flank_batch_t *b, const uint32_t *cigar_ops,
+                         const uint64_t *cigar_offsets, const int64_t *ref_starts, uint32_t flank_len,
+                         trgt_bamlet_clip_t *clips_out) {
+  if (!e) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!b) b = e->one_flank;  // the batch of the last one-shot trgt_flank_spans* call
+  if (!b || (b->n_reads && !b->ran)) return fail(e, TRGT_ERR_ARG, "trgt_bamlet_clip: the flank batch has not been run");
+  CU(e, cudaSetDevice(e->device));
+  const uint64_t n_reads = b->n_reads;
+  if (n_reads == 0) return 0;
+  if (!cigar_offsets || !ref_starts || !clips_out) return fail(e, TRGT_ERR_ARG, "trgt_bamlet_clip: null argument");
+  for (uint64_t i = 0; i < n_reads; i++)
+    if (cigar_offsets[i + 1] < cigar_offsets[i]) return fail(e, TRGT_ERR_ARG, "cigar_offsets not monotone");
+  const uint64_t n_ops = cigar_offsets[n_reads];
+  if (n_ops && !cigar_ops) return fail(e, TRGT_ERR_ARG, "cigar_ops is null");
+  DevBuf *d = e->d_ed;
+  TRY(h2d(e, d[0], cigar_ops, (size_t)n_ops * sizeof(uint32_t)));
+  TRY(h2d(e, d[1], cigar_offsets, (size_t)(n_reads + 1) * sizeof(uint64_t)));
+  TRY(h2d(e, d[2], ref_starts, (size_t)n_reads * sizeof(int64_t)));
+  TRY(dev_reserve(e, d[5], (size_t)n_reads * sizeof(trgt_bamlet_clip_t)));
+  {
+    int grid = 0;
+    TRY(persistent_grid(e, k_bamlet_clip, 256, 0, &grid));
+    const uint32_t need = (uint32_t)((n_reads + 7) / 8);
+    if ((uint32_t)grid > need) grid = (int)need;
+    LaunchScope ls(e, "k_bamlet_clip");
+    k_bamlet_clip<<<grid, 256, 0, e->stream>>>((const uint8_t *)b->reads.p, (const uint64_t *)b->read_off.p,
+                                               (const trgt_span_t *)b->spans.p, (const uint32_t *)d[0].p,
+                                               (const uint64_t *)d[1].p, (const long long *)d[2].p, flank_len,
+                                               (uint32_t)n_reads, (trgt_bamlet_clip_t *)d[5].p);
+    TRY(check_launch(e, "k_bamlet_clip"));
+  }
+  CU(e, cudaMemcpyAsync(clips_out, d[5].p, (size_t)n_reads * sizeof(trgt_bamlet_clip_t), cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaStreamSynchronize(e->stream));
   return 0;
 }

@@ -120,6 +120,26 @@ k_unpack_seq4(const uint8_t *__restrict__ data, const uint64_t *__restrict__ sta
     seq4_unpack_read(g, data, starts[r], lengths[r], out, (uint64_t)out_off[r]);
 }
 
+// clip_bases for the BAMlet (write_bam.rs:72-92, clip_bases.rs:9-119) on the resident reads and spans of a phase-A
+// batch: a warp per read counts the read's CG dinucleotides, lane 0 walks its CIGAR.  Bytes per read: the read once,
+// 4 * n_ops + 8 + 12 in, 48 out.
+__global__ void __launch_bounds__(256)
+k_bamlet_clip(const uint8_t *__restrict__ reads, const uint64_t *__restrict__ read_off,
+              const trgt_span_t *__restrict__ spans, const uint32_t *__restrict__ ops,
+              const uint64_t *__restrict__ op_off, const long long *__restrict__ ref_starts, uint32_t flank_len,
+              uint32_t n_reads, trgt_bamlet_clip_t *__restrict__ out) {
+  const WarpGroup g;
+  const uint32_t wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  for (uint32_t r = blockIdx.x * wpb + warp; r < n_reads; r += gridDim.x * wpb) {
+    const trgt_span_t sp = spans[r];
+    const uint64_t o = read_off[r];
+    const trgt_bamlet_clip_t c = bamlet_clip_read(g, reads + o, (uint32_t)(read_off[r + 1] - o), sp.found != 0, sp.start,
+                                                  sp.end, flank_len, ops + op_off[r], (uint32_t)(op_off[r + 1] - op_off[r]),
+                                                  ref_starts[r]);
+    if (g.lane() == 0) out[r] = c;
+  }
+}
+
 // ------------------------------------------------------------------ phase A: flank location ---
 
 #define FL_TXT 1664        // bytes per staged read buffer (reads up to ~1.6 KB take the on-chip path)
@@ -537,29 +557,30 @@ k_flank_seed(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
   }
 }
 
-#define FB1_THREADS 128
+#define FB1_THREADS 64
 
-struct __align__(16) FlankBand1Smem {
-  uint8_t win[FB1_THREADS][FT1_WIN_BYTES];               // a lane's text window, filled by its own bulk copy
-  int16_t hist[FB1_THREADS / 32][FT1_HIST_HALFS][32];    // 16-bit wavefront history, the lanes of a warp interleaved
-  unsigned long long bar[FB1_THREADS];                   // a lane's copy-complete barrier
-};
+// dynamic shared memory of k_flank_band1 for `rows` history rows (scores that can have a wavefront under the
+// scoring, ft1_live_scores): per lane a text window filled by its own bulk copy, its copy-complete barrier, and
+// rows * 3 * FT1_WMAX 16-bit history cells (the lanes of a warp interleaved)
+__host__ __device__ inline size_t fb1_smem_bytes(int rows) {
+  return (size_t)FB1_THREADS * (FT1_WIN_BYTES + 8) + (size_t)FB1_THREADS * rows * 3 * FT1_WMAX * sizeof(int16_t);
+}
 
 // Phase A, step 2b (band pass of the first cost tier, see flank_tier1_band_thread).  ONE LANE PER LISTED PAIR, dense
-// warps: the lane fetches the <= 304 bytes of the read its band can touch with one bulk copy into its own window
+// warps: the lane fetches the <= 288 bytes of the read its band can touch with one bulk copy into its own window
 // and then runs the narrow-band wavefronts, their history and the back-trace entirely on chip; only the piece is
 // read through L1 (the ~13 pending pairs of a locus sit next to each other in the list).  Writes the hit, or hands
 // the pair on to `work2` (cost above this tier's cap).
-__global__ void __launch_bounds__(FB1_THREADS, 3)
+__global__ void __launch_bounds__(FB1_THREADS)
 k_flank_band1(WfaSrc src, const uint2 *__restrict__ list1, const unsigned int *n_list1_ptr, int band_budget,
-              double min_flank_id_frac, const uint8_t *reads_end, trgt_flank_hit_t *__restrict__ hits,
+              double min_flank_id_frac, const uint8_t *reads_end, int rows, trgt_flank_hit_t *__restrict__ hits,
               uint32_t *__restrict__ work2, Counters *ctr) {
   extern __shared__ __align__(16) unsigned char fb1_raw[];
-  FlankBand1Smem &sm = *reinterpret_cast<FlankBand1Smem *>(fb1_raw);
   const int tid = threadIdx.x;
-  uint8_t *win = sm.win[tid];
-  int16_t *hist = &sm.hist[tid >> 5][0][tid & 31];
-  unsigned long long *bar = &sm.bar[tid];
+  uint8_t *win = fb1_raw + (size_t)tid * FT1_WIN_BYTES;
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(fb1_raw + (size_t)FB1_THREADS * FT1_WIN_BYTES) + tid;
+  int16_t *hist = reinterpret_cast<int16_t *>(fb1_raw + (size_t)FB1_THREADS * (FT1_WIN_BYTES + 8)) +
+                  (size_t)(tid >> 5) * rows * 3 * FT1_WMAX * 32 + (tid & 31);
   mbar_init(bar, 1);
   mbar_init_fence();
   __syncthreads();

@@ -1508,21 +1508,43 @@ TRGT_HD int flank_tier1_seed_thread(const KmerIndex &idx, const WfaProb &pr, int
   return *khi - *klo + 1 <= FT1_WMAX ? 1 : 0;
 }
 
-#define FT1_WIN_BYTES 304  // text window of a pair: <= 256 of piece + band + 15 of alignment + 11 of over-read, in 16-byte chunks
+#define FT1_WIN_BYTES 288  // text window of a pair: <= 256 of piece + 3 of band + 15 of alignment + 12 of over-read, in 16-byte chunks
 #define FT1_PMAX 256       // longest piece the band pass takes
 #define FT1_HIST_HALFS ((FT1_SMAX + 1) * 3 * FT1_WMAX)  // 16-bit cells of one pair's history (216 bytes)
 
 // History of the band pass: cell (s, component, k) at h[((s * 3 + c) * FT1_WMAX + k - blo) * LS] as offset - blo
 // (never negative for a reachable cell), -1 = null.  LS = distance between a lane's consecutive cells (cells of
 // the lanes of a warp interleaved: every lane of a converged access hits its own bank).
+// which scores can have an M wavefront at all under a scoring (bit s), up to s_cap: a property of the scoring alone
+TRGT_HD unsigned ft1_live_scores(int x, int oe, int e, int s_cap, unsigned *live_gap) {
+  unsigned live_m = 1u, live_g = 0u;
+  for (int s = 1; s <= s_cap; s++) {
+    const int sx = s - x, so = s - oe, se = s - e;
+    const bool g = (so >= 0 && ((live_m >> so) & 1u)) || (se >= 1 && ((live_g >> se) & 1u));
+    if (g) live_g |= 1u << s;
+    if (g || (sx >= 0 && ((live_m >> sx) & 1u))) live_m |= 1u << s;
+  }
+  if (live_gap) *live_gap = live_g;
+  return live_m;
+}
+// the history keeps a row only for those scores: row of score s
+TRGT_HD int ft1_row(unsigned live_m, int s) {
+#if defined(__CUDA_ARCH__)
+  return __popc(live_m & ((1u << s) - 1u));
+#else
+  return __builtin_popcount(live_m & ((1u << s) - 1u));
+#endif
+}
+
 template <int LS>
 struct Ft1Hist {
   int16_t *h;
   int blo, W;
   unsigned present;  // bit s: score s has a wavefront
+  unsigned live_m;   // ft1_live_scores of the scoring (row numbering)
   TRGT_HD int cell(int s, int c, int k) const {
     if (s < 0 || !((present >> s) & 1u) || k < blo || k >= blo + W) return TRGT_WFA_NULL;
-    const int v = h[((s * 3 + c) * FT1_WMAX + (k - blo)) * LS];
+    const int v = h[((ft1_row(live_m, s) * 3 + c) * FT1_WMAX + (k - blo)) * LS];
     return v < 0 ? TRGT_WFA_NULL : v + blo;
   }
   TRGT_HD int m(int s, int k) const { return cell(s, 0, k); }
@@ -1531,77 +1553,43 @@ struct Ft1Hist {
 };
 
 // wfa_forward_band_hist_narrow_thread on the staged window: text offset h lives at win[h - a0].
-// Written as ONE loop whose iteration is "one 8-byte step of the match extension in progress, then -- if that
-// extension is over -- record the cell and start the next one": the lanes of a warp, each on its own pair, have
-// their long extensions in different cells, and with a loop per cell every cell would cost the warp its longest
-// extension among 32 pairs.  This way a lane's trip count is (cells + 8-byte steps), nearly the same for all.
-// lanes: the lanes of the warp that call this together (they leave the loop together, so that the hardware keeps
-// them on one instruction stream; 0 = a lane on its own); idle: this lane has no pair and only keeps company.
+// The lanes of a warp, each on its own pair, walk the SAME sequence of cells (which scores have a wavefront
+// depends only on the scoring; the band is FT1_WMAX diagonals for everybody, the ones past a lane's own band
+// masked), so the recurrences, the first eight bytes of every match extension and all history traffic run
+// with the whole warp.  What differs between lanes is where the long extensions are (the error-free stretches
+// of the piece, ~P bases in all): a cell that is not settled by its first eight bytes is parked, and after the
+// cells of a score all parked extensions are finished in one loop, sixteen bytes a step, that the lanes leave
+// together.  (With a loop per cell every cell costs the warp its longest extension among 32 pairs.)
+// lanes: the lanes of the warp that call this together (0 = a lane on its own); idle: this lane has no pair
+// and only keeps company.  An all-null wavefront reads exactly like an absent one, so a score that only has
+// null predecessors may be computed (here: whenever the scoring allows a wavefront) or skipped alike.
 template <int LS>
 TRGT_HD WfaEnd ft1_forward(const WfaProb &pr, int s_cap, const uint8_t *win, int a0, int16_t *hist, unsigned *present_out,
                            unsigned lanes, bool idle) {
   WfaEnd out;
   out.status = TRGT_WFA_OK; out.s = 0; out.k = 0; out.off = 0;
-  const int W = pr.bhi - pr.blo + 1;
-  unsigned present = 0;       // bit s: score s has a wavefront with some cell that is not null (an all-null wavefront
-                              // reads exactly like an absent one, so it is neither computed nor stored)
-  unsigned present_gap = 0;   // bit s: some I or D cell of score s is not null
-  bool row_m = false, row_gap = false;
-#define FT1_LD(s_, c_, i_) ft1_ld(hist[(((s_) * 3 + (c_)) * FT1_WMAX + (i_)) * LS], pr.blo)
-#define FT1_ST(s_, c_, i_, val) hist[(((s_) * 3 + (c_)) * FT1_WMAX + (i_)) * LS] = (int16_t)((val) < 0 ? -1 : (val) - pr.blo)
-  int s = 0, idx = -1;       // the cell in progress (idx = -1: none yet)
-  int cur = TRGT_WFA_NULL;   // its offset so far
-  int n_rem = 0;             // bases its extension may still cover
-  int endk = INT_MAX, endoff = 0;
-  bool px = false, po = false, pe = false;
+  const int W = idle ? 0 : pr.bhi - pr.blo + 1;
+  unsigned live_g = 0u;
+  const unsigned live_m = ft1_live_scores(pr.x, pr.oe, pr.e, s_cap, &live_g);  // bit s: the scoring allows an M / a gap wavefront
+  unsigned present = 0;
   bool done = idle;
-  while (TRGT_ANY(lanes, !done)) {
-    if (!done && n_rem > 0) {  // one step of the match extension along the diagonal
-      const int v = cur - (pr.blo + idx);
-      const uint64_t x = ft1_ld64_piece(pr.p + v) ^ ft1_ld64_win(win + (cur - a0));
-      int adv = x ? (wfa_ctz64(x) >> 3) : 8;
-      if (adv > n_rem) adv = n_rem;
-      cur += adv;
-      n_rem = x ? 0 : n_rem - adv;
-    }
-    if (!done && n_rem == 0) {
-      if (idx >= 0) {  // the cell is complete
-        FT1_ST(s, 0, idx, cur);
-        row_m |= cur >= 0;
-        if (endk == INT_MAX && cur >= 0) {  // end condition, lowest diagonal first
-          const int h = cur, v = cur - (pr.blo + idx);
-          if (v >= 0 && v <= pr.P && h <= pr.T &&
-              ((h >= pr.T && pr.P - v <= pr.pef) || (v >= pr.P && pr.T - h <= pr.tef))) { endk = pr.blo + idx; endoff = cur; }
-        }
-      }
-      idx++;
-      if (idx == W) {  // the wavefront of score s is complete
-        if (row_m || row_gap) present |= 1u << s;
-        if (row_gap) present_gap |= 1u << s;
-        row_m = row_gap = false;
-        if (endk != INT_MAX) {
-          out.s = s; out.k = endk; out.off = endoff;
-          done = true;
-        }
-        bool live = done;
-        while (!live && ++s <= s_cap) {
-          const int sx = s - pr.x, so = s - pr.oe, se = s - pr.e;
-          px = sx >= 0 && ((present >> sx) & 1u);
-          po = so >= 0 && ((present >> so) & 1u);
-          pe = se >= 1 && ((present_gap >> se) & 1u);
-          live = px || po || pe;
-        }
-        if (!live) { out.status = TRGT_WFA_MAX_STEPS; done = true; }
-        idx = 0;
-      }
-      // start of cell (s, idx)
+#define FT1_LD(s_, c_, i_) ft1_ld(hist[((ft1_row(live_m, (s_)) * 3 + (c_)) * FT1_WMAX + (i_)) * LS], pr.blo)
+#define FT1_ST(s_, c_, i_, val) hist[((ft1_row(live_m, (s_)) * 3 + (c_)) * FT1_WMAX + (i_)) * LS] = (int16_t)((val) < 0 ? -1 : (val) - pr.blo)
+  for (int s = 0; s <= s_cap; s++) {
+    if (!((live_m >> s) & 1u)) continue;  // the same for every lane
+    if (!TRGT_ANY(lanes, !done)) break;
+    const int sx = s - pr.x, so = s - pr.oe, se = s - pr.e;
+    const bool px = sx >= 0 && ((live_m >> sx) & 1u), po = so >= 0 && ((live_m >> so) & 1u);
+    const bool pe = se >= 1 && ((live_g >> se) & 1u);
+    unsigned parked = 0;  // bit idx: the extension of cell (s, idx) is not finished
+#pragma unroll
+    for (int idx = 0; idx < FT1_WMAX; idx++) {
+      if (done || idx >= W) continue;
       const int k = pr.blo + idx;
       int mx = TRGT_WFA_NULL;
-      if (done) {
-      } else if (s == 0) {
+      if (s == 0) {
         if (k >= -pr.pbf && k <= pr.tbf) mx = k >= 0 ? k : 0;
       } else {
-        const int sx = s - pr.x, so = s - pr.oe, se = s - pr.e;
         const int o_l = (po && idx > 0) ? FT1_LD(so, 0, idx - 1) : TRGT_WFA_NULL;
         const int o_r = (po && idx + 1 < W) ? FT1_LD(so, 0, idx + 1) : TRGT_WFA_NULL;
         const int i_l = (pe && idx > 0) ? FT1_LD(se, 1, idx - 1) : TRGT_WFA_NULL;
@@ -1614,14 +1602,57 @@ TRGT_HD WfaEnd ft1_forward(const WfaProb &pr, int s_cap, const uint8_t *win, int
         if (mx < 0 || h > pr.T || v > pr.P || v < 0) mx = TRGT_WFA_NULL;
         FT1_ST(s, 1, idx, i1);
         FT1_ST(s, 2, idx, d1);
-        row_gap |= i1 >= 0 || d1 >= 0;
       }
-      cur = mx;
-      n_rem = mx >= 0 ? wfa_imax(0, wfa_imin(pr.P - (mx - k), pr.T - mx)) : 0;
+      if (mx >= 0) {  // the first eight bytes of the match extension along the diagonal
+        const int v = mx - k, n = wfa_imin(pr.P - v, pr.T - mx);
+        if (n > 0) {
+          const uint64_t x = ft1_ld64_piece(pr.p + v) ^ ft1_ld64_win(win + (mx - a0));
+          int adv = x ? (wfa_ctz64(x) >> 3) : 8;
+          if (adv > n) adv = n;
+          mx += adv;
+          if (!x && n > 8) parked |= 1u << idx;
+        }
+      }
+      FT1_ST(s, 0, idx, mx);
+    }
+    while (TRGT_ANY(lanes, parked != 0)) {  // the parked extensions, sixteen bytes a step
+      if (parked) {
+#if defined(__CUDA_ARCH__)
+        const int idx = __ffs((int)parked) - 1;
+#else
+        const int idx = __builtin_ctz(parked);
+#endif
+        const int k = pr.blo + idx;
+        int mx = FT1_LD(s, 0, idx);
+        const int v = mx - k, n = wfa_imin(pr.P - v, pr.T - mx);
+        const uint64_t x0 = ft1_ld64_piece(pr.p + v) ^ ft1_ld64_win(win + (mx - a0));
+        const uint64_t x1 = n > 8 ? ft1_ld64_piece(pr.p + v + 8) ^ ft1_ld64_win(win + (mx - a0) + 8) : 0;  // (stays inside the padding)
+        int adv = x0 ? (wfa_ctz64(x0) >> 3) : (x1 ? 8 + (wfa_ctz64(x1) >> 3) : 16);
+        if (adv > n) adv = n;
+        mx += adv;
+        FT1_ST(s, 0, idx, mx);
+        if (x0 || x1 || n <= 16) parked &= ~(1u << idx);
+      }
+    }
+    if (!done) {  // end condition, lowest diagonal first
+      present |= 1u << s;
+      for (int idx = 0; idx < W; idx++) {
+        const int k = pr.blo + idx;
+        const int mx = FT1_LD(s, 0, idx);
+        if (mx < 0) continue;
+        const int h = mx, v = mx - k;
+        if (v >= 0 && v <= pr.P && h <= pr.T &&
+            ((h >= pr.T && pr.P - v <= pr.pef) || (v >= pr.P && pr.T - h <= pr.tef))) {
+          out.s = s; out.k = k; out.off = mx;
+          done = true;
+          break;
+        }
+      }
     }
   }
 #undef FT1_LD
 #undef FT1_ST
+  if (!done) out.status = TRGT_WFA_MAX_STEPS;
   *present_out = present;
   return out;
 }
@@ -1640,7 +1671,7 @@ TRGT_HD int flank_tier1_band_thread(const WfaProb &pr, int klo, int khi, int S, 
   unsigned present = 0;
   const WfaEnd end = ft1_forward<LS>(bp, cap, win, a0, hist, &present, lanes, skip);
   if (skip || end.status != TRGT_WFA_OK) return 1;
-  const Ft1Hist<LS> H{hist, klo, khi - klo + 1, present};
+  const Ft1Hist<LS> H{hist, klo, khi - klo + 1, present, ft1_live_scores(pr.x, pr.oe, pr.e, cap, nullptr)};
   WfaFlankSink sink(pr.T);
   wfa_backtrace_h(pr, end.s, end.k, end.off, H, sink);
   hit->matches = sink.matches;

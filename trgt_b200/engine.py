@@ -61,6 +61,10 @@ class _Annotations(C.Structure):
 CLIP_DTYPE = np.dtype([("ref_start", np.int64), ("query_start", np.uint64), ("query_end", np.uint64),
                        ("first_op", np.uint32), ("n_ops", np.uint32), ("first_word", np.uint32),
                        ("last_word", np.uint32), ("status", np.int32)], align=True)
+BAMLET_CLIP_DTYPE = np.dtype([("ref_pos", np.int64), ("base_start", np.uint32), ("base_end", np.uint32),
+                              ("meth_start", np.uint32), ("meth_end", np.uint32), ("first_op", np.uint32),
+                              ("n_ops", np.uint32), ("first_word", np.uint32), ("last_word", np.uint32),
+                              ("status", np.int32), ("pad", np.uint32)], align=True)
 SEQ4_ALPHABET = b"=ACMGRSVTWYHKDBN"
 SPAN_DTYPE = np.dtype([("found", np.int32), ("start", np.uint32), ("end", np.uint32)])
 HIT_DTYPE = np.dtype([("via", np.int32), ("matches", np.int32), ("score", np.int32),
@@ -73,7 +77,7 @@ EXPORTS = [
     "trgt_engine_set_flank_band_budget", "trgt_engine_set_hmm_lane_path",
     "trgt_host_alloc", "trgt_host_free",
     "trgt_clip_reads", "trgt_seq4_decode", "trgt_flank_spans_seq4", "trgt_flank_upload_seq4",
-    "trgt_flank_trs", "trgt_vcf_fields",
+    "trgt_flank_trs", "trgt_vcf_fields", "trgt_bamlet_clip",
     "trgt_flank_spans", "trgt_align_e2e", "trgt_consensus", "trgt_edit_dist", "trgt_hmm_label",
     "trgt_cluster", "trgt_cluster_trs", "trgt_consensus_trs",
     "trgt_flank_upload", "trgt_flank_run", "trgt_flank_download", "trgt_flank_free", "trgt_flank_device_views",
@@ -149,6 +153,7 @@ def load_library(build: bool = True):
     L.trgt_edit_dist.argtypes = [vp, sp, vp, u32, vp]
     L.trgt_cluster.argtypes = [vp, sp, vp, u32, vp, vp, vp]
     L.trgt_cluster_trs.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
+    L.trgt_bamlet_clip.argtypes = [vp, vp, vp, vp, vp, u32, vp]
     L.trgt_consensus_trs.argtypes = [vp, vp, vp, vp, vp, u32, C.POINTER(_SeqsOut)]
     L.trgt_hmm_label.argtypes = [vp, sp, vp, u32, sp, vp, i32, C.POINTER(_Annotations)]
     L.trgt_hmm_upload.argtypes = [vp, sp, vp, u32, sp, vp, i32, C.POINTER(vp)]
@@ -708,6 +713,19 @@ class Engine:
             a, b = int(lso[l]), int(lso[l + 1])
             out.append((group[a:b].tolist(), tuple(None if c == 0xFFFFFFFF else int(c) for c in central[l]), int(ng[l])))
         return out
+
+    def bamlet_clip(self, b, cigar_ops: np.ndarray, cigar_offsets: np.ndarray, ref_starts: np.ndarray,
+                    flank_len: int) -> np.ndarray:
+        """clip_bases as BamWriter::write asks for it (write_bam.rs:72-92, clip_bases.rs:9-119) for every read of
+        flank batch b (None: the last one-shot call) -> BAMLET_CLIP_DTYPE[n_reads]"""
+        ops = np.ascontiguousarray(cigar_ops, dtype=np.uint32)
+        offs = np.ascontiguousarray(cigar_offsets, dtype=np.uint64)
+        rs = np.ascontiguousarray(ref_starts, dtype=np.int64)
+        n = rs.size
+        out = np.zeros(max(1, n), dtype=BAMLET_CLIP_DTYPE)
+        self._check(self._L.trgt_bamlet_clip(self._h, b, ops.ctypes.data if ops.size else None, offs.ctypes.data,
+                                             rs.ctypes.data, int(flank_len), out.ctypes.data), "trgt_bamlet_clip")
+        return out[:n]
 
     def cluster_trs(self, b, reads: np.ndarray, locus_offsets: np.ndarray):
         """trgt_cluster_trs: the same on the repeat sequences of flank batch b (None: the last one-shot call),
