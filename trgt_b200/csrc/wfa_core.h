@@ -405,6 +405,21 @@ TRGT_HD int wfa_trace_forward(const G &g, const WfaProb &pr, int s_end, int k_en
 // presence of a score is one bit of a mask.  Every band cell is evaluated at every live score; cells
 // the general routine would leave outside a wavefront come out as (drifted) NULLs, which every
 // consumer treats as NULL.  Writes the same history layout as the general routine.
+// Which scores can have an M wavefront at all under a scoring (bit s, s <= s_cap < 64), and which a gap (I / D)
+// wavefront: a property of the scoring alone.  A wavefront whose predecessors are all null is all null and reads
+// exactly like an absent one, so the banded passes only compute the scores named here.
+TRGT_HD unsigned long long wfa_live_scores(int x, int oe, int e, int s_cap, unsigned long long *live_gap) {
+  unsigned long long live_m = 1ull, live_g = 0ull;
+  for (int s = 1; s <= s_cap && s < 64; s++) {
+    const int sx = s - x, so = s - oe, se = s - e;
+    const bool g = (so >= 0 && ((live_m >> so) & 1ull)) || (se >= 1 && ((live_g >> se) & 1ull));
+    if (g) live_g |= 1ull << s;
+    if (g || (sx >= 0 && ((live_m >> sx) & 1ull))) live_m |= 1ull << s;
+  }
+  if (live_gap) *live_gap = live_g;
+  return live_m;
+}
+
 template <class G>
 TRGT_HD WfaEnd wfa_forward_band_hist_narrow(const G &g, const WfaProb &pr, int s_cap, int *ws, size_t cap_ints) {
   WfaEnd out;
@@ -1005,6 +1020,23 @@ TRGT_HD bool fxt_verify(const uint8_t *copies, int P, const uint8_t *a) {
 #define TRGT_ANY(lanes, p) ((void)(lanes), (p))
 #endif
 
+// ask L2 for the sectors a verification of t[s .. s+P) will read (no registers held; the verification's
+// dependent rounds of loads then wait for L2 instead of DRAM)
+#ifndef TRGT_FXT_PREFETCH
+#define TRGT_FXT_PREFETCH 128  // bytes between prefetches (measured: 128 = 64 = 32 > none), 0 = off
+#endif
+TRGT_HD void fxt_prefetch(const uint8_t *a, int P) {
+#if defined(__CUDA_ARCH__)
+  if (TRGT_FXT_PREFETCH > 0) {
+    const uintptr_t b = (uintptr_t)a & ~(uintptr_t)31, e = (uintptr_t)a + (uintptr_t)P;
+    for (uintptr_t q = b; q < e; q += (TRGT_FXT_PREFETCH > 0 ? TRGT_FXT_PREFETCH : 32))
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(q));
+  }
+#else
+  (void)a; (void)P;
+#endif
+}
+
 TRGT_HD int flank_exact_thread(const KmerIndex &idx, const uint8_t *copies, int P, const uint8_t *t, int T,
                                unsigned lanes = 0) {
   const int n_starts = T - P + 1;
@@ -1031,6 +1063,7 @@ TRGT_HD int flank_exact_thread(const KmerIndex &idx, const uint8_t *copies, int 
         const int s = j - (int)(v & 511u);
         if (s < 0 || s >= n_starts) continue;
         if (n == 0) c0 = s; else if (n == 1) c1 = s; else if (n == 2) c2 = s; else if (n == 3) c3 = s; else many = true;
+        if (n == 0) fxt_prefetch(t + s, P);  // the first candidate is the answer for ~4 pairs of 5
         n++;
       }
     }
@@ -1515,17 +1548,12 @@ TRGT_HD int flank_tier1_seed_thread(const KmerIndex &idx, const WfaProb &pr, int
 // History of the band pass: cell (s, component, k) at h[((s * 3 + c) * FT1_WMAX + k - blo) * LS] as offset - blo
 // (never negative for a reachable cell), -1 = null.  LS = distance between a lane's consecutive cells (cells of
 // the lanes of a warp interleaved: every lane of a converged access hits its own bank).
-// which scores can have an M wavefront at all under a scoring (bit s), up to s_cap: a property of the scoring alone
+// wfa_live_scores for the first tier (s_cap <= FT1_SMAX)
 TRGT_HD unsigned ft1_live_scores(int x, int oe, int e, int s_cap, unsigned *live_gap) {
-  unsigned live_m = 1u, live_g = 0u;
-  for (int s = 1; s <= s_cap; s++) {
-    const int sx = s - x, so = s - oe, se = s - e;
-    const bool g = (so >= 0 && ((live_m >> so) & 1u)) || (se >= 1 && ((live_g >> se) & 1u));
-    if (g) live_g |= 1u << s;
-    if (g || (sx >= 0 && ((live_m >> sx) & 1u))) live_m |= 1u << s;
-  }
-  if (live_gap) *live_gap = live_g;
-  return live_m;
+  unsigned long long lg = 0;
+  const unsigned long long lm = wfa_live_scores(x, oe, e, s_cap, &lg);
+  if (live_gap) *live_gap = (unsigned)lg;
+  return (unsigned)lm;
 }
 // the history keeps a row only for those scores: row of score s
 TRGT_HD int ft1_row(unsigned live_m, int s) {
