@@ -104,6 +104,22 @@ pub struct TrgtClip {
     pub status: i32,
 }
 pub enum TrgtEngine {}
+/// `trgt_bamlet_clip_t`: what `HiFiRead::clip_bases` (clip_bases.rs:9-119) keeps of one read for the BAMlet
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct TrgtBamletClip {
+    pub ref_pos: i64,
+    pub base_start: u32,
+    pub base_end: u32,
+    pub meth_start: u32,
+    pub meth_end: u32,
+    pub first_op: u32,
+    pub n_ops: u32,
+    pub first_word: u32,
+    pub last_word: u32,
+    pub status: i32,
+    pub pad: u32,
+}
 pub enum TrgtFlankBatch {}
 pub enum TrgtAlignBatch {}
 pub enum TrgtHmmBatch {}
@@ -131,6 +147,9 @@ extern "C" {
     pub fn trgt_flank_spans_seq4(eng: *mut TrgtEngine, left: *const TrgtSeqs, right: *const TrgtSeqs, reads: *const TrgtSeq4,
         locus_read_offsets: *const u32, n_loci: u32, scoring: TrgtScoring, min_flank_id_frac: f64,
         spans_out: *mut TrgtSpan, hits_out: *mut TrgtFlankHit) -> i32;
+    pub fn trgt_bamlet_clip(eng: *mut TrgtEngine, batch: *mut TrgtFlankBatch, cigar_ops: *const u32,
+                            cigar_offsets: *const u64, ref_starts: *const i64, flank_len: u32,
+                            clips_out: *mut TrgtBamletClip) -> i32;
     pub fn trgt_seq4_decode(eng: *mut TrgtEngine, reads: *const TrgtSeq4, ascii_out: *mut u8, offsets_out: *mut u64) -> i32;
     pub fn trgt_flank_trs(eng: *mut TrgtEngine, batch: *mut TrgtFlankBatch, out: *mut TrgtSeqsOut) -> i32;
 

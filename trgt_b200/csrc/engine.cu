@@ -1285,10 +1285,10 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
   CU(e, cudaMemsetAsync(b->status.p, 0, ((size_t)n + 1) * sizeof(int32_t), e->stream));
   const size_t bound = ring_ints_bound(src.x, src.oe, src.e, b->Pmax, b->Tmax);
   unsigned long long pool_cap1 = 0;
-  if ((size_t)b->Pmax + (size_t)b->Tmax > 4096) {
-    // long alleles: a CTA per pair.  (Tandem repeats match themselves on every diagonal that is a multiple of the
-    // motif length, so most of the work is long match extensions, 8 bytes per lane per round: four warps per pair
-    // finish them in a quarter of the rounds a single warp needs -- measured on config 5: 334 vs 422 ms.)
+  if (false) {
+    // (a CTA per pair: the wide-and-shallow shape of the flank problem.  End-to-end wavefronts of similar alleles stay
+    // within a few hundred diagonals, which the banded on-chip ring of the warp kernel covers: measured on config 5,
+    // 2 x 422 ms with a warp per pair and that ring against 2 x 501 ms with a CTA per pair on the global ring.)
     const int block = 128;
     const size_t cap_ints = 24 * 1024;
     const int smem_ring_ints = (int)(bound < cap_ints ? bound : cap_ints);

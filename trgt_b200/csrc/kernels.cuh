@@ -777,6 +777,7 @@ k_tr_gather(const uint8_t *__restrict__ reads, const uint64_t *__restrict__ read
 #define E2E_NARROW_COST 16    // cost cap of the one-pass path for short consensus pairs
 #define E2E_NARROW_INTS 1280  // its history: 6*17 header + 3 * 23 diagonals * 17 scores
 #define E2E_NARROW_WORDS 48   // its CIGAR: at most 2 * cost + a few words
+#define E2E_MID_COST 256      // cost cap of the banded on-chip ring for long similar pairs (halved until the ring fits)
 
 // Phase B, first steps for short repeat sequences: ONE LANE PER (backbone, member) PAIR.  A member equal
 // to its backbone (92 % on HiFi) is a single '=' run (k_e2e_identity, which compacts the others into a
@@ -953,7 +954,29 @@ __global__ void k_wfa_score(WfaSrc src, const uint32_t *__restrict__ work, const
         if (done) continue;
         const size_t need = wfa_ring_ints(pr);
         int *ring = (need <= (size_t)smem_ring_ints) ? my_smem : (gring ? gring + (size_t)slot * gring_stride : nullptr);
-        if (ring == nullptr || (ring != my_smem && need > gring_stride)) {
+        // long, similar pair (alleles of kilobases a few hundred edits apart): with cost cap S nothing is reachable
+        // outside |k| <= (S - o) / e (wfa_e2e_narrow's argument), so a ring over that band -- on chip -- is the full
+        // computation; only a costlier pair needs the ring over all P + T + 1 diagonals in HBM
+        bool scored = false;
+        if (ring != my_smem) {
+          const int o = pr.oe - pr.e;
+          int S = E2E_MID_COST;
+          WfaProb bp = pr;
+          for (;;) {
+            const int R = S > o ? (S - o) / pr.e : 0;
+            bp.blo = wfa_imax(-pr.P, -R);
+            bp.bhi = wfa_imin(pr.T, R);
+            if (wfa_ring_ints(bp) <= (size_t)smem_ring_ints || S <= E2E_NARROW_COST) break;
+            S >>= 1;
+          }
+          if (S > E2E_NARROW_COST && wfa_ring_ints(bp) <= (size_t)smem_ring_ints) {
+            end = wfa_score_ring(g, bp, my_smem, S);
+            __syncwarp();
+            scored = end.status == TRGT_WFA_OK;
+          }
+        }
+        if (scored) {
+        } else if (ring == nullptr || (ring != my_smem && need > gring_stride)) {
           end.status = TRGT_WFA_OOM; end.s = 0; end.k = 0; end.off = 0;
         } else {
           end = wfa_score_ring(g, pr, ring, wfa_score_cap(pr));
