@@ -464,7 +464,13 @@ int launch_trace(trgt_engine *e, const WfaSrc &src, const uint32_t *work, const 
                  unsigned long long *cig_off, uint32_t *cig_n, int32_t *status, Counters *ctr) {
   if (n_work_host == 0) return 0;
   const int block = 128, wpb = block / 32;
-  const size_t smem_cap_ints = 3072;  // 12 KB per warp: cones up to cost ~25 stay on chip
+  // 12 KB per warp: cones up to cost ~25 stay on chip.  A batch whose largest cone is far beyond that (alleles of
+  // kilobases, costs in the hundreds) works out of the global slots anyway: it gets a token of shared memory and
+  // four times the resident warps instead.
+#ifndef TRGT_TRACE_LONG_FACTOR
+#define TRGT_TRACE_LONG_FACTOR 16
+#endif
+  const size_t smem_cap_ints = max_trace_ints > (unsigned long long)TRGT_TRACE_LONG_FACTOR * 3072ull ? 512 : 3072;
   const int smem_ws_ints = (int)(max_trace_ints < smem_cap_ints ? (max_trace_ints ? max_trace_ints : 1) : smem_cap_ints);
   const size_t smem = (size_t)wpb * smem_ws_ints * sizeof(int);
   int grid = 0;
@@ -1311,14 +1317,20 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
     TRY(check_launch(e, "k_wfa_score_block"));
   } else {
     const int block = 128, wpb = 4;
-    const size_t cap_ints = 6 * 1024;  // 24 KB per warp
+#ifndef TRGT_E2E_RING_INTS
+#define TRGT_E2E_RING_INTS 1536  // 6 KB per warp: the rings of long pairs live in L2 anyway, and resident warps are what hides their latency
+                                 // (config 5, k_wfa_score_warp: 301 ms at 24 KB, 180 at 12, 157 at 8, 144 at 6)
+#endif
+    const size_t cap_ints = TRGT_E2E_RING_INTS;
     size_t want = bound < cap_ints ? bound : cap_ints;
     if (want < (size_t)(E2E_NARROW_INTS + E2E_NARROW_WORDS)) want = E2E_NARROW_INTS + E2E_NARROW_WORDS;
     const int smem_ring_ints = (int)want;
     const size_t smem = (size_t)wpb * smem_ring_ints * sizeof(int);
     int grid = 0;
     TRY(persistent_grid(e, k_wfa_score<false>, block, smem, &grid));
-    const uint32_t need = (n + 32 * wpb - 1) / (32 * wpb);
+    // the kernel walks the list of members the lane-per-pair kernels handed on, one member per warp and round
+    // (a handful of 20 kb pairs must not queue 32 deep behind four warps)
+    const uint32_t need = (n + wpb - 1) / wpb;
     if ((uint32_t)grid > need) grid = (int)need;
     int *gring = nullptr;
     size_t stride = 0;
