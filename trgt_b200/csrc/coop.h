@@ -69,7 +69,7 @@ struct TileGroup {
   TRGT_D TileGroup() {
     const unsigned lane = threadIdx.x & 31u;
     l = (int)(lane & (unsigned)(N - 1));
-    mask = ((1u << N) - 1u) << (lane & ~(unsigned)(N - 1));
+    mask = (unsigned)((1ull << N) - 1ull) << (lane & ~(unsigned)(N - 1));
   }
   TRGT_D int lane() const { return l; }
   TRGT_D int size() const { return N; }

@@ -310,7 +310,9 @@ k_flank_exact_t(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_
   }
 }
 
+#ifndef FB_LT
 #define FB_LT 16          // lanes per locus in the first cost tier
+#endif
 #define FB_LOCI (128 / FB_LT)  // loci in flight per CTA of 128 threads
 #define FB_LIST 64        // pending pairs gathered per pass over a locus' reads
 
@@ -703,7 +705,9 @@ k_flank_band2(WfaSrc src, const uint32_t *__restrict__ work2, const unsigned int
 // banded routine (index or linear seed scan, any band width, history or ring + cone), budgets 24 then 36.
 // What it settles is struck from the work list (0xFFFFFFFF); only pairs without any usable seed are
 // left for the full-width kernels.
-#define FLW_WS_INTS 8192
+#ifndef FLW_WS_INTS
+#define FLW_WS_INTS 5120  // (8192: 0.50 ms, 5120: 0.46 ms, 4096: 0.39 ms but 0.2 ms more in the full-width kernels behind it)
+#endif
 
 __global__ void __launch_bounds__(32)
 k_flank_band_wide(WfaSrc src, uint32_t *__restrict__ work, const unsigned int *n_work_ptr, double min_flank_id_frac,

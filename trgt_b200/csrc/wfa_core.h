@@ -540,15 +540,20 @@ TRGT_HD WfaEnd wfa_forward_band_hist(const G &g, const WfaProb &pr, int s_cap, i
 
 // The wavefront history as wfa_trace_forward / wfa_forward_band_hist* leave it in `ws`, read cell by cell
 // (TRGT_WFA_NULL for a cell that is not stored).
+struct WfaWsRow {
+  WfaView v;
+  TRGT_HD int m(int k) const { return wfa_at(v.m, v, k); }
+  TRGT_HD int i(int k) const { return wfa_at(v.i, v, k); }
+  TRGT_HD int d(int k) const { return wfa_at(v.d, v, k); }
+};
 struct WfaWsHist {
   int *ws;
-  TRGT_HD int m(int s, int k) const { const WfaView v = wfa_hist_view(ws, s); return wfa_at(v.m, v, k); }
-  TRGT_HD int i(int s, int k) const { const WfaView v = wfa_hist_view(ws, s); return wfa_at(v.i, v, k); }
-  TRGT_HD int d(int s, int k) const { const WfaView v = wfa_hist_view(ws, s); return wfa_at(v.d, v, k); }
+  typedef WfaWsRow Row;
+  TRGT_HD Row row(int s) const { Row r; r.v = wfa_hist_view(ws, s); return r; }  // the score's header, read once
 };
 
-// Back-trace from (s_end, k_end) through a wavefront history (any type with m / i / d readers, see
-// WfaWsHist); ops are handed to the sink from the LAST operation to the first.  One lane.
+// Back-trace from (s_end, k_end) through a wavefront history (any type with a row(s) whose m / i / d read a cell,
+// TRGT_WFA_NULL for one that is not stored; see WfaWsHist); ops are handed to the sink from the LAST operation to the first.  One lane.
 template <class Hist, class Sink>
 TRGT_HD void wfa_backtrace_h(const WfaProb &pr, int s_end, int k_end, int off_end, const Hist &hist, Sink &sink) {
   enum { T_I1O = 1, T_I1E = 2, T_D1O = 5, T_D1E = 6, T_M = 9 };
@@ -561,11 +566,12 @@ TRGT_HD void wfa_backtrace_h(const WfaProb &pr, int s_end, int k_end, int off_en
 #define TRGT_PG(o, tag) ((o) < 0 ? (long long)TRGT_WFA_NULL : ((((long long)(o)) << 4) | (tag)))
   while (v > 0 && h > 0 && sc > 0) {
     const int sx = sc - pr.x, so = sc - pr.oe, se = sc - pr.e;
-    const long long c_m = TRGT_PG(hist.m(sx, k) + 1, T_M);
-    const long long c_io = TRGT_PG(hist.m(so, k - 1) + 1, T_I1O);
-    const long long c_ie = TRGT_PG(hist.i(se, k - 1) + 1, T_I1E);
-    const long long c_do = TRGT_PG(hist.m(so, k + 1), T_D1O);
-    const long long c_de = TRGT_PG(hist.d(se, k + 1), T_D1E);
+    const typename Hist::Row rx = hist.row(sx), ro = hist.row(so), re = hist.row(se);
+    const long long c_m = TRGT_PG(rx.m(k) + 1, T_M);
+    const long long c_io = TRGT_PG(ro.m(k - 1) + 1, T_I1O);
+    const long long c_ie = TRGT_PG(re.i(k - 1) + 1, T_I1E);
+    const long long c_do = TRGT_PG(ro.m(k + 1), T_D1O);
+    const long long c_de = TRGT_PG(re.d(k + 1), T_D1E);
     long long mx;
     if (mt == C_M) {
       mx = c_m;
@@ -1575,9 +1581,14 @@ struct Ft1Hist {
     const int v = h[((ft1_row(live_m, s) * 3 + c) * FT1_WMAX + (k - blo)) * LS];
     return v < 0 ? TRGT_WFA_NULL : v + blo;
   }
-  TRGT_HD int m(int s, int k) const { return cell(s, 0, k); }
-  TRGT_HD int i(int s, int k) const { return s < 1 ? TRGT_WFA_NULL : cell(s, 1, k); }
-  TRGT_HD int d(int s, int k) const { return s < 1 ? TRGT_WFA_NULL : cell(s, 2, k); }
+  struct Row {
+    const Ft1Hist *h;
+    int s;
+    TRGT_HD int m(int k) const { return h->cell(s, 0, k); }
+    TRGT_HD int i(int k) const { return s < 1 ? TRGT_WFA_NULL : h->cell(s, 1, k); }
+    TRGT_HD int d(int k) const { return s < 1 ? TRGT_WFA_NULL : h->cell(s, 2, k); }
+  };
+  TRGT_HD Row row(int s) const { Row r; r.h = this; r.s = s; return r; }
 };
 
 // wfa_forward_band_hist_narrow_thread on the staged window: text offset h lives at win[h - a0].
