@@ -52,6 +52,12 @@ def parse_args():
                     help="loci per chunk of the end-to-end driver (0: two chunks per host thread)")
     ap.add_argument("--host-threads", type=int, default=0,
                     help="host threads (one engine each) of the e2e driver (0: host cores / ranks, between 2 and 8)")
+    ap.add_argument("--upload-slots", type=int, default=2,
+                    help="chunks that may be inside their phase-A call (the PCIe-heavy one) at a time; 0 = no limit")
+    ap.add_argument("--uploaders", type=int, default=0,
+                    help="host threads that only upload phase A's inputs (resident-batch API), the others process; 0 = every "
+                         "thread runs whole chunks through the one-shot calls")
+    ap.add_argument("--max-inflight", type=int, default=4, help="chunks the uploaders may be ahead of the workers")
     ap.add_argument("--e2e-input", default="seq4", choices=["seq4", "ascii"],
                     help="how the e2e driver hands reads to phase A: BAM 4-bit bases (trgt_flank_spans_seq4) or ASCII")
     return ap.parse_args()
@@ -351,7 +357,8 @@ def run_b200(args):
     engines = [eng] + [trgt_b200.Engine(device=local_rank) for _ in range(max(1, args.host_threads) - 1)]
     # host cores are shared by all ranks of the box and all host threads of a rank
     glue_threads = max(1, host_cores() // max(1, world * len(engines)))
-    chp = ChunkedHotPath(engines, w, chunk_loci=args.chunk_loci, glue_threads=glue_threads, use_seq4=use_seq4)
+    chp = ChunkedHotPath(engines, w, chunk_loci=args.chunk_loci, glue_threads=glue_threads, use_seq4=use_seq4,
+                         upload_slots=args.upload_slots, uploaders=args.uploaders, max_inflight=args.max_inflight)
 
     # ---- warm-up: end-to-end passes (also builds the resident batches) ----
     res = None
@@ -642,6 +649,7 @@ def run_b200(args):
         "gpu_launches_per_step": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),
+                "upload_slots": args.upload_slots, "uploaders": args.uploaders,
                 "reads_in": "BAM 4-bit bases (trgt_flank_spans_seq4), decoded on the device" if use_seq4 else "ASCII (trgt_flank_spans)",
                 "glue_threads": glue_threads, "phase_ms_summed_over_host_threads": e2e_phases},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "clip_row": clip, "vcf_row": vcf,

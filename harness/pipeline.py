@@ -75,21 +75,58 @@ class HotPath:
         return int(n)
 
     # -- end to end through the one-shot C-ABI calls ------------------------------------------
-    def run_e2e(self, copy: bool = False) -> HotPathResult:
-        """copy=False: results alias pinned buffers (the engine's, this object's) until the next pass."""
-        w, eng = self.w, self.eng
+    def run_e2e(self, copy: bool = False, eng=None, uploaded=None) -> HotPathResult:
+        """copy=False: results alias pinned buffers (the engine's, this object's) until the next pass.
+        eng: the engine to call (default: the one this object was built on; its pinned buffers serve any engine of
+        the process); uploaded: called once the phase-A call -- the one that moves the reads over PCIe -- has returned."""
+        w = self.w
+        eng = eng or self.eng
         t0 = time.perf_counter()
-        if self.use_seq4:
-            spans, hits = eng.flank_spans_seq4(w.left, w.right, w.reads4, w.locus_read_off, w.scoring,
-                                               w.min_flank_id_frac, want_hits=self.want_hits,
-                                               spans_out=self._spans, hits_out=self._hits)
-        else:
-            spans, hits = eng.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring,
-                                                 w.min_flank_id_frac, want_hits=self.want_hits,
-                                                 spans_out=self._spans, hits_out=self._hits)
+        try:
+            if self.use_seq4:
+                spans, hits = eng.flank_spans_seq4(w.left, w.right, w.reads4, w.locus_read_off, w.scoring,
+                                                   w.min_flank_id_frac, want_hits=self.want_hits,
+                                                   spans_out=self._spans, hits_out=self._hits)
+            else:
+                spans, hits = eng.flank_spans_packed(w.left, w.right, w.reads, w.locus_read_off, w.scoring,
+                                                     w.min_flank_id_frac, want_hits=self.want_hits,
+                                                     spans_out=self._spans, hits_out=self._hits)
+        finally:
+            if uploaded is not None:
+                uploaded()
         trs = eng.flank_trs() if self.use_seq4 else None  # the host holds no ASCII reads to cut them from
         t1 = time.perf_counter()
         glue = genotype_glue(w, spans, threads=self.glue_threads, ctx=self._glue_ctx, trs=trs)
+        t2 = time.perf_counter()
+        cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off, copy=copy)
+        t3 = time.perf_counter()
+        ann = eng.hmm_label_packed(w.motifs, w.locus_motif_off, glue.backbones, glue.group_locus, copy=copy)
+        t4 = time.perf_counter()
+        for k, v in (("flank", t1 - t0), ("glue", t2 - t1), ("align", t3 - t2), ("hmm", t4 - t3)):
+            self.timing[k] += v
+        return HotPathResult(spans, hits, glue, cigars, ann)
+
+    # -- end to end, phase A's upload done by somebody else --------------------------------------
+    def upload(self, eng):
+        """phase A's inputs of this chunk into a resident batch (blocks until they have landed)"""
+        w = self.w
+        if self.use_seq4:
+            return eng.flank_upload_seq4(w.left, w.right, w.reads4, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+        return eng.flank_upload(w.left, w.right, w.reads, w.locus_read_off, w.scoring, w.min_flank_id_frac)
+
+    def run_uploaded(self, eng, fb, copy: bool = False) -> HotPathResult:
+        """the rest of the end-to-end pass on a batch `upload` produced (frees it)"""
+        w = self.w
+        t0 = time.perf_counter()
+        try:
+            eng.flank_run(fb)
+            spans, hits = eng.flank_download(fb, w.n_reads, want_hits=self.want_hits, spans_out=self._spans,
+                                             hits_out=self._hits)
+            trs = eng.flank_trs(fb) if self.use_seq4 else None
+            t1 = time.perf_counter()
+            glue = genotype_glue(w, spans, threads=self.glue_threads, ctx=self._glue_ctx, trs=trs)
+        finally:
+            eng.flank_free(fb)  # (the repeat sequences were views of the batch's pinned buffers: the glue has copied them)
         t2 = time.perf_counter()
         cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off, copy=copy)
         t3 = time.perf_counter()
@@ -147,8 +184,21 @@ class ChunkedHotPath:
     runs phases A, glue, B, C per chunk through the blocking C ABI, so one chunk's PCIe transfers
     overlap another chunk's kernels and host glue."""
 
-    def __init__(self, engines, w: Workload, chunk_loci: int = 16384, glue_threads: int = 0, use_seq4: bool = False):
+    def __init__(self, engines, w: Workload, chunk_loci: int = 16384, glue_threads: int = 0, use_seq4: bool = False,
+                 upload_slots: int = 2, uploaders: int = 0, max_inflight: int = 4):
+        """upload_slots: how many chunks may be inside their phase-A call (the one that moves the reads over PCIe)
+        at a time; 0 = no limit and chunk i statically on thread i mod threads.  Without a limit all threads
+        upload together, then all compute together while the link idles (measured: 52 ms per 125 k-locus shard at
+        8 threads where the copies alone take 40); with one or two slots the chunks go up one after the other, in
+        order, and every other phase of a chunk overlaps the uploads of the next ones."""
         self.engines = list(engines)
+        self.upload_slots = upload_slots
+        # uploaders > 0: that many of the host threads do nothing but phase A's uploads (trgt_flank_upload*), chunk after
+        # chunk in order, at most max_inflight chunks ahead; the others take the uploaded batches through
+        # trgt_flank_run / _download / _trs, the glue and phases B and C.  The link never waits for a kernel or the host.
+        self.uploaders = min(uploaders, max(0, len(self.engines) - 1))
+        self.max_inflight = max_inflight
+        self.upload_s = 0.0
         self.w = w
         self.bounds = [(l0, min(l0 + chunk_loci, w.n_loci)) for l0 in range(0, w.n_loci, chunk_loci)]
         # every chunk's arrays (the rebased offsets are fresh copies) in pinned memory, as a host that packs into
@@ -166,15 +216,91 @@ class ChunkedHotPath:
                 out[k] += p.timing[k]
         return out
 
+    def _run_pipelined(self):
+        n, engines, U = len(self.paths), self.engines, self.uploaders
+        ready = [threading.Event() for _ in range(n)]
+        fbs = [None] * n
+        results = [None] * n
+        errors = []
+        inflight = threading.Semaphore(self.max_inflight)
+        lock = threading.Lock()
+        nxt = {"up": 0, "wk": 0}
+
+        def take(kind):
+            with lock:
+                i = nxt[kind]
+                nxt[kind] += 1
+            return i
+
+        def uploader(k):
+            try:
+                while True:
+                    inflight.acquire()
+                    i = take("up")
+                    if i >= n or errors:
+                        inflight.release()
+                        return
+                    t0 = time.perf_counter()
+                    fbs[i] = self.paths[i].upload(engines[k])
+                    self.upload_s += time.perf_counter() - t0
+                    ready[i].set()
+            except Exception as exc:
+                errors.append(exc)
+                for ev in ready:
+                    ev.set()
+
+        def worker(k):
+            try:
+                while True:
+                    i = take("wk")
+                    if i >= n:
+                        return
+                    ready[i].wait()
+                    if errors:
+                        return
+                    results[i] = self.paths[i].run_uploaded(engines[k], fbs[i], copy=True)
+                    fbs[i] = None
+                    inflight.release()
+            except Exception as exc:
+                errors.append(exc)
+                inflight.release()
+
+        threads = [threading.Thread(target=uploader, args=(k,)) for k in range(U)]
+        threads += [threading.Thread(target=worker, args=(k,)) for k in range(U, len(engines))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results
+
     def run_e2e(self):
+        if self.uploaders > 0:
+            return self._run_pipelined()
         n_eng = len(self.engines)
         results = [None] * len(self.paths)
         errors = []
 
+        gate = threading.Semaphore(self.upload_slots) if self.upload_slots > 0 else None
+        take = threading.Lock()
+        nxt = [0]
+
         def work(k):
             try:
-                for i in range(k, len(self.paths), n_eng):
-                    results[i] = self.paths[i].run_e2e(copy=True)
+                if gate is None:
+                    for i in range(k, len(self.paths), n_eng):
+                        results[i] = self.paths[i].run_e2e(copy=True)
+                    return
+                while True:
+                    gate.acquire()          # a slot on the link first, then the next chunk: chunks go up in order
+                    with take:
+                        i = nxt[0]
+                        nxt[0] += 1
+                    if i >= len(self.paths):
+                        gate.release()
+                        return
+                    results[i] = self.paths[i].run_e2e(copy=True, eng=self.engines[k], uploaded=gate.release)
             except Exception as exc:  # surfaced to the caller below
                 errors.append(exc)
 

@@ -11,6 +11,7 @@
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -116,15 +117,76 @@ int fail(trgt_engine *e, int code, const char *fmt, ...) {
     if (rc_ != 0) return rc_; \
   } while (0)
 
+// Buffers of resident batches that have been freed wait here for the next batch (process-wide, per device): a host
+// that streams chunk after chunk through trgt_*_upload / _free would otherwise pay a cudaMalloc / cudaFree (each a
+// device-wide synchronisation) and a cudaMallocHost per array and chunk.  Emptied when the last engine of the
+// device is destroyed.
+struct PoolEntry { void *p; size_t cap; int device; };
+struct BufPool {
+  std::mutex mu;
+  std::vector<PoolEntry> dev, pin;
+  size_t dev_bytes = 0, pin_bytes = 0;
+  int engines[64] = {0};
+  unsigned long long hits = 0, misses = 0, puts = 0, rejected = 0;  // TRGT_TRACE prints them when a device's last engine goes
+};
+BufPool g_pool;
+const size_t POOL_DEV_MAX = 32ull << 30, POOL_PIN_MAX = 4ull << 30;
+
+// best fit: the smallest pooled buffer that holds `bytes` without being wastefully large
+void *pool_take(std::vector<PoolEntry> &v, size_t &total, int device, size_t bytes, size_t *cap_out) {
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  int best = -1;
+  for (size_t i = 0; i < v.size(); i++)
+    if (v[i].device == device && v[i].cap >= bytes && v[i].cap <= 4 * bytes + (4u << 20) &&
+        (best < 0 || v[i].cap < v[(size_t)best].cap))
+      best = (int)i;
+  if (best < 0) { g_pool.misses++; return nullptr; }
+  g_pool.hits++;
+  void *p = v[(size_t)best].p;
+  *cap_out = v[(size_t)best].cap;
+  total -= v[(size_t)best].cap;
+  v[(size_t)best] = v.back();
+  v.pop_back();
+  return p;
+}
+
+bool pool_put(std::vector<PoolEntry> &v, size_t &total, size_t max_total, int device, void *p, size_t cap) {
+  std::lock_guard<std::mutex> lk(g_pool.mu);
+  if (device < 0 || device >= 64 || g_pool.engines[device] <= 0 || total + cap > max_total) { g_pool.rejected++; return false; }
+  g_pool.puts++;
+  v.push_back(PoolEntry{p, cap, device});
+  total += cap;
+  return true;
+}
+
+void pool_release(int device) {
+  std::vector<PoolEntry> d, h;
+  {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    for (size_t i = 0; i < g_pool.dev.size();)
+      if (g_pool.dev[i].device == device) {
+        d.push_back(g_pool.dev[i]); g_pool.dev_bytes -= g_pool.dev[i].cap;
+        g_pool.dev[i] = g_pool.dev.back(); g_pool.dev.pop_back();
+      } else i++;
+    for (size_t i = 0; i < g_pool.pin.size();)
+      if (g_pool.pin[i].device == device) {
+        h.push_back(g_pool.pin[i]); g_pool.pin_bytes -= g_pool.pin[i].cap;
+        g_pool.pin[i] = g_pool.pin.back(); g_pool.pin.pop_back();
+      } else i++;
+  }
+  for (auto &x : d) cudaFree(x.p);
+  for (auto &x : h) cudaFreeHost(x.p);
+}
+
 int dev_reserve(trgt_engine *e, DevBuf &b, size_t bytes, bool keep = false) {
   if (bytes <= b.cap && b.p) return 0;
-  size_t ncap = bytes + bytes / 8 + 256;
-  void *np = nullptr;
-  CU(e, cudaMalloc(&np, ncap));
+  size_t ncap = bytes + bytes / 8 + 256;  // (a pooled buffer only has to hold `bytes`: the slack is for fresh ones)
+  void *np = pool_take(g_pool.dev, g_pool.dev_bytes, e->device, bytes, &ncap);
+  if (!np) CU(e, cudaMalloc(&np, ncap));
   if (keep && b.p && b.cap) CU(e, cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, e->stream));
   if (b.p) {
     CU(e, cudaStreamSynchronize(e->stream));
-    CU(e, cudaFree(b.p));
+    if (!pool_put(g_pool.dev, g_pool.dev_bytes, POOL_DEV_MAX, e->device, b.p, b.cap)) CU(e, cudaFree(b.p));
   }
   b.p = np;
   b.cap = ncap;
@@ -133,23 +195,25 @@ int dev_reserve(trgt_engine *e, DevBuf &b, size_t bytes, bool keep = false) {
 
 int pin_reserve(trgt_engine *e, PinBuf &b, size_t bytes) {
   if (bytes <= b.cap && b.p) return 0;
-  if (b.p) cudaFreeHost(b.p);
+  if (b.p && !pool_put(g_pool.pin, g_pool.pin_bytes, POOL_PIN_MAX, e->device, b.p, b.cap)) cudaFreeHost(b.p);
   b.p = nullptr;
   b.cap = 0;
-  const size_t ncap = bytes + bytes / 8 + 256;
-  CU(e, cudaMallocHost(&b.p, ncap));
+  size_t ncap = bytes + bytes / 8 + 256;
+  b.p = pool_take(g_pool.pin, g_pool.pin_bytes, e->device, bytes, &ncap);
+  if (!b.p) CU(e, cudaMallocHost(&b.p, ncap));
   b.cap = ncap;
   return 0;
 }
 
-void pin_free(PinBuf &b) {
-  if (b.p) cudaFreeHost(b.p);
+// device >= 0: the buffer goes to the pool of that device (the caller has made sure nothing in flight uses it)
+void pin_free(PinBuf &b, int device = -1) {
+  if (b.p && !pool_put(g_pool.pin, g_pool.pin_bytes, POOL_PIN_MAX, device, b.p, b.cap)) cudaFreeHost(b.p);
   b.p = nullptr;
   b.cap = 0;
 }
 
-void dev_free(DevBuf &b) {
-  if (b.p) cudaFree(b.p);
+void dev_free(DevBuf &b, int device = -1) {
+  if (b.p && !pool_put(g_pool.dev, g_pool.dev_bytes, POOL_DEV_MAX, device, b.p, b.cap)) cudaFree(b.p);
   b.p = nullptr;
   b.cap = 0;
 }
@@ -334,6 +398,10 @@ int32_t trgt_engine_create(int32_t device, trgt_engine_t **out) {
     }
   }
   e->hmm_consts = hmm_make_consts();
+  {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    if (e->device >= 0 && e->device < 64) g_pool.engines[e->device]++;
+  }
   *out = e;
   return TRGT_OK;
 }
@@ -356,6 +424,17 @@ void trgt_engine_destroy(trgt_engine_t *e) {
   if (e->h_u64) cudaFreeHost(e->h_u64);
   cudaStreamDestroy(e->stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  bool last = false;
+  {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    if (e->device >= 0 && e->device < 64) last = --g_pool.engines[e->device] == 0;
+  }
+  if (last) {
+    if (getenv("TRGT_TRACE"))
+      fprintf(stderr, "[trgt] buffer pool: %llu hits, %llu misses, %llu puts, %llu not pooled\n", g_pool.hits, g_pool.misses,
+              g_pool.puts, g_pool.rejected);
+    pool_release(e->device);
+  }
   delete e;
 }
 
@@ -514,9 +593,10 @@ void trgt_flank_free(trgt_engine_t *e, trgt_flank_batch_t *b) {
   DevBuf *all[] = {&b->reads, &b->read_off, &b->lp, &b->lp_off, &b->rp, &b->rp_off, &b->locus_read_off,
                    &b->read_locus, &b->hits, &b->spans, &b->work, &b->work2, &b->list1, &b->ends, &b->ctr, &b->gring, &b->gws,
                    &b->seq4, &b->seq4_starts, &b->seq4_len, &b->tr_len, &b->tr_off, &b->tr_data, &b->kidx};
-  for (auto *d : all) dev_free(*d);
-  pin_free(b->h_tr_off);
-  pin_free(b->h_tr_data);
+  const int device = e ? e->device : -1;  // with an engine (its stream has drained): the buffers wait for the next batch
+  for (auto *d : all) dev_free(*d, device);
+  pin_free(b->h_tr_off, device);
+  pin_free(b->h_tr_data, device);
   delete b;
 }
 
@@ -978,10 +1058,23 @@ int32_t trgt_flank_spans_seq4(trgt_engine_t *e, const trgt_seqs_t *left_pieces, 
   if (!e) return TRGT_ERR_ARG;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->one_flank) e->one_flank = new trgt_flank_batch();
+  static const bool trace = getenv("TRGT_TRACE") != nullptr;  // host-side stage times of this call, to stderr
+  const auto t0 = std::chrono::steady_clock::now();
   TRY(flank_upload_seq4_into(e, e->one_flank, left_pieces, right_pieces, reads, locus_read_offsets, n_loci, scoring,
                              min_flank_id_frac));
+  const auto t1 = std::chrono::steady_clock::now();
   TRY(flank_oneshot_seq4_locked(e, e->one_flank, reads, locus_read_offsets, n_loci));
-  return flank_download_locked(e, e->one_flank, spans_out, hits_out);
+  const auto t2 = std::chrono::steady_clock::now();
+  const int rc = flank_download_locked(e, e->one_flank, spans_out, hits_out);
+  if (trace) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    fprintf(stderr, "[trgt] flank_spans_seq4: checks + small uploads %.3f ms, reads + kernels %.3f ms, download %.3f ms\n",
+            ms(t0, t1), ms(t1, t2), ms(t2, t3));
+  }
+  return rc;
 }
 
 int32_t trgt_seq4_decode(trgt_engine_t *e, const trgt_seq4_t *reads, uint8_t *ascii_out, uint64_t *ascii_offsets_out) {

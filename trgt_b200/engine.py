@@ -504,9 +504,10 @@ class Engine:
     def flank_run(self, b):
         self._check(self._L.trgt_flank_run(self._h, b), "trgt_flank_run")
 
-    def flank_download(self, b, n_reads: int, want_hits: bool = True):
-        spans = np.zeros(n_reads, dtype=SPAN_DTYPE)
-        hits = np.zeros(2 * n_reads, dtype=HIT_DTYPE) if want_hits else None
+    def flank_download(self, b, n_reads: int, want_hits: bool = True, spans_out=None, hits_out=None):
+        """spans_out / hits_out: caller's (pinned) arrays to fill instead of fresh ones"""
+        spans = spans_out if spans_out is not None else np.zeros(n_reads, dtype=SPAN_DTYPE)
+        hits = (hits_out if hits_out is not None else np.zeros(2 * n_reads, dtype=HIT_DTYPE)) if want_hits else None
         self._check(self._L.trgt_flank_download(self._h, b, spans.ctypes.data,
                                                 hits.ctypes.data if hits is not None else None), "trgt_flank_download")
         return spans, hits
