@@ -67,3 +67,16 @@ def test_plain_c_caller_on_the_gpu(tmp_path):
     assert lines[1] == "span 1 1 350 383 via 2 1"
     assert lines[2].startswith("span 2 0 ")
     assert int(lines[3].split()[1]) > 0
+    got = {l.split()[0] + (" " + l.split()[1] if l.split()[0] in ("tr", "bamlet", "cigar", "allele") else ""): l for l in lines[4:]}
+    assert got["tr 0"] == "tr 0 " + ("CAG" * 10) and got["tr 1"] == "tr 1 " + ("CAG" * 11) and got["tr 2"].strip() == "tr 2"
+    # write_bam.rs:80-92: 50 bases of flank either side of the span; read 2 has no span -> no record
+    assert got["bamlet 0"] == "bamlet 0 status 1 bases 300 430 ref 1300 ops 1 first 130="
+    assert got["bamlet 1"] == "bamlet 1 status 1 bases 300 433 ref 2300 ops 1 first 133="
+    assert got["bamlet 2"].startswith("bamlet 2 status 0 ")
+    assert got["cigar 0"] == "cigar 0 score 0: 30="
+    assert got["cigar 1"].startswith("cigar 1 score -8:") and got["cigar 2"] == "cigar 2 score -2: 11= 1X 18="
+    assert got["consensus"] == "consensus " + "CAG" * 10
+    assert got["dist"] == "dist 1.732051 1.000000 1.732051"
+    assert got["allele 0"] == "allele 0 MC 11 MS 0(0-33) AP 1.000000" and got["allele 1"] == got["allele 0"].replace("allele 0", "allele 1")
+    assert got["vcf"] == "vcf 33,33 11,11 0(0-33),0(0-33) 1.000000,1.000000"      # docs/tutorial.md:44
+    assert got["clip"] == "clip status 1 ref 12 query 2 5 ops 3"                    # clip_region.rs:257-269

@@ -61,6 +61,7 @@ struct trgt_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // H2D of read chunks, overlapped with phase A kernels
+  cudaEvent_t sleep_ev = nullptr;      // blocking-sync event: waits on the stream sleep instead of spinning (TRGT_SYNC=sleep)
   int sm_count = 0;
   int smem_optin = 0;
   std::string error;
@@ -116,6 +117,16 @@ int fail(trgt_engine *e, int code, const char *fmt, ...) {
     int rc_ = (expr);      \
     if (rc_ != 0) return rc_; \
   } while (0)
+
+// Wait for everything queued on the engine's stream.  A host that drives one engine per thread, several threads per
+// GPU, has as many threads inside such waits as it has engines: spinning (the driver's default) takes a core each
+// away from the host's own work, sleeping on a blocking-sync event gives it back at the price of a wake-up.
+cudaError_t engine_wait(trgt_engine *e) {
+  if (e->sleep_ev == nullptr) return cudaStreamSynchronize(e->stream);
+  cudaError_t err = cudaEventRecord(e->sleep_ev, e->stream);
+  if (err != cudaSuccess) return err;
+  return cudaEventSynchronize(e->sleep_ev);
+}
 
 // Buffers of resident batches that have been freed wait here for the next batch (process-wide, per device): a host
 // that streams chunk after chunk through trgt_*_upload / _free would otherwise pay a cudaMalloc / cudaFree (each a
@@ -185,7 +196,7 @@ int dev_reserve(trgt_engine *e, DevBuf &b, size_t bytes, bool keep = false) {
   if (!np) CU(e, cudaMalloc(&np, ncap));
   if (keep && b.p && b.cap) CU(e, cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, e->stream));
   if (b.p) {
-    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, engine_wait(e));
     if (!pool_put(g_pool.dev, g_pool.dev_bytes, POOL_DEV_MAX, e->device, b.p, b.cap)) CU(e, cudaFree(b.p));
   }
   b.p = np;
@@ -266,7 +277,7 @@ struct LaunchScope {
 
 void resolve_pending(trgt_engine *e) {
   if (e->pending.empty()) return;
-  cudaStreamSynchronize(e->stream);
+  engine_wait(e);
   for (auto &p : e->pending) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) e->stats[p.stat].total_ms += ms;
@@ -383,6 +394,15 @@ int32_t trgt_engine_create(int32_t device, trgt_engine_t **out) {
     delete e;
     return TRGT_ERR_CUDA;
   }
+  {
+    const char *mode = getenv("TRGT_SYNC");
+    if (mode && strcmp(mode, "sleep") == 0 &&
+        (err = cudaEventCreateWithFlags(&e->sleep_ev, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) {
+      g_create_error = std::string("engine setup failed: ") + cudaGetErrorString(err);
+      trgt_engine_destroy(e);
+      return TRGT_ERR_CUDA;
+    }
+  }
   // Dynamic shared memory limits are per-function process state: raise them once to the device
   // maximum (never per launch, engines on other host threads may be launching concurrently).
   {
@@ -390,6 +410,7 @@ int32_t trgt_engine_create(int32_t device, trgt_engine_t **out) {
     if ((err = cudaFuncSetAttribute(k_wfa_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_wfa_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_wfa_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
+        (err = cudaFuncSetAttribute(k_flank_band1, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_hmm_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_hmm_viterbi_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) {
       g_create_error = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(err);
@@ -409,7 +430,7 @@ int32_t trgt_engine_create(int32_t device, trgt_engine_t **out) {
 void trgt_engine_destroy(trgt_engine_t *e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  cudaStreamSynchronize(e->stream);
+  engine_wait(e);
   if (e->one_flank) trgt_flank_free(e, e->one_flank);
   if (e->one_align) trgt_align_free(e, e->one_align);
   if (e->one_hmm) trgt_hmm_free(e, e->one_hmm);
@@ -422,6 +443,7 @@ void trgt_engine_destroy(trgt_engine_t *e) {
   for (auto &b : e->d_cl) dev_free(b);
   if (e->h_ctr) cudaFreeHost(e->h_ctr);
   if (e->h_u64) cudaFreeHost(e->h_u64);
+  if (e->sleep_ev) cudaEventDestroy(e->sleep_ev);
   cudaStreamDestroy(e->stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   bool last = false;
@@ -444,7 +466,7 @@ int32_t trgt_engine_sm_count(const trgt_engine_t *e) { return e ? e->sm_count : 
 
 int32_t trgt_engine_sync(trgt_engine_t *e) {
   if (!e) return TRGT_ERR_ARG;
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   return 0;
 }
 
@@ -587,7 +609,7 @@ void trgt_flank_free(trgt_engine_t *e, trgt_flank_batch_t *b) {
   if (!b) return;
   if (e) {
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
+    engine_wait(e);
     if (e->one_flank == b) e->one_flank = nullptr;
   }
   DevBuf *all[] = {&b->reads, &b->read_off, &b->lp, &b->lp_off, &b->rp, &b->rp_off, &b->locus_read_off,
@@ -677,7 +699,7 @@ int32_t trgt_flank_upload(trgt_engine_t *e, const trgt_seqs_t *left_pieces, cons
                              min_flank_id_frac);
   // the copies were queued from the caller's buffers: with pinned sources they are asynchronous to the host, and
   // the header promises that no pointer is retained after return
-  if (rc == 0 && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(e, TRGT_ERR_CUDA, "flank upload failed");
+  if (rc == 0 && engine_wait(e) != cudaSuccess) rc = fail(e, TRGT_ERR_CUDA, "flank upload failed");
   if (rc != 0) {
     trgt_flank_free(nullptr, b);
     return rc;
@@ -750,7 +772,6 @@ static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src
       rows = __builtin_popcount(live);
     }
     const size_t smem = fb1_smem_bytes(rows);
-    CU(e, cudaFuncSetAttribute(k_flank_band1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb1_smem_bytes(FT1_SMAX + 1)));
     int grid = 0;
     TRY(persistent_grid(e, k_flank_band1, FB1_THREADS, smem, &grid));
     LaunchScope ls(e, "k_flank_band1");
@@ -802,7 +823,7 @@ static int flank_finish(trgt_engine_t *e, trgt_flank_batch *b, const WfaSrc &src
     TRY(check_launch(e, "k_wfa_score_block"));
   }
   CU(e, cudaMemcpyAsync(e->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   b->last_n_work = e->h_ctr->n_work - e->h_ctr->n_banded;  // pairs that needed the full-width kernels
   b->last_n_tier2 = e->h_ctr->n_tier2;
   b->last_n_wide = e->h_ctr->n_work;
@@ -953,7 +974,7 @@ int32_t trgt_flank_upload_seq4(trgt_engine_t *e, const trgt_seqs_t *left_pieces,
     if (err != cudaSuccess) rc = fail(e, TRGT_ERR_CUDA, "seq4 upload failed: %s", cudaGetErrorString(err));
   }
   if (rc == 0) rc = launch_unpack(e, b->seq4, b->seq4_starts, b->seq4_len, b->read_off, b->reads, 0, b->n_reads);
-  if (rc == 0 && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(e, TRGT_ERR_CUDA, "seq4 decode failed");
+  if (rc == 0 && engine_wait(e) != cudaSuccess) rc = fail(e, TRGT_ERR_CUDA, "seq4 decode failed");
   if (rc != 0) {
     trgt_flank_free(nullptr, b);
     return rc;
@@ -1028,7 +1049,7 @@ static int flank_download_locked(trgt_engine_t *e, trgt_flank_batch *b, trgt_spa
     if (hits_out)
       CU(e, cudaMemcpyAsync(hits_out, b->hits.p, (size_t)b->n_reads * 2 * sizeof(trgt_flank_hit_t), cudaMemcpyDeviceToHost, e->stream));
   }
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   return 0;
 }
 
@@ -1091,7 +1112,7 @@ int32_t trgt_seq4_decode(trgt_engine_t *e, const trgt_seq4_t *reads, uint8_t *as
   TRY(launch_unpack(e, d[0], d[1], d[2], d[4], d[3], 0, (uint32_t)reads->n));
   if (total) CU(e, cudaMemcpyAsync(ascii_out, d[3].p, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaMemcpyAsync(ascii_offsets_out, d[4].p, (size_t)(reads->n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   return 0;
 }
 
@@ -1128,7 +1149,7 @@ int32_t trgt_bamlet_clip(trgt_engine_t *e, trgt_flank_batch_t *b, const uint32_t
     TRY(check_launch(e, "k_bamlet_clip"));
   }
   CU(e, cudaMemcpyAsync(clips_out, d[5].p, (size_t)n_reads * sizeof(trgt_bamlet_clip_t), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   return 0;
 }
 
@@ -1177,7 +1198,7 @@ int32_t trgt_clip_reads(trgt_engine_t *e, const uint32_t *cigar_ops, const uint6
     TRY(check_launch(e, "k_clip_cigar"));
   }
   CU(e, cudaMemcpyAsync(clips_out, d_clips, (size_t)n_reads * sizeof(trgt_clip_t), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   return 0;
 }
 
@@ -1204,7 +1225,7 @@ int32_t trgt_flank_trs(trgt_engine_t *e, trgt_flank_batch_t *b, trgt_seqs_out_t 
   }
   TRY(exclusive_scan_u32(e, (const uint32_t *)b->tr_len.p, (unsigned long long *)b->tr_off.p, (size_t)n + 1));
   CU(e, cudaMemcpyAsync(h_off, b->tr_off.p, ((size_t)n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   const uint64_t total = h_off[n];
   TRY(dev_reserve(e, b->tr_data, (size_t)total + 16));
   TRY(pin_reserve(e, b->h_tr_data, (size_t)total + 16));
@@ -1221,7 +1242,7 @@ int32_t trgt_flank_trs(trgt_engine_t *e, trgt_flank_batch_t *b, trgt_seqs_out_t 
       TRY(check_launch(e, "k_tr_gather"));
     }
     CU(e, cudaMemcpyAsync(b->h_tr_data.p, b->tr_data.p, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, engine_wait(e));
   }
   out->data = b->h_tr_data.as<uint8_t>();
   return 0;
@@ -1289,7 +1310,7 @@ void trgt_align_free(trgt_engine_t *e, trgt_align_batch_t *b) {
   if (!b) return;
   if (e) {
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
+    engine_wait(e);
     if (e->one_align == b) e->one_align = nullptr;
   }
   DevBuf *all[] = {&b->bb, &b->bb_off, &b->seqs, &b->seq_off, &b->group_off, &b->seq_group, &b->ends, &b->trace_work,
@@ -1362,7 +1383,7 @@ int32_t trgt_align_upload(trgt_engine_t *e, const trgt_seqs_t *backbones, const 
   trgt_align_batch *b = new trgt_align_batch();
   int rc = align_upload_into(e, b, backbones, seqs, group_seq_offsets, n_groups);
   // as trgt_flank_upload: the caller's buffers are free again when this returns
-  if (rc == 0 && cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail(e, TRGT_ERR_CUDA, "align upload failed");
+  if (rc == 0 && engine_wait(e) != cudaSuccess) rc = fail(e, TRGT_ERR_CUDA, "align upload failed");
   if (rc != 0) {
     trgt_align_free(nullptr, b);
     return rc;
@@ -1468,7 +1489,7 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
     TRY(check_launch(e, "k_wfa_score_warp"));
   }
   CU(e, cudaMemcpyAsync(e->h_ctr, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   // pool = words the one-pass path already placed + room for everything the trace pass may emit
   const unsigned long long words_bound = e->h_ctr->pool_used + e->h_ctr->words_bound;
   TRY(dev_reserve(e, b->pool, (size_t)(words_bound + 1) * sizeof(uint32_t), /*keep=*/true));
@@ -1510,13 +1531,13 @@ static int align_download_locked(trgt_engine_t *e, trgt_align_batch *b, trgt_cig
     CU(e, cudaMemcpyAsync(b->h_off.p, b->out_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(b->h_scores.p, b->scores.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(b->h_status.p, b->status.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, engine_wait(e));
     b->total_words = b->h_off.as<uint64_t>()[n];
   }
   TRY(pin_reserve(e, b->h_words, (size_t)(b->total_words + 1) * sizeof(uint32_t)));
   if (b->total_words) {
     CU(e, cudaMemcpyAsync(b->h_words.p, b->out_words.p, (size_t)b->total_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, engine_wait(e));
   }
   out->n = n;
   out->offsets = b->h_off.as<uint64_t>();
@@ -1575,7 +1596,7 @@ static int consensus_run_locked(trgt_engine_t *e, trgt_align_batch *b, trgt_seqs
   TRY(dev_reserve(e, b->cons_off, (ng + 2) * sizeof(unsigned long long)));
   // total CIGAR words bound the insertion records (one slot per word, plus one per group)
   CU(e, cudaMemcpyAsync(&e->h_u64[2], (unsigned long long *)b->out_off.p + b->n_seqs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   const unsigned long long total_words = b->n_seqs ? e->h_u64[2] : 0;
   TRY(dev_reserve(e, b->cons_recs, (size_t)(total_words + ng + 1) * sizeof(ConsRec)));
   const int block = 128, wpb = 4;
@@ -1608,7 +1629,7 @@ static int consensus_run_locked(trgt_engine_t *e, trgt_align_batch *b, trgt_seqs
   TRY(exclusive_scan_u32(e, (const uint32_t *)b->cons_len.p, (unsigned long long *)b->cons_off.p, ng + 1));
   CU(e, cudaMemcpyAsync(b->h_cons_off.p, b->cons_off.p, (ng + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaMemcpyAsync(b->h_cons_status.p, b->cons_status.p, ng * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   const unsigned long long total = b->h_cons_off.as<uint64_t>()[ng];
   TRY(dev_reserve(e, b->cons_data, (size_t)total + 16));
   TRY(pin_reserve(e, b->h_cons_data, (size_t)total + 16));
@@ -1621,7 +1642,7 @@ static int consensus_run_locked(trgt_engine_t *e, trgt_align_batch *b, trgt_seqs
         (const unsigned long long *)b->cons_off.p, (uint8_t *)b->cons_data.p);
     TRY(check_launch(e, "k_consensus_vote_write"));
     CU(e, cudaMemcpyAsync(b->h_cons_data.p, b->cons_data.p, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, engine_wait(e));
   }
   out->data = b->h_cons_data.as<uint8_t>();
   return 0;
@@ -1649,7 +1670,7 @@ static int edit_dist_device(trgt_engine_t *e, const uint8_t *d_seqs, const uint6
   TRY(h2d(e, e->d_ed[2], locus_seq_offsets, ((size_t)n_loci + 1) * sizeof(uint32_t)));
   TRY(h2d(e, e->d_ed[3], pair_off.data(), pair_off.size() * sizeof(unsigned long long)));
   TRY(dev_reserve(e, e->d_ed[4], (size_t)(total + 1) * sizeof(double)));
-  CU(e, cudaStreamSynchronize(e->stream));  // pair_off is a local
+  CU(e, engine_wait(e));  // pair_off is a local
   if (total == 0) return 0;
   int grid = 0;
   TRY(persistent_grid(e, k_edit_dist, 128, 0, &grid));
@@ -1676,7 +1697,7 @@ int32_t trgt_edit_dist(trgt_engine_t *e, const trgt_seqs_t *seqs, const uint32_t
   if (total == 0) return 0;
   if (!dists_out) return fail(e, TRGT_ERR_ARG, "dists_out is null");
   CU(e, cudaMemcpyAsync(dists_out, e->d_ed[4].p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   return 0;
 }
 
@@ -1705,7 +1726,7 @@ static int cluster_device(trgt_engine_t *e, uint32_t n_loci, uint64_t n_seqs, ui
   if (n_seqs) CU(e, cudaMemcpyAsync(group_out, e->d_cl[1].p, (size_t)n_seqs * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   CU(e, cudaMemcpyAsync(central_out, e->d_cl[2].p, (size_t)n_loci * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
   if (n_groups_out) CU(e, cudaMemcpyAsync(n_groups_out, e->d_cl[3].p, (size_t)n_loci * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   return 0;
 }
 
@@ -1779,7 +1800,7 @@ int32_t trgt_consensus_trs(trgt_engine_t *e, trgt_flank_batch_t *fb, const uint3
   std::vector<trgt_span_t> h_spans(fb->n_reads ? fb->n_reads : 1);
   if (fb->n_reads)
     CU(e, cudaMemcpyAsync(h_spans.data(), fb->spans.p, (size_t)fb->n_reads * sizeof(trgt_span_t), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   int pm = 0, tm = 0;
   for (int k = 0; k < 2; k++) {
     Part &p = parts[k];
@@ -1807,7 +1828,7 @@ int32_t trgt_consensus_trs(trgt_engine_t *e, trgt_flank_batch_t *fb, const uint3
                                                 (const unsigned long long *)p.off->p, p.n, (uint8_t *)p.data->p);
       TRY(check_launch(e, "k_trs_gather"));
     }
-    CU(e, cudaStreamSynchronize(e->stream));  // `off` and the index buffer are reused by the next part
+    CU(e, engine_wait(e));  // `off` and the index buffer are reused by the next part
   }
   if ((uint64_t)pm + (uint64_t)tm > 0x0fffffffull) return fail(e, TRGT_ERR_ARG, "sequence too long");
   TRY(align_prepare(e, b, group_offsets, n_groups, n_seqs, pm, tm));
@@ -1852,7 +1873,7 @@ void trgt_hmm_free(trgt_engine_t *e, trgt_hmm_batch_t *b) {
   if (!b) return;
   if (e) {
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
+    engine_wait(e);
     if (e->one_hmm == b) e->one_hmm = nullptr;
   }
   DevBuf *all[] = {&b->motifs, &b->motif_off, &b->locus_motif_off, &b->alleles, &b->allele_off, &b->allele_locus,
@@ -2015,7 +2036,7 @@ static int hmm_upload_into(trgt_engine_t *e, trgt_hmm_batch *b, const trgt_seqs_
   if (e->jump_uploaded_len != e->jump.lp.size() || !e->d_mm_lp.p) {
     TRY(h2d(e, e->d_mm_off, e->jump.off.data(), e->jump.off.size() * sizeof(uint32_t)));
     TRY(h2d(e, e->d_mm_lp, e->jump.lp.data(), e->jump.lp.size() * sizeof(double)));
-    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, engine_wait(e));
     e->jump_uploaded_len = e->jump.lp.size();
   }
   TRY(upload_seqs(e, motifs, b->motifs, b->motif_off));
@@ -2034,7 +2055,7 @@ static int hmm_upload_into(trgt_engine_t *e, trgt_hmm_batch *b, const trgt_seqs_
     TRY(h2d(e, b->group_n, b->h_group_n.data(), b->h_group_n.size()));
   }
   TRY(h2d(e, b->mc_off, b->h_mc_off.data(), (n + 1) * sizeof(unsigned long long)));
-  CU(e, cudaStreamSynchronize(e->stream));  // h_* vectors may be reallocated by the next upload
+  CU(e, engine_wait(e));  // h_* vectors may be reallocated by the next upload
   TRY(dev_reserve(e, b->mc, (size_t)(b->h_mc_off[n] + 1) * sizeof(uint32_t)));
   TRY(dev_reserve(e, b->purity, (n + 1) * sizeof(double)));
   TRY(dev_reserve(e, b->n_spans, (n + 2) * sizeof(uint32_t)));
@@ -2200,7 +2221,7 @@ static int hmm_run_locked(trgt_engine_t *e, trgt_hmm_batch *b) {
     TRY(check_launch(e, "k_scan_u64_serial"));
     CU(e, cudaMemcpyAsync(&e->h_u64[1], (unsigned long long *)b->path_off.p + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
   }
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   const unsigned long long span_end = e->h_u64[0];
   const unsigned long long path_end = b->want_paths ? e->h_u64[1] : 0;
   TRY(dev_reserve(e, b->spans, (size_t)(span_end + 1) * sizeof(trgt_motif_span_t)));
@@ -2278,7 +2299,7 @@ static int hmm_download_locked(trgt_engine_t *e, trgt_hmm_batch *b, trgt_annotat
       if (b->total_path)
         CU(e, cudaMemcpyAsync(b->r_paths.p, b->paths.p, (size_t)b->total_path * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     }
-    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, engine_wait(e));
   }
   out->n = n;
   out->motif_count_offsets = b->h_mc_off.empty() ? zero_off : (const uint64_t *)b->h_mc_off.data();
@@ -2330,7 +2351,7 @@ int32_t trgt_vcf_fields(trgt_engine_t *e, trgt_hmm_batch_t *b, trgt_seqs_out_t *
   }
   TRY(exclusive_scan_u32(e, (const uint32_t *)b->vcf_len.p, (unsigned long long *)b->vcf_off.p, nf + 1));
   CU(e, cudaMemcpyAsync(h_off, b->vcf_off.p, (nf + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   const uint64_t total = h_off[nf];
   TRY(dev_reserve(e, b->vcf_data, (size_t)total + 16));
   TRY(pin_reserve(e, b->r_vcf_data, (size_t)total + 16));
@@ -2341,7 +2362,7 @@ int32_t trgt_vcf_fields(trgt_engine_t *e, trgt_hmm_batch_t *b, trgt_seqs_out_t *
   }
 #undef VCF_ARGS
   if (total) CU(e, cudaMemcpyAsync(b->r_vcf_data.p, b->vcf_data.p, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
-  CU(e, cudaStreamSynchronize(e->stream));
+  CU(e, engine_wait(e));
   out->data = b->r_vcf_data.as<uint8_t>();
   return 0;
 }
