@@ -1,9 +1,11 @@
-"""Aggregate the ncu per-line instruction shares of one kernel by enclosing function (line ranges
+"""Usage: ncu_by_func.py <report> <mangled-kernel-substring> [lib.so].
+Aggregate the ncu per-line instruction shares of one kernel by enclosing function (line ranges
 taken from the source files by a crude scan for TRGT_HD / __global__ / template heads)."""
 import os, re, subprocess, sys, collections
 rep, kern = sys.argv[1], sys.argv[2]
+lib = [sys.argv[3]] if len(sys.argv) > 3 else []   # the .so the report was captured with (default: the current build)
 here = os.path.dirname(os.path.abspath(__file__))
-out = subprocess.run([sys.executable, os.path.join(here, "ncu_by_line.py"), rep, kern, "--all"], capture_output=True, text=True).stdout
+out = subprocess.run([sys.executable, os.path.join(here, "ncu_by_line.py"), rep, kern] + lib + ["--all"], capture_output=True, text=True).stdout
 csrc = os.path.join(os.path.dirname(here), "trgt_b200", "csrc")
 bounds = {}
 for f in os.listdir(csrc):
