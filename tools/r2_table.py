@@ -1,7 +1,7 @@
 """Markdown table of the step's kernels: CUDA-event time and share from a bench line, algorithmic bytes and achieved
-GB/s from the same line, DRAM traffic / issue-active / warps-active / lanes-per-instruction from the ncu captures
-gpurun_out/<tag>_<kernel>.ncu-rep.  Usage: r2_table.py <bench.json> <tag> [--traffic-json out.json]"""
-import csv, io, json, os, subprocess, sys
+GB/s from the same line, DRAM traffic / issue-active / warps-active / lanes-per-instruction from the ncu captures'
+key metrics <tag>_metrics_<kernel>.json (gpurun_out/ or profiles/).  Usage: r2_table.py <bench.json> <tag> [--traffic-json out.json]"""
+import json, os, sys
 
 bench, tag = sys.argv[1], sys.argv[2]
 d = json.loads(open(bench).read().strip().splitlines()[-1])
@@ -9,33 +9,15 @@ peak = d["roofline"]["peak"]
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def ncu(kernel):
-    rep = os.path.join(root, "gpurun_out", f"{tag}_{kernel}.ncu-rep")
-    if not os.path.exists(rep):
-        return {}
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))
-    if len(rows) < 3:
-        return {}
-    h, u, v = rows[0], rows[1], rows[2]
-    m = {}
-    for a, b, c in zip(h, u, v):
-        m[a] = (b, c)
-    def val(k, scale=None):
-        if k not in m:
-            return None
-        unit, x = m[k]
-        try:
-            x = float(x.replace(",", ""))
-        except ValueError:
-            return None
-        if scale == "bytes":
-            x *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-        return x
-    return {"traffic": (val("dram__bytes_read.sum", "bytes") or 0) + (val("dram__bytes_write.sum", "bytes") or 0),
-            "issue": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-            "warps": val("sm__warps_active.avg.pct_of_peak_sustained_active"),
-            "lanes": val("smsp__thread_inst_executed_per_inst_executed.ratio"),
-            "inst": val("smsp__inst_executed.sum"), "regs": val("launch__registers_per_thread")}
+    """key metrics of the kernel's capture: gpurun_out/<tag>_metrics_<kernel>.json (tools/ncu_metrics.py)"""
+    for d_ in ("gpurun_out", "profiles"):
+        f = os.path.join(root, d_, f"{tag}_metrics_{kernel}.json")
+        if os.path.exists(f):
+            m = json.load(open(f))
+            return {"traffic": (m.get("dram_read") or 0) + (m.get("dram_write") or 0), "issue": m.get("issue_active_pct"),
+                    "warps": m.get("warps_active_pct"), "lanes": m.get("lanes_per_inst"), "inst": m.get("warp_inst"),
+                    "regs": m.get("regs")}
+    return {}
 
 traffic = {}
 print("| Kernel | ms / launch | share | algorithmic bytes | achieved GB/s | frac of %d | DRAM traffic (ncu) | warp-instr | issue-active | warps active | lanes / instr | regs |" % peak)

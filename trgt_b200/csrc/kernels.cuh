@@ -588,6 +588,10 @@ k_flank_band1(WfaSrc src, const uint2 *__restrict__ list1, const unsigned int *n
   __syncthreads();
   unsigned parity = 0;
   const uint32_t n = *n_list1_ptr;
+  // which scores can have a wavefront at all: a property of the scoring, the same for every pair
+  const int cap1 = wfa_imin(band_budget, wfa_imax(src.x, src.oe));
+  unsigned live_g = 0;
+  const unsigned live_m = cap1 <= FT1_SMAX ? ft1_live_scores(src.x, src.oe, src.e, cap1, &live_g) : 1u;
   // whole warps walk the list (a lane past its end keeps company): the wavefront loop runs warp-uniform
   for (uint32_t base = blockIdx.x * FB1_THREADS + (uint32_t)(tid & ~31); base < n; base += gridDim.x * FB1_THREADS) {
     const uint32_t i = base + (uint32_t)(tid & 31);
@@ -623,7 +627,7 @@ k_flank_band1(WfaSrc src, const uint2 *__restrict__ list1, const unsigned int *n
     FlankHit fh;
     fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
     const int deferred = flank_tier1_band_thread<32>(pr, klo, khi, band_budget, min_flank_id_frac, win, a0, hist, &fh,
-                                                     0xffffffffu, !have);
+                                                     0xffffffffu, !have, live_m, live_g);
     __syncwarp();
     if (have) {
       trgt_flank_hit_t h;

@@ -1600,16 +1600,15 @@ struct Ft1Hist {
 // cells of a score all parked extensions are finished in one loop, sixteen bytes a step, that the lanes leave
 // together.  (With a loop per cell every cell costs the warp its longest extension among 32 pairs.)
 // lanes: the lanes of the warp that call this together (0 = a lane on its own); idle: this lane has no pair
-// and only keeps company.  An all-null wavefront reads exactly like an absent one, so a score that only has
-// null predecessors may be computed (here: whenever the scoring allows a wavefront) or skipped alike.
+// and only keeps company.  live_m / live_g: ft1_live_scores of the scoring (the same for every pair of a launch,
+// so the caller computes them once).  An all-null wavefront reads exactly like an absent one, so a score that
+// only has null predecessors may be computed (here: whenever the scoring allows a wavefront) or skipped alike.
 template <int LS>
 TRGT_HD WfaEnd ft1_forward(const WfaProb &pr, int s_cap, const uint8_t *win, int a0, int16_t *hist, unsigned *present_out,
-                           unsigned lanes, bool idle) {
+                           unsigned lanes, bool idle, unsigned live_m, unsigned live_g) {
   WfaEnd out;
   out.status = TRGT_WFA_OK; out.s = 0; out.k = 0; out.off = 0;
   const int W = idle ? 0 : pr.bhi - pr.blo + 1;
-  unsigned live_g = 0u;
-  const unsigned live_m = ft1_live_scores(pr.x, pr.oe, pr.e, s_cap, &live_g);  // bit s: the scoring allows an M / a gap wavefront
   unsigned present = 0;
   bool done = idle;
 #define FT1_LD(s_, c_, i_) ft1_ld(hist[((ft1_row(live_m, (s_)) * 3 + (c_)) * FT1_WMAX + (i_)) * LS], pr.blo)
@@ -1702,15 +1701,16 @@ TRGT_HD WfaEnd ft1_forward(const WfaProb &pr, int s_cap, const uint8_t *win, int
 template <int LS>
 TRGT_HD int flank_tier1_band_thread(const WfaProb &pr, int klo, int khi, int S, double min_flank_id_frac,
                                     const uint8_t *win, int a0, int16_t *hist, FlankHit *hit, unsigned lanes = 0,
-                                    bool idle = false) {
+                                    bool idle = false, unsigned live_m = 0, unsigned live_g = 0) {
   const int cap = wfa_imin(S, wfa_imax(pr.x, pr.oe));
   const bool skip = idle || cap > FT1_SMAX || khi - klo + 1 > FT1_WMAX;
+  if (live_m == 0 && !skip) live_m = ft1_live_scores(pr.x, pr.oe, pr.e, cap, &live_g);  // (bit 0 is always set)
   WfaProb bp = pr;
   bp.blo = klo; bp.bhi = khi;
   unsigned present = 0;
-  const WfaEnd end = ft1_forward<LS>(bp, cap, win, a0, hist, &present, lanes, skip);
+  const WfaEnd end = ft1_forward<LS>(bp, cap, win, a0, hist, &present, lanes, skip, live_m, live_g);
   if (skip || end.status != TRGT_WFA_OK) return 1;
-  const Ft1Hist<LS> H{hist, klo, khi - klo + 1, present, ft1_live_scores(pr.x, pr.oe, pr.e, cap, nullptr)};
+  const Ft1Hist<LS> H{hist, klo, khi - klo + 1, present, live_m};
   WfaFlankSink sink(pr.T);
   wfa_backtrace_h(pr, end.s, end.k, end.off, H, sink);
   hit->matches = sink.matches;
