@@ -63,15 +63,29 @@ TRGT_HD void cons_decide(const ConsGroup &gr, const int *row, int p, const ConsR
   const int k = row[5];
   if (k > (int)(gr.n / 2)) {  // consensus.rs:57
     const int without = (int)gr.n - k;
+    // the column's own records first (one pass over the group's list, in list order), then the quadratic count among
+    // those few: a group of long alleles has hundreds of records and a handful per column
+    enum { MINE = 64 };
+    int mine[MINE];
+    int m = 0;
+    bool all = true;
+    for (int a = 0; a < n_rec; a++)
+      if ((int)recs[a].y == p) {
+        if (m < MINE) mine[m++] = a; else all = false;
+      }
     int best = -1, best_cnt = 0;
-    for (int a = 0; a < n_rec; a++) {
+    const int na = all ? m : n_rec;
+    for (int ia = 0; ia < na; ia++) {
+      const int a = all ? mine[ia] : ia;
       if ((int)recs[a].y != p) continue;
       const uint8_t *sa = gr.seqs + gr.seq_off[recs[a].seq] + recs[a].x;
       int cnt = 0;
-      for (int b = 0; b < n_rec; b++)
+      for (int ib = 0; ib < na; ib++) {
+        const int b = all ? mine[ib] : ib;
         if ((int)recs[b].y == p &&
             cons_cmp(sa, recs[a].len, gr.seqs + gr.seq_off[recs[b].seq] + recs[b].x, recs[b].len) == 0)
           cnt++;
+      }
       bool better = best < 0 || cnt > best_cnt;
       if (!better && cnt == best_cnt)
         better = cons_cmp(sa, recs[a].len, gr.seqs + gr.seq_off[recs[best].seq] + recs[best].x, recs[best].len) < 0;

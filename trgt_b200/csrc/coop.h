@@ -122,6 +122,26 @@ struct BlockGroup {
     return r;
   }
   TRGT_D int any(int p) const { return __syncthreads_or(p); }
+  // exclusive prefix sum over the CTA's threads (scan within each warp, then across the warps' totals)
+  TRGT_D int excl_scan_i(int v, int *total) const {
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, d);
+      if ((int)(threadIdx.x & 31u) >= d) x += y;
+    }
+    const unsigned w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if ((threadIdx.x & 31u) == 31u) scratch[w] = x;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (unsigned i = 0; i < nw; i++) {
+      if (i < w) base += scratch[i];
+      tot += scratch[i];
+    }
+    __syncthreads();
+    *total = tot;
+    return base + x - v;
+  }
   TRGT_D int bcast0(int v) const { return bcast(v, 0); }
   TRGT_D int bcast(int v, int src_lane) const {
     if ((int)threadIdx.x == src_lane) scratch[32] = v;

@@ -1599,9 +1599,12 @@ static int consensus_run_locked(trgt_engine_t *e, trgt_align_batch *b, trgt_seqs
   CU(e, engine_wait(e));
   const unsigned long long total_words = b->n_seqs ? e->h_u64[2] : 0;
   TRY(dev_reserve(e, b->cons_recs, (size_t)(total_words + ng + 1) * sizeof(ConsRec)));
-  const int block = 128, wpb = 4;
+  // long backbones: a CTA per group (the members' CIGAR walks and the columns over four warps); else a warp per group
+  const bool per_cta = b->Pmax > 2048;
+  const int block = 128, wpb = per_cta ? 1 : 4;
   int grid = 0;
-  TRY(persistent_grid(e, k_consensus_vote<false>, block, 0, &grid));
+  if (per_cta) TRY(persistent_grid(e, k_consensus_vote<false, true>, block, 0, &grid));
+  else TRY(persistent_grid(e, k_consensus_vote<false, false>, block, 0, &grid));
   const uint32_t need = (uint32_t)((ng + wpb - 1) / wpb);
   if ((uint32_t)grid > need) grid = (int)need;
   const size_t stride = (size_t)6 * (size_t)(b->Pmax > 0 ? b->Pmax : 1);
@@ -1619,10 +1622,16 @@ static int consensus_run_locked(trgt_engine_t *e, trgt_align_batch *b, trgt_seqs
   TRY(dev_reserve(e, b->cons_counts, (size_t)grid * wpb * stride * sizeof(int)));
   {
     LaunchScope ls(e, "k_consensus_vote_count");
-    k_consensus_vote<false><<<grid, block, 0, e->stream>>>(
-        src, (const uint32_t *)b->group_off.p, n_groups, (const uint32_t *)b->out_words.p,
-        (const unsigned long long *)b->out_off.p, (const int32_t *)b->status.p, (int *)b->cons_counts.p, stride,
-        (ConsRec *)b->cons_recs.p, (uint32_t *)b->cons_len.p, (int32_t *)b->cons_status.p, nullptr, nullptr);
+    if (per_cta)
+      k_consensus_vote<false, true><<<grid, block, 0, e->stream>>>(
+          src, (const uint32_t *)b->group_off.p, n_groups, (const uint32_t *)b->out_words.p,
+          (const unsigned long long *)b->out_off.p, (const int32_t *)b->status.p, (int *)b->cons_counts.p, stride,
+          (ConsRec *)b->cons_recs.p, (uint32_t *)b->cons_len.p, (int32_t *)b->cons_status.p, nullptr, nullptr);
+    else
+      k_consensus_vote<false, false><<<grid, block, 0, e->stream>>>(
+          src, (const uint32_t *)b->group_off.p, n_groups, (const uint32_t *)b->out_words.p,
+          (const unsigned long long *)b->out_off.p, (const int32_t *)b->status.p, (int *)b->cons_counts.p, stride,
+          (ConsRec *)b->cons_recs.p, (uint32_t *)b->cons_len.p, (int32_t *)b->cons_status.p, nullptr, nullptr);
     TRY(check_launch(e, "k_consensus_vote_count"));
   }
   CU(e, cudaMemsetAsync((uint32_t *)b->cons_len.p + ng, 0, sizeof(uint32_t), e->stream));
@@ -1635,11 +1644,18 @@ static int consensus_run_locked(trgt_engine_t *e, trgt_align_batch *b, trgt_seqs
   TRY(pin_reserve(e, b->h_cons_data, (size_t)total + 16));
   if (total) {
     LaunchScope ls(e, "k_consensus_vote_write");
-    k_consensus_vote<true><<<grid, block, 0, e->stream>>>(
-        src, (const uint32_t *)b->group_off.p, n_groups, (const uint32_t *)b->out_words.p,
-        (const unsigned long long *)b->out_off.p, (const int32_t *)b->status.p, (int *)b->cons_counts.p, stride,
-        (ConsRec *)b->cons_recs.p, (uint32_t *)b->cons_len.p, (int32_t *)b->cons_status.p,
-        (const unsigned long long *)b->cons_off.p, (uint8_t *)b->cons_data.p);
+    if (per_cta)
+      k_consensus_vote<true, true><<<grid, block, 0, e->stream>>>(
+          src, (const uint32_t *)b->group_off.p, n_groups, (const uint32_t *)b->out_words.p,
+          (const unsigned long long *)b->out_off.p, (const int32_t *)b->status.p, (int *)b->cons_counts.p, stride,
+          (ConsRec *)b->cons_recs.p, (uint32_t *)b->cons_len.p, (int32_t *)b->cons_status.p,
+          (const unsigned long long *)b->cons_off.p, (uint8_t *)b->cons_data.p);
+    else
+      k_consensus_vote<true, false><<<grid, block, 0, e->stream>>>(
+          src, (const uint32_t *)b->group_off.p, n_groups, (const uint32_t *)b->out_words.p,
+          (const unsigned long long *)b->out_off.p, (const int32_t *)b->status.p, (int *)b->cons_counts.p, stride,
+          (ConsRec *)b->cons_recs.p, (uint32_t *)b->cons_len.p, (int32_t *)b->cons_status.p,
+          (const unsigned long long *)b->cons_off.p, (uint8_t *)b->cons_data.p);
     TRY(check_launch(e, "k_consensus_vote_write"));
     CU(e, cudaMemcpyAsync(b->h_cons_data.p, b->cons_data.p, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
     CU(e, engine_wait(e));

@@ -1187,17 +1187,15 @@ __global__ void k_cigar_gather(WfaSrc src, uint32_t n_seqs, const WfaEnd *__rest
 // pass (lens[g] = consensus length, status[g]); WRITE = true: bytes at data + off[g].
 //   counts: per-warp slot of 6 * B_max ints; recs: one record slot per CIGAR word (indexed by the
 //   group's first word); align_status: per-sequence status of the alignment pass.
-template <bool WRITE>
-__global__ void __launch_bounds__(128)
-k_consensus_vote(WfaSrc src, const uint32_t *__restrict__ group_off, uint32_t n_groups,
-                 const uint32_t *__restrict__ words, const unsigned long long *__restrict__ word_off,
-                 const int32_t *__restrict__ align_status, int *counts, size_t counts_stride, ConsRec *recs,
-                 uint32_t *__restrict__ lens, int32_t *__restrict__ status, const unsigned long long *__restrict__ off,
-                 uint8_t *__restrict__ data) {
-  __shared__ int shared[4][2];
-  const WarpGroup g;
-  const uint32_t wib = threadIdx.x >> 5;
-  const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + wib, n_slots = gridDim.x * (blockDim.x >> 5);
+template <bool WRITE, class G>
+__device__ __forceinline__ void consensus_vote_groups(const G &g, uint32_t slot, uint32_t n_slots, int *sh, const WfaSrc &src,
+                                                      const uint32_t *__restrict__ group_off, uint32_t n_groups,
+                                                      const uint32_t *__restrict__ words,
+                                                      const unsigned long long *__restrict__ word_off,
+                                                      const int32_t *__restrict__ align_status, int *counts,
+                                                      size_t counts_stride, ConsRec *recs, uint32_t *__restrict__ lens,
+                                                      int32_t *__restrict__ status,
+                                                      const unsigned long long *__restrict__ off, uint8_t *__restrict__ data) {
   for (uint32_t gi = slot; gi < n_groups; gi += n_slots) {
     ConsGroup gr;
     gr.B = (int)(src.bb_off[gi + 1] - src.bb_off[gi]);
@@ -1205,21 +1203,46 @@ k_consensus_vote(WfaSrc src, const uint32_t *__restrict__ group_off, uint32_t n_
     gr.n = group_off[gi + 1] - gr.s0;
     gr.seqs = src.seqs; gr.seq_off = src.seq_off; gr.words = words; gr.word_off = word_off;
     int st = 0;
-    for (uint32_t m = (uint32_t)g.lane(); m < gr.n; m += 32)
+    for (uint32_t m = (uint32_t)g.lane(); m < gr.n; m += (uint32_t)g.size())
       if (align_status[gr.s0 + m] != 0) st = align_status[gr.s0 + m];
-    st = __reduce_min_sync(0xffffffffu, st);  // statuses are <= 0
+    st = g.min_i(st);  // statuses are <= 0
     if (WRITE && status[gi] != 0) continue;
     long long len = 0;
     if (st == 0) {
       const uint32_t rec_cap = (uint32_t)(word_off[gr.s0 + gr.n] - word_off[gr.s0]) + 1u;
-      len = consensus_vote(g, gr, counts + (size_t)slot * counts_stride, recs + word_off[gr.s0] + gi, rec_cap,
-                           shared[wib], WRITE ? data + off[gi] : nullptr);
+      len = consensus_vote(g, gr, counts + (size_t)slot * counts_stride, recs + word_off[gr.s0] + gi, rec_cap, sh,
+                           WRITE ? data + off[gi] : nullptr);
     }
     if (!WRITE && g.lane() == 0) {
       status[gi] = st != 0 ? st : (len == -1 ? TRGT_ITEM_INVALID_BASE : (len < 0 ? TRGT_ITEM_OOM : 0));
       lens[gi] = (st == 0 && len > 0) ? (uint32_t)len : 0u;
     }
-    __syncwarp();
+    g.sync();
+  }
+}
+
+// BLOCK = false: a warp per group (groups of a few dozen short repeat sequences: a genome-wide catalog);
+// BLOCK = true: a CTA per group (alleles of kilobases: the members' CIGAR walks and the columns spread over four
+// warps, and 2 048 groups fill the device instead of a fifth of it).
+template <bool WRITE, bool BLOCK>
+__global__ void __launch_bounds__(128)
+k_consensus_vote(WfaSrc src, const uint32_t *__restrict__ group_off, uint32_t n_groups,
+                 const uint32_t *__restrict__ words, const unsigned long long *__restrict__ word_off,
+                 const int32_t *__restrict__ align_status, int *counts, size_t counts_stride, ConsRec *recs,
+                 uint32_t *__restrict__ lens, int32_t *__restrict__ status, const unsigned long long *__restrict__ off,
+                 uint8_t *__restrict__ data) {
+  __shared__ int shared[4][2];
+  __shared__ int scratch[40];
+  if (BLOCK) {
+    const BlockGroup g(scratch);
+    consensus_vote_groups<WRITE>(g, blockIdx.x, gridDim.x, shared[0], src, group_off, n_groups, words, word_off,
+                                 align_status, counts, counts_stride, recs, lens, status, off, data);
+  } else {
+    const WarpGroup g;
+    const uint32_t wib = threadIdx.x >> 5;
+    consensus_vote_groups<WRITE>(g, blockIdx.x * (blockDim.x >> 5) + wib, gridDim.x * (blockDim.x >> 5), shared[wib], src,
+                                 group_off, n_groups, words, word_off, align_status, counts, counts_stride, recs, lens,
+                                 status, off, data);
   }
 }
 
