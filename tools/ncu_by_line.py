@@ -19,7 +19,7 @@ for l in dis[start:end]:
     if m:
         cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
-    if re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
+    if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
         line_of[idx] = cur
         idx += 1
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass", "--csv"], capture_output=True, text=True).stdout
