@@ -293,7 +293,7 @@ int emu_flank_tier1_split(const uint8_t *p_in, int P, const uint8_t *t_in, int T
   if (P > FT1_PMAX || flank_tier1_seed_thread(idx, pr, S, &klo, &khi) != 1) return 0;
   const int first = klo > 0 ? klo : 0;
   const int a0 = first - slack;  // may be negative: bytes before the text are never read
-  uint8_t win[FT1_WIN_BYTES];
+  uint8_t win[FT1_WIN_STRIDE];
   memset(win, 0xEE, sizeof win);
   for (int i = 0; i < FT1_WIN_BYTES; i++) {
     const int h = a0 + i;

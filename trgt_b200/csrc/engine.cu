@@ -395,6 +395,10 @@ int32_t trgt_engine_create(int32_t device, trgt_engine_t **out) {
     return TRGT_ERR_CUDA;
   }
   {
+    const char *lane = getenv("TRGT_HMM_LANE");  // "0": single-motif loci take the generic HMM kernels too (measurements)
+    if (lane && lane[0] == '0') e->hmm_lane = false;
+  }
+  {
     const char *mode = getenv("TRGT_SYNC");
     if (mode && strcmp(mode, "sleep") == 0 &&
         (err = cudaEventCreateWithFlags(&e->sleep_ev, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) {

@@ -565,7 +565,7 @@ k_flank_seed(WfaSrc src, const uint32_t *__restrict__ locus_read_off, uint32_t l
 // scoring, ft1_live_scores): per lane a text window filled by its own bulk copy, its copy-complete barrier, and
 // rows * 3 * FT1_WMAX 16-bit history cells (the lanes of a warp interleaved)
 __host__ __device__ inline size_t fb1_smem_bytes(int rows) {
-  return (size_t)FB1_THREADS * (FT1_WIN_BYTES + 8) + (size_t)FB1_THREADS * rows * 3 * FT1_WMAX * sizeof(int16_t);
+  return (size_t)FB1_THREADS * (FT1_WIN_STRIDE + 8) + (size_t)FB1_THREADS * rows * 3 * FT1_WMAX * sizeof(int16_t);
 }
 
 // Phase A, step 2b (band pass of the first cost tier, see flank_tier1_band_thread).  ONE LANE PER LISTED PAIR, dense
@@ -579,9 +579,9 @@ k_flank_band1(WfaSrc src, const uint2 *__restrict__ list1, const unsigned int *n
               uint32_t *__restrict__ work2, Counters *ctr) {
   extern __shared__ __align__(16) unsigned char fb1_raw[];
   const int tid = threadIdx.x;
-  uint8_t *win = fb1_raw + (size_t)tid * FT1_WIN_BYTES;
-  unsigned long long *bar = reinterpret_cast<unsigned long long *>(fb1_raw + (size_t)FB1_THREADS * FT1_WIN_BYTES) + tid;
-  int16_t *hist = reinterpret_cast<int16_t *>(fb1_raw + (size_t)FB1_THREADS * (FT1_WIN_BYTES + 8)) +
+  uint8_t *win = fb1_raw + (size_t)tid * FT1_WIN_STRIDE;
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(fb1_raw + (size_t)FB1_THREADS * FT1_WIN_STRIDE) + tid;
+  int16_t *hist = reinterpret_cast<int16_t *>(fb1_raw + (size_t)FB1_THREADS * (FT1_WIN_STRIDE + 8)) +
                   (size_t)(tid >> 5) * rows * 3 * FT1_WMAX * 32 + (tid & 31);
   mbar_init(bar, 1);
   mbar_init_fence();

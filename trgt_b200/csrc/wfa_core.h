@@ -1548,6 +1548,7 @@ TRGT_HD int flank_tier1_seed_thread(const KmerIndex &idx, const WfaProb &pr, int
 }
 
 #define FT1_WIN_BYTES 288  // text window of a pair: <= 256 of piece + 3 of band + 15 of alignment + 12 of over-read, in 16-byte chunks
+#define FT1_WIN_STRIDE 304  // bytes between the windows of two lanes: an 8-byte read of the window's last bytes touches the 12 after them
 #define FT1_PMAX 256       // longest piece the band pass takes
 #define FT1_HIST_HALFS ((FT1_SMAX + 1) * 3 * FT1_WMAX)  // 16-bit cells of one pair's history (216 bytes)
 
