@@ -273,6 +273,10 @@ def test_flank_spans_synthetic_hifi(engine, oracle, band_budget):
     n_wfa = _check_flanks(oracle, w, spans, hits, w.scoring, w.min_flank_id_frac)
     assert n_wfa > 20  # the WFA fallback was exercised
     assert "k_flank_exact_t" in stats
+    if band_budget > 0:   # the first cost tier ran in its two passes (seed pass, band pass on bulk-copied windows)
+        assert stats["k_flank_seed"][0] >= 1 and stats["k_flank_band1"][0] >= 1 and "k_flank_band2" in stats
+    else:
+        assert "k_flank_seed" not in stats and "k_wfa_score_block" in stats
 
 
 def test_flank_spans_long_reads_and_repetitive_flanks(engine, oracle):
