@@ -54,6 +54,8 @@ def parse_args():
                     help="host threads (one engine each) of the e2e driver (0: host cores / ranks, between 2 and 8)")
     ap.add_argument("--upload-slots", type=int, default=2,
                     help="chunks that may be inside their phase-A call (the PCIe-heavy one) at a time; 0 = no limit")
+    ap.add_argument("--guided", type=int, default=0, help="1: chunks shrink towards the end of the shard and go to whichever host thread is free")
+    ap.add_argument("--min-chunk-loci", type=int, default=1500)
     ap.add_argument("--uploaders", type=int, default=0,
                     help="host threads that only upload phase A's inputs (resident-batch API), the others process; 0 = every "
                          "thread runs whole chunks through the one-shot calls")
@@ -358,7 +360,8 @@ def run_b200(args):
     # host cores are shared by all ranks of the box and all host threads of a rank
     glue_threads = max(1, host_cores() // max(1, world * len(engines)))
     chp = ChunkedHotPath(engines, w, chunk_loci=args.chunk_loci, glue_threads=glue_threads, use_seq4=use_seq4,
-                         upload_slots=args.upload_slots, uploaders=args.uploaders, max_inflight=args.max_inflight)
+                         upload_slots=args.upload_slots, uploaders=args.uploaders, max_inflight=args.max_inflight,
+                         guided=bool(args.guided), min_chunk_loci=args.min_chunk_loci)
 
     # ---- warm-up: end-to-end passes (also builds the resident batches) ----
     res = None
@@ -649,7 +652,7 @@ def run_b200(args):
         "gpu_launches_per_step": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),
-                "upload_slots": args.upload_slots, "uploaders": args.uploaders,
+                "upload_slots": args.upload_slots, "uploaders": args.uploaders, "guided": args.guided, "chunks": len(chp.paths),
                 "reads_in": "BAM 4-bit bases (trgt_flank_spans_seq4), decoded on the device" if use_seq4 else "ASCII (trgt_flank_spans)",
                 "glue_threads": glue_threads, "phase_ms_summed_over_host_threads": e2e_phases},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "clip_row": clip, "vcf_row": vcf,

@@ -185,7 +185,8 @@ class ChunkedHotPath:
     overlap another chunk's kernels and host glue."""
 
     def __init__(self, engines, w: Workload, chunk_loci: int = 16384, glue_threads: int = 0, use_seq4: bool = False,
-                 upload_slots: int = 2, uploaders: int = 0, max_inflight: int = 4):
+                 upload_slots: int = 2, uploaders: int = 0, max_inflight: int = 4, guided: bool = False,
+                 min_chunk_loci: int = 1500):
         """upload_slots: how many chunks may be inside their phase-A call (the one that moves the reads over PCIe)
         at a time; 0 = no limit and chunk i statically on thread i mod threads.  Without a limit all threads
         upload together, then all compute together while the link idles (measured: 52 ms per 125 k-locus shard at
@@ -200,7 +201,22 @@ class ChunkedHotPath:
         self.max_inflight = max_inflight
         self.upload_s = 0.0
         self.w = w
-        self.bounds = [(l0, min(l0 + chunk_loci, w.n_loci)) for l0 in range(0, w.n_loci, chunk_loci)]
+        self.guided = guided
+        if guided:
+            # guided self-scheduling: chunks of chunk_loci while plenty is left, then ever smaller ones (what is left /
+            # threads, at least min_chunk_loci), handed to whichever thread is free.  Phase A saturates the link for as
+            # long as there are reads to send; what is left after the last upload -- glue, phases B and C of the chunks
+            # still in flight -- is proportional to the size of the last chunks (measured: 51.6 ms with 16 equal chunks,
+            # 40.1 ms for their phase A alone).
+            self.bounds = []
+            l0 = 0
+            while l0 < w.n_loci:
+                left = w.n_loci - l0
+                size = max(min_chunk_loci, min(chunk_loci, -(-left // max(1, len(self.engines)))))
+                self.bounds.append((l0, min(l0 + size, w.n_loci)))
+                l0 += size
+        else:
+            self.bounds = [(l0, min(l0 + chunk_loci, w.n_loci)) for l0 in range(0, w.n_loci, chunk_loci)]
         # every chunk's arrays (the rebased offsets are fresh copies) in pinned memory, as a host that packs into
         # trgt_host_alloc buffers has them
         self.paths = [HotPath(self.engines[i % len(self.engines)],
@@ -288,10 +304,18 @@ class ChunkedHotPath:
 
         def work(k):
             try:
-                if gate is None:
+                if gate is None and not self.guided:
                     for i in range(k, len(self.paths), n_eng):
                         results[i] = self.paths[i].run_e2e(copy=True)
                     return
+                if gate is None:   # chunks in order to whichever thread is free
+                    while True:
+                        with take:
+                            i = nxt[0]
+                            nxt[0] += 1
+                        if i >= len(self.paths):
+                            return
+                        results[i] = self.paths[i].run_e2e(copy=True, eng=self.engines[k])
                 while True:
                     gate.acquire()          # a slot on the link first, then the next chunk: chunks go up in order
                     with take:
