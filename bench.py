@@ -573,6 +573,43 @@ def run_b200(args):
             a14 = {"error": repr(exc)}
 
     # ---- next row: VCF sample fields encoded behind phase C, timed on its own ----
+    # ---- next row (BAMlet): clip_bases for every read of the resident phase-A batch, timed on its own ----
+    bamlet = None
+    if world == 1 and getattr(hp, "_fb", None):
+        try:
+            rl = np.diff(w.reads.offsets.astype(np.int64)).astype(np.uint32)
+            # CIGAR of every clipped read: 10 soft-clipped bases, the rest one '=' run (query length = read length)
+            ops = np.empty(2 * w.n_reads, dtype=np.uint32)
+            ops[0::2] = (10 << 4) | 4
+            ops[1::2] = ((rl - 10) << 4) | 7
+            ooff = np.arange(0, 2 * w.n_reads + 1, 2, dtype=np.uint64)
+            refs = np.arange(w.n_reads, dtype=np.int64) * 1000
+            eng.bamlet_clip(hp._fb, ops, ooff, refs, 250)  # warm-up
+            t0 = time.perf_counter()
+            bc = eng.bamlet_clip(hp._fb, ops, ooff, refs, 250)
+            dt = time.perf_counter() - t0
+            bamlet = {"call": "trgt_bamlet_clip (clip_bases of clip_bases.rs:9-119 as write_bam.rs:72-92 asks for it; reads and "
+                              "spans resident, CIGARs in and clips out over PCIe)", "reads": int(w.n_reads), "ms": dt * 1e3,
+                      "reads_per_s": w.n_reads / dt, "records": int((bc["status"] == 1).sum())}
+            if not args.no_cpu_baseline:
+                from oracle import oracle as orc
+                spans_r, _ = eng.flank_download(hp._fb, w.n_reads, want_hits=False)
+                nchk, same = min(w.n_reads, 2000), 0
+                for r in range(nchk):
+                    sp = (int(spans_r[r]["start"]), int(spans_r[r]["end"])) if spans_r[r]["found"] else None
+                    exp = orc.bamlet_clip(w.reads.get(r), [int(ops[2 * r]), int(ops[2 * r + 1])], int(refs[r]), sp, 250) if sp else None
+                    c = bc[r]
+                    if exp is None:
+                        same += int(c["status"]) == 0
+                    else:
+                        b0, b1, m0, m1, (rp, words) = exp
+                        got_words = [int(c["first_word"])] if c["n_ops"] == 1 else [int(c["first_word"]), int(c["last_word"])]
+                        same += (int(c["status"]) == 1 and (int(c["base_start"]), int(c["base_end"]), int(c["meth_start"]),
+                                 int(c["meth_end"]), int(c["ref_pos"])) == (b0, b1, m0, m1, rp) and got_words == list(words))
+                bamlet["parity"] = f"{same}/{nchk} reads identical to the oracle"
+        except Exception as exc:  # never let the extra row break the headline line
+            bamlet = {"error": repr(exc)}
+
     vcf = None
     if world == 1:
         try:
@@ -656,7 +693,7 @@ def run_b200(args):
                 "reads_in": "BAM 4-bit bases (trgt_flank_spans_seq4), decoded on the device" if use_seq4 else "ASCII (trgt_flank_spans)",
                 "glue_threads": glue_threads, "phase_ms_summed_over_host_threads": e2e_phases},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "clip_row": clip, "vcf_row": vcf,
-        "a14_row": a14, "kernels": kernels,
+        "a14_row": a14, "bamlet_row": bamlet, "kernels": kernels,
         "wfa_fallback_pairs": hp.n_wfa(), "flank_fallback_counts": dict(zip(("second_tier", "wide_band", "full_width"), hp.fallback_counts())),
         "workload_gen_s": t_gen,
     }
