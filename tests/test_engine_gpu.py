@@ -312,6 +312,32 @@ def test_flank_spans_noisy_targeted_scoring(engine, oracle):
     assert 2 in vias and 3 in vias
 
 
+@pytest.mark.parametrize("scoring", [(3, 3, 1), (4, 6, 2), (1, 0, 1), (2, 1, 1), (6, 5, 1)])
+def test_flank_spans_custom_scorings_with_decoys(engine, oracle, scoring):
+    """--aln-scoring other than the presets through every tier (a cheap gap open moves the seed filter's block count,
+    flank_seed_blocks; the first tier's cost cap and live scores follow the scoring), HiFi-like noise so that most
+    misses are one edit, plus reads that carry a second, damaged copy of a flank piece (an index hit off the
+    alignment: the first tier's hull has to be verified or handed on)."""
+    from harness import workload
+    from trgt_b200 import PackedSeqs
+    w = workload.generate(30, 10, seed=11 + scoring[0], sub_rate=1e-3, ins_rate=1e-3, del_rate=1e-3)
+    rng = random.Random(scoring[1])
+    reads = []
+    for r in range(w.n_reads):
+        read = w.reads.get(r)
+        if r % 7 == 3:    # a decoy: 60 bases of the left piece, one of them changed, ahead of the read
+            l = int(np.searchsorted(w.locus_read_off, r, side="right") - 1)
+            bit = bytearray(w.left.get(l)[40:100])
+            bit[30] = ord("A") if bit[30] != ord("A") else ord("C")
+            read = bytes(bit) + rnd(rng, 40) + read
+        reads.append(read)
+    packed = PackedSeqs.from_list(reads)
+    w.reads = packed
+    spans, hits = engine.flank_spans_packed(w.left, w.right, packed, w.locus_read_off, scoring, 0.7)
+    n_wfa = _check_flanks(oracle, w, spans, hits, scoring, 0.7)
+    assert n_wfa > 10
+
+
 def test_flank_spans_edge_cases(engine, oracle):
     rng = random.Random(21)
     lf = rnd(rng, 300)
