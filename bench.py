@@ -54,6 +54,8 @@ def parse_args():
                     help="host threads (one engine each) of the e2e driver (0: host cores / ranks, between 2 and 8)")
     ap.add_argument("--upload-slots", type=int, default=2,
                     help="chunks that may be inside their phase-A call (the PCIe-heavy one) at a time; 0 = no limit")
+    ap.add_argument("--align-by-index", type=int, default=0,
+                    help="1: end to end, phase B names backbones and members by read index (trgt_align_trs) instead of uploading their bases")
     ap.add_argument("--guided", type=int, default=0, help="1: chunks shrink towards the end of the shard and go to whichever host thread is free")
     ap.add_argument("--min-chunk-loci", type=int, default=1500)
     ap.add_argument("--uploaders", type=int, default=0,
@@ -361,7 +363,8 @@ def run_b200(args):
     glue_threads = max(1, host_cores() // max(1, world * len(engines)))
     chp = ChunkedHotPath(engines, w, chunk_loci=args.chunk_loci, glue_threads=glue_threads, use_seq4=use_seq4,
                          upload_slots=args.upload_slots, uploaders=args.uploaders, max_inflight=args.max_inflight,
-                         guided=bool(args.guided), min_chunk_loci=args.min_chunk_loci)
+                         guided=bool(args.guided), min_chunk_loci=args.min_chunk_loci,
+                         align_by_index=bool(args.align_by_index))
 
     # ---- warm-up: end-to-end passes (also builds the resident batches) ----
     res = None
@@ -689,7 +692,7 @@ def run_b200(args):
         "gpu_launches_per_step": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "chunk_loci": args.chunk_loci, "host_threads": len(engines),
-                "upload_slots": args.upload_slots, "uploaders": args.uploaders, "guided": args.guided, "chunks": len(chp.paths),
+                "upload_slots": args.upload_slots, "uploaders": args.uploaders, "guided": args.guided, "chunks": len(chp.paths), "align_by_index": args.align_by_index,
                 "reads_in": "BAM 4-bit bases (trgt_flank_spans_seq4), decoded on the device" if use_seq4 else "ASCII (trgt_flank_spans)",
                 "glue_threads": glue_threads, "phase_ms_summed_over_host_threads": e2e_phases},
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "consensus_row": consensus, "clip_row": clip, "vcf_row": vcf,

@@ -30,9 +30,12 @@ class HotPathResult:
 
 class HotPath:
     def __init__(self, engine: Engine, w: Workload, want_hits: bool = False, pinned_outputs: bool = True,
-                 glue_threads: int = 0, use_seq4: bool = False):
+                 glue_threads: int = 0, use_seq4: bool = False, align_by_index: bool = False):
         self.eng = engine
         self.w = w
+        # end to end, phase B names backbones and members by read index (trgt_align_trs: the device gathers the repeat
+        # sequences it cut itself) instead of sending their bases up again; same CIGARs
+        self.align_by_index = align_by_index
         # end-to-end input of phase A: the reads as BAM 4-bit bases (w.reads4) instead of ASCII
         self.use_seq4 = bool(use_seq4 and w.reads4 is not None)
         self.want_hits = want_hits
@@ -58,8 +61,13 @@ class HotPath:
             n += w.reads4.data.nbytes + w.reads4.starts.nbytes + w.reads4.lengths.nbytes
         else:
             n += w.reads.data.nbytes + w.reads.offsets.nbytes
-        for s in (w.left, w.right, glue.backbones, glue.seqs, w.motifs):
+        for s in (w.left, w.right, w.motifs):
             n += s.data.nbytes + s.offsets.nbytes
+        if self.align_by_index and self.use_seq4:   # only the read indices: lengths, offsets and bytes are produced on the device
+            n += 4 * (len(glue.backbones) + len(glue.seqs))
+        else:
+            for s in (glue.backbones, glue.seqs):
+                n += s.data.nbytes + s.offsets.nbytes
         n += glue.backbones.data.nbytes + glue.backbones.offsets.nbytes  # alleles = backbones, sent again for phase C
         n += w.locus_read_off.nbytes + glue.group_seq_off.nbytes + w.locus_motif_off.nbytes + glue.group_locus.nbytes
         n += 2 * 8 * (len(glue.backbones) + 1)  # bp / mc offsets of the HMM batch
@@ -98,7 +106,10 @@ class HotPath:
         t1 = time.perf_counter()
         glue = genotype_glue(w, spans, threads=self.glue_threads, ctx=self._glue_ctx, trs=trs)
         t2 = time.perf_counter()
-        cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off, copy=copy)
+        if self.align_by_index and self.use_seq4:
+            cigars = eng.align_trs(None, glue.seq_read[glue.group_seq_off[:-1]], glue.seq_read, glue.group_seq_off, copy=copy)
+        else:
+            cigars = eng.align_packed(glue.backbones, glue.seqs, glue.group_seq_off, copy=copy)
         t3 = time.perf_counter()
         ann = eng.hmm_label_packed(w.motifs, w.locus_motif_off, glue.backbones, glue.group_locus, copy=copy)
         t4 = time.perf_counter()
@@ -186,7 +197,7 @@ class ChunkedHotPath:
 
     def __init__(self, engines, w: Workload, chunk_loci: int = 16384, glue_threads: int = 0, use_seq4: bool = False,
                  upload_slots: int = 2, uploaders: int = 0, max_inflight: int = 4, guided: bool = False,
-                 min_chunk_loci: int = 1500):
+                 min_chunk_loci: int = 1500, align_by_index: bool = False):
         """upload_slots: how many chunks may be inside their phase-A call (the one that moves the reads over PCIe)
         at a time; 0 = no limit and chunk i statically on thread i mod threads.  Without a limit all threads
         upload together, then all compute together while the link idles (measured: 52 ms per 125 k-locus shard at
@@ -221,7 +232,7 @@ class ChunkedHotPath:
         # trgt_host_alloc buffers has them
         self.paths = [HotPath(self.engines[i % len(self.engines)],
                               w.slice(l0, l1).pinned(self.engines[i % len(self.engines)].pinned_array),
-                              glue_threads=glue_threads, use_seq4=use_seq4)
+                              glue_threads=glue_threads, use_seq4=use_seq4, align_by_index=align_by_index)
                       for i, (l0, l1) in enumerate(self.bounds)]
 
     def timing(self) -> dict:

@@ -288,6 +288,14 @@ int32_t trgt_consensus_trs(trgt_engine_t *eng, trgt_flank_batch_t *batch, const 
                            const uint32_t *member_reads, const uint32_t *group_offsets, uint32_t n_groups,
                            trgt_seqs_out_t *out);
 
+/* trgt_align_e2e with backbones and members named by read index of a flank batch (the repeat sequences are gathered
+ * on the device from the batch's reads and spans): utils::align (src/utils/align.rs:14-28) for hosts that took their
+ * repeat sequences from trgt_flank_trs -- 4 bytes per member go up instead of its bases and a 64-bit offset.
+ * batch == NULL: the batch of the last one-shot trgt_flank_spans* call.  `out` as for trgt_align_e2e. */
+int32_t trgt_align_trs(trgt_engine_t *eng, trgt_flank_batch_t *batch, const uint32_t *backbone_reads,
+                       const uint32_t *member_reads, const uint32_t *group_offsets, uint32_t n_groups,
+                       trgt_cigars_t *out);
+
 /* ---- phase C: motif HMM (a7-a13) ---------------------------------------- */
 
 typedef struct {

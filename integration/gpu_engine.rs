@@ -163,6 +163,8 @@ extern "C" {
         group_out: *mut i32, central_out: *mut u32, n_groups_out: *mut u32) -> i32;
     pub fn trgt_cluster_trs(eng: *mut TrgtEngine, batch: *mut TrgtFlankBatch, reads: *const u32, locus_offsets: *const u32,
         n_loci: u32, group_out: *mut i32, central_out: *mut u32, n_groups_out: *mut u32) -> i32;
+    pub fn trgt_align_trs(eng: *mut TrgtEngine, batch: *mut TrgtFlankBatch, backbone_reads: *const u32,
+        member_reads: *const u32, group_offsets: *const u32, n_groups: u32, out: *mut TrgtCigars) -> i32;
     pub fn trgt_consensus_trs(eng: *mut TrgtEngine, batch: *mut TrgtFlankBatch, backbone_reads: *const u32,
         member_reads: *const u32, group_offsets: *const u32, n_groups: u32, out: *mut TrgtSeqsOut) -> i32;
 

@@ -721,6 +721,21 @@ def test_flank_spans_seq4_matches_ascii_path(engine, oracle):
     assert sp0.size == 0
 
 
+def test_align_trs_matches_align_packed(engine, oracle):
+    """trgt_align_trs (backbones and members named by read index, gathered on the device from the flank batch) gives the
+    CIGARs of trgt_align_e2e on the same sequences, and the whole pass through it matches the oracle"""
+    from harness import workload
+    from harness.pipeline import HotPath, compare_with_oracle, oracle_pass
+    w = workload.generate(80, 14, seed=123)
+    w.pack_seq4()
+    hp = HotPath(engine, w, want_hits=False, pinned_outputs=False, use_seq4=True, align_by_index=True)
+    res = hp.run_e2e(copy=True)
+    compare_with_oracle(res, oracle_pass(oracle, w, 4))
+    ref = engine.align_packed(res.glue.backbones, res.glue.seqs, res.glue.group_seq_off)
+    assert np.array_equal(ref.words, res.cigars.words) and np.array_equal(ref.offsets, res.cigars.offsets)
+    assert "k_trs_gather" in engine.kernel_stats()
+
+
 def test_flank_trs_are_the_span_slices(engine, oracle):
     """trgt_flank_trs = read.bases[span.0..span.1] per spanning read (tr.rs:58-62), for one-shot (ASCII and
     BAM 4-bit input) and resident batches; and the host glue fed with them builds the same phase B/C input."""

@@ -1796,63 +1796,92 @@ int32_t trgt_cluster_trs(trgt_engine_t *e, trgt_flank_batch_t *b, const uint32_t
   return cluster_device(e, n_loci, n_sel, n_max, group_out, central_out, n_groups_out);
 }
 
-int32_t trgt_consensus_trs(trgt_engine_t *e, trgt_flank_batch_t *fb, const uint32_t *backbone_reads,
-                           const uint32_t *member_reads, const uint32_t *group_offsets, uint32_t n_groups,
-                           trgt_seqs_out_t *out) {
-  if (!e || !out) return TRGT_ERR_ARG;
-  std::lock_guard<std::mutex> lk(e->mu);
+// Backbones and members named by read index of a flank batch -> the engine's one-shot align batch, sequences gathered
+// on the device from the batch's reads and spans (index, lengths, scan, bytes) and everything else prepared.
+static int align_gather_trs(trgt_engine_t *e, trgt_flank_batch_t *fb, const uint32_t *backbone_reads,
+                            const uint32_t *member_reads, const uint32_t *group_offsets, uint32_t n_groups,
+                            const char *what, trgt_align_batch **b_out) {
   if (!fb) fb = e->one_flank;
-  if (!fb || (fb->n_reads && !fb->ran)) return fail(e, TRGT_ERR_ARG, "trgt_consensus_trs: the flank batch has not been run");
-  if (n_groups && (!group_offsets || !backbone_reads)) return fail(e, TRGT_ERR_ARG, "trgt_consensus_trs: null argument");
+  if (!fb || (fb->n_reads && !fb->ran)) return fail(e, TRGT_ERR_ARG, "%s: the flank batch has not been run", what);
+  if (n_groups && (!group_offsets || !backbone_reads)) return fail(e, TRGT_ERR_ARG, "%s: null argument", what);
   const uint32_t n_seqs = n_groups ? group_offsets[n_groups] : 0;
   if (n_groups && group_offsets[0] != 0) return fail(e, TRGT_ERR_ARG, "group_offsets must start at 0");
   for (uint32_t g = 0; g < n_groups; g++)
     if (group_offsets[g + 1] < group_offsets[g]) return fail(e, TRGT_ERR_ARG, "group_offsets not monotone");
-  TRY(check_read_index(e, fb, backbone_reads, n_groups, "trgt_consensus_trs"));
-  TRY(check_read_index(e, fb, member_reads, n_seqs, "trgt_consensus_trs"));
+  TRY(check_read_index(e, fb, backbone_reads, n_groups, what));
+  TRY(check_read_index(e, fb, member_reads, n_seqs, what));
   CU(e, cudaSetDevice(e->device));
   if (!e->one_align) e->one_align = new trgt_align_batch();
   trgt_align_batch *b = e->one_align;
-  // Backbones and members are gathered on the device from the reads of the flank batch: index, lengths, scan, bytes.
-  // The two longest sequences size the wavefront rings: read back from the scans' inputs.
-  struct Part { const uint32_t *idx; uint32_t n; DevBuf *data, *off; int *mx; } parts[2] = {
-      {backbone_reads, n_groups, &b->bb, &b->bb_off, &b->Pmax}, {member_reads, n_seqs, &b->seqs, &b->seq_off, &b->Tmax}};
-  std::vector<trgt_span_t> h_spans(fb->n_reads ? fb->n_reads : 1);
-  if (fb->n_reads)
-    CU(e, cudaMemcpyAsync(h_spans.data(), fb->spans.p, (size_t)fb->n_reads * sizeof(trgt_span_t), cudaMemcpyDeviceToHost, e->stream));
-  CU(e, engine_wait(e));
-  int pm = 0, tm = 0;
+  // Lengths, offsets (a scan) and bytes of both sets are produced on the device from the batch's spans; only the two
+  // index lists go up, and the two totals and the two longest lengths (they size buffers and wavefront rings) come back.
+  struct Part { const uint32_t *idx; uint32_t n; DevBuf *data, *off, *d_idx, *d_len; } parts[2] = {
+      {backbone_reads, n_groups, &b->bb, &b->bb_off, &e->d_cl[4], &e->d_ed[1]},
+      {member_reads, n_seqs, &b->seqs, &b->seq_off, &e->d_ed[0], &e->d_ed[2]}};
+  unsigned long long *h = e->h_u64;  // pinned: [0..1] totals, [2..3] longest lengths (as 32-bit words)
+  TRY(dev_reserve(e, e->d_ed[3], 4 * sizeof(unsigned int)));
+  CU(e, cudaMemsetAsync(e->d_ed[3].p, 0, 4 * sizeof(unsigned int), e->stream));
+  static const uint32_t zero32[1] = {0};
   for (int k = 0; k < 2; k++) {
     Part &p = parts[k];
-    std::vector<unsigned long long> off((size_t)p.n + 1, 0);
-    uint32_t mx = 0;
-    for (uint32_t i = 0; i < p.n; i++) {
-      const trgt_span_t sp = h_spans[p.idx[i]];
-      const uint32_t len = sp.found ? sp.end - sp.start : 0u;
-      off[i + 1] = off[i] + len;
-      if (len > mx) mx = len;
+    TRY(h2d(e, *p.d_idx, p.n ? p.idx : zero32, (size_t)(p.n ? p.n : 1) * sizeof(uint32_t)));
+    TRY(dev_reserve(e, *p.d_len, ((size_t)p.n + 1) * sizeof(uint32_t)));
+    TRY(dev_reserve(e, *p.off, ((size_t)p.n + 1) * sizeof(unsigned long long) + 16));
+    {
+      LaunchScope ls(e, "k_trs_len");
+      k_trs_len<<<(p.n + 256) / 256, 256, 0, e->stream>>>((const trgt_span_t *)fb->spans.p, (const uint32_t *)p.d_idx->p, p.n,
+                                                         (uint32_t *)p.d_len->p, (unsigned int *)e->d_ed[3].p + k);
+      TRY(check_launch(e, "k_trs_len"));
     }
-    (k == 0 ? pm : tm) = (int)mx;
-    static const uint32_t zero32[1] = {0};
-    TRY(h2d(e, e->d_cl[4], p.n ? p.idx : zero32, (size_t)(p.n ? p.n : 1) * sizeof(uint32_t)));
-    TRY(h2d(e, *p.off, off.data(), off.size() * sizeof(unsigned long long)));
-    TRY(dev_reserve(e, *p.data, (size_t)off[p.n] + 16));
-    if (off[p.n]) {
+    TRY(exclusive_scan_u32(e, (const uint32_t *)p.d_len->p, (unsigned long long *)p.off->p, (size_t)p.n + 1));
+    CU(e, cudaMemcpyAsync(&h[k], (const unsigned long long *)p.off->p + p.n, sizeof(unsigned long long),
+                          cudaMemcpyDeviceToHost, e->stream));
+  }
+  CU(e, cudaMemcpyAsync(&h[2], e->d_ed[3].p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
+  CU(e, engine_wait(e));
+  const unsigned int *h_max = (const unsigned int *)&h[2];
+  const int pm = (int)h_max[0], tm = (int)h_max[1];
+  for (int k = 0; k < 2; k++) {
+    Part &p = parts[k];
+    const unsigned long long total = h[k];
+    TRY(dev_reserve(e, *p.data, (size_t)total + 16));
+    if (total) {
       int grid = 0;
       TRY(persistent_grid(e, k_trs_gather, 256, 0, &grid));
       const uint32_t need = (p.n + 7) / 8;
       if ((uint32_t)grid > need) grid = (int)need;
       LaunchScope ls(e, "k_trs_gather");
       k_trs_gather<<<grid, 256, 0, e->stream>>>((const uint8_t *)fb->reads.p, (const uint64_t *)fb->read_off.p,
-                                                (const trgt_span_t *)fb->spans.p, (const uint32_t *)e->d_cl[4].p,
+                                                (const trgt_span_t *)fb->spans.p, (const uint32_t *)p.d_idx->p,
                                                 (const unsigned long long *)p.off->p, p.n, (uint8_t *)p.data->p);
       TRY(check_launch(e, "k_trs_gather"));
     }
-    CU(e, engine_wait(e));  // `off` and the index buffer are reused by the next part
   }
   if ((uint64_t)pm + (uint64_t)tm > 0x0fffffffull) return fail(e, TRGT_ERR_ARG, "sequence too long");
   TRY(align_prepare(e, b, group_offsets, n_groups, n_seqs, pm, tm));
+  *b_out = b;
+  return 0;
+}
+
+int32_t trgt_consensus_trs(trgt_engine_t *e, trgt_flank_batch_t *fb, const uint32_t *backbone_reads,
+                           const uint32_t *member_reads, const uint32_t *group_offsets, uint32_t n_groups,
+                           trgt_seqs_out_t *out) {
+  if (!e || !out) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  trgt_align_batch *b = nullptr;
+  TRY(align_gather_trs(e, fb, backbone_reads, member_reads, group_offsets, n_groups, "trgt_consensus_trs", &b));
   return consensus_run_locked(e, b, out);
+}
+
+int32_t trgt_align_trs(trgt_engine_t *e, trgt_flank_batch_t *fb, const uint32_t *backbone_reads,
+                       const uint32_t *member_reads, const uint32_t *group_offsets, uint32_t n_groups,
+                       trgt_cigars_t *out) {
+  if (!e || !out) return TRGT_ERR_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  trgt_align_batch *b = nullptr;
+  TRY(align_gather_trs(e, fb, backbone_reads, member_reads, group_offsets, n_groups, "trgt_align_trs", &b));
+  TRY(align_run_locked(e, b));
+  return align_download_locked(e, b, out);
 }
 
 }  // extern "C"

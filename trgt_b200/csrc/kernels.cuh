@@ -1324,6 +1324,25 @@ __global__ void k_trs_len(const trgt_span_t *__restrict__ spans, const uint32_t 
   }
 }
 
+// lengths of the repeat sequences of the reads index[0..n) (0 without a span), len[n] = 0, and their maximum
+__global__ void __launch_bounds__(256)
+k_trs_len(const trgt_span_t *__restrict__ spans, const uint32_t *__restrict__ index, uint32_t n,
+          uint32_t *__restrict__ len, unsigned int *__restrict__ max_out) {
+  const uint32_t gsz = gridDim.x * blockDim.x;
+  unsigned int mx = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gsz) {
+    uint32_t l = 0;
+    if (i < n) {
+      const trgt_span_t sp = spans[index[i]];
+      l = sp.found ? sp.end - sp.start : 0u;
+    }
+    len[i] = l;
+    mx = l > mx ? l : mx;
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31u) == 0 && mx) atomicMax(max_out, mx);
+}
+
 __global__ void __launch_bounds__(256)
 k_trs_gather(const uint8_t *__restrict__ reads, const uint64_t *__restrict__ read_off,
              const trgt_span_t *__restrict__ spans, const uint32_t *__restrict__ index,

@@ -79,7 +79,7 @@ EXPORTS = [
     "trgt_clip_reads", "trgt_seq4_decode", "trgt_flank_spans_seq4", "trgt_flank_upload_seq4",
     "trgt_flank_trs", "trgt_vcf_fields", "trgt_bamlet_clip",
     "trgt_flank_spans", "trgt_align_e2e", "trgt_consensus", "trgt_edit_dist", "trgt_hmm_label",
-    "trgt_cluster", "trgt_cluster_trs", "trgt_consensus_trs",
+    "trgt_cluster", "trgt_cluster_trs", "trgt_consensus_trs", "trgt_align_trs",
     "trgt_flank_upload", "trgt_flank_run", "trgt_flank_download", "trgt_flank_free", "trgt_flank_device_views",
     "trgt_flank_fallback_counts",
     "trgt_align_upload", "trgt_align_run", "trgt_align_download", "trgt_align_free",
@@ -154,6 +154,7 @@ def load_library(build: bool = True):
     L.trgt_cluster.argtypes = [vp, sp, vp, u32, vp, vp, vp]
     L.trgt_cluster_trs.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
     L.trgt_bamlet_clip.argtypes = [vp, vp, vp, vp, vp, u32, vp]
+    L.trgt_align_trs.argtypes = [vp, vp, vp, vp, vp, u32, vp]
     L.trgt_consensus_trs.argtypes = [vp, vp, vp, vp, vp, u32, C.POINTER(_SeqsOut)]
     L.trgt_hmm_label.argtypes = [vp, sp, vp, u32, sp, vp, i32, C.POINTER(_Annotations)]
     L.trgt_hmm_upload.argtypes = [vp, sp, vp, u32, sp, vp, i32, C.POINTER(vp)]
@@ -741,6 +742,19 @@ class Engine:
                                       group.ctypes.data, central.ctypes.data, ng.ctypes.data)
         self._check(rc, "trgt_cluster_trs")
         return group[:rd.size], central[:n_loci], ng[:n_loci]
+
+    def align_trs(self, b, backbone_reads: np.ndarray, member_reads: np.ndarray, group_offsets: np.ndarray,
+                  copy: bool = True) -> CigarBatch:
+        """trgt_align_trs: utils::align with backbones and members named by read index of flank batch b (None: the last
+        one-shot call); copy=False: the result arrays alias the engine's pinned buffers"""
+        bb = np.ascontiguousarray(backbone_reads, dtype=np.uint32)
+        mr = np.ascontiguousarray(member_reads, dtype=np.uint32)
+        go = np.ascontiguousarray(group_offsets, dtype=np.uint32)
+        out = _Cigars()
+        rc = self._L.trgt_align_trs(self._h, b, bb.ctypes.data if bb.size else None, mr.ctypes.data if mr.size else None,
+                                    go.ctypes.data, bb.size, C.byref(out))
+        self._check(rc, "trgt_align_trs")
+        return self._cigars(out, copy)
 
     def consensus_trs(self, b, backbone_reads: np.ndarray, member_reads: np.ndarray, group_offsets: np.ndarray):
         """trgt_consensus_trs -> (PackedSeqs of one repaired consensus per group, status int32[n_groups])"""
