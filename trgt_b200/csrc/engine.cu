@@ -1562,9 +1562,22 @@ int32_t trgt_align_e2e(trgt_engine_t *e, const trgt_seqs_t *backbones, const trg
   if (!e) return TRGT_ERR_ARG;
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->one_align) e->one_align = new trgt_align_batch();
+  static const bool trace = getenv("TRGT_TRACE") != nullptr;  // host-side stage times of this call, to stderr
+  const auto t0 = std::chrono::steady_clock::now();
   TRY(align_upload_into(e, e->one_align, backbones, seqs, group_seq_offsets, n_groups));
+  const auto t1 = std::chrono::steady_clock::now();
   TRY(align_run_locked(e, e->one_align));
-  return align_download_locked(e, e->one_align, out);
+  const auto t2 = std::chrono::steady_clock::now();
+  const int rc = align_download_locked(e, e->one_align, out);
+  if (trace) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    fprintf(stderr, "[trgt] align_e2e: checks + uploads queued %.3f ms, kernels (two read-backs) %.3f ms, download %.3f ms\n",
+            ms(t0, t1), ms(t1, t2), ms(t2, t3));
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------------ consensus (next row) ------
