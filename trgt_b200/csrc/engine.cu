@@ -78,6 +78,9 @@ struct trgt_engine {
   size_t jump_uploaded_len = 0;
   // scan scratch
   DevBuf d_scan_tmp;
+  // pinned arena for host-built lists on their way to the device (see h2d_staged)
+  PinBuf h_stage;
+  size_t stage_used = 0;
   // pinned staging for small read-backs
   Counters *h_ctr = nullptr;
   unsigned long long *h_u64 = nullptr;
@@ -232,6 +235,27 @@ void dev_free(DevBuf &b, int device = -1) {
 int h2d(trgt_engine *e, DevBuf &b, const void *src, size_t bytes, size_t pad = 16) {
   TRY(dev_reserve(e, b, bytes + pad));
   if (bytes) CU(e, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream));
+  return 0;
+}
+
+// Lists the engine builds on the host (std::vector: pageable memory) go up through a pinned arena: an upload from
+// pageable memory makes the runtime synchronise the stream first and stage the bytes itself, one blocking step per
+// list behind whatever the stream still has queued on a shared link; from the arena they are ordinary asynchronous
+// copies.  stage_begin reserves the arena for one call's lists (the call ends with a wait on the stream, so the arena is
+// free again for the next call).
+int stage_begin(trgt_engine *e, size_t total_bytes) {
+  TRY(pin_reserve(e, e->h_stage, total_bytes + 256));
+  e->stage_used = 0;
+  return 0;
+}
+int h2d_staged(trgt_engine *e, DevBuf &b, const void *src, size_t bytes, size_t pad = 16) {
+  TRY(dev_reserve(e, b, bytes + pad));
+  if (!bytes) return 0;
+  const size_t at = (e->stage_used + 15) & ~(size_t)15;
+  if (at + bytes > e->h_stage.cap) return h2d(e, b, src, bytes, pad);  // (not reserved for: the plain path)
+  memcpy((uint8_t *)e->h_stage.p + at, src, bytes);
+  e->stage_used = at + bytes;
+  CU(e, cudaMemcpyAsync(b.p, (const uint8_t *)e->h_stage.p + at, bytes, cudaMemcpyHostToDevice, e->stream));
   return 0;
 }
 
@@ -445,6 +469,7 @@ void trgt_engine_destroy(trgt_engine_t *e) {
   dev_free(e->d_scan_tmp);
   for (auto &b : e->d_ed) dev_free(b);
   for (auto &b : e->d_cl) dev_free(b);
+  pin_free(e->h_stage);
   if (e->h_ctr) cudaFreeHost(e->h_ctr);
   if (e->h_u64) cudaFreeHost(e->h_u64);
   if (e->sleep_ev) cudaEventDestroy(e->sleep_ev);
@@ -2106,17 +2131,20 @@ static int hmm_upload_into(trgt_engine_t *e, trgt_hmm_batch *b, const trgt_seqs_
   static const uint32_t zero32[1] = {0};
   TRY(h2d(e, b->locus_motif_off, n_loci ? locus_motif_offsets : zero32, ((size_t)n_loci + 1) * sizeof(uint32_t)));
   TRY(h2d(e, b->allele_locus, allele_locus, n * sizeof(uint32_t)));
+  TRY(stage_begin(e, (n_gen + 1) * 2 * sizeof(unsigned long long) + n_gen * sizeof(uint32_t) +
+                         b->h_slots.size() * sizeof(uint32_t) + b->h_group_off.size() * sizeof(unsigned long long) +
+                         b->h_group_n.size() + (n + 1) * sizeof(unsigned long long) + 8 * 16));
   if (n_gen) {
-    TRY(h2d(e, b->bp_off, b->h_bp_off.data(), (n_gen + 1) * sizeof(unsigned long long)));
-    TRY(h2d(e, b->scr_off, b->h_scr_off.data(), (n_gen + 1) * sizeof(unsigned long long)));
-    if (n_gen != n) TRY(h2d(e, b->list, b->h_list.data(), n_gen * sizeof(uint32_t)));  // (all of them: identity)
+    TRY(h2d_staged(e, b->bp_off, b->h_bp_off.data(), (n_gen + 1) * sizeof(unsigned long long)));
+    TRY(h2d_staged(e, b->scr_off, b->h_scr_off.data(), (n_gen + 1) * sizeof(unsigned long long)));
+    if (n_gen != n) TRY(h2d_staged(e, b->list, b->h_list.data(), n_gen * sizeof(uint32_t)));  // (all of them: identity)
   }
   if (n_lane) {
-    TRY(h2d(e, b->slots, b->h_slots.data(), b->h_slots.size() * sizeof(uint32_t)));
-    TRY(h2d(e, b->group_off, b->h_group_off.data(), b->h_group_off.size() * sizeof(unsigned long long)));
-    TRY(h2d(e, b->group_n, b->h_group_n.data(), b->h_group_n.size()));
+    TRY(h2d_staged(e, b->slots, b->h_slots.data(), b->h_slots.size() * sizeof(uint32_t)));
+    TRY(h2d_staged(e, b->group_off, b->h_group_off.data(), b->h_group_off.size() * sizeof(unsigned long long)));
+    TRY(h2d_staged(e, b->group_n, b->h_group_n.data(), b->h_group_n.size()));
   }
-  TRY(h2d(e, b->mc_off, b->h_mc_off.data(), (n + 1) * sizeof(unsigned long long)));
+  TRY(h2d_staged(e, b->mc_off, b->h_mc_off.data(), (n + 1) * sizeof(unsigned long long)));
   CU(e, engine_wait(e));  // h_* vectors may be reallocated by the next upload
   TRY(dev_reserve(e, b->mc, (size_t)(b->h_mc_off[n] + 1) * sizeof(uint32_t)));
   TRY(dev_reserve(e, b->purity, (n + 1) * sizeof(double)));
