@@ -291,7 +291,7 @@ def kernel_bytes(name: str, w, hp, res) -> float | None:
         if name == "k_hmm_lane_walk":      # the words once, MC / purity / span count / scratch spans out
             return float((4.0 * L).sum() + (4.0 + 8.0 + 4.0 + 8.0) * L.size + 12.0 * a.spans.shape[0])
         return float(24.0 * a.spans.shape[0] + 16.0 * L.size)
-    if name in ("k_e2e_thread", "k_wfa_score_warp", "k_cigar_gather") and res.cigars is not None:
+    if name in ("k_e2e_lane", "k_wfa_score_warp", "k_cigar_gather") and res.cigars is not None:
         c = res.cigars
         slen = np.diff(g.seqs.offsets.astype(np.int64)).astype(np.float64)
         blen = np.diff(g.backbones.offsets.astype(np.int64)).astype(np.float64)[
@@ -299,7 +299,7 @@ def kernel_bytes(name: str, w, hp, res) -> float | None:
         nw = np.diff(c.offsets.astype(np.int64)).astype(np.float64)
         if name == "k_cigar_gather":       # every CIGAR word read from the pool and written in CSR order, end / offsets / score / status
             return float(8.0 * nw.sum() + (16.0 + 8.0 + 8.0 + 8.0) * nw.size)
-        sel = (c.scores != 0) if name == "k_e2e_thread" else (c.scores < -8)   # members that differ / cost above the lane cap
+        sel = (c.scores != 0) if name == "k_e2e_lane" else (c.scores < -8)   # members that differ / cost above the lane cap
         return float((slen[sel] + blen[sel] + 4.0 * nw[sel] + 16.0 + 4.0).sum())
     if name == "k_e2e_identity":  # every member and its backbone once, one end record and its CIGAR words per member
         per_seq_bb = np.diff(g.backbones.offsets.astype(np.int64))[

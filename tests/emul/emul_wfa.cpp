@@ -227,6 +227,30 @@ int emu_e2e_narrow(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x
   return 0;
 }
 
+// end-to-end alignment of a short pair by one lane on 16-bit history rows (e2e_narrow_lane): out[0] status, out[1] score,
+// out[2] number of CIGAR words
+int emu_e2e_lane(const uint8_t *p_in, int P, const uint8_t *t_in, int T, int x, int o, int e, int S, int *out,
+                 uint32_t *words, uint32_t words_cap) {
+  std::vector<uint8_t> pbuf(P + 32, 0), tbuf(T + 32, 0);
+  memcpy(pbuf.data(), p_in, P);
+  memcpy(tbuf.data(), t_in, T);
+  WfaProb pr;
+  pr.p = pbuf.data(); pr.P = P; pr.t = tbuf.data(); pr.T = T; pr.x = x; pr.oe = o + e; pr.e = e;
+  pr.pbf = pr.pef = pr.tbf = pr.tef = 0;
+  wfa_unband(pr);
+  int16_t hist[(FT1_SMAX + 1) * 3 * E2L_WMAX];
+  for (auto &h : hist) h = 0x7ead;
+  unsigned live_g = 0;
+  const unsigned live_m = S <= FT1_SMAX ? ft1_live_scores(pr.x, pr.oe, pr.e, S, &live_g) : 1u;
+  WfaEnd end{};
+  WfaCigarSink cs(words, words_cap);
+  e2e_narrow_lane<1>(pr, S, hist, 0u, false, live_m, live_g, &end, cs);
+  out[0] = end.status; out[1] = -end.s; out[2] = 0;
+  if (end.status != TRGT_WFA_OK) return end.status;
+  out[2] = (int)cs.finish();
+  return 0;
+}
+
 // exact search by one lane per pair (flank_exact_thread): copies and index built by `lanes` lanes;
 // text must carry 16 readable bytes on both sides
 int emu_flank_exact_thread(const uint8_t *p, int P, const uint8_t *t, int T, int lanes) {

@@ -434,6 +434,31 @@ def test_e2e_narrow_core(emul, oracle):
     assert resolved > 100
 
 
+def test_e2e_lane_core(emul, oracle):
+    """Phase B's lane routine (e2e_narrow_lane: cost cap 8 on |k| <= 3, 16-bit history rows only for the scores the
+    scoring allows, cells in lockstep with parked extensions): whatever it settles is the reference's CIGAR and score,
+    and it settles every pair whose cost is at most 8."""
+    rng = random.Random(4711)
+    resolved = 0
+    for _ in range(1500):
+        unit = rnd(rng, rng.randint(2, 6))
+        p = unit * rng.randint(1, 25) if rng.random() < 0.7 else rnd(rng, rng.randint(1, 80))
+        r = rng.random()
+        t = (mutate(rng, p, rng.choice([0.01, 0.02, 0.05])) if r < 0.7 else
+             p + unit * rng.randint(1, 2) if r < 0.85 else p[:len(p) - rng.randint(0, 3)]) or b"A"
+        words, score = oracle.align_words(p, t)
+        out = (C.c_int * 3)()
+        cap = len(p) + len(t) + 8
+        w = (C.c_uint32 * cap)()
+        rc = emul.emu_e2e_lane(p, len(p), t, len(t), 2, 5, 1, 8, out, w, cap)
+        if rc == 0:
+            resolved += 1
+            assert out[1] == score and list(w[:out[2]]) == words, (p, t)
+        else:
+            assert -score > 8, (p, t, score)
+    assert resolved > 700
+
+
 def test_hmm_core_thread_per_allele(emul, oracle):
     """hmm_viterbi_thread (one lane does the whole allele, strided score columns, table-free model)
     must give the oracle's state path, MC, MS and AP."""

@@ -24,7 +24,7 @@ cap k_flank_band1 'k_flank_band1$' 1 13k_flank_band1E
 cap k_flank_band2 'k_flank_band2$' 1 13k_flank_band2E
 cap k_flank_band_wide 'k_flank_band_wide$' 1 17k_flank_band_wideE
 cap k_e2e_identity 'k_e2e_identity$' 1 14k_e2e_identityE
-cap k_e2e_thread 'k_e2e_thread$' 1 12k_e2e_threadE
+cap k_e2e_lane 'k_e2e_lane$' 1 10k_e2e_laneE
 cap k_hmm_lane_viterbi 'k_hmm_lane_viterbi$' 1 18k_hmm_lane_viterbiE
 cap k_hmm_lane_walk 'k_hmm_lane_walk$' 1 15k_hmm_lane_walkE
 cap k_wfa_score_warp 'k_wfa_score' 3 11k_wfa_scoreILb0E

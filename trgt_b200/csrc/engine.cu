@@ -439,6 +439,7 @@ int32_t trgt_engine_create(int32_t device, trgt_engine_t **out) {
         (err = cudaFuncSetAttribute(k_wfa_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_wfa_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_flank_band1, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
+        (err = cudaFuncSetAttribute(k_e2e_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_hmm_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
         (err = cudaFuncSetAttribute(k_hmm_viterbi_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) {
       g_create_error = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(err);
@@ -1500,15 +1501,18 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
       TRY(check_launch(e, "k_e2e_identity"));
     }
     {
+      // the members that differ, one lane each, history rows (the scores the scoring allows up to the lane cap) on chip
+      const int rows = __builtin_popcount(ft1_live_scores(src.x, src.oe, src.e, E2T_COST, nullptr));
+      const size_t lsmem = (size_t)128 * rows * 3 * E2L_WMAX * sizeof(int16_t);
       int tgrid = 0;
-      TRY(persistent_grid(e, k_e2e_thread, 128, 0, &tgrid));
+      TRY(persistent_grid(e, k_e2e_lane, 128, lsmem, &tgrid));
       const uint32_t tneed = (n + 127) / 128;
       if ((uint32_t)tgrid > tneed) tgrid = (int)tneed;
-      LaunchScope ls(e, "k_e2e_thread");
-      k_e2e_thread<<<tgrid, 128, 0, e->stream>>>(src, (const uint32_t *)b->diff.p, &ctr->n_diff, (WfaEnd *)b->ends.p,
-                                                 (uint32_t *)b->cig_n.p, (unsigned long long *)b->cig_off.p,
-                                                 (uint32_t *)b->pool.p, pool_cap1, (uint32_t *)b->resid.p, ctr);
-      TRY(check_launch(e, "k_e2e_thread"));
+      LaunchScope ls(e, "k_e2e_lane");
+      k_e2e_lane<<<tgrid, 128, lsmem, e->stream>>>(src, (const uint32_t *)b->diff.p, &ctr->n_diff, (WfaEnd *)b->ends.p,
+                                                   (uint32_t *)b->cig_n.p, (unsigned long long *)b->cig_off.p,
+                                                   (uint32_t *)b->pool.p, pool_cap1, (uint32_t *)b->resid.p, ctr, rows);
+      TRY(check_launch(e, "k_e2e_lane"));
     }
     LaunchScope ls(e, "k_wfa_score_warp");
     k_wfa_score<false><<<grid, block, smem, e->stream>>>(src, (const uint32_t *)b->resid.p, &ctr->n_resid, 0, (WfaEnd *)b->ends.p, gring, stride,

@@ -38,7 +38,7 @@ struct Counters {
   unsigned int n_failed;                // items that ended with a non-OK status
   unsigned int n_banded;                // flank: pairs settled by k_flank_band_wide
   unsigned int n_tier2;                 // flank: pairs the first cost tier handed to k_flank_band2
-  unsigned int n_resid;                 // e2e: pairs k_e2e_thread handed to the warp kernel
+  unsigned int n_resid;                 // e2e: pairs k_e2e_lane handed to the warp kernel
   unsigned int n_diff;                  // e2e: members that differ from their backbone (k_e2e_identity)
   unsigned int n_list1;                // flank: pairs the seed pass listed for the band pass (k_flank_seed -> k_flank_band1)
 };
@@ -789,14 +789,10 @@ k_tr_gather(const uint8_t *__restrict__ reads, const uint64_t *__restrict__ read
 
 // Phase B, first steps for short repeat sequences: ONE LANE PER (backbone, member) PAIR.  A member equal
 // to its backbone (92 % on HiFi) is a single '=' run (k_e2e_identity, which compacts the others into a
-// list); a lane of k_e2e_thread then runs the end-to-end alignment of one listed member itself with cost
-// cap E2T_COST: every cell the full computation can reach then lies on
-// |k| <= (E2T_COST - o) / e, so the band of <= E2T_W diagonals IS the full computation (wfa_e2e_narrow's
-// argument), its history sits in the lane's local memory and the CIGAR comes straight from the
-// back-trace.  Costlier pairs are appended to `resid` for the warp kernel.
+// list); a lane of k_e2e_lane then runs the end-to-end alignment of one listed member itself with cost
+// cap E2T_COST and writes the CIGAR straight from its back-trace.  Costlier pairs are appended to `resid`
+// for the warp kernel.
 #define E2T_COST 8
-#define E2T_W 7
-#define E2T_WS_INTS (TRGT_WFA_META * (E2T_COST + 1) + 3 * E2T_W * (E2T_COST + 1))
 #define E2T_WORDS 32
 
 // step 1: identity test, one lane per member; the ones that differ are compacted into `diff`
@@ -829,45 +825,54 @@ k_e2e_identity(WfaSrc src, uint32_t n, WfaEnd *__restrict__ ends, uint32_t *__re
   }
 }
 
-// step 2: one lane per member that differs (all lanes of a warp busy)
+// step 2: the members that differ, ONE LANE PER MEMBER on the first flank tier's machinery (e2e_narrow_lane: cost
+// cap E2T_COST, so nothing outside |k| <= (E2T_COST - o) / e is reachable; 16-bit history rows for the scores the
+// scoring allows, in shared memory with the lanes of a warp interleaved; all lanes walk the same cells and long
+// extensions are parked until the warp has only those left).  Whole warps walk the list; what a lane cannot settle
+// (cost above the cap, band wider than E2L_WMAX, CIGAR pool full) goes to `resid` for the warp kernel.
 __global__ void __launch_bounds__(128)
-k_e2e_thread(WfaSrc src, const uint32_t *__restrict__ diff, const unsigned int *n_diff_ptr, WfaEnd *__restrict__ ends,
-             uint32_t *__restrict__ cig_n, unsigned long long *__restrict__ cig_off, uint32_t *__restrict__ pool,
-             unsigned long long pool_cap, uint32_t *__restrict__ resid, Counters *ctr) {
-  const uint32_t gsz = gridDim.x * blockDim.x;
+k_e2e_lane(WfaSrc src, const uint32_t *__restrict__ diff, const unsigned int *n_diff_ptr, WfaEnd *__restrict__ ends,
+           uint32_t *__restrict__ cig_n, unsigned long long *__restrict__ cig_off, uint32_t *__restrict__ pool,
+           unsigned long long pool_cap, uint32_t *__restrict__ resid, Counters *ctr, int rows) {
+  extern __shared__ __align__(16) unsigned char e2l_raw[];
+  const int tid = threadIdx.x;
+  int16_t *hist = reinterpret_cast<int16_t *>(e2l_raw) + (size_t)(tid >> 5) * rows * 3 * E2L_WMAX * 32 + (tid & 31);
+  unsigned live_g = 0;
+  const unsigned live_m = ft1_live_scores(src.x, src.oe, src.e, E2T_COST, &live_g);
   const uint32_t n = *n_diff_ptr;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gsz) {
-    const uint32_t id = diff[i];
-    const WfaProb pr = wfa_prob_of(src, id);
+  for (uint32_t base = blockIdx.x * blockDim.x + (uint32_t)(tid & ~31); base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t i = base + (uint32_t)(tid & 31);
+    const bool have = i < n;
+    uint32_t id = 0;
+    WfaProb pr;
+    pr.p = nullptr; pr.t = nullptr; pr.P = 0; pr.T = 0; pr.x = src.x; pr.oe = src.oe; pr.e = src.e;
+    pr.pbf = pr.pef = pr.tbf = pr.tef = 0; pr.blo = 0; pr.bhi = 0;
+    if (have) {
+      id = diff[i];
+      pr = wfa_prob_of(src, id);
+    }
+    uint32_t wbuf[E2T_WORDS];
+    WfaCigarSink sink(wbuf, E2T_WORDS);
     WfaEnd end;
+    e2e_narrow_lane<32>(pr, E2T_COST, hist, 0xffffffffu, !have, live_m, live_g, &end, sink);
+    __syncwarp();
+    if (!have) continue;
     bool done = false;
-    const int o = pr.oe - pr.e;
-    const int R = E2T_COST > o ? (E2T_COST - o) / pr.e : 0;
-    WfaProb bp = pr;
-    bp.blo = wfa_imax(-pr.P, -R);
-    bp.bhi = wfa_imin(pr.T, R);
-    if (bp.bhi - bp.blo + 1 <= E2T_W) {
-      int ws[E2T_WS_INTS];
-      end = wfa_forward_band_hist_narrow_thread(bp, E2T_COST, ws, E2T_WS_INTS);
-      if (end.status == TRGT_WFA_OK) {
-        uint32_t wbuf[E2T_WORDS];
-        WfaCigarSink sink(wbuf, E2T_WORDS);
-        wfa_backtrace(pr, end.s, end.k, end.off, ws, sink);
-        const uint32_t nw = sink.finish();
-        if (!sink.overflow) {
-          unsigned long long off = 0;
-          bool ok = true;
-          if (nw) {
-            off = atomicAdd(&ctr->pool_used, (unsigned long long)nw);
-            if (off + nw > pool_cap) ok = false;  // pool full: the warp kernel's generic path takes the pair
-          }
-          if (ok) {
-            for (uint32_t w = 0; w < nw; w++) pool[off + w] = wbuf[w];
-            cig_off[id] = off;
-            cig_n[id] = nw;
-            ends[id] = end;
-            done = true;
-          }
+    if (end.status == TRGT_WFA_OK) {
+      const uint32_t nw = sink.finish();
+      if (!sink.overflow) {
+        unsigned long long off = 0;
+        bool ok = true;
+        if (nw) {
+          off = atomicAdd(&ctr->pool_used, (unsigned long long)nw);
+          if (off + nw > pool_cap) ok = false;  // pool full: the warp kernel's generic path takes the pair
+        }
+        if (ok) {
+          for (uint32_t w = 0; w < nw; w++) pool[off + w] = wbuf[w];
+          cig_off[id] = off;
+          cig_n[id] = nw;
+          ends[id] = end;
+          done = true;
         }
       }
     }

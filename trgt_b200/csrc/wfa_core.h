@@ -1552,7 +1552,7 @@ TRGT_HD int flank_tier1_seed_thread(const KmerIndex &idx, const WfaProb &pr, int
 #define FT1_PMAX 256       // longest piece the band pass takes
 #define FT1_HIST_HALFS ((FT1_SMAX + 1) * 3 * FT1_WMAX)  // 16-bit cells of one pair's history (216 bytes)
 
-// History of the band pass: cell (s, component, k) at h[((s * 3 + c) * FT1_WMAX + k - blo) * LS] as offset - blo
+// History of the band pass: cell (s, component, k) at h[((row(s) * 3 + c) * WM + k - blo) * LS] as offset - blo
 // (never negative for a reachable cell), -1 = null.  LS = distance between a lane's consecutive cells (cells of
 // the lanes of a warp interleaved: every lane of a converged access hits its own bank).
 // wfa_live_scores for the first tier (s_cap <= FT1_SMAX)
@@ -1571,7 +1571,7 @@ TRGT_HD int ft1_row(unsigned live_m, int s) {
 #endif
 }
 
-template <int LS>
+template <int LS, int WM = FT1_WMAX>
 struct Ft1Hist {
   int16_t *h;
   int blo, W;
@@ -1579,7 +1579,7 @@ struct Ft1Hist {
   unsigned live_m;   // ft1_live_scores of the scoring (row numbering)
   TRGT_HD int cell(int s, int c, int k) const {
     if (s < 0 || !((present >> s) & 1u) || k < blo || k >= blo + W) return TRGT_WFA_NULL;
-    const int v = h[((ft1_row(live_m, s) * 3 + c) * FT1_WMAX + (k - blo)) * LS];
+    const int v = h[((ft1_row(live_m, s) * 3 + c) * WM + (k - blo)) * LS];
     return v < 0 ? TRGT_WFA_NULL : v + blo;
   }
   struct Row {
@@ -1604,7 +1604,9 @@ struct Ft1Hist {
 // and only keeps company.  live_m / live_g: ft1_live_scores of the scoring (the same for every pair of a launch,
 // so the caller computes them once).  An all-null wavefront reads exactly like an absent one, so a score that
 // only has null predecessors may be computed (here: whenever the scoring allows a wavefront) or skipped alike.
-template <int LS>
+// WM: diagonals a row has room for (the band may be narrower); SHARED: the text (win) is in shared memory, else in
+// global memory like the pattern.
+template <int LS, int WM = FT1_WMAX, bool SHARED = true>
 TRGT_HD WfaEnd ft1_forward(const WfaProb &pr, int s_cap, const uint8_t *win, int a0, int16_t *hist, unsigned *present_out,
                            unsigned lanes, bool idle, unsigned live_m, unsigned live_g) {
   WfaEnd out;
@@ -1612,8 +1614,8 @@ TRGT_HD WfaEnd ft1_forward(const WfaProb &pr, int s_cap, const uint8_t *win, int
   const int W = idle ? 0 : pr.bhi - pr.blo + 1;
   unsigned present = 0;
   bool done = idle;
-#define FT1_LD(s_, c_, i_) ft1_ld(hist[((ft1_row(live_m, (s_)) * 3 + (c_)) * FT1_WMAX + (i_)) * LS], pr.blo)
-#define FT1_ST(s_, c_, i_, val) hist[((ft1_row(live_m, (s_)) * 3 + (c_)) * FT1_WMAX + (i_)) * LS] = (int16_t)((val) < 0 ? -1 : (val) - pr.blo)
+#define FT1_LD(s_, c_, i_) ft1_ld(hist[((ft1_row(live_m, (s_)) * 3 + (c_)) * WM + (i_)) * LS], pr.blo)
+#define FT1_ST(s_, c_, i_, val) hist[((ft1_row(live_m, (s_)) * 3 + (c_)) * WM + (i_)) * LS] = (int16_t)((val) < 0 ? -1 : (val) - pr.blo)
   for (int s = 0; s <= s_cap; s++) {
     if (!((live_m >> s) & 1u)) continue;  // the same for every lane
     if (!TRGT_ANY(lanes, !done)) break;
@@ -1622,7 +1624,7 @@ TRGT_HD WfaEnd ft1_forward(const WfaProb &pr, int s_cap, const uint8_t *win, int
     const bool pe = se >= 1 && ((live_g >> se) & 1u);
     unsigned parked = 0;  // bit idx: the extension of cell (s, idx) is not finished
 #pragma unroll
-    for (int idx = 0; idx < FT1_WMAX; idx++) {
+    for (int idx = 0; idx < WM; idx++) {
       if (done || idx >= W) continue;
       const int k = pr.blo + idx;
       int mx = TRGT_WFA_NULL;
@@ -1645,7 +1647,7 @@ TRGT_HD WfaEnd ft1_forward(const WfaProb &pr, int s_cap, const uint8_t *win, int
       if (mx >= 0) {  // the first eight bytes of the match extension along the diagonal
         const int v = mx - k, n = wfa_imin(pr.P - v, pr.T - mx);
         if (n > 0) {
-          const uint64_t x = ft1_ld64_piece(pr.p + v) ^ ft1_ld64_win(win + (mx - a0));
+          const uint64_t x = ft1_ld64_piece(pr.p + v) ^ (SHARED ? ft1_ld64_win(win + (mx - a0)) : ft1_ld64_piece(win + (mx - a0)));
           int adv = x ? (wfa_ctz64(x) >> 3) : 8;
           if (adv > n) adv = n;
           mx += adv;
@@ -1664,8 +1666,8 @@ TRGT_HD WfaEnd ft1_forward(const WfaProb &pr, int s_cap, const uint8_t *win, int
         const int k = pr.blo + idx;
         int mx = FT1_LD(s, 0, idx);
         const int v = mx - k, n = wfa_imin(pr.P - v, pr.T - mx);
-        const uint64_t x0 = ft1_ld64_piece(pr.p + v) ^ ft1_ld64_win(win + (mx - a0));
-        const uint64_t x1 = n > 8 ? ft1_ld64_piece(pr.p + v + 8) ^ ft1_ld64_win(win + (mx - a0) + 8) : 0;  // (stays inside the padding)
+        const uint64_t x0 = ft1_ld64_piece(pr.p + v) ^ (SHARED ? ft1_ld64_win(win + (mx - a0)) : ft1_ld64_piece(win + (mx - a0)));
+        const uint64_t x1 = n > 8 ? ft1_ld64_piece(pr.p + v + 8) ^ (SHARED ? ft1_ld64_win(win + (mx - a0) + 8) : ft1_ld64_piece(win + (mx - a0) + 8)) : 0;  // (stays inside the padding)
         int adv = x0 ? (wfa_ctz64(x0) >> 3) : (x1 ? 8 + (wfa_ctz64(x1) >> 3) : 16);
         if (adv > n) adv = n;
         mx += adv;
@@ -1722,6 +1724,28 @@ TRGT_HD int flank_tier1_band_thread(const WfaProb &pr, int klo, int khi, int S, 
     hit->via = 3; hit->start = 0; hit->end = 0;
   }
   return 0;
+}
+
+// End-to-end alignment of a short pair by one lane with the same machinery (phase B's members that differ from their
+// backbone): with cost cap S nothing is reachable outside |k| <= (S - o) / e (wfa_e2e_narrow's argument), so that band
+// is the whole computation.  Both sequences are read where they lie (a few dozen bases each); the history is the
+// lane's 16-bit rows.  Fills *end (status OK / MAX_STEPS); on OK the back-trace hands the CIGAR to `sink`.
+#define E2L_WMAX 8   // room for |k| <= 3: cost cap 8 under the consensus scoring 2 / 5 / 1
+template <int LS, class Sink>
+TRGT_HD void e2e_narrow_lane(const WfaProb &pr, int S, int16_t *hist, unsigned lanes, bool idle, unsigned live_m,
+                             unsigned live_g, WfaEnd *end, Sink &sink) {
+  const int o = pr.oe - pr.e;
+  const int R = S > o ? (S - o) / pr.e : 0;
+  WfaProb bp = pr;
+  bp.blo = wfa_imax(-pr.P, -R);
+  bp.bhi = wfa_imin(pr.T, R);
+  const bool skip = idle || bp.bhi - bp.blo + 1 > E2L_WMAX || S > FT1_SMAX;
+  unsigned present = 0;
+  *end = ft1_forward<LS, E2L_WMAX, false>(bp, S, pr.t, 0, hist, &present, lanes, skip, live_m, live_g);
+  if (skip) { end->status = TRGT_WFA_MAX_STEPS; return; }
+  if (end->status != TRGT_WFA_OK) return;
+  const Ft1Hist<LS, E2L_WMAX> H{hist, bp.blo, bp.bhi - bp.blo + 1, present, live_m};
+  wfa_backtrace_h(pr, end->s, end->k, end->off, H, sink);
 }
 
 // ---------------------------------------------------------------- unit-cost edit distance ------
