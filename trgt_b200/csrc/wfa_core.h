@@ -957,18 +957,25 @@ TRGT_HD uint64_t fxt_mask_to(int hi) { return hi >= 8 ? ~0ull : (hi <= 0 ? 0ull 
 template <class G>
 TRGT_HD void fxt_build_copies(const G &g, const uint8_t *piece, int P, uint8_t *copies) {
   const int W = FXT_STRIDE / 8;
-  for (int idx = g.lane(); idx < FXT_COPIES * W; idx += g.size()) {
-    const int k = idx / W, wd = idx - k * W;
-    const int i0 = 8 * wd - 8 - k;  // piece index of the word's first byte
+  // copy 0 (the piece at byte 8, zeros around it) from the piece, then copy k = copy 0 moved up k bytes: two
+  // words of copy 0 give a word of each of the other copies
+  uint64_t *c0 = (uint64_t *)copies;
+  for (int wd = g.lane(); wd < W; wd += g.size()) {
+    const int i0 = 8 * wd - 8;
     uint64_t v = 0;
-    if (i0 + 8 > 0 && i0 < P) {  // (words wholly outside the piece are never compared unmasked)
-      // a word that straddles an end of the piece comes from the piece's first / last 8 bytes, shifted
-      const int lo = i0 < 0 ? -i0 : 0, hi = i0 + 8 > P ? i0 + 8 - P : 0;  // bytes missing at its low / high end
-      v = wfa_ld64u(piece + (lo ? 0 : hi ? P - 8 : i0));
-      if (lo) v <<= 8 * lo;
+    if (i0 >= 0 && i0 < P) {
+      const int hi = i0 + 8 > P ? i0 + 8 - P : 0;
+      v = wfa_ld64u(piece + (hi ? P - 8 : i0));
       if (hi) v >>= 8 * hi;
     }
-    *(uint64_t *)(copies + k * FXT_STRIDE + 8 * wd) = v;
+    c0[wd] = v;
+  }
+  g.sync();
+  for (int wd = g.lane(); wd < W; wd += g.size()) {
+    const uint64_t a = c0[wd], b = wd ? c0[wd - 1] : 0ull;
+#pragma unroll
+    for (int k = 1; k < FXT_COPIES; k++)
+      *(uint64_t *)(copies + k * FXT_STRIDE + 8 * wd) = (a << (8 * k)) | (b >> (64 - 8 * k));
   }
   g.sync();
 }
