@@ -1503,13 +1503,13 @@ static int align_run_locked(trgt_engine_t *e, trgt_align_batch *b) {
     {
       // the members that differ, one lane each, history rows (the scores the scoring allows up to the lane cap) on chip
       const int rows = __builtin_popcount(ft1_live_scores(src.x, src.oe, src.e, E2T_COST, nullptr));
-      const size_t lsmem = (size_t)128 * rows * 3 * E2L_WMAX * sizeof(int16_t);
+      const size_t lsmem = (size_t)E2L_THREADS * rows * 3 * E2L_WMAX * sizeof(int16_t);
       int tgrid = 0;
-      TRY(persistent_grid(e, k_e2e_lane, 128, lsmem, &tgrid));
-      const uint32_t tneed = (n + 127) / 128;
+      TRY(persistent_grid(e, k_e2e_lane, E2L_THREADS, lsmem, &tgrid));
+      const uint32_t tneed = (n + E2L_THREADS - 1) / E2L_THREADS;
       if ((uint32_t)tgrid > tneed) tgrid = (int)tneed;
       LaunchScope ls(e, "k_e2e_lane");
-      k_e2e_lane<<<tgrid, 128, lsmem, e->stream>>>(src, (const uint32_t *)b->diff.p, &ctr->n_diff, (WfaEnd *)b->ends.p,
+      k_e2e_lane<<<tgrid, E2L_THREADS, lsmem, e->stream>>>(src, (const uint32_t *)b->diff.p, &ctr->n_diff, (WfaEnd *)b->ends.p,
                                                    (uint32_t *)b->cig_n.p, (unsigned long long *)b->cig_off.p,
                                                    (uint32_t *)b->pool.p, pool_cap1, (uint32_t *)b->resid.p, ctr, rows);
       TRY(check_launch(e, "k_e2e_lane"));

@@ -41,6 +41,7 @@ struct Counters {
   unsigned int n_resid;                 // e2e: pairs k_e2e_lane handed to the warp kernel
   unsigned int n_diff;                  // e2e: members that differ from their backbone (k_e2e_identity)
   unsigned int n_list1;                // flank: pairs the seed pass listed for the band pass (k_flank_seed -> k_flank_band1)
+  unsigned int wide_next;               // flank: next position of the work list k_flank_band_wide hands out
 };
 
 enum { WFA_MODE_FLANK = 0, WFA_MODE_E2E = 1 };
@@ -706,9 +707,19 @@ k_flank_band2(WfaSrc src, const uint32_t *__restrict__ work2, const unsigned int
 
 // Phase A, step 3.  Second chance for the pairs k_flank_band deferred (band wider than a warp, cost
 // above its budget, scratch too small): one warp per pair with 32 KB of scratch and the general
-// banded routine (index or linear seed scan, any band width, history or ring + cone), budgets 24 then 36.
+// banded routine (index or linear seed scan, any band width, history or ring + cone), budgets 18 then 36; the warps
+// draw their pairs from a counter (the pairs' costs differ widely).
 // What it settles is struck from the work list (0xFFFFFFFF); only pairs without any usable seed are
 // left for the full-width kernels.
+#ifndef FLW_S0
+#define FLW_S0 18  // budgets of the wide pass: FLW_S0, FLW_S1 (if larger), 36  (24, 36: 0.44 ms; 20: 0.37; 18: 0.34; 18, 24, 36: 0.38)
+#endif
+#ifndef FLW_S1
+#define FLW_S1 0
+#endif
+#ifndef TRGT_WIDE_DYNAMIC
+#define TRGT_WIDE_DYNAMIC 1
+#endif
 #ifndef FLW_WS_INTS
 #define FLW_WS_INTS 5120  // (8192: 0.50 ms, 5120: 0.46 ms, 4096: 0.39 ms but 0.2 ms more in the full-width kernels behind it)
 #endif
@@ -723,7 +734,16 @@ k_flank_band_wide(WfaSrc src, uint32_t *__restrict__ work, const unsigned int *n
   const WarpGroup g;
   const int lane = g.lane();
   const uint32_t n = *n_work_ptr;
+#if TRGT_WIDE_DYNAMIC
+  // pairs differ widely in cost (budgets 24 and 36, bands of any width): the warps draw them from a counter
+  for (;;) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(&ctr->wide_next, 1u);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= n) break;
+#else
   for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+#endif
     const uint32_t id = work[i];
     const WfaProb pr = wfa_prob_of(src, id);
     __syncwarp();
@@ -740,9 +760,12 @@ k_flank_band_wide(WfaSrc src, uint32_t *__restrict__ work, const unsigned int *n
     FlankHit fh;
     fh.via = 0; fh.matches = 0; fh.score = 0; fh.start = 0; fh.end = 0;
 #pragma unroll 1
-    for (int S = 24; S <= 36 && !settled; S += 12)
+    for (int b = 0; b < 3 && !settled; b++) {
+      const int S = b == 0 ? FLW_S0 : b == 1 ? FLW_S1 : 36;
+      if (b == 1 && FLW_S1 <= FLW_S0) continue;
       settled = flank_locate_banded(g, pr, S, min_flank_id_frac, keys, ws, FLW_WS_INTS, &fh, indexed ? &idx : nullptr,
                                     cand) == 0;
+    }
     if (lane == 0 && settled) {
       trgt_flank_hit_t h;
       h.via = fh.via; h.matches = fh.matches; h.score = fh.score;
@@ -830,7 +853,10 @@ k_e2e_identity(WfaSrc src, uint32_t n, WfaEnd *__restrict__ ends, uint32_t *__re
 // scoring allows, in shared memory with the lanes of a warp interleaved; all lanes walk the same cells and long
 // extensions are parked until the warp has only those left).  Whole warps walk the list; what a lane cannot settle
 // (cost above the cap, band wider than E2L_WMAX, CIGAR pool full) goes to `resid` for the warp kernel.
-__global__ void __launch_bounds__(128)
+#ifndef E2L_THREADS
+#define E2L_THREADS 128
+#endif
+__global__ void __launch_bounds__(E2L_THREADS)
 k_e2e_lane(WfaSrc src, const uint32_t *__restrict__ diff, const unsigned int *n_diff_ptr, WfaEnd *__restrict__ ends,
            uint32_t *__restrict__ cig_n, unsigned long long *__restrict__ cig_off, uint32_t *__restrict__ pool,
            unsigned long long pool_cap, uint32_t *__restrict__ resid, Counters *ctr, int rows) {
