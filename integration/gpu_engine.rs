@@ -135,6 +135,13 @@ extern "C" {
     pub fn trgt_engine_sync(eng: *mut TrgtEngine) -> i32;
     pub fn trgt_engine_set_workspace_budget(eng: *mut TrgtEngine, bytes: usize);
     pub fn trgt_engine_set_flank_band_budget(eng: *mut TrgtEngine, max_cost: i32);
+    // instrumentation (per-kernel device times through CUDA events on the engine stream; launch counter)
+    pub fn trgt_engine_set_profiling(eng: *mut TrgtEngine, on: i32);
+    pub fn trgt_engine_reset_stats(eng: *mut TrgtEngine);
+    pub fn trgt_engine_kernel_count(eng: *mut TrgtEngine) -> i32;
+    pub fn trgt_engine_kernel_stat(eng: *mut TrgtEngine, i: i32, name: *mut *const c_char, launches: *mut u64,
+        total_ms: *mut f64) -> i32;
+    pub fn trgt_engine_launches(eng: *const TrgtEngine) -> u64;
     pub fn trgt_engine_set_hmm_lane_path(eng: *mut TrgtEngine, on: i32);
     pub fn trgt_host_alloc(bytes: usize) -> *mut c_void;
     pub fn trgt_host_free(p: *mut c_void);
@@ -183,6 +190,10 @@ extern "C" {
     pub fn trgt_flank_download(eng: *mut TrgtEngine, batch: *mut TrgtFlankBatch, spans_out: *mut TrgtSpan,
         hits_out: *mut TrgtFlankHit) -> i32;
     pub fn trgt_flank_free(eng: *mut TrgtEngine, batch: *mut TrgtFlankBatch);
+    // device pointers of a resident flank batch, for device-side consumers; how the last run settled the misses
+    pub fn trgt_flank_device_views(batch: *mut TrgtFlankBatch, d_reads: *mut *const c_void, d_read_off: *mut *const c_void,
+        d_spans: *mut *const c_void, d_hits: *mut *const c_void, n_reads: *mut u32, n_wfa: *mut u32) -> i32;
+    pub fn trgt_flank_fallback_counts(batch: *mut TrgtFlankBatch, out: *mut u32) -> i32; // out[3]
     pub fn trgt_align_upload(eng: *mut TrgtEngine, backbones: *const TrgtSeqs, seqs: *const TrgtSeqs,
         group_seq_offsets: *const u32, n_groups: u32, out: *mut *mut TrgtAlignBatch) -> i32;
     pub fn trgt_align_run(eng: *mut TrgtEngine, batch: *mut TrgtAlignBatch) -> i32;
