@@ -42,6 +42,16 @@ def test_library_exports_every_declared_symbol():
     assert sorted(trgt_b200.EXPORTS) == names, set(names) ^ set(trgt_b200.EXPORTS)
 
 
+def test_rust_binding_declares_every_symbol():
+    """integration/gpu_engine.rs (the binding a maintainer adds; not compiled here: no rustc) must declare every
+    function of the header in its extern "C" block."""
+    import re
+    rs = open(os.path.join(os.path.dirname(HEADER), "..", "integration", "gpu_engine.rs")).read()
+    declared = set(re.findall(r"pub fn (trgt_[a-z0-9_]+)\s*\(", rs))
+    missing = [n for n in declared_functions() if n not in declared]
+    assert not missing, missing
+
+
 def test_plain_c_caller_links_and_fails_loudly_without_gpu(tmp_path):
     exe = build_driver(tmp_path)
     try:
