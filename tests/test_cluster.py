@@ -117,3 +117,33 @@ def test_cluster_core_matches_oracle(lanes):
         assert tuple(None if c == 0xFFFFFFFF else int(c) for c in got_c) == central
         if n >= 3:   # the matrix the linkage leaves behind (central_read reads it) is bit-identical
             assert np.array_equal(dd[:-1], ref_mat)
+
+
+def _levenshtein(a: bytes, b: bytes) -> int:
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
+def test_get_dist_matrix_correctness(oracle):  # genotype_cluster.rs:330-356, and each entry against a plain DP
+    """The reference's own test: the condensed matrix equals pair-by-pair get_dist (10 random sequences of 50-150
+    bases, 1e-9); on top of it every entry is sqrt(Levenshtein) or, past MAX_OPS (`:239-243`), sqrt(|len1 - len2|)."""
+    import math
+    import random
+    rng = random.Random(330)
+    seqs = [bytes(rng.choice(b"ACGT") for _ in range(rng.randint(50, 150))) for _ in range(10)]
+    got = oracle.get_dist_matrix(seqs)
+    assert len(got) == 45
+    k = 0
+    for i in range(10):
+        for j in range(i + 1, 10):
+            assert abs(got[k] - oracle.get_dist(seqs[i], seqs[j])) < 1e-9
+            if len(seqs[i]) * len(seqs[j]) > 10000:
+                assert got[k] == math.sqrt(abs(len(seqs[i]) - len(seqs[j])))
+            else:
+                assert got[k] == math.sqrt(_levenshtein(seqs[i], seqs[j]))
+            k += 1
