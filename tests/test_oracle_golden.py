@@ -317,6 +317,23 @@ def test_find_span_exact_and_fallback(oracle):
     assert span is None and via == 3 and nm < 175
 
 
+@pytest.mark.parametrize("seq, piece, expect", [  # span_locater.rs:73-119 (the exact search of find_spans, :10-12)
+    (b"ABCDEFG", b"CDE", (2, 5)), (b"ABCDEFG", b"XYZ", None), (b"ABCABCABC", b"ABC", (0, 3)),
+    (b"ABCDEFG", b"ABC", (0, 3)), (b"ABCDEFG", b"EFG", (4, 7)), (b"ABCDEFG", b"ABCDEFG", (0, 7)),
+    (b"ABC", b"ABCDEFG", None), (b"", b"ABC", None), (b"ABCDEFG", b"A", (0, 1)), (b"ABCDEFG", b"G", (6, 7)),
+    (b"ABCDEFG", b"D", (3, 4)), (b"AAAAA", b"AA", (0, 2)), (b"ACGTNACGT", b"N", (4, 5)),
+])
+def test_find_vs_windows_comparison(oracle, seq, piece, expect):
+    """The reference's vectors for the exact search: first occurrence, as `windows().position()` finds it.  Where it
+    expects None the exact search must miss (what the WFA fallback then makes of such toy inputs is not part of the
+    reference's test)."""
+    span, via, nm = oracle.find_span(piece, seq)
+    if expect is None:
+        assert via != 1
+    else:
+        assert span == expect and via == 1 and nm == len(piece)
+
+
 # ------------------------------------------------------------- consensus (next row) --
 
 def test_repair_consensus_reference_examples(oracle):
