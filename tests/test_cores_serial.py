@@ -434,6 +434,18 @@ def test_e2e_narrow_core(emul, oracle):
     assert resolved > 100
 
 
+def test_flank_scan_core_reference_vectors(emul):
+    """The reference's exact-search vectors (span_locater.rs:73-119) through the device core of the general exact
+    search (flank_scan, as k_flank_exact runs it for pieces outside 16..256 bases), serial and with 7 lock-step lanes."""
+    cases = [(b"ABCDEFG", b"CDE", 2), (b"ABCDEFG", b"XYZ", -1), (b"ABCABCABC", b"ABC", 0), (b"ABCDEFG", b"ABC", 0),
+             (b"ABCDEFG", b"EFG", 4), (b"ABCDEFG", b"ABCDEFG", 0), (b"ABC", b"ABCDEFG", -1), (b"", b"ABC", -1),
+             (b"ABCDEFG", b"A", 0), (b"ABCDEFG", b"G", 6), (b"ABCDEFG", b"D", 3), (b"AAAAA", b"AA", 0),
+             (b"ACGTNACGT", b"N", 4)]
+    for seq, piece, start in cases:
+        assert emul.emu_flank_scan(piece, len(piece), seq, len(seq)) == start, (seq, piece)
+        assert emul.emu_flank_scan_lanes(piece, len(piece), seq, len(seq), 7) == start, (seq, piece)
+
+
 def test_e2e_lane_core(emul, oracle):
     """Phase B's lane routine (e2e_narrow_lane: cost cap 8 on |k| <= 3, 16-bit history rows only for the scores the
     scoring allows, cells in lockstep with parked extensions): whatever it settles is the reference's CIGAR and score,
