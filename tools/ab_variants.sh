@@ -1,5 +1,5 @@
 #!/bin/bash
-# Build variants of libtrgt_b200.so that differ by -D flags (here, no GPU needed) into gpurun_out/ab/, and -- under
+# Build variants of libtrgt_b200.so that differ by -D flags (here, no GPU needed) into build/ab/ (which travels to the box; gpurun_out/ does not), and -- under
 # gpurun -- time each one's resident pass.  Usage:
 #   tools/ab_variants.sh build name1 "-DX=1" name2 "-DX=2" ...     (in the container)
 #   tools/ab_variants.sh run name1 name2 ...                        (on the GPU box; prints kernel times)
